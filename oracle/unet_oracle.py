@@ -1,0 +1,316 @@
+"""Functional CPU restatement of the reference U-Net, its objective and its input standardisation.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Every function cites the reference
+file:line (paths relative to the SDU-Gary/PCSS-Unet tree) whose call sequence it restates.
+Arithmetic is delegated to ``torch.nn.functional`` on the CPU -- the same third-party library the
+reference itself calls -- so the oracle and the reference agree bit-for-bit when run with the same
+thread count (checked by ``tests/test_oracle_golden.py`` against vectors produced by the real
+reference classes, ``tests/golden/make_golden.py``).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+__all__ = [
+    "BLOCKS", "DROPOUT_P", "init_params", "param_names", "buffer_names", "even_fix", "double_conv",
+    "unet_forward", "upsample_and_match", "l1_loss", "custom_loss", "custom_loss_grad",
+    "perturb_inputs", "perturbation_loss", "perturbation_loss_grad", "standardise",
+    "conv_stage_eval", "train_step_grads", "calibrate_bn", "replay_conv5_checkpoint",
+]
+
+# (name, in_ch, out_ch) in construction AND forward order -- Unetmodel.py:39,42,45,48,52,55,58,61
+BLOCKS = [
+    ("conv2", 16, 64), ("conv3", 64, 128), ("conv4", 128, 512), ("conv5", 512, 1024),
+    ("conv6", 1024, 512), ("conv7", 512, 128), ("conv8", 128, 64), ("conv9", 64, 16),
+]
+
+
+def DROPOUT_P(name: str, dropout_rate: float = 0.2) -> float:
+    """Dropout2d probability of a block: ``dropout_rate`` everywhere, half of it in conv9
+    (Unetmodel.py:61)."""
+    return dropout_rate / 2 if name == "conv9" else dropout_rate
+
+
+def init_params(seed: Optional[int] = 42) -> Dict[str, torch.Tensor]:
+    """Default-initialised parameters and BN buffers with the reference's state_dict keys.
+
+    Follows the construction order of ``Unet.__init__`` (Unetmodel.py:36-63) and of
+    ``DoubleConv.__init__`` (Unetmodel.py:18-30): only ``nn.Conv2d.reset_parameters`` consumes
+    random numbers, so building the same Conv2d modules in the same order after
+    ``torch.manual_seed(seed)`` reproduces ``torch.manual_seed(seed); Unet()`` exactly
+    (main.py:73-92 seeds with 42)."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    P: Dict[str, torch.Tensor] = {}
+
+    def conv(key, cin, cout, k):
+        m = torch.nn.Conv2d(cin, cout, k, padding=k // 2)
+        P[f"{key}.weight"] = m.weight.detach().clone()
+        P[f"{key}.bias"] = m.bias.detach().clone()
+
+    def bn(key, c):
+        P[f"{key}.weight"] = torch.ones(c)
+        P[f"{key}.bias"] = torch.zeros(c)
+        P[f"{key}.running_mean"] = torch.zeros(c)
+        P[f"{key}.running_var"] = torch.ones(c)
+        P[f"{key}.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+
+    for name, cin, cout in BLOCKS:
+        conv(f"{name}.conv.0", cin, cin, 3)      # Unetmodel.py:21
+        bn(f"{name}.conv.1", cin)                # Unetmodel.py:22
+        conv(f"{name}.conv.4", cin, cout, 1)     # Unetmodel.py:26
+        bn(f"{name}.conv.5", cout)               # Unetmodel.py:27
+    conv("conv10", 16, 4, 1)                     # Unetmodel.py:63
+    return P
+
+
+def param_names() -> List[str]:
+    """The 66 trainable tensors in ``named_parameters()`` order."""
+    out = []
+    for name, _, _ in BLOCKS:
+        for idx in (0, 1, 4, 5):
+            out += [f"{name}.conv.{idx}.weight", f"{name}.conv.{idx}.bias"]
+    return out + ["conv10.weight", "conv10.bias"]
+
+
+def buffer_names() -> List[str]:
+    out = []
+    for name, _, _ in BLOCKS:
+        for idx in (1, 5):
+            out += [f"{name}.conv.{idx}.running_mean", f"{name}.conv.{idx}.running_var",
+                    f"{name}.conv.{idx}.num_batches_tracked"]
+    return out
+
+
+def even_fix(x: torch.Tensor) -> torch.Tensor:
+    """Unetmodel.py:92-97 -- odd H or W is bilinearly resized (align_corners) to the even floor."""
+    H, W = x.shape[2:]
+    if H % 2 or W % 2:
+        x = F.interpolate(x, (H - H % 2, W - W % 2), mode="bilinear", align_corners=True)
+    return x
+
+
+def _bn(y, P, key, training, momentum=0.1):
+    """nn.BatchNorm2d(eps=1e-5, momentum=0.1) -- Unetmodel.py:22,27.  In training mode the batch
+    statistics normalise, the running buffers are updated in place and num_batches_tracked += 1."""
+    if training:
+        P[f"{key}.num_batches_tracked"] += 1
+    return F.batch_norm(y, P[f"{key}.running_mean"], P[f"{key}.running_var"], P[f"{key}.weight"],
+                        P[f"{key}.bias"], training, momentum, 1e-5)
+
+
+def double_conv(x, P, name, training=False, p_drop=0.0, mask=None, momentum=0.1, taps=None):
+    """DoubleConv.forward (Unetmodel.py:17-33): Conv3x3(in->in,pad 1) -> BN -> LeakyReLU(0.2) ->
+    Dropout2d -> Conv1x1(in->out) -> BN -> LeakyReLU(0.2).  ``mask`` ([N,C,1,1], already divided
+    by 1-p) replays a Dropout2d draw; without it ``F.dropout2d`` draws from the global generator
+    exactly as ``nn.Dropout2d`` does."""
+    y = F.conv2d(x, P[f"{name}.conv.0.weight"], P[f"{name}.conv.0.bias"], padding=1)
+    if taps is not None:
+        taps[f"{name}.z0"] = y
+    y = _bn(y, P, f"{name}.conv.1", training, momentum)
+    y = F.leaky_relu(y, 0.2)
+    if training:
+        if mask is not None:
+            y = y * mask.to(y.dtype)
+        elif p_drop > 0:
+            y = F.dropout2d(y, p_drop, True)
+    if taps is not None:
+        taps[f"{name}.a0"] = y
+    y = F.conv2d(y, P[f"{name}.conv.4.weight"], P[f"{name}.conv.4.bias"])
+    if taps is not None:
+        taps[f"{name}.z1"] = y
+    y = _bn(y, P, f"{name}.conv.5", training, momentum)
+    return F.leaky_relu(y, 0.2)
+
+
+def upsample_and_match(src, size):
+    """nn.Upsample(scale_factor=2, bilinear, align_corners=True) followed by
+    ``_upsample_and_match`` = F.interpolate(size=skip.shape[2:], bilinear, align_corners=True)
+    (Unetmodel.py:51-60,118-119,122-141)."""
+    up = F.interpolate(src, scale_factor=2, mode="bilinear", align_corners=True)
+    return F.interpolate(up, size=tuple(size), mode="bilinear", align_corners=True)
+
+
+def unet_forward(x, P, training=False, dropout_rate=0.2, masks: Optional[Sequence] = None,
+                 bf16=False, momentum=0.1, taps: Optional[dict] = None):
+    """Unet.forward (Unetmodel.py:90-149).  ``P`` holds the state_dict tensors (BN buffers are
+    updated in place when ``training``).  ``masks`` replays the eight Dropout2d draws in block order
+    conv2..conv9.  ``bf16`` wraps the pass in ``torch.autocast('cpu', bfloat16)`` as main.py:257-259
+    does on CPU.  The reference's ``checkpoint(conv5_block, use_reentrant=False)``
+    (Unetmodel.py:114-116) recomputes conv5 in backward with the RNG state restored: values and
+    gradients are unchanged, but the recomputation is a second train-mode pass through conv5's two
+    BatchNorms, so their running statistics and ``num_batches_tracked`` advance TWICE per step that
+    runs backward (pinned by tests/golden: ``train_nbt == 2``).  The oracle evaluates conv5 directly
+    and ``replay_conv5_checkpoint`` applies that second update.  ``taps`` (optional dict) receives
+    every intermediate tensor."""
+    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
+    with ctx:
+        x = even_fix(x)                                   # :92-97
+        x = x.to(torch.float32)                           # :100
+        x = F.pixel_unshuffle(x, 2)                       # :101
+        t = taps if taps is not None else {}
+        t["x16"] = x
+
+        def blk(i, inp):
+            name = BLOCKS[i][0]
+            m = None if masks is None else masks[i]
+            p = 0.0 if masks is not None else DROPOUT_P(name, dropout_rate)
+            return double_conv(inp, P, name, training, p, m, momentum, taps)
+
+        c2 = blk(0, x); p2 = F.avg_pool2d(c2, 2)          # :104-105
+        c3 = blk(1, p2); p3 = F.avg_pool2d(c3, 2)         # :107-108
+        c4 = blk(2, p3); p4 = F.avg_pool2d(c4, 2)         # :110-111
+        t["_rng_conv5"] = torch.get_rng_state()
+        c5 = blk(3, p4)                                   # :114-116
+        u6 = upsample_and_match(c5, c4.shape[2:]); m6 = blk(4, u6) + c4     # :122-125
+        u7 = upsample_and_match(m6, c3.shape[2:]); m7 = blk(5, u7) + c3     # :128-131
+        u8 = upsample_and_match(m7, c2.shape[2:]); m8 = blk(6, u8) + c2     # :134-137
+        u9 = upsample_and_match(m8, x.shape[2:]); c9 = blk(7, u9)           # :140-142
+        c10 = F.conv2d(c9, P["conv10.weight"], P["conv10.bias"])            # :143
+        out = torch.sigmoid(F.pixel_shuffle(c10, 2))                        # :147-148
+        t.update(c2=c2, p2=p2, c3=c3, p3=p3, c4=c4, p4=p4, c5=c5, u6=u6, m6=m6, u7=u7, m7=m7,
+                 u8=u8, m8=m8, u9=u9, c9=c9, c10=c10, out=out)
+    return out
+
+
+def replay_conv5_checkpoint(P, taps, dropout_rate=0.2, masks=None, bf16=False, momentum=0.1):
+    """Second train-mode evaluation of conv5 that ``torch.utils.checkpoint`` performs during backward
+    (Unetmodel.py:114-116): same input ``p4``, same Dropout2d draw (RNG state restored), result
+    discarded; only the BN buffer side effects remain."""
+    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
+    with torch.no_grad(), ctx, torch.random.fork_rng():
+        torch.set_rng_state(taps["_rng_conv5"])
+        m = None if masks is None else masks[3]
+        p = 0.0 if masks is not None else DROPOUT_P("conv5", dropout_rate)
+        double_conv(taps["p4"].detach(), P, "conv5", True, p, m, momentum)
+
+
+def calibrate_bn(P, x, generator=None):
+    """Oracle hygiene: randomise BN affine parameters and set the running statistics
+    to the real activation statistics (one train-mode pass with momentum 1.0), so eval-mode tests
+    exercise non-trivial scale/shift at every layer."""
+    for k in list(P):
+        if k.endswith(("conv.1.weight", "conv.5.weight")):
+            P[k] = torch.empty_like(P[k]).uniform_(0.5, 1.5, generator=generator)
+        elif k.endswith(("conv.1.bias", "conv.5.bias")):
+            P[k] = torch.empty_like(P[k]).uniform_(-0.5, 0.5, generator=generator)
+    with torch.no_grad():
+        unet_forward(x, P, training=True, masks=[None] * 8, momentum=1.0)
+    return P
+
+
+# ------------------------------------------------------------------------------------------------
+# Objective
+# ------------------------------------------------------------------------------------------------
+
+def l1_loss(output, target):
+    """nn.L1Loss() -- customLoss.py:96,134; pert_loss.py:23,86."""
+    return F.l1_loss(output, target)
+
+
+def custom_loss(output, target, alpha=0.9, vgg_const=0.0):
+    """CustomLoss.forward (customLoss.py:129-193).  The function asserts 0<=output<=1 (:131), forms
+    L1 (:134) and returns ``alpha*l1 + (1-alpha)*vgg`` (:160,:193).  The VGG term is re-wrapped by
+    ``torch.tensor(total_loss, requires_grad=True)`` (customLoss.py:90), i.e. a detached constant:
+    it is passed here as ``vgg_const`` (frozen torchvision VGG19 with ImageNet weights that cannot be
+    downloaded offline -- SURVEY 8c/8f).  The high-frequency, penumbra and Sobel terms
+    (:139-185) are computed and discarded by the reference and are not restated."""
+    assert output.min() >= 0 and output.max() <= 1
+    return alpha * l1_loss(output, target) + (1 - alpha) * vgg_const
+
+
+def custom_loss_grad(output, target, alpha=0.9):
+    """d custom_loss / d output = alpha * sign(output - target) / numel  (autograd of nn.L1Loss;
+    sign(0) = 0)."""
+    return alpha * torch.sign(output - target) / output.numel()
+
+
+def perturb_inputs(x, count=3, std_factor=0.01, noises: Optional[Sequence] = None):
+    """PerturbationLoss.perturb_input (pert_loss.py:26-59): per-channel unbiased std over
+    (B,H,W) (:42-45), then ``count`` copies x + randn * std_c * std_factor drawn channel by channel
+    (:50-57).  ``noises[i][c]`` ([B,1,H,W]) replays the draws; otherwise torch.randn_like consumes
+    the global generator in the reference's order."""
+    C = x.shape[1]
+    stds = [torch.std(x[:, c]).item() for c in range(C)]
+    outs = []
+    for i in range(count):
+        p = x.clone()
+        for c in range(C):
+            n = noises[i][c] if noises is not None else torch.randn_like(x[:, c:c + 1])
+            p[:, c:c + 1] += n * stds[c] * std_factor
+        outs.append(p)
+    return outs
+
+
+def perturbation_loss(model_fn: Callable, x, out, count=3, noises=None):
+    """PerturbationLoss.forward (pert_loss.py:61-90): no-grad forwards of the SAME model (in whatever
+    train/eval mode it is in) on the perturbed inputs (:78-81), mean over copies of L1(out, y_i)
+    (:84-90)."""
+    with torch.no_grad():
+        ys = [model_fn(p) for p in perturb_inputs(x, count, noises=noises)]
+    total = 0
+    for y in ys:
+        total = total + l1_loss(out, y)
+    return total / len(ys), ys
+
+
+def perturbation_loss_grad(out, ys):
+    """d perturbation_loss / d out = sum_i sign(out - y_i) / (p * numel)."""
+    g = torch.zeros_like(out)
+    for y in ys:
+        g += torch.sign(out - y)
+    return g / (len(ys) * out.numel())
+
+
+def standardise(x, means, stds):
+    """MmapLiverDataset.__getitem__ (setdata.py:306-316): (x - mean_c) / (std_c + 1e-8), fp32,
+    channel axis is the one of length 4 ahead of (H, W)."""
+    means = torch.as_tensor(means, dtype=torch.float32).view(-1, 1, 1)
+    stds = torch.as_tensor(stds, dtype=torch.float32).view(-1, 1, 1)
+    return (x - means) / (stds + 1e-8)
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage-level helpers used by the per-kernel GPU parity tests
+# ------------------------------------------------------------------------------------------------
+
+def conv_stage_eval(x, w, b, rm, rv, g, beta, residual=None, pool=False, lrelu=True, bf16=False):
+    """One conv -> eval-BN -> LeakyReLU(0.2) [-> + residual] [-> AvgPool2d(2)] stage assembled from
+    the same F ops DoubleConv uses (Unetmodel.py:21-23,26-28,40,125)."""
+    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
+    with ctx:
+        y = F.conv2d(x, w, b, padding=w.shape[-1] // 2)
+        y = F.batch_norm(y, rm, rv, g, beta, False, 0.1, 1e-5)
+        if lrelu:
+            y = F.leaky_relu(y, 0.2)
+        if residual is not None:
+            y = y + residual
+        p = F.avg_pool2d(y, 2) if pool else None
+    return y, p
+
+
+def train_step_grads(x, target, P, masks=None, alpha=0.9, dropout_rate=0.2, bf16=False,
+                     input_grad=False):
+    """One training forward + backward of the L1 objective exactly as main.py:263-281 drives it
+    (model in train mode, CustomLoss, ``loss.backward()``); returns (out, loss, {name: grad})."""
+    names = param_names()
+    leaves = {k: P[k].detach().clone().requires_grad_(True) for k in names}
+    Q = dict(P)
+    Q.update(leaves)
+    xin = x.detach().clone().requires_grad_(input_grad)
+    taps = {}
+    out = unet_forward(xin, Q, training=True, dropout_rate=dropout_rate, masks=masks, bf16=bf16,
+                       taps=taps)
+    loss = custom_loss(out.float(), target, alpha)
+    loss.backward()
+    replay_conv5_checkpoint(Q, taps, dropout_rate, masks, bf16)
+    for k in buffer_names():
+        P[k] = Q[k]
+    grads = {k: v.grad for k, v in leaves.items()}
+    if input_grad:
+        grads["input"] = xin.grad
+    return out.detach(), loss.detach(), grads
