@@ -1,0 +1,125 @@
+/* nsm_b200.h -- C ABI of libnsm_b200.so, the B200 (sm_100a) implementation of the Neural-Shadow-Mapping U-Net
+ * hot path of SDU-Gary/PCSS-Unet.
+ *
+ * Conventions:
+ *   - plain C: raw device pointers, explicit sizes, `void* stream` is a cudaStream_t (NULL = legacy default
+ *     stream); no C++ types, no exceptions cross this boundary;
+ *   - every function returns 0 on success; on failure a non-zero code and a message retrievable with
+ *     nsm_last_error() (thread-local).  Work is only enqueued on `stream`; nothing synchronises except the
+ *     *_host entry point, which is documented to;
+ *   - the caller owns every buffer (weights blob, workspace, inputs, outputs).  Sizes are queried first;
+ *   - thread-safe: PyTorch calls backward from its autograd worker thread (main.py:281).
+ *
+ * `mode` selects the arithmetic:
+ *   NSM_MODE_BF16  activations/weights bf16, fp32 accumulate, rounding points of torch.autocast(bfloat16)
+ *   NSM_MODE_FP32  fp32-accurate: every tensor is held as hi+lo bf16 planes, products hi*hi+hi*lo+lo*hi are
+ *                  accumulated in fp32 on the tensor cores (network output within 1e-4 of the fp32 reference)
+ *
+ * Each entry point cites the reference interface (file:line in SDU-Gary/PCSS-Unet) it stands in for.
+ */
+#ifndef NSM_B200_H_
+#define NSM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSM_MODE_BF16 0
+#define NSM_MODE_FP32 1
+
+/* number of fp32 tensors nsm_unet_pack() consumes, in this order:
+ *   for K in conv2..conv9 (Unetmodel.py:39-61):
+ *     conv.0.weight, conv.0.bias, conv.1.weight, conv.1.bias, conv.1.running_mean, conv.1.running_var,
+ *     conv.4.weight, conv.4.bias, conv.5.weight, conv.5.bias, conv.5.running_mean, conv.5.running_var
+ *   conv10.weight, conv10.bias (Unetmodel.py:63)                                                      */
+#define NSM_UNET_NUM_TENSORS 98
+
+const char* nsm_last_error(void);
+int nsm_version(void);
+/* 0 if the current CUDA device is compute capability 10.x (B200), else non-zero + message */
+int nsm_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Whole network, eval mode:  Unet.forward under model.eval()  (Unetmodel.py:90-149; call sites infer.py:65,
+ * inference.py:194, main.py:611, validate_consistency.py:49,68)
+ * --------------------------------------------------------------------------------------------------------- */
+size_t nsm_unet_packed_bytes(int mode);
+/* state_dict tensors (device pointers, reference layouts: OIHW weights, [C] vectors) -> packed blob */
+int nsm_unet_pack(const float* const* tensors, int mode, void* blob, void* stream);
+size_t nsm_unet_workspace_bytes(int B, int H, int W, int mode);
+/* x: [B,4,H,W] fp32 NCHW (device).  y: [B,1,H-H%2,W-W%2] fp32 (device).  mean/std: optional [4] device vectors:
+ * fuses MmapLiverDataset's (x-mean)/(std+1e-8) (setdata.py:316) into the first load; NULL = input already
+ * standardised (what main.py feeds) or raw (what infer.py feeds). */
+int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int W, const float* mean,
+                   const float* std, float* y, void* workspace, size_t workspace_bytes, void* stream);
+/* Same with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, stream synchronise. */
+int nsm_unet_infer_host(const void* blob, int mode, const float* x_host, int B, int H, int W, const float* mean,
+                        const float* std, float* y_host, void* workspace, size_t workspace_bytes, void* stream);
+/* Copy a named intermediate of the last nsm_unet_infer() on this workspace to NCHW fp32 (tests / debugging).
+ * names: c2 p2 t3 c3 p3 t4 c4 p4 t5 c5 u6 t6 m6 u7 t7 m7 u8 t8 m8 u9 t9.  *C,*h,*w receive its shape. */
+int nsm_unet_tap(const void* workspace, int B, int H, int W, int mode, const char* name, float* out, int* C,
+                 int* h, int* w, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stage-level entry points (per-fused-stage parity tests; SURVEY.md 8c tolerance protocol)
+ * Activations are NHWC bf16 "planes": plane 0 (= the value in bf16 mode, the hi part in fp32 mode), plane 1
+ * (lo part, fp32 mode only).
+ * --------------------------------------------------------------------------------------------------------- */
+int nsm_nchw_to_planes(const float* x, int N, int C, int H, int W, int mode, void* plane0, void* plane1,
+                       void* stream);
+int nsm_planes_to_nchw(const void* plane0, const void* plane1, int N, int C, int H, int W, int mode, float* y,
+                       void* stream);
+/* nn.Conv2d weight [Cout,Cin,k,k] -> GEMM operand [Cout][k*k][Cin] (dgrad!=0: [Cin][k*k mirrored][Cout]) */
+int nsm_pack_conv_weight(const float* w, int Cout, int Cin, int ksize, int dgrad, int mode, void* plane0,
+                         void* plane1, void* stream);
+
+typedef struct nsm_conv_args {
+  int N, H, W, Cin, Cout, ksize; /* ksize 1 or 3 (pad 1); Cin, Cout multiples of 64 */
+  int mode;
+  const void* in[2];       /* [N,H,W,Cin] planes */
+  const void* weight[2];   /* packed planes */
+  const float* bias;       /* [Cout] or NULL                           nn.Conv2d bias      Unetmodel.py:21,26 */
+  const float* bn_scale;   /* [Cout] or NULL  gamma/sqrt(var+eps)      nn.BatchNorm2d      Unetmodel.py:22,27 */
+  const float* bn_shift;   /* [Cout]          beta - mean*scale                                              */
+  int lrelu;               /* LeakyReLU(0.2)                                               Unetmodel.py:23,28 */
+  void* out[2];            /* [N,H,W,Cout] planes or NULL */
+  const void* residual[2]; /* [N,H,W,Cout] planes or NULL: skip add    Unetmodel.py:125,131,137              */
+  void* pool[2];           /* [N,H/2,W/2,Cout] planes or NULL: AvgPool2d(2)               Unetmodel.py:40,43,46 */
+  float* out_f32;          /* optional [N,H,W,Cout] fp32: conv + bias before BN */
+} nsm_conv_args;
+int nsm_conv_fwd(const nsm_conv_args* a, void* stream);
+
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=True) then F.interpolate(size=(hd,wd)) -- Unetmodel.py:51-60,
+ * 118-141 */
+int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, void* const* dst, int hd, int wd,
+                       int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Objective: nn.L1Loss value + gradient (customLoss.py:96,134,160; pert_loss.py:23,84-90) in one pass.
+ *   acc[0] += sum|out-target|   acc[1] += sum_i sum|out-perturbed_i|   acc[2] += #{out<0 or out>1 or NaN}
+ *   grad    = coef_l1*sign(out-target) + coef_pert*sum_i sign(out-perturbed_i)        (grad may be NULL)
+ * target may be NULL; n_perturbed <= 4.  acc must be zeroed by the caller. */
+int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
+                        long long numel, float coef_l1, float coef_pert, float* grad, double* acc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Input statistics / standardisation / perturbation
+ * --------------------------------------------------------------------------------------------------------- */
+/* calculate_dataset_stats.py:59-79: x [S,C,HW] fp32; means==NULL: sums[c] += sum x, else sums[c] += sum (x-means[c])^2 */
+int nsm_channel_sums(const float* x, long long S, int C, long long HW, const double* means, double* sums,
+                     void* stream);
+/* setdata.py:316: y = (x - mean[c]) / (std[c] + 1e-8) */
+int nsm_standardize(const float* x, float* y, long long S, int C, long long HW, const float* mean,
+                    const float* std, void* stream);
+/* pert_loss.py:50-57: out[i] = x + (noise[i] * stds[c]) * std_factor, i < count; out [count,B,C,HW];
+ * noise [count,C,B,HW] (one contiguous block per randn_like draw of the reference) */
+int nsm_perturb(const float* x, const float* noise, float* out, int count, long long B, int C, long long HW,
+                const float* stds, float std_factor, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSM_B200_H_ */

@@ -1,0 +1,396 @@
+// C ABI of libnsm_b200.so (see include/nsm_b200.h) and the eval-mode whole-network orchestration.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nsm_b200.h"
+#include "conv_gemm.cuh"
+#include "nsm_common.cuh"
+#include "stream_kernels.cuh"
+
+namespace nsm {
+const char* last_error();
+
+// ------------------------------------------------------------------------------------------------
+// network description (Unetmodel.py:36-63)
+// ------------------------------------------------------------------------------------------------
+struct BlockDef {
+  int cin, cout;
+};
+static const BlockDef kBlocks[8] = {{16, 64},   {64, 128},  {128, 512}, {512, 1024},
+                                    {1024, 512}, {512, 128}, {128, 64},  {64, 16}};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Packed parameter blob: for every block the two per-channel vector triples (bias, BN scale, BN shift) and the
+// weights either as GEMM operand planes (tensor-core layers) or as fp32 OIHW (head: conv2, tail: conv9 1x1, conv10).
+struct PackedLayout {
+  size_t w3[8][2];  // 3x3 weight planes (block 0: fp32 OIHW copy in [0])
+  size_t w1[8][2];  // 1x1 weight planes (blocks 0 and 7: fp32 copy in [0])
+  size_t v3[8][3];  // bias, scale, shift of the 3x3 stage  [cin]
+  size_t v1[8][3];  // bias, scale, shift of the 1x1 stage  [cout]
+  size_t w10, b10;
+  size_t total;
+};
+
+static PackedLayout packed_layout(int mode) {
+  const int np = mode == NSM_MODE_FP32 ? 2 : 1;
+  PackedLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  for (int b = 0; b < 8; ++b) {
+    const size_t cin = kBlocks[b].cin, cout = kBlocks[b].cout;
+    const bool gemm3 = b != 0, gemm1 = (b != 0 && b != 7);
+    for (int p = 0; p < 2; ++p) {
+      if (gemm3) L.w3[b][p] = p < np ? take(cin * cin * 9 * 2) : 0;   // bf16 GEMM operand plane
+      else L.w3[b][p] = p == 0 ? take(cin * cin * 9 * 4) : 0;         // fp32 OIHW for the SIMT head
+      if (gemm1) L.w1[b][p] = p < np ? take(cin * cout * 2) : 0;
+      else L.w1[b][p] = p == 0 ? take(cin * cout * 4) : 0;
+    }
+    for (int k = 0; k < 3; ++k) {
+      L.v3[b][k] = take(cin * 4);
+      L.v1[b][k] = take(cout * 4);
+    }
+  }
+  L.w10 = take(4 * 16 * 4);
+  L.b10 = take(4 * 4);
+  L.total = off;
+  return L;
+}
+
+// Workspace: one NHWC planes buffer per intermediate (names as in nsm_unet_tap).
+struct Level {
+  int h, w;
+};
+struct TapDef {
+  const char* name;
+  int level;  // 1..4 : spatial level (h1 = H/2 ... h4)
+  int C;
+};
+static const TapDef kTaps[] = {
+    {"c2", 1, 64},   {"p2", 2, 64},   {"t3", 2, 64},   {"c3", 2, 128},  {"p3", 3, 128}, {"t4", 3, 128},
+    {"c4", 3, 512},  {"p4", 4, 512},  {"t5", 4, 512},  {"c5", 4, 1024}, {"u6", 3, 1024}, {"t6", 3, 1024},
+    {"m6", 3, 512},  {"u7", 2, 512},  {"t7", 2, 512},  {"m7", 2, 128},  {"u8", 1, 128}, {"t8", 1, 128},
+    {"m8", 1, 64},   {"u9", 1, 64},   {"t9", 1, 64},
+};
+constexpr int kNumTaps = sizeof(kTaps) / sizeof(kTaps[0]);
+
+struct WorkspaceLayout {
+  Level lv[5];
+  size_t off[kNumTaps][2];
+  size_t x_stage;  // device staging of the input for the *_host entry point
+  size_t y_stage;
+  size_t total;
+};
+
+static WorkspaceLayout workspace_layout(int B, int H, int W, int mode) {
+  const int np = mode == NSM_MODE_FP32 ? 2 : 1;
+  WorkspaceLayout L;
+  const int He = H - (H & 1), We = W - (W & 1);
+  L.lv[0] = {He, We};
+  L.lv[1] = {He / 2, We / 2};
+  for (int l = 2; l <= 4; ++l) L.lv[l] = {L.lv[l - 1].h / 2, L.lv[l - 1].w / 2};
+  size_t off = 0;
+  for (int t = 0; t < kNumTaps; ++t) {
+    const Level& v = L.lv[kTaps[t].level];
+    const size_t bytes = size_t(B) * v.h * v.w * kTaps[t].C * 2;
+    for (int p = 0; p < 2; ++p) {
+      L.off[t][p] = off;
+      if (p < np) off = align_up(off + bytes, 1024);
+    }
+  }
+  L.x_stage = off;
+  off = align_up(off + size_t(B) * 4 * H * W * 4, 1024);
+  L.y_stage = off;
+  off = align_up(off + size_t(B) * He * We * 4, 1024);
+  L.total = off;
+  return L;
+}
+
+static int tap_index(const char* name) {
+  for (int t = 0; t < kNumTaps; ++t)
+    if (!strcmp(kTaps[t].name, name)) return t;
+  return -1;
+}
+
+static Planes ws_planes(const WorkspaceLayout& L, void* ws, const char* name, int np) {
+  const int t = tap_index(name);
+  Planes p;
+  p.p[0] = reinterpret_cast<uint8_t*>(ws) + L.off[t][0];
+  p.p[1] = np == 2 ? reinterpret_cast<uint8_t*>(ws) + L.off[t][1] : nullptr;
+  return p;
+}
+
+}  // namespace nsm
+
+using namespace nsm;
+
+#define NSM_TRY(expr)          \
+  do {                         \
+    if ((expr) != 0) return 1; \
+  } while (0)
+
+extern "C" {
+
+const char* nsm_last_error(void) { return nsm::last_error(); }
+int nsm_version(void) { return 100; }
+
+int nsm_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    set_error("device %d is sm_%d%d; libnsm_b200 is built for sm_100a only (no fallback path)", dev, major, minor);
+    return 2;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- pack
+size_t nsm_unet_packed_bytes(int mode) { return packed_layout(mode).total; }
+
+int nsm_unet_pack(const float* const* T, int mode, void* blob, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode != NSM_MODE_BF16 && mode != NSM_MODE_FP32) {
+    set_error("nsm_unet_pack: bad mode %d", mode);
+    return 1;
+  }
+  const PackedLayout L = packed_layout(mode);
+  const int rb = mode == NSM_MODE_BF16;
+  uint8_t* base = reinterpret_cast<uint8_t*>(blob);
+  for (int b = 0; b < 8; ++b) {
+    const float* const* t = T + 12 * b;
+    const int cin = kBlocks[b].cin, cout = kBlocks[b].cout;
+    // 3x3 stage
+    if (b == 0) {
+      NSM_TRY(copy_round(t[0], reinterpret_cast<float*>(base + L.w3[b][0]), cin * cin * 9, rb, st));
+    } else {
+      NSM_TRY(pack_conv_weight(t[0], cin, cin, 3, 0, base + L.w3[b][0], rb ? nullptr : base + L.w3[b][1], st));
+    }
+    NSM_TRY(copy_round(t[1], reinterpret_cast<float*>(base + L.v3[b][0]), cin, rb, st));
+    NSM_TRY(bn_fold_eval(t[2], t[3], t[4], t[5], cin, 1e-5f, reinterpret_cast<float*>(base + L.v3[b][1]),
+                         reinterpret_cast<float*>(base + L.v3[b][2]), st));
+    // 1x1 stage
+    if (b == 0 || b == 7) {
+      NSM_TRY(copy_round(t[6], reinterpret_cast<float*>(base + L.w1[b][0]), cin * cout, rb, st));
+    } else {
+      NSM_TRY(pack_conv_weight(t[6], cout, cin, 1, 0, base + L.w1[b][0], rb ? nullptr : base + L.w1[b][1], st));
+    }
+    NSM_TRY(copy_round(t[7], reinterpret_cast<float*>(base + L.v1[b][0]), cout, rb, st));
+    NSM_TRY(bn_fold_eval(t[8], t[9], t[10], t[11], cout, 1e-5f, reinterpret_cast<float*>(base + L.v1[b][1]),
+                         reinterpret_cast<float*>(base + L.v1[b][2]), st));
+  }
+  NSM_TRY(copy_round(T[96], reinterpret_cast<float*>(base + L.w10), 64, rb, st));
+  NSM_TRY(copy_round(T[97], reinterpret_cast<float*>(base + L.b10), 4, rb, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- infer
+size_t nsm_unet_workspace_bytes(int B, int H, int W, int mode) {
+  if (B < 1 || H < 16 || W < 16) return 0;
+  return workspace_layout(B, H, W, mode).total;
+}
+
+int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int W, const float* mean,
+                   const float* std, float* y, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode != NSM_MODE_BF16 && mode != NSM_MODE_FP32) {
+    set_error("nsm_unet_infer: bad mode %d", mode);
+    return 1;
+  }
+  if (B < 1 || H < 16 || W < 16) {
+    set_error("nsm_unet_infer: input %dx%dx%d too small (need H,W >= 16)", B, H, W);
+    return 1;
+  }
+  const WorkspaceLayout WL = workspace_layout(B, H, W, mode);
+  if (ws_bytes < WL.total) {
+    set_error("nsm_unet_infer: workspace %zu B < required %zu B", ws_bytes, WL.total);
+    return 1;
+  }
+  const PackedLayout PL = packed_layout(mode);
+  const int np = mode == NSM_MODE_FP32 ? 2 : 1;
+  const uint8_t* pb = reinterpret_cast<const uint8_t*>(blob);
+  auto fvec = [&](size_t off) { return reinterpret_cast<const float*>(pb + off); };
+  auto wplanes = [&](const size_t (&o)[2]) {
+    Planes p;
+    p.p[0] = const_cast<uint8_t*>(pb + o[0]);
+    p.p[1] = np == 2 ? const_cast<uint8_t*>(pb + o[1]) : nullptr;
+    return p;
+  };
+  auto buf = [&](const char* name) { return ws_planes(WL, ws, name, np); };
+  const Planes none = {{nullptr, nullptr}};
+
+  // ---- head: conv2 block + pool
+  {
+    HeadParams hp;
+    hp.x = x; hp.N = B; hp.Hin = H; hp.Win = W; hp.mean = mean; hp.std = std;
+    hp.w0 = fvec(PL.w3[0][0]); hp.b0 = fvec(PL.v3[0][0]); hp.s0 = fvec(PL.v3[0][1]); hp.t0 = fvec(PL.v3[0][2]);
+    hp.w1 = fvec(PL.w1[0][0]); hp.b1 = fvec(PL.v1[0][0]); hp.s1 = fvec(PL.v1[0][1]); hp.t1 = fvec(PL.v1[0][2]);
+    hp.planes = np; hp.c2 = buf("c2"); hp.p2 = buf("p2"); hp.x16 = none;
+    NSM_TRY(head_eval(hp, st));
+  }
+  // ---- one DoubleConv on the tensor cores
+  auto double_conv = [&](int b, int level, const Planes& in, const char* tname, const char* oname,
+                         const char* resname, const char* poolname) -> int {
+    const Level& lv = WL.lv[level];
+    ConvShape s3 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cin, 9, np};
+    ConvEpilogue e3;
+    e3.bias = fvec(PL.v3[b][0]); e3.scale = fvec(PL.v3[b][1]); e3.shift = fvec(PL.v3[b][2]);
+    e3.lrelu = 1; e3.round_bf16 = np == 1; e3.out = buf(tname); e3.residual = none; e3.pool = none;
+    e3.out_f32 = nullptr;
+    NSM_TRY(conv_gemm_launch(s3, in, wplanes(PL.w3[b]), e3, st));
+    if (!oname) return 0;
+    ConvShape s1 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cout, 1, np};
+    ConvEpilogue e1 = e3;
+    e1.bias = fvec(PL.v1[b][0]); e1.scale = fvec(PL.v1[b][1]); e1.shift = fvec(PL.v1[b][2]);
+    e1.out = buf(oname);
+    e1.residual = resname ? buf(resname) : none;
+    e1.pool = poolname ? buf(poolname) : none;
+    NSM_TRY(conv_gemm_launch(s1, buf(tname), wplanes(PL.w1[b]), e1, st));
+    return 0;
+  };
+  auto up = [&](const char* src, int slevel, int C, const char* dst, int dlevel) -> int {
+    return upsample_match(buf(src), B, WL.lv[slevel].h, WL.lv[slevel].w, C, buf(dst), WL.lv[dlevel].h,
+                          WL.lv[dlevel].w, np, st);
+  };
+  NSM_TRY(double_conv(1, 2, buf("p2"), "t3", "c3", nullptr, "p3"));   // conv3 + pool3
+  NSM_TRY(double_conv(2, 3, buf("p3"), "t4", "c4", nullptr, "p4"));   // conv4 + pool4
+  NSM_TRY(double_conv(3, 4, buf("p4"), "t5", "c5", nullptr, nullptr));  // conv5
+  NSM_TRY(up("c5", 4, 1024, "u6", 3));
+  NSM_TRY(double_conv(4, 3, buf("u6"), "t6", "m6", "c4", nullptr));   // conv6 + skip
+  NSM_TRY(up("m6", 3, 512, "u7", 2));
+  NSM_TRY(double_conv(5, 2, buf("u7"), "t7", "m7", "c3", nullptr));   // conv7 + skip
+  NSM_TRY(up("m7", 2, 128, "u8", 1));
+  NSM_TRY(double_conv(6, 1, buf("u8"), "t8", "m8", "c2", nullptr));   // conv8 + skip
+  NSM_TRY(up("m8", 1, 64, "u9", 1));                                   // x2 up then back down to (h1, w1)
+  NSM_TRY(double_conv(7, 1, buf("u9"), "t9", nullptr, nullptr, nullptr));  // conv9 3x3 stage
+  // ---- tail: conv9 1x1 + conv10 + sigmoid + pixel_shuffle
+  {
+    TailParams tp;
+    tp.a = buf("t9"); tp.N = B; tp.h = WL.lv[1].h; tp.w = WL.lv[1].w;
+    tp.w1 = fvec(PL.w1[7][0]); tp.b1 = fvec(PL.v1[7][0]); tp.s1 = fvec(PL.v1[7][1]); tp.t1 = fvec(PL.v1[7][2]);
+    tp.w10 = fvec(PL.w10); tp.b10 = fvec(PL.b10); tp.planes = np; tp.y = y;
+    NSM_TRY(tail_eval(tp, st));
+  }
+  return 0;
+}
+
+int nsm_unet_infer_host(const void* blob, int mode, const float* x_host, int B, int H, int W, const float* mean,
+                        const float* std, float* y_host, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 1 || H < 16 || W < 16) {
+    set_error("nsm_unet_infer_host: bad shape");
+    return 1;
+  }
+  const WorkspaceLayout WL = workspace_layout(B, H, W, mode);
+  if (ws_bytes < WL.total) {
+    set_error("nsm_unet_infer_host: workspace %zu B < required %zu B", ws_bytes, WL.total);
+    return 1;
+  }
+  float* xd = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + WL.x_stage);
+  float* yd = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + WL.y_stage);
+  const size_t xin = size_t(B) * 4 * H * W * 4, yout = size_t(B) * WL.lv[0].h * WL.lv[0].w * 4;
+  cudaError_t e = cudaMemcpyAsync(xd, x_host, xin, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) {
+    set_error("H2D copy: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  NSM_TRY(nsm_unet_infer(blob, mode, xd, B, H, W, mean, std, yd, ws, ws_bytes, stream));
+  e = cudaMemcpyAsync(y_host, yd, yout, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error("D2H copy / sync: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int nsm_unet_tap(const void* ws, int B, int H, int W, int mode, const char* name, float* out, int* C, int* h,
+                 int* w, void* stream) {
+  const int t = tap_index(name);
+  if (t < 0) {
+    set_error("nsm_unet_tap: unknown tap '%s'", name);
+    return 1;
+  }
+  const WorkspaceLayout WL = workspace_layout(B, H, W, mode);
+  const int np = mode == NSM_MODE_FP32 ? 2 : 1;
+  const Level& lv = WL.lv[kTaps[t].level];
+  if (C) *C = kTaps[t].C;
+  if (h) *h = lv.h;
+  if (w) *w = lv.w;
+  if (!out) return 0;
+  const Planes p = ws_planes(WL, const_cast<void*>(ws), name, np);
+  return planes_to_nchw(p.p[0], p.p[1], B, kTaps[t].C, lv.h, lv.w, np, out, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------- stages
+int nsm_nchw_to_planes(const float* x, int N, int C, int H, int W, int mode, void* p0, void* p1, void* stream) {
+  return nchw_to_planes(x, N, C, H, W, mode == NSM_MODE_FP32 ? 2 : 1, p0, p1, static_cast<cudaStream_t>(stream));
+}
+int nsm_planes_to_nchw(const void* p0, const void* p1, int N, int C, int H, int W, int mode, float* y,
+                       void* stream) {
+  return planes_to_nchw(p0, p1, N, C, H, W, mode == NSM_MODE_FP32 ? 2 : 1, y, static_cast<cudaStream_t>(stream));
+}
+int nsm_pack_conv_weight(const float* w, int Cout, int Cin, int ksize, int dgrad, int mode, void* p0, void* p1,
+                         void* stream) {
+  return pack_conv_weight(w, Cout, Cin, ksize, dgrad, p0, mode == NSM_MODE_FP32 ? p1 : nullptr,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int nsm_conv_fwd(const nsm_conv_args* a, void* stream) {
+  if (!a) {
+    set_error("nsm_conv_fwd: null args");
+    return 1;
+  }
+  const int np = a->mode == NSM_MODE_FP32 ? 2 : 1;
+  ConvShape s = {a->N, a->H, a->W, a->Cin, a->Cout, a->ksize * a->ksize, np};
+  Planes in = {{const_cast<void*>(a->in[0]), const_cast<void*>(a->in[1])}};
+  Planes w = {{const_cast<void*>(a->weight[0]), const_cast<void*>(a->weight[1])}};
+  ConvEpilogue e;
+  e.bias = a->bias; e.scale = a->bn_scale; e.shift = a->bn_shift; e.lrelu = a->lrelu;
+  e.round_bf16 = a->mode == NSM_MODE_BF16;
+  e.out = {{a->out[0], a->out[1]}};
+  e.residual = {{const_cast<void*>(a->residual[0]), const_cast<void*>(a->residual[1])}};
+  e.pool = {{a->pool[0], a->pool[1]}};
+  e.out_f32 = a->out_f32;
+  return conv_gemm_launch(s, in, w, e, static_cast<cudaStream_t>(stream));
+}
+
+int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, void* const* dst, int hd, int wd,
+                       int mode, void* stream) {
+  Planes s = {{const_cast<void*>(src[0]), const_cast<void*>(src[1])}};
+  Planes d = {{dst[0], dst[1]}};
+  return upsample_match(s, N, hs, ws, C, d, hd, wd, mode == NSM_MODE_FP32 ? 2 : 1,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
+                        long long numel, float coef_l1, float coef_pert, float* grad, double* acc, void* stream) {
+  return l1_loss_fwd_bwd(out, target, perturbed, n_perturbed, numel, coef_l1, coef_pert, grad, acc,
+                         static_cast<cudaStream_t>(stream));
+}
+int nsm_channel_sums(const float* x, long long S, int C, long long HW, const double* means, double* sums,
+                     void* stream) {
+  return channel_sums(x, S, C, HW, means, sums, static_cast<cudaStream_t>(stream));
+}
+int nsm_standardize(const float* x, float* y, long long S, int C, long long HW, const float* mean,
+                    const float* std, void* stream) {
+  return standardize(x, y, S, C, HW, mean, std, static_cast<cudaStream_t>(stream));
+}
+int nsm_perturb(const float* x, const float* noise, float* out, int count, long long B, int C, long long HW,
+                const float* stds, float std_factor, void* stream) {
+  return perturb(x, noise, out, count, B, C, HW, stds, std_factor, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

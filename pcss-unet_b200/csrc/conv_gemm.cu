@@ -1,0 +1,482 @@
+// Implicit-GEMM convolution (3x3 pad 1 / 1x1, stride 1) for NHWC bf16 "planes" on Blackwell tensor cores.
+//
+//   GEMM view:  D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * Wp[cout, tap, cin]
+//   M tile  = 8 x 16 spatial patch (128 pixels)           -> TMEM lanes
+//   N tile  = BN output channels (64 / 128 / 256)          -> TMEM columns (fp32 accumulators, 2 stages)
+//   K block = one filter tap x 64 input channels (128-byte swizzled smem rows)
+//
+// A tiles are fetched by ONE 4-D tiled TMA box {64 ch, 16, 8, 1} whose (x, y) start is shifted by the tap
+// offset; out-of-bounds (incl. negative) coordinates are zero-filled by the TMA unit, which is exactly the
+// convolution's zero padding and also pads ragged right/bottom tiles.  The box lands in shared memory as 128
+// rows of 128 B with the 128-byte swizzle = the canonical K-major UMMA operand layout, so no im2col buffer,
+// no index math and no smem transform is needed.  B tiles (weights, pre-packed [Cout][tap][Cin]) are 2-D boxes.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over work items):
+//   warp 0    TMA producer          (smem full/empty mbarrier ring)
+//   warp 1    tcgen05.mma issuer    (single thread; accumulators double-buffered in TMEM)
+//   warps 2-5 epilogue              (tcgen05.ld -> bias, BN affine, LeakyReLU, residual add, 2x2 avg-pool,
+//                                    bf16 (or hi/lo split) NHWC stores)
+//
+// fp32 mode ("planes == 2"): every activation/weight is stored as hi + lo bf16 planes and the issuer runs
+// hi*hi + hi*lo + lo*hi into the same fp32 accumulator (error ~2^-17 per product, 1.5e-5 on the network output).
+#include <mutex>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "conv_gemm.cuh"
+#include "nsm_common.cuh"
+
+namespace nsm {
+
+// ------------------------------------------------------------------------------------------------
+// error string (thread local), shared by all translation units
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor encoding through the driver entry point
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(map, dt, rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)", int(r), rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+struct ConvKernelParams {
+  int N, H, W, Cin, Cout, taps;
+  int tiles_x, tiles_y, n_blocks, total_items, kc_per_tap;
+  ConvEpilogue ep;
+};
+
+template <int BN, int NP>
+struct GemmCfg {
+  static constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 bf16
+  static constexpr int B_BYTES = BN * 128;   // BN channels x 64 bf16
+  static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+};
+
+__device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item, int& n, int& y0, int& x0,
+                                            int& nb) {
+  nb = item % p.n_blocks;
+  int t = item / p.n_blocks;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  n = t / p.tiles_y;
+  y0 = ty * kTileH;
+  x0 = tx * kTileW;
+}
+
+template <int BN, int NP>
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ ConvKernelParams p) {
+  using Cfg = GemmCfg<BN, NP>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // 1024-byte aligned (SWIZZLE_128B)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (NP == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.taps * p.kc_per_tap;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int n, y0, x0, nb;
+        decode_item(p, item, n, y0, x0, nb);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
+          const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + NP * Cfg::A_BYTES;
+            tma_load_4d(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+            if (NP == 2) tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+            tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, nb * BN);
+            if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, nb * BN);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_hi = a_hi + NP * Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < kKChunk / 16; ++k) {
+            const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, 1024);
+            const uint64_t db_hi = make_desc_sw128(b_hi + k * 32, 16, 1024);
+            umma_bf16(d, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (NP == 2) {
+              const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
+              const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
+              umma_bf16(d, da_hi, db_lo, idesc, 1u);
+              umma_bf16(d, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;         // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;  // pixel index inside the patch
+    const int ly = row / kTileW, lx = row % kTileW;
+    const ConvEpilogue& ep = p.ep;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int n, y0, x0, nb;
+      decode_item(p, item, n, y0, x0, nb);
+      const int y = y0 + ly, x = x0 + lx;
+      const bool valid = (y < p.H) && (x < p.W);
+      const size_t pix = (size_t(n) * p.H + y) * p.W + x;
+      const int Hp = p.H >> 1, Wp = p.W >> 1;
+      const bool pool_anchor = ((lane & 1) == 0) && ((lane & 16) == 0) && ((y >> 1) < Hp) && ((x >> 1) < Wp);
+      const size_t ppix = (size_t(n) * Hp + (y >> 1)) * Wp + (x >> 1);
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c0, r);
+        tmem_ld_wait();
+        const int cb = nb * BN + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + cb + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.out_f32 && valid) {
+          float4* o = reinterpret_cast<float4*>(ep.out_f32 + pix * p.Cout + cb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (ep.round_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+        }
+        if (ep.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(ep.scale + cb + j));
+            const float4 t = __ldg(reinterpret_cast<const float4*>(ep.shift + cb + j));
+            v[j] = fmaf(v[j], s.x, t.x); v[j + 1] = fmaf(v[j + 1], s.y, t.y);
+            v[j + 2] = fmaf(v[j + 2], s.z, t.z); v[j + 3] = fmaf(v[j + 3], s.w, t.w);
+          }
+          if (ep.round_bf16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+          }
+        }
+        if (ep.lrelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
+          if (ep.round_bf16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+          }
+        }
+        if (ep.residual.p[0] && valid) {
+          const uint8_t* r0 = reinterpret_cast<const uint8_t*>(ep.residual.p[0]) + (pix * p.Cout + cb) * 2;
+          const uint8_t* r1 = NP == 2 ? reinterpret_cast<const uint8_t*>(ep.residual.p[1]) + (pix * p.Cout + cb) * 2
+                                      : nullptr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 h = ldg16(r0 + 16 * j);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[8 * j + 2 * e] += bf16lo_to_f32(hw[e]);
+              v[8 * j + 2 * e + 1] += bf16hi_to_f32(hw[e]);
+            }
+            if (NP == 2) {
+              const uint4 l = ldg16(r1 + 16 * j);
+              const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[8 * j + 2 * e] += bf16lo_to_f32(lw[e]);
+                v[8 * j + 2 * e + 1] += bf16hi_to_f32(lw[e]);
+              }
+            }
+          }
+          if (ep.round_bf16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+          }
+        }
+        if (ep.out.p[0] && valid) {
+          uint8_t* o0 = reinterpret_cast<uint8_t*>(ep.out.p[0]) + (pix * p.Cout + cb) * 2;
+          uint8_t* o1 = NP == 2 ? reinterpret_cast<uint8_t*>(ep.out.p[1]) + (pix * p.Cout + cb) * 2 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+              hw[e] = pack_bf16(a, b);
+              if (NP == 2) lw[e] = pack_bf16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
+            }
+            stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+            if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+          }
+        }
+        if (ep.pool.p[0]) {  // warp-uniform: AvgPool2d(2) over (lane^1, lane^16) partners
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float s = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            s *= 0.25f;
+            v[j] = ep.round_bf16 ? rbf(s) : s;
+          }
+          if (pool_anchor) {
+            uint8_t* o0 = reinterpret_cast<uint8_t*>(ep.pool.p[0]) + (ppix * p.Cout + cb) * 2;
+            uint8_t* o1 = NP == 2 ? reinterpret_cast<uint8_t*>(ep.pool.p[1]) + (ppix * p.Cout + cb) * 2 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+                hw[e] = pack_bf16(a, b);
+                if (NP == 2) lw[e] = pack_bf16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
+              }
+              stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+              if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
+template <int BN, int NP>
+static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, NP>;
+  auto kern = conv_gemm_kernel<BN, NP>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(conv_gemm<%d,%d>, %d B smem): %s", BN, NP, Cfg::SMEM_BYTES,
+                cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("conv_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int g_force_bn = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+    const char* f = getenv("NSM_FORCE_BN");
+    if (f) g_force_bn = atoi(f);
+  }
+  return g_num_sms;
+}
+
+int conv_gemm_pick_bn(const ConvShape& s) {
+  num_sms();
+  if (g_force_bn && s.Cout % g_force_bn == 0) return g_force_bn;
+  if (s.planes == 1 && s.Cout % 256 == 0) return 256;
+  if (s.Cout % 128 == 0) return 128;
+  return 64;
+}
+
+int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, const ConvEpilogue& ep,
+                     cudaStream_t stream) {
+  if (s.Cin % kKChunk || s.Cout % 64 || (s.taps != 1 && s.taps != 9) || (s.planes != 1 && s.planes != 2) ||
+      s.N <= 0 || s.H <= 0 || s.W <= 0) {
+    set_error("conv_gemm: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d taps=%d planes=%d", s.N, s.H, s.W,
+              s.Cin, s.Cout, s.taps, s.planes);
+    return 1;
+  }
+  const int BN = conv_gemm_pick_bn(s);
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  const uint64_t adims[4] = {uint64_t(s.Cin), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
+  const uint64_t astr[3] = {uint64_t(s.Cin) * 2, uint64_t(s.W) * s.Cin * 2, uint64_t(s.H) * s.W * s.Cin * 2};
+  const uint32_t abox[4] = {uint32_t(kKChunk), uint32_t(kTileW), uint32_t(kTileH), 1};
+  const uint64_t K = uint64_t(s.taps) * s.Cin;
+  const uint64_t bdims[2] = {K, uint64_t(s.Cout)};
+  const uint64_t bstr[1] = {K * 2};
+  const uint32_t bbox[2] = {uint32_t(kKChunk), uint32_t(BN)};
+  for (int pl = 0; pl < s.planes; ++pl) {
+    if (!in.p[pl] || !w.p[pl]) {
+      set_error("conv_gemm: null operand plane %d", pl);
+      return 1;
+    }
+    if (encode_tmap_tiled(&maps[pl], in.p[pl], 4, adims, astr, abox, 2)) return 1;
+    if (encode_tmap_tiled(&maps[2 + pl], w.p[pl], 2, bdims, bstr, bbox, 2)) return 1;
+  }
+  if (s.planes == 1) {
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+  }
+  ConvKernelParams kp;
+  kp.N = s.N; kp.H = s.H; kp.W = s.W; kp.Cin = s.Cin; kp.Cout = s.Cout; kp.taps = s.taps;
+  kp.tiles_x = (s.W + kTileW - 1) / kTileW;
+  kp.tiles_y = (s.H + kTileH - 1) / kTileH;
+  kp.n_blocks = s.Cout / BN;
+  kp.total_items = s.N * kp.tiles_x * kp.tiles_y * kp.n_blocks;
+  kp.kc_per_tap = s.Cin / kKChunk;
+  kp.ep = ep;
+  const int grid = kp.total_items < num_sms() ? kp.total_items : num_sms();
+  if (s.planes == 1) {
+    if (BN == 256) return launch_t<256, 1>(maps, kp, grid, stream);
+    if (BN == 128) return launch_t<128, 1>(maps, kp, grid, stream);
+    return launch_t<64, 1>(maps, kp, grid, stream);
+  }
+  if (BN == 256) return launch_t<256, 2>(maps, kp, grid, stream);
+  if (BN == 128) return launch_t<128, 2>(maps, kp, grid, stream);
+  return launch_t<64, 2>(maps, kp, grid, stream);
+}
+
+}  // namespace nsm

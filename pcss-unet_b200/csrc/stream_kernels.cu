@@ -1,0 +1,798 @@
+// HBM-streaming kernels (see stream_kernels.cuh).  All are bandwidth-bound: vectorised 16-byte accesses, one pass
+// over each tensor, per-channel parameters broadcast from shared memory, warp-shuffle reductions.
+#include <stdio.h>
+
+#include "nsm_common.cuh"
+#include "stream_kernels.cuh"
+
+namespace nsm {
+
+#define NSM_CHECK_LAUNCH(name)                                             \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) {                                              \
+      set_error("%s launch failed: %s", name, cudaGetErrorString(e__));    \
+      return 1;                                                            \
+    }                                                                      \
+  } while (0)
+
+static inline int grid_for(long long work, int block, int cap = 148 * 16) {
+  long long g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return int(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int flip_t,
+                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // destination index i -> (row, tap, col)
+    long long dst_rows_k = flip_t ? Cout : Cin;  // inner (K) extent per tap
+    int col = int(i % dst_rows_k);
+    long long t = i / dst_rows_k;
+    int tap = int(t % taps);
+    int row = int(t / taps);
+    int co, ci, stap;
+    if (!flip_t) {
+      co = row; ci = col; stap = tap;
+    } else {  // dgrad: rows = Cin, inner = Cout, taps mirrored
+      ci = row; co = col; stap = taps - 1 - tap;
+    }
+    const float v = w[((long long)co * Cin + ci) * taps + stap];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+int pack_conv_weight(const float* w, int Cout, int Cin, int ksize, int flip_transpose, void* hi, void* lo,
+                     cudaStream_t st) {
+  const int taps = ksize * ksize;
+  const long long total = (long long)Cout * Cin * taps;
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, Cout, Cin, taps, flip_transpose,
+                                                               (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  NSM_CHECK_LAUNCH("pack_conv_weight");
+  return 0;
+}
+
+__global__ void bn_fold_eval_kernel(const float* g, const float* b, const float* m, const float* v, int C, float eps,
+                                    float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float inv = 1.0f / sqrtf(v[c] + eps);
+    const float s = g[c] * inv;
+    scale[c] = s;
+    shift[c] = b[c] - m[c] * s;
+  }
+}
+int bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, int C, float eps,
+                 float* scale, float* shift, cudaStream_t st) {
+  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, C, eps, scale, shift);
+  NSM_CHECK_LAUNCH("bn_fold_eval");
+  return 0;
+}
+
+__global__ void copy_round_kernel(const float* src, float* dst, int n, int r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = r ? rbf(src[i]) : src[i];
+}
+int copy_round(const float* src, float* dst, int n, int round_bf16, cudaStream_t st) {
+  copy_round_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n, round_bf16);
+  NSM_CHECK_LAUNCH("copy_round");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion NCHW fp32 <-> NHWC bf16 planes (smem transpose, 32 channels x 32 pixels tiles)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_planes_kernel(const float* __restrict__ x, int C, long long HW, __nv_bfloat16* hi,
+                                      __nv_bfloat16* lo) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? x[((long long)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    if (c < C && p < HW) {
+      __nv_bfloat16 h, l;
+      split_bf16(tile[threadIdx.x][i], h, l);
+      const long long o = ((long long)n * HW + p) * C + c;
+      hi[o] = h;
+      if (lo) lo[o] = l;
+    }
+  }
+}
+int nchw_to_planes(const float* x, int N, int C, int H, int W, int planes, void* hi, void* lo, cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nchw_to_planes_kernel<<<grid, block, 0, st>>>(x, C, HW, (__nv_bfloat16*)hi, planes == 2 ? (__nv_bfloat16*)lo : nullptr);
+  NSM_CHECK_LAUNCH("nchw_to_planes");
+  return 0;
+}
+
+__global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                      int C, long long HW, float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && p < HW) {
+      const long long o = ((long long)n * HW + p) * C + c;
+      v = __bfloat162float(hi[o]);
+      if (lo) v += __bfloat162float(lo[o]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long p = p0 + threadIdx.x;
+    if (c < C && p < HW) y[((long long)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+int planes_to_nchw(const void* hi, const void* lo, int N, int C, int H, int W, int planes, float* y,
+                   cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  planes_to_nchw_kernel<<<grid, block, 0, st>>>((const __nv_bfloat16*)hi,
+                                                planes == 2 ? (const __nv_bfloat16*)lo : nullptr, C, HW, y);
+  NSM_CHECK_LAUNCH("planes_to_nchw");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear helpers (align_corners=True), mirroring ATen's area_pixel_compute_scale / source_index:
+//   scale = (in-1)/(out-1) (0 if out==1); src = scale*dst; i0 = floor(src) clamped; lambda = src - i0
+// ------------------------------------------------------------------------------------------------
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Lerp make_lerp(int dst, int in_size, int out_size) {
+  const float scale = out_size > 1 ? float(in_size - 1) / float(out_size - 1) : 0.f;
+  const float src = scale * float(dst);
+  int i0 = int(src);
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  Lerp l;
+  l.i0 = i0;
+  l.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  float lam = src - float(i0);
+  lam = fminf(fmaxf(lam, 0.f), 1.f);
+  l.w1 = lam;
+  l.w0 = 1.f - lam;
+  return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// head stage
+// ------------------------------------------------------------------------------------------------
+constexpr int HEAD_T = 16;  // output tile 16 x 16 pixels at (h, w) resolution, 256 threads
+
+struct HeadSmem {
+  float x16[16][HEAD_T + 2][HEAD_T + 3];  // un-shuffled (optionally standardised / even-fixed) input + halo
+  float w0[16 * 9 * 16];                  // [ci][tap][co]
+  float w1[16 * 64];                      // [ci][co]
+  float b0[16], s0[16], t0[16];
+  float b1[64], s1[64], t1[64];
+};
+
+__device__ __forceinline__ float head_fetch(const HeadParams& p, int n, int c, int Y, int X, int H, int W,
+                                            bool resize) {
+  // value of the (standardised, even-fixed) full-resolution input at (Y, X), channel c
+  const float* base = p.x + ((size_t)n * 4 + c) * p.Hin * p.Win;
+  const float mu = p.mean ? p.mean[c] : 0.f;
+  const float sd = p.mean ? (p.std[c] + 1e-8f) : 1.f;
+  if (!resize) {
+    float v = base[(size_t)Y * p.Win + X];
+    return p.mean ? (v - mu) / sd : v;
+  }
+  const Lerp ly = make_lerp(Y, p.Hin, H), lx = make_lerp(X, p.Win, W);
+  float v00 = base[(size_t)ly.i0 * p.Win + lx.i0], v01 = base[(size_t)ly.i0 * p.Win + lx.i1];
+  float v10 = base[(size_t)ly.i1 * p.Win + lx.i0], v11 = base[(size_t)ly.i1 * p.Win + lx.i1];
+  if (p.mean) {
+    v00 = (v00 - mu) / sd; v01 = (v01 - mu) / sd; v10 = (v10 - mu) / sd; v11 = (v11 - mu) / sd;
+  }
+  return ly.w0 * (lx.w0 * v00 + lx.w1 * v01) + ly.w1 * (lx.w0 * v10 + lx.w1 * v11);
+}
+
+__device__ __forceinline__ void store_planes64(const Planes& dst, size_t elem_off, const float* v, int planes) {
+  uint8_t* o0 = reinterpret_cast<uint8_t*>(dst.p[0]) + elem_off * 2;
+  uint8_t* o1 = planes == 2 ? reinterpret_cast<uint8_t*>(dst.p[1]) + elem_off * 2 : nullptr;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+      hw[e] = pack_bf16(a, b);
+      lw[e] = pack_bf16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
+    }
+    stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+    if (planes == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+  }
+}
+
+__global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ uint8_t head_smem_raw[];
+  HeadSmem& s = *reinterpret_cast<HeadSmem*>(head_smem_raw);
+  const int H = p.Hin - (p.Hin & 1), W = p.Win - (p.Win & 1);
+  const int h = H >> 1, w = W >> 1;
+  const bool resize = (p.Hin & 1) || (p.Win & 1);
+  const bool rb = p.planes == 1;
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * HEAD_T, x0 = blockIdx.x * HEAD_T;
+  const int tid = threadIdx.x;
+
+  // parameters -> smem ([ci][tap][co] and [ci][co] so that one LDS.128 feeds four FMAs)
+  for (int i = tid; i < 16 * 9 * 16; i += 256) {
+    const int co = i & 15, tap = (i >> 4) % 9, ci = i / 144;
+    s.w0[i] = p.w0[(co * 16 + ci) * 9 + tap];
+  }
+  for (int i = tid; i < 16 * 64; i += 256) {
+    const int co = i & 63, ci = i >> 6;
+    s.w1[i] = p.w1[co * 16 + ci];
+  }
+  if (tid < 16) { s.b0[tid] = p.b0[tid]; s.s0[tid] = p.s0[tid]; s.t0[tid] = p.t0[tid]; }
+  if (tid < 64) { s.b1[tid] = p.b1[tid]; s.s1[tid] = p.s1[tid]; s.t1[tid] = p.t1[tid]; }
+
+  // input tile: full-resolution rows 2*(y0-1) .. 2*(y0+17)-1, zero outside the (even-fixed) image
+  constexpr int FR = 2 * (HEAD_T + 2);
+  for (int i = tid; i < 4 * FR * FR; i += 256) {
+    const int fx = i % FR, fy = (i / FR) % FR, c = i / (FR * FR);
+    const int Y = 2 * (y0 - 1) + fy, X = 2 * (x0 - 1) + fx;
+    float v = 0.f;
+    if (Y >= 0 && Y < H && X >= 0 && X < W) {
+      v = head_fetch(p, n, c, Y, X, H, W, resize);
+      if (rb) v = rbf(v);  // autocast casts the conv input to bf16
+    }
+    s.x16[c * 4 + (fy & 1) * 2 + (fx & 1)][fy >> 1][fx >> 1] = v;  // pixel_unshuffle(2): ch = c*4 + dy*2 + dx
+  }
+  __syncthreads();
+
+  // thread -> pixel: a warp covers 2 rows x 16 columns so 2x2 pooling partners are lane^1 / lane^16
+  const int lane = tid & 31, wrp = tid >> 5;
+  const int ly = 2 * wrp + (lane >> 4), lx = lane & 15;
+  const int y = y0 + ly, x = x0 + lx;
+  const bool valid = y < h && x < w;
+  const size_t pix = ((size_t)n * h + y) * w + x;
+
+  if (p.x16.p[0] && valid) {  // optional tap for tests
+    float t[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) t[c] = s.x16[c][ly + 1][lx + 1];
+    uint8_t* o0 = reinterpret_cast<uint8_t*>(p.x16.p[0]) + pix * 16 * 2;
+    uint8_t* o1 = p.planes == 2 ? reinterpret_cast<uint8_t*>(p.x16.p[1]) + pix * 16 * 2 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = t[8 * j + 2 * e], b = t[8 * j + 2 * e + 1];
+        hw[e] = pack_bf16(a, b);
+        lw[e] = pack_bf16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
+      }
+      stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    }
+  }
+
+  // conv2.conv.0 : 3x3, 16 -> 16
+  float a[16];
+#pragma unroll
+  for (int co = 0; co < 16; ++co) a[co] = 0.f;
+#pragma unroll 1
+  for (int ci = 0; ci < 16; ++ci) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float xv = s.x16[ci][ly + tap / 3][lx + tap % 3];
+      const float4* wv = reinterpret_cast<const float4*>(&s.w0[(ci * 9 + tap) * 16]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 ww = wv[q];
+        a[4 * q] = fmaf(xv, ww.x, a[4 * q]); a[4 * q + 1] = fmaf(xv, ww.y, a[4 * q + 1]);
+        a[4 * q + 2] = fmaf(xv, ww.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(xv, ww.w, a[4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 16; ++co) {
+    float v = a[co] + s.b0[co];
+    if (rb) v = rbf(v);
+    v = fmaf(v, s.s0[co], s.t0[co]);
+    if (rb) v = rbf(v);
+    v = lrelu02(v);
+    if (rb) v = rbf(v);
+    a[co] = v;
+  }
+  // conv2.conv.4 : 1x1, 16 -> 64
+  float o[64];
+#pragma unroll
+  for (int co = 0; co < 64; ++co) o[co] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < 16; ++ci) {
+    const float av = a[ci];
+    const float4* wv = reinterpret_cast<const float4*>(&s.w1[ci * 64]);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 ww = wv[q];
+      o[4 * q] = fmaf(av, ww.x, o[4 * q]); o[4 * q + 1] = fmaf(av, ww.y, o[4 * q + 1]);
+      o[4 * q + 2] = fmaf(av, ww.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(av, ww.w, o[4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 64; ++co) {
+    float v = o[co] + s.b1[co];
+    if (rb) v = rbf(v);
+    v = fmaf(v, s.s1[co], s.t1[co]);
+    if (rb) v = rbf(v);
+    v = lrelu02(v);
+    if (rb) v = rbf(v);
+    o[co] = v;
+  }
+  if (valid) store_planes64(p.c2, pix * 64, o, p.planes);
+  // AvgPool2d(2): partners lane^1 (x) and lane^16 (y)
+  const int hp = h >> 1, wp = w >> 1;
+#pragma unroll
+  for (int co = 0; co < 64; ++co) {
+    float t = o[co] + __shfl_xor_sync(0xffffffffu, o[co], 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    t *= 0.25f;
+    o[co] = rb ? rbf(t) : t;
+  }
+  if (!(lane & 1) && !(lane & 16) && (y >> 1) < hp && (x >> 1) < wp)
+    store_planes64(p.p2, (((size_t)n * hp + (y >> 1)) * wp + (x >> 1)) * 64, o, p.planes);
+}
+
+int head_eval(const HeadParams& p, cudaStream_t st) {
+  const int H = p.Hin - (p.Hin & 1), W = p.Win - (p.Win & 1);
+  const int h = H / 2, w = W / 2;
+  if (h < 1 || w < 1 || p.N < 1) {
+    set_error("head_eval: bad shape N=%d Hin=%d Win=%d", p.N, p.Hin, p.Win);
+    return 1;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(head_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(HeadSmem));
+    if (e != cudaSuccess) {
+      set_error("head_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr = true;
+  }
+  dim3 grid((w + HEAD_T - 1) / HEAD_T, (h + HEAD_T - 1) / HEAD_T, p.N);
+  head_eval_kernel<<<grid, 256, sizeof(HeadSmem), st>>>(p);
+  NSM_CHECK_LAUNCH("head_eval");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tail stage
+// ------------------------------------------------------------------------------------------------
+struct TailSmem {
+  float w1[64 * 16];  // [ci][co]
+  float w10[16 * 4];  // [ci][co]
+  float b1[16], s1[16], t1[16], b10[4];
+};
+
+__global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ TailParams p) {
+  __shared__ TailSmem s;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 64 * 16; i += 256) {
+    const int co = i & 15, ci = i >> 4;
+    s.w1[i] = p.w1[co * 64 + ci];
+  }
+  if (tid < 64) {
+    const int co = tid & 3, ci = tid >> 2;
+    s.w10[tid] = p.w10[co * 16 + ci];
+  }
+  if (tid < 16) { s.b1[tid] = p.b1[tid]; s.s1[tid] = p.s1[tid]; s.t1[tid] = p.t1[tid]; }
+  if (tid < 4) s.b10[tid] = p.b10[tid];
+  __syncthreads();
+  const bool rb = p.planes == 1;
+  const long long npix = (long long)p.N * p.h * p.w;
+  const int W = 2 * p.w, H = 2 * p.h;
+  for (long long pix = blockIdx.x * 256LL + tid; pix < npix; pix += (long long)gridDim.x * 256) {
+    float a[16];
+#pragma unroll
+    for (int co = 0; co < 16; ++co) a[co] = 0.f;
+    const uint8_t* a0 = reinterpret_cast<const uint8_t*>(p.a.p[0]) + pix * 128;
+    const uint8_t* a1 = p.planes == 2 ? reinterpret_cast<const uint8_t*>(p.a.p[1]) + pix * 128 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 hv = ldg16(a0 + 16 * j);
+      uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+      float xin[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xin[2 * e] = bf16lo_to_f32(hw[e]);
+        xin[2 * e + 1] = bf16hi_to_f32(hw[e]);
+      }
+      if (a1) {
+        const uint4 lv = ldg16(a1 + 16 * j);
+        uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          xin[2 * e] += bf16lo_to_f32(lw[e]);
+          xin[2 * e + 1] += bf16hi_to_f32(lw[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4* wv = reinterpret_cast<const float4*>(&s.w1[(8 * j + e) * 16]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = wv[q];
+          a[4 * q] = fmaf(xin[e], ww.x, a[4 * q]); a[4 * q + 1] = fmaf(xin[e], ww.y, a[4 * q + 1]);
+          a[4 * q + 2] = fmaf(xin[e], ww.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(xin[e], ww.w, a[4 * q + 3]);
+        }
+      }
+    }
+    float c10[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) {
+      float v = a[ci] + s.b1[ci];
+      if (rb) v = rbf(v);
+      v = fmaf(v, s.s1[ci], s.t1[ci]);
+      if (rb) v = rbf(v);
+      v = lrelu02(v);
+      if (rb) v = rbf(v);
+      const float4 ww = *reinterpret_cast<const float4*>(&s.w10[ci * 4]);
+      c10[0] = fmaf(v, ww.x, c10[0]); c10[1] = fmaf(v, ww.y, c10[1]);
+      c10[2] = fmaf(v, ww.z, c10[2]); c10[3] = fmaf(v, ww.w, c10[3]);
+    }
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = c10[k] + s.b10[k];
+      if (rb) v = rbf(v);
+      v = 1.f / (1.f + expf(-v));
+      r[k] = rb ? rbf(v) : v;
+    }
+    // pixel_shuffle(2): channel k = dy*2 + dx -> (2y+dy, 2x+dx)
+    const int x = int(pix % p.w);
+    const long long t = pix / p.w;
+    const int y = int(t % p.h);
+    const long long n = t / p.h;
+    float* o = p.y + ((size_t)n * H + 2 * y) * W + 2 * x;
+    *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
+    *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
+  }
+}
+
+int tail_eval(const TailParams& p, cudaStream_t st) {
+  const long long npix = (long long)p.N * p.h * p.w;
+  tail_eval_kernel<<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
+  NSM_CHECK_LAUNCH("tail_eval");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// up-sample x2 (align_corners) then resize to (hd, wd) (align_corners); NHWC planes, 8 channels / thread
+// ------------------------------------------------------------------------------------------------
+struct UpParams {
+  const uint8_t* s0;
+  const uint8_t* s1;
+  uint8_t* d0;
+  uint8_t* d1;
+  int N, hs, ws, C, hd, wd, planes;
+};
+
+__device__ __forceinline__ void load8(const UpParams& p, size_t elem, float* v) {
+  const uint4 hv = ldg16(p.s0 + elem * 2);
+  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = bf16lo_to_f32(hw[e]);
+    v[2 * e + 1] = bf16hi_to_f32(hw[e]);
+  }
+  if (p.planes == 2) {
+    const uint4 lv = ldg16(p.s1 + elem * 2);
+    const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] += bf16lo_to_f32(lw[e]);
+      v[2 * e + 1] += bf16hi_to_f32(lw[e]);
+    }
+  }
+}
+
+// value of the x2 up-sampled tensor at intermediate pixel (Y, X), 8 channels
+__device__ __forceinline__ void up2_at(const UpParams& p, size_t nbase, int Y, int X, int cg, bool rb, float* out) {
+  const Lerp ly = make_lerp(Y, p.hs, 2 * p.hs), lx = make_lerp(X, p.ws, 2 * p.ws);
+  float v00[8], v01[8], v10[8], v11[8];
+  load8(p, ((nbase + (size_t)ly.i0 * p.ws + lx.i0) * p.C) + cg * 8, v00);
+  load8(p, ((nbase + (size_t)ly.i0 * p.ws + lx.i1) * p.C) + cg * 8, v01);
+  load8(p, ((nbase + (size_t)ly.i1 * p.ws + lx.i0) * p.C) + cg * 8, v10);
+  load8(p, ((nbase + (size_t)ly.i1 * p.ws + lx.i1) * p.C) + cg * 8, v11);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float v = ly.w0 * (lx.w0 * v00[e] + lx.w1 * v01[e]) + ly.w1 * (lx.w0 * v10[e] + lx.w1 * v11[e]);
+    out[e] = rb ? rbf(v) : v;
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p) {
+  const int cgs = p.C / 8;
+  const long long total = (long long)p.N * p.hd * p.wd * cgs;
+  const bool rb = p.planes == 1;
+  const bool same = (p.hd == 2 * p.hs) && (p.wd == 2 * p.ws);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i % cgs);
+    long long t = i / cgs;
+    const int x = int(t % p.wd);
+    t /= p.wd;
+    const int y = int(t % p.hd);
+    const int n = int(t / p.hd);
+    const size_t nbase = (size_t)n * p.hs * p.ws;
+    float r[8];
+    if (same) {
+      up2_at(p, nbase, y, x, cg, rb, r);  // second resize has scale 1 -> exact copy
+    } else {
+      const Lerp my = make_lerp(y, 2 * p.hs, p.hd), mx = make_lerp(x, 2 * p.ws, p.wd);
+      float u00[8], u01[8], u10[8], u11[8];
+      up2_at(p, nbase, my.i0, mx.i0, cg, rb, u00);
+      up2_at(p, nbase, my.i0, mx.i1, cg, rb, u01);
+      up2_at(p, nbase, my.i1, mx.i0, cg, rb, u10);
+      up2_at(p, nbase, my.i1, mx.i1, cg, rb, u11);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = my.w0 * (mx.w0 * u00[e] + mx.w1 * u01[e]) + my.w1 * (mx.w0 * u10[e] + mx.w1 * u11[e]);
+        r[e] = rb ? rbf(v) : v;
+      }
+    }
+    const size_t o = (((size_t)n * p.hd + y) * p.wd + x) * p.C + cg * 8;
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hw[e] = pack_bf16(r[2 * e], r[2 * e + 1]);
+      lw[e] = pack_bf16(r[2 * e] - bf16lo_to_f32(hw[e]), r[2 * e + 1] - bf16hi_to_f32(hw[e]));
+    }
+    stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+    if (p.planes == 2) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+  }
+}
+
+int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes& dst, int hd, int wd, int planes,
+                   cudaStream_t st) {
+  if (C % 8) {
+    set_error("upsample_match: C=%d not a multiple of 8", C);
+    return 1;
+  }
+  UpParams p;
+  p.s0 = (const uint8_t*)src.p[0]; p.s1 = (const uint8_t*)src.p[1];
+  p.d0 = (uint8_t*)dst.p[0]; p.d1 = (uint8_t*)dst.p[1];
+  p.N = N; p.hs = hs; p.ws = ws; p.C = C; p.hd = hd; p.wd = wd; p.planes = planes;
+  const long long total = (long long)N * hd * wd * (C / 8);
+  upsample_match_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, st>>>(p);
+  NSM_CHECK_LAUNCH("upsample_match");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// objective: L1 (+ perturbation L1) value and gradient in one pass
+// ------------------------------------------------------------------------------------------------
+struct LossParams {
+  const float* out;
+  const float* target;
+  const float* pert[4];
+  int n_pert;
+  long long numel;
+  float coef_l1, coef_pert;
+  float* grad;
+  double* acc;
+};
+__device__ __forceinline__ float sgn(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) l1_loss_kernel(const LossParams p) {
+  float s_l1 = 0.f, s_p = 0.f, bad = 0.f;
+  const long long n4 = p.numel >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 o = __ldg(reinterpret_cast<const float4*>(p.out) + i);
+    const float ov[4] = {o.x, o.y, o.z, o.w};
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.target) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p.target) + i);
+      const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = ov[e] - tv[e];
+        s_l1 += fabsf(d);
+        g[e] = p.coef_l1 * sgn(d);
+      }
+    }
+    for (int k = 0; k < p.n_pert; ++k) {
+      const float4 y = __ldg(reinterpret_cast<const float4*>(p.pert[k]) + i);
+      const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = ov[e] - yv[e];
+        s_p += fabsf(d);
+        g[e] += p.coef_pert * sgn(d);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bad += (ov[e] < 0.f || ov[e] > 1.f || ov[e] != ov[e]) ? 1.f : 0.f;
+    if (p.grad) reinterpret_cast<float4*>(p.grad)[i] = make_float4(g[0], g[1], g[2], g[3]);
+  }
+  // scalar tail
+  for (long long i = (n4 << 2) + blockIdx.x * 256LL + threadIdx.x; i < p.numel; i += (long long)gridDim.x * 256) {
+    const float o = p.out[i];
+    float g = 0.f;
+    if (p.target) {
+      const float d = o - p.target[i];
+      s_l1 += fabsf(d);
+      g = p.coef_l1 * sgn(d);
+    }
+    for (int k = 0; k < p.n_pert; ++k) {
+      const float d = o - p.pert[k][i];
+      s_p += fabsf(d);
+      g += p.coef_pert * sgn(d);
+    }
+    bad += (o < 0.f || o > 1.f || o != o) ? 1.f : 0.f;
+    if (p.grad) p.grad[i] = g;
+  }
+  __shared__ float red[3][8];
+  s_l1 = warp_sum(s_l1); s_p = warp_sum(s_p); bad = warp_sum(bad);
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wrp] = s_l1; red[1][wrp] = s_p; red[2][wrp] = bad; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += double(red[threadIdx.x][k]);
+    if (t != 0.0) atomicAdd(&p.acc[threadIdx.x], t);
+  }
+}
+
+int l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
+                    long long numel, float coef_l1, float coef_pert, float* grad, double* acc, cudaStream_t st) {
+  if (n_perturbed < 0 || n_perturbed > 4) {
+    set_error("l1_loss: at most 4 perturbed outputs per launch (got %d)", n_perturbed);
+    return 1;
+  }
+  LossParams p;
+  p.out = out; p.target = target; p.n_pert = n_perturbed; p.numel = numel;
+  for (int k = 0; k < 4; ++k) p.pert[k] = k < n_perturbed ? perturbed[k] : nullptr;
+  p.coef_l1 = coef_l1; p.coef_pert = coef_pert; p.grad = grad; p.acc = acc;
+  l1_loss_kernel<<<grid_for((numel + 3) / 4, 256, 148 * 8), 256, 0, st>>>(p);
+  NSM_CHECK_LAUNCH("l1_loss");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel sums over [S][C][HW] in fp64 (two-pass statistics like calculate_dataset_stats.py)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) channel_sums_kernel(const float* __restrict__ x, long long S, int C,
+                                                           long long HW, const double* __restrict__ means,
+                                                           double* __restrict__ sums, int chunks) {
+  // blockIdx.x = (plane index s*C + c) * chunks + chunk
+  const long long plane = blockIdx.x / chunks;
+  const int chunk = blockIdx.x % chunks;
+  const int c = int(plane % C);
+  const float* base = x + plane * HW;
+  const long long per = (HW + chunks - 1) / chunks;
+  const long long lo = chunk * per, hi = (lo + per < HW) ? lo + per : HW;
+  const double mu = means ? means[c] : 0.0;
+  double acc = 0.0;
+  const float* b = base + lo;
+  const long long n = hi - lo;
+  const long long nv = ((reinterpret_cast<uintptr_t>(b) & 15) == 0) ? (n >> 2) : 0;  // 16-byte vector part
+  for (long long k = threadIdx.x; k < nv; k += 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(b) + k);
+    if (means) {
+      const double a0 = double(v.x) - mu, a1 = double(v.y) - mu, a2 = double(v.z) - mu, a3 = double(v.w) - mu;
+      acc += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    } else {
+      acc += (double(v.x) + double(v.y)) + (double(v.z) + double(v.w));
+    }
+  }
+  for (long long j = (nv << 2) + threadIdx.x; j < n; j += 256) {  // ragged end / unaligned planes
+    const double v = double(b[j]) - mu;
+    acc += means ? v * v : v;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(&sums[c], t);
+  }
+}
+
+int channel_sums(const float* x, long long S, int C, long long HW, const double* means, double* sums,
+                 cudaStream_t st) {
+  const long long planes = S * C;
+  int chunks = int((148LL * 8 + planes - 1) / planes);
+  if (chunks < 1) chunks = 1;
+  const long long max_chunks = (HW + 4095) / 4096;
+  if (chunks > max_chunks) chunks = int(max_chunks);
+  if (planes * chunks > 0x7fffffffLL) {
+    set_error("channel_sums: too many blocks");
+    return 1;
+  }
+  channel_sums_kernel<<<(unsigned)(planes * chunks), 256, 0, st>>>(x, S, C, HW, means, sums, chunks);
+  NSM_CHECK_LAUNCH("channel_sums");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) standardize_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                          long long planes, int C, long long HW,
+                                                          const float* __restrict__ mean,
+                                                          const float* __restrict__ std) {
+  const long long total = planes * HW;
+  const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  if (vec) {
+    const long long n4 = total >> 2;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+      const int c = int(((i << 2) / HW) % C);
+      const float mu = mean[c], sd = std[c] + 1e-8f;
+      float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      v.x = (v.x - mu) / sd; v.y = (v.y - mu) / sd; v.z = (v.z - mu) / sd; v.w = (v.w - mu) / sd;
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+  } else {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+      const int c = int((i / HW) % C);
+      y[i] = (x[i] - mean[c]) / (std[c] + 1e-8f);
+    }
+  }
+}
+int standardize(const float* x, float* y, long long S, int C, long long HW, const float* mean, const float* std,
+                cudaStream_t st) {
+  standardize_kernel<<<grid_for(S * C * HW / 4 + 1, 256), 256, 0, st>>>(x, y, S * C, C, HW, mean, std);
+  NSM_CHECK_LAUNCH("standardize");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) perturb_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                                      float* __restrict__ out, int count, long long per_copy, int C,
+                                                      long long HW, const float* __restrict__ stds,
+                                                      float std_factor) {
+  const long long total = per_copy * count;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long j = i % per_copy;              // offset inside one [B][C][HW] copy
+    const long long copy = i / per_copy;
+    const long long hw = j % HW;
+    const int c = int((j / HW) % C);
+    const long long b = j / (HW * C);
+    const long long B = per_copy / (HW * C);
+    // noise is laid out [count][C][B][HW]: each (copy, channel) block is one contiguous randn_like draw
+    const float nz = noise[((copy * C + c) * B + b) * HW + hw];
+    out[i] = x[j] + (nz * stds[c]) * std_factor;   // pert_loss.py:54-55 evaluation order
+  }
+}
+int perturb(const float* x, const float* noise, float* out, int count, long long B, int C, long long HW,
+            const float* stds, float std_factor, cudaStream_t st) {
+  const long long per = B * C * HW;
+  perturb_kernel<<<grid_for(per * count, 256), 256, 0, st>>>(x, noise, out, count, per, C, HW, stds, std_factor);
+  NSM_CHECK_LAUNCH("perturb");
+  return 0;
+}
+
+}  // namespace nsm

@@ -1,0 +1,295 @@
+"""ctypes binding of libnsm_b200.so (C ABI declared in include/nsm_b200.h).
+
+PyTorch is used only for device memory, streams and (in the trainer) torch.distributed; all arithmetic of the hot
+path runs in the hand-written sm_100a kernels behind this boundary.  There is NO fallback: if the library is missing
+or the device is not a B200 the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnsm_b200.so")
+
+MODE_BF16 = 0
+MODE_FP32 = 1
+MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32}
+NUM_TENSORS = 98
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NsmError(RuntimeError):
+    pass
+
+
+class ConvArgs(Structure):
+    _fields_ = [
+        ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int), ("ksize", c_int),
+        ("mode", c_int),
+        ("inp", c_void_p * 2), ("weight", c_void_p * 2),
+        ("bias", c_void_p), ("bn_scale", c_void_p), ("bn_shift", c_void_p),
+        ("lrelu", c_int),
+        ("out", c_void_p * 2), ("residual", c_void_p * 2), ("pool", c_void_p * 2),
+        ("out_f32", c_void_p),
+    ]
+
+
+def _declare(lib):
+    lib.nsm_last_error.restype = c_char_p
+    lib.nsm_version.restype = c_int
+    lib.nsm_check_device.restype = c_int
+    lib.nsm_unet_packed_bytes.restype = c_size_t
+    lib.nsm_unet_packed_bytes.argtypes = [c_int]
+    lib.nsm_unet_pack.argtypes = [POINTER(c_void_p), c_int, c_void_p, c_void_p]
+    lib.nsm_unet_workspace_bytes.restype = c_size_t
+    lib.nsm_unet_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    infer_args = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                  c_size_t, c_void_p]
+    lib.nsm_unet_infer.argtypes = infer_args
+    lib.nsm_unet_infer_host.argtypes = infer_args
+    lib.nsm_unet_tap.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_char_p, c_void_p, POINTER(c_int),
+                                 POINTER(c_int), POINTER(c_int), c_void_p]
+    lib.nsm_nchw_to_planes.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.nsm_planes_to_nchw.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.nsm_pack_conv_weight.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.nsm_conv_fwd.argtypes = [POINTER(ConvArgs), c_void_p]
+    lib.nsm_upsample_match.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int, POINTER(c_void_p), c_int,
+                                       c_int, c_int, c_void_p]
+    lib.nsm_l1_loss_fwd_bwd.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_longlong, c_float, c_float,
+                                        c_void_p, c_void_p, c_void_p]
+    lib.nsm_channel_sums.argtypes = [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p]
+    lib.nsm_standardize.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p]
+    lib.nsm_perturb.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_longlong, c_void_p,
+                                c_float, c_void_p]
+    for name in ("nsm_unet_pack", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
+                 "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match",
+                 "nsm_l1_loss_fwd_bwd", "nsm_channel_sums", "nsm_standardize", "nsm_perturb"):
+        getattr(lib, name).restype = c_int
+
+
+EXPORTS = [
+    "nsm_last_error", "nsm_version", "nsm_check_device", "nsm_unet_packed_bytes", "nsm_unet_pack",
+    "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
+    "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
+    "nsm_channel_sums", "nsm_standardize", "nsm_perturb",
+]
+
+
+def lib():
+    """Load the shared library once.  Raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NsmError(f"{LIB_PATH} is missing: build it with `python pcss-unet_b200/build.py` "
+                                   "(there is no CPU / PyTorch fallback for the hot path)")
+                l = ctypes.CDLL(LIB_PATH)
+                _declare(l)
+                _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().nsm_last_error().decode(errors="replace")
+        raise NsmError(f"{what or 'nsm call'} failed (code {rc}): {msg}")
+
+
+def require_device(t: torch.Tensor = None):
+    if not torch.cuda.is_available():
+        raise NsmError("CUDA device required: the B200 hot path has no CPU fallback "
+                       "(use the reference classes on CPU)")
+    if t is not None and not t.is_cuda:
+        raise NsmError("tensor must live on the CUDA device")
+    check(lib().nsm_check_device(), "nsm_check_device")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def mode_planes(mode: int) -> int:
+    return 2 if mode == MODE_FP32 else 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# thin typed wrappers
+# ---------------------------------------------------------------------------------------------------------------
+
+def unet_pack(tensors, mode: int) -> torch.Tensor:
+    """tensors: the 98 fp32 CUDA tensors in the order of include/nsm_b200.h -> packed uint8 blob."""
+    assert len(tensors) == NUM_TENSORS
+    dev = tensors[0].device
+    keep = [t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in tensors]
+    arr = (c_void_p * NUM_TENSORS)(*[t.data_ptr() for t in keep])
+    blob = torch.empty(lib().nsm_unet_packed_bytes(mode), dtype=torch.uint8, device=dev)
+    check(lib().nsm_unet_pack(arr, mode, blob.data_ptr(), stream_ptr()), "nsm_unet_pack")
+    return blob
+
+
+def unet_workspace(B, H, W, mode, device) -> torch.Tensor:
+    n = lib().nsm_unet_workspace_bytes(B, H, W, mode)
+    if n == 0:
+        raise NsmError(f"input {B}x4x{H}x{W} not supported (need H, W >= 16)")
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def unet_infer(blob, mode, x, y, ws, mean=None, std=None):
+    B, C, H, W = x.shape
+    assert C == 4 and x.dtype == torch.float32 and x.is_contiguous()
+    check(lib().nsm_unet_infer(blob.data_ptr(), mode, x.data_ptr(), B, H, W, ptr(mean), ptr(std), y.data_ptr(),
+                               ws.data_ptr(), ws.numel(), stream_ptr()), "nsm_unet_infer")
+
+
+def unet_infer_host(blob, mode, x_host, y_host, ws, mean=None, std=None):
+    B, C, H, W = x_host.shape
+    assert C == 4 and x_host.dtype == torch.float32 and x_host.is_contiguous() and not x_host.is_cuda
+    check(lib().nsm_unet_infer_host(blob.data_ptr(), mode, x_host.data_ptr(), B, H, W, ptr(mean), ptr(std),
+                                    y_host.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()),
+          "nsm_unet_infer_host")
+
+
+def unet_tap(ws, B, H, W, mode, name) -> torch.Tensor:
+    C, h, w = c_int(), c_int(), c_int()
+    check(lib().nsm_unet_tap(ws.data_ptr(), B, H, W, mode, name.encode(), None, byref(C), byref(h), byref(w),
+                             stream_ptr()), "nsm_unet_tap")
+    out = torch.empty(B, C.value, h.value, w.value, dtype=torch.float32, device=ws.device)
+    check(lib().nsm_unet_tap(ws.data_ptr(), B, H, W, mode, name.encode(), out.data_ptr(), None, None, None,
+                             stream_ptr()), "nsm_unet_tap")
+    return out
+
+
+class PlaneTensor:
+    """NHWC bf16 planes of one activation (plane 1 only in fp32 mode)."""
+
+    def __init__(self, N, C, H, W, mode, device):
+        self.shape = (N, C, H, W)
+        self.mode = mode
+        self.p0 = torch.empty(N, H, W, C, dtype=torch.bfloat16, device=device)
+        self.p1 = torch.empty(N, H, W, C, dtype=torch.bfloat16, device=device) if mode == MODE_FP32 else None
+
+    @classmethod
+    def from_nchw(cls, x, mode):
+        N, C, H, W = x.shape
+        x = x.to(torch.float32).contiguous()
+        t = cls(N, C, H, W, mode, x.device)
+        check(lib().nsm_nchw_to_planes(x.data_ptr(), N, C, H, W, mode, ptr(t.p0), ptr(t.p1), stream_ptr()),
+              "nsm_nchw_to_planes")
+        return t
+
+    def to_nchw(self):
+        N, C, H, W = self.shape
+        y = torch.empty(N, C, H, W, dtype=torch.float32, device=self.p0.device)
+        check(lib().nsm_planes_to_nchw(ptr(self.p0), ptr(self.p1), N, C, H, W, self.mode, y.data_ptr(),
+                                       stream_ptr()), "nsm_planes_to_nchw")
+        return y
+
+    def pair(self):
+        return (c_void_p * 2)(ptr(self.p0), ptr(self.p1))
+
+
+def pack_conv_weight(w, mode, dgrad=False):
+    """nn.Conv2d weight [Cout,Cin,k,k] fp32 -> (plane0, plane1|None) bf16 [rows][k*k][inner]."""
+    Cout, Cin, k, _ = w.shape
+    w = w.detach().to(torch.float32).contiguous()
+    rows, inner = (Cin, Cout) if dgrad else (Cout, Cin)
+    p0 = torch.empty(rows, k * k, inner, dtype=torch.bfloat16, device=w.device)
+    p1 = torch.empty_like(p0) if mode == MODE_FP32 else None
+    check(lib().nsm_pack_conv_weight(w.data_ptr(), Cout, Cin, k, int(dgrad), mode, ptr(p0), ptr(p1), stream_ptr()),
+          "nsm_pack_conv_weight")
+    return p0, p1
+
+
+def conv_fwd(x: PlaneTensor, wp, ksize, Cout, mode, bias=None, bn_scale=None, bn_shift=None, lrelu=False,
+             residual: PlaneTensor = None, pool=False, want_f32=False, want_out=True):
+    """One fused conv stage on the tensor cores.  Returns (out PlaneTensor|None, pooled|None, raw fp32 NHWC|None)."""
+    N, Cin, H, W = x.shape
+    dev = x.p0.device
+    out = PlaneTensor(N, Cout, H, W, mode, dev) if want_out else None
+    pl = PlaneTensor(N, Cout, H // 2, W // 2, mode, dev) if pool else None
+    raw = torch.empty(N, H, W, Cout, dtype=torch.float32, device=dev) if want_f32 else None
+    a = ConvArgs()
+    a.N, a.H, a.W, a.Cin, a.Cout, a.ksize, a.mode = N, H, W, Cin, Cout, ksize, mode
+    a.inp = x.pair()
+    a.weight = (c_void_p * 2)(ptr(wp[0]), ptr(wp[1]))
+    a.bias, a.bn_scale, a.bn_shift = ptr(bias) or None, ptr(bn_scale) or None, ptr(bn_shift) or None
+    a.lrelu = int(lrelu)
+    a.out = out.pair() if out is not None else (c_void_p * 2)(None, None)
+    a.residual = residual.pair() if residual is not None else (c_void_p * 2)(None, None)
+    a.pool = pl.pair() if pl is not None else (c_void_p * 2)(None, None)
+    a.out_f32 = ptr(raw) or None
+    check(lib().nsm_conv_fwd(byref(a), stream_ptr()), "nsm_conv_fwd")
+    return out, pl, raw
+
+
+def upsample_match(x: PlaneTensor, hd, wd):
+    N, C, hs, ws = x.shape
+    out = PlaneTensor(N, C, hd, wd, x.mode, x.p0.device)
+    check(lib().nsm_upsample_match(x.pair(), N, hs, ws, C, out.pair(), hd, wd, x.mode, stream_ptr()),
+          "nsm_upsample_match")
+    return out
+
+
+def l1_loss_fwd_bwd(out, target=None, perturbed=(), coef_l1=0.0, coef_pert=0.0, want_grad=True):
+    """Returns (acc[3] float64 device tensor: sum|o-t|, sum_i sum|o-y_i|, #out-of-range; grad or None)."""
+    out = out.contiguous()
+    assert out.dtype == torch.float32
+    n = out.numel()
+    acc = torch.zeros(3, dtype=torch.float64, device=out.device)
+    grad = torch.empty_like(out) if want_grad else None
+    pert = [p.contiguous() for p in perturbed]
+    arr = (c_void_p * max(1, len(pert)))(*[p.data_ptr() for p in pert])
+    tgt = None if target is None else target.to(torch.float32).contiguous()
+    check(lib().nsm_l1_loss_fwd_bwd(out.data_ptr(), ptr(tgt), arr, len(pert), n, coef_l1, coef_pert, ptr(grad),
+                                    acc.data_ptr(), stream_ptr()), "nsm_l1_loss_fwd_bwd")
+    return acc, grad
+
+
+def channel_sums(x, means=None):
+    """x: [S,C,...] fp32 CUDA.  Returns float64 [C]: sum x (means None) or sum (x-mean_c)^2."""
+    x = x.contiguous()
+    S, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (S * C)
+    sums = torch.zeros(C, dtype=torch.float64, device=x.device)
+    m = None if means is None else means.to(device=x.device, dtype=torch.float64).contiguous()
+    check(lib().nsm_channel_sums(x.data_ptr(), S, C, HW, ptr(m), sums.data_ptr(), stream_ptr()),
+          "nsm_channel_sums")
+    return sums
+
+
+def standardize(x, mean, std):
+    x = x.contiguous()
+    C = mean.numel()
+    if x.dim() == 3:
+        S, HW = 1, x.shape[1] * x.shape[2]
+    else:
+        S, HW = x.shape[0], x.numel() // (x.shape[0] * C)
+    y = torch.empty_like(x)
+    check(lib().nsm_standardize(x.data_ptr(), y.data_ptr(), S, C, HW, mean.data_ptr(), std.data_ptr(),
+                                stream_ptr()), "nsm_standardize")
+    return y
+
+
+def perturb(x, noise, stds, std_factor):
+    """x [B,C,H,W], noise [count,C,B,H,W] (one block per reference randn_like draw), stds [C] -> [count,B,C,H,W]."""
+    x = x.contiguous()
+    noise = noise.contiguous()
+    count = noise.shape[0]
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    out = torch.empty((count,) + tuple(x.shape), dtype=torch.float32, device=x.device)
+    check(lib().nsm_perturb(x.data_ptr(), noise.data_ptr(), out.data_ptr(), count, B, C, HW, stds.data_ptr(),
+                            float(std_factor), stream_ptr()), "nsm_perturb")
+    return out

@@ -1,0 +1,93 @@
+"""Objective, statistics and perturbation kernels against the oracle and the reference golden vectors (GPU)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nsm():
+    import nsm as _nsm
+    _nsm.require_device()
+    return _nsm
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def test_custom_loss_matches_reference_golden(nsm, golden):
+    from customLoss import CustomLoss
+    o = torch.from_numpy(golden["loss_o"]).cuda().requires_grad_(True)
+    t = torch.from_numpy(golden["loss_t"]).cuda()
+    crit = CustomLoss("cuda", alpha=0.9)
+    loss = crit(o, t, None)
+    loss.backward()
+    assert abs(loss.item() - float(golden["loss_val"])) <= 1e-6
+    assert torch.equal(o.grad.cpu(), torch.from_numpy(golden["loss_grad"]))     # alpha*sign/N is exact
+    l1 = crit.l1(o, t)
+    assert abs(((loss - crit.alpha * l1) / (1 - crit.alpha)).item()) < 1e-5     # main.py:277 back-derivation of vgg
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 7, 9), (3, 1, 64, 96), (2, 1, 1080, 1920)])
+def test_l1_value_and_sign_gradient(nsm, shape):
+    o = torch.rand(*shape, generator=gen(1))
+    t = torch.rand(*shape, generator=gen(2))
+    o.view(-1)[::5] = t.view(-1)[::5]                       # exact ties: sign(0) = 0
+    acc, grad = nsm.l1_loss_fwd_bwd(o.cuda(), t.cuda(), (), coef_l1=0.9 / o.numel())
+    assert abs(acc[0].item() / o.numel() - oracle.l1_loss(o, t).item()) <= 1e-6
+    assert torch.equal(grad.cpu(), oracle.custom_loss_grad(o, t, 0.9))
+    assert acc[2].item() == 0
+
+
+def test_range_assert(nsm):
+    from customLoss import CustomLoss
+    o = torch.rand(1, 1, 16, 16, device="cuda") * 1.5
+    with pytest.raises(AssertionError):
+        CustomLoss("cuda")(o, torch.rand(1, 1, 16, 16, device="cuda"), None)
+
+
+def test_perturbation_loss_value_and_grad(nsm):
+    out = torch.rand(2, 1, 32, 48, generator=gen(3))
+    ys = [torch.rand(2, 1, 32, 48, generator=gen(4 + i)) for i in range(3)]
+    ys[1].view(-1)[::7] = out.view(-1)[::7]
+    o = out.cuda().requires_grad_(True)
+    from pert_loss import _FusedPerturbL1
+    total, _, pert, _ = _FusedPerturbL1.apply(o, None, 0.0, 1.0, *[y.cuda() for y in ys])
+    total.backward()
+    ref = sum(oracle.l1_loss(out, y) for y in ys) / 3
+    assert abs(total.item() - ref.item()) <= 1e-6 and abs(pert.item() - ref.item()) <= 1e-6
+    assert torch.allclose(o.grad.cpu(), oracle.perturbation_loss_grad(out, ys), atol=1e-12)
+
+
+def test_perturb_inputs_match_reference_order(nsm):
+    from pert_loss import PerturbationLoss
+    x = torch.randn(2, 4, 24, 40, generator=gen(8)) * torch.tensor([1.0, 2.0, 3.0, 0.5]).view(1, 4, 1, 1)
+    noises = [[torch.randn(2, 1, 24, 40, generator=gen(100 + 4 * i + c)) for c in range(4)] for i in range(3)]
+    ref = oracle.perturb_inputs(x, 3, noises=noises)
+    nz = torch.stack([torch.stack(n) for n in noises]).cuda()             # [count, C, B, 1, H, W]
+    got = PerturbationLoss(3).perturb_input(x.cuda(), noise=nz)
+    for g, r in zip(got, ref):
+        assert (g.cpu() - r).abs().max().item() <= 2e-7 * 4
+
+
+def test_channel_stats_match_reference_golden(nsm, golden, tmp_path):
+    rng = np.random.default_rng(0)
+    mu = np.array([0.1, -1.0, 5.0, 0.0], dtype=np.float32).reshape(1, 4, 1, 1)
+    sg = np.array([1.0, 2.0, 3.0, 0.5], dtype=np.float32).reshape(1, 4, 1, 1)
+    data = (rng.standard_normal((6, 4, 64, 96), dtype=np.float32) * sg + mu).astype(np.float32)
+    np.save(tmp_path / "train_inputs.npy", data)
+    from calculate_dataset_stats import calculate_dataset_stats
+    st = calculate_dataset_stats(str(tmp_path))
+    assert st is not None
+    assert np.allclose(st["means"], golden["stats_means"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(st["stds"], golden["stats_stds"], rtol=1e-6)
+    loaded = np.load(tmp_path / "train_stats.npy", allow_pickle=True).item()   # same file format as the reference
+    assert set(loaded) == {"means", "stds"} and len(loaded["means"]) == 4
+    # ragged / unaligned plane sizes
+    x = torch.randn(3, 4, 13, 7, generator=gen(5))
+    s = nsm.channel_sums(x.cuda()).cpu()
+    assert torch.allclose(s, x.double().sum(dim=(0, 2, 3)), rtol=1e-12, atol=1e-9)

@@ -1,0 +1,142 @@
+"""Per-fused-stage parity of the sm_100a kernels against the CPU oracle (SURVEY 8c tolerance protocol).
+
+Every test calls the CUDA path through the C ABI (nsm.py -> libnsm_b200.so) and checks it against oracle/ on the same
+seeded inputs.  Tolerances:
+  fp32 mode : |err| <= 3e-5 * max(1, max|ref|)   (split-bf16 products, fp32 accumulate; north-star 1e-4 on [0,1])
+  bf16 mode : same rounding points as the autocast oracle -> isolated one-ulp flips only:
+              |err| <= 2^-6 * max(|ref|, 0.1 max|ref|) element-wise and < 3 % of elements differ at all
+"""
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nsm():
+    import nsm as _nsm
+    _nsm.require_device()
+    return _nsm
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def describe(err, ref):
+    """Error-structure dump that makes a descriptor / swizzle / indexing bug recognisable from one log."""
+    N, C, H, W = err.shape
+    e = err.abs()
+    lines = [f"max|err|={e.max():.4g} max|ref|={ref.abs().max():.4g} mean|err|={e.mean():.4g}"]
+    lines.append("by channel%16: " + " ".join(f"{e[:, c::16].max():.2g}" for c in range(min(16, C))))
+    lines.append("by channel//32: " + " ".join(f"{e[:, c:c + 32].max():.2g}" for c in range(0, min(C, 256), 32)))
+    lines.append("by y%8: " + " ".join(f"{e[:, :, y::8].max():.2g}" for y in range(min(8, H))))
+    lines.append("by x%16: " + " ".join(f"{e[:, :, :, x::16].max():.2g}" for x in range(min(16, W))))
+    idx = torch.nonzero(e == e.max())[0].tolist()
+    lines.append(f"argmax at (n,c,y,x)={idx}")
+    return "\n".join(lines)
+
+
+def check_close(got, ref, mode_name, what):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = got - ref
+    if mode_name == "fp32":
+        tol = 3e-5 * max(1.0, ref.abs().max().item())
+        assert err.abs().max().item() <= tol, f"{what} [fp32]\n" + describe(err, ref)
+    else:
+        bound = (2.0 ** -6) * torch.maximum(ref.abs(), 0.1 * ref.abs().max())
+        bad = (err.abs() > bound)
+        frac = (err != 0).float().mean().item()
+        assert not bad.any() and frac < 0.03, f"{what} [bf16] differing={frac:.4f}\n" + describe(err, ref)
+
+
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32"])
+def test_layout_roundtrip(nsm, mode_name):
+    mode = nsm.MODES[mode_name]
+    x = torch.randn(2, 72, 9, 21, generator=gen(0))
+    t = nsm.PlaneTensor.from_nchw(x.cuda(), mode)
+    y = t.to_nchw().cpu()
+    if mode_name == "bf16":
+        assert torch.equal(y, bf(x))
+    else:
+        assert (y - x).abs().max() <= 2.0 ** -17 * x.abs().max()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, residual, pool
+    (1, 8, 16, 64, 64, 1, False, False),      # exactly one tile, one k-block
+    (1, 8, 16, 64, 64, 3, False, False),      # 9 taps, zero padding on all sides
+    (2, 13, 21, 128, 128, 3, False, False),   # ragged tiles, 2 k-chunks per tap
+    (1, 16, 32, 64, 128, 1, False, True),     # fused AvgPool2d(2)
+    (1, 9, 15, 128, 64, 1, True, False),      # residual add, odd sizes
+    (1, 17, 30, 512, 512, 3, False, False),   # conv7-like, multi n-block, long K loop
+    (1, 10, 12, 1024, 512, 1, True, False),   # conv6 1x1-like
+    (1, 11, 14, 128, 512, 1, False, True),    # conv4 1x1 + pool with odd sizes (floor)
+]
+
+
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_stage(nsm, mode_name, case):
+    N, H, W, Cin, Cout, k, use_res, use_pool = case
+    mode = nsm.MODES[mode_name]
+    g = gen(hash(case) % 1000)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    gamma = torch.empty(Cout).uniform_(0.5, 1.5, generator=g)
+    beta = torch.empty(Cout).uniform_(-0.5, 0.5, generator=g)
+    rm = torch.randn(Cout, generator=g) * 0.2
+    rv = torch.empty(Cout).uniform_(0.5, 1.5, generator=g)
+    res = torch.randn(N, Cout, H, W, generator=g) if use_res else None
+    if mode_name == "bf16":  # what autocast would feed: bf16-representable activations
+        x = bf(x)
+        res = bf(res) if res is not None else None
+    res_o = res.to(torch.bfloat16) if (use_res and mode_name == "bf16") else res
+    ref, ref_pool = oracle.conv_stage_eval(x, w, b, rm, rv, gamma, beta, residual=res_o, pool=use_pool,
+                                           bf16=(mode_name == "bf16"))
+    scale = gamma / torch.sqrt(rv + 1e-5)
+    shift = beta - rm * scale
+    bias = bf(b) if mode_name == "bf16" else b
+    xt = nsm.PlaneTensor.from_nchw(x.cuda(), mode)
+    rt = nsm.PlaneTensor.from_nchw(res.cuda(), mode) if use_res else None
+    wp = nsm.pack_conv_weight(w.cuda(), mode)
+    out, pl, raw = nsm.conv_fwd(xt, wp, k, Cout, mode, bias=bias.cuda(), bn_scale=scale.cuda(),
+                                bn_shift=shift.cuda(), lrelu=True, residual=rt, pool=use_pool, want_f32=True)
+    torch.cuda.synchronize()
+    # raw accumulators (conv + bias, fp32) first: isolates the GEMM from the epilogue
+    if mode_name == "bf16":
+        ref_raw = torch.nn.functional.conv2d(x, bf(w), bias, padding=k // 2)
+    else:
+        ref_raw = torch.nn.functional.conv2d(x, w, b, padding=k // 2)
+    got_raw = raw.permute(0, 3, 1, 2).cpu()
+    tol = (2e-5 if mode_name == "fp32" else 1e-5) * max(1.0, ref_raw.abs().max().item())
+    assert (got_raw - ref_raw).abs().max().item() <= tol, "raw GEMM\n" + describe(got_raw - ref_raw, ref_raw)
+    check_close(out.to_nchw(), ref, mode_name, "conv stage output")
+    if use_pool:
+        check_close(pl.to_nchw(), ref_pool, mode_name, "pooled output")
+
+
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("shape", [(1, 64, 8, 12, 16, 24), (2, 128, 67, 120, 135, 240), (1, 64, 20, 28, 20, 28),
+                                   (1, 512, 5, 7, 10, 14), (1, 64, 3, 2, 7, 5)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_upsample_match(nsm, mode_name, shape):
+    N, C, hs, ws, hd, wd = shape
+    mode = nsm.MODES[mode_name]
+    x = torch.randn(N, C, hs, ws, generator=gen(5))
+    if mode_name == "bf16":
+        x = bf(x)
+        ref = oracle.upsample_and_match(x.to(torch.bfloat16), (hd, wd)).float()
+    else:
+        ref = oracle.upsample_and_match(x, (hd, wd))
+    got = nsm.upsample_match(nsm.PlaneTensor.from_nchw(x.cuda(), mode), hd, wd).to_nchw()
+    check_close(got, ref, mode_name, f"upsample {shape}")

@@ -1,0 +1,135 @@
+"""Whole-network eval-mode parity (Unet.forward under model.eval()) through the drop-in module and the C ABI.
+
+Checked against (a) the committed golden vectors produced by the unmodified reference classes and (b) the CPU oracle
+on the same seeded inputs, including every intermediate tensor (nsm_unet_tap), the odd-size / odd-level paths, the
+1080p frame of BASELINE config 1, fused standardisation and the host-buffer entry point.
+Tolerances (BASELINE.json north_star): output max-abs <= 1e-4 in fp32 mode vs the fp32 reference, <= 1e-2 in bf16
+mode vs the bf16-autocast reference, on values in [0,1].
+"""
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+@pytest.fixture(scope="module")
+def nsm():
+    import nsm as _nsm
+    _nsm.require_device()
+    return _nsm
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def make_net(P, precision):
+    from Unetmodel import Unet
+    net = Unet(precision=precision)
+    net.load_state_dict(P, strict=True)
+    return net.cuda().eval()
+
+
+def calibrated(shape, seed=1):
+    P = oracle.init_params(42)
+    x = torch.randn(*shape, generator=gen(seed))
+    oracle.calibrate_bn(P, x, generator=gen(2))
+    return P, x
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["eval_a", "eval_b", "eval_c"])
+def test_against_reference_golden(nsm, golden, precision, tag):
+    shape = tuple(int(v) for v in golden[f"{tag}_shape"])
+    P, x = calibrated(shape)
+    net = make_net(P, precision)
+    with torch.inference_mode():
+        y = net(x.cuda())
+    ref = torch.from_numpy(golden[f"{tag}_out" if precision == "fp32" else f"{tag}_out_bf16"])
+    assert y.shape == ref.shape
+    assert y.dtype == (torch.float32 if precision == "fp32" else torch.bfloat16)
+    err = (y.float().cpu() - ref).abs().max().item()
+    assert err <= TOL[precision], (tag, precision, err)
+    assert 0.0 <= float(y.min()) and float(y.max()) <= 1.0
+
+
+TAPS = [("c2", "c2"), ("p2", "p2"), ("t3", "conv3.a0"), ("c3", "c3"), ("p3", "p3"), ("t4", "conv4.a0"),
+        ("c4", "c4"), ("p4", "p4"), ("t5", "conv5.a0"), ("c5", "c5"), ("u6", "u6"), ("t6", "conv6.a0"),
+        ("m6", "m6"), ("u7", "u7"), ("t7", "conv7.a0"), ("m7", "m7"), ("u8", "u8"), ("t8", "conv8.a0"),
+        ("m8", "m8"), ("u9", "u9"), ("t9", "conv9.a0")]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 4, 32, 48), (1, 4, 41, 57), (1, 4, 80, 112)], ids=lambda s: "x".join(map(str, s)))
+def test_every_intermediate_against_oracle(nsm, precision, shape):
+    P, x = calibrated(shape)
+    net = make_net(P, precision)
+    taps = {}
+    with torch.no_grad():
+        ref = oracle.unet_forward(x, P, training=False, bf16=(precision == "bf16"), taps=taps)
+        y = net(x.cuda())
+    ws, B, H, W, mode = net.last_workspace
+    report = []
+    worst = 0.0
+    for mine, theirs in TAPS:
+        got = nsm.unet_tap(ws, B, H, W, mode, mine).cpu()
+        r = taps[theirs].float()
+        assert got.shape == r.shape, (mine, got.shape, r.shape)
+        rel = ((got - r).abs().max() / r.abs().max().clamp_min(1e-6)).item()
+        report.append(f"{mine}:{rel:.2e}")
+        worst = max(worst, rel)
+    err = (y.float().cpu() - ref.float()).abs().max().item()
+    print(precision, shape, "out err", err, " ".join(report))
+    assert worst <= (1e-4 if precision == "fp32" else 0.1), " ".join(report)
+    assert err <= TOL[precision], (err, " ".join(report))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_1080p_frame(nsm, precision):
+    """BASELINE config 1: single 1920x1080 frame; level sizes 540x960 / 270x480 / 135x240 / 67x120 (odd level:
+    AvgPool floors 135 -> 67 and up6 is resized 134 -> 135)."""
+    P, _ = calibrated((1, 4, 64, 64))
+    x = torch.randn(1, 4, 1080, 1920, generator=gen(9))
+    net = make_net(P, precision)
+    with torch.no_grad():
+        ref = oracle.unet_forward(x, P, training=False, bf16=(precision == "bf16")).float()
+    with torch.inference_mode():
+        y = net(x.cuda())
+    err = (y.float().cpu() - ref).abs().max().item()
+    print("1080p", precision, "max abs err", err)
+    assert y.shape == (1, 1, 1080, 1920)
+    assert err <= TOL[precision]
+
+
+def test_fused_standardise_and_host_entry(nsm):
+    P, xs = calibrated((1, 4, 48, 64))
+    mean = torch.tensor([0.1, -1.0, 5.0, 0.0])
+    std = torch.tensor([1.0, 2.0, 3.0, 0.5])
+    raw = xs * (std.view(1, 4, 1, 1) + 1e-8) + mean.view(1, 4, 1, 1)
+    x_std = oracle.standardise(raw[0], mean.tolist(), std.tolist()).unsqueeze(0)
+    net = make_net(P, "fp32")
+    with torch.no_grad():
+        ref = oracle.unet_forward(x_std, P, training=False)
+        net.set_input_stats(mean, std)
+        y = net(raw.cuda())
+        assert (y.cpu() - ref).abs().max().item() <= 1e-4
+        # stand-alone standardise kernel is bit-exact with setdata.py:316
+        got = nsm.standardize(raw.cuda(), mean.cuda(), std.cuda()).cpu()
+        assert torch.equal(got, x_std)
+        # host-buffer entry point (H2D + forward + D2H inside one C-ABI call)
+        yh = net.infer_host(raw.pin_memory())
+        assert torch.equal(yh, y.cpu())
+
+
+def test_rejects_bad_input(nsm):
+    from Unetmodel import Unet
+    net = Unet().cuda().eval()
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 3, 32, 32, device="cuda"))
+    with pytest.raises(nsm.NsmError):
+        net(torch.zeros(1, 4, 8, 8, device="cuda"))
+    with pytest.raises(nsm.NsmError):
+        net(torch.zeros(1, 4, 32, 32))          # CPU tensor: no fallback
