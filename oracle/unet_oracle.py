@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 __all__ = [
     "BLOCKS", "DROPOUT_P", "init_params", "param_names", "buffer_names", "even_fix", "double_conv",
-    "unet_forward", "upsample_and_match", "l1_loss", "custom_loss", "custom_loss_grad",
+    "unet_forward", "upsample_and_match", "upsample_and_match_bf16", "l1_loss", "custom_loss", "custom_loss_grad",
     "perturb_inputs", "perturbation_loss", "perturbation_loss_grad", "standardise",
     "conv_stage_eval", "train_step_grads", "calibrate_bn", "replay_conv5_checkpoint",
 ]
@@ -133,6 +133,17 @@ def upsample_and_match(src, size):
     (Unetmodel.py:51-60,118-119,122-141)."""
     up = F.interpolate(src, scale_factor=2, mode="bilinear", align_corners=True)
     return F.interpolate(up, size=tuple(size), mode="bilinear", align_corners=True)
+
+
+def upsample_and_match_bf16(src, size):
+    """bf16 variant of ``upsample_and_match`` with the semantics of ATen's CUDA kernel (what the reference runs on a
+    GPU under autocast): interpolation weights and accumulation in fp32, one rounding to bf16 after each of the two
+    resizes.  ATen's *CPU* bf16 kernel additionally rounds its interpolation weights to bf16 for larger tensors (an
+    implementation artefact: ~50 % of elements move by one bf16 ulp), so stage-level bf16 checks of the up-sampler use
+    this restatement instead of ``F.interpolate`` on bf16 CPU tensors."""
+    src = src.to(torch.bfloat16).float()
+    up = F.interpolate(src, scale_factor=2, mode="bilinear", align_corners=True).to(torch.bfloat16).float()
+    return F.interpolate(up, size=tuple(size), mode="bilinear", align_corners=True).to(torch.bfloat16).float()
 
 
 def unet_forward(x, P, training=False, dropout_rate=0.2, masks: Optional[Sequence] = None,

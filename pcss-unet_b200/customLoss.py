@@ -25,8 +25,9 @@ class _FusedL1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, output, target, check_range):
         o32 = output.detach().to(torch.float32).contiguous()
-        acc, grad = nsm.l1_loss_fwd_bwd(o32, target.detach(), (), coef_l1=1.0 / o32.numel(), want_grad=True)
-        ctx.save_for_backward(grad)
+        acc, sign = nsm.l1_loss_fwd_bwd(o32, target.detach(), (), coef_l1=1.0, want_grad=True)
+        ctx.save_for_backward(sign)       # sign(o - t) in {-1, 0, +1}
+        ctx.numel = o32.numel()
         ctx.out_dtype = output.dtype
         if check_range and float(acc[2].item()) != 0.0:     # one sync; the reference does two (:131)
             raise AssertionError("输出必须经过Sigmoid激活!")
@@ -34,8 +35,9 @@ class _FusedL1(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        return (grad * g).to(ctx.out_dtype), None, None
+        (sign,) = ctx.saved_tensors
+        # same evaluation order as autograd of (o - t).abs().mean(): (g / N) * sign  -> bit-identical gradient
+        return (sign * (g / ctx.numel)).to(ctx.out_dtype), None, None
 
 
 class L1Loss(nn.Module):

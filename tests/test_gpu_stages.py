@@ -135,7 +135,7 @@ def test_upsample_match(nsm, mode_name, shape):
     x = torch.randn(N, C, hs, ws, generator=gen(5))
     if mode_name == "bf16":
         x = bf(x)
-        ref = oracle.upsample_and_match(x.to(torch.bfloat16), (hd, wd)).float()
+        ref = oracle.upsample_and_match_bf16(x, (hd, wd))
     else:
         ref = oracle.upsample_and_match(x, (hd, wd))
     got = nsm.upsample_match(nsm.PlaneTensor.from_nchw(x.cuda(), mode), hd, wd).to_nchw()

@@ -83,7 +83,7 @@ def test_every_intermediate_against_oracle(nsm, precision, shape):
         worst = max(worst, rel)
     err = (y.float().cpu() - ref.float()).abs().max().item()
     print(precision, shape, "out err", err, " ".join(report))
-    assert worst <= (1e-4 if precision == "fp32" else 0.1), " ".join(report)
+    assert worst <= (3e-4 if precision == "fp32" else 0.1), " ".join(report)
     assert err <= TOL[precision], (err, " ".join(report))
 
 
