@@ -63,6 +63,12 @@ int nsm_unet_infer_host(const void* blob, int mode, const float* x_host, int B, 
 int nsm_unet_tap(const void* workspace, int B, int H, int W, int mode, const char* name, float* out, int* C,
                  int* h, int* w, void* stream);
 
+/* Optional per-launch timing for bench.py: while enabled, every kernel launch of nsm_unet_infer is bracketed by CUDA
+ * events on the launch stream.  nsm_profile_read() waits for them and writes "name,ms,flops,bytes\n" lines
+ * (algorithmic FLOPs / bytes of that launch) into `out`, then clears the records. */
+int nsm_profile_enable(int on);
+int nsm_profile_read(char* out, size_t cap);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Stage-level entry points (per-fused-stage parity tests; SURVEY.md 8c tolerance protocol)
  * Activations are NHWC bf16 "planes": plane 0 (= the value in bf16 mode, the hi part in fp32 mode), plane 1

@@ -1,6 +1,8 @@
 // C ABI of libnsm_b200.so (see include/nsm_b200.h) and the eval-mode whole-network orchestration.
+#include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -126,6 +128,39 @@ static Planes ws_planes(const WorkspaceLayout& L, void* ws, const char* name, in
   return p;
 }
 
+// ------------------------------------------------------------------------------------------------
+// optional per-launch timing: CUDA events recorded on the launch stream around every kernel of a forward
+// ------------------------------------------------------------------------------------------------
+struct ProfRecord {
+  std::string name;
+  double flops, bytes;
+  cudaEvent_t start, stop;
+};
+static std::mutex g_prof_mutex;
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+
+struct ProfScope {
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(const char* name, double flops, double bytes, cudaStream_t s) : st(s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    ProfRecord r;
+    r.name = name; r.flops = flops; r.bytes = bytes;
+    cudaEventCreate(&r.start);
+    cudaEventCreate(&r.stop);
+    cudaEventRecord(r.start, st);
+    g_prof.push_back(r);
+    idx = int(g_prof.size()) - 1;
+  }
+  ~ProfScope() {
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    cudaEventRecord(g_prof[idx].stop, st);
+  }
+};
+
 }  // namespace nsm
 
 using namespace nsm;
@@ -238,6 +273,9 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     hp.w0 = fvec(PL.w3[0][0]); hp.b0 = fvec(PL.v3[0][0]); hp.s0 = fvec(PL.v3[0][1]); hp.t0 = fvec(PL.v3[0][2]);
     hp.w1 = fvec(PL.w1[0][0]); hp.b1 = fvec(PL.v1[0][0]); hp.s1 = fvec(PL.v1[0][1]); hp.t1 = fvec(PL.v1[0][2]);
     hp.planes = np; hp.c2 = buf("c2"); hp.p2 = buf("p2"); hp.x16 = none;
+    const double px = double(B) * WL.lv[1].h * WL.lv[1].w;
+    ProfScope ps("head(conv2)", px * 2.0 * (16 * 144 + 16 * 64),
+                 double(B) * 4 * H * W * 4 + px * 64 * 2 * np * 1.25, st);
     NSM_TRY(head_eval(hp, st));
   }
   // ---- one DoubleConv on the tensor cores
@@ -249,7 +287,13 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     e3.bias = fvec(PL.v3[b][0]); e3.scale = fvec(PL.v3[b][1]); e3.shift = fvec(PL.v3[b][2]);
     e3.lrelu = 1; e3.round_bf16 = np == 1; e3.out = buf(tname); e3.residual = none; e3.pool = none;
     e3.out_f32 = nullptr;
-    NSM_TRY(conv_gemm_launch(s3, in, wplanes(PL.w3[b]), e3, st));
+    const double px = double(B) * lv.h * lv.w, ci = kBlocks[b].cin, co = kBlocks[b].cout;
+    char nm[32];
+    {
+      snprintf(nm, sizeof(nm), "conv%d.3x3", b + 2);
+      ProfScope ps(nm, 2.0 * px * 9 * ci * ci, (px * ci * 2 + ci * ci * 9) * 2.0 * np, st);
+      NSM_TRY(conv_gemm_launch(s3, in, wplanes(PL.w3[b]), e3, st));
+    }
     if (!oname) return 0;
     ConvShape s1 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cout, 1, np};
     ConvEpilogue e1 = e3;
@@ -257,10 +301,16 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     e1.out = buf(oname);
     e1.residual = resname ? buf(resname) : none;
     e1.pool = poolname ? buf(poolname) : none;
+    snprintf(nm, sizeof(nm), "conv%d.1x1", b + 2);
+    ProfScope ps(nm, 2.0 * px * ci * co,
+                 (px * (ci + co * (1.0 + (resname ? 1.0 : 0.0) + (poolname ? 0.25 : 0.0))) + ci * co) * 2.0 * np, st);
     NSM_TRY(conv_gemm_launch(s1, buf(tname), wplanes(PL.w1[b]), e1, st));
     return 0;
   };
   auto up = [&](const char* src, int slevel, int C, const char* dst, int dlevel) -> int {
+    ProfScope ps("upsample", 0.0,
+                 (double(B) * WL.lv[slevel].h * WL.lv[slevel].w + double(B) * WL.lv[dlevel].h * WL.lv[dlevel].w) *
+                     C * 2.0 * np, st);
     return upsample_match(buf(src), B, WL.lv[slevel].h, WL.lv[slevel].w, C, buf(dst), WL.lv[dlevel].h,
                           WL.lv[dlevel].w, np, st);
   };
@@ -281,6 +331,8 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     tp.a = buf("t9"); tp.N = B; tp.h = WL.lv[1].h; tp.w = WL.lv[1].w;
     tp.w1 = fvec(PL.w1[7][0]); tp.b1 = fvec(PL.v1[7][0]); tp.s1 = fvec(PL.v1[7][1]); tp.t1 = fvec(PL.v1[7][2]);
     tp.w10 = fvec(PL.w10); tp.b10 = fvec(PL.b10); tp.planes = np; tp.y = y;
+    const double px = double(B) * tp.h * tp.w;
+    ProfScope ps("tail(conv9.1x1+conv10)", px * 2.0 * (64 * 16 + 16 * 4), px * (64 * 2.0 * np + 16), st);
     NSM_TRY(tail_eval(tp, st));
   }
   return 0;
@@ -332,6 +384,43 @@ int nsm_unet_tap(const void* ws, int B, int H, int W, int mode, const char* name
   if (!out) return 0;
   const Planes p = ws_planes(WL, const_cast<void*>(ws), name, np);
   return planes_to_nchw(p.p[0], p.p[1], B, kTaps[t].C, lv.h, lv.w, np, out, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------- profiling
+int nsm_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  g_prof_on = on != 0;
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  g_prof.clear();
+  return 0;
+}
+
+int nsm_profile_read(char* out, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  std::string txt;
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.stop) != cudaSuccess) {
+      set_error("nsm_profile_read: event sync failed");
+      return 1;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.start, r.stop);
+    char line[160];
+    snprintf(line, sizeof(line), "%s,%.6f,%.6e,%.6e\n", r.name.c_str(), ms, r.flops, r.bytes);
+    txt += line;
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  g_prof.clear();
+  if (txt.size() + 1 > cap) {
+    set_error("nsm_profile_read: buffer too small (%zu needed)", txt.size() + 1);
+    return 1;
+  }
+  memcpy(out, txt.c_str(), txt.size() + 1);
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- stages

@@ -44,10 +44,14 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
       ci = row; co = col; stap = taps - 1 - tap;
     }
     const float v = w[((long long)co * Cin + ci) * taps + stap];
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    if (lo) {  // fp32 mode: both planes fp16
+      __half h, l;
+      split_weight(v, h, l);
+      reinterpret_cast<__half*>(hi)[i] = h;
+      reinterpret_cast<__half*>(lo)[i] = l;
+    } else {
+      hi[i] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -107,11 +111,12 @@ __global__ void nchw_to_planes_kernel(const float* __restrict__ x, int C, long l
     const long long p = p0 + i;
     const int c = c0 + threadIdx.x;
     if (c < C && p < HW) {
-      __nv_bfloat16 h, l;
-      split_bf16(tile[threadIdx.x][i], h, l);
+      __nv_bfloat16 h;
+      __half l;
+      split_act(tile[threadIdx.x][i], h, l);
       const long long o = ((long long)n * HW + p) * C + c;
       hi[o] = h;
-      if (lo) lo[o] = l;
+      if (lo) reinterpret_cast<__half*>(lo)[o] = l;
     }
   }
 }
@@ -136,7 +141,7 @@ __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, cons
     if (c < C && p < HW) {
       const long long o = ((long long)n * HW + p) * C + c;
       v = __bfloat162float(hi[o]);
-      if (lo) v += __bfloat162float(lo[o]);
+      if (lo) v += __half2float(reinterpret_cast<const __half*>(lo)[o]);
     }
     tile[i][threadIdx.x] = v;
   }
@@ -222,7 +227,7 @@ __device__ __forceinline__ void store_planes64(const Planes& dst, size_t elem_of
     for (int e = 0; e < 4; ++e) {
       const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
       hw[e] = pack_bf16(a, b);
-      lw[e] = pack_bf16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
+      lw[e] = pack_f16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
     }
     stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
     if (planes == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
       for (int e = 0; e < 4; ++e) {
         const float a = t[8 * j + 2 * e], b = t[8 * j + 2 * e + 1];
         hw[e] = pack_bf16(a, b);
-        lw[e] = pack_bf16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
+        lw[e] = pack_f16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
       }
       stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
       if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
@@ -430,8 +435,8 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
         uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          xin[2 * e] += bf16lo_to_f32(lw[e]);
-          xin[2 * e + 1] += bf16hi_to_f32(lw[e]);
+          xin[2 * e] += f16lo_to_f32(lw[e]);
+          xin[2 * e + 1] += f16hi_to_f32(lw[e]);
         }
       }
 #pragma unroll
@@ -508,8 +513,8 @@ __device__ __forceinline__ void load8(const UpParams& p, size_t elem, float* v) 
     const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      v[2 * e] += bf16lo_to_f32(lw[e]);
-      v[2 * e + 1] += bf16hi_to_f32(lw[e]);
+      v[2 * e] += f16lo_to_f32(lw[e]);
+      v[2 * e + 1] += f16hi_to_f32(lw[e]);
     }
   }
 }
@@ -563,7 +568,7 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       hw[e] = pack_bf16(r[2 * e], r[2 * e + 1]);
-      lw[e] = pack_bf16(r[2 * e] - bf16lo_to_f32(hw[e]), r[2 * e + 1] - bf16hi_to_f32(hw[e]));
+      lw[e] = pack_f16(r[2 * e] - bf16lo_to_f32(hw[e]), r[2 * e + 1] - bf16hi_to_f32(hw[e]));
     }
     stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
     if (p.planes == 2) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));

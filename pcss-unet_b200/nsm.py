@@ -68,7 +68,9 @@ def _declare(lib):
     lib.nsm_standardize.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p]
     lib.nsm_perturb.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_longlong, c_void_p,
                                 c_float, c_void_p]
-    for name in ("nsm_unet_pack", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
+    lib.nsm_profile_enable.argtypes = [c_int]
+    lib.nsm_profile_read.argtypes = [c_char_p, c_size_t]
+    for name in ("nsm_profile_enable", "nsm_profile_read", "nsm_unet_pack", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
                  "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match",
                  "nsm_l1_loss_fwd_bwd", "nsm_channel_sums", "nsm_standardize", "nsm_perturb"):
         getattr(lib, name).restype = c_int
@@ -78,7 +80,7 @@ EXPORTS = [
     "nsm_last_error", "nsm_version", "nsm_check_device", "nsm_unet_packed_bytes", "nsm_unet_pack",
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
-    "nsm_channel_sums", "nsm_standardize", "nsm_perturb",
+    "nsm_channel_sums", "nsm_standardize", "nsm_perturb", "nsm_profile_enable", "nsm_profile_read",
 ]
 
 
@@ -127,6 +129,21 @@ def mode_planes(mode: int) -> int:
 # ---------------------------------------------------------------------------------------------------------------
 # thin typed wrappers
 # ---------------------------------------------------------------------------------------------------------------
+
+def profile_enable(on: bool):
+    check(lib().nsm_profile_enable(int(on)), "nsm_profile_enable")
+
+
+def profile_read():
+    """[(name, ms, flops, bytes)] for every launch since profile_enable(True) / the previous read."""
+    buf = ctypes.create_string_buffer(1 << 20)
+    check(lib().nsm_profile_read(buf, len(buf)), "nsm_profile_read")
+    rows = []
+    for line in buf.value.decode().splitlines():
+        name, ms, fl, by = line.rsplit(",", 3)
+        rows.append((name, float(ms), float(fl), float(by)))
+    return rows
+
 
 def unet_pack(tensors, mode: int) -> torch.Tensor:
     """tensors: the 98 fp32 CUDA tensors in the order of include/nsm_b200.h -> packed uint8 blob."""

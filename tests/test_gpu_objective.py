@@ -27,7 +27,11 @@ def test_custom_loss_matches_reference_golden(nsm, golden):
     loss = crit(o, t, None)
     loss.backward()
     assert abs(loss.item() - float(golden["loss_val"])) <= 1e-6
-    assert torch.equal(o.grad.cpu(), torch.from_numpy(golden["loss_grad"]))     # alpha*sign/N is exact
+    # alpha * sign(o - t) / N; ATen's CUDA "divide by a scalar" multiplies by the reciprocal whereas the CPU golden
+    # divides, so the coefficient may differ in the last bit -- the signs must agree exactly.
+    ref_grad = torch.from_numpy(golden["loss_grad"])
+    assert torch.equal(torch.sign(o.grad.cpu()), torch.sign(ref_grad))
+    assert torch.allclose(o.grad.cpu(), ref_grad, rtol=2e-7, atol=0)
     l1 = crit.l1(o, t)
     assert abs(((loss - crit.alpha * l1) / (1 - crit.alpha)).item()) < 1e-5     # main.py:277 back-derivation of vgg
 
@@ -39,7 +43,7 @@ def test_l1_value_and_sign_gradient(nsm, shape):
     o.view(-1)[::5] = t.view(-1)[::5]                       # exact ties: sign(0) = 0
     acc, grad = nsm.l1_loss_fwd_bwd(o.cuda(), t.cuda(), (), coef_l1=0.9 / o.numel())
     assert abs(acc[0].item() / o.numel() - oracle.l1_loss(o, t).item()) <= 1e-6
-    assert torch.equal(grad.cpu(), oracle.custom_loss_grad(o, t, 0.9))
+    assert torch.allclose(grad.cpu(), oracle.custom_loss_grad(o, t, 0.9), rtol=1e-6, atol=0)
     assert acc[2].item() == 0
 
 
@@ -60,7 +64,7 @@ def test_perturbation_loss_value_and_grad(nsm):
     total.backward()
     ref = sum(oracle.l1_loss(out, y) for y in ys) / 3
     assert abs(total.item() - ref.item()) <= 1e-6 and abs(pert.item() - ref.item()) <= 1e-6
-    assert torch.allclose(o.grad.cpu(), oracle.perturbation_loss_grad(out, ys), atol=1e-12)
+    assert torch.allclose(o.grad.cpu(), oracle.perturbation_loss_grad(out, ys), rtol=1e-6, atol=0)
 
 
 def test_perturb_inputs_match_reference_order(nsm):
