@@ -30,17 +30,14 @@ __device__ __forceinline__ bool elect_one() {
 // round-to-nearest-even fp32 -> bf16 -> fp32 (the rounding points of torch.autocast(bfloat16))
 __device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-// fp32-mode activation split: v ~= hi (bf16, full fp32 range) + lo (fp16, 11-bit significand):
-// |v - hi - lo| <= max(2^-20 |v|, 2^-25)
-__device__ __forceinline__ void split_act(float v, __nv_bfloat16& hi, __half& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2half_rn(v - __bfloat162float(hi));
-}
-// fp32-mode weight split: both parts fp16 (weights are bounded): |w - hi - lo| <= max(2^-23 |w|, 2^-25), and the
-// dropped lo*lo product of the 3-term GEMM is <= 2^-21 relative.
-__device__ __forceinline__ void split_weight(float v, __half& hi, __half& lo) {
-  hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
+// fp32-mode split of activations and weights: v ~= hi (fp16, saturated to +-65504) + lo (fp16):
+// |v - hi - lo| <= max(2^-23 |v|, 2^-25) for |v| <= 65504; the dropped lo*lo product of the 3-term GEMM is <= 2^-22
+// relative.  (kind::f16 MMAs must not mix fp16 and bf16 operands -- the hardware raises an illegal instruction -- so
+// both planes of both operands are fp16 in this mode; bf16 mode uses one bf16 plane.)
+__device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(sat_f16(v));
+  lo = __float2half_rn(sat_f16(v - __half2float(hi)));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -55,6 +52,21 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
 }
 __device__ __forceinline__ float f16lo_to_f32(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
 __device__ __forceinline__ float f16hi_to_f32(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+// plane-format dispatch: planes == 1 -> bf16 value plane, planes == 2 -> fp16 hi plane
+__device__ __forceinline__ uint32_t pack_hi(float a, float b, int planes) {
+  return planes == 2 ? pack_f16(sat_f16(a), sat_f16(b)) : pack_bf16(a, b);
+}
+__device__ __forceinline__ float hi_lo_to_f32(uint32_t w, int planes) {
+  return planes == 2 ? f16lo_to_f32(w) : bf16lo_to_f32(w);
+}
+__device__ __forceinline__ float hi_hi_to_f32(uint32_t w, int planes) {
+  return planes == 2 ? f16hi_to_f32(w) : bf16hi_to_f32(w);
+}
+// lo plane of a pair given the packed hi word
+__device__ __forceinline__ uint32_t pack_lo_resid(float a, float b, uint32_t hw) {
+  return pack_f16(sat_f16(a - f16lo_to_f32(hw)), sat_f16(b - f16hi_to_f32(hw)));
+}
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 

@@ -46,7 +46,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
     const float v = w[((long long)co * Cin + ci) * taps + stap];
     if (lo) {  // fp32 mode: both planes fp16
       __half h, l;
-      split_weight(v, h, l);
+      split_f16(v, h, l);
       reinterpret_cast<__half*>(hi)[i] = h;
       reinterpret_cast<__half*>(lo)[i] = l;
     } else {
@@ -111,12 +111,15 @@ __global__ void nchw_to_planes_kernel(const float* __restrict__ x, int C, long l
     const long long p = p0 + i;
     const int c = c0 + threadIdx.x;
     if (c < C && p < HW) {
-      __nv_bfloat16 h;
-      __half l;
-      split_act(tile[threadIdx.x][i], h, l);
       const long long o = ((long long)n * HW + p) * C + c;
-      hi[o] = h;
-      if (lo) reinterpret_cast<__half*>(lo)[o] = l;
+      if (lo) {
+        __half h, l;
+        split_f16(tile[threadIdx.x][i], h, l);
+        reinterpret_cast<__half*>(hi)[o] = h;
+        reinterpret_cast<__half*>(lo)[o] = l;
+      } else {
+        hi[o] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+      }
     }
   }
 }
@@ -140,8 +143,8 @@ __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, cons
     float v = 0.f;
     if (c < C && p < HW) {
       const long long o = ((long long)n * HW + p) * C + c;
-      v = __bfloat162float(hi[o]);
-      if (lo) v += __half2float(reinterpret_cast<const __half*>(lo)[o]);
+      if (lo) v = __half2float(reinterpret_cast<const __half*>(hi)[o]) + __half2float(reinterpret_cast<const __half*>(lo)[o]);
+      else v = __bfloat162float(hi[o]);
     }
     tile[i][threadIdx.x] = v;
   }
@@ -226,8 +229,8 @@ __device__ __forceinline__ void store_planes64(const Planes& dst, size_t elem_of
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-      hw[e] = pack_bf16(a, b);
-      lw[e] = pack_f16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
+      hw[e] = pack_hi(a, b, planes);
+      lw[e] = pack_lo_resid(a, b, hw[e]);
     }
     stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
     if (planes == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
@@ -290,8 +293,8 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float a = t[8 * j + 2 * e], b = t[8 * j + 2 * e + 1];
-        hw[e] = pack_bf16(a, b);
-        lw[e] = pack_f16(a - bf16lo_to_f32(hw[e]), b - bf16hi_to_f32(hw[e]));
+        hw[e] = pack_hi(a, b, p.planes);
+        lw[e] = pack_lo_resid(a, b, hw[e]);
       }
       stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
       if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
@@ -427,8 +430,8 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
       float xin[8];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        xin[2 * e] = bf16lo_to_f32(hw[e]);
-        xin[2 * e + 1] = bf16hi_to_f32(hw[e]);
+        xin[2 * e] = hi_lo_to_f32(hw[e], p.planes);
+        xin[2 * e + 1] = hi_hi_to_f32(hw[e], p.planes);
       }
       if (a1) {
         const uint4 lv = ldg16(a1 + 16 * j);
@@ -505,8 +508,8 @@ __device__ __forceinline__ void load8(const UpParams& p, size_t elem, float* v) 
   const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    v[2 * e] = bf16lo_to_f32(hw[e]);
-    v[2 * e + 1] = bf16hi_to_f32(hw[e]);
+    v[2 * e] = hi_lo_to_f32(hw[e], p.planes);
+    v[2 * e + 1] = hi_hi_to_f32(hw[e], p.planes);
   }
   if (p.planes == 2) {
     const uint4 lv = ldg16(p.s1 + elem * 2);
@@ -567,8 +570,8 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p) {
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      hw[e] = pack_bf16(r[2 * e], r[2 * e + 1]);
-      lw[e] = pack_f16(r[2 * e] - bf16lo_to_f32(hw[e]), r[2 * e + 1] - bf16hi_to_f32(hw[e]));
+      hw[e] = pack_hi(r[2 * e], r[2 * e + 1], p.planes);
+      lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e]);
     }
     stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
     if (p.planes == 2) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
