@@ -103,17 +103,25 @@ struct ConvKernelParams {
 
 template <int BN, int NP>
 struct GemmCfg {
-  static constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 bf16
-  static constexpr int B_BYTES = BN * 128;   // BN channels x 64 bf16
+  static constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 elements (2 B)
+  static constexpr int B_BYTES = BN * 128;   // BN channels x 64 elements
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = 2 * BN;
+  // fp32 mode keeps two accumulators per stage: [main = a_hi*w_hi | cross = a_hi*w_lo + a_lo*w_hi]
+  static constexpr int ACC_COLS = NP * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
-  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two <= 512");
 };
+
+// fp32 mode: the tensor core adds into its fp32 accumulator with truncation, so the error of one accumulator grows like
+// (#MMAs) * 2^-24 (measured: ~1e-4 relative after K = 9216).  The K loop is therefore cut into chunks of at most
+// kChunkKB k-blocks; every chunk accumulates from zero in TMEM and the epilogue warps add the chunk results into
+// fp32 registers with round-to-nearest.
+constexpr int kChunkKB = 8;
 
 __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item, int& n, int& y0, int& x0,
                                             int& nb) {
@@ -125,6 +133,119 @@ __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item,
   n = t / p.tiles_y;
   y0 = ty * kTileH;
   x0 = tx * kTileW;
+}
+
+// Epilogue math + stores for 32 consecutive output channels [cb, cb+32) of one pixel (one thread).
+template <int NP>
+__device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelParams& p, int cb, bool valid,
+                                              size_t pix, bool pool_anchor, size_t ppix) {
+  const ConvEpilogue& ep = p.ep;
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + cb + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (ep.out_f32 && valid) {
+    float4* o = reinterpret_cast<float4*>(ep.out_f32 + pix * p.Cout + cb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (ep.round_bf16) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+  }
+  if (ep.scale) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(ep.scale + cb + j));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(ep.shift + cb + j));
+      v[j] = fmaf(v[j], s.x, t.x); v[j + 1] = fmaf(v[j + 1], s.y, t.y);
+      v[j + 2] = fmaf(v[j + 2], s.z, t.z); v[j + 3] = fmaf(v[j + 3], s.w, t.w);
+    }
+    if (ep.round_bf16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+    }
+  }
+  if (ep.lrelu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
+    if (ep.round_bf16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+    }
+  }
+  if (ep.residual.p[0] && valid) {
+    const uint8_t* r0 = reinterpret_cast<const uint8_t*>(ep.residual.p[0]) + (pix * p.Cout + cb) * 2;
+    const uint8_t* r1 =
+        NP == 2 ? reinterpret_cast<const uint8_t*>(ep.residual.p[1]) + (pix * p.Cout + cb) * 2 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 h = ldg16(r0 + 16 * j);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[8 * j + 2 * e] += hi_lo_to_f32(hw[e], NP);
+        v[8 * j + 2 * e + 1] += hi_hi_to_f32(hw[e], NP);
+      }
+      if (NP == 2) {
+        const uint4 l = ldg16(r1 + 16 * j);
+        const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[8 * j + 2 * e] += f16lo_to_f32(lw[e]);
+          v[8 * j + 2 * e + 1] += f16hi_to_f32(lw[e]);
+        }
+      }
+    }
+    if (ep.round_bf16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+    }
+  }
+  if (ep.out.p[0] && valid) {
+    uint8_t* o0 = reinterpret_cast<uint8_t*>(ep.out.p[0]) + (pix * p.Cout + cb) * 2;
+    uint8_t* o1 = NP == 2 ? reinterpret_cast<uint8_t*>(ep.out.p[1]) + (pix * p.Cout + cb) * 2 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+        hw[e] = pack_hi(a, b, NP);
+        if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e]);
+      }
+      stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    }
+  }
+  if (ep.pool.p[0]) {  // warp-uniform: AvgPool2d(2) over (lane^1, lane^16) partners
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float s = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      s *= 0.25f;
+      v[j] = ep.round_bf16 ? rbf(s) : s;
+    }
+    if (pool_anchor) {
+      uint8_t* o0 = reinterpret_cast<uint8_t*>(ep.pool.p[0]) + (ppix * p.Cout + cb) * 2;
+      uint8_t* o1 = NP == 2 ? reinterpret_cast<uint8_t*>(ep.pool.p[1]) + (ppix * p.Cout + cb) * 2 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+          hw[e] = pack_hi(a, b, NP);
+          if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e]);
+        }
+        stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+      }
+    }
+  }
 }
 
 template <int BN, int NP>
@@ -170,6 +291,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = p.taps * p.kc_per_tap;
+  // accumulation chunks (fp32 mode only; bf16 mode accumulates the whole K in one TMEM accumulator)
+  const int num_chunks = NP == 2 ? (num_kb + kChunkKB - 1) / kChunkKB : 1;
+  const int chunk_len = (num_kb + num_chunks - 1) / num_chunks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -203,35 +327,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_len) {
+          const int kb1 = kb0 + chunk_len < num_kb ? kb0 + chunk_len : num_kb;
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_hi = a_hi + NP * Cfg::A_BYTES;
+          const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
+          const uint32_t d_cross = d_main + BN;  // fp32 mode only
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t b_hi = a_hi + NP * Cfg::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < kKChunk / 16; ++k) {
-            const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, 1024);
-            const uint64_t db_hi = make_desc_sw128(b_hi + k * 32, 16, 1024);
-            umma_bf16(d, da_hi, db_hi, p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
-            if (NP == 2) {
-              const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
-              const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
-              umma_bf16(d, da_hi, db_lo, p.idesc_hi, 1u);
-              umma_bf16(d, da_lo, db_hi, p.idesc_lo, 1u);
+            for (int k = 0; k < kKChunk / 16; ++k) {
+              const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;  // first MMA of a chunk overwrites
+              const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, 1024);
+              const uint64_t db_hi = make_desc_sw128(b_hi + k * 32, 16, 1024);
+              umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
+              if (NP == 2) {
+                const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
+                const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
+                umma_bf16(d_cross, da_hi, db_lo, p.idesc_hi, accum);
+                umma_bf16(d_cross, da_lo, db_hi, p.idesc_lo, 1u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
             }
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
-          if (++stage == Cfg::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          umma_commit(&tfull_bar[acc]);  // chunk accumulator complete -> epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
@@ -239,7 +368,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q = warp & 3;         // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;  // pixel index inside the patch
     const int ly = row / kTileW, lx = row % kTileW;
-    const ConvEpilogue& ep = p.ep;
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
     uint32_t acc = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int n, y0, x0, nb;
@@ -251,129 +380,55 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const bool pool_anchor = ((lane & 1) == 0) && ((lane & 16) == 0) && ((y >> 1) < Hp) && ((x >> 1) < Wp);
       const size_t ppix = (size_t(n) * Hp + (y >> 1)) * Wp + (x >> 1);
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+      if (NP == 1) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c0, r);
-        tmem_ld_wait();
-        const int cb = nb * BN + c0;
-        float v[32];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + c0, r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + cb + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_cols<NP>(v, p, nb * BN + c0, valid, pix, pool_anchor, ppix);
         }
-        if (ep.out_f32 && valid) {
-          float4* o = reinterpret_cast<float4*>(ep.out_f32 + pix * p.Cout + cb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        // fp32 mode: sum the chunk accumulators (main + cross) in registers with round-to-nearest adds
+        float sum[BN];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+        for (int ch = 0; ch < num_chunks; ++ch) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + c0, r0);
+            tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + BN + c0, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-        if (ep.round_bf16) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
-        }
-        if (ep.scale) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(ep.scale + cb + j));
-            const float4 t = __ldg(reinterpret_cast<const float4*>(ep.shift + cb + j));
-            v[j] = fmaf(v[j], s.x, t.x); v[j + 1] = fmaf(v[j + 1], s.y, t.y);
-            v[j + 2] = fmaf(v[j + 2], s.z, t.z); v[j + 3] = fmaf(v[j + 3], s.w, t.w);
-          }
-          if (ep.round_bf16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
-          }
-        }
-        if (ep.lrelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
-          if (ep.round_bf16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
-          }
-        }
-        if (ep.residual.p[0] && valid) {
-          const uint8_t* r0 = reinterpret_cast<const uint8_t*>(ep.residual.p[0]) + (pix * p.Cout + cb) * 2;
-          const uint8_t* r1 = NP == 2 ? reinterpret_cast<const uint8_t*>(ep.residual.p[1]) + (pix * p.Cout + cb) * 2
-                                      : nullptr;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 h = ldg16(r0 + 16 * j);
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[8 * j + 2 * e] += hi_lo_to_f32(hw[e], NP);
-              v[8 * j + 2 * e + 1] += hi_hi_to_f32(hw[e], NP);
-            }
-            if (NP == 2) {
-              const uint4 l = ldg16(r1 + 16 * j);
-              const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[8 * j + 2 * e] += f16lo_to_f32(lw[e]);
-                v[8 * j + 2 * e + 1] += f16hi_to_f32(lw[e]);
-              }
-            }
-          }
-          if (ep.round_bf16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
-          }
-        }
-        if (ep.out.p[0] && valid) {
-          uint8_t* o0 = reinterpret_cast<uint8_t*>(ep.out.p[0]) + (pix * p.Cout + cb) * 2;
-          uint8_t* o1 = NP == 2 ? reinterpret_cast<uint8_t*>(ep.out.p[1]) + (pix * p.Cout + cb) * 2 : nullptr;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-              hw[e] = pack_hi(a, b, NP);
-              if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e]);
-            }
-            stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-            if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-          }
-        }
-        if (ep.pool.p[0]) {  // warp-uniform: AvgPool2d(2) over (lane^1, lane^16) partners
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float s = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
-            s *= 0.25f;
-            v[j] = ep.round_bf16 ? rbf(s) : s;
-          }
-          if (pool_anchor) {
-            uint8_t* o0 = reinterpret_cast<uint8_t*>(ep.pool.p[0]) + (ppix * p.Cout + cb) * 2;
-            uint8_t* o1 = NP == 2 ? reinterpret_cast<uint8_t*>(ep.pool.p[1]) + (ppix * p.Cout + cb) * 2 : nullptr;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-                hw[e] = pack_hi(a, b, NP);
-                if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e]);
-              }
-              stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-              if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-            }
-          }
+          for (int j = 0; j < 32; ++j) v[j] = sum[c0 + j];
+          epilogue_cols<NP>(v, p, nb * BN + c0, valid, pix, pool_anchor, ppix);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -427,7 +482,7 @@ static int num_sms() {
 
 int conv_gemm_pick_bn(const ConvShape& s) {
   num_sms();
-  if (g_force_bn && s.Cout % g_force_bn == 0) return g_force_bn;
+  if (g_force_bn && s.Cout % g_force_bn == 0 && !(s.planes == 2 && g_force_bn == 256)) return g_force_bn;
   if (s.planes == 1 && s.Cout % 256 == 0) return 256;
   if (s.Cout % 128 == 0) return 128;
   return 64;
@@ -484,7 +539,6 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     if (BN == 128) return launch_t<128, 1>(maps, kp, grid, stream);
     return launch_t<64, 1>(maps, kp, grid, stream);
   }
-  if (BN == 256) return launch_t<256, 2>(maps, kp, grid, stream);
   if (BN == 128) return launch_t<128, 2>(maps, kp, grid, stream);
   return launch_t<64, 2>(maps, kp, grid, stream);
 }
