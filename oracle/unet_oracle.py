@@ -158,7 +158,9 @@ def unet_forward(x, P, training=False, dropout_rate=0.2, masks: Optional[Sequenc
     runs backward (pinned by tests/golden: ``train_nbt == 2``).  The oracle evaluates conv5 directly
     and ``replay_conv5_checkpoint`` applies that second update.  ``taps`` (optional dict) receives
     every intermediate tensor."""
-    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
+    # device-agnostic: on CPU tensors this is the CPU oracle; fed CUDA tensors the very same call sequence runs through
+    # stock PyTorch/cuDNN (the "reference on the same GPU" of SURVEY 8c/8d) -- used only as a second checker.
+    ctx = torch.autocast(x.device.type, dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
     with ctx:
         x = even_fix(x)                                   # :92-97
         x = x.to(torch.float32)                           # :100

@@ -90,18 +90,41 @@ def test_every_intermediate_against_oracle(nsm, precision, shape):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_1080p_frame(nsm, precision):
     """BASELINE config 1: single 1920x1080 frame; level sizes 540x960 / 270x480 / 135x240 / 67x120 (odd level:
-    AvgPool floors 135 -> 67 and up6 is resized 134 -> 135)."""
+    AvgPool floors 135 -> 67 and up6 is resized 134 -> 135).
+
+    fp32 mode is asserted against the CPU fp32 oracle.  bf16 mode is asserted against the same call sequence executed
+    by stock PyTorch on the GPU under autocast(bfloat16) with TF32 off (the reference path as main.py:257-263 runs it
+    on a GPU); the CPU bf16 oracle is reported next to it together with the reference-vs-reference floor, because
+    ATen's CPU bf16 kernels round differently from its CUDA kernels (e.g. bf16 interpolation weights)."""
     P, _ = calibrated((1, 4, 64, 64))
     x = torch.randn(1, 4, 1080, 1920, generator=gen(9))
     net = make_net(P, precision)
+    bf16 = precision == "bf16"
     with torch.no_grad():
-        ref = oracle.unet_forward(x, P, training=False, bf16=(precision == "bf16")).float()
+        ref_cpu = oracle.unet_forward(x, P, training=False, bf16=bf16).float()
     with torch.inference_mode():
-        y = net(x.cuda())
-    err = (y.float().cpu() - ref).abs().max().item()
-    print("1080p", precision, "max abs err", err)
+        y = net(x.cuda()).float().cpu()
     assert y.shape == (1, 1, 1080, 1920)
-    assert err <= TOL[precision]
+    err_cpu = (y - ref_cpu).abs().max().item()
+    if not bf16:
+        print("1080p fp32 max abs err vs CPU oracle", err_cpu)
+        assert err_cpu <= TOL[precision]
+        return
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        Pg = {k: v.cuda() for k, v in P.items()}
+        with torch.no_grad():
+            ref_gpu = oracle.unet_forward(x.cuda(), Pg, training=False, bf16=True).float().cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    err_gpu = (y - ref_gpu).abs().max().item()
+    floor = (ref_gpu - ref_cpu).abs().max().item()
+    print(f"1080p bf16 max abs err: vs stock-PyTorch-on-GPU bf16 {err_gpu:.4g}, vs CPU bf16 oracle {err_cpu:.4g}; "
+          f"reference-vs-reference (GPU vs CPU bf16) {floor:.4g}; mean abs err vs GPU ref "
+          f"{(y - ref_gpu).abs().mean().item():.3g}")
+    assert err_gpu <= TOL[precision]
+    assert err_cpu <= max(TOL[precision], 1.5 * floor)
 
 
 def test_fused_standardise_and_host_entry(nsm):
