@@ -28,7 +28,8 @@ extern "C" {
 #endif
 
 #define NSM_MODE_BF16 0
-#define NSM_MODE_FP32 1
+#define NSM_MODE_FP32 1       /* eval / forward-only: hi+lo fp16 planes (|activation| <= 65504), 22 significand bits */
+#define NSM_MODE_FP32_TRAIN 2 /* training: hi+lo bf16 planes (full fp32 range, safe for tiny gradients), 16 bits     */
 
 /* number of fp32 tensors nsm_unet_pack() consumes, in this order:
  *   for K in conv2..conv9 (Unetmodel.py:39-61):

@@ -37,7 +37,7 @@ struct PackedLayout {
 };
 
 static PackedLayout packed_layout(int mode) {
-  const int np = mode == NSM_MODE_FP32 ? 2 : 1;
+  const int np = fmt_planes(mode);
   PackedLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -91,7 +91,7 @@ struct WorkspaceLayout {
 };
 
 static WorkspaceLayout workspace_layout(int B, int H, int W, int mode) {
-  const int np = mode == NSM_MODE_FP32 ? 2 : 1;
+  const int np = fmt_planes(mode);
   WorkspaceLayout L;
   const int He = H - (H & 1), We = W - (W & 1);
   L.lv[0] = {He, We};
@@ -197,7 +197,7 @@ size_t nsm_unet_packed_bytes(int mode) { return packed_layout(mode).total; }
 
 int nsm_unet_pack(const float* const* T, int mode, void* blob, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode != NSM_MODE_BF16 && mode != NSM_MODE_FP32) {
+  if (mode < 0 || mode > 2) {
     set_error("nsm_unet_pack: bad mode %d", mode);
     return 1;
   }
@@ -211,7 +211,7 @@ int nsm_unet_pack(const float* const* T, int mode, void* blob, void* stream) {
     if (b == 0) {
       NSM_TRY(copy_round(t[0], reinterpret_cast<float*>(base + L.w3[b][0]), cin * cin * 9, rb, st));
     } else {
-      NSM_TRY(pack_conv_weight(t[0], cin, cin, 3, 0, base + L.w3[b][0], rb ? nullptr : base + L.w3[b][1], st));
+      NSM_TRY(pack_conv_weight(t[0], cin, cin, 3, 0, mode, base + L.w3[b][0], rb ? nullptr : base + L.w3[b][1], st));
     }
     NSM_TRY(copy_round(t[1], reinterpret_cast<float*>(base + L.v3[b][0]), cin, rb, st));
     NSM_TRY(bn_fold_eval(t[2], t[3], t[4], t[5], cin, 1e-5f, reinterpret_cast<float*>(base + L.v3[b][1]),
@@ -220,7 +220,7 @@ int nsm_unet_pack(const float* const* T, int mode, void* blob, void* stream) {
     if (b == 0 || b == 7) {
       NSM_TRY(copy_round(t[6], reinterpret_cast<float*>(base + L.w1[b][0]), cin * cout, rb, st));
     } else {
-      NSM_TRY(pack_conv_weight(t[6], cout, cin, 1, 0, base + L.w1[b][0], rb ? nullptr : base + L.w1[b][1], st));
+      NSM_TRY(pack_conv_weight(t[6], cout, cin, 1, 0, mode, base + L.w1[b][0], rb ? nullptr : base + L.w1[b][1], st));
     }
     NSM_TRY(copy_round(t[7], reinterpret_cast<float*>(base + L.v1[b][0]), cout, rb, st));
     NSM_TRY(bn_fold_eval(t[8], t[9], t[10], t[11], cout, 1e-5f, reinterpret_cast<float*>(base + L.v1[b][1]),
@@ -240,7 +240,7 @@ size_t nsm_unet_workspace_bytes(int B, int H, int W, int mode) {
 int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int W, const float* mean,
                    const float* std, float* y, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode != NSM_MODE_BF16 && mode != NSM_MODE_FP32) {
+  if (mode < 0 || mode > 2) {
     set_error("nsm_unet_infer: bad mode %d", mode);
     return 1;
   }
@@ -254,7 +254,7 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     return 1;
   }
   const PackedLayout PL = packed_layout(mode);
-  const int np = mode == NSM_MODE_FP32 ? 2 : 1;
+  const int np = fmt_planes(mode);
   const uint8_t* pb = reinterpret_cast<const uint8_t*>(blob);
   auto fvec = [&](size_t off) { return reinterpret_cast<const float*>(pb + off); };
   auto wplanes = [&](const size_t (&o)[2]) {
@@ -272,7 +272,7 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     hp.x = x; hp.N = B; hp.Hin = H; hp.Win = W; hp.mean = mean; hp.std = std;
     hp.w0 = fvec(PL.w3[0][0]); hp.b0 = fvec(PL.v3[0][0]); hp.s0 = fvec(PL.v3[0][1]); hp.t0 = fvec(PL.v3[0][2]);
     hp.w1 = fvec(PL.w1[0][0]); hp.b1 = fvec(PL.v1[0][0]); hp.s1 = fvec(PL.v1[0][1]); hp.t1 = fvec(PL.v1[0][2]);
-    hp.planes = np; hp.c2 = buf("c2"); hp.p2 = buf("p2"); hp.x16 = none;
+    hp.fmt = mode; hp.c2 = buf("c2"); hp.p2 = buf("p2"); hp.x16 = none;
     const double px = double(B) * WL.lv[1].h * WL.lv[1].w;
     ProfScope ps("head(conv2)", px * 2.0 * (16 * 144 + 16 * 64),
                  double(B) * 4 * H * W * 4 + px * 64 * 2 * np * 1.25, st);
@@ -282,7 +282,7 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
   auto double_conv = [&](int b, int level, const Planes& in, const char* tname, const char* oname,
                          const char* resname, const char* poolname) -> int {
     const Level& lv = WL.lv[level];
-    ConvShape s3 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cin, 9, np};
+    ConvShape s3 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cin, 9, mode};
     ConvEpilogue e3;
     e3.bias = fvec(PL.v3[b][0]); e3.scale = fvec(PL.v3[b][1]); e3.shift = fvec(PL.v3[b][2]);
     e3.lrelu = 1; e3.round_bf16 = np == 1; e3.out = buf(tname); e3.residual = none; e3.pool = none;
@@ -295,7 +295,7 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
       NSM_TRY(conv_gemm_launch(s3, in, wplanes(PL.w3[b]), e3, st));
     }
     if (!oname) return 0;
-    ConvShape s1 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cout, 1, np};
+    ConvShape s1 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cout, 1, mode};
     ConvEpilogue e1 = e3;
     e1.bias = fvec(PL.v1[b][0]); e1.scale = fvec(PL.v1[b][1]); e1.shift = fvec(PL.v1[b][2]);
     e1.out = buf(oname);
@@ -312,7 +312,7 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
                  (double(B) * WL.lv[slevel].h * WL.lv[slevel].w + double(B) * WL.lv[dlevel].h * WL.lv[dlevel].w) *
                      C * 2.0 * np, st);
     return upsample_match(buf(src), B, WL.lv[slevel].h, WL.lv[slevel].w, C, buf(dst), WL.lv[dlevel].h,
-                          WL.lv[dlevel].w, np, st);
+                          WL.lv[dlevel].w, mode, st);
   };
   NSM_TRY(double_conv(1, 2, buf("p2"), "t3", "c3", nullptr, "p3"));   // conv3 + pool3
   NSM_TRY(double_conv(2, 3, buf("p3"), "t4", "c4", nullptr, "p4"));   // conv4 + pool4
@@ -330,7 +330,7 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     TailParams tp;
     tp.a = buf("t9"); tp.N = B; tp.h = WL.lv[1].h; tp.w = WL.lv[1].w;
     tp.w1 = fvec(PL.w1[7][0]); tp.b1 = fvec(PL.v1[7][0]); tp.s1 = fvec(PL.v1[7][1]); tp.t1 = fvec(PL.v1[7][2]);
-    tp.w10 = fvec(PL.w10); tp.b10 = fvec(PL.b10); tp.planes = np; tp.y = y;
+    tp.w10 = fvec(PL.w10); tp.b10 = fvec(PL.b10); tp.fmt = mode; tp.y = y;
     const double px = double(B) * tp.h * tp.w;
     ProfScope ps("tail(conv9.1x1+conv10)", px * 2.0 * (64 * 16 + 16 * 4), px * (64 * 2.0 * np + 16), st);
     NSM_TRY(tail_eval(tp, st));
@@ -376,14 +376,14 @@ int nsm_unet_tap(const void* ws, int B, int H, int W, int mode, const char* name
     return 1;
   }
   const WorkspaceLayout WL = workspace_layout(B, H, W, mode);
-  const int np = mode == NSM_MODE_FP32 ? 2 : 1;
+  const int np = fmt_planes(mode);
   const Level& lv = WL.lv[kTaps[t].level];
   if (C) *C = kTaps[t].C;
   if (h) *h = lv.h;
   if (w) *w = lv.w;
   if (!out) return 0;
   const Planes p = ws_planes(WL, const_cast<void*>(ws), name, np);
-  return planes_to_nchw(p.p[0], p.p[1], B, kTaps[t].C, lv.h, lv.w, np, out, static_cast<cudaStream_t>(stream));
+  return planes_to_nchw(p.p[0], p.p[1], B, kTaps[t].C, lv.h, lv.w, mode, out, static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------------------------- profiling
@@ -425,15 +425,15 @@ int nsm_profile_read(char* out, size_t cap) {
 
 // ---------------------------------------------------------------------------------------------- stages
 int nsm_nchw_to_planes(const float* x, int N, int C, int H, int W, int mode, void* p0, void* p1, void* stream) {
-  return nchw_to_planes(x, N, C, H, W, mode == NSM_MODE_FP32 ? 2 : 1, p0, p1, static_cast<cudaStream_t>(stream));
+  return nchw_to_planes(x, N, C, H, W, mode, p0, p1, static_cast<cudaStream_t>(stream));
 }
 int nsm_planes_to_nchw(const void* p0, const void* p1, int N, int C, int H, int W, int mode, float* y,
                        void* stream) {
-  return planes_to_nchw(p0, p1, N, C, H, W, mode == NSM_MODE_FP32 ? 2 : 1, y, static_cast<cudaStream_t>(stream));
+  return planes_to_nchw(p0, p1, N, C, H, W, mode, y, static_cast<cudaStream_t>(stream));
 }
 int nsm_pack_conv_weight(const float* w, int Cout, int Cin, int ksize, int dgrad, int mode, void* p0, void* p1,
                          void* stream) {
-  return pack_conv_weight(w, Cout, Cin, ksize, dgrad, p0, mode == NSM_MODE_FP32 ? p1 : nullptr,
+  return pack_conv_weight(w, Cout, Cin, ksize, dgrad, mode, p0, mode != NSM_MODE_BF16 ? p1 : nullptr,
                           static_cast<cudaStream_t>(stream));
 }
 
@@ -442,8 +442,7 @@ int nsm_conv_fwd(const nsm_conv_args* a, void* stream) {
     set_error("nsm_conv_fwd: null args");
     return 1;
   }
-  const int np = a->mode == NSM_MODE_FP32 ? 2 : 1;
-  ConvShape s = {a->N, a->H, a->W, a->Cin, a->Cout, a->ksize * a->ksize, np};
+  ConvShape s = {a->N, a->H, a->W, a->Cin, a->Cout, a->ksize * a->ksize, a->mode};
   Planes in = {{const_cast<void*>(a->in[0]), const_cast<void*>(a->in[1])}};
   Planes w = {{const_cast<void*>(a->weight[0]), const_cast<void*>(a->weight[1])}};
   ConvEpilogue e;
@@ -460,8 +459,7 @@ int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, voi
                        int mode, void* stream) {
   Planes s = {{const_cast<void*>(src[0]), const_cast<void*>(src[1])}};
   Planes d = {{dst[0], dst[1]}};
-  return upsample_match(s, N, hs, ws, C, d, hd, wd, mode == NSM_MODE_FP32 ? 2 : 1,
-                        static_cast<cudaStream_t>(stream));
+  return upsample_match(s, N, hs, ws, C, d, hd, wd, mode, static_cast<cudaStream_t>(stream));
 }
 
 int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,

@@ -96,6 +96,7 @@ int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64
 struct ConvKernelParams {
   int N, H, W, Cin, Cout, taps;
   int tiles_x, tiles_y, n_blocks, total_items, kc_per_tap;
+  int fmt;
   uint32_t idesc_hi;  // A hi-plane x B (bf16 x bf16 in bf16 mode; bf16 x fp16 in fp32 mode)
   uint32_t idesc_lo;  // A lo-plane (fp16) x B hi-plane (fp16), fp32 mode only
   ConvEpilogue ep;
@@ -187,16 +188,16 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
       const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        v[8 * j + 2 * e] += hi_lo_to_f32(hw[e], NP);
-        v[8 * j + 2 * e + 1] += hi_hi_to_f32(hw[e], NP);
+        v[8 * j + 2 * e] += hi_lo_to_f32(hw[e], p.fmt);
+        v[8 * j + 2 * e + 1] += hi_hi_to_f32(hw[e], p.fmt);
       }
       if (NP == 2) {
         const uint4 l = ldg16(r1 + 16 * j);
         const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          v[8 * j + 2 * e] += f16lo_to_f32(lw[e]);
-          v[8 * j + 2 * e + 1] += f16hi_to_f32(lw[e]);
+          v[8 * j + 2 * e] += lo_lo_to_f32(lw[e], p.fmt);
+          v[8 * j + 2 * e + 1] += lo_hi_to_f32(lw[e], p.fmt);
         }
       }
     }
@@ -214,8 +215,8 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-        hw[e] = pack_hi(a, b, NP);
-        if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e]);
+        hw[e] = pack_hi(a, b, p.fmt);
+        if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e], p.fmt);
       }
       stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
       if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
@@ -238,8 +239,8 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-          hw[e] = pack_hi(a, b, NP);
-          if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e]);
+          hw[e] = pack_hi(a, b, p.fmt);
+          if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e], p.fmt);
         }
         stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
         if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
@@ -482,18 +483,18 @@ static int num_sms() {
 
 int conv_gemm_pick_bn(const ConvShape& s) {
   num_sms();
-  if (g_force_bn && s.Cout % g_force_bn == 0 && !(s.planes == 2 && g_force_bn == 256)) return g_force_bn;
-  if (s.planes == 1 && s.Cout % 256 == 0) return 256;
+  if (g_force_bn && s.Cout % g_force_bn == 0 && !(s.fmt != 0 && g_force_bn == 256)) return g_force_bn;
+  if (s.fmt == 0 && s.Cout % 256 == 0) return 256;
   if (s.Cout % 128 == 0) return 128;
   return 64;
 }
 
 int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, const ConvEpilogue& ep,
                      cudaStream_t stream) {
-  if (s.Cin % kKChunk || s.Cout % 64 || (s.taps != 1 && s.taps != 9) || (s.planes != 1 && s.planes != 2) ||
+  if (s.Cin % kKChunk || s.Cout % 64 || (s.taps != 1 && s.taps != 9) || (s.fmt < 0 || s.fmt > 2) ||
       s.N <= 0 || s.H <= 0 || s.W <= 0) {
-    set_error("conv_gemm: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d taps=%d planes=%d", s.N, s.H, s.W,
-              s.Cin, s.Cout, s.taps, s.planes);
+    set_error("conv_gemm: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d taps=%d fmt=%d", s.N, s.H, s.W,
+              s.Cin, s.Cout, s.taps, s.fmt);
     return 1;
   }
   const int BN = conv_gemm_pick_bn(s);
@@ -506,7 +507,8 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   const uint64_t bdims[2] = {K, uint64_t(s.Cout)};
   const uint64_t bstr[1] = {K * 2};
   const uint32_t bbox[2] = {uint32_t(kKChunk), uint32_t(BN)};
-  for (int pl = 0; pl < s.planes; ++pl) {
+  const int planes = fmt_planes(s.fmt);
+  for (int pl = 0; pl < planes; ++pl) {
     if (!in.p[pl] || !w.p[pl]) {
       set_error("conv_gemm: null operand plane %d", pl);
       return 1;
@@ -514,7 +516,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     if (encode_tmap_tiled(&maps[pl], in.p[pl], 4, adims, astr, abox, 2)) return 1;
     if (encode_tmap_tiled(&maps[2 + pl], w.p[pl], 2, bdims, bstr, bbox, 2)) return 1;
   }
-  if (s.planes == 1) {
+  if (planes == 1) {
     maps[1] = maps[0];
     maps[3] = maps[2];
   }
@@ -525,16 +527,13 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.n_blocks = s.Cout / BN;
   kp.total_items = s.N * kp.tiles_x * kp.tiles_y * kp.n_blocks;
   kp.kc_per_tap = s.Cin / kKChunk;
-  if (s.planes == 1) {
-    kp.idesc_hi = make_idesc_f16(128, BN, kFmtBF16, kFmtBF16, 0, 0);
-    kp.idesc_lo = kp.idesc_hi;
-  } else {  // fp32 mode: all four operand planes are fp16
-    kp.idesc_hi = make_idesc_f16(128, BN, kFmtF16, kFmtF16, 0, 0);
-    kp.idesc_lo = kp.idesc_hi;
-  }
+  kp.fmt = s.fmt;
+  const uint32_t ef = s.fmt == kFmtF16x2 ? kFmtF16 : kFmtBF16;  // all operand planes of a launch share one element type
+  kp.idesc_hi = make_idesc_f16(128, BN, ef, ef, 0, 0);
+  kp.idesc_lo = kp.idesc_hi;
   kp.ep = ep;
   const int grid = kp.total_items < num_sms() ? kp.total_items : num_sms();
-  if (s.planes == 1) {
+  if (planes == 1) {
     if (BN == 256) return launch_t<256, 1>(maps, kp, grid, stream);
     if (BN == 128) return launch_t<128, 1>(maps, kp, grid, stream);
     return launch_t<64, 1>(maps, kp, grid, stream);

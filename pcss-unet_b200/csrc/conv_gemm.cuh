@@ -32,7 +32,7 @@ struct ConvShape {
   int N, H, W;     // batch and spatial size (stride 1, "same" padding => input == output size)
   int Cin, Cout;   // multiples of 64
   int taps;        // 1 (1x1) or 9 (3x3, pad 1)
-  int planes;      // 1 = bf16 mode, 2 = split-bf16 (fp32 mode)
+  int fmt;         // storage format (nsm_common.cuh): 0 bf16, 1 fp16 hi+lo, 2 bf16 hi+lo
 };
 
 // in: NHWC planes [N,H,W,Cin]; w: packed [Cout][taps][Cin] bf16 planes.  Returns cudaError-like 0 on success.

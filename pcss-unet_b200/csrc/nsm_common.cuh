@@ -53,19 +53,39 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
 __device__ __forceinline__ float f16lo_to_f32(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
 __device__ __forceinline__ float f16hi_to_f32(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
-// plane-format dispatch: planes == 1 -> bf16 value plane, planes == 2 -> fp16 hi plane
-__device__ __forceinline__ uint32_t pack_hi(float a, float b, int planes) {
-  return planes == 2 ? pack_f16(sat_f16(a), sat_f16(b)) : pack_bf16(a, b);
+// Activation / weight storage formats ("fmt", equal to the C ABI's NSM_MODE_* values):
+//   0  one bf16 plane                      (bf16 mode, autocast rounding points)
+//   1  hi + lo fp16 planes, |v| <= 65504   (fp32 mode, eval: 22 significand bits)
+//   2  hi + lo bf16 planes, full range     (fp32 mode, training: 16 significand bits, safe for tiny gradients)
+constexpr int kFmtBf16 = 0, kFmtF16x2 = 1, kFmtBf16x2 = 2;
+__host__ __device__ __forceinline__ int fmt_planes(int fmt) { return fmt == 0 ? 1 : 2; }
+
+__device__ __forceinline__ uint32_t pack_hi(float a, float b, int fmt) {
+  return fmt == kFmtF16x2 ? pack_f16(sat_f16(a), sat_f16(b)) : pack_bf16(a, b);
 }
-__device__ __forceinline__ float hi_lo_to_f32(uint32_t w, int planes) {
-  return planes == 2 ? f16lo_to_f32(w) : bf16lo_to_f32(w);
+__device__ __forceinline__ float hi_lo_to_f32(uint32_t w, int fmt) {
+  return fmt == kFmtF16x2 ? f16lo_to_f32(w) : bf16lo_to_f32(w);
 }
-__device__ __forceinline__ float hi_hi_to_f32(uint32_t w, int planes) {
-  return planes == 2 ? f16hi_to_f32(w) : bf16hi_to_f32(w);
+__device__ __forceinline__ float hi_hi_to_f32(uint32_t w, int fmt) {
+  return fmt == kFmtF16x2 ? f16hi_to_f32(w) : bf16hi_to_f32(w);
 }
-// lo plane of a pair given the packed hi word
-__device__ __forceinline__ uint32_t pack_lo_resid(float a, float b, uint32_t hw) {
-  return pack_f16(sat_f16(a - f16lo_to_f32(hw)), sat_f16(b - f16hi_to_f32(hw)));
+// lo plane word of a value pair given the packed hi word
+__device__ __forceinline__ uint32_t pack_lo_resid(float a, float b, uint32_t hw, int fmt) {
+  return fmt == kFmtF16x2 ? pack_f16(sat_f16(a - f16lo_to_f32(hw)), sat_f16(b - f16hi_to_f32(hw)))
+                          : pack_bf16(a - bf16lo_to_f32(hw), b - bf16hi_to_f32(hw));
+}
+__device__ __forceinline__ float lo_lo_to_f32(uint32_t w, int fmt) { return hi_lo_to_f32(w, fmt); }
+__device__ __forceinline__ float lo_hi_to_f32(uint32_t w, int fmt) { return hi_hi_to_f32(w, fmt); }
+// scalar split used by the (non-vectorised) packing kernels: returns raw 16-bit patterns
+__device__ __forceinline__ void split_fmt(float v, int fmt, unsigned short& hi, unsigned short& lo) {
+  const uint32_t hw = pack_hi(v, 0.f, fmt);
+  hi = (unsigned short)(hw & 0xffffu);
+  lo = (unsigned short)(pack_lo_resid(v, 0.f, hw, fmt) & 0xffffu);
+}
+__device__ __forceinline__ float join_fmt(unsigned short hi, unsigned short lo, int fmt) {
+  float v = hi_lo_to_f32(hi, fmt);
+  if (fmt != kFmtBf16) v += lo_lo_to_f32(lo, fmt);
+  return v;
 }
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }

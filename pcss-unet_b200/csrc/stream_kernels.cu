@@ -27,7 +27,7 @@ static inline int grid_for(long long work, int block, int cap = 148 * 16) {
 // parameter packing
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int flip_t,
-                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                        int fmt, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo) {
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -44,23 +44,19 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
       ci = row; co = col; stap = taps - 1 - tap;
     }
     const float v = w[((long long)co * Cin + ci) * taps + stap];
-    if (lo) {  // fp32 mode: both planes fp16
-      __half h, l;
-      split_f16(v, h, l);
-      reinterpret_cast<__half*>(hi)[i] = h;
-      reinterpret_cast<__half*>(lo)[i] = l;
-    } else {
-      hi[i] = __float2bfloat16_rn(v);
-    }
+    unsigned short h, l;
+    split_fmt(v, fmt, h, l);
+    hi[i] = h;
+    if (fmt != kFmtBf16) lo[i] = l;
   }
 }
 
-int pack_conv_weight(const float* w, int Cout, int Cin, int ksize, int flip_transpose, void* hi, void* lo,
+int pack_conv_weight(const float* w, int Cout, int Cin, int ksize, int flip_transpose, int fmt, void* hi, void* lo,
                      cudaStream_t st) {
   const int taps = ksize * ksize;
   const long long total = (long long)Cout * Cin * taps;
-  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, Cout, Cin, taps, flip_transpose,
-                                                               (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, Cout, Cin, taps, flip_transpose, fmt,
+                                                               (unsigned short*)hi, (unsigned short*)lo);
   NSM_CHECK_LAUNCH("pack_conv_weight");
   return 0;
 }
@@ -95,8 +91,8 @@ int copy_round(const float* src, float* dst, int n, int round_bf16, cudaStream_t
 // ------------------------------------------------------------------------------------------------
 // layout conversion NCHW fp32 <-> NHWC bf16 planes (smem transpose, 32 channels x 32 pixels tiles)
 // ------------------------------------------------------------------------------------------------
-__global__ void nchw_to_planes_kernel(const float* __restrict__ x, int C, long long HW, __nv_bfloat16* hi,
-                                      __nv_bfloat16* lo) {
+__global__ void nchw_to_planes_kernel(const float* __restrict__ x, int C, long long HW, int fmt, unsigned short* hi,
+                                      unsigned short* lo) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -112,27 +108,23 @@ __global__ void nchw_to_planes_kernel(const float* __restrict__ x, int C, long l
     const int c = c0 + threadIdx.x;
     if (c < C && p < HW) {
       const long long o = ((long long)n * HW + p) * C + c;
-      if (lo) {
-        __half h, l;
-        split_f16(tile[threadIdx.x][i], h, l);
-        reinterpret_cast<__half*>(hi)[o] = h;
-        reinterpret_cast<__half*>(lo)[o] = l;
-      } else {
-        hi[o] = __float2bfloat16_rn(tile[threadIdx.x][i]);
-      }
+      unsigned short h, l;
+      split_fmt(tile[threadIdx.x][i], fmt, h, l);
+      hi[o] = h;
+      if (fmt != kFmtBf16) lo[o] = l;
     }
   }
 }
-int nchw_to_planes(const float* x, int N, int C, int H, int W, int planes, void* hi, void* lo, cudaStream_t st) {
+int nchw_to_planes(const float* x, int N, int C, int H, int W, int fmt, void* hi, void* lo, cudaStream_t st) {
   const long long HW = (long long)H * W;
   dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
-  nchw_to_planes_kernel<<<grid, block, 0, st>>>(x, C, HW, (__nv_bfloat16*)hi, planes == 2 ? (__nv_bfloat16*)lo : nullptr);
+  nchw_to_planes_kernel<<<grid, block, 0, st>>>(x, C, HW, fmt, (unsigned short*)hi, (unsigned short*)lo);
   NSM_CHECK_LAUNCH("nchw_to_planes");
   return 0;
 }
 
-__global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                      int C, long long HW, float* __restrict__ y) {
+__global__ void planes_to_nchw_kernel(const unsigned short* __restrict__ hi, const unsigned short* __restrict__ lo,
+                                      int fmt, int C, long long HW, float* __restrict__ y) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -143,8 +135,7 @@ __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, cons
     float v = 0.f;
     if (c < C && p < HW) {
       const long long o = ((long long)n * HW + p) * C + c;
-      if (lo) v = __half2float(reinterpret_cast<const __half*>(hi)[o]) + __half2float(reinterpret_cast<const __half*>(lo)[o]);
-      else v = __bfloat162float(hi[o]);
+      v = join_fmt(hi[o], fmt != kFmtBf16 ? lo[o] : (unsigned short)0, fmt);
     }
     tile[i][threadIdx.x] = v;
   }
@@ -155,12 +146,11 @@ __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, cons
     if (c < C && p < HW) y[((long long)n * C + c) * HW + p] = tile[threadIdx.x][i];
   }
 }
-int planes_to_nchw(const void* hi, const void* lo, int N, int C, int H, int W, int planes, float* y,
+int planes_to_nchw(const void* hi, const void* lo, int N, int C, int H, int W, int fmt, float* y,
                    cudaStream_t st) {
   const long long HW = (long long)H * W;
   dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
-  planes_to_nchw_kernel<<<grid, block, 0, st>>>((const __nv_bfloat16*)hi,
-                                                planes == 2 ? (const __nv_bfloat16*)lo : nullptr, C, HW, y);
+  planes_to_nchw_kernel<<<grid, block, 0, st>>>((const unsigned short*)hi, (const unsigned short*)lo, fmt, C, HW, y);
   NSM_CHECK_LAUNCH("planes_to_nchw");
   return 0;
 }
@@ -220,20 +210,20 @@ __device__ __forceinline__ float head_fetch(const HeadParams& p, int n, int c, i
   return ly.w0 * (lx.w0 * v00 + lx.w1 * v01) + ly.w1 * (lx.w0 * v10 + lx.w1 * v11);
 }
 
-__device__ __forceinline__ void store_planes64(const Planes& dst, size_t elem_off, const float* v, int planes) {
+__device__ __forceinline__ void store_planes64(const Planes& dst, size_t elem_off, const float* v, int fmt) {
   uint8_t* o0 = reinterpret_cast<uint8_t*>(dst.p[0]) + elem_off * 2;
-  uint8_t* o1 = planes == 2 ? reinterpret_cast<uint8_t*>(dst.p[1]) + elem_off * 2 : nullptr;
+  uint8_t* o1 = fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(dst.p[1]) + elem_off * 2 : nullptr;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-      hw[e] = pack_hi(a, b, planes);
-      lw[e] = pack_lo_resid(a, b, hw[e]);
+      hw[e] = pack_hi(a, b, fmt);
+      lw[e] = pack_lo_resid(a, b, hw[e], fmt);
     }
     stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-    if (planes == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    if (fmt != kFmtBf16) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
   }
 }
 
@@ -243,7 +233,7 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
   const int H = p.Hin - (p.Hin & 1), W = p.Win - (p.Win & 1);
   const int h = H >> 1, w = W >> 1;
   const bool resize = (p.Hin & 1) || (p.Win & 1);
-  const bool rb = p.planes == 1;
+  const bool rb = p.fmt == kFmtBf16;
   const int n = blockIdx.z;
   const int y0 = blockIdx.y * HEAD_T, x0 = blockIdx.x * HEAD_T;
   const int tid = threadIdx.x;
@@ -286,15 +276,15 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
 #pragma unroll
     for (int c = 0; c < 16; ++c) t[c] = s.x16[c][ly + 1][lx + 1];
     uint8_t* o0 = reinterpret_cast<uint8_t*>(p.x16.p[0]) + pix * 16 * 2;
-    uint8_t* o1 = p.planes == 2 ? reinterpret_cast<uint8_t*>(p.x16.p[1]) + pix * 16 * 2 : nullptr;
+    uint8_t* o1 = p.fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(p.x16.p[1]) + pix * 16 * 2 : nullptr;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       uint32_t hw[4], lw[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float a = t[8 * j + 2 * e], b = t[8 * j + 2 * e + 1];
-        hw[e] = pack_hi(a, b, p.planes);
-        lw[e] = pack_lo_resid(a, b, hw[e]);
+        hw[e] = pack_hi(a, b, p.fmt);
+        lw[e] = pack_lo_resid(a, b, hw[e], p.fmt);
       }
       stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
       if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
@@ -354,7 +344,7 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
     if (rb) v = rbf(v);
     o[co] = v;
   }
-  if (valid) store_planes64(p.c2, pix * 64, o, p.planes);
+  if (valid) store_planes64(p.c2, pix * 64, o, p.fmt);
   // AvgPool2d(2): partners lane^1 (x) and lane^16 (y)
   const int hp = h >> 1, wp = w >> 1;
 #pragma unroll
@@ -365,7 +355,7 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
     o[co] = rb ? rbf(t) : t;
   }
   if (!(lane & 1) && !(lane & 16) && (y >> 1) < hp && (x >> 1) < wp)
-    store_planes64(p.p2, (((size_t)n * hp + (y >> 1)) * wp + (x >> 1)) * 64, o, p.planes);
+    store_planes64(p.p2, (((size_t)n * hp + (y >> 1)) * wp + (x >> 1)) * 64, o, p.fmt);
 }
 
 int head_eval(const HeadParams& p, cudaStream_t st) {
@@ -414,7 +404,7 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
   if (tid < 16) { s.b1[tid] = p.b1[tid]; s.s1[tid] = p.s1[tid]; s.t1[tid] = p.t1[tid]; }
   if (tid < 4) s.b10[tid] = p.b10[tid];
   __syncthreads();
-  const bool rb = p.planes == 1;
+  const bool rb = p.fmt == kFmtBf16;
   const long long npix = (long long)p.N * p.h * p.w;
   const int W = 2 * p.w, H = 2 * p.h;
   for (long long pix = blockIdx.x * 256LL + tid; pix < npix; pix += (long long)gridDim.x * 256) {
@@ -422,7 +412,7 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
 #pragma unroll
     for (int co = 0; co < 16; ++co) a[co] = 0.f;
     const uint8_t* a0 = reinterpret_cast<const uint8_t*>(p.a.p[0]) + pix * 128;
-    const uint8_t* a1 = p.planes == 2 ? reinterpret_cast<const uint8_t*>(p.a.p[1]) + pix * 128 : nullptr;
+    const uint8_t* a1 = p.fmt != kFmtBf16 ? reinterpret_cast<const uint8_t*>(p.a.p[1]) + pix * 128 : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint4 hv = ldg16(a0 + 16 * j);
@@ -430,16 +420,16 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
       float xin[8];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        xin[2 * e] = hi_lo_to_f32(hw[e], p.planes);
-        xin[2 * e + 1] = hi_hi_to_f32(hw[e], p.planes);
+        xin[2 * e] = hi_lo_to_f32(hw[e], p.fmt);
+        xin[2 * e + 1] = hi_hi_to_f32(hw[e], p.fmt);
       }
       if (a1) {
         const uint4 lv = ldg16(a1 + 16 * j);
         uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          xin[2 * e] += f16lo_to_f32(lw[e]);
-          xin[2 * e + 1] += f16hi_to_f32(lw[e]);
+          xin[2 * e] += lo_lo_to_f32(lw[e], p.fmt);
+          xin[2 * e + 1] += lo_hi_to_f32(lw[e], p.fmt);
         }
       }
 #pragma unroll
@@ -500,7 +490,7 @@ struct UpParams {
   const uint8_t* s1;
   uint8_t* d0;
   uint8_t* d1;
-  int N, hs, ws, C, hd, wd, planes;
+  int N, hs, ws, C, hd, wd, fmt;
 };
 
 __device__ __forceinline__ void load8(const UpParams& p, size_t elem, float* v) {
@@ -508,16 +498,16 @@ __device__ __forceinline__ void load8(const UpParams& p, size_t elem, float* v) 
   const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    v[2 * e] = hi_lo_to_f32(hw[e], p.planes);
-    v[2 * e + 1] = hi_hi_to_f32(hw[e], p.planes);
+    v[2 * e] = hi_lo_to_f32(hw[e], p.fmt);
+    v[2 * e + 1] = hi_hi_to_f32(hw[e], p.fmt);
   }
-  if (p.planes == 2) {
+  if (p.fmt != kFmtBf16) {
     const uint4 lv = ldg16(p.s1 + elem * 2);
     const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      v[2 * e] += f16lo_to_f32(lw[e]);
-      v[2 * e + 1] += f16hi_to_f32(lw[e]);
+      v[2 * e] += lo_lo_to_f32(lw[e], p.fmt);
+      v[2 * e + 1] += lo_hi_to_f32(lw[e], p.fmt);
     }
   }
 }
@@ -540,7 +530,7 @@ __device__ __forceinline__ void up2_at(const UpParams& p, size_t nbase, int Y, i
 __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p) {
   const int cgs = p.C / 8;
   const long long total = (long long)p.N * p.hd * p.wd * cgs;
-  const bool rb = p.planes == 1;
+  const bool rb = p.fmt == kFmtBf16;
   const bool same = (p.hd == 2 * p.hs) && (p.wd == 2 * p.ws);
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int cg = int(i % cgs);
@@ -570,15 +560,15 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p) {
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      hw[e] = pack_hi(r[2 * e], r[2 * e + 1], p.planes);
-      lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e]);
+      hw[e] = pack_hi(r[2 * e], r[2 * e + 1], p.fmt);
+      lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], p.fmt);
     }
     stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-    if (p.planes == 2) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    if (p.fmt != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
   }
 }
 
-int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes& dst, int hd, int wd, int planes,
+int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes& dst, int hd, int wd, int fmt,
                    cudaStream_t st) {
   if (C % 8) {
     set_error("upsample_match: C=%d not a multiple of 8", C);
@@ -587,7 +577,7 @@ int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes
   UpParams p;
   p.s0 = (const uint8_t*)src.p[0]; p.s1 = (const uint8_t*)src.p[1];
   p.d0 = (uint8_t*)dst.p[0]; p.d1 = (uint8_t*)dst.p[1];
-  p.N = N; p.hs = hs; p.ws = ws; p.C = C; p.hd = hd; p.wd = wd; p.planes = planes;
+  p.N = N; p.hs = hs; p.ws = ws; p.C = C; p.hd = hd; p.wd = wd; p.fmt = fmt;
   const long long total = (long long)N * hd * wd * (C / 8);
   upsample_match_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, st>>>(p);
   NSM_CHECK_LAUNCH("upsample_match");

@@ -11,7 +11,7 @@ namespace nsm {
 // ---- parameter packing --------------------------------------------------------------------------------------
 // OIHW fp32 [Cout][Cin][k][k] -> [Cout][tap][Cin] bf16 planes (hi[, lo]).  flip_transpose: dgrad form
 // [Cin][tap'][Cout] with tap' = mirrored tap.
-int pack_conv_weight(const float* w, int Cout, int Cin, int ksize, int flip_transpose, void* hi, void* lo,
+int pack_conv_weight(const float* w, int Cout, int Cin, int ksize, int flip_transpose, int fmt, void* hi, void* lo,
                      cudaStream_t st);
 // eval-mode BatchNorm as an affine: scale = gamma / sqrt(var + eps), shift = beta - mean * scale
 int bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, int C, float eps,
@@ -20,8 +20,8 @@ int bn_fold_eval(const float* gamma, const float* beta, const float* mean, const
 int copy_round(const float* src, float* dst, int n, int round_bf16, cudaStream_t st);
 
 // ---- layout conversion (tests, debugging taps) --------------------------------------------------------------
-int nchw_to_planes(const float* x, int N, int C, int H, int W, int planes, void* hi, void* lo, cudaStream_t st);
-int planes_to_nchw(const void* hi, const void* lo, int N, int C, int H, int W, int planes, float* y,
+int nchw_to_planes(const float* x, int N, int C, int H, int W, int fmt, void* hi, void* lo, cudaStream_t st);
+int planes_to_nchw(const void* hi, const void* lo, int N, int C, int H, int W, int fmt, float* y,
                    cudaStream_t st);
 
 // ---- head: [standardise] + even-size fix + pixel_unshuffle(2) + conv2 DoubleConv (16->16 3x3, 16->64 1x1) -----
@@ -38,7 +38,7 @@ struct HeadParams {
   const float* b1;  // [64]
   const float* s1;
   const float* t1;
-  int planes;       // 1: bf16 mode (autocast rounding points), 2: fp32 mode
+  int fmt;          // storage format: 0 bf16 (autocast rounding points), 1 fp16 hi+lo, 2 bf16 hi+lo
   Planes c2;        // [N,h,w,64]
   Planes p2;        // [N,h/2,w/2,64]
   Planes x16;       // optional tap of the un-shuffled input [N,h,w,16] (tests) or {nullptr}
@@ -55,13 +55,13 @@ struct TailParams {
   const float* t1;
   const float* w10;  // [4][16]
   const float* b10;  // [4]
-  int planes;
+  int fmt;
   float* y;          // [N,1,2h,2w] fp32
 };
 int tail_eval(const TailParams& p, cudaStream_t st);
 
 // ---- nn.Upsample(x2, bilinear, align_corners) followed by F.interpolate(size=(hd, wd)) -----------------------
-int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes& dst, int hd, int wd, int planes,
+int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes& dst, int hd, int wd, int fmt,
                    cudaStream_t st);
 
 // ---- objective ---------------------------------------------------------------------------------------------------

@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(HERE, "libnsm_b200.so")
 
 MODE_BF16 = 0
 MODE_FP32 = 1
-MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32}
+MODE_FP32_TRAIN = 2
+MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "fp32_train": MODE_FP32_TRAIN}
 NUM_TENSORS = 98
 
 _lib = None
@@ -123,7 +124,7 @@ def ptr(t) -> int:
 
 
 def mode_planes(mode: int) -> int:
-    return 2 if mode == MODE_FP32 else 1
+    return 1 if mode == MODE_BF16 else 2
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -195,7 +196,7 @@ class PlaneTensor:
         self.shape = (N, C, H, W)
         self.mode = mode
         self.p0 = torch.empty(N, H, W, C, dtype=torch.bfloat16, device=device)
-        self.p1 = torch.empty(N, H, W, C, dtype=torch.bfloat16, device=device) if mode == MODE_FP32 else None
+        self.p1 = torch.empty(N, H, W, C, dtype=torch.bfloat16, device=device) if mode != MODE_BF16 else None
 
     @classmethod
     def from_nchw(cls, x, mode):
@@ -223,7 +224,7 @@ def pack_conv_weight(w, mode, dgrad=False):
     w = w.detach().to(torch.float32).contiguous()
     rows, inner = (Cin, Cout) if dgrad else (Cout, Cin)
     p0 = torch.empty(rows, k * k, inner, dtype=torch.bfloat16, device=w.device)
-    p1 = torch.empty_like(p0) if mode == MODE_FP32 else None
+    p1 = torch.empty_like(p0) if mode != MODE_BF16 else None
     check(lib().nsm_pack_conv_weight(w.data_ptr(), Cout, Cin, k, int(dgrad), mode, ptr(p0), ptr(p1), stream_ptr()),
           "nsm_pack_conv_weight")
     return p0, p1

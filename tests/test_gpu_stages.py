@@ -2,7 +2,8 @@
 
 Every test calls the CUDA path through the C ABI (nsm.py -> libnsm_b200.so) and checks it against oracle/ on the same
 seeded inputs.  Tolerances:
-  fp32 mode : |err| <= 3e-5 * max(1, max|ref|)   (split-bf16 products, fp32 accumulate; north-star 1e-4 on [0,1])
+  fp32 mode : |err| <= 3e-5 * max(1, max|ref|)   (hi+lo fp16 split products, fp32 accumulate; north-star 1e-4 on [0,1])
+  fp32_train: |err| <= 1e-4 * max(1, max|ref|)   (hi+lo bf16 planes: the range-safe format used for training)
   bf16 mode : same rounding points as the autocast oracle -> isolated one-ulp flips only:
               |err| <= 2^-6 * max(|ref|, 0.1 max|ref|) element-wise and < 3 % of elements differ at all
 """
@@ -48,9 +49,9 @@ def check_close(got, ref, mode_name, what):
     ref = ref.detach().float().cpu()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     err = got - ref
-    if mode_name == "fp32":
-        tol = 3e-5 * max(1.0, ref.abs().max().item())
-        assert err.abs().max().item() <= tol, f"{what} [fp32]\n" + describe(err, ref)
+    if mode_name != "bf16":
+        tol = (3e-5 if mode_name == "fp32" else 1e-4) * max(1.0, ref.abs().max().item())
+        assert err.abs().max().item() <= tol, f"{what} [{mode_name}]\n" + describe(err, ref)
     else:
         bound = (2.0 ** -6) * torch.maximum(ref.abs(), 0.1 * ref.abs().max())
         bad = (err.abs() > bound)
@@ -58,7 +59,7 @@ def check_close(got, ref, mode_name, what):
         assert not bad.any() and frac < 0.03, f"{what} [bf16] differing={frac:.4f}\n" + describe(err, ref)
 
 
-@pytest.mark.parametrize("mode_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32", "fp32_train"])
 def test_layout_roundtrip(nsm, mode_name):
     mode = nsm.MODES[mode_name]
     x = torch.randn(2, 72, 9, 21, generator=gen(0))
@@ -67,7 +68,7 @@ def test_layout_roundtrip(nsm, mode_name):
     if mode_name == "bf16":
         assert torch.equal(y, bf(x))
     else:
-        assert (y - x).abs().max() <= 2.0 ** -17 * x.abs().max()
+        assert (y - x).abs().max() <= 2.0 ** (-21 if mode_name == "fp32" else -16) * x.abs().max()
 
 
 CONV_CASES = [
@@ -83,7 +84,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32", "fp32_train"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
 def test_conv_stage(nsm, mode_name, case):
     N, H, W, Cin, Cout, k, use_res, use_pool = case
@@ -118,14 +119,14 @@ def test_conv_stage(nsm, mode_name, case):
     else:
         ref_raw = torch.nn.functional.conv2d(x, w, b, padding=k // 2)
     got_raw = raw.permute(0, 3, 1, 2).cpu()
-    tol = (2e-5 if mode_name == "fp32" else 1e-5) * max(1.0, ref_raw.abs().max().item())
+    tol = {"fp32": 2e-5, "fp32_train": 1e-4, "bf16": 1e-5}[mode_name] * max(1.0, ref_raw.abs().max().item())
     assert (got_raw - ref_raw).abs().max().item() <= tol, "raw GEMM\n" + describe(got_raw - ref_raw, ref_raw)
     check_close(out.to_nchw(), ref, mode_name, "conv stage output")
     if use_pool:
         check_close(pl.to_nchw(), ref_pool, mode_name, "pooled output")
 
 
-@pytest.mark.parametrize("mode_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32", "fp32_train"])
 @pytest.mark.parametrize("shape", [(1, 64, 8, 12, 16, 24), (2, 128, 67, 120, 135, 240), (1, 64, 20, 28, 20, 28),
                                    (1, 512, 5, 7, 10, 14), (1, 64, 3, 2, 7, 5)],
                          ids=lambda s: "x".join(map(str, s)))
