@@ -126,6 +126,50 @@ int nsm_standardize(const float* x, float* y, long long S, int C, long long HW, 
 int nsm_perturb(const float* x, const float* noise, float* out, int count, long long B, int C, long long HW,
                 const float* stds, float std_factor, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Training path (Unet.forward under model.train() + autograd backward, main.py:263-281).  All 17 convolutions run
+ * through nsm_conv_fwd (forward and dgrad = nsm_conv_fwd with weights packed with dgrad=1) and nsm_wgrad; thin layers
+ * (16 / 4 channels) are zero-padded to 64 channels.  `p0/p1` arguments are the two planes of an NHWC tensor.
+ * --------------------------------------------------------------------------------------------------------- */
+/* nn.BatchNorm2d in training mode (Unetmodel.py:22,27): batch statistics, running-stat update, affine + LeakyReLU(0.2)
+ * + Dropout2d mask (Unetmodel.py:23-24) (+ skip add :125 / AvgPool2d :40) */
+int nsm_bn_stats(const void* z0, const void* z1, long long P, int C, int mode, double* sums /*[2C], zeroed*/,
+                 void* stream);
+int nsm_bn_finalize(const double* sums, long long P, int C, const float* gamma, const float* beta, float eps,
+                    float momentum, int updates, float* running_mean, float* running_var, float* scale, float* shift,
+                    float* save_mean, float* save_invstd, void* stream);
+int nsm_bn_act(const void* z0, const void* z1, int N, int H, int W, int C, int mode, const float* scale,
+               const float* shift, const float* mask /*[N][C] or NULL*/, int lrelu, const void* res0, const void* res1,
+               void* out0, void* out1, void* pool0, void* pool1, void* stream);
+/* backward of the above: g = dy*mask*LeakyReLU'(.), BatchNorm backward with batch statistics */
+int nsm_bn_bwd(const void* dy0, const void* dy1, const void* z0, const void* z1, int N, int H, int W, int C, int mode,
+               const float* scale, const float* shift, const float* mask, const float* mean, const float* invstd,
+               int lrelu, double* sums /*[3C] scratch, zeroed*/, void* dz0, void* dz1, float* dgamma, float* dbeta,
+               float* dbias /*conv bias grad = sum dz, or NULL*/, void* stream);
+/* adjoint of AvgPool2d(2) (+ optional second gradient `a`), plain add, adjoint of one bilinear align_corners resize */
+int nsm_pool_bwd_add(const void* a0, const void* a1, const void* dp0, const void* dp1, void* out0, void* out1, int N,
+                     int H, int W, int C, int mode, void* stream);
+int nsm_planes_add(const void* a0, const void* a1, const void* b0, const void* b1, void* out0, void* out1,
+                   long long numel, int mode, void* stream);
+int nsm_bilinear_bwd(const void* dout0, const void* dout1, int N, int ho, int wo, int C, void* din0, void* din1, int hi,
+                     int wi, int mode, void* stream);
+/* network input (even fix + pixel_unshuffle, Unetmodel.py:92-101; 16 -> 64 channels zero padded) and its adjoint */
+int nsm_train_input_prep(const float* x, int N, int Hin, int Win, void* out0, void* out1, int mode, void* stream);
+int nsm_train_input_grad(const void* d0, const void* d1, int N, int H, int W, float* dx, int mode, void* stream);
+/* sigmoid(pixel_shuffle(c10)) (Unetmodel.py:147-148) and its adjoint; c10 planes have 64 channels, 4 used */
+int nsm_sigmoid_shuffle_fwd(const void* c0, const void* c1, int N, int h, int w, int mode, float* y, void* stream);
+int nsm_sigmoid_shuffle_bwd(const float* dy, const float* y, int N, int h, int w, int mode, void* d0, void* d1,
+                            void* stream);
+int nsm_pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int dgrad, int mode,
+                                void* plane0, void* plane1, void* stream);
+int nsm_pad_vector(const float* src, int n, int npad, float fill, int round_bf16, float* dst, void* stream);
+/* weight gradient dW = dz^T (*) x  (autograd of nn.Conv2d): tcgen05 GEMM over the pixel axis with split-K */
+size_t nsm_wgrad_workspace_bytes(int N, int H, int W, int Cout, int Cin, int ksize, int mode);
+int nsm_wgrad(const void* dz0, const void* dz1, const void* x0, const void* x1, int N, int H, int W, int Cout, int Cin,
+              int ksize, int mode, int Cout_real, int Cin_real, void* workspace, size_t workspace_bytes, float* dw,
+              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

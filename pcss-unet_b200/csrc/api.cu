@@ -10,6 +10,7 @@
 #include "conv_gemm.cuh"
 #include "nsm_common.cuh"
 #include "stream_kernels.cuh"
+#include "train_kernels.cuh"
 
 namespace nsm {
 const char* last_error();
@@ -478,6 +479,82 @@ int nsm_standardize(const float* x, float* y, long long S, int C, long long HW, 
 int nsm_perturb(const float* x, const float* noise, float* out, int count, long long B, int C, long long HW,
                 const float* stds, float std_factor, void* stream) {
   return perturb(x, noise, out, count, B, C, HW, stds, std_factor, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------- training stages
+static inline Planes mk(const void* a, const void* b) { return Planes{{const_cast<void*>(a), const_cast<void*>(b)}}; }
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+int nsm_bn_stats(const void* z0, const void* z1, long long P, int C, int mode, double* sums, void* stream) {
+  return bn_stats(mk(z0, z1), P, C, mode, sums, S(stream));
+}
+int nsm_bn_finalize(const double* sums, long long P, int C, const float* gamma, const float* beta, float eps,
+                    float momentum, int updates, float* running_mean, float* running_var, float* scale, float* shift,
+                    float* save_mean, float* save_invstd, void* stream) {
+  return bn_finalize(sums, P, C, gamma, beta, eps, momentum, updates, running_mean, running_var, scale, shift, save_mean,
+                     save_invstd, S(stream));
+}
+int nsm_bn_act(const void* z0, const void* z1, int N, int H, int W, int C, int mode, const float* scale,
+               const float* shift, const float* mask, int lrelu, const void* res0, const void* res1, void* out0,
+               void* out1, void* pool0, void* pool1, void* stream) {
+  BnActParams p;
+  p.z = mk(z0, z1); p.out = mk(out0, out1); p.residual = mk(res0, res1); p.pool = mk(pool0, pool1);
+  p.N = N; p.H = H; p.W = W; p.C = C; p.fmt = mode; p.scale = scale; p.shift = shift; p.mask = mask; p.lrelu = lrelu;
+  return bn_act(p, S(stream));
+}
+int nsm_bn_bwd(const void* dy0, const void* dy1, const void* z0, const void* z1, int N, int H, int W, int C, int mode,
+               const float* scale, const float* shift, const float* mask, const float* mean, const float* invstd,
+               int lrelu, double* sums, void* dz0, void* dz1, float* dgamma, float* dbeta, float* dbias, void* stream) {
+  BnBwdParams p;
+  p.dy = mk(dy0, dy1); p.z = mk(z0, z1); p.dz = mk(dz0, dz1);
+  p.N = N; p.H = H; p.W = W; p.C = C; p.fmt = mode; p.scale = scale; p.shift = shift; p.mask = mask; p.mean = mean;
+  p.invstd = invstd; p.lrelu = lrelu; p.sums = sums; p.dbias = sums + 2 * C;
+  NSM_TRY(bn_bwd_reduce(p, S(stream)));
+  NSM_TRY(bn_bwd_apply(p, S(stream)));
+  return bn_bwd_finalize(sums, sums + 2 * C, C, mode == NSM_MODE_BF16, dgamma, dbeta, dbias, S(stream));
+}
+int nsm_pool_bwd_add(const void* a0, const void* a1, const void* dp0, const void* dp1, void* out0, void* out1, int N,
+                     int H, int W, int C, int mode, void* stream) {
+  return pool_bwd_add(mk(a0, a1), mk(dp0, dp1), mk(out0, out1), N, H, W, C, mode, S(stream));
+}
+int nsm_planes_add(const void* a0, const void* a1, const void* b0, const void* b1, void* out0, void* out1,
+                   long long numel, int mode, void* stream) {
+  return planes_add(mk(a0, a1), mk(b0, b1), mk(out0, out1), numel, mode, S(stream));
+}
+int nsm_bilinear_bwd(const void* dout0, const void* dout1, int N, int ho, int wo, int C, void* din0, void* din1, int hi,
+                     int wi, int mode, void* stream) {
+  return bilinear_bwd(mk(dout0, dout1), N, ho, wo, C, mk(din0, din1), hi, wi, mode, S(stream));
+}
+int nsm_train_input_prep(const float* x, int N, int Hin, int Win, void* out0, void* out1, int mode, void* stream) {
+  return train_input_prep(x, N, Hin, Win, mk(out0, out1), mode, S(stream));
+}
+int nsm_train_input_grad(const void* d0, const void* d1, int N, int H, int W, float* dx, int mode, void* stream) {
+  return train_input_grad(mk(d0, d1), N, H, W, dx, mode, S(stream));
+}
+int nsm_sigmoid_shuffle_fwd(const void* c0, const void* c1, int N, int h, int w, int mode, float* y, void* stream) {
+  return sigmoid_shuffle_fwd(mk(c0, c1), N, h, w, mode, y, S(stream));
+}
+int nsm_sigmoid_shuffle_bwd(const float* dy, const float* y, int N, int h, int w, int mode, void* d0, void* d1,
+                            void* stream) {
+  return sigmoid_shuffle_bwd(dy, y, N, h, w, mode, mk(d0, d1), S(stream));
+}
+int nsm_pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int dgrad, int mode,
+                                void* plane0, void* plane1, void* stream) {
+  return pack_conv_weight_padded(w, Cout, Cin, ksize, CoutP, CinP, dgrad, mode, plane0, plane1, S(stream));
+}
+int nsm_pad_vector(const float* src, int n, int npad, float fill, int round_bf16, float* dst, void* stream) {
+  return pad_vector(src, n, npad, fill, round_bf16, dst, S(stream));
+}
+size_t nsm_wgrad_workspace_bytes(int N, int H, int W, int Cout, int Cin, int ksize, int mode) {
+  WgradShape s = {N, H, W, Cout, Cin, ksize * ksize, mode};
+  return wgrad_workspace_bytes(s);
+}
+int nsm_wgrad(const void* dz0, const void* dz1, const void* x0, const void* x1, int N, int H, int W, int Cout, int Cin,
+              int ksize, int mode, int Cout_real, int Cin_real, void* workspace, size_t workspace_bytes, float* dw,
+              void* stream) {
+  WgradShape s = {N, H, W, Cout, Cin, ksize * ksize, mode};
+  return wgrad_launch(s, mk(dz0, dz1), mk(x0, x1), workspace, workspace_bytes, Cout_real, Cin_real,
+                      mode == NSM_MODE_BF16, dw, S(stream));
 }
 
 }  // extern "C"

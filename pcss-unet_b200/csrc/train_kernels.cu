@@ -1,0 +1,724 @@
+// Streaming kernels of the training path (see train_kernels.cuh).  NHWC planes, 8 channels (16 bytes) per thread,
+// per-channel reductions: fp32 in registers over short runs -> fp64 per thread -> shared memory -> one fp64 atomic per
+// channel and block.
+#include <stdio.h>
+
+#include "nsm_common.cuh"
+#include "train_kernels.cuh"
+
+namespace nsm {
+
+#define NSM_CHECK_LAUNCH(name)                                             \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) {                                              \
+      set_error("%s launch failed: %s", name, cudaGetErrorString(e__));    \
+      return 1;                                                            \
+    }                                                                      \
+  } while (0)
+
+static inline int grid_for(long long work, int block, int cap = 148 * 16) {
+  long long g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return int(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 8-channel plane access
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const Planes& p, size_t elem, int fmt, float* v) {
+  const uint4 hv = ldg16(reinterpret_cast<const uint8_t*>(p.p[0]) + elem * 2);
+  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = hi_lo_to_f32(hw[e], fmt);
+    v[2 * e + 1] = hi_hi_to_f32(hw[e], fmt);
+  }
+  if (fmt != kFmtBf16) {
+    const uint4 lv = ldg16(reinterpret_cast<const uint8_t*>(p.p[1]) + elem * 2);
+    const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] += lo_lo_to_f32(lw[e], fmt);
+      v[2 * e + 1] += lo_hi_to_f32(lw[e], fmt);
+    }
+  }
+}
+__device__ __forceinline__ void store8(const Planes& p, size_t elem, int fmt, const float* v) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    hw[e] = pack_hi(v[2 * e], v[2 * e + 1], fmt);
+    lw[e] = pack_lo_resid(v[2 * e], v[2 * e + 1], hw[e], fmt);
+  }
+  stg16(reinterpret_cast<uint8_t*>(p.p[0]) + elem * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+  if (fmt != kFmtBf16) stg16(reinterpret_cast<uint8_t*>(p.p[1]) + elem * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+}
+
+// Block-level per-channel reduction of NV value sets; thread t owns channel group (t % groups), 256 threads.
+template <int NV>
+__device__ __forceinline__ void block_channel_reduce(const double (&acc)[NV][8], int C, double* out) {
+  __shared__ double red[256][NV * 8 + 1];
+  const int tid = threadIdx.x, groups = C / 8, lanes = 256 / groups;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[tid][v * 8 + e] = acc[v][e];
+  __syncthreads();
+  for (int i = tid; i < NV * C; i += 256) {
+    const int v = i / C, c = i % C;
+    double s = 0.0;
+    for (int l = 0; l < lanes; ++l) s += red[l * groups + (c >> 3)][v * 8 + (c & 7)];
+    if (s != 0.0) atomicAdd(&out[v * C + c], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_kernel(const Planes z, long long P, int C, int fmt, double* sums) {
+  const int groups = C / 8, lanes = 256 / groups;
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  double acc[2][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.0;
+  const long long stride = (long long)gridDim.x * lanes;
+  long long p = (long long)blockIdx.x * lanes + lane;
+  while (p < P) {
+    float fs[8], fq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) fs[e] = fq[e] = 0.f;
+    for (int it = 0; it < 16 && p < P; ++it, p += stride) {
+      float v[8];
+      load8(z, (size_t)p * C + cg * 8, fmt, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        fs[e] += v[e];
+        fq[e] = fmaf(v[e], v[e], fq[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += double(fs[e]);
+      acc[1][e] += double(fq[e]);
+    }
+  }
+  block_channel_reduce<2>(acc, C, sums);
+}
+
+static int check_c(const char* who, int C) {
+  if (C % 8 || C < 8 || (256 % (C / 8)) || C > 2048) {
+    set_error("%s: unsupported channel count %d", who, C);
+    return 1;
+  }
+  return 0;
+}
+
+int bn_stats(const Planes& z, long long P, int C, int fmt, double* sums, cudaStream_t st) {
+  if (check_c("bn_stats", C)) return 1;
+  const int lanes = 256 / (C / 8);
+  bn_stats_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(z, P, C, fmt, sums);
+  NSM_CHECK_LAUNCH("bn_stats");
+  return 0;
+}
+
+__global__ void bn_finalize_kernel(const double* sums, long long P, int C, const float* gamma, const float* beta,
+                                   float eps, float momentum, int updates, float* running_mean, float* running_var,
+                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = double(P);
+  const double mean = sums[c] / n;
+  double var = sums[C + c] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = 1.0f / sqrtf(float(var) + eps);
+  const float s = gamma[c] * invstd;
+  scale[c] = s;
+  shift[c] = beta[c] - float(mean) * s;
+  if (save_mean) save_mean[c] = float(mean);
+  if (save_invstd) save_invstd[c] = invstd;
+  if (running_mean) {
+    const float unbiased = float(P > 1 ? var * n / (n - 1.0) : var);
+    float rm = running_mean[c], rv = running_var[c];
+    for (int u = 0; u < updates; ++u) {
+      rm = (1.f - momentum) * rm + momentum * float(mean);
+      rv = (1.f - momentum) * rv + momentum * unbiased;
+    }
+    running_mean[c] = rm;
+    running_var[c] = rv;
+  }
+}
+
+int bn_finalize(const double* sums, long long P, int C, const float* gamma, const float* beta, float eps,
+                float momentum, int updates, float* running_mean, float* running_var, float* scale, float* shift,
+                float* save_mean, float* save_invstd, cudaStream_t st) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, updates, running_mean,
+                                                      running_var, scale, shift, save_mean, save_invstd);
+  NSM_CHECK_LAUNCH("bn_finalize");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply + LeakyReLU + Dropout2d mask (+ residual, + AvgPool2d(2))
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bn_act8(float* v, const BnActParams& p, int n, int c0, bool rb) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float t = fmaf(v[e], __ldg(p.scale + c0 + e), __ldg(p.shift + c0 + e));
+    if (rb) t = rbf(t);
+    if (p.lrelu) {
+      t = lrelu02(t);
+      if (rb) t = rbf(t);
+    }
+    if (p.mask) {
+      t *= __ldg(p.mask + (size_t)n * p.C + c0 + e);
+      if (rb) t = rbf(t);
+    }
+    v[e] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
+  const int cgs = p.C / 8;
+  const bool rb = p.fmt == kFmtBf16;
+  const long long total = (long long)p.N * p.H * p.W * cgs;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i % cgs);
+    const long long pix = i / cgs;
+    const int n = int(pix / ((long long)p.H * p.W));
+    float v[8];
+    load8(p.z, (size_t)pix * p.C + cg * 8, p.fmt, v);
+    bn_act8(v, p, n, cg * 8, rb);
+    if (p.residual.p[0]) {
+      float r[8];
+      load8(p.residual, (size_t)pix * p.C + cg * 8, p.fmt, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = rb ? rbf(v[e] + r[e]) : v[e] + r[e];
+    }
+    store8(p.out, (size_t)pix * p.C + cg * 8, p.fmt, v);
+  }
+}
+
+// quad variant: one thread = 2x2 pixels x 8 channels, writes the activation and its 2x2 average
+__global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
+  const int cgs = p.C / 8;
+  const bool rb = p.fmt == kFmtBf16;
+  const int Hq = (p.H + 1) / 2, Wq = (p.W + 1) / 2, Hp = p.H / 2, Wp = p.W / 2;
+  const long long total = (long long)p.N * Hq * Wq * cgs;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i % cgs);
+    long long t = i / cgs;
+    const int qx = int(t % Wq);
+    t /= Wq;
+    const int qy = int(t % Hq);
+    const int n = int(t / Hq);
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int y = 2 * qy + (k >> 1), x = 2 * qx + (k & 1);
+      if (y < p.H && x < p.W) {
+        const size_t pix = ((size_t)n * p.H + y) * p.W + x;
+        float v[8];
+        load8(p.z, pix * p.C + cg * 8, p.fmt, v);
+        bn_act8(v, p, n, cg * 8, rb);
+        store8(p.out, pix * p.C + cg * 8, p.fmt, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += v[e];
+      }
+    }
+    if (qy < Hp && qx < Wp) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = rb ? rbf(s[e] * 0.25f) : s[e] * 0.25f;
+      store8(p.pool, (((size_t)n * Hp + qy) * Wp + qx) * p.C + cg * 8, p.fmt, s);
+    }
+  }
+}
+
+int bn_act(const BnActParams& p, cudaStream_t st) {
+  if (check_c("bn_act", p.C)) return 1;
+  if (p.pool.p[0]) {
+    if (p.residual.p[0]) {
+      set_error("bn_act: pool and residual are not combined in this network");
+      return 1;
+    }
+    const long long total = (long long)p.N * ((p.H + 1) / 2) * ((p.W + 1) / 2) * (p.C / 8);
+    bn_act_pool_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  } else {
+    const long long total = (long long)p.N * p.H * p.W * (p.C / 8);
+    bn_act_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  }
+  NSM_CHECK_LAUNCH("bn_act");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm backward
+// ------------------------------------------------------------------------------------------------
+// g = dy * mask * LeakyReLU'(z*scale + shift), with the bf16 rounding points of autograd under autocast
+__device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, size_t elem, int n, int c0, bool rb, float* g,
+                                          float* xhat) {
+  float dy[8], z[8];
+  load8(p.dy, elem, p.fmt, dy);
+  load8(p.z, elem, p.fmt, z);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float t = dy[e];
+    if (p.mask) {
+      t *= __ldg(p.mask + (size_t)n * p.C + c0 + e);
+      if (rb) t = rbf(t);
+    }
+    if (p.lrelu) {
+      float y = fmaf(z[e], __ldg(p.scale + c0 + e), __ldg(p.shift + c0 + e));
+      if (rb) y = rbf(y);
+      if (!(y > 0.f)) {
+        t *= 0.2f;
+        if (rb) t = rbf(t);
+      }
+    }
+    g[e] = t;
+    xhat[e] = (z[e] - __ldg(p.mean + c0 + e)) * __ldg(p.invstd + c0 + e);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
+  const int groups = p.C / 8, lanes = 256 / groups;
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const bool rb = p.fmt == kFmtBf16;
+  const long long P = (long long)p.N * p.H * p.W, HW = (long long)p.H * p.W;
+  double acc[2][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.0;
+  const long long stride = (long long)gridDim.x * lanes;
+  long long px = (long long)blockIdx.x * lanes + lane;
+  while (px < P) {
+    float fs[8], fq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) fs[e] = fq[e] = 0.f;
+    for (int it = 0; it < 16 && px < P; ++it, px += stride) {
+      float g[8], xh[8];
+      bn_bwd_g8(p, (size_t)px * p.C + cg * 8, int(px / HW), cg * 8, rb, g, xh);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        fs[e] += g[e];
+        fq[e] = fmaf(g[e], xh[e], fq[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += double(fs[e]);
+      acc[1][e] += double(fq[e]);
+    }
+  }
+  block_channel_reduce<2>(acc, p.C, p.sums);
+}
+
+int bn_bwd_reduce(const BnBwdParams& p, cudaStream_t st) {
+  if (check_c("bn_bwd_reduce", p.C)) return 1;
+  const long long P = (long long)p.N * p.H * p.W;
+  const int lanes = 256 / (p.C / 8);
+  bn_bwd_reduce_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(p);
+  NSM_CHECK_LAUNCH("bn_bwd_reduce");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+  const int groups = p.C / 8, lanes = 256 / groups;
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const bool rb = p.fmt == kFmtBf16;
+  const long long P = (long long)p.N * p.H * p.W, HW = (long long)p.H * p.W;
+  float mg[8], mgx[8], sc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mg[e] = float(p.sums[cg * 8 + e] / double(P));
+    mgx[e] = float(p.sums[p.C + cg * 8 + e] / double(P));
+    sc[e] = __ldg(p.scale + cg * 8 + e);
+  }
+  double acc[1][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[0][e] = 0.0;
+  const long long stride = (long long)gridDim.x * lanes;
+  long long px = (long long)blockIdx.x * lanes + lane;
+  while (px < P) {
+    float fs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) fs[e] = 0.f;
+    for (int it = 0; it < 16 && px < P; ++it, px += stride) {
+      float g[8], xh[8], dz[8];
+      const size_t elem = (size_t)px * p.C + cg * 8;
+      bn_bwd_g8(p, elem, int(px / HW), cg * 8, rb, g, xh);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = sc[e] * (g[e] - mg[e] - xh[e] * mgx[e]);
+        if (rb) t = rbf(t);
+        dz[e] = t;
+        fs[e] += t;
+      }
+      store8(p.dz, elem, p.fmt, dz);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[0][e] += double(fs[e]);
+  }
+  if (p.dbias) block_channel_reduce<1>(acc, p.C, p.dbias);
+}
+
+int bn_bwd_apply(const BnBwdParams& p, cudaStream_t st) {
+  if (check_c("bn_bwd_apply", p.C)) return 1;
+  const long long P = (long long)p.N * p.H * p.W;
+  const int lanes = 256 / (p.C / 8);
+  bn_bwd_apply_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(p);
+  NSM_CHECK_LAUNCH("bn_bwd_apply");
+  return 0;
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* sums, const double* dbias, int C, int rb, float* dgamma,
+                                       float* dbeta, float* dbias_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  // invstd is already folded into xhat: dgamma = sum g * xhat, dbeta = sum g
+  dgamma[c] = float(sums[C + c]);
+  dbeta[c] = float(sums[c]);
+  if (dbias_out) {
+    const float v = dbias ? float(dbias[c]) : 0.f;
+    dbias_out[c] = rb ? rbf(v) : v;
+  }
+}
+int bn_bwd_finalize(const double* sums, const double* dbias, int C, int round_bf16, float* dgamma, float* dbeta,
+                    float* dbias_out, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dbias, C, round_bf16, dgamma, dbeta, dbias_out);
+  NSM_CHECK_LAUNCH("bn_bwd_finalize");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AvgPool2d(2) adjoint (+ skip gradient), plane add, bilinear adjoint
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_bwd_add_kernel(const Planes a, const Planes dpool, const Planes out, int N,
+                                                           int H, int W, int C, int fmt) {
+  const int cgs = C / 8, Hp = H / 2, Wp = W / 2;
+  const bool rb = fmt == kFmtBf16;
+  const long long total = (long long)N * H * W * cgs;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i % cgs);
+    long long t = i / cgs;
+    const int x = int(t % W);
+    t /= W;
+    const int y = int(t % H);
+    const int n = int(t / H);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (a.p[0]) load8(a, (size_t)(i / cgs) * C + cg * 8, fmt, v);
+    if ((y >> 1) < Hp && (x >> 1) < Wp) {
+      float d[8];
+      load8(dpool, (((size_t)n * Hp + (y >> 1)) * Wp + (x >> 1)) * C + cg * 8, fmt, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = rb ? rbf(v[e] + d[e] * 0.25f) : v[e] + d[e] * 0.25f;
+    }
+    store8(out, (size_t)(i / cgs) * C + cg * 8, fmt, v);
+  }
+}
+int pool_bwd_add(const Planes& a, const Planes& dpool, const Planes& out, int N, int H, int W, int C, int fmt,
+                 cudaStream_t st) {
+  if (check_c("pool_bwd_add", C)) return 1;
+  pool_bwd_add_kernel<<<grid_for((long long)N * H * W * (C / 8), 256), 256, 0, st>>>(a, dpool, out, N, H, W, C, fmt);
+  NSM_CHECK_LAUNCH("pool_bwd_add");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) planes_add_kernel(const Planes a, const Planes b, const Planes out,
+                                                         long long n8, int fmt) {
+  const bool rb = fmt == kFmtBf16;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    float x[8], y[8];
+    load8(a, (size_t)i * 8, fmt, x);
+    load8(b, (size_t)i * 8, fmt, y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = rb ? rbf(x[e] + y[e]) : x[e] + y[e];
+    store8(out, (size_t)i * 8, fmt, x);
+  }
+}
+int planes_add(const Planes& a, const Planes& b, const Planes& out, long long numel, int fmt, cudaStream_t st) {
+  if (numel % 8) {
+    set_error("planes_add: numel %lld not a multiple of 8", numel);
+    return 1;
+  }
+  planes_add_kernel<<<grid_for(numel / 8, 256), 256, 0, st>>>(a, b, out, numel / 8, fmt);
+  NSM_CHECK_LAUNCH("planes_add");
+  return 0;
+}
+
+// forward weights of output index `dst` of an align_corners resize in_size -> out_size (same arithmetic as
+// stream_kernels.cu / ATen)
+struct Lerp2 {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Lerp2 lerp_of(int dst, int in_size, int out_size) {
+  const float scale = out_size > 1 ? float(in_size - 1) / float(out_size - 1) : 0.f;
+  const float src = scale * float(dst);
+  int i0 = int(src);
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  Lerp2 l;
+  l.i0 = i0;
+  l.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  float lam = fminf(fmaxf(src - float(i0), 0.f), 1.f);
+  l.w1 = lam;
+  l.w0 = 1.f - lam;
+  return l;
+}
+// range of output indices whose interpolation may touch input index r
+__device__ __forceinline__ void touch_range(int r, int in_size, int out_size, int& lo, int& hi) {
+  if (out_size <= 1 || in_size <= 1) {
+    lo = 0;
+    hi = out_size - 1;
+    return;
+  }
+  const float inv = float(out_size - 1) / float(in_size - 1);
+  lo = int(floorf(float(r - 1) * inv)) - 1;
+  hi = int(ceilf(float(r + 1) * inv)) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out_size - 1) hi = out_size - 1;
+}
+
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const Planes dout, int N, int ho, int wo, int C,
+                                                           const Planes din, int hi, int wi, int fmt) {
+  const int cgs = C / 8;
+  const long long total = (long long)N * hi * wi * cgs;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i % cgs);
+    long long t = i / cgs;
+    const int q = int(t % wi);
+    t /= wi;
+    const int r = int(t % hi);
+    const int n = int(t / hi);
+    int ylo, yhi, xlo, xhi;
+    touch_range(r, hi, ho, ylo, yhi);
+    touch_range(q, wi, wo, xlo, xhi);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      const Lerp2 ly = lerp_of(y, hi, ho);
+      const float wy = (ly.i0 == r ? ly.w0 : 0.f) + (ly.i1 == r ? ly.w1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = xlo; x <= xhi; ++x) {
+        const Lerp2 lx = lerp_of(x, wi, wo);
+        const float wx = (lx.i0 == q ? lx.w0 : 0.f) + (lx.i1 == q ? lx.w1 : 0.f);
+        if (wx == 0.f) continue;
+        float d[8];
+        load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, fmt, d);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, d[e], acc[e]);
+      }
+    }
+    store8(din, (size_t)(i / cgs) * C + cg * 8, fmt, acc);
+  }
+}
+int bilinear_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,
+                 cudaStream_t st) {
+  if (check_c("bilinear_bwd", C)) return 1;
+  bilinear_bwd_kernel<<<grid_for((long long)N * hi * wi * (C / 8), 256), 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi,
+                                                                                         fmt);
+  NSM_CHECK_LAUNCH("bilinear_bwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// network input / output stages
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) train_input_prep_kernel(const float* __restrict__ x, int N, int Hin, int Win,
+                                                               const Planes out, int fmt) {
+  const int H = Hin - (Hin & 1), W = Win - (Win & 1), h = H / 2, w = W / 2;
+  const bool resize = (Hin & 1) || (Win & 1);
+  const bool rb = fmt == kFmtBf16;
+  // one thread = one output pixel x one 8-channel group of the 64 padded channels (groups 2..7 are zero)
+  const long long total = (long long)N * h * w * 8;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i & 7);
+    const long long pix = i >> 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (cg < 2) {
+      const int px = int(pix % w);
+      const long long t = pix / w;
+      const int py = int(t % h);
+      const int n = int(t / h);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = cg * 8 + e;           // un-shuffled channel = c*4 + dy*2 + dx
+        const int c = ch >> 2, dy = (ch >> 1) & 1, dx = ch & 1;
+        const int Y = 2 * py + dy, X = 2 * px + dx;
+        const float* base = x + ((size_t)n * 4 + c) * Hin * Win;
+        float val;
+        if (!resize) {
+          val = base[(size_t)Y * Win + X];
+        } else {
+          const Lerp2 ly = lerp_of(Y, Hin, H), lx = lerp_of(X, Win, W);
+          const float v00 = base[(size_t)ly.i0 * Win + lx.i0], v01 = base[(size_t)ly.i0 * Win + lx.i1];
+          const float v10 = base[(size_t)ly.i1 * Win + lx.i0], v11 = base[(size_t)ly.i1 * Win + lx.i1];
+          val = ly.w0 * (lx.w0 * v00 + lx.w1 * v01) + ly.w1 * (lx.w0 * v10 + lx.w1 * v11);
+        }
+        v[e] = rb ? rbf(val) : val;
+      }
+    }
+    store8(out, (size_t)pix * 64 + cg * 8, fmt, v);
+  }
+}
+int train_input_prep(const float* x, int N, int Hin, int Win, const Planes& out, int fmt, cudaStream_t st) {
+  const long long total = (long long)N * (Hin / 2) * (Win / 2) * 8;
+  train_input_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, N, Hin, Win, out, fmt);
+  NSM_CHECK_LAUNCH("train_input_prep");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) train_input_grad_kernel(const Planes dx16, int N, int H, int W, float* dx,
+                                                               int fmt) {
+  const int h = H / 2, w = W / 2;
+  const long long total = (long long)N * h * w * 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i & 1);
+    const long long pix = i >> 1;
+    const int px = int(pix % w);
+    const long long t = pix / w;
+    const int py = int(t % h);
+    const int n = int(t / h);
+    float v[8];
+    load8(dx16, (size_t)pix * 64 + cg * 8, fmt, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = cg * 8 + e;
+      const int c = ch >> 2, dy = (ch >> 1) & 1, dxx = ch & 1;
+      dx[(((size_t)n * 4 + c) * H + 2 * py + dy) * W + 2 * px + dxx] = v[e];
+    }
+  }
+}
+int train_input_grad(const Planes& dx16, int N, int H, int W, float* dx, int fmt, cudaStream_t st) {
+  if ((H & 1) || (W & 1)) {
+    set_error("train_input_grad: odd input sizes are not supported for the input gradient");
+    return 1;
+  }
+  train_input_grad_kernel<<<grid_for((long long)N * (H / 2) * (W / 2) * 2, 256), 256, 0, st>>>(dx16, N, H, W, dx, fmt);
+  NSM_CHECK_LAUNCH("train_input_grad");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) sigmoid_shuffle_fwd_kernel(const Planes c10, int N, int h, int w, int fmt,
+                                                                  float* y) {
+  const bool rb = fmt == kFmtBf16;
+  const long long total = (long long)N * h * w;
+  const int W = 2 * w, H = 2 * h;
+  for (long long pix = blockIdx.x * 256LL + threadIdx.x; pix < total; pix += (long long)gridDim.x * 256) {
+    float v[8];
+    load8(c10, (size_t)pix * 64, fmt, v);
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float s = 1.f / (1.f + expf(-v[k]));
+      r[k] = rb ? rbf(s) : s;
+    }
+    const int x = int(pix % w);
+    const long long t = pix / w;
+    const int yy = int(t % h);
+    const long long n = t / h;
+    float* o = y + ((size_t)n * H + 2 * yy) * W + 2 * x;
+    *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
+    *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
+  }
+}
+int sigmoid_shuffle_fwd(const Planes& c10, int N, int h, int w, int fmt, float* y, cudaStream_t st) {
+  sigmoid_shuffle_fwd_kernel<<<grid_for((long long)N * h * w, 256), 256, 0, st>>>(c10, N, h, w, fmt, y);
+  NSM_CHECK_LAUNCH("sigmoid_shuffle_fwd");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) sigmoid_shuffle_bwd_kernel(const float* __restrict__ dy,
+                                                                  const float* __restrict__ y, int N, int h, int w,
+                                                                  int fmt, const Planes dc10) {
+  const bool rb = fmt == kFmtBf16;
+  const long long total = (long long)N * h * w * 8;
+  const int W = 2 * w, H = 2 * h;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i & 7);
+    const long long pix = i >> 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (cg == 0) {
+      const int x = int(pix % w);
+      const long long t = pix / w;
+      const int yy = int(t % h);
+      const long long n = t / h;
+      const size_t o = ((size_t)n * H + 2 * yy) * W + 2 * x;
+      const float2 g0 = *reinterpret_cast<const float2*>(dy + o), g1 = *reinterpret_cast<const float2*>(dy + o + W);
+      const float2 s0 = *reinterpret_cast<const float2*>(y + o), s1 = *reinterpret_cast<const float2*>(y + o + W);
+      const float g[4] = {g0.x, g0.y, g1.x, g1.y}, s[4] = {s0.x, s0.y, s1.x, s1.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float gg = rb ? rbf(g[k]) : g[k];
+        const float d = gg * ((1.f - s[k]) * s[k]);   // sigmoid_backward: grad * (1 - y) * y
+        v[k] = rb ? rbf(d) : d;
+      }
+    }
+    store8(dc10, (size_t)pix * 64 + cg * 8, fmt, v);
+  }
+}
+int sigmoid_shuffle_bwd(const float* dy, const float* y, int N, int h, int w, int fmt, const Planes& dc10,
+                        cudaStream_t st) {
+  sigmoid_shuffle_bwd_kernel<<<grid_for((long long)N * h * w * 8, 256), 256, 0, st>>>(dy, y, N, h, w, fmt, dc10);
+  NSM_CHECK_LAUNCH("sigmoid_shuffle_bwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// padded packing helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_padded_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int CoutP,
+                                               int CinP, int flip_t, int fmt, unsigned short* __restrict__ hi,
+                                               unsigned short* __restrict__ lo) {
+  const long long total = (long long)CoutP * CinP * taps;
+  const int inner = flip_t ? CoutP : CinP;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = int(i % inner);
+    long long t = i / inner;
+    const int tap = int(t % taps);
+    const int row = int(t / taps);
+    int co, ci, stap;
+    if (!flip_t) {
+      co = row; ci = col; stap = tap;
+    } else {
+      ci = row; co = col; stap = taps - 1 - tap;
+    }
+    const float v = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * taps + stap] : 0.f;
+    unsigned short h, l;
+    split_fmt(v, fmt, h, l);
+    hi[i] = h;
+    if (fmt != kFmtBf16) lo[i] = l;
+  }
+}
+int pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int flip_transpose,
+                            int fmt, void* hi, void* lo, cudaStream_t st) {
+  const int taps = ksize * ksize;
+  const long long total = (long long)CoutP * CinP * taps;
+  pack_conv_weight_padded_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, Cout, Cin, taps, CoutP, CinP, flip_transpose,
+                                                                       fmt, (unsigned short*)hi, (unsigned short*)lo);
+  NSM_CHECK_LAUNCH("pack_conv_weight_padded");
+  return 0;
+}
+
+__global__ void pad_vector_kernel(const float* src, int n, int npad, float fill, int rb, float* dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npad) dst[i] = i < n ? (rb ? rbf(src[i]) : src[i]) : fill;
+}
+int pad_vector(const float* src, int n, int npad, float fill, int round_bf16, float* dst, cudaStream_t st) {
+  pad_vector_kernel<<<(npad + 127) / 128, 128, 0, st>>>(src, n, npad, fill, round_bf16, dst);
+  NSM_CHECK_LAUNCH("pad_vector");
+  return 0;
+}
+
+}  // namespace nsm

@@ -71,13 +71,41 @@ def _declare(lib):
                                 c_float, c_void_p]
     lib.nsm_profile_enable.argtypes = [c_int]
     lib.nsm_profile_read.argtypes = [c_char_p, c_size_t]
+    vp, ll, fp = c_void_p, c_longlong, c_float
+    lib.nsm_bn_stats.argtypes = [vp, vp, ll, c_int, c_int, vp, vp]
+    lib.nsm_bn_finalize.argtypes = [vp, ll, c_int, vp, vp, fp, fp, c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.nsm_bn_act.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.nsm_bn_bwd.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, c_int, vp, vp, vp,
+                               vp, vp, vp, vp]
+    lib.nsm_pool_bwd_add.argtypes = [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
+    lib.nsm_planes_add.argtypes = [vp, vp, vp, vp, vp, vp, ll, c_int, vp]
+    lib.nsm_bilinear_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, vp]
+    lib.nsm_train_input_prep.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, vp]
+    lib.nsm_train_input_grad.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_int, vp]
+    lib.nsm_sigmoid_shuffle_fwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp]
+    lib.nsm_sigmoid_shuffle_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp]
+    lib.nsm_pack_conv_weight_padded.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp]
+    lib.nsm_pad_vector.argtypes = [vp, c_int, c_int, fp, c_int, vp, vp]
+    lib.nsm_wgrad_workspace_bytes.restype = c_size_t
+    lib.nsm_wgrad_workspace_bytes.argtypes = [c_int] * 7
+    lib.nsm_wgrad.argtypes = [vp, vp, vp, vp] + [c_int] * 9 + [vp, c_size_t, vp, vp]
+    for name in TRAIN_EXPORTS:
+        if name != "nsm_wgrad_workspace_bytes":
+            getattr(lib, name).restype = c_int
     for name in ("nsm_profile_enable", "nsm_profile_read", "nsm_unet_pack", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
                  "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match",
                  "nsm_l1_loss_fwd_bwd", "nsm_channel_sums", "nsm_standardize", "nsm_perturb"):
         getattr(lib, name).restype = c_int
 
 
-EXPORTS = [
+TRAIN_EXPORTS = [
+    "nsm_bn_stats", "nsm_bn_finalize", "nsm_bn_act", "nsm_bn_bwd", "nsm_pool_bwd_add", "nsm_planes_add",
+    "nsm_bilinear_bwd", "nsm_train_input_prep", "nsm_train_input_grad", "nsm_sigmoid_shuffle_fwd",
+    "nsm_sigmoid_shuffle_bwd", "nsm_pack_conv_weight_padded", "nsm_pad_vector", "nsm_wgrad_workspace_bytes",
+    "nsm_wgrad",
+]
+
+EXPORTS = TRAIN_EXPORTS + [
     "nsm_last_error", "nsm_version", "nsm_check_device", "nsm_unet_packed_bytes", "nsm_unet_pack",
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
@@ -311,3 +339,151 @@ def perturb(x, noise, stds, std_factor):
     check(lib().nsm_perturb(x.data_ptr(), noise.data_ptr(), out.data_ptr(), count, B, C, HW, stds.data_ptr(),
                             float(std_factor), stream_ptr()), "nsm_perturb")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training-stage wrappers (all arithmetic in libnsm_b200.so; torch only allocates)
+# ---------------------------------------------------------------------------------------------------------------
+
+def _pp(t):
+    """(plane0 ptr, plane1 ptr) of a PlaneTensor or (0, 0) for None."""
+    return (0, 0) if t is None else (ptr(t.p0), ptr(t.p1))
+
+
+def bn_stats(z: PlaneTensor):
+    N, C, H, W = z.shape
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=z.p0.device)
+    check(lib().nsm_bn_stats(*_pp(z), N * H * W, C, z.mode, sums.data_ptr(), stream_ptr()), "nsm_bn_stats")
+    return sums
+
+
+def bn_finalize(sums, P, gamma, beta, running_mean, running_var, updates=1, eps=1e-5, momentum=0.1):
+    C = gamma.numel()
+    dev = gamma.device
+    out = torch.empty(4, C, dtype=torch.float32, device=dev)   # scale, shift, mean, invstd
+    check(lib().nsm_bn_finalize(sums.data_ptr(), P, C, gamma.data_ptr(), beta.data_ptr(), eps, momentum, updates,
+                                ptr(running_mean), ptr(running_var), out[0].data_ptr(), out[1].data_ptr(),
+                                out[2].data_ptr(), out[3].data_ptr(), stream_ptr()), "nsm_bn_finalize")
+    return out
+
+
+def bn_act(z: PlaneTensor, scale, shift, mask=None, lrelu=True, residual: PlaneTensor = None, pool=False):
+    N, C, H, W = z.shape
+    dev = z.p0.device
+    out = PlaneTensor(N, C, H, W, z.mode, dev)
+    pl = PlaneTensor(N, C, H // 2, W // 2, z.mode, dev) if pool else None
+    check(lib().nsm_bn_act(*_pp(z), N, H, W, C, z.mode, scale.data_ptr(), shift.data_ptr(), ptr(mask), int(lrelu),
+                           *_pp(residual), *_pp(out), *_pp(pl), stream_ptr()), "nsm_bn_act")
+    return out, pl
+
+
+def bn_bwd(dy: PlaneTensor, z: PlaneTensor, scale, shift, mean, invstd, mask=None, lrelu=True, want_dbias=True):
+    """Returns (dz planes, dgamma[C], dbeta[C], dbias[C]|None)."""
+    N, C, H, W = z.shape
+    dev = z.p0.device
+    dz = PlaneTensor(N, C, H, W, z.mode, dev)
+    sums = torch.zeros(3 * C, dtype=torch.float64, device=dev)
+    g = torch.empty(3, C, dtype=torch.float32, device=dev)
+    check(lib().nsm_bn_bwd(*_pp(dy), *_pp(z), N, H, W, C, z.mode, scale.data_ptr(), shift.data_ptr(), ptr(mask),
+                           mean.data_ptr(), invstd.data_ptr(), int(lrelu), sums.data_ptr(), *_pp(dz),
+                           g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr() if want_dbias else 0, stream_ptr()),
+          "nsm_bn_bwd")
+    return dz, g[0], g[1], (g[2] if want_dbias else None)
+
+
+def pool_bwd_add(a: PlaneTensor, dpool: PlaneTensor, shape):
+    N, C, H, W = shape
+    out = PlaneTensor(N, C, H, W, dpool.mode, dpool.p0.device)
+    check(lib().nsm_pool_bwd_add(*_pp(a), *_pp(dpool), *_pp(out), N, H, W, C, dpool.mode, stream_ptr()),
+          "nsm_pool_bwd_add")
+    return out
+
+
+def planes_add(a: PlaneTensor, b: PlaneTensor):
+    out = PlaneTensor(*a.shape, a.mode, a.p0.device)
+    check(lib().nsm_planes_add(*_pp(a), *_pp(b), *_pp(out), a.p0.numel(), a.mode, stream_ptr()), "nsm_planes_add")
+    return out
+
+
+def bilinear_bwd(dout: PlaneTensor, hi, wi):
+    N, C, ho, wo = dout.shape
+    din = PlaneTensor(N, C, hi, wi, dout.mode, dout.p0.device)
+    check(lib().nsm_bilinear_bwd(*_pp(dout), N, ho, wo, C, *_pp(din), hi, wi, dout.mode, stream_ptr()),
+          "nsm_bilinear_bwd")
+    return din
+
+
+def upsample_match_bwd(dout: PlaneTensor, hs, ws):
+    """Adjoint of upsample_match: (hd, wd) -> [(2hs, 2ws) ->] (hs, ws)."""
+    _, _, hd, wd = dout.shape
+    if (hd, wd) != (2 * hs, 2 * ws):
+        dout = bilinear_bwd(dout, 2 * hs, 2 * ws)
+    return bilinear_bwd(dout, hs, ws)
+
+
+def train_input_prep(x, mode):
+    N, _, Hin, Win = x.shape
+    out = PlaneTensor(N, 64, (Hin - Hin % 2) // 2, (Win - Win % 2) // 2, mode, x.device)
+    check(lib().nsm_train_input_prep(x.data_ptr(), N, Hin, Win, *_pp(out), mode, stream_ptr()), "nsm_train_input_prep")
+    return out
+
+
+def train_input_grad(d: PlaneTensor, H, W):
+    N = d.shape[0]
+    dx = torch.empty(N, 4, H, W, dtype=torch.float32, device=d.p0.device)
+    check(lib().nsm_train_input_grad(*_pp(d), N, H, W, dx.data_ptr(), d.mode, stream_ptr()), "nsm_train_input_grad")
+    return dx
+
+
+def sigmoid_shuffle_fwd(c10: PlaneTensor):
+    N, _, h, w = c10.shape
+    y = torch.empty(N, 1, 2 * h, 2 * w, dtype=torch.float32, device=c10.p0.device)
+    check(lib().nsm_sigmoid_shuffle_fwd(*_pp(c10), N, h, w, c10.mode, y.data_ptr(), stream_ptr()),
+          "nsm_sigmoid_shuffle_fwd")
+    return y
+
+
+def sigmoid_shuffle_bwd(dy, y, mode):
+    N, _, H, W = y.shape
+    d = PlaneTensor(N, 64, H // 2, W // 2, mode, y.device)
+    dy = dy.to(torch.float32).contiguous()
+    check(lib().nsm_sigmoid_shuffle_bwd(dy.data_ptr(), y.data_ptr(), N, H // 2, W // 2, mode, *_pp(d), stream_ptr()),
+          "nsm_sigmoid_shuffle_bwd")
+    return d
+
+
+def pack_conv_weight_padded(w, mode, CoutP, CinP, dgrad=False):
+    Cout, Cin, k, _ = w.shape
+    w = w.detach().to(torch.float32).contiguous()
+    rows, inner = (CinP, CoutP) if dgrad else (CoutP, CinP)
+    p0 = torch.empty(rows, k * k, inner, dtype=torch.bfloat16, device=w.device)
+    p1 = torch.empty_like(p0) if mode != MODE_BF16 else None
+    check(lib().nsm_pack_conv_weight_padded(w.data_ptr(), Cout, Cin, k, CoutP, CinP, int(dgrad), mode, ptr(p0), ptr(p1),
+                                            stream_ptr()), "nsm_pack_conv_weight_padded")
+    return p0, p1
+
+
+def pad_vector(v, npad, fill=0.0, round_bf16=False):
+    v = v.detach().to(torch.float32).contiguous()
+    out = torch.empty(npad, dtype=torch.float32, device=v.device)
+    check(lib().nsm_pad_vector(v.data_ptr(), v.numel(), npad, fill, int(round_bf16), out.data_ptr(), stream_ptr()),
+          "nsm_pad_vector")
+    return out
+
+
+_wgrad_ws = {}
+
+
+def wgrad(dz: PlaneTensor, x: PlaneTensor, ksize, Cout_real, Cin_real):
+    """dW [Cout_real, Cin_real, k, k] fp32 = sum over pixels of dz (x) x (tap-shifted)."""
+    N, Cout, H, W = dz.shape
+    Cin = x.shape[1]
+    dev = dz.p0.device
+    need = lib().nsm_wgrad_workspace_bytes(N, H, W, Cout, Cin, ksize, dz.mode)
+    ws = _wgrad_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = _wgrad_ws[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+    dw = torch.empty(Cout_real, Cin_real, ksize, ksize, dtype=torch.float32, device=dev)
+    check(lib().nsm_wgrad(*_pp(dz), *_pp(x), N, H, W, Cout, Cin, ksize, dz.mode, Cout_real, Cin_real, ws.data_ptr(),
+                          ws.numel(), dw.data_ptr(), stream_ptr()), "nsm_wgrad")
+    return dw

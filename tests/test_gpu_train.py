@@ -1,0 +1,286 @@
+"""Training path parity (GPU): per-stage kernels against autograd of the same torch ops (oracle protocol of SURVEY 8c:
+tolerances asserted per fused stage on identical inputs) and the whole forward+backward step against the CPU oracle and
+the golden vectors produced by the unmodified reference (CustomLoss, Dropout2d masks replayed, checkpoint(conv5) quirk).
+
+Tolerances: fp32_train mode (hi+lo bf16 planes): outputs 1e-4 abs on [0,1], stage gradients rel-L2 1e-3;
+bf16 mode: stage gradients rel-L2 1e-2.  End-to-end gradients are reported next to the reference-vs-reference floor
+(1.2e-3 .. 2.5e-3 in fp32 from LeakyReLU mask flips, ~0.2 between bf16 and fp32)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+MODES = ["fp32_train", "bf16"]
+GTOL = {"fp32_train": 1e-3, "bf16": 1e-2}
+
+
+@pytest.fixture(scope="module")
+def nsm():
+    import nsm as _nsm
+    _nsm.require_device()
+    return _nsm
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def planes(nsm, x, mode):
+    return nsm.PlaneTensor.from_nchw(x.cuda(), mode)
+
+
+@pytest.mark.parametrize("mode_name", MODES)
+@pytest.mark.parametrize("shape", [(2, 64, 9, 14), (1, 128, 16, 16), (2, 512, 5, 6), (1, 1024, 4, 4)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_bn_train_forward_and_backward(nsm, mode_name, shape):
+    """conv output -> BatchNorm(train) -> LeakyReLU -> Dropout2d mask, and its backward, vs autograd of F ops."""
+    mode = nsm.MODES[mode_name]
+    N, C, H, W = shape
+    g = gen(C + H)
+    z = torch.randn(N, C, H, W, generator=g) * 2 + 0.5
+    gamma = torch.empty(C).uniform_(0.5, 1.5, generator=g)
+    beta = torch.empty(C).uniform_(-0.5, 0.5, generator=g)
+    rm0, rv0 = torch.randn(C, generator=g), torch.empty(C).uniform_(0.5, 2, generator=g)
+    mask = torch.empty(N, C, 1, 1).bernoulli_(0.8, generator=g).div_(0.8)
+    dy = torch.randn(N, C, H, W, generator=g) * 1e-3
+    if mode_name == "bf16":
+        z, dy = bf(z), bf(dy)
+    # reference (fp32 math on the same, already rounded, inputs)
+    zr = z.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    a = F.leaky_relu(F.batch_norm(zr, rm, rv, gr, br, True, 0.1, 1e-5), 0.2) * mask
+    a.backward(dy)
+    # B200
+    zt = planes(nsm, z, mode)
+    sums = nsm.bn_stats(zt)
+    rmg, rvg = rm0.cuda(), rv0.cuda()
+    st = nsm.bn_finalize(sums, N * H * W, gamma.cuda(), beta.cuda(), rmg, rvg)
+    out, _ = nsm.bn_act(zt, st[0], st[1], mask=mask.reshape(N, C).cuda().contiguous(), lrelu=True)
+    assert torch.allclose(rmg.cpu(), rm, rtol=1e-5, atol=1e-6) and torch.allclose(rvg.cpu(), rv, rtol=1e-5, atol=1e-6)
+    tol = 2e-5 if mode_name != "bf16" else 2e-2
+    assert (out.to_nchw().cpu() - a.detach()).abs().max().item() <= tol * max(1.0, a.abs().max().item())
+    dz, dg, db, dbias = nsm.bn_bwd(planes(nsm, dy, mode), zt, st[0], st[1], st[2], st[3],
+                                   mask=mask.reshape(N, C).cuda().contiguous(), lrelu=True)
+    assert rel(dz.to_nchw(), zr.grad) <= GTOL[mode_name]
+    assert rel(dg, gr.grad) <= GTOL[mode_name] and rel(db, br.grad) <= GTOL[mode_name]
+    # conv-bias gradient = sum dz: analytically 0 behind a train-mode BN; must be tiny relative to sum |dz|
+    assert dbias.abs().max().item() <= 1e-2 * zr.grad.abs().sum(dim=(0, 2, 3)).max().item() + 1e-12
+
+
+@pytest.mark.parametrize("mode_name", MODES)
+def test_bn_act_residual_and_pool(nsm, mode_name):
+    mode = nsm.MODES[mode_name]
+    g = gen(11)
+    z = torch.randn(2, 64, 11, 14, generator=g)
+    res = torch.randn(2, 64, 11, 14, generator=g)
+    scale, shift = torch.empty(64).uniform_(0.5, 1.5, generator=g), torch.randn(64, generator=g) * 0.3
+    if mode_name == "bf16":
+        z, res = bf(z), bf(res)
+    y = F.leaky_relu(z * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.2)
+    tol = 2e-5 if mode_name != "bf16" else 2e-2
+    out, _ = nsm.bn_act(planes(nsm, z, mode), scale.cuda(), shift.cuda(), residual=planes(nsm, res, mode))
+    assert (out.to_nchw().cpu() - (y + res)).abs().max().item() <= tol * 4
+    out, pl = nsm.bn_act(planes(nsm, z, mode), scale.cuda(), shift.cuda(), pool=True)
+    assert (out.to_nchw().cpu() - y).abs().max().item() <= tol * 4
+    assert (pl.to_nchw().cpu() - F.avg_pool2d(y, 2)).abs().max().item() <= tol * 4
+
+
+@pytest.mark.parametrize("mode_name", MODES)
+@pytest.mark.parametrize("case", [(1, 64, 8, 16, 64, 3), (2, 128, 13, 21, 64, 3), (1, 64, 17, 30, 128, 1),
+                                  (2, 512, 9, 12, 512, 3), (1, 1024, 10, 12, 512, 1), (1, 64, 24, 40, 64, 1)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_dgrad_and_wgrad(nsm, mode_name, case):
+    """dgrad (tcgen05 conv kernel with mirrored/transposed weights) and wgrad (MN-major tcgen05 GEMM, split-K) vs
+    autograd of F.conv2d."""
+    N, Cin, H, W, Cout, k = case
+    mode = nsm.MODES[mode_name]
+    g = gen(Cin + Cout + H)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    dz = torch.randn(N, Cout, H, W, generator=g) * 1e-2
+    if mode_name == "bf16":
+        x, dz = bf(x), bf(dz)
+    xr, wr = x.clone().requires_grad_(True), (bf(w) if mode_name == "bf16" else w).clone().requires_grad_(True)
+    F.conv2d(xr, wr, None, padding=k // 2).backward(dz)
+    dzt, xt = planes(nsm, dz, mode), planes(nsm, x, mode)
+    dx, _, _ = nsm.conv_fwd(dzt, nsm.pack_conv_weight(w.cuda(), mode, dgrad=True), k, Cin, mode)
+    assert rel(dx.to_nchw(), xr.grad) <= GTOL[mode_name]
+    dw = nsm.wgrad(dzt, xt, k, Cout, Cin)
+    assert dw.shape == w.shape
+    assert rel(dw, wr.grad) <= GTOL[mode_name], (rel(dw, wr.grad), dw.abs().max().item(), wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("mode_name", MODES)
+def test_padded_thin_layers(nsm, mode_name):
+    """16- and 4-channel layers run zero-padded to 64 channels; gradients are cut back to the real block."""
+    mode = nsm.MODES[mode_name]
+    g = gen(3)
+    x = torch.randn(2, 16, 12, 20, generator=g)
+    w = torch.randn(4, 16, 1, 1, generator=g) * 0.3
+    dz = torch.randn(2, 4, 12, 20, generator=g) * 1e-2
+    if mode_name == "bf16":
+        x, dz = bf(x), bf(dz)
+    xp = torch.zeros(2, 64, 12, 20); xp[:, :16] = x
+    dzp = torch.zeros(2, 64, 12, 20); dzp[:, :4] = dz
+    wr = (bf(w) if mode_name == "bf16" else w).clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    y = F.conv2d(xr, wr)
+    y.backward(dz)
+    wp = nsm.pack_conv_weight_padded(w.cuda(), mode, 64, 64)
+    out, _, _ = nsm.conv_fwd(planes(nsm, xp, mode), wp, 1, 64, mode)
+    o = out.to_nchw().cpu()
+    assert o[:, 4:].abs().max().item() == 0.0
+    assert rel(o[:, :4], y) <= (1e-4 if mode_name != "bf16" else 1e-2)
+    dw = nsm.wgrad(planes(nsm, dzp, mode), planes(nsm, xp, mode), 1, 4, 16)
+    assert rel(dw, wr.grad) <= GTOL[mode_name]
+    wpt = nsm.pack_conv_weight_padded(w.cuda(), mode, 64, 64, dgrad=True)
+    dx, _, _ = nsm.conv_fwd(planes(nsm, dzp, mode), wpt, 1, 64, mode)
+    d = dx.to_nchw().cpu()
+    assert d[:, 16:].abs().max().item() == 0.0 and rel(d[:, :16], xr.grad) <= GTOL[mode_name]
+
+
+@pytest.mark.parametrize("mode_name", MODES)
+@pytest.mark.parametrize("shape", [(1, 64, 8, 12, 16, 24), (2, 64, 10, 14, 10, 14), (1, 128, 5, 7, 11, 15),
+                                   (1, 64, 67, 120, 135, 240)], ids=lambda s: "x".join(map(str, s)))
+def test_upsample_and_pool_adjoints(nsm, mode_name, shape):
+    N, C, hs, ws, hd, wd = shape
+    mode = nsm.MODES[mode_name]
+    g = gen(hs * wd)
+    x = torch.randn(N, C, hs, ws, generator=g).requires_grad_(True)
+    dy = torch.randn(N, C, hd, wd, generator=g)
+    if mode_name == "bf16":
+        dy = bf(dy)
+    oracle.upsample_and_match(x, (hd, wd)).backward(dy)
+    got = nsm.upsample_match_bwd(planes(nsm, dy, mode), hs, ws)
+    assert rel(got.to_nchw(), x.grad) <= GTOL[mode_name]
+    # AvgPool2d(2) adjoint + skip-gradient add
+    c = torch.randn(N, C, hd, wd, generator=g).requires_grad_(True)
+    dp = torch.randn(N, C, hd // 2, wd // 2, generator=g)
+    skip = torch.randn(N, C, hd, wd, generator=g)
+    if mode_name == "bf16":
+        dp, skip = bf(dp), bf(skip)
+    F.avg_pool2d(c, 2).backward(dp)
+    got = nsm.pool_bwd_add(planes(nsm, skip, mode), planes(nsm, dp, mode), (N, C, hd, wd))
+    assert rel(got.to_nchw(), c.grad + skip) <= GTOL[mode_name]
+
+
+def _masks(seed, N, rate=0.2):
+    torch.manual_seed(seed)
+    out = []
+    for name, cin, _ in oracle.BLOCKS:
+        p = oracle.DROPOUT_P(name, rate)
+        out.append(torch.empty(N, cin, 1, 1).bernoulli_(1 - p).div_(1 - p))
+    return out
+
+
+def _gpu_step(P, x, t, masks, precision, alpha=0.9, input_grad=True):
+    from Unetmodel import Unet
+    from customLoss import CustomLoss
+    net = Unet(dropout_rate=0.2, precision=precision)
+    net.load_state_dict({k: v.clone() for k, v in P.items()})
+    net = net.cuda().train()
+    net._replay_masks = masks
+    xg = x.cuda().requires_grad_(input_grad)
+    out = net(xg)
+    loss = CustomLoss("cuda", alpha=alpha)(out, t.cuda(), xg)
+    loss.backward()
+    grads = {n: p.grad.detach().cpu() for n, p in net.named_parameters()}
+    if input_grad:
+        grads["input"] = xg.grad.detach().cpu()
+    return net, out.detach().float().cpu(), loss.item(), grads
+
+
+def test_train_step_against_reference_golden(nsm, golden):
+    """Same step as tests/golden/make_golden.py G3 (unmodified reference: Unet.train(), CustomLoss, backward)."""
+    P = oracle.init_params(42)
+    x = torch.randn(2, 4, 32, 48, generator=gen(3))
+    t = torch.rand(2, 1, 32, 48, generator=gen(4))
+    net, out, loss, grads = _gpu_step(P, x, t, _masks(7, 2), "fp32")
+    assert (out - torch.from_numpy(golden["train_out"])).abs().max().item() <= 1e-4
+    assert abs(loss - float(golden["train_loss"])) <= 1e-5
+    names = list(golden["train_grad_names"])
+    num = den = 0.0
+    for n, ref in zip(names, golden["train_grad_norms"]):
+        num += (float(grads[n].double().norm()) - ref) ** 2
+        den += ref ** 2
+    print("global grad-norm rel diff vs reference golden:", (num / den) ** 0.5)
+    assert (num / den) ** 0.5 <= 1e-2
+    for k in golden.files:
+        if k.startswith("train_grad::"):
+            r = rel(grads[k.split("::")[1]], torch.from_numpy(golden[k]))
+            print(k, "rel-L2", r)
+            assert r <= 2e-2, (k, r)          # end-to-end: floor 1.2e-3..2.5e-3 (LeakyReLU mask flips)
+        if k.startswith("train_buf::"):
+            got = net.state_dict()[k.split("::")[1]].cpu()
+            assert torch.allclose(got, torch.from_numpy(golden[k]), rtol=1e-4, atol=1e-5), k
+    sd = net.state_dict()
+    assert int(sd["conv5.conv.1.num_batches_tracked"]) == int(golden["train_nbt"]) == 2   # checkpoint(conv5) quirk
+    assert int(sd["conv4.conv.1.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 4, 64, 96), (1, 4, 80, 112)], ids=lambda s: "x".join(map(str, s)))
+def test_train_step_against_oracle(nsm, precision, shape):
+    P = oracle.init_params(42)
+    x = torch.randn(*shape, generator=gen(5))
+    t = torch.rand(shape[0], 1, shape[2], shape[3], generator=gen(6))
+    masks = _masks(9, shape[0])
+    Po = {k: v.clone() for k, v in P.items()}
+    o_ref, l_ref, g_ref = oracle.train_step_grads(x, t, Po, masks=masks, bf16=(precision == "bf16"), input_grad=True)
+    net, out, loss, grads = _gpu_step(P, x, t, masks, precision)
+    err = (out - o_ref.float()).abs().max().item()
+    names = oracle.param_names()
+    num = sum(float((grads[n].double() - g_ref[n].double()).pow(2).sum()) for n in names)
+    den = sum(float(g_ref[n].double().pow(2).sum()) for n in names)
+    gl = (num / den) ** 0.5
+    worst = max(((rel(grads[n], g_ref[n]), n) for n in names if not n.endswith(("conv.0.bias", "conv.4.bias"))))
+    print(f"{precision} {shape}: out err {err:.3g} loss {loss:.6f} vs {l_ref.item():.6f}; global grad rel-L2 {gl:.3g}; "
+          f"worst tensor {worst[1]} {worst[0]:.3g}; input grad rel {rel(grads['input'], g_ref['input']):.3g}")
+    assert err <= (1e-4 if precision == "fp32" else 2e-2)
+    assert abs(loss - l_ref.item()) <= (1e-5 if precision == "fp32" else 2e-3)
+    # end-to-end gradients: reference-vs-reference floor is 1.2e-3..2.5e-3 (fp32) / ~0.2 (bf16 vs fp32), SURVEY 3.7
+    assert gl <= (1e-2 if precision == "fp32" else 0.3)
+    sd = net.state_dict()
+    for k in oracle.buffer_names():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(Po[k]), k
+        elif precision == "fp32":
+            assert torch.allclose(sd[k].cpu(), Po[k], rtol=1e-3, atol=1e-4), k
+
+
+def test_no_grad_train_mode_forward_and_perturbation_loss(nsm):
+    """PerturbationLoss runs train-mode forwards under no_grad (pert_loss.py:78-81): BN counters advance once each."""
+    from Unetmodel import Unet
+    from pert_loss import PerturbationLoss
+    P = oracle.init_params(42)
+    net = Unet(dropout_rate=0.0, precision="fp32")
+    net.load_state_dict(P)
+    net = net.cuda().train()
+    x = torch.randn(2, 4, 32, 48, generator=gen(5))
+    out = net(x.cuda())
+    noises = [[torch.randn(2, 1, 32, 48, generator=gen(200 + 4 * i + c)) for c in range(4)] for i in range(3)]
+    nz = torch.stack([torch.stack(n) for n in noises]).cuda()
+    val = PerturbationLoss(3)(net, x.cuda(), out, noise=nz)
+    val.backward()
+    Po = oracle.init_params(42)
+    fwd = lambda inp: oracle.unet_forward(inp, Po, training=True, dropout_rate=0.0)  # noqa: E731
+    with torch.no_grad():
+        o_ref = fwd(x)
+    v_ref, _ = oracle.perturbation_loss(fwd, x, o_ref, count=3, noises=noises)
+    print("perturbation loss", val.item(), "oracle", v_ref.item())
+    assert abs(val.item() - v_ref.item()) <= 2e-5
+    assert int(net.state_dict()["conv2.conv.1.num_batches_tracked"]) == 4
+    assert int(net.state_dict()["conv5.conv.1.num_batches_tracked"]) == 5     # 4 forwards + 1 checkpoint replay
