@@ -281,21 +281,165 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# training workload (BASELINE.json configs[2]/[3]): batch 32 of 512x512 crops per GPU, bf16, CustomLoss + PerturbationLoss
+# ----------------------------------------------------------------------------------------------------------------
+TRAIN_FLOP_PER_SAMPLE = 3 * 747680.0 * 512 * 512           # fwd + dgrad + wgrad
+PERT_FLOP_PER_SAMPLE = 3 * 747680.0 * 512 * 512            # + 3 no-grad forwards of the perturbation loss
+
+
+def run_b200_train(args):
+    import torch.distributed as dist
+    import nsm
+    from Unetmodel import Unet
+    from pert_loss import EnhancedCustomLoss
+    from parallel import GradSync
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nsm.require_device()
+    precision = args.precision or "bf16"
+    B = args.batch or 32
+    H, W = args.height or 512, args.width or 512
+    use_pert = not args.no_perturb
+
+    torch.manual_seed(42)
+    net = Unet(dropout_rate=0.2, precision=precision).to(dev).train()
+    crit = EnhancedCustomLoss(dev, alpha=0.9, perturb_weight=0.1 if use_pert else 0.0).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=7e-4, weight_decay=1e-3, fused=True)   # main.py:955
+    sync = GradSync(net) if world > 1 else None
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = torch.randn(B, 4, H, W, generator=g).pin_memory()
+    t_host = torch.rand(B, 1, H, W, generator=g).pin_memory()
+    x, t = x_host.to(dev), t_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(xd, td):
+        opt.zero_grad(set_to_none=True)
+        out = net(xd)
+        loss, _ = crit(net, out, td, xd)
+        loss.backward()
+        if sync is not None:
+            sync.finish()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)               # main.py:405
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step(x, t)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(x, t)
+        e.record()
+        evs.append((s, e))
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    t_e2e = 0.0
+    last = None
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        xd = x_host.to(dev, non_blocking=True)
+        td = t_host.to(dev, non_blocking=True)
+        last = step(xd, td).item()                       # D2H read of the step's loss
+        t_e2e += time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    nsm.profile_enable(True)
+    step(x, t)
+    torch.cuda.synchronize()
+    rows = nsm.profile_read()
+    nsm.profile_enable(False)
+
+    tt = torch.tensor([dev_ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = tt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * B * args.steps / (dev_ms * 1e-3)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    pk = peaks()
+    fam = {}
+    for name, ms, fl, by in rows:
+        d = fam.setdefault(name.split()[0], [0.0, 0.0, 0])
+        d[0] += ms; d[1] += fl; d[2] += 1
+    conv_ms = sum(v[0] for v in fam.values())
+    conv_fl = sum(v[1] for v in fam.values())
+    achieved = conv_fl / max(conv_ms, 1e-9) / 1e9
+    step_ms = dev_ms / args.steps
+    roofline = {"kernel": "conv_gemm_kernel + wgrad_gemm_kernel (tcgen05 implicit GEMM; fwd, dgrad, wgrad)",
+                "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": f"{pk['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)",
+                "kernel_share_of_step": conv_ms / step_ms,
+                "families": {k: {"ms": v[0], "tflops": v[1] / max(v[0], 1e-9) / 1e9, "launches": v[2]}
+                             for k, v in fam.items()},
+                "note": "padded thin layers (16/4 -> 64 channels) are counted with their padded FLOPs"}
+    flop = (TRAIN_FLOP_PER_SAMPLE + (PERT_FLOP_PER_SAMPLE if use_pert else 0)) * (H * W) / (512 * 512)
+    line = {"metric": "U-Net train samples/s", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
+            "config": {"workload": f"cfg2: U-Net training step, batch {B} of {H}x{W} crops per GPU, {precision}, "
+                                   f"CustomLoss(alpha 0.9){' + PerturbationLoss(3 copies, weight 0.1)' if use_pert else ''}"
+                                   ", Dropout2d, train-mode BatchNorm, grad clip 1.0, AdamW (torch fused)",
+                       "algorithmic_tflop_per_step": flop * B / 1e12,
+                       "model_tflops": flop * B * world / (step_ms * 1e-3) / 1e12,
+                       "l2": "256 MiB buffer written before every timed step; activations >> L2",
+                       "parallelism": f"dp{world}: per-rank batch, NCCL gradient all-reduce overlapped with backward"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": (x_host.numel() + t_host.numel()) * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_loss": last},
+            "gpu_launches": len(rows) and None,
+            "roofline": roofline}
+    line["gpu_launches"] = int(getattr(nsm, "launch_count", lambda: 0)()) or None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
-    ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--height", type=int, default=H1080)
-    ap.add_argument("--width", type=int, default=W1080)
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-perturb", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_b200_train(args)
     else:
+        args.precision = args.precision or "fp32"
+        args.batch, args.height, args.width = args.batch or 1, args.height or H1080, args.width or W1080
         run_b200(args)
 
 

@@ -453,6 +453,12 @@ int nsm_conv_fwd(const nsm_conv_args* a, void* stream) {
   e.residual = {{const_cast<void*>(a->residual[0]), const_cast<void*>(a->residual[1])}};
   e.pool = {{a->pool[0], a->pool[1]}};
   e.out_f32 = a->out_f32;
+  char nm[64];
+  snprintf(nm, sizeof(nm), "conv_gemm k%d %d->%d @%dx%d", a->ksize, a->Cin, a->Cout, a->H, a->W);
+  const double px = double(a->N) * a->H * a->W;
+  ProfScope ps(nm, 2.0 * px * s.taps * a->Cin * a->Cout,
+               (px * (a->Cin + a->Cout) + double(s.taps) * a->Cin * a->Cout) * 2.0 * fmt_planes(a->mode),
+               static_cast<cudaStream_t>(stream));
   return conv_gemm_launch(s, in, w, e, static_cast<cudaStream_t>(stream));
 }
 
@@ -553,6 +559,10 @@ int nsm_wgrad(const void* dz0, const void* dz1, const void* x0, const void* x1, 
               int ksize, int mode, int Cout_real, int Cin_real, void* workspace, size_t workspace_bytes, float* dw,
               void* stream) {
   WgradShape s = {N, H, W, Cout, Cin, ksize * ksize, mode};
+  char nm[64];
+  snprintf(nm, sizeof(nm), "wgrad_gemm k%d %d->%d @%dx%d", ksize, Cin, Cout, H, W);
+  const double px = double(N) * H * W;
+  ProfScope ps(nm, 2.0 * px * ksize * ksize * Cin * Cout, px * (Cin + Cout) * 2.0 * fmt_planes(mode), S(stream));
   return wgrad_launch(s, mk(dz0, dz1), mk(x0, x1), workspace, workspace_bytes, Cout_real, Cin_real,
                       mode == NSM_MODE_BF16, dw, S(stream));
 }

@@ -195,10 +195,18 @@ def _forward(model, x, mode, save):
 
 def _backward(model, st, dy, mode, need_dx):
     pk, sv = st["pk"], st["sv"]
-    G = {}
+    sync = getattr(model, "_grad_sync", None)      # parallel.GradSync: bucketed all-reduce overlapped with backward
+
+    class _G(dict):
+        def update(self, g):                        # every finished block is handed to the gradient synchroniser
+            super().update(g)
+            if sync is not None:
+                sync.reduce_ready(g)
+
+    G = _G()
     dc10 = nsm.sigmoid_shuffle_bwd(dy, st["y"], mode)
-    G["conv10.weight"] = nsm.wgrad(dc10, st["c9"], 1, 4, 16)
-    G["conv10.bias"] = nsm.bn_stats(dc10)[:4].to(torch.float32)
+    G.update({"conv10.weight": nsm.wgrad(dc10, st["c9"], 1, 4, 16),
+              "conv10.bias": nsm.bn_stats(dc10)[:4].to(torch.float32)})
     dc9, _, _ = nsm.conv_fwd(dc10, pk.w10t, 1, 64, mode)
     du9, g = _block_backward(model, pk, 7, sv[7], dc9, mode); G.update(g)
     dm8 = nsm.upsample_match_bwd(du9, *st["sizes"]["m8"])
@@ -224,6 +232,8 @@ def _backward(model, st, dy, mode, need_dx):
     if need_dx:
         N, Hin, Win = st["in_shape"]
         dx = nsm.train_input_grad(dx16, Hin, Win)
+    if sync is not None:
+        sync.flush()
     return dx, G
 
 
