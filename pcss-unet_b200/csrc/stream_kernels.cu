@@ -465,10 +465,11 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
       r[k] = rb ? rbf(v) : v;
     }
     // pixel_shuffle(2): channel k = dy*2 + dx -> (2y+dy, 2x+dx)
-    const int x = int(pix % p.w);
-    const long long t = pix / p.w;
-    const int y = int(t % p.h);
-    const long long n = t / p.h;
+    const unsigned pix32 = (unsigned)pix;           // npix < 2^31 (checked on the host): 32-bit div/mod
+    const unsigned t = pix32 / (unsigned)p.w;
+    const int x = int(pix32 - t * (unsigned)p.w);
+    const unsigned n = t / (unsigned)p.h;
+    const int y = int(t - n * (unsigned)p.h);
     float* o = p.y + ((size_t)n * H + 2 * y) * W + 2 * x;
     *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
     *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
@@ -477,6 +478,10 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
 
 int tail_eval(const TailParams& p, cudaStream_t st) {
   const long long npix = (long long)p.N * p.h * p.w;
+  if (npix >= (1LL << 31)) {
+    set_error("tail_eval: too many pixels");
+    return 1;
+  }
   tail_eval_kernel<<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
   NSM_CHECK_LAUNCH("tail_eval");
   return 0;
@@ -512,14 +517,16 @@ __device__ __forceinline__ void load8(const UpParams& p, size_t elem, float* v) 
   }
 }
 
-// value of the x2 up-sampled tensor at intermediate pixel (Y, X), 8 channels
-__device__ __forceinline__ void up2_at(const UpParams& p, size_t nbase, int Y, int X, int cg, bool rb, float* out) {
-  const Lerp ly = make_lerp(Y, p.hs, 2 * p.hs), lx = make_lerp(X, p.ws, 2 * p.ws);
+// value of the x2 up-sampled tensor at intermediate pixel (row lerp ly given, column X), 8 channels
+__device__ __forceinline__ void up2_at(const UpParams& p, size_t nbase, const Lerp& ly, int X, int cg, bool rb,
+                                       float* out) {
+  const Lerp lx = make_lerp(X, p.ws, 2 * p.ws);
   float v00[8], v01[8], v10[8], v11[8];
-  load8(p, ((nbase + (size_t)ly.i0 * p.ws + lx.i0) * p.C) + cg * 8, v00);
-  load8(p, ((nbase + (size_t)ly.i0 * p.ws + lx.i1) * p.C) + cg * 8, v01);
-  load8(p, ((nbase + (size_t)ly.i1 * p.ws + lx.i0) * p.C) + cg * 8, v10);
-  load8(p, ((nbase + (size_t)ly.i1 * p.ws + lx.i1) * p.C) + cg * 8, v11);
+  const size_t r0 = nbase + (size_t)ly.i0 * p.ws, r1 = nbase + (size_t)ly.i1 * p.ws;
+  load8(p, (r0 + lx.i0) * p.C + cg * 8, v00);
+  load8(p, (r0 + lx.i1) * p.C + cg * 8, v01);
+  load8(p, (r1 + lx.i0) * p.C + cg * 8, v10);
+  load8(p, (r1 + lx.i1) * p.C + cg * 8, v11);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float v = ly.w0 * (lx.w0 * v00[e] + lx.w1 * v01[e]) + ly.w1 * (lx.w0 * v10[e] + lx.w1 * v11[e]);
@@ -527,59 +534,60 @@ __device__ __forceinline__ void up2_at(const UpParams& p, size_t nbase, int Y, i
   }
 }
 
-__global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p) {
-  const int cgs = p.C / 8;
-  const long long total = (long long)p.N * p.hd * p.wd * cgs;
+// grid: x = output row (n * hd + y), y = 256-thread chunks of the row's (pixel, channel-group) pairs.  All index
+// arithmetic is 32-bit with shifts (channel-group counts are powers of two); the row interpolation is per block.
+__global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, int cg_shift) {
+  const int cgs = 1 << cg_shift;
+  const int j = blockIdx.y * 256 + threadIdx.x;
+  if (j >= p.wd * cgs) return;
+  const int cg = j & (cgs - 1), x = j >> cg_shift;
+  const int n = blockIdx.x / p.hd, y = blockIdx.x - n * p.hd;
   const bool rb = p.fmt == kFmtBf16;
   const bool same = (p.hd == 2 * p.hs) && (p.wd == 2 * p.ws);
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int cg = int(i % cgs);
-    long long t = i / cgs;
-    const int x = int(t % p.wd);
-    t /= p.wd;
-    const int y = int(t % p.hd);
-    const int n = int(t / p.hd);
-    const size_t nbase = (size_t)n * p.hs * p.ws;
-    float r[8];
-    if (same) {
-      up2_at(p, nbase, y, x, cg, rb, r);  // second resize has scale 1 -> exact copy
-    } else {
-      const Lerp my = make_lerp(y, 2 * p.hs, p.hd), mx = make_lerp(x, 2 * p.ws, p.wd);
-      float u00[8], u01[8], u10[8], u11[8];
-      up2_at(p, nbase, my.i0, mx.i0, cg, rb, u00);
-      up2_at(p, nbase, my.i0, mx.i1, cg, rb, u01);
-      up2_at(p, nbase, my.i1, mx.i0, cg, rb, u10);
-      up2_at(p, nbase, my.i1, mx.i1, cg, rb, u11);
+  const size_t nbase = (size_t)n * p.hs * p.ws;
+  float r[8];
+  if (same) {
+    up2_at(p, nbase, make_lerp(y, p.hs, 2 * p.hs), x, cg, rb, r);  // second resize has scale 1 -> exact copy
+  } else {
+    const Lerp my = make_lerp(y, 2 * p.hs, p.hd), mx = make_lerp(x, 2 * p.ws, p.wd);
+    const Lerp ly0 = make_lerp(my.i0, p.hs, 2 * p.hs), ly1 = make_lerp(my.i1, p.hs, 2 * p.hs);
+    float u00[8], u01[8], u10[8], u11[8];
+    up2_at(p, nbase, ly0, mx.i0, cg, rb, u00);
+    up2_at(p, nbase, ly0, mx.i1, cg, rb, u01);
+    up2_at(p, nbase, ly1, mx.i0, cg, rb, u10);
+    up2_at(p, nbase, ly1, mx.i1, cg, rb, u11);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float v = my.w0 * (mx.w0 * u00[e] + mx.w1 * u01[e]) + my.w1 * (mx.w0 * u10[e] + mx.w1 * u11[e]);
-        r[e] = rb ? rbf(v) : v;
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float v = my.w0 * (mx.w0 * u00[e] + mx.w1 * u01[e]) + my.w1 * (mx.w0 * u10[e] + mx.w1 * u11[e]);
+      r[e] = rb ? rbf(v) : v;
     }
-    const size_t o = (((size_t)n * p.hd + y) * p.wd + x) * p.C + cg * 8;
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      hw[e] = pack_hi(r[2 * e], r[2 * e + 1], p.fmt);
-      lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], p.fmt);
-    }
-    stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-    if (p.fmt != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
   }
+  const size_t o = (((size_t)n * p.hd + y) * p.wd + x) * p.C + cg * 8;
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    hw[e] = pack_hi(r[2 * e], r[2 * e + 1], p.fmt);
+    lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], p.fmt);
+  }
+  stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+  if (p.fmt != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
 }
 
 int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes& dst, int hd, int wd, int fmt,
                    cudaStream_t st) {
-  if (C % 8) {
-    set_error("upsample_match: C=%d not a multiple of 8", C);
+  const int cgs = C / 8;
+  if (C % 8 || (cgs & (cgs - 1))) {
+    set_error("upsample_match: C=%d must be 8 x a power of two", C);
     return 1;
   }
+  int shift = 0;
+  while ((1 << shift) < cgs) ++shift;
   UpParams p;
   p.s0 = (const uint8_t*)src.p[0]; p.s1 = (const uint8_t*)src.p[1];
   p.d0 = (uint8_t*)dst.p[0]; p.d1 = (uint8_t*)dst.p[1];
   p.N = N; p.hs = hs; p.ws = ws; p.C = C; p.hd = hd; p.wd = wd; p.fmt = fmt;
-  const long long total = (long long)N * hd * wd * (C / 8);
-  upsample_match_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, st>>>(p);
+  dim3 grid((unsigned)(N * hd), (unsigned)((wd * cgs + 255) / 256));
+  upsample_match_kernel<<<grid, 256, 0, st>>>(p, shift);
   NSM_CHECK_LAUNCH("upsample_match");
   return 0;
 }

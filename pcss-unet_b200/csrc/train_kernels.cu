@@ -107,6 +107,14 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const Planes z, long long
   block_channel_reduce<2>(acc, C, sums);
 }
 
+static int check_32(const char* who, long long total) {
+  if (total >= (1LL << 32)) {
+    set_error("%s: %lld work items exceed the 32-bit index range", who, total);
+    return 1;
+  }
+  return 0;
+}
+
 static int check_c(const char* who, int C) {
   if (C % 8 || C < 8 || (256 % (C / 8)) || C > 2048) {
     set_error("%s: unsupported channel count %d", who, C);
@@ -183,10 +191,13 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
   const int cgs = p.C / 8;
   const bool rb = p.fmt == kFmtBf16;
   const long long total = (long long)p.N * p.H * p.W * cgs;
+  const int cg_shift = __ffs(cgs) - 1;                 // channel-group counts are powers of two
+  const unsigned HW = (unsigned)(p.H * p.W);
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int cg = int(i % cgs);
-    const long long pix = i / cgs;
-    const int n = int(pix / ((long long)p.H * p.W));
+    const unsigned iu = (unsigned)i;                   // total < 2^32 (host check): 32-bit index math only
+    const int cg = int(iu & (unsigned)(cgs - 1));
+    const unsigned pix = iu >> cg_shift;
+    const int n = int(pix / HW);
     float v[8];
     load8(p.z, (size_t)pix * p.C + cg * 8, p.fmt, v);
     bn_act8(v, p, n, cg * 8, rb);
@@ -207,12 +218,13 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
   const int Hq = (p.H + 1) / 2, Wq = (p.W + 1) / 2, Hp = p.H / 2, Wp = p.W / 2;
   const long long total = (long long)p.N * Hq * Wq * cgs;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int cg = int(i % cgs);
-    long long t = i / cgs;
-    const int qx = int(t % Wq);
-    t /= Wq;
-    const int qy = int(t % Hq);
-    const int n = int(t / Hq);
+    const unsigned iu = (unsigned)i;
+    const int cg = int(iu % (unsigned)cgs);
+    unsigned t = iu / (unsigned)cgs;
+    const unsigned t1 = t / (unsigned)Wq;
+    const int qx = int(t - t1 * (unsigned)Wq);
+    const int n = int(t1 / (unsigned)Hq);
+    const int qy = int(t1 - (unsigned)n * (unsigned)Hq);
     float s[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[e] = 0.f;
@@ -299,7 +311,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
     for (int e = 0; e < 8; ++e) fs[e] = fq[e] = 0.f;
     for (int it = 0; it < 16 && px < P; ++it, px += stride) {
       float g[8], xh[8];
-      bn_bwd_g8(p, (size_t)px * p.C + cg * 8, int(px / HW), cg * 8, rb, g, xh);
+      bn_bwd_g8(p, (size_t)px * p.C + cg * 8, int((unsigned)px / (unsigned)HW), cg * 8, rb, g, xh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         fs[e] += g[e];
@@ -348,7 +360,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
     for (int it = 0; it < 16 && px < P; ++it, px += stride) {
       float g[8], xh[8], dz[8];
       const size_t elem = (size_t)px * p.C + cg * 8;
-      bn_bwd_g8(p, elem, int(px / HW), cg * 8, rb, g, xh);
+      bn_bwd_g8(p, elem, int((unsigned)px / (unsigned)HW), cg * 8, rb, g, xh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         float t = sc[e] * (g[e] - mg[e] - xh[e] * mgx[e]);
@@ -401,23 +413,24 @@ __global__ void __launch_bounds__(256) pool_bwd_add_kernel(const Planes a, const
   const bool rb = fmt == kFmtBf16;
   const long long total = (long long)N * H * W * cgs;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int cg = int(i % cgs);
-    long long t = i / cgs;
-    const int x = int(t % W);
-    t /= W;
-    const int y = int(t % H);
-    const int n = int(t / H);
+    const unsigned iu = (unsigned)i;
+    const int cg = int(iu % (unsigned)cgs);
+    const unsigned pixi = iu / (unsigned)cgs;
+    const unsigned t1 = pixi / (unsigned)W;
+    const int x = int(pixi - t1 * (unsigned)W);
+    const int n = int(t1 / (unsigned)H);
+    const int y = int(t1 - (unsigned)n * (unsigned)H);
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (a.p[0]) load8(a, (size_t)(i / cgs) * C + cg * 8, fmt, v);
+    if (a.p[0]) load8(a, (size_t)pixi * C + cg * 8, fmt, v);
     if ((y >> 1) < Hp && (x >> 1) < Wp) {
       float d[8];
       load8(dpool, (((size_t)n * Hp + (y >> 1)) * Wp + (x >> 1)) * C + cg * 8, fmt, d);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = rb ? rbf(v[e] + d[e] * 0.25f) : v[e] + d[e] * 0.25f;
     }
-    store8(out, (size_t)(i / cgs) * C + cg * 8, fmt, v);
+    store8(out, (size_t)pixi * C + cg * 8, fmt, v);
   }
 }
 int pool_bwd_add(const Planes& a, const Planes& dpool, const Planes& out, int N, int H, int W, int C, int fmt,
@@ -488,12 +501,13 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const Planes dout, in
   const int cgs = C / 8;
   const long long total = (long long)N * hi * wi * cgs;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int cg = int(i % cgs);
-    long long t = i / cgs;
-    const int q = int(t % wi);
-    t /= wi;
-    const int r = int(t % hi);
-    const int n = int(t / hi);
+    const unsigned iu = (unsigned)i;
+    const int cg = int(iu % (unsigned)cgs);
+    const unsigned pixi = iu / (unsigned)cgs;
+    const unsigned t1 = pixi / (unsigned)wi;
+    const int q = int(pixi - t1 * (unsigned)wi);
+    const int n = int(t1 / (unsigned)hi);
+    const int r = int(t1 - (unsigned)n * (unsigned)hi);
     int ylo, yhi, xlo, xhi;
     touch_range(r, hi, ho, ylo, yhi);
     touch_range(q, wi, wo, xlo, xhi);
@@ -515,7 +529,7 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const Planes dout, in
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, d[e], acc[e]);
       }
     }
-    store8(din, (size_t)(i / cgs) * C + cg * 8, fmt, acc);
+    store8(din, (size_t)pixi * C + cg * 8, fmt, acc);
   }
 }
 int bilinear_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,
@@ -544,10 +558,10 @@ __global__ void __launch_bounds__(256) train_input_prep_kernel(const float* __re
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
     if (cg < 2) {
-      const int px = int(pix % w);
-      const long long t = pix / w;
-      const int py = int(t % h);
-      const int n = int(t / h);
+      const unsigned t = (unsigned)pix / (unsigned)w;
+      const int px = int((unsigned)pix - t * (unsigned)w);
+      const int n = int(t / (unsigned)h);
+      const int py = int(t - (unsigned)n * (unsigned)h);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int ch = cg * 8 + e;           // un-shuffled channel = c*4 + dy*2 + dx
@@ -583,10 +597,10 @@ __global__ void __launch_bounds__(256) train_input_grad_kernel(const Planes dx16
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int cg = int(i & 1);
     const long long pix = i >> 1;
-    const int px = int(pix % w);
-    const long long t = pix / w;
-    const int py = int(t % h);
-    const int n = int(t / h);
+    const unsigned t = (unsigned)pix / (unsigned)w;
+    const int px = int((unsigned)pix - t * (unsigned)w);
+    const int n = int(t / (unsigned)h);
+    const int py = int(t - (unsigned)n * (unsigned)h);
     float v[8];
     load8(dx16, (size_t)pix * 64 + cg * 8, fmt, v);
 #pragma unroll
@@ -621,10 +635,10 @@ __global__ void __launch_bounds__(256) sigmoid_shuffle_fwd_kernel(const Planes c
       const float s = 1.f / (1.f + expf(-v[k]));
       r[k] = rb ? rbf(s) : s;
     }
-    const int x = int(pix % w);
-    const long long t = pix / w;
-    const int yy = int(t % h);
-    const long long n = t / h;
+    const unsigned t = (unsigned)pix / (unsigned)w;
+    const int x = int((unsigned)pix - t * (unsigned)w);
+    const unsigned n = t / (unsigned)h;
+    const int yy = int(t - n * (unsigned)h);
     float* o = y + ((size_t)n * H + 2 * yy) * W + 2 * x;
     *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
     *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
@@ -649,10 +663,10 @@ __global__ void __launch_bounds__(256) sigmoid_shuffle_bwd_kernel(const float* _
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
     if (cg == 0) {
-      const int x = int(pix % w);
-      const long long t = pix / w;
-      const int yy = int(t % h);
-      const long long n = t / h;
+      const unsigned t = (unsigned)pix / (unsigned)w;
+      const int x = int((unsigned)pix - t * (unsigned)w);
+      const unsigned n = t / (unsigned)h;
+      const int yy = int(t - n * (unsigned)h);
       const size_t o = ((size_t)n * H + 2 * yy) * W + 2 * x;
       const float2 g0 = *reinterpret_cast<const float2*>(dy + o), g1 = *reinterpret_cast<const float2*>(dy + o + W);
       const float2 s0 = *reinterpret_cast<const float2*>(y + o), s1 = *reinterpret_cast<const float2*>(y + o + W);
