@@ -11,11 +11,12 @@
 // rows of 128 B with the 128-byte swizzle = the canonical K-major UMMA operand layout, so no im2col buffer,
 // no index math and no smem transform is needed.  B tiles (weights, pre-packed [Cout][tap][Cin]) are 2-D boxes.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over work items):
+// Warp roles (320 threads, 1 CTA / SM, persistent over work items):
 //   warp 0    TMA producer          (smem full/empty mbarrier ring)
 //   warp 1    tcgen05.mma issuer    (single thread; accumulators double-buffered in TMEM)
-//   warps 2-5 epilogue              (tcgen05.ld -> bias, BN affine, LeakyReLU, residual add, 2x2 avg-pool,
-//                                    bf16 (or hi/lo split) NHWC stores)
+//   warps 2-9 epilogue              (tcgen05.ld -> bias, BN affine, LeakyReLU, residual add, 2x2 avg-pool,
+//                                    bf16 (or hi/lo split) NHWC stores); two warps per TMEM lane quarter, each
+//                                    owning half of the tile's columns, for memory-level parallelism on thin layers
 //
 // fp32 mode ("planes == 2"): activations and weights are stored as hi + lo fp16 planes (value = hi + lo, 22
 // significand bits) and the issuer runs a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into the same fp32 accumulator: operand
@@ -97,6 +98,7 @@ struct ConvKernelParams {
   int N, H, W, Cin, Cout, taps;
   int tiles_x, tiles_y, n_blocks, total_items, kc_per_tap;
   int fmt;
+  int chunk_kb;       // fp32 modes: k-blocks per TMEM accumulation chunk
   uint32_t idesc_hi;  // A hi-plane x B (bf16 x bf16 in bf16 mode; bf16 x fp16 in fp32 mode)
   uint32_t idesc_lo;  // A lo-plane (fp16) x B hi-plane (fp16), fp32 mode only
   ConvEpilogue ep;
@@ -122,7 +124,8 @@ struct GemmCfg {
 // (#MMAs) * 2^-24 (measured: ~1e-4 relative after K = 9216).  The K loop is therefore cut into chunks of at most
 // kChunkKB k-blocks; every chunk accumulates from zero in TMEM and the epilogue warps add the chunk results into
 // fp32 registers with round-to-nearest.
-constexpr int kChunkKB = 8;
+constexpr int kChunkKBDefault = 16;
+constexpr int kConvThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two column halves x four lane quarters)
 
 __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item, int& n, int& y0, int& x0,
                                             int& nb) {
@@ -250,7 +253,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
 }
 
 template <int BN, int NP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ ConvKernelParams p) {
@@ -281,7 +284,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
   }
@@ -293,7 +296,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int num_kb = p.taps * p.kc_per_tap;
   // accumulation chunks (fp32 mode only; bf16 mode accumulates the whole K in one TMEM accumulator)
-  const int num_chunks = NP == 2 ? (num_kb + kChunkKB - 1) / kChunkKB : 1;
+  const int num_chunks = NP == 2 ? (num_kb + p.chunk_kb - 1) / p.chunk_kb : 1;
   const int chunk_len = (num_kb + num_chunks - 1) / num_chunks;
 
   if (warp == 0) {
@@ -365,11 +368,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;         // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // warp -> TMEM lane quarter (warp & 3, a hardware restriction) and column half ((warp - 2) >> 2)
+    constexpr int HB = BN / 2;      // columns per epilogue warp
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;  // pixel index inside the patch
     const int ly = row / kTileW, lx = row % kTileW;
-    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + half * HB;
     uint32_t acc = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int n, y0, x0, nb;
@@ -380,19 +386,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int Hp = p.H >> 1, Wp = p.W >> 1;
       const bool pool_anchor = ((lane & 1) == 0) && ((lane & 16) == 0) && ((y >> 1) < Hp) && ((x >> 1) < Wp);
       const size_t ppix = (size_t(n) * Hp + (y >> 1)) * Wp + (x >> 1);
+      const int cbase = nb * BN + half * HB;
 
       if (NP == 1) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < HB; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + c0, r);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_cols<NP>(v, p, nb * BN + c0, valid, pix, pool_anchor, ppix);
+          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, pool_anchor, ppix);
         }
         tc_fence_before();
         __syncwarp();
@@ -401,14 +408,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
       } else {
         // fp32 mode: sum the chunk accumulators (main + cross) in registers with round-to-nearest adds
-        float sum[BN];
+        float sum[HB];
 #pragma unroll
-        for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+        for (int j = 0; j < HB; ++j) sum[j] = 0.f;
         for (int ch = 0; ch < num_chunks; ++ch) {
           mbar_wait(&tfull_bar[acc], acc_phase);
           tc_fence_after();
 #pragma unroll
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = 0; c0 < HB; c0 += 32) {
             uint32_t r0[32], r1[32];
             tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + c0, r0);
             tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + BN + c0, r1);
@@ -423,11 +430,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (acc == 0) acc_phase ^= 1;
         }
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < HB; c0 += 32) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = sum[c0 + j];
-          epilogue_cols<NP>(v, p, nb * BN + c0, valid, pix, pool_anchor, ppix);
+          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, pool_anchor, ppix);
         }
       }
     }
@@ -458,7 +465,7 @@ static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int gri
     }
     attr_set = true;
   }
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  kern<<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("conv_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
@@ -469,6 +476,7 @@ static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int gri
 
 static int g_num_sms = 0;
 static int g_force_bn = 0;
+static int g_chunk_kb = kChunkKBDefault;
 static int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -477,6 +485,8 @@ static int num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
     const char* f = getenv("NSM_FORCE_BN");
     if (f) g_force_bn = atoi(f);
+    const char* c = getenv("NSM_CHUNK_KB");
+    if (c && atoi(c) > 0) g_chunk_kb = atoi(c);
   }
   return g_num_sms;
 }
@@ -528,6 +538,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.total_items = s.N * kp.tiles_x * kp.tiles_y * kp.n_blocks;
   kp.kc_per_tap = s.Cin / kKChunk;
   kp.fmt = s.fmt;
+  kp.chunk_kb = g_chunk_kb;
   const uint32_t ef = s.fmt == kFmtF16x2 ? kFmtF16 : kFmtBF16;  // all operand planes of a launch share one element type
   kp.idesc_hi = make_idesc_f16(128, BN, ef, ef, 0, 0);
   kp.idesc_lo = kp.idesc_hi;

@@ -50,8 +50,12 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   __half2 t = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ float f16lo_to_f32(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
-__device__ __forceinline__ float f16hi_to_f32(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+__device__ __forceinline__ float f16lo_to_f32(uint32_t w) {
+  return __low2float(*reinterpret_cast<const __half2*>(&w));
+}
+__device__ __forceinline__ float f16hi_to_f32(uint32_t w) {
+  return __high2float(*reinterpret_cast<const __half2*>(&w));
+}
 
 // Activation / weight storage formats ("fmt", equal to the C ABI's NSM_MODE_* values):
 //   0  one bf16 plane                      (bf16 mode, autocast rounding points)
@@ -60,8 +64,14 @@ __device__ __forceinline__ float f16hi_to_f32(uint32_t w) { return __half2float(
 constexpr int kFmtBf16 = 0, kFmtF16x2 = 1, kFmtBf16x2 = 2;
 __host__ __device__ __forceinline__ int fmt_planes(int fmt) { return fmt == 0 ? 1 : 2; }
 
+// two floats -> packed fp16 pair, saturating to +-65504 in ONE instruction (low half = a)
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_hi(float a, float b, int fmt) {
-  return fmt == kFmtF16x2 ? pack_f16(sat_f16(a), sat_f16(b)) : pack_bf16(a, b);
+  return fmt == kFmtF16x2 ? pack_f16_sat(a, b) : pack_bf16(a, b);
 }
 __device__ __forceinline__ float hi_lo_to_f32(uint32_t w, int fmt) {
   return fmt == kFmtF16x2 ? f16lo_to_f32(w) : bf16lo_to_f32(w);
@@ -71,7 +81,8 @@ __device__ __forceinline__ float hi_hi_to_f32(uint32_t w, int fmt) {
 }
 // lo plane word of a value pair given the packed hi word
 __device__ __forceinline__ uint32_t pack_lo_resid(float a, float b, uint32_t hw, int fmt) {
-  return fmt == kFmtF16x2 ? pack_f16(sat_f16(a - f16lo_to_f32(hw)), sat_f16(b - f16hi_to_f32(hw)))
+  // |residual| <= half an ulp of hi, so it cannot overflow unless hi itself saturated (then satfinite clamps it)
+  return fmt == kFmtF16x2 ? pack_f16_sat(a - f16lo_to_f32(hw), b - f16hi_to_f32(hw))
                           : pack_bf16(a - bf16lo_to_f32(hw), b - bf16hi_to_f32(hw));
 }
 __device__ __forceinline__ float lo_lo_to_f32(uint32_t w, int fmt) { return hi_lo_to_f32(w, fmt); }

@@ -573,6 +573,72 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
   if (p.fmt != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
 }
 
+// Fast path of the plain x2 up-sample (destination exactly 2hs x 2ws): one thread produces a 2x2 output block of 8
+// channels from the 3x3 source neighbourhood (rows/cols {b-1, b, b+1} clamped).  With align_corners the even output row
+// 2b interpolates source rows (b-1, b) and the odd row 2b+1 rows (b, b+1) -- see make_lerp: src = dst*(hs-1)/(2hs-1) --
+// so all register indices are static; horizontal interpolation is done once per source row (separable).
+__device__ __forceinline__ void up2x_weights(int b, int in_size, float& we0, float& we1, float& wo0, float& wo1) {
+  const int out_size = 2 * in_size;
+  const float scale = out_size > 1 ? float(in_size - 1) / float(out_size - 1) : 0.f;
+  const float se = scale * float(2 * b), so = scale * float(2 * b + 1);
+  // even: rows (b-1, b); ATen's (i0, lambda) may be (b, 0) when se rounds to b: identical value with weights (0, 1)
+  we1 = b == 0 ? 1.f : fminf(fmaxf(se - float(b - 1), 0.f), 1.f);
+  we0 = 1.f - we1;
+  wo1 = b >= in_size - 1 ? 0.f : fminf(fmaxf(so - float(b), 0.f), 1.f);
+  wo0 = 1.f - wo1;
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p, int cg_shift) {
+  const int cgs = 1 << cg_shift;
+  const int j = blockIdx.y * 256 + threadIdx.x;
+  if (j >= p.ws * cgs) return;
+  const int cg = j & (cgs - 1), xb = j >> cg_shift;
+  const int n = blockIdx.x / p.hs, yb = blockIdx.x - n * p.hs;
+  const bool rb = p.fmt == kFmtBf16;
+  float wye0, wye1, wyo0, wyo1, wxe0, wxe1, wxo0, wxo1;
+  up2x_weights(yb, p.hs, wye0, wye1, wyo0, wyo1);
+  up2x_weights(xb, p.ws, wxe0, wxe1, wxo0, wxo1);
+  const int rows[3] = {yb > 0 ? yb - 1 : 0, yb, yb < p.hs - 1 ? yb + 1 : p.hs - 1};
+  const int cols[3] = {xb > 0 ? xb - 1 : 0, xb, xb < p.ws - 1 ? xb + 1 : p.ws - 1};
+  float he[3][8], ho[3][8];   // horizontally interpolated source rows for the even / odd output column
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const size_t rbase = ((size_t)n * p.hs + rows[r]) * p.ws;
+    float a[8], b[8], c[8];
+    load8(p, (rbase + cols[0]) * p.C + cg * 8, a);
+    load8(p, (rbase + cols[1]) * p.C + cg * 8, b);
+    load8(p, (rbase + cols[2]) * p.C + cg * 8, c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      he[r][e] = wxe0 * a[e] + wxe1 * b[e];
+      ho[r][e] = wxo0 * b[e] + wxo1 * c[e];
+    }
+  }
+#pragma unroll
+  for (int oy = 0; oy < 2; ++oy) {
+    const float w0 = oy ? wyo0 : wye0, w1 = oy ? wyo1 : wye1;
+#pragma unroll
+    for (int ox = 0; ox < 2; ++ox) {
+      float r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float top = ox ? ho[oy][e] : he[oy][e], bot = ox ? ho[oy + 1][e] : he[oy + 1][e];
+        const float v = w0 * top + w1 * bot;
+        r[e] = rb ? rbf(v) : v;
+      }
+      const size_t o = (((size_t)n * p.hd + 2 * yb + oy) * p.wd + 2 * xb + ox) * p.C + cg * 8;
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        hw[e] = pack_hi(r[2 * e], r[2 * e + 1], p.fmt);
+        lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], p.fmt);
+      }
+      stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      if (p.fmt != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    }
+  }
+}
+
 int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes& dst, int hd, int wd, int fmt,
                    cudaStream_t st) {
   const int cgs = C / 8;
@@ -586,8 +652,13 @@ int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes
   p.s0 = (const uint8_t*)src.p[0]; p.s1 = (const uint8_t*)src.p[1];
   p.d0 = (uint8_t*)dst.p[0]; p.d1 = (uint8_t*)dst.p[1];
   p.N = N; p.hs = hs; p.ws = ws; p.C = C; p.hd = hd; p.wd = wd; p.fmt = fmt;
-  dim3 grid((unsigned)(N * hd), (unsigned)((wd * cgs + 255) / 256));
-  upsample_match_kernel<<<grid, 256, 0, st>>>(p, shift);
+  if (hd == 2 * hs && wd == 2 * ws) {
+    dim3 grid((unsigned)(N * hs), (unsigned)((ws * cgs + 255) / 256));
+    upsample2x_kernel<<<grid, 256, 0, st>>>(p, shift);
+  } else {
+    dim3 grid((unsigned)(N * hd), (unsigned)((wd * cgs + 255) / 256));
+    upsample_match_kernel<<<grid, 256, 0, st>>>(p, shift);
+  }
   NSM_CHECK_LAUNCH("upsample_match");
   return 0;
 }
