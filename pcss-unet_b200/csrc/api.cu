@@ -309,7 +309,9 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     return 0;
   };
   auto up = [&](const char* src, int slevel, int C, const char* dst, int dlevel) -> int {
-    ProfScope ps("upsample", 0.0,
+    char unm[32];
+    snprintf(unm, sizeof(unm), "upsample %s", dst);
+    ProfScope ps(unm, 0.0,
                  (double(B) * WL.lv[slevel].h * WL.lv[slevel].w + double(B) * WL.lv[dlevel].h * WL.lv[dlevel].w) *
                      C * 2.0 * np, st);
     return upsample_match(buf(src), B, WL.lv[slevel].h, WL.lv[slevel].w, C, buf(dst), WL.lv[dlevel].h,
