@@ -44,6 +44,21 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def measured_traffic():
+    """dram__bytes_read+write of the dominant launch from the latest committed `ncu --set full` capture (profiles/)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None
+    try:
+        d = json.load(open(files[-1]))
+        k = next(iter(d))
+        return {"kernel_launch": k, "dram_bytes": d[k]["dram_bytes_per_launch"],
+                "algorithmic_bytes": d[k]["algorithmic_bytes_per_launch"], "source": os.path.basename(files[-1])}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -186,6 +201,7 @@ def run_b200(args):
         # ---- device-resident timing -------------------------------------------------------------------------
         evs = []
         barrier()
+        launches0 = nsm.launch_count()
         for _ in range(args.steps):
             flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -194,6 +210,7 @@ def run_b200(args):
             e.record()
             evs.append((s, e))
         barrier()
+        launches = nsm.launch_count() - launches0
         dev_ms = sum(s.elapsed_time(e) for s, e in evs)
         # ---- end-to-end timing through the host-buffer entry point -------------------------------------------
         for _ in range(2):
@@ -247,7 +264,7 @@ def run_b200(args):
     roofline = {"kernel": f"conv_gemm_kernel<BN,{planes}> (tcgen05 implicit GEMM, {len(conv) // max(args.steps, 1)} "
                           "launches/step)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops"], "traffic": None,
+                "frac": achieved / pk["bf16_tflops"], "traffic": measured_traffic(),
                 "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json)",
                 "mma_work_factor": 3 if precision == "fp32" else 1,
                 "note": "achieved = algorithmic 2*M*K*N FLOPs of the conv launches / their CUDA-event time inside "
@@ -259,7 +276,7 @@ def run_b200(args):
     line = {"metric": "U-Net inference Mpix/s @1080p", "value": value, "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32 (split-bf16 x3, fp32 accumulate)" if precision == "fp32" else "bf16",
+            "dtype": "fp32 (hi+lo fp16 split, 3 MMAs/MAC, fp32 accumulate)" if precision == "fp32" else "bf16",
             "data": "synthetic",
             "config": {"workload": f"cfg1: U-Net inference, one {W}x{H} synthetic G-buffer frame per GPU "
                                    f"(batch {B}), {precision} mode, eval BatchNorm",
@@ -268,7 +285,7 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 19 * args.steps,
+            "gpu_launches": launches,
             "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -343,6 +360,7 @@ def run_b200_train(args):
     sampler.start()
     evs = []
     barrier()
+    launches0 = nsm.launch_count()
     for _ in range(args.steps):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,6 +369,7 @@ def run_b200_train(args):
         e.record()
         evs.append((s, e))
     barrier()
+    launches = nsm.launch_count() - launches0
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
     t_e2e = 0.0
     last = None
@@ -411,9 +430,8 @@ def run_b200_train(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": (x_host.numel() + t_host.numel()) * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_loss": last},
-            "gpu_launches": len(rows) and None,
+            "gpu_launches": launches,
             "roofline": roofline}
-    line["gpu_launches"] = int(getattr(nsm, "launch_count", lambda: 0)()) or None
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -40,6 +40,8 @@ extern "C" {
 
 const char* nsm_last_error(void);
 int nsm_version(void);
+/* kernels launched by this library since load (bench.py: gpu_launches) */
+long long nsm_launch_count(void);
 /* 0 if the current CUDA device is compute capability 10.x (B200), else non-zero + message */
 int nsm_check_device(void);
 

@@ -175,6 +175,7 @@ extern "C" {
 
 const char* nsm_last_error(void) { return nsm::last_error(); }
 int nsm_version(void) { return 100; }
+long long nsm_launch_count(void) { return launch_count(); }
 
 int nsm_check_device(void) {
   int dev = 0;

@@ -22,6 +22,7 @@
 // significand bits) and the issuer runs a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into the same fp32 accumulator: operand
 // residuals <= 2^-23, dropped a_lo*w_lo <= 2^-22 -> ~4e-6 on the network output (CPU emulation), i.e. 3xTF32-class
 // accuracy at bf16-pipe speed.  Values are saturated to the fp16 range (|v| <= 65504).
+#include <atomic>
 #include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
@@ -43,6 +44,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------
 // TMA descriptor encoding through the driver entry point
@@ -471,6 +476,7 @@ static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int gri
     set_error("conv_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
     return 1;
   }
+  count_launch();
   return 0;
 }
 

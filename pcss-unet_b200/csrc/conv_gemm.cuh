@@ -44,5 +44,8 @@ int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64
                       const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes);
 
 void set_error(const char* fmt, ...);
+// number of kernels this library has launched (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
+long long launch_count();
 
 }  // namespace nsm

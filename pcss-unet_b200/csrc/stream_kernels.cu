@@ -14,6 +14,7 @@ namespace nsm {
       set_error("%s launch failed: %s", name, cudaGetErrorString(e__));    \
       return 1;                                                            \
     }                                                                      \
+    count_launch();                                                        \
   } while (0)
 
 static inline int grid_for(long long work, int block, int cap = 148 * 16) {

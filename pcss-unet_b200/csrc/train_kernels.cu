@@ -15,6 +15,7 @@ namespace nsm {
       set_error("%s launch failed: %s", name, cudaGetErrorString(e__));    \
       return 1;                                                            \
     }                                                                      \
+    count_launch();                                                        \
   } while (0)
 
 static inline int grid_for(long long work, int block, int cap = 148 * 16) {
@@ -170,17 +171,35 @@ int bn_finalize(const double* sums, long long P, int C, const float* gamma, cons
 // ------------------------------------------------------------------------------------------------
 // BN apply + LeakyReLU + Dropout2d mask (+ residual, + AvgPool2d(2))
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bn_act8(float* v, const BnActParams& p, int n, int c0, bool rb) {
+struct Chan8 {
+  float s[8], t[8];   // BN scale / shift of the thread's 8 channels
+};
+__device__ __forceinline__ Chan8 load_chan8(const float* scale, const float* shift, int c0) {
+  Chan8 c;
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+  const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift + c0)), t1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+  c.s[0] = s0.x; c.s[1] = s0.y; c.s[2] = s0.z; c.s[3] = s0.w; c.s[4] = s1.x; c.s[5] = s1.y; c.s[6] = s1.z; c.s[7] = s1.w;
+  c.t[0] = t0.x; c.t[1] = t0.y; c.t[2] = t0.z; c.t[3] = t0.w; c.t[4] = t1.x; c.t[5] = t1.y; c.t[6] = t1.z; c.t[7] = t1.w;
+  return c;
+}
+__device__ __forceinline__ void load_mask8(const float* mask, size_t off, float* m) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(mask + off)), b = __ldg(reinterpret_cast<const float4*>(mask + off + 4));
+  m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+}
+
+__device__ __forceinline__ void bn_act8(float* v, const BnActParams& p, const Chan8& ch, int n, int c0, bool rb) {
+  float m[8];
+  if (p.mask) load_mask8(p.mask, (size_t)n * p.C + c0, m);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    float t = fmaf(v[e], __ldg(p.scale + c0 + e), __ldg(p.shift + c0 + e));
+    float t = fmaf(v[e], ch.s[e], ch.t[e]);
     if (rb) t = rbf(t);
     if (p.lrelu) {
       t = lrelu02(t);
       if (rb) t = rbf(t);
     }
     if (p.mask) {
-      t *= __ldg(p.mask + (size_t)n * p.C + c0 + e);
+      t *= m[e];
       if (rb) t = rbf(t);
     }
     v[e] = t;
@@ -193,6 +212,8 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
   const long long total = (long long)p.N * p.H * p.W * cgs;
   const int cg_shift = __ffs(cgs) - 1;                 // channel-group counts are powers of two
   const unsigned HW = (unsigned)(p.H * p.W);
+  // the grid stride (gridDim.x * 256) is a multiple of cgs, so a thread's channel group never changes
+  const Chan8 ch = load_chan8(p.scale, p.shift, int((blockIdx.x * 256u + threadIdx.x) & (unsigned)(cgs - 1)) * 8);
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const unsigned iu = (unsigned)i;                   // total < 2^32 (host check): 32-bit index math only
     const int cg = int(iu & (unsigned)(cgs - 1));
@@ -200,7 +221,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
     const int n = int(pix / HW);
     float v[8];
     load8(p.z, (size_t)pix * p.C + cg * 8, p.fmt, v);
-    bn_act8(v, p, n, cg * 8, rb);
+    bn_act8(v, p, ch, n, cg * 8, rb);
     if (p.residual.p[0]) {
       float r[8];
       load8(p.residual, (size_t)pix * p.C + cg * 8, p.fmt, r);
@@ -217,6 +238,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
   const bool rb = p.fmt == kFmtBf16;
   const int Hq = (p.H + 1) / 2, Wq = (p.W + 1) / 2, Hp = p.H / 2, Wp = p.W / 2;
   const long long total = (long long)p.N * Hq * Wq * cgs;
+  const Chan8 ch = load_chan8(p.scale, p.shift, int((blockIdx.x * 256u + threadIdx.x) % (unsigned)cgs) * 8);
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const unsigned iu = (unsigned)i;
     const int cg = int(iu % (unsigned)cgs);
@@ -235,7 +257,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
         const size_t pix = ((size_t)n * p.H + y) * p.W + x;
         float v[8];
         load8(p.z, pix * p.C + cg * 8, p.fmt, v);
-        bn_act8(v, p, n, cg * 8, rb);
+        bn_act8(v, p, ch, n, cg * 8, rb);
         store8(p.out, pix * p.C + cg * 8, p.fmt, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) s[e] += v[e];
@@ -270,20 +292,35 @@ int bn_act(const BnActParams& p, cudaStream_t st) {
 // BatchNorm backward
 // ------------------------------------------------------------------------------------------------
 // g = dy * mask * LeakyReLU'(z*scale + shift), with the bf16 rounding points of autograd under autocast
-__device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, size_t elem, int n, int c0, bool rb, float* g,
-                                          float* xhat) {
-  float dy[8], z[8];
+struct BwdChan8 {
+  float s[8], t[8], mu[8], is[8];
+};
+__device__ __forceinline__ BwdChan8 load_bwd_chan8(const BnBwdParams& p, int c0) {
+  BwdChan8 c;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    c.s[e] = __ldg(p.scale + c0 + e);
+    c.t[e] = __ldg(p.shift + c0 + e);
+    c.mu[e] = __ldg(p.mean + c0 + e);
+    c.is[e] = __ldg(p.invstd + c0 + e);
+  }
+  return c;
+}
+__device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, const BwdChan8& ch, size_t elem, int n, int c0, bool rb,
+                                          float* g, float* xhat) {
+  float dy[8], z[8], m[8];
   load8(p.dy, elem, p.fmt, dy);
   load8(p.z, elem, p.fmt, z);
+  if (p.mask) load_mask8(p.mask, (size_t)n * p.C + c0, m);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     float t = dy[e];
     if (p.mask) {
-      t *= __ldg(p.mask + (size_t)n * p.C + c0 + e);
+      t *= m[e];
       if (rb) t = rbf(t);
     }
     if (p.lrelu) {
-      float y = fmaf(z[e], __ldg(p.scale + c0 + e), __ldg(p.shift + c0 + e));
+      float y = fmaf(z[e], ch.s[e], ch.t[e]);
       if (rb) y = rbf(y);
       if (!(y > 0.f)) {
         t *= 0.2f;
@@ -291,7 +328,7 @@ __device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, size_t elem, int
       }
     }
     g[e] = t;
-    xhat[e] = (z[e] - __ldg(p.mean + c0 + e)) * __ldg(p.invstd + c0 + e);
+    xhat[e] = (z[e] - ch.mu[e]) * ch.is[e];
   }
 }
 
@@ -300,6 +337,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const bool rb = p.fmt == kFmtBf16;
   const long long P = (long long)p.N * p.H * p.W, HW = (long long)p.H * p.W;
+  const BwdChan8 ch = load_bwd_chan8(p, cg * 8);
   double acc[2][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.0;
@@ -311,7 +349,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
     for (int e = 0; e < 8; ++e) fs[e] = fq[e] = 0.f;
     for (int it = 0; it < 16 && px < P; ++it, px += stride) {
       float g[8], xh[8];
-      bn_bwd_g8(p, (size_t)px * p.C + cg * 8, int((unsigned)px / (unsigned)HW), cg * 8, rb, g, xh);
+      bn_bwd_g8(p, ch, (size_t)px * p.C + cg * 8, int((unsigned)px / (unsigned)HW), cg * 8, rb, g, xh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         fs[e] += g[e];
@@ -341,12 +379,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const bool rb = p.fmt == kFmtBf16;
   const long long P = (long long)p.N * p.H * p.W, HW = (long long)p.H * p.W;
+  const BwdChan8 ch = load_bwd_chan8(p, cg * 8);
   float mg[8], mgx[8], sc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     mg[e] = float(p.sums[cg * 8 + e] / double(P));
     mgx[e] = float(p.sums[p.C + cg * 8 + e] / double(P));
-    sc[e] = __ldg(p.scale + cg * 8 + e);
+    sc[e] = ch.s[e];
   }
   double acc[1][8];
 #pragma unroll
@@ -360,7 +399,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
     for (int it = 0; it < 16 && px < P; ++it, px += stride) {
       float g[8], xh[8], dz[8];
       const size_t elem = (size_t)px * p.C + cg * 8;
-      bn_bwd_g8(p, elem, int((unsigned)px / (unsigned)HW), cg * 8, rb, g, xh);
+      bn_bwd_g8(p, ch, elem, int((unsigned)px / (unsigned)HW), cg * 8, rb, g, xh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         float t = sc[e] * (g[e] - mg[e] - xh[e] * mgx[e]);
@@ -532,9 +571,84 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const Planes dout, in
     store8(din, (size_t)pixi * C + cg * 8, fmt, acc);
   }
 }
+// Adjoint of the plain x2 align_corners up-sample (ho == 2hi, wo == 2wi): source pixel r receives from output rows
+// 2r-1 (weight wo1(r-1)), 2r (we1(r)), 2r+1 (wo0(r)), 2r+2 (we0(r+1)) -- the transposed stencil of upsample2x_kernel in
+// stream_kernels.cu -- and likewise for columns; separable, 16 loads of 16 B per thread, static indices.
+__device__ __forceinline__ void up2x_w(int b, int in_size, float& we0, float& we1, float& wo0, float& wo1) {
+  const int out_size = 2 * in_size;
+  const float scale = out_size > 1 ? float(in_size - 1) / float(out_size - 1) : 0.f;
+  const float se = scale * float(2 * b), so = scale * float(2 * b + 1);
+  we1 = b == 0 ? 1.f : fminf(fmaxf(se - float(b - 1), 0.f), 1.f);
+  we0 = 1.f - we1;
+  wo1 = b >= in_size - 1 ? 0.f : fminf(fmaxf(so - float(b), 0.f), 1.f);
+  wo0 = 1.f - wo1;
+}
+__device__ __forceinline__ void up2x_adjoint_weights(int r, int in_size, float* w) {
+  float a0, a1, b0, b1;
+  w[0] = w[3] = 0.f;
+  if (r > 0) {
+    up2x_w(r - 1, in_size, a0, a1, b0, b1);
+    w[0] = b1;                       // odd row 2(r-1)+1 uses sources (r-1, r)
+  }
+  up2x_w(r, in_size, a0, a1, b0, b1);
+  w[1] = a1;                         // even row 2r uses (r-1, r)
+  w[2] = b0;                         // odd row 2r+1 uses (r, r+1)
+  if (r == 0) w[1] = a0 + a1;        // row 0: both taps hit source 0
+  if (r == in_size - 1) w[2] = b0 + b1;
+  if (r < in_size - 1) {
+    up2x_w(r + 1, in_size, a0, a1, b0, b1);
+    w[3] = a0;                       // even row 2(r+1) uses (r, r+1)
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const Planes dout, int N, int C, const Planes din, int hi,
+                                                             int wi, int fmt, int cg_shift) {
+  const int cgs = 1 << cg_shift;
+  const int j = blockIdx.y * 256 + threadIdx.x;
+  if (j >= wi * cgs) return;
+  const int cg = j & (cgs - 1), q = j >> cg_shift;
+  const int n = blockIdx.x / hi, r = blockIdx.x - n * hi;
+  const int ho = 2 * hi, wo = 2 * wi;
+  float wy[4], wx[4];
+  up2x_adjoint_weights(r, hi, wy);
+  up2x_adjoint_weights(q, wi, wx);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int y = 2 * r - 1 + a;
+    if (y < 0 || y >= ho || wy[a] == 0.f) continue;
+    float t[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t[e] = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int x = 2 * q - 1 + b;
+      if (x < 0 || x >= wo || wx[b] == 0.f) continue;
+      float d[8];
+      load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, fmt, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = fmaf(wx[b], d[e], t[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(wy[a], t[e], acc[e]);
+  }
+  store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, fmt, acc);
+}
+
 int bilinear_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,
                  cudaStream_t st) {
   if (check_c("bilinear_bwd", C)) return 1;
+  if (ho == 2 * hi && wo == 2 * wi) {
+    const int cgs = C / 8;
+    int shift = 0;
+    while ((1 << shift) < cgs) ++shift;
+    dim3 grid((unsigned)(N * hi), (unsigned)((wi * cgs + 255) / 256));
+    upsample2x_bwd_kernel<<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+    NSM_CHECK_LAUNCH("upsample2x_bwd");
+    return 0;
+  }
   bilinear_bwd_kernel<<<grid_for((long long)N * hi * wi * (C / 8), 256), 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi,
                                                                                          fmt);
   NSM_CHECK_LAUNCH("bilinear_bwd");

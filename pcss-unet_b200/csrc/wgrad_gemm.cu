@@ -304,6 +304,7 @@ static int wgrad_launch_t(const CUtensorMap* maps, const WgradKernelParams& kp, 
     set_error("wgrad_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
     return 1;
   }
+  count_launch(2);   // GEMM + split-K reduce
   return 0;
 }
 

@@ -45,6 +45,7 @@ class ConvArgs(Structure):
 def _declare(lib):
     lib.nsm_last_error.restype = c_char_p
     lib.nsm_version.restype = c_int
+    lib.nsm_launch_count.restype = c_longlong
     lib.nsm_check_device.restype = c_int
     lib.nsm_unet_packed_bytes.restype = c_size_t
     lib.nsm_unet_packed_bytes.argtypes = [c_int]
@@ -106,6 +107,7 @@ TRAIN_EXPORTS = [
 ]
 
 EXPORTS = TRAIN_EXPORTS + [
+    "nsm_launch_count",
     "nsm_last_error", "nsm_version", "nsm_check_device", "nsm_unet_packed_bytes", "nsm_unet_pack",
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
@@ -158,6 +160,10 @@ def mode_planes(mode: int) -> int:
 # ---------------------------------------------------------------------------------------------------------------
 # thin typed wrappers
 # ---------------------------------------------------------------------------------------------------------------
+
+def launch_count() -> int:
+    return int(lib().nsm_launch_count())
+
 
 def profile_enable(on: bool):
     check(lib().nsm_profile_enable(int(on)), "nsm_profile_enable")
