@@ -166,6 +166,9 @@ struct ProfScope {
 
 using namespace nsm;
 
+static inline Planes mk(const void* a, const void* b) { return Planes{{const_cast<void*>(a), const_cast<void*>(b)}}; }
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
 #define NSM_TRY(expr)          \
   do {                         \
     if ((expr) != 0) return 1; \
@@ -467,6 +470,7 @@ int nsm_conv_fwd(const nsm_conv_args* a, void* stream) {
 
 int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, void* const* dst, int hd, int wd,
                        int mode, void* stream) {
+  ProfScope ps_("upsample_match", 0.0, (double(N) * hs * ws + double(N) * hd * wd) * C * 2.0 * fmt_planes(mode), S(stream));
   Planes s = {{const_cast<void*>(src[0]), const_cast<void*>(src[1])}};
   Planes d = {{dst[0], dst[1]}};
   return upsample_match(s, N, hs, ws, C, d, hd, wd, mode, static_cast<cudaStream_t>(stream));
@@ -474,6 +478,7 @@ int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, voi
 
 int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
                         long long numel, float coef_l1, float coef_pert, float* grad, double* acc, void* stream) {
+  ProfScope ps_("l1_loss", 0.0, double(numel) * 4.0 * (3 + n_perturbed), S(stream));
   return l1_loss_fwd_bwd(out, target, perturbed, n_perturbed, numel, coef_l1, coef_pert, grad, acc,
                          static_cast<cudaStream_t>(stream));
 }
@@ -491,10 +496,9 @@ int nsm_perturb(const float* x, const float* noise, float* out, int count, long 
 }
 
 // ---------------------------------------------------------------------------------------------- training stages
-static inline Planes mk(const void* a, const void* b) { return Planes{{const_cast<void*>(a), const_cast<void*>(b)}}; }
-static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
 int nsm_bn_stats(const void* z0, const void* z1, long long P, int C, int mode, double* sums, void* stream) {
+  ProfScope ps_("bn_stats", 0.0, double(P) * C * 2.0 * fmt_planes(mode), S(stream));
   return bn_stats(mk(z0, z1), P, C, mode, sums, S(stream));
 }
 int nsm_bn_finalize(const double* sums, long long P, int C, const float* gamma, const float* beta, float eps,
@@ -506,6 +510,7 @@ int nsm_bn_finalize(const double* sums, long long P, int C, const float* gamma, 
 int nsm_bn_act(const void* z0, const void* z1, int N, int H, int W, int C, int mode, const float* scale,
                const float* shift, const float* mask, int lrelu, const void* res0, const void* res1, void* out0,
                void* out1, void* pool0, void* pool1, void* stream) {
+  ProfScope ps_("bn_act", 0.0, double(N) * H * W * C * 4.0 * fmt_planes(mode), S(stream));
   BnActParams p;
   p.z = mk(z0, z1); p.out = mk(out0, out1); p.residual = mk(res0, res1); p.pool = mk(pool0, pool1);
   p.N = N; p.H = H; p.W = W; p.C = C; p.fmt = mode; p.scale = scale; p.shift = shift; p.mask = mask; p.lrelu = lrelu;
@@ -514,16 +519,18 @@ int nsm_bn_act(const void* z0, const void* z1, int N, int H, int W, int C, int m
 int nsm_bn_bwd(const void* dy0, const void* dy1, const void* z0, const void* z1, int N, int H, int W, int C, int mode,
                const float* scale, const float* shift, const float* mask, const float* mean, const float* invstd,
                int lrelu, double* sums, void* dz0, void* dz1, float* dgamma, float* dbeta, float* dbias, void* stream) {
+  ProfScope ps_("bn_bwd", 0.0, double(N) * H * W * C * 10.0 * fmt_planes(mode), S(stream));
   BnBwdParams p;
   p.dy = mk(dy0, dy1); p.z = mk(z0, z1); p.dz = mk(dz0, dz1);
   p.N = N; p.H = H; p.W = W; p.C = C; p.fmt = mode; p.scale = scale; p.shift = shift; p.mask = mask; p.mean = mean;
   p.invstd = invstd; p.lrelu = lrelu; p.sums = sums; p.dbias = sums + 2 * C;
   NSM_TRY(bn_bwd_reduce(p, S(stream)));
   NSM_TRY(bn_bwd_apply(p, S(stream)));
-  return bn_bwd_finalize(sums, sums + 2 * C, C, mode == NSM_MODE_BF16, dgamma, dbeta, dbias, S(stream));
+  return bn_bwd_finalize(sums, sums + 2 * C, mean, invstd, C, mode == NSM_MODE_BF16, dgamma, dbeta, dbias, S(stream));
 }
 int nsm_pool_bwd_add(const void* a0, const void* a1, const void* dp0, const void* dp1, void* out0, void* out1, int N,
                      int H, int W, int C, int mode, void* stream) {
+  ProfScope ps_("pool_bwd_add", 0.0, double(N) * H * W * C * 4.5 * fmt_planes(mode), S(stream));
   return pool_bwd_add(mk(a0, a1), mk(dp0, dp1), mk(out0, out1), N, H, W, C, mode, S(stream));
 }
 int nsm_planes_add(const void* a0, const void* a1, const void* b0, const void* b1, void* out0, void* out1,
@@ -532,19 +539,23 @@ int nsm_planes_add(const void* a0, const void* a1, const void* b0, const void* b
 }
 int nsm_bilinear_bwd(const void* dout0, const void* dout1, int N, int ho, int wo, int C, void* din0, void* din1, int hi,
                      int wi, int mode, void* stream) {
+  ProfScope ps_("bilinear_bwd", 0.0, (double(N) * ho * wo + double(N) * hi * wi) * C * 2.0 * fmt_planes(mode), S(stream));
   return bilinear_bwd(mk(dout0, dout1), N, ho, wo, C, mk(din0, din1), hi, wi, mode, S(stream));
 }
 int nsm_train_input_prep(const float* x, int N, int Hin, int Win, void* out0, void* out1, int mode, void* stream) {
+  ProfScope ps_("train_input_prep", 0.0, double(N) * Hin * Win * 16.0, S(stream));
   return train_input_prep(x, N, Hin, Win, mk(out0, out1), mode, S(stream));
 }
 int nsm_train_input_grad(const void* d0, const void* d1, int N, int H, int W, float* dx, int mode, void* stream) {
   return train_input_grad(mk(d0, d1), N, H, W, dx, mode, S(stream));
 }
 int nsm_sigmoid_shuffle_fwd(const void* c0, const void* c1, int N, int h, int w, int mode, float* y, void* stream) {
+  ProfScope ps_("sigmoid_shuffle_fwd", 0.0, double(N) * h * w * 16.0, S(stream));
   return sigmoid_shuffle_fwd(mk(c0, c1), N, h, w, mode, y, S(stream));
 }
 int nsm_sigmoid_shuffle_bwd(const float* dy, const float* y, int N, int h, int w, int mode, void* d0, void* d1,
                             void* stream) {
+  ProfScope ps_("sigmoid_shuffle_bwd", 0.0, double(N) * h * w * 32.0, S(stream));
   return sigmoid_shuffle_bwd(dy, y, N, h, w, mode, mk(d0, d1), S(stream));
 }
 int nsm_pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int dgrad, int mode,

@@ -57,6 +57,35 @@ __device__ __forceinline__ void store8(const Planes& p, size_t elem, int fmt, co
   if (fmt != kFmtBf16) stg16(reinterpret_cast<uint8_t*>(p.p[1]) + elem * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
 }
 
+// raw 16-byte words of 8 channels (both planes): lets a loop issue several independent loads before converting
+struct Raw8 {
+  uint4 h, l;
+};
+__device__ __forceinline__ Raw8 load_raw8(const Planes& p, size_t elem, int fmt) {
+  Raw8 r;
+  r.h = ldg16(reinterpret_cast<const uint8_t*>(p.p[0]) + elem * 2);
+  if (fmt != kFmtBf16) r.l = ldg16(reinterpret_cast<const uint8_t*>(p.p[1]) + elem * 2);
+  else r.l = make_uint4(0, 0, 0, 0);
+  return r;
+}
+__device__ __forceinline__ void unpack8(const Raw8& r, int fmt, float* v) {
+  const uint32_t hw[4] = {r.h.x, r.h.y, r.h.z, r.h.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = hi_lo_to_f32(hw[e], fmt);
+    v[2 * e + 1] = hi_hi_to_f32(hw[e], fmt);
+  }
+  if (fmt != kFmtBf16) {
+    const uint32_t lw[4] = {r.l.x, r.l.y, r.l.z, r.l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] += lo_lo_to_f32(lw[e], fmt);
+      v[2 * e + 1] += lo_hi_to_f32(lw[e], fmt);
+    }
+  }
+}
+constexpr int kBatch = 4;   // independent pixels in flight per thread (memory-level parallelism)
+
 // Block-level per-channel reduction of NV value sets; thread t owns channel group (t % groups), 256 threads.
 template <int NV>
 __device__ __forceinline__ void block_channel_reduce(const double (&acc)[NV][8], int C, double* out) {
@@ -90,13 +119,22 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const Planes z, long long
     float fs[8], fq[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) fs[e] = fq[e] = 0.f;
-    for (int it = 0; it < 16 && p < P; ++it, p += stride) {
-      float v[8];
-      load8(z, (size_t)p * C + cg * 8, fmt, v);
+    for (int it = 0; it < 4 && p < P; ++it, p += kBatch * stride) {
+      Raw8 r[kBatch];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        fs[e] += v[e];
-        fq[e] = fmaf(v[e], v[e], fq[e]);
+      for (int u = 0; u < kBatch; ++u)
+        if (p + u * stride < P) r[u] = load_raw8(z, (size_t)(p + u * stride) * C + cg * 8, fmt);
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (p + u * stride < P) {
+          float v[8];
+          unpack8(r[u], fmt, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            fs[e] += v[e];
+            fq[e] = fmaf(v[e], v[e], fq[e]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -127,7 +165,7 @@ static int check_c(const char* who, int C) {
 int bn_stats(const Planes& z, long long P, int C, int fmt, double* sums, cudaStream_t st) {
   if (check_c("bn_stats", C)) return 1;
   const int lanes = 256 / (C / 8);
-  bn_stats_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(z, P, C, fmt, sums);
+  bn_stats_kernel<<<grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8), 256, 0, st>>>(z, P, C, fmt, sums);
   NSM_CHECK_LAUNCH("bn_stats");
   return 0;
 }
@@ -292,25 +330,48 @@ int bn_act(const BnActParams& p, cudaStream_t st) {
 // BatchNorm backward
 // ------------------------------------------------------------------------------------------------
 // g = dy * mask * LeakyReLU'(z*scale + shift), with the bf16 rounding points of autograd under autocast
-struct BwdChan8 {
-  float s[8], t[8], mu[8], is[8];
-};
-__device__ __forceinline__ BwdChan8 load_bwd_chan8(const BnBwdParams& p, int c0) {
-  BwdChan8 c;
+// Lean formulation (the kernels are instruction-bound, not byte-bound):
+//   g    = dy * mask * (z*s + t > 0 ? 1 : 0.2)                 (bf16 rounding points of autograd kept in bf16 mode)
+//   pass 1 accumulates S1 = sum g and S2 = sum g*z              (sum g*xhat = (S2 - mean*S1) * invstd)
+//   pass 2 writes dz = s*g + A*z + B with per-channel A = -s*invstd*m2, B = -s*m1 + s*invstd*m2*mean,
+//          m1 = S1/P, m2 = sum g*xhat / P                       (= s * (g - m1 - xhat*m2))
+// Training tensors always hold bf16 elements (fmt 0: one plane, fmt 2: hi+lo planes) -> NPL template, shift unpack.
+template <int NPL>
+__device__ __forceinline__ void unpack8_bf16(const Raw8& r, float* v) {
+  const uint32_t hw[4] = {r.h.x, r.h.y, r.h.z, r.h.w};
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    c.s[e] = __ldg(p.scale + c0 + e);
-    c.t[e] = __ldg(p.shift + c0 + e);
-    c.mu[e] = __ldg(p.mean + c0 + e);
-    c.is[e] = __ldg(p.invstd + c0 + e);
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = bf16lo_to_f32(hw[e]);
+    v[2 * e + 1] = bf16hi_to_f32(hw[e]);
   }
-  return c;
+  if (NPL == 2) {
+    const uint32_t lw[4] = {r.l.x, r.l.y, r.l.z, r.l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] += bf16lo_to_f32(lw[e]);
+      v[2 * e + 1] += bf16hi_to_f32(lw[e]);
+    }
+  }
 }
-__device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, const BwdChan8& ch, size_t elem, int n, int c0, bool rb,
-                                          float* g, float* xhat) {
-  float dy[8], z[8], m[8];
-  load8(p.dy, elem, p.fmt, dy);
-  load8(p.z, elem, p.fmt, z);
+template <int NPL>
+__device__ __forceinline__ Raw8 load_raw8_t(const Planes& p, size_t elem) {
+  Raw8 r;
+  r.h = ldg16(reinterpret_cast<const uint8_t*>(p.p[0]) + elem * 2);
+  if (NPL == 2) r.l = ldg16(reinterpret_cast<const uint8_t*>(p.p[1]) + elem * 2);
+  return r;
+}
+
+struct BwdChan8 {
+  float s[8], t[8];
+};
+
+template <int NPL>
+__device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, const BwdChan8& ch, const Raw8& rdy, const Raw8& rz, int n,
+                                          int c0, float* g, float* z) {
+  constexpr bool rb = NPL == 1;
+  float dy[8], m[8];
+  unpack8_bf16<NPL>(rdy, dy);
+  unpack8_bf16<NPL>(rz, z);
   if (p.mask) load_mask8(p.mask, (size_t)n * p.C + c0, m);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -319,25 +380,26 @@ __device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, const BwdChan8& 
       t *= m[e];
       if (rb) t = rbf(t);
     }
-    if (p.lrelu) {
-      float y = fmaf(z[e], ch.s[e], ch.t[e]);
-      if (rb) y = rbf(y);
-      if (!(y > 0.f)) {
-        t *= 0.2f;
-        if (rb) t = rbf(t);
-      }
+    if (p.lrelu && !(fmaf(z[e], ch.s[e], ch.t[e]) > 0.f)) {   // the sign of y survives its bf16 rounding
+      t *= 0.2f;
+      if (rb) t = rbf(t);
     }
     g[e] = t;
-    xhat[e] = (z[e] - ch.mu[e]) * ch.is[e];
   }
 }
 
+template <int NPL>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
   const int groups = p.C / 8, lanes = 256 / groups;
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
-  const bool rb = p.fmt == kFmtBf16;
-  const long long P = (long long)p.N * p.H * p.W, HW = (long long)p.H * p.W;
-  const BwdChan8 ch = load_bwd_chan8(p, cg * 8);
+  const long long P = (long long)p.N * p.H * p.W;
+  const unsigned HW = (unsigned)(p.H * p.W);
+  BwdChan8 ch;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    ch.s[e] = __ldg(p.scale + cg * 8 + e);
+    ch.t[e] = __ldg(p.shift + cg * 8 + e);
+  }
   double acc[2][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.0;
@@ -347,13 +409,28 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
     float fs[8], fq[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) fs[e] = fq[e] = 0.f;
-    for (int it = 0; it < 16 && px < P; ++it, px += stride) {
-      float g[8], xh[8];
-      bn_bwd_g8(p, ch, (size_t)px * p.C + cg * 8, int((unsigned)px / (unsigned)HW), cg * 8, rb, g, xh);
+    for (int it = 0; it < 8 && px < P; ++it, px += 2 * stride) {
+      const bool ok1 = px + stride < P;
+      const size_t e0 = (size_t)px * p.C + cg * 8, e1 = (size_t)(px + stride) * p.C + cg * 8;
+      Raw8 dy0 = load_raw8_t<NPL>(p.dy, e0), z0 = load_raw8_t<NPL>(p.z, e0), dy1, z1;
+      if (ok1) {
+        dy1 = load_raw8_t<NPL>(p.dy, e1);
+        z1 = load_raw8_t<NPL>(p.z, e1);
+      }
+      float g[8], z[8];
+      bn_bwd_g8<NPL>(p, ch, dy0, z0, int((unsigned)px / HW), cg * 8, g, z);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         fs[e] += g[e];
-        fq[e] = fmaf(g[e], xh[e], fq[e]);
+        fq[e] = fmaf(g[e], z[e], fq[e]);
+      }
+      if (ok1) {
+        bn_bwd_g8<NPL>(p, ch, dy1, z1, int((unsigned)(px + stride) / HW), cg * 8, g, z);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          fs[e] += g[e];
+          fq[e] = fmaf(g[e], z[e], fq[e]);
+        }
       }
     }
 #pragma unroll
@@ -367,25 +444,38 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
 
 int bn_bwd_reduce(const BnBwdParams& p, cudaStream_t st) {
   if (check_c("bn_bwd_reduce", p.C)) return 1;
+  if (p.fmt == kFmtF16x2) {
+    set_error("bn_bwd: training tensors use fmt 0 or 2");
+    return 1;
+  }
   const long long P = (long long)p.N * p.H * p.W;
   const int lanes = 256 / (p.C / 8);
-  bn_bwd_reduce_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(p);
+  const int grid = grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8);
+  if (p.fmt == kFmtBf16) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(p);
+  else bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(p);
   NSM_CHECK_LAUNCH("bn_bwd_reduce");
   return 0;
 }
 
+template <int NPL>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+  constexpr bool rb = NPL == 1;
   const int groups = p.C / 8, lanes = 256 / groups;
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
-  const bool rb = p.fmt == kFmtBf16;
-  const long long P = (long long)p.N * p.H * p.W, HW = (long long)p.H * p.W;
-  const BwdChan8 ch = load_bwd_chan8(p, cg * 8);
-  float mg[8], mgx[8], sc[8];
+  const long long P = (long long)p.N * p.H * p.W;
+  const unsigned HW = (unsigned)(p.H * p.W);
+  BwdChan8 ch;
+  float A[8], B[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    mg[e] = float(p.sums[cg * 8 + e] / double(P));
-    mgx[e] = float(p.sums[p.C + cg * 8 + e] / double(P));
-    sc[e] = ch.s[e];
+    const int c = cg * 8 + e;
+    ch.s[e] = __ldg(p.scale + c);
+    ch.t[e] = __ldg(p.shift + c);
+    const double mu = double(__ldg(p.mean + c)), is = double(__ldg(p.invstd + c));
+    const double m1 = p.sums[c] / double(P);
+    const double m2 = (p.sums[p.C + c] - mu * p.sums[c]) * is / double(P);
+    A[e] = float(-double(ch.s[e]) * is * m2);
+    B[e] = float(-double(ch.s[e]) * m1 + double(ch.s[e]) * is * m2 * mu);
   }
   double acc[1][8];
 #pragma unroll
@@ -396,18 +486,35 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
     float fs[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) fs[e] = 0.f;
-    for (int it = 0; it < 16 && px < P; ++it, px += stride) {
-      float g[8], xh[8], dz[8];
-      const size_t elem = (size_t)px * p.C + cg * 8;
-      bn_bwd_g8(p, ch, elem, int((unsigned)px / (unsigned)HW), cg * 8, rb, g, xh);
+    for (int it = 0; it < 8 && px < P; ++it, px += 2 * stride) {
+      const bool ok1 = px + stride < P;
+      const size_t e0 = (size_t)px * p.C + cg * 8, e1 = (size_t)(px + stride) * p.C + cg * 8;
+      Raw8 dy0 = load_raw8_t<NPL>(p.dy, e0), z0 = load_raw8_t<NPL>(p.z, e0), dy1, z1;
+      if (ok1) {
+        dy1 = load_raw8_t<NPL>(p.dy, e1);
+        z1 = load_raw8_t<NPL>(p.z, e1);
+      }
+      float g[8], z[8], dz[8];
+      bn_bwd_g8<NPL>(p, ch, dy0, z0, int((unsigned)px / HW), cg * 8, g, z);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float t = sc[e] * (g[e] - mg[e] - xh[e] * mgx[e]);
+        float t = fmaf(ch.s[e], g[e], fmaf(A[e], z[e], B[e]));
         if (rb) t = rbf(t);
         dz[e] = t;
         fs[e] += t;
       }
-      store8(p.dz, elem, p.fmt, dz);
+      store8(p.dz, e0, p.fmt, dz);
+      if (ok1) {
+        bn_bwd_g8<NPL>(p, ch, dy1, z1, int((unsigned)(px + stride) / HW), cg * 8, g, z);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float t = fmaf(ch.s[e], g[e], fmaf(A[e], z[e], B[e]));
+          if (rb) t = rbf(t);
+          dz[e] = t;
+          fs[e] += t;
+        }
+        store8(p.dz, e1, p.fmt, dz);
+      }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] += double(fs[e]);
@@ -419,26 +526,29 @@ int bn_bwd_apply(const BnBwdParams& p, cudaStream_t st) {
   if (check_c("bn_bwd_apply", p.C)) return 1;
   const long long P = (long long)p.N * p.H * p.W;
   const int lanes = 256 / (p.C / 8);
-  bn_bwd_apply_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(p);
+  const int grid = grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8);
+  if (p.fmt == kFmtBf16) bn_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(p);
+  else bn_bwd_apply_kernel<2><<<grid, 256, 0, st>>>(p);
   NSM_CHECK_LAUNCH("bn_bwd_apply");
   return 0;
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* sums, const double* dbias, int C, int rb, float* dgamma,
-                                       float* dbeta, float* dbias_out) {
+__global__ void bn_bwd_finalize_kernel(const double* sums, const double* dbias, const float* mean, const float* invstd,
+                                       int C, int rb, float* dgamma, float* dbeta, float* dbias_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  // invstd is already folded into xhat: dgamma = sum g * xhat, dbeta = sum g
-  dgamma[c] = float(sums[C + c]);
+  // sums[c] = sum g, sums[C + c] = sum g*z  ->  dgamma = sum g*xhat, dbeta = sum g
+  dgamma[c] = float((sums[C + c] - double(mean[c]) * sums[c]) * double(invstd[c]));
   dbeta[c] = float(sums[c]);
   if (dbias_out) {
     const float v = dbias ? float(dbias[c]) : 0.f;
     dbias_out[c] = rb ? rbf(v) : v;
   }
 }
-int bn_bwd_finalize(const double* sums, const double* dbias, int C, int round_bf16, float* dgamma, float* dbeta,
-                    float* dbias_out, cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dbias, C, round_bf16, dgamma, dbeta, dbias_out);
+int bn_bwd_finalize(const double* sums, const double* dbias, const float* mean, const float* invstd, int C,
+                    int round_bf16, float* dgamma, float* dbeta, float* dbias_out, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dbias, mean, invstd, C, round_bf16, dgamma, dbeta,
+                                                          dbias_out);
   NSM_CHECK_LAUNCH("bn_bwd_finalize");
   return 0;
 }

@@ -28,7 +28,7 @@ struct BnActParams {
 int bn_act(const BnActParams& p, cudaStream_t st);
 
 // ---- BatchNorm backward ---------------------------------------------------------------------------------------------------
-// g = dy * mask[n][c] * LeakyReLU'(z*scale+shift);  sums[0..C) += sum g, sums[C..2C) += sum g * xhat
+// g = dy * mask[n][c] * LeakyReLU'(z*scale+shift);  sums[0..C) += sum g, sums[C..2C) += sum g * z
 struct BnBwdParams {
   Planes dy, z, dz;
   int N, H, W, C, fmt;
@@ -44,8 +44,8 @@ struct BnBwdParams {
 int bn_bwd_reduce(const BnBwdParams& p, cudaStream_t st);
 // dz = scale * (g - mean(g) - xhat * mean(g*xhat));  dgamma = sum g*xhat, dbeta = sum g written by bn_bwd_finalize
 int bn_bwd_apply(const BnBwdParams& p, cudaStream_t st);
-int bn_bwd_finalize(const double* sums, const double* dbias, int C, int round_bf16, float* dgamma, float* dbeta,
-                    float* dbias_out, cudaStream_t st);
+int bn_bwd_finalize(const double* sums, const double* dbias, const float* mean, const float* invstd, int C,
+                    int round_bf16, float* dgamma, float* dbeta, float* dbias_out, cudaStream_t st);
 
 // ---- adjoints of AvgPool2d(2) (+ skip-gradient add) and of one bilinear align_corners resize -------------------------
 // out[n,y,x,c] = (a ? a : 0) + 0.25 * dpool[n,y/2,x/2,c] (inside the pooled footprint)
