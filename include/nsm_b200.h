@@ -156,6 +156,9 @@ int nsm_planes_add(const void* a0, const void* a1, const void* b0, const void* b
                    long long numel, int mode, void* stream);
 int nsm_bilinear_bwd(const void* dout0, const void* dout1, int N, int ho, int wo, int C, void* din0, void* din1, int hi,
                      int wi, int mode, void* stream);
+/* adjoint of nsm_upsample_match in one pass (dout [N,ho,wo,C] -> din [N,hi,wi,C]) */
+int nsm_upsample_match_bwd(const void* dout0, const void* dout1, int N, int ho, int wo, int C, void* din0, void* din1,
+                           int hi, int wi, int mode, void* stream);
 /* network input (even fix + pixel_unshuffle, Unetmodel.py:92-101; 16 -> 64 channels zero padded) and its adjoint */
 int nsm_train_input_prep(const float* x, int N, int Hin, int Win, void* out0, void* out1, int mode, void* stream);
 int nsm_train_input_grad(const void* d0, const void* d1, int N, int H, int W, float* dx, int mode, void* stream);

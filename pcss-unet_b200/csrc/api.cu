@@ -542,6 +542,12 @@ int nsm_bilinear_bwd(const void* dout0, const void* dout1, int N, int ho, int wo
   ProfScope ps_("bilinear_bwd", 0.0, (double(N) * ho * wo + double(N) * hi * wi) * C * 2.0 * fmt_planes(mode), S(stream));
   return bilinear_bwd(mk(dout0, dout1), N, ho, wo, C, mk(din0, din1), hi, wi, mode, S(stream));
 }
+int nsm_upsample_match_bwd(const void* dout0, const void* dout1, int N, int ho, int wo, int C, void* din0, void* din1,
+                           int hi, int wi, int mode, void* stream) {
+  ProfScope ps_("upsample_match_bwd", 0.0, (double(N) * ho * wo + double(N) * hi * wi) * C * 2.0 * fmt_planes(mode),
+                S(stream));
+  return upsample_match_bwd(mk(dout0, dout1), N, ho, wo, C, mk(din0, din1), hi, wi, mode, S(stream));
+}
 int nsm_train_input_prep(const float* x, int N, int Hin, int Win, void* out0, void* out1, int mode, void* stream) {
   ProfScope ps_("train_input_prep", 0.0, double(N) * Hin * Win * 16.0, S(stream));
   return train_input_prep(x, N, Hin, Win, mk(out0, out1), mode, S(stream));

@@ -3,6 +3,7 @@
 #include <stdio.h>
 
 #include "nsm_common.cuh"
+#include "resample.cuh"
 #include "stream_kernels.cuh"
 
 namespace nsm {
@@ -160,25 +161,6 @@ int planes_to_nchw(const void* hi, const void* lo, int N, int C, int H, int W, i
 // bilinear helpers (align_corners=True), mirroring ATen's area_pixel_compute_scale / source_index:
 //   scale = (in-1)/(out-1) (0 if out==1); src = scale*dst; i0 = floor(src) clamped; lambda = src - i0
 // ------------------------------------------------------------------------------------------------
-struct Lerp {
-  int i0, i1;
-  float w0, w1;
-};
-__device__ __forceinline__ Lerp make_lerp(int dst, int in_size, int out_size) {
-  const float scale = out_size > 1 ? float(in_size - 1) / float(out_size - 1) : 0.f;
-  const float src = scale * float(dst);
-  int i0 = int(src);
-  if (i0 > in_size - 1) i0 = in_size - 1;
-  Lerp l;
-  l.i0 = i0;
-  l.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
-  float lam = src - float(i0);
-  lam = fminf(fmaxf(lam, 0.f), 1.f);
-  l.w1 = lam;
-  l.w0 = 1.f - lam;
-  return l;
-}
-
 // ------------------------------------------------------------------------------------------------
 // head stage
 // ------------------------------------------------------------------------------------------------
@@ -550,17 +532,32 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
   if (same) {
     up2_at(p, nbase, make_lerp(y, p.hs, 2 * p.hs), x, cg, rb, r);  // second resize has scale 1 -> exact copy
   } else {
-    const Lerp my = make_lerp(y, 2 * p.hs, p.hd), mx = make_lerp(x, 2 * p.ws, p.wd);
-    const Lerp ly0 = make_lerp(my.i0, p.hs, 2 * p.hs), ly1 = make_lerp(my.i1, p.hs, 2 * p.hs);
-    float u00[8], u01[8], u10[8], u11[8];
-    up2_at(p, nbase, ly0, mx.i0, cg, rb, u00);
-    up2_at(p, nbase, ly0, mx.i1, cg, rb, u01);
-    up2_at(p, nbase, ly1, mx.i0, cg, rb, u10);
-    up2_at(p, nbase, ly1, mx.i1, cg, rb, u11);
+    // composite of the two resizes = separable stencil over <= 3x3 source pixels (resample.cuh); evaluated in fp32 with
+    // one final rounding (the x2 intermediate is never materialised)
+    const Tap3 ty = composite_taps(y, p.hs, p.hd), tx = composite_taps(x, p.ws, p.wd);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float v = my.w0 * (mx.w0 * u00[e] + mx.w1 * u01[e]) + my.w1 * (mx.w0 * u10[e] + mx.w1 * u11[e]);
-      r[e] = rb ? rbf(v) : v;
+    for (int e = 0; e < 8; ++e) r[e] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (ty.w[i] == 0.f) continue;
+      const size_t rbase = nbase + (size_t)(ty.rmin + i) * p.ws;
+      float row[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) row[e] = 0.f;
+#pragma unroll
+      for (int jx = 0; jx < 3; ++jx) {
+        if (tx.w[jx] == 0.f) continue;
+        float v[8];
+        load8(p, (rbase + tx.rmin + jx) * p.C + cg * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) row[e] = fmaf(tx.w[jx], v[e], row[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = fmaf(ty.w[i], row[e], r[e]);
+    }
+    if (rb) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = rbf(r[e]);
     }
   }
   const size_t o = (((size_t)n * p.hd + y) * p.wd + x) * p.C + cg * 8;

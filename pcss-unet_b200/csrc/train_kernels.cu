@@ -4,6 +4,7 @@
 #include <stdio.h>
 
 #include "nsm_common.cuh"
+#include "resample.cuh"
 #include "train_kernels.cuh"
 
 namespace nsm {
@@ -745,6 +746,66 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const Planes dout, 
     for (int e = 0; e < 8; ++e) acc[e] = fmaf(wy[a], t[e], acc[e]);
   }
   store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, fmt, acc);
+}
+
+// Adjoint of the composite (x2 up-sample then resize to (ho, wo)) in one pass: source pixel (r, q) gathers from every
+// output whose 3-tap window (resample.cuh: composite_taps) contains it.
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const Planes dout, int N, int ho, int wo, int C,
+                                                            const Planes din, int hi, int wi, int fmt, int cg_shift) {
+  const int cgs = 1 << cg_shift;
+  const int j = blockIdx.y * 256 + threadIdx.x;
+  if (j >= wi * cgs) return;
+  const int cg = j & (cgs - 1), q = j >> cg_shift;
+  const int n = blockIdx.x / hi, r = blockIdx.x - n * hi;
+  auto range = [](int idx, int in_size, int out_size, int& lo, int& hi_) {
+    if (in_size <= 1 || out_size <= 1) {
+      lo = 0;
+      hi_ = out_size - 1;
+      return;
+    }
+    const float inv = float(out_size - 1) / float(in_size - 1);
+    lo = int(floorf(float(idx - 2) * inv)) - 1;
+    hi_ = int(ceilf(float(idx + 2) * inv)) + 1;
+    if (lo < 0) lo = 0;
+    if (hi_ > out_size - 1) hi_ = out_size - 1;
+  };
+  int ylo, yhi, xlo, xhi;
+  range(r, hi, ho, ylo, yhi);
+  range(q, wi, wo, xlo, xhi);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int y = ylo; y <= yhi; ++y) {
+    const Tap3 ty = composite_taps(y, hi, ho);
+    const int dy = r - ty.rmin;
+    const float wy = dy == 0 ? ty.w[0] : (dy == 1 ? ty.w[1] : (dy == 2 ? ty.w[2] : 0.f));
+    if (wy == 0.f) continue;
+    for (int x = xlo; x <= xhi; ++x) {
+      const Tap3 tx = composite_taps(x, wi, wo);
+      const int dx = q - tx.rmin;
+      const float wx = dx == 0 ? tx.w[0] : (dx == 1 ? tx.w[1] : (dx == 2 ? tx.w[2] : 0.f));
+      if (wx == 0.f) continue;
+      float d[8];
+      load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, fmt, d);
+      const float wgt = wy * wx;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, d[e], acc[e]);
+    }
+  }
+  store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, fmt, acc);
+}
+
+int upsample_match_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,
+                       cudaStream_t st) {
+  if (check_c("upsample_match_bwd", C)) return 1;
+  const int cgs = C / 8;
+  int shift = 0;
+  while ((1 << shift) < cgs) ++shift;
+  dim3 grid((unsigned)(N * hi), (unsigned)((wi * cgs + 255) / 256));
+  if (ho == 2 * hi && wo == 2 * wi) upsample2x_bwd_kernel<<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+  else composite_bwd_kernel<<<grid, 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi, fmt, shift);
+  NSM_CHECK_LAUNCH("upsample_match_bwd");
+  return 0;
 }
 
 int bilinear_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,

@@ -57,6 +57,10 @@ int planes_add(const Planes& a, const Planes& b, const Planes& out, long long nu
 int bilinear_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,
                  cudaStream_t st);
 
+// adjoint of upsample_match (x2 up-sample then resize to (ho, wo)): dout [N,ho,wo,C] -> din [N,hi,wi,C], one pass
+int upsample_match_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,
+                       cudaStream_t st);
+
 // ---- network input / output stages of the training path ----------------------------------------------------------------
 // x [N,4,Hin,Win] fp32 -> (even-size fix) -> pixel_unshuffle(2) -> NHWC planes [N,h,w,64] (channels 16..63 zero)
 int train_input_prep(const float* x, int N, int Hin, int Win, const Planes& out, int fmt, cudaStream_t st);

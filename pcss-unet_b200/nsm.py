@@ -81,6 +81,7 @@ def _declare(lib):
     lib.nsm_pool_bwd_add.argtypes = [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
     lib.nsm_planes_add.argtypes = [vp, vp, vp, vp, vp, vp, ll, c_int, vp]
     lib.nsm_bilinear_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, vp]
+    lib.nsm_upsample_match_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, vp]
     lib.nsm_train_input_prep.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, vp]
     lib.nsm_train_input_grad.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_int, vp]
     lib.nsm_sigmoid_shuffle_fwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp]
@@ -101,7 +102,7 @@ def _declare(lib):
 
 TRAIN_EXPORTS = [
     "nsm_bn_stats", "nsm_bn_finalize", "nsm_bn_act", "nsm_bn_bwd", "nsm_pool_bwd_add", "nsm_planes_add",
-    "nsm_bilinear_bwd", "nsm_train_input_prep", "nsm_train_input_grad", "nsm_sigmoid_shuffle_fwd",
+    "nsm_bilinear_bwd", "nsm_upsample_match_bwd", "nsm_train_input_prep", "nsm_train_input_grad", "nsm_sigmoid_shuffle_fwd",
     "nsm_sigmoid_shuffle_bwd", "nsm_pack_conv_weight_padded", "nsm_pad_vector", "nsm_wgrad_workspace_bytes",
     "nsm_wgrad",
 ]
@@ -421,10 +422,11 @@ def bilinear_bwd(dout: PlaneTensor, hi, wi):
 
 def upsample_match_bwd(dout: PlaneTensor, hs, ws):
     """Adjoint of upsample_match: (hd, wd) -> [(2hs, 2ws) ->] (hs, ws)."""
-    _, _, hd, wd = dout.shape
-    if (hd, wd) != (2 * hs, 2 * ws):
-        dout = bilinear_bwd(dout, 2 * hs, 2 * ws)
-    return bilinear_bwd(dout, hs, ws)
+    N, C, hd, wd = dout.shape
+    din = PlaneTensor(N, C, hs, ws, dout.mode, dout.p0.device)
+    check(lib().nsm_upsample_match_bwd(*_pp(dout), N, hd, wd, C, *_pp(din), hs, ws, dout.mode, stream_ptr()),
+          "nsm_upsample_match_bwd")
+    return din
 
 
 def train_input_prep(x, mode):

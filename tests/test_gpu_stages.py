@@ -44,7 +44,7 @@ def describe(err, ref):
     return "\n".join(lines)
 
 
-def check_close(got, ref, mode_name, what):
+def check_close(got, ref, mode_name, what, max_frac=0.03):
     got = got.detach().float().cpu()
     ref = ref.detach().float().cpu()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
@@ -56,7 +56,7 @@ def check_close(got, ref, mode_name, what):
         bound = (2.0 ** -6) * torch.maximum(ref.abs(), 0.1 * ref.abs().max())
         bad = (err.abs() > bound)
         frac = (err != 0).float().mean().item()
-        assert not bad.any() and frac < 0.03, f"{what} [bf16] differing={frac:.4f}\n" + describe(err, ref)
+        assert not bad.any() and frac < max_frac, f"{what} [bf16] differing={frac:.4f}\n" + describe(err, ref)
 
 
 @pytest.mark.parametrize("mode_name", ["bf16", "fp32", "fp32_train"])
@@ -140,4 +140,7 @@ def test_upsample_match(nsm, mode_name, shape):
     else:
         ref = oracle.upsample_and_match(x, (hd, wd))
     got = nsm.upsample_match(nsm.PlaneTensor.from_nchw(x.cuda(), mode), hd, wd).to_nchw()
-    check_close(got, ref, mode_name, f"upsample {shape}")
+    # the composite (destination != 2x source) is evaluated in fp32 with ONE final rounding, whereas autocast rounds the x2
+    # intermediate to bf16 as well: results may differ by one bf16 ulp on many elements (still within the 2^-6 bound)
+    composite = (hd, wd) != (2 * hs, 2 * ws)
+    check_close(got, ref, mode_name, f"upsample {shape}", max_frac=0.75 if composite else 0.03)
