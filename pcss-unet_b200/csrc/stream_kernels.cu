@@ -373,6 +373,7 @@ struct TailSmem {
   float b1[16], s1[16], t1[16], b10[4];
 };
 
+template <int FMT>
 __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ TailParams p) {
   __shared__ TailSmem s;
   const int tid = threadIdx.x;
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
   if (tid < 16) { s.b1[tid] = p.b1[tid]; s.s1[tid] = p.s1[tid]; s.t1[tid] = p.t1[tid]; }
   if (tid < 4) s.b10[tid] = p.b10[tid];
   __syncthreads();
-  const bool rb = p.fmt == kFmtBf16;
+  const bool rb = FMT == kFmtBf16;
   const long long npix = (long long)p.N * p.h * p.w;
   const int W = 2 * p.w, H = 2 * p.h;
   for (long long pix = blockIdx.x * 256LL + tid; pix < npix; pix += (long long)gridDim.x * 256) {
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
 #pragma unroll
     for (int co = 0; co < 16; ++co) a[co] = 0.f;
     const uint8_t* a0 = reinterpret_cast<const uint8_t*>(p.a.p[0]) + pix * 128;
-    const uint8_t* a1 = p.fmt != kFmtBf16 ? reinterpret_cast<const uint8_t*>(p.a.p[1]) + pix * 128 : nullptr;
+    const uint8_t* a1 = FMT != kFmtBf16 ? reinterpret_cast<const uint8_t*>(p.a.p[1]) + pix * 128 : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint4 hv = ldg16(a0 + 16 * j);
@@ -403,16 +404,16 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
       float xin[8];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        xin[2 * e] = hi_lo_to_f32(hw[e], p.fmt);
-        xin[2 * e + 1] = hi_hi_to_f32(hw[e], p.fmt);
+        xin[2 * e] = hi_lo_to_f32(hw[e], FMT);
+        xin[2 * e + 1] = hi_hi_to_f32(hw[e], FMT);
       }
       if (a1) {
         const uint4 lv = ldg16(a1 + 16 * j);
         uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          xin[2 * e] += lo_lo_to_f32(lw[e], p.fmt);
-          xin[2 * e + 1] += lo_hi_to_f32(lw[e], p.fmt);
+          xin[2 * e] += lo_lo_to_f32(lw[e], FMT);
+          xin[2 * e + 1] += lo_hi_to_f32(lw[e], FMT);
         }
       }
 #pragma unroll
@@ -465,7 +466,11 @@ int tail_eval(const TailParams& p, cudaStream_t st) {
     set_error("tail_eval: too many pixels");
     return 1;
   }
-  tail_eval_kernel<<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
+  {
+    if (p.fmt == kFmtBf16) tail_eval_kernel<kFmtBf16><<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
+    else if (p.fmt == kFmtF16x2) tail_eval_kernel<kFmtF16x2><<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
+    else tail_eval_kernel<kFmtBf16x2><<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
+  }
   NSM_CHECK_LAUNCH("tail_eval");
   return 0;
 }
@@ -481,35 +486,37 @@ struct UpParams {
   int N, hs, ws, C, hd, wd, fmt;
 };
 
+template <int FMT>
 __device__ __forceinline__ void load8(const UpParams& p, size_t elem, float* v) {
   const uint4 hv = ldg16(p.s0 + elem * 2);
   const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    v[2 * e] = hi_lo_to_f32(hw[e], p.fmt);
-    v[2 * e + 1] = hi_hi_to_f32(hw[e], p.fmt);
+    v[2 * e] = hi_lo_to_f32(hw[e], FMT);
+    v[2 * e + 1] = hi_hi_to_f32(hw[e], FMT);
   }
-  if (p.fmt != kFmtBf16) {
+  if (FMT != kFmtBf16) {
     const uint4 lv = ldg16(p.s1 + elem * 2);
     const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      v[2 * e] += lo_lo_to_f32(lw[e], p.fmt);
-      v[2 * e + 1] += lo_hi_to_f32(lw[e], p.fmt);
+      v[2 * e] += lo_lo_to_f32(lw[e], FMT);
+      v[2 * e + 1] += lo_hi_to_f32(lw[e], FMT);
     }
   }
 }
 
 // value of the x2 up-sampled tensor at intermediate pixel (row lerp ly given, column X), 8 channels
+template <int FMT>
 __device__ __forceinline__ void up2_at(const UpParams& p, size_t nbase, const Lerp& ly, int X, int cg, bool rb,
                                        float* out) {
   const Lerp lx = make_lerp(X, p.ws, 2 * p.ws);
   float v00[8], v01[8], v10[8], v11[8];
   const size_t r0 = nbase + (size_t)ly.i0 * p.ws, r1 = nbase + (size_t)ly.i1 * p.ws;
-  load8(p, (r0 + lx.i0) * p.C + cg * 8, v00);
-  load8(p, (r0 + lx.i1) * p.C + cg * 8, v01);
-  load8(p, (r1 + lx.i0) * p.C + cg * 8, v10);
-  load8(p, (r1 + lx.i1) * p.C + cg * 8, v11);
+  load8<FMT>(p, (r0 + lx.i0) * p.C + cg * 8, v00);
+  load8<FMT>(p, (r0 + lx.i1) * p.C + cg * 8, v01);
+  load8<FMT>(p, (r1 + lx.i0) * p.C + cg * 8, v10);
+  load8<FMT>(p, (r1 + lx.i1) * p.C + cg * 8, v11);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float v = ly.w0 * (lx.w0 * v00[e] + lx.w1 * v01[e]) + ly.w1 * (lx.w0 * v10[e] + lx.w1 * v11[e]);
@@ -519,18 +526,19 @@ __device__ __forceinline__ void up2_at(const UpParams& p, size_t nbase, const Le
 
 // grid: x = output row (n * hd + y), y = 256-thread chunks of the row's (pixel, channel-group) pairs.  All index
 // arithmetic is 32-bit with shifts (channel-group counts are powers of two); the row interpolation is per block.
+template <int FMT>
 __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, int cg_shift) {
   const int cgs = 1 << cg_shift;
   const int j = blockIdx.y * 256 + threadIdx.x;
   if (j >= p.wd * cgs) return;
   const int cg = j & (cgs - 1), x = j >> cg_shift;
   const int n = blockIdx.x / p.hd, y = blockIdx.x - n * p.hd;
-  const bool rb = p.fmt == kFmtBf16;
+  const bool rb = FMT == kFmtBf16;
   const bool same = (p.hd == 2 * p.hs) && (p.wd == 2 * p.ws);
   const size_t nbase = (size_t)n * p.hs * p.ws;
   float r[8];
   if (same) {
-    up2_at(p, nbase, make_lerp(y, p.hs, 2 * p.hs), x, cg, rb, r);  // second resize has scale 1 -> exact copy
+    up2_at<FMT>(p, nbase, make_lerp(y, p.hs, 2 * p.hs), x, cg, rb, r);  // second resize has scale 1 -> exact copy
   } else {
     // composite of the two resizes = separable stencil over <= 3x3 source pixels (resample.cuh); evaluated in fp32 with
     // one final rounding (the x2 intermediate is never materialised)
@@ -548,7 +556,7 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
       for (int jx = 0; jx < 3; ++jx) {
         if (tx.w[jx] == 0.f) continue;
         float v[8];
-        load8(p, (rbase + tx.rmin + jx) * p.C + cg * 8, v);
+        load8<FMT>(p, (rbase + tx.rmin + jx) * p.C + cg * 8, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) row[e] = fmaf(tx.w[jx], v[e], row[e]);
       }
@@ -564,11 +572,11 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
   uint32_t hw[4], lw[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    hw[e] = pack_hi(r[2 * e], r[2 * e + 1], p.fmt);
-    lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], p.fmt);
+    hw[e] = pack_hi(r[2 * e], r[2 * e + 1], FMT);
+    lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], FMT);
   }
   stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-  if (p.fmt != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+  if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
 }
 
 // Fast path of the plain x2 up-sample (destination exactly 2hs x 2ws): one thread produces a 2x2 output block of 8
@@ -586,13 +594,14 @@ __device__ __forceinline__ void up2x_weights(int b, int in_size, float& we0, flo
   wo0 = 1.f - wo1;
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p, int cg_shift) {
   const int cgs = 1 << cg_shift;
   const int j = blockIdx.y * 256 + threadIdx.x;
   if (j >= p.ws * cgs) return;
   const int cg = j & (cgs - 1), xb = j >> cg_shift;
   const int n = blockIdx.x / p.hs, yb = blockIdx.x - n * p.hs;
-  const bool rb = p.fmt == kFmtBf16;
+  const bool rb = FMT == kFmtBf16;
   float wye0, wye1, wyo0, wyo1, wxe0, wxe1, wxo0, wxo1;
   up2x_weights(yb, p.hs, wye0, wye1, wyo0, wyo1);
   up2x_weights(xb, p.ws, wxe0, wxe1, wxo0, wxo1);
@@ -603,9 +612,9 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p, int c
   for (int r = 0; r < 3; ++r) {
     const size_t rbase = ((size_t)n * p.hs + rows[r]) * p.ws;
     float a[8], b[8], c[8];
-    load8(p, (rbase + cols[0]) * p.C + cg * 8, a);
-    load8(p, (rbase + cols[1]) * p.C + cg * 8, b);
-    load8(p, (rbase + cols[2]) * p.C + cg * 8, c);
+    load8<FMT>(p, (rbase + cols[0]) * p.C + cg * 8, a);
+    load8<FMT>(p, (rbase + cols[1]) * p.C + cg * 8, b);
+    load8<FMT>(p, (rbase + cols[2]) * p.C + cg * 8, c);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       he[r][e] = wxe0 * a[e] + wxe1 * b[e];
@@ -628,11 +637,11 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p, int c
       uint32_t hw[4], lw[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        hw[e] = pack_hi(r[2 * e], r[2 * e + 1], p.fmt);
-        lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], p.fmt);
+        hw[e] = pack_hi(r[2 * e], r[2 * e + 1], FMT);
+        lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], FMT);
       }
       stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-      if (p.fmt != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+      if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
     }
   }
 }
@@ -652,10 +661,18 @@ int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes
   p.N = N; p.hs = hs; p.ws = ws; p.C = C; p.hd = hd; p.wd = wd; p.fmt = fmt;
   if (hd == 2 * hs && wd == 2 * ws) {
     dim3 grid((unsigned)(N * hs), (unsigned)((ws * cgs + 255) / 256));
-    upsample2x_kernel<<<grid, 256, 0, st>>>(p, shift);
+    {
+      if (fmt == kFmtBf16) upsample2x_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift);
+      else if (fmt == kFmtF16x2) upsample2x_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift);
+      else upsample2x_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift);
+    }
   } else {
     dim3 grid((unsigned)(N * hd), (unsigned)((wd * cgs + 255) / 256));
-    upsample_match_kernel<<<grid, 256, 0, st>>>(p, shift);
+    {
+      if (fmt == kFmtBf16) upsample_match_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift);
+      else if (fmt == kFmtF16x2) upsample_match_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift);
+      else upsample_match_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift);
+    }
   }
   NSM_CHECK_LAUNCH("upsample_match");
   return 0;

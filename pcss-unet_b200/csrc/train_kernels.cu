@@ -108,6 +108,7 @@ __device__ __forceinline__ void block_channel_reduce(const double (&acc)[NV][8],
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics
 // ------------------------------------------------------------------------------------------------
+template <int FMT>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const Planes z, long long P, int C, int fmt, double* sums) {
   const int groups = C / 8, lanes = 256 / groups;
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
@@ -124,12 +125,12 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const Planes z, long long
       Raw8 r[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u)
-        if (p + u * stride < P) r[u] = load_raw8(z, (size_t)(p + u * stride) * C + cg * 8, fmt);
+        if (p + u * stride < P) r[u] = load_raw8(z, (size_t)(p + u * stride) * C + cg * 8, FMT);
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         if (p + u * stride < P) {
           float v[8];
-          unpack8(r[u], fmt, v);
+          unpack8(r[u], FMT, v);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             fs[e] += v[e];
@@ -166,7 +167,11 @@ static int check_c(const char* who, int C) {
 int bn_stats(const Planes& z, long long P, int C, int fmt, double* sums, cudaStream_t st) {
   if (check_c("bn_stats", C)) return 1;
   const int lanes = 256 / (C / 8);
-  bn_stats_kernel<<<grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8), 256, 0, st>>>(z, P, C, fmt, sums);
+  {
+    if (fmt == kFmtBf16) bn_stats_kernel<kFmtBf16><<<grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8), 256, 0, st>>>(z, P, C, fmt, sums);
+    else if (fmt == kFmtF16x2) bn_stats_kernel<kFmtF16x2><<<grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8), 256, 0, st>>>(z, P, C, fmt, sums);
+    else bn_stats_kernel<kFmtBf16x2><<<grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8), 256, 0, st>>>(z, P, C, fmt, sums);
+  }
   NSM_CHECK_LAUNCH("bn_stats");
   return 0;
 }
@@ -245,9 +250,10 @@ __device__ __forceinline__ void bn_act8(float* v, const BnActParams& p, const Ch
   }
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
   const int cgs = p.C / 8;
-  const bool rb = p.fmt == kFmtBf16;
+  const bool rb = FMT == kFmtBf16;
   const long long total = (long long)p.N * p.H * p.W * cgs;
   const int cg_shift = __ffs(cgs) - 1;                 // channel-group counts are powers of two
   const unsigned HW = (unsigned)(p.H * p.W);
@@ -259,22 +265,23 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
     const unsigned pix = iu >> cg_shift;
     const int n = int(pix / HW);
     float v[8];
-    load8(p.z, (size_t)pix * p.C + cg * 8, p.fmt, v);
+    load8(p.z, (size_t)pix * p.C + cg * 8, FMT, v);
     bn_act8(v, p, ch, n, cg * 8, rb);
     if (p.residual.p[0]) {
       float r[8];
-      load8(p.residual, (size_t)pix * p.C + cg * 8, p.fmt, r);
+      load8(p.residual, (size_t)pix * p.C + cg * 8, FMT, r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = rb ? rbf(v[e] + r[e]) : v[e] + r[e];
     }
-    store8(p.out, (size_t)pix * p.C + cg * 8, p.fmt, v);
+    store8(p.out, (size_t)pix * p.C + cg * 8, FMT, v);
   }
 }
 
 // quad variant: one thread = 2x2 pixels x 8 channels, writes the activation and its 2x2 average
+template <int FMT>
 __global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
   const int cgs = p.C / 8;
-  const bool rb = p.fmt == kFmtBf16;
+  const bool rb = FMT == kFmtBf16;
   const int Hq = (p.H + 1) / 2, Wq = (p.W + 1) / 2, Hp = p.H / 2, Wp = p.W / 2;
   const long long total = (long long)p.N * Hq * Wq * cgs;
   const Chan8 ch = load_chan8(p.scale, p.shift, int((blockIdx.x * 256u + threadIdx.x) % (unsigned)cgs) * 8);
@@ -295,9 +302,9 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
       if (y < p.H && x < p.W) {
         const size_t pix = ((size_t)n * p.H + y) * p.W + x;
         float v[8];
-        load8(p.z, pix * p.C + cg * 8, p.fmt, v);
+        load8(p.z, pix * p.C + cg * 8, FMT, v);
         bn_act8(v, p, ch, n, cg * 8, rb);
-        store8(p.out, pix * p.C + cg * 8, p.fmt, v);
+        store8(p.out, pix * p.C + cg * 8, FMT, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) s[e] += v[e];
       }
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
     if (qy < Hp && qx < Wp) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) s[e] = rb ? rbf(s[e] * 0.25f) : s[e] * 0.25f;
-      store8(p.pool, (((size_t)n * Hp + qy) * Wp + qx) * p.C + cg * 8, p.fmt, s);
+      store8(p.pool, (((size_t)n * Hp + qy) * Wp + qx) * p.C + cg * 8, FMT, s);
     }
   }
 }
@@ -318,10 +325,18 @@ int bn_act(const BnActParams& p, cudaStream_t st) {
       return 1;
     }
     const long long total = (long long)p.N * ((p.H + 1) / 2) * ((p.W + 1) / 2) * (p.C / 8);
-    bn_act_pool_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+    {
+      if (p.fmt == kFmtBf16) bn_act_pool_kernel<kFmtBf16><<<grid_for(total, 256), 256, 0, st>>>(p);
+      else if (p.fmt == kFmtF16x2) bn_act_pool_kernel<kFmtF16x2><<<grid_for(total, 256), 256, 0, st>>>(p);
+      else bn_act_pool_kernel<kFmtBf16x2><<<grid_for(total, 256), 256, 0, st>>>(p);
+    }
   } else {
     const long long total = (long long)p.N * p.H * p.W * (p.C / 8);
-    bn_act_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+    {
+      if (p.fmt == kFmtBf16) bn_act_kernel<kFmtBf16><<<grid_for(total, 256), 256, 0, st>>>(p);
+      else if (p.fmt == kFmtF16x2) bn_act_kernel<kFmtF16x2><<<grid_for(total, 256), 256, 0, st>>>(p);
+      else bn_act_kernel<kFmtBf16x2><<<grid_for(total, 256), 256, 0, st>>>(p);
+    }
   }
   NSM_CHECK_LAUNCH("bn_act");
   return 0;
@@ -557,10 +572,11 @@ int bn_bwd_finalize(const double* sums, const double* dbias, const float* mean, 
 // ------------------------------------------------------------------------------------------------
 // AvgPool2d(2) adjoint (+ skip gradient), plane add, bilinear adjoint
 // ------------------------------------------------------------------------------------------------
+template <int FMT>
 __global__ void __launch_bounds__(256) pool_bwd_add_kernel(const Planes a, const Planes dpool, const Planes out, int N,
                                                            int H, int W, int C, int fmt) {
   const int cgs = C / 8, Hp = H / 2, Wp = W / 2;
-  const bool rb = fmt == kFmtBf16;
+  const bool rb = FMT == kFmtBf16;
   const long long total = (long long)N * H * W * cgs;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const unsigned iu = (unsigned)i;
@@ -573,34 +589,39 @@ __global__ void __launch_bounds__(256) pool_bwd_add_kernel(const Planes a, const
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (a.p[0]) load8(a, (size_t)pixi * C + cg * 8, fmt, v);
+    if (a.p[0]) load8(a, (size_t)pixi * C + cg * 8, FMT, v);
     if ((y >> 1) < Hp && (x >> 1) < Wp) {
       float d[8];
-      load8(dpool, (((size_t)n * Hp + (y >> 1)) * Wp + (x >> 1)) * C + cg * 8, fmt, d);
+      load8(dpool, (((size_t)n * Hp + (y >> 1)) * Wp + (x >> 1)) * C + cg * 8, FMT, d);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = rb ? rbf(v[e] + d[e] * 0.25f) : v[e] + d[e] * 0.25f;
     }
-    store8(out, (size_t)pixi * C + cg * 8, fmt, v);
+    store8(out, (size_t)pixi * C + cg * 8, FMT, v);
   }
 }
 int pool_bwd_add(const Planes& a, const Planes& dpool, const Planes& out, int N, int H, int W, int C, int fmt,
                  cudaStream_t st) {
   if (check_c("pool_bwd_add", C)) return 1;
-  pool_bwd_add_kernel<<<grid_for((long long)N * H * W * (C / 8), 256), 256, 0, st>>>(a, dpool, out, N, H, W, C, fmt);
+  {
+    if (fmt == kFmtBf16) pool_bwd_add_kernel<kFmtBf16><<<grid_for((long long)N * H * W * (C / 8), 256), 256, 0, st>>>(a, dpool, out, N, H, W, C, fmt);
+    else if (fmt == kFmtF16x2) pool_bwd_add_kernel<kFmtF16x2><<<grid_for((long long)N * H * W * (C / 8), 256), 256, 0, st>>>(a, dpool, out, N, H, W, C, fmt);
+    else pool_bwd_add_kernel<kFmtBf16x2><<<grid_for((long long)N * H * W * (C / 8), 256), 256, 0, st>>>(a, dpool, out, N, H, W, C, fmt);
+  }
   NSM_CHECK_LAUNCH("pool_bwd_add");
   return 0;
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(256) planes_add_kernel(const Planes a, const Planes b, const Planes out,
                                                          long long n8, int fmt) {
-  const bool rb = fmt == kFmtBf16;
+  const bool rb = FMT == kFmtBf16;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
     float x[8], y[8];
-    load8(a, (size_t)i * 8, fmt, x);
-    load8(b, (size_t)i * 8, fmt, y);
+    load8(a, (size_t)i * 8, FMT, x);
+    load8(b, (size_t)i * 8, FMT, y);
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = rb ? rbf(x[e] + y[e]) : x[e] + y[e];
-    store8(out, (size_t)i * 8, fmt, x);
+    store8(out, (size_t)i * 8, FMT, x);
   }
 }
 int planes_add(const Planes& a, const Planes& b, const Planes& out, long long numel, int fmt, cudaStream_t st) {
@@ -608,7 +629,11 @@ int planes_add(const Planes& a, const Planes& b, const Planes& out, long long nu
     set_error("planes_add: numel %lld not a multiple of 8", numel);
     return 1;
   }
-  planes_add_kernel<<<grid_for(numel / 8, 256), 256, 0, st>>>(a, b, out, numel / 8, fmt);
+  {
+    if (fmt == kFmtBf16) planes_add_kernel<kFmtBf16><<<grid_for(numel / 8, 256), 256, 0, st>>>(a, b, out, numel / 8, fmt);
+    else if (fmt == kFmtF16x2) planes_add_kernel<kFmtF16x2><<<grid_for(numel / 8, 256), 256, 0, st>>>(a, b, out, numel / 8, fmt);
+    else planes_add_kernel<kFmtBf16x2><<<grid_for(numel / 8, 256), 256, 0, st>>>(a, b, out, numel / 8, fmt);
+  }
   NSM_CHECK_LAUNCH("planes_add");
   return 0;
 }
@@ -646,6 +671,7 @@ __device__ __forceinline__ void touch_range(int r, int in_size, int out_size, in
   if (hi > out_size - 1) hi = out_size - 1;
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const Planes dout, int N, int ho, int wo, int C,
                                                            const Planes din, int hi, int wi, int fmt) {
   const int cgs = C / 8;
@@ -673,13 +699,13 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const Planes dout, in
         const float wx = (lx.i0 == q ? lx.w0 : 0.f) + (lx.i1 == q ? lx.w1 : 0.f);
         if (wx == 0.f) continue;
         float d[8];
-        load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, fmt, d);
+        load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, FMT, d);
         const float wgt = wy * wx;
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, d[e], acc[e]);
       }
     }
-    store8(din, (size_t)pixi * C + cg * 8, fmt, acc);
+    store8(din, (size_t)pixi * C + cg * 8, FMT, acc);
   }
 }
 // Adjoint of the plain x2 align_corners up-sample (ho == 2hi, wo == 2wi): source pixel r receives from output rows
@@ -712,6 +738,7 @@ __device__ __forceinline__ void up2x_adjoint_weights(int r, int in_size, float* 
   }
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const Planes dout, int N, int C, const Planes din, int hi,
                                                              int wi, int fmt, int cg_shift) {
   const int cgs = 1 << cg_shift;
@@ -738,18 +765,19 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const Planes dout, 
       const int x = 2 * q - 1 + b;
       if (x < 0 || x >= wo || wx[b] == 0.f) continue;
       float d[8];
-      load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, fmt, d);
+      load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, FMT, d);
 #pragma unroll
       for (int e = 0; e < 8; ++e) t[e] = fmaf(wx[b], d[e], t[e]);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = fmaf(wy[a], t[e], acc[e]);
   }
-  store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, fmt, acc);
+  store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, FMT, acc);
 }
 
 // Adjoint of the composite (x2 up-sample then resize to (ho, wo)) in one pass: source pixel (r, q) gathers from every
 // output whose 3-tap window (resample.cuh: composite_taps) contains it.
+template <int FMT>
 __global__ void __launch_bounds__(256) composite_bwd_kernel(const Planes dout, int N, int ho, int wo, int C,
                                                             const Planes din, int hi, int wi, int fmt, int cg_shift) {
   const int cgs = 1 << cg_shift;
@@ -786,13 +814,13 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const Planes dout, i
       const float wx = dx == 0 ? tx.w[0] : (dx == 1 ? tx.w[1] : (dx == 2 ? tx.w[2] : 0.f));
       if (wx == 0.f) continue;
       float d[8];
-      load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, fmt, d);
+      load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, FMT, d);
       const float wgt = wy * wx;
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, d[e], acc[e]);
     }
   }
-  store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, fmt, acc);
+  store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, FMT, acc);
 }
 
 int upsample_match_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,
@@ -802,8 +830,16 @@ int upsample_match_bwd(const Planes& dout, int N, int ho, int wo, int C, const P
   int shift = 0;
   while ((1 << shift) < cgs) ++shift;
   dim3 grid((unsigned)(N * hi), (unsigned)((wi * cgs + 255) / 256));
-  if (ho == 2 * hi && wo == 2 * wi) upsample2x_bwd_kernel<<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
-  else composite_bwd_kernel<<<grid, 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi, fmt, shift);
+  if (ho == 2 * hi && wo == 2 * wi) {
+    if (fmt == kFmtBf16) upsample2x_bwd_kernel<kFmtBf16><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+    else if (fmt == kFmtF16x2) upsample2x_bwd_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+    else upsample2x_bwd_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+  }
+  else {
+    if (fmt == kFmtBf16) composite_bwd_kernel<kFmtBf16><<<grid, 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi, fmt, shift);
+    else if (fmt == kFmtF16x2) composite_bwd_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi, fmt, shift);
+    else composite_bwd_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi, fmt, shift);
+  }
   NSM_CHECK_LAUNCH("upsample_match_bwd");
   return 0;
 }
@@ -816,12 +852,22 @@ int bilinear_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes&
     int shift = 0;
     while ((1 << shift) < cgs) ++shift;
     dim3 grid((unsigned)(N * hi), (unsigned)((wi * cgs + 255) / 256));
-    upsample2x_bwd_kernel<<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+    {
+      if (fmt == kFmtBf16) upsample2x_bwd_kernel<kFmtBf16><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+      else if (fmt == kFmtF16x2) upsample2x_bwd_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+      else upsample2x_bwd_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
+    }
     NSM_CHECK_LAUNCH("upsample2x_bwd");
     return 0;
   }
-  bilinear_bwd_kernel<<<grid_for((long long)N * hi * wi * (C / 8), 256), 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi,
+  {
+    if (fmt == kFmtBf16) bilinear_bwd_kernel<kFmtBf16><<<grid_for((long long)N * hi * wi * (C / 8), 256), 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi,
                                                                                          fmt);
+    else if (fmt == kFmtF16x2) bilinear_bwd_kernel<kFmtF16x2><<<grid_for((long long)N * hi * wi * (C / 8), 256), 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi,
+                                                                                         fmt);
+    else bilinear_bwd_kernel<kFmtBf16x2><<<grid_for((long long)N * hi * wi * (C / 8), 256), 256, 0, st>>>(dout, N, ho, wo, C, din, hi, wi,
+                                                                                         fmt);
+  }
   NSM_CHECK_LAUNCH("bilinear_bwd");
   return 0;
 }
