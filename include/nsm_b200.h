@@ -98,6 +98,8 @@ typedef struct nsm_conv_args {
   const void* residual[2]; /* [N,H,W,Cout] planes or NULL: skip add    Unetmodel.py:125,131,137              */
   void* pool[2];           /* [N,H/2,W/2,Cout] planes or NULL: AvgPool2d(2)               Unetmodel.py:40,43,46 */
   float* out_f32;          /* optional [N,H,W,Cout] fp32: conv + bias before BN */
+  double* stats;           /* optional [2*Cout] fp64, zeroed by the caller: += per-channel sum / sum of squares of the
+                              stored conv+bias output = train-mode BatchNorm statistics (Unetmodel.py:22,27) */
 } nsm_conv_args;
 int nsm_conv_fwd(const nsm_conv_args* a, void* stream);
 

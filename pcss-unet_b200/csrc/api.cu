@@ -292,6 +292,7 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     e3.bias = fvec(PL.v3[b][0]); e3.scale = fvec(PL.v3[b][1]); e3.shift = fvec(PL.v3[b][2]);
     e3.lrelu = 1; e3.round_bf16 = np == 1; e3.out = buf(tname); e3.residual = none; e3.pool = none;
     e3.out_f32 = nullptr;
+    e3.stats = nullptr;
     const double px = double(B) * lv.h * lv.w, ci = kBlocks[b].cin, co = kBlocks[b].cout;
     char nm[32];
     {
@@ -459,6 +460,7 @@ int nsm_conv_fwd(const nsm_conv_args* a, void* stream) {
   e.residual = {{const_cast<void*>(a->residual[0]), const_cast<void*>(a->residual[1])}};
   e.pool = {{a->pool[0], a->pool[1]}};
   e.out_f32 = a->out_f32;
+  e.stats = a->stats;
   char nm[64];
   snprintf(nm, sizeof(nm), "conv_gemm k%d %d->%d @%dx%d", a->ksize, a->Cin, a->Cout, a->H, a->W);
   const double px = double(a->N) * a->H * a->W;

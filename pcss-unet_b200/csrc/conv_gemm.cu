@@ -165,6 +165,30 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
   }
+  if (ep.stats) {
+    // Per-channel sum / sum of squares over the warp's 32 pixels by a butterfly "transpose reduction" (31 shuffles per
+    // quantity): after the five halving steps lane l holds the totals of channel cb + l; one fp64 atomic each.
+    float s1[32], s2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s1[j] = valid ? v[j] : 0.f;
+      s2[j] = s1[j] * s1[j];
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float keep1 = upper ? s1[i + off] : s1[i], send1 = upper ? s1[i] : s1[i + off];
+        const float keep2 = upper ? s2[i + off] : s2[i], send2 = upper ? s2[i] : s2[i + off];
+        s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+        s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+      }
+    }
+    atomicAdd(ep.stats + cb + lane, double(s1[0]));
+    atomicAdd(ep.stats + p.Cout + cb + lane, double(s2[0]));
+  }
   if (ep.scale) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {

@@ -26,6 +26,8 @@ struct ConvEpilogue {
   Planes residual;       // [N,H,W,Cout] added after the activation (skip connection) or {nullptr}
   Planes pool;           // [N,H/2,W/2,Cout] AvgPool2d(2) of the output or {nullptr}
   float* out_f32;        // optional fp32 NHWC output (raw accumulators + bias), or nullptr
+  double* stats;         // optional [2*Cout] fp64: += per-channel sum and sum of squares of the stored conv+bias values
+                         // (train-mode BatchNorm statistics fused into the producing convolution)
 };
 
 struct ConvShape {

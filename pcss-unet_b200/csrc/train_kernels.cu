@@ -800,18 +800,29 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const Planes dout, i
   int ylo, yhi, xlo, xhi;
   range(r, hi, ho, ylo, yhi);
   range(q, wi, wo, xlo, xhi);
+  // weights of this source pixel in every candidate output row / column, computed once (<= kMaxCand candidates)
+  constexpr int kMaxCand = 16;
+  float wyv[kMaxCand], wxv[kMaxCand];
+  if (yhi - ylo >= kMaxCand) yhi = ylo + kMaxCand - 1;   // cannot happen for the ratios of this network (<= 12)
+  if (xhi - xlo >= kMaxCand) xhi = xlo + kMaxCand - 1;
+  for (int y = ylo; y <= yhi; ++y) {
+    const Tap3 t = composite_taps(y, hi, ho);
+    const int d = r - t.rmin;
+    wyv[y - ylo] = d == 0 ? t.w[0] : (d == 1 ? t.w[1] : (d == 2 ? t.w[2] : 0.f));
+  }
+  for (int x = xlo; x <= xhi; ++x) {
+    const Tap3 t = composite_taps(x, wi, wo);
+    const int d = q - t.rmin;
+    wxv[x - xlo] = d == 0 ? t.w[0] : (d == 1 ? t.w[1] : (d == 2 ? t.w[2] : 0.f));
+  }
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   for (int y = ylo; y <= yhi; ++y) {
-    const Tap3 ty = composite_taps(y, hi, ho);
-    const int dy = r - ty.rmin;
-    const float wy = dy == 0 ? ty.w[0] : (dy == 1 ? ty.w[1] : (dy == 2 ? ty.w[2] : 0.f));
+    const float wy = wyv[y - ylo];
     if (wy == 0.f) continue;
     for (int x = xlo; x <= xhi; ++x) {
-      const Tap3 tx = composite_taps(x, wi, wo);
-      const int dx = q - tx.rmin;
-      const float wx = dx == 0 ? tx.w[0] : (dx == 1 ? tx.w[1] : (dx == 2 ? tx.w[2] : 0.f));
+      const float wx = wxv[x - xlo];
       if (wx == 0.f) continue;
       float d[8];
       load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, FMT, d);

@@ -39,6 +39,7 @@ class ConvArgs(Structure):
         ("lrelu", c_int),
         ("out", c_void_p * 2), ("residual", c_void_p * 2), ("pool", c_void_p * 2),
         ("out_f32", c_void_p),
+        ("stats", c_void_p),
     ]
 
 
@@ -266,7 +267,7 @@ def pack_conv_weight(w, mode, dgrad=False):
 
 
 def conv_fwd(x: PlaneTensor, wp, ksize, Cout, mode, bias=None, bn_scale=None, bn_shift=None, lrelu=False,
-             residual: PlaneTensor = None, pool=False, want_f32=False, want_out=True):
+             residual: PlaneTensor = None, pool=False, want_f32=False, want_out=True, stats=None):
     """One fused conv stage on the tensor cores.  Returns (out PlaneTensor|None, pooled|None, raw fp32 NHWC|None)."""
     N, Cin, H, W = x.shape
     dev = x.p0.device
@@ -283,6 +284,7 @@ def conv_fwd(x: PlaneTensor, wp, ksize, Cout, mode, bias=None, bn_scale=None, bn
     a.residual = residual.pair() if residual is not None else (c_void_p * 2)(None, None)
     a.pool = pl.pair() if pl is not None else (c_void_p * 2)(None, None)
     a.out_f32 = ptr(raw) or None
+    a.stats = ptr(stats) or None
     check(lib().nsm_conv_fwd(byref(a), stream_ptr()), "nsm_conv_fwd")
     return out, pl, raw
 

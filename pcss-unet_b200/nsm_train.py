@@ -83,11 +83,19 @@ def _running(bn, cpad):
     return rm, rv, c
 
 
-def _bn_train(z, gamma, beta, bn, updates=1):
+def _conv_stats(x, w, ksize, cout, mode, bias):
+    """Raw convolution (+bias) with the BatchNorm batch statistics accumulated by the conv epilogue itself."""
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device=x.p0.device)
+    z, _, _ = nsm.conv_fwd(x, w, ksize, cout, mode, bias=bias, stats=sums)
+    return z, sums
+
+
+def _bn_train(z, gamma, beta, bn, updates=1, sums=None):
     """Batch statistics + running-stat update of one nn.BatchNorm2d (eps 1e-5, momentum 0.1).  Returns the [4, C]
     (scale, shift, mean, invstd) tensor and the fp64 sums (kept for the checkpoint replay of conv5)."""
     N, C, H, W = z.shape
-    sums = nsm.bn_stats(z)
+    if sums is None:
+        sums = nsm.bn_stats(z)
     rm, rv, real = _running(bn, C)
     st = nsm.bn_finalize(sums, N * H * W, gamma, beta, rm, rv, updates=updates, eps=bn.eps,
                          momentum=bn.momentum if bn.momentum is not None else 0.1)
@@ -137,11 +145,11 @@ def _block_forward(model, pk, i, x, mode, mask, residual=None, pool=False, save=
     seq = getattr(model, name).conv
     d = pk.blocks[i]
     cip, cop = _pad64(cin), _pad64(cout)
-    z0, _, _ = nsm.conv_fwd(x, d["w3"], 3, cip, mode, bias=d["b3"])
-    st0, sums0 = _bn_train(z0, d["g3"], d["be3"], seq[1])
+    z0, s0 = _conv_stats(x, d["w3"], 3, cip, mode, d["b3"])
+    st0, sums0 = _bn_train(z0, d["g3"], d["be3"], seq[1], sums=s0)
     a0, _ = nsm.bn_act(z0, st0[0], st0[1], mask=mask, lrelu=True)
-    z1, _, _ = nsm.conv_fwd(a0, d["w1"], 1, cop, mode, bias=d["b1"])
-    st1, sums1 = _bn_train(z1, d["g1"], d["be1"], seq[5])
+    z1, s1 = _conv_stats(a0, d["w1"], 1, cop, mode, d["b1"])
+    st1, sums1 = _bn_train(z1, d["g1"], d["be1"], seq[5], sums=s1)
     y, pooled = nsm.bn_act(z1, st1[0], st1[1], mask=None, lrelu=True, residual=residual, pool=pool)
     saved = dict(x=x, z0=z0, a0=a0, z1=z1, st0=st0, st1=st1, mask=mask, sums0=sums0, sums1=sums1) if save else None
     return y, pooled, saved

@@ -81,6 +81,25 @@ def test_bn_train_forward_and_backward(nsm, mode_name, shape):
 
 
 @pytest.mark.parametrize("mode_name", MODES)
+def test_conv_epilogue_bn_statistics(nsm, mode_name):
+    """Train-mode BatchNorm statistics accumulated by the conv epilogue (fp64 atomics) == statistics of the stored output."""
+    mode = nsm.MODES[mode_name]
+    g = gen(21)
+    x = torch.randn(2, 64, 19, 27, generator=g)
+    w = torch.randn(128, 64, 3, 3, generator=g) / 24
+    b = torch.randn(128, generator=g) * 0.1
+    if mode_name == "bf16":
+        x, b = bf(x), bf(b)
+    sums = torch.zeros(256, dtype=torch.float64, device="cuda")
+    z, _, _ = nsm.conv_fwd(planes(nsm, x, mode), nsm.pack_conv_weight(w.cuda(), mode), 3, 128, mode, bias=b.cuda(),
+                           stats=sums)
+    zz = z.to_nchw().double().cpu()
+    assert torch.allclose(sums[:128].cpu(), zz.sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-4)
+    assert torch.allclose(sums[128:].cpu(), (zz * zz).sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-4)
+    assert torch.allclose(nsm.bn_stats(z).cpu(), sums.cpu(), rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode_name", MODES)
 def test_bn_act_residual_and_pool(nsm, mode_name):
     mode = nsm.MODES[mode_name]
     g = gen(11)
