@@ -147,7 +147,7 @@ __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item,
 // Epilogue math + stores for 32 consecutive output channels [cb, cb+32) of one pixel (one thread).
 template <int NP>
 __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelParams& p, int cb, bool valid,
-                                              size_t pix, bool pool_anchor, size_t ppix) {
+                                              size_t pix, bool pool_anchor, size_t ppix, double& st1, double& st2) {
   const ConvEpilogue& ep = p.ep;
   if (ep.bias) {
 #pragma unroll
@@ -167,7 +167,8 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
   }
   if (ep.stats) {
     // Per-channel sum / sum of squares over the warp's 32 pixels by a butterfly "transpose reduction" (31 shuffles per
-    // quantity): after the five halving steps lane l holds the totals of channel cb + l; one fp64 atomic each.
+    // quantity): after the five halving steps lane l holds the totals of channel cb + l, which it keeps accumulating in
+    // fp64 registers across the tiles of this CTA.
     float s1[32], s2[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -186,8 +187,8 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
         s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
       }
     }
-    atomicAdd(ep.stats + cb + lane, double(s1[0]));
-    atomicAdd(ep.stats + p.Cout + cb + lane, double(s2[0]));
+    st1 += double(s1[0]);   // flushed with one fp64 atomic per channel when the CTA's column block changes / at the end
+    st2 += double(s2[0]);
   }
   if (ep.scale) {
 #pragma unroll
@@ -406,9 +407,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int ly = row / kTileW, lx = row % kTileW;
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + half * HB;
     uint32_t acc = 0, acc_phase = 0;
+    // fused BatchNorm statistics: lane l owns channels (column block base + 32*k + l), k < HB/32
+    constexpr int NCH = HB / 32;
+    double st1[NCH], st2[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) st1[k] = st2[k] = 0.0;
+    int st_nb = -1;
+    auto flush_stats = [&](int nb_old) {
+      if (p.ep.stats == nullptr || nb_old < 0) return;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c = nb_old * BN + half * HB + 32 * k + lane;
+        if (st1[k] != 0.0) atomicAdd(p.ep.stats + c, st1[k]);
+        if (st2[k] != 0.0) atomicAdd(p.ep.stats + p.Cout + c, st2[k]);
+        st1[k] = st2[k] = 0.0;
+      }
+    };
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int n, y0, x0, nb;
       decode_item(p, item, n, y0, x0, nb);
+      if (nb != st_nb) {
+        flush_stats(st_nb);
+        st_nb = nb;
+      }
       const int y = y0 + ly, x = x0 + lx;
       const bool valid = (y < p.H) && (x < p.W);
       const size_t pix = (size_t(n) * p.H + y) * p.W + x;
@@ -420,7 +441,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (NP == 1) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < HB; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + c0, r);
@@ -428,7 +449,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, pool_anchor, ppix);
+          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, pool_anchor, ppix, st1[c0 / 32], st2[c0 / 32]);
         }
         tc_fence_before();
         __syncwarp();
@@ -463,10 +484,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = sum[c0 + j];
-          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, pool_anchor, ppix);
+          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, pool_anchor, ppix, st1[c0 / 32], st2[c0 / 32]);
         }
       }
     }
+    flush_stats(st_nb);
   }
 
   tc_fence_before();
