@@ -530,19 +530,29 @@ template <int FMT>
 __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, int cg_shift) {
   const int cgs = 1 << cg_shift;
   const int j = blockIdx.y * 256 + threadIdx.x;
-  if (j >= p.wd * cgs) return;
-  const int cg = j & (cgs - 1), x = j >> cg_shift;
+  const bool active = j < p.wd * cgs;   // no early return: the block synchronises on its shared tap tables
+  const int cg = j & (cgs - 1), x = active ? (j >> cg_shift) : 0;
   const int n = blockIdx.x / p.hd, y = blockIdx.x - n * p.hd;
   const bool rb = FMT == kFmtBf16;
   const bool same = (p.hd == 2 * p.hs) && (p.wd == 2 * p.ws);
   const size_t nbase = (size_t)n * p.hs * p.ws;
+  // block-shared composite taps: the row's (one per block) and those of the <= 256/cgs + 1 columns this block touches
+  __shared__ Tap3 s_ty, s_tx[260];
+  const int x_first = (blockIdx.y * 256) >> cg_shift;
+  if (!same) {
+    const int x_count = ((blockIdx.y * 256 + 255) >> cg_shift) - x_first + 1;
+    if (threadIdx.x == 0) s_ty = composite_taps(y, p.hs, p.hd);
+    if ((int)threadIdx.x < x_count && x_first + (int)threadIdx.x < p.wd)
+      s_tx[threadIdx.x] = composite_taps(x_first + threadIdx.x, p.ws, p.wd);
+    __syncthreads();
+  }
   float r[8];
   if (same) {
     up2_at<FMT>(p, nbase, make_lerp(y, p.hs, 2 * p.hs), x, cg, rb, r);  // second resize has scale 1 -> exact copy
   } else {
     // composite of the two resizes = separable stencil over <= 3x3 source pixels (resample.cuh); evaluated in fp32 with
-    // one final rounding (the x2 intermediate is never materialised)
-    const Tap3 ty = composite_taps(y, p.hs, p.hd), tx = composite_taps(x, p.ws, p.wd);
+    // one final rounding (the x2 intermediate is never materialised).  Taps come from the block's shared tables.
+    const Tap3 ty = s_ty, tx = s_tx[x - x_first];
 #pragma unroll
     for (int e = 0; e < 8; ++e) r[e] = 0.f;
 #pragma unroll
@@ -568,6 +578,7 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
       for (int e = 0; e < 8; ++e) r[e] = rbf(r[e]);
     }
   }
+  if (!active) return;
   const size_t o = (((size_t)n * p.hd + y) * p.wd + x) * p.C + cg * 8;
   uint32_t hw[4], lw[4];
 #pragma unroll

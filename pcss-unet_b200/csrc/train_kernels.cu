@@ -780,52 +780,74 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const Planes dout, 
 template <int FMT>
 __global__ void __launch_bounds__(256) composite_bwd_kernel(const Planes dout, int N, int ho, int wo, int C,
                                                             const Planes din, int hi, int wi, int fmt, int cg_shift) {
+  constexpr int kMaxCand = 16;
   const int cgs = 1 << cg_shift;
   const int j = blockIdx.y * 256 + threadIdx.x;
-  if (j >= wi * cgs) return;
-  const int cg = j & (cgs - 1), q = j >> cg_shift;
+  const bool active = j < wi * cgs;
+  const int cg = j & (cgs - 1), q = active ? (j >> cg_shift) : 0;
   const int n = blockIdx.x / hi, r = blockIdx.x - n * hi;
-  auto range = [](int idx, int in_size, int out_size, int& lo, int& hi_) {
+  // Block-shared weight tables: for the source row r (one per block) and for each of the <= 256/cgs + 1 source columns
+  // of this block, the weight of that source index in every candidate output index (resample.cuh: composite_taps).
+  __shared__ float s_wy[kMaxCand], s_wx[260][kMaxCand + 1];
+  __shared__ int s_ylo, s_ny, s_xlo[260], s_nx[260];
+  auto range = [](int idx, int in_size, int out_size, int& lo, int& cnt) {
+    int hi_;
     if (in_size <= 1 || out_size <= 1) {
       lo = 0;
       hi_ = out_size - 1;
-      return;
+    } else {
+      const float inv = float(out_size - 1) / float(in_size - 1);
+      lo = int(floorf(float(idx - 2) * inv)) - 1;
+      hi_ = int(ceilf(float(idx + 2) * inv)) + 1;
+      if (lo < 0) lo = 0;
+      if (hi_ > out_size - 1) hi_ = out_size - 1;
     }
-    const float inv = float(out_size - 1) / float(in_size - 1);
-    lo = int(floorf(float(idx - 2) * inv)) - 1;
-    hi_ = int(ceilf(float(idx + 2) * inv)) + 1;
-    if (lo < 0) lo = 0;
-    if (hi_ > out_size - 1) hi_ = out_size - 1;
+    cnt = hi_ - lo + 1;
+    if (cnt > kMaxCand) cnt = kMaxCand;   // cannot happen for the ratios of this network (<= 12)
   };
-  int ylo, yhi, xlo, xhi;
-  range(r, hi, ho, ylo, yhi);
-  range(q, wi, wo, xlo, xhi);
-  // weights of this source pixel in every candidate output row / column, computed once (<= kMaxCand candidates)
-  constexpr int kMaxCand = 16;
-  float wyv[kMaxCand], wxv[kMaxCand];
-  if (yhi - ylo >= kMaxCand) yhi = ylo + kMaxCand - 1;   // cannot happen for the ratios of this network (<= 12)
-  if (xhi - xlo >= kMaxCand) xhi = xlo + kMaxCand - 1;
-  for (int y = ylo; y <= yhi; ++y) {
-    const Tap3 t = composite_taps(y, hi, ho);
-    const int d = r - t.rmin;
-    wyv[y - ylo] = d == 0 ? t.w[0] : (d == 1 ? t.w[1] : (d == 2 ? t.w[2] : 0.f));
+  auto weight_of = [](int src, int out_idx, int in_size, int out_size) {
+    const Tap3 t = composite_taps(out_idx, in_size, out_size);
+    const int d = src - t.rmin;
+    return d == 0 ? t.w[0] : (d == 1 ? t.w[1] : (d == 2 ? t.w[2] : 0.f));
+  };
+  const int q_first = (blockIdx.y * 256) >> cg_shift;
+  const int q_count = ((blockIdx.y * 256 + 255) >> cg_shift) - q_first + 1;
+  if (threadIdx.x < 32) {   // warp 0: row table
+    int lo, cnt;
+    range(r, hi, ho, lo, cnt);
+    if (threadIdx.x == 0) {
+      s_ylo = lo;
+      s_ny = cnt;
+    }
+    if ((int)threadIdx.x < cnt) s_wy[threadIdx.x] = weight_of(r, lo + threadIdx.x, hi, ho);
   }
-  for (int x = xlo; x <= xhi; ++x) {
-    const Tap3 t = composite_taps(x, wi, wo);
-    const int d = q - t.rmin;
-    wxv[x - xlo] = d == 0 ? t.w[0] : (d == 1 ? t.w[1] : (d == 2 ? t.w[2] : 0.f));
+  // column tables: (column, candidate) pairs spread over the block
+  for (int k = threadIdx.x; k < q_count * kMaxCand; k += 256) {
+    const int qi = k / kMaxCand, c = k % kMaxCand, qq = q_first + qi;
+    if (qq < wi) {
+      int lo, cnt;
+      range(qq, wi, wo, lo, cnt);
+      if (c == 0) {
+        s_xlo[qi] = lo;
+        s_nx[qi] = cnt;
+      }
+      s_wx[qi][c] = c < cnt ? weight_of(qq, lo + c, wi, wo) : 0.f;
+    }
   }
+  __syncthreads();
+  if (!active) return;
+  const int ylo = s_ylo, ny = s_ny, qi = q - q_first, xlo = s_xlo[qi], nx = s_nx[qi];
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int y = ylo; y <= yhi; ++y) {
-    const float wy = wyv[y - ylo];
+  for (int ky = 0; ky < ny; ++ky) {
+    const float wy = s_wy[ky];
     if (wy == 0.f) continue;
-    for (int x = xlo; x <= xhi; ++x) {
-      const float wx = wxv[x - xlo];
+    for (int kx = 0; kx < nx; ++kx) {
+      const float wx = s_wx[qi][kx];
       if (wx == 0.f) continue;
       float d[8];
-      load8(dout, (((size_t)n * ho + y) * wo + x) * C + cg * 8, FMT, d);
+      load8(dout, (((size_t)n * ho + ylo + ky) * wo + xlo + kx) * C + cg * 8, FMT, d);
       const float wgt = wy * wx;
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, d[e], acc[e]);
