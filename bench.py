@@ -328,7 +328,8 @@ def run_b200_train(args):
     torch.manual_seed(42)
     net = Unet(dropout_rate=0.2, precision=precision).to(dev).train()
     crit = EnhancedCustomLoss(dev, alpha=0.9, perturb_weight=0.1 if use_pert else 0.0).train()
-    opt = torch.optim.AdamW(net.parameters(), lr=7e-4, weight_decay=1e-3, fused=True)   # main.py:955
+    from nsm_optim import FusedAdamWClip
+    opt = FusedAdamWClip(net.parameters(), lr=7e-4, weight_decay=1e-3, max_norm=1.0)    # main.py:405,955 in two launches
     sync = GradSync(net) if world > 1 else None
     g = torch.Generator().manual_seed(100 + rank)
     x_host = torch.randn(B, 4, H, W, generator=g).pin_memory()
@@ -349,8 +350,7 @@ def run_b200_train(args):
         loss.backward()
         if sync is not None:
             sync.finish()
-        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)               # main.py:405
-        opt.step()
+        opt.step()                                  # non-finite scan + clip_grad_norm_(1.0) + AdamW, no host sync
         return loss
 
     for _ in range(max(args.warmup, 3)):
@@ -430,7 +430,7 @@ def run_b200_train(args):
             "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
             "config": {"workload": f"cfg2: U-Net training step, batch {B} of {H}x{W} crops per GPU, {precision}, "
                                    f"CustomLoss(alpha 0.9){' + PerturbationLoss(3 copies, weight 0.1)' if use_pert else ''}"
-                                   ", Dropout2d, train-mode BatchNorm, grad clip 1.0, AdamW (torch fused)",
+                                   ", Dropout2d, train-mode BatchNorm, fused non-finite scan + grad clip 1.0 + AdamW",
                        "algorithmic_tflop_per_step": flop * B / 1e12,
                        "model_tflops": flop * B * world / (step_ms * 1e-3) / 1e12,
                        "l2": "256 MiB buffer written before every timed step; activations >> L2",

@@ -177,6 +177,16 @@ int nsm_wgrad(const void* dz0, const void* dz1, const void* x0, const void* x1, 
               int ksize, int mode, int Cout_real, int Cin_real, void* workspace, size_t workspace_bytes, float* dw,
               void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimizer + gradient hygiene (main.py:295-423, :955): non-finite scan, global-norm clip
+ * (torch.nn.utils.clip_grad_norm_ semantics) and AdamW over up to 128 tensors in two launches, no host sync.
+ *   acc[0] = sum of squared gradients (before clipping), acc[1] = number of NaN/Inf gradient elements; when
+ *   acc[1] != 0 the update is skipped entirely (GradScaler.step behaviour).  `step` is the 1-based AdamW step.
+ * --------------------------------------------------------------------------------------------------------- */
+int nsm_adamw_clip_step(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, const long long* numel, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float max_norm, int step, double* acc /*[2] device*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,8 @@ def _declare(lib):
     lib.nsm_wgrad_workspace_bytes.restype = c_size_t
     lib.nsm_wgrad_workspace_bytes.argtypes = [c_int] * 7
     lib.nsm_wgrad.argtypes = [vp, vp, vp, vp] + [c_int] * 9 + [vp, c_size_t, vp, vp]
+    lib.nsm_adamw_clip_step.argtypes = [c_int, POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(ll), fp, fp,
+                                        fp, fp, fp, fp, c_int, vp, vp]
     for name in TRAIN_EXPORTS:
         if name != "nsm_wgrad_workspace_bytes":
             getattr(lib, name).restype = c_int
@@ -105,7 +107,7 @@ TRAIN_EXPORTS = [
     "nsm_bn_stats", "nsm_bn_finalize", "nsm_bn_act", "nsm_bn_bwd", "nsm_pool_bwd_add", "nsm_planes_add",
     "nsm_bilinear_bwd", "nsm_upsample_match_bwd", "nsm_train_input_prep", "nsm_train_input_grad", "nsm_sigmoid_shuffle_fwd",
     "nsm_sigmoid_shuffle_bwd", "nsm_pack_conv_weight_padded", "nsm_pad_vector", "nsm_wgrad_workspace_bytes",
-    "nsm_wgrad",
+    "nsm_wgrad", "nsm_adamw_clip_step",
 ]
 
 EXPORTS = TRAIN_EXPORTS + [

@@ -305,3 +305,38 @@ def test_no_grad_train_mode_forward_and_perturbation_loss(nsm):
     assert abs(val.item() - v_ref.item()) <= 2e-5
     assert int(net.state_dict()["conv2.conv.1.num_batches_tracked"]) == 4
     assert int(net.state_dict()["conv5.conv.1.num_batches_tracked"]) == 5     # 4 forwards + 1 checkpoint replay
+
+
+def test_fused_adamw_clip_matches_torch(nsm):
+    """nsm_adamw_clip_step (non-finite scan + clip_grad_norm_ + AdamW in two launches) vs torch.optim.AdamW +
+    torch.nn.utils.clip_grad_norm_ (main.py:405,955), including a skipped step on a NaN gradient."""
+    from nsm_optim import FusedAdamWClip
+    g = gen(77)
+    shapes = [(64, 16, 3, 3), (1024,), (4,), (512, 1024, 1, 1), (7, 5)]
+    pa = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedAdamWClip(pa, lr=7e-4, weight_decay=1e-3, max_norm=1.0)
+    ob = torch.optim.AdamW(pb, lr=7e-4, weight_decay=1e-3)
+    for step in range(4):
+        scale = [0.05, 3.0, 1e-3, 0.5][step]          # below and above the clip threshold
+        for x, y in zip(pa, pb):
+            gr = (torch.randn(x.shape, generator=g) * scale).cuda()
+            x.grad, y.grad = gr.clone(), gr.clone()
+        v0 = pa[0]._version
+        oa.step()
+        norm_ref = torch.nn.utils.clip_grad_norm_(pb, max_norm=1.0)
+        ob.step()
+        assert pa[0]._version > v0                     # packed-weight caches keyed on _version must be invalidated
+        assert abs(oa.last_grad_norm.item() - norm_ref.item()) <= 1e-5 * norm_ref.item()
+        for x, y in zip(pa, pb):
+            assert torch.allclose(x, y, rtol=1e-5, atol=1e-7), (step, (x - y).abs().max().item())
+    before = [p.detach().clone() for p in pa]
+    for x in pa:
+        x.grad = torch.zeros_like(x)
+    pa[1].grad[3] = float("nan")
+    oa.step()
+    assert oa.last_nonfinite.item() == 1
+    for x, b in zip(pa, before):
+        assert torch.equal(x, b)                        # update skipped
+    sd = oa.state_dict()["state"][0]
+    assert set(sd) == {"step", "exp_avg", "exp_avg_sq"}
