@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
       s_tx[threadIdx.x] = composite_taps(x_first + threadIdx.x, p.ws, p.wd);
     __syncthreads();
   }
+  if (!active) return;   // (only after the barrier; inactive threads must not index the tap tables)
   float r[8];
   if (same) {
     up2_at<FMT>(p, nbase, make_lerp(y, p.hs, 2 * p.hs), x, cg, rb, r);  // second resize has scale 1 -> exact copy
@@ -578,7 +579,6 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
       for (int e = 0; e < 8; ++e) r[e] = rbf(r[e]);
     }
   }
-  if (!active) return;
   const size_t o = (((size_t)n * p.hd + y) * p.wd + x) * p.C + cg * 8;
   uint32_t hw[4], lw[4];
 #pragma unroll
