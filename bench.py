@@ -110,11 +110,38 @@ class ClockSampler:
 
 
 def make_params(seed=42):
-    import oracle  # checker-side helper used only to build seeded weights/BN statistics for the synthetic workload
+    """Weights for the CPU legs only (cpu_baseline / --impl reference): seeded default init + calibrated BN buffers."""
+    import oracle
     g = torch.Generator().manual_seed(0)
     P = oracle.init_params(seed)
     oracle.calibrate_bn(P, torch.randn(1, 4, 64, 64, generator=g), generator=g)
     return P
+
+
+def make_model(precision, dev, seed=42):
+    """B200 arm: the drop-in Unet with seeded default init (main.py:73-92) and BN buffers calibrated by one train-mode
+    pass of the product path itself (momentum 1.0) -- nothing under oracle/ is touched by the measured arm."""
+    from Unetmodel import Unet
+    torch.manual_seed(seed)
+    net = Unet(precision=precision).to(dev)
+    g = torch.Generator().manual_seed(0)
+    bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    with torch.no_grad():
+        for m in bns:
+            m.weight.copy_(torch.empty(m.num_features).uniform_(0.5, 1.5, generator=g))
+            m.bias.copy_(torch.empty(m.num_features).uniform_(-0.5, 0.5, generator=g))
+            m.momentum = 1.0
+        net.train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p_saved, m.p = m.p, 0.0
+        net(torch.randn(1, 4, 64, 64, generator=g).to(dev))
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p = m.p_saved
+        for m in bns:
+            m.momentum = 0.1
+    return net.eval()
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -176,10 +203,7 @@ def run_b200(args):
     precision = args.precision
     B, H, W = args.batch, args.height, args.width
 
-    P = make_params()
-    net = Unet(precision=precision)
-    net.load_state_dict(P)
-    net = net.to(dev).eval()
+    net = make_model(precision, dev)
     g = torch.Generator().manual_seed(100 + rank)
     x_host = torch.randn(B, 4, H, W, generator=g).pin_memory()
     y_host = torch.empty(B, 1, H - H % 2, W - W % 2).pin_memory()
@@ -289,7 +313,7 @@ def run_b200(args):
             "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sec = cpu_forward_timer(P, H, W, 2, 1)
+        sec = cpu_forward_timer(make_params(), H, W, 2, 1)
         line["cpu_baseline"] = {"value": H * W / 1e6 / sec, "unit": "Mpix/s", "cores": cores, "kind": "port",
                                 "sample": f"2 timed + 1 warm-up eval forwards of one {W}x{H} frame, fp32, torch CPU "
                                           f"ops on {cores} threads (oracle port of Unetmodel.py:90-149)"}
