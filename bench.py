@@ -282,15 +282,26 @@ def run_b200(args):
     for name, ms, fl, by in rows:
         d = per_layer.setdefault(name, [0.0, 0.0, 0.0, 0])
         d[0] += ms; d[1] += fl; d[2] += by; d[3] += 1
-    layers = {k: {"ms": v[0] / v[3], "tflops": v[1] / max(v[0], 1e-9) / 1e9, "gbs": v[2] / max(v[0], 1e-9) / 1e6}
-              for k, v in per_layer.items()}
+    mma_factor = 3 if precision == "fp32" else 1
+    layers = {}
+    for k, v in per_layer.items():
+        ms, fl, by = v[0] / v[3], v[1] / v[3], v[2] / v[3]
+        # per-layer roofline: the slower of tensor time (issued MMA work / measured bf16 peak) and HBM time
+        t_tensor = fl * mma_factor / (pk["bf16_tflops"] * 1e12) * 1e3
+        t_hbm = by / (pk["hbm_gbs"] * 1e9) * 1e3
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        layers[k] = {"ms": ms, "tflops": fl / max(ms, 1e-9) / 1e9, "gbs": by / max(ms, 1e-9) / 1e6, "bound": bound,
+                     "roofline_ms": max(t_tensor, t_hbm), "frac_of_roofline": max(t_tensor, t_hbm) / max(ms, 1e-9)}
+    t_roof = sum(v["roofline_ms"] for v in layers.values())
     planes = 2 if precision == "fp32" else 1
     roofline = {"kernel": f"conv_gemm_kernel<BN,{planes}> (tcgen05 implicit GEMM, {len(conv) // max(args.steps, 1)} "
                           "launches/step)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"], "traffic": measured_traffic(),
                 "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json)",
-                "mma_work_factor": 3 if precision == "fp32" else 1,
+                "mma_work_factor": mma_factor,
+                "frac_of_issued_mma": achieved * mma_factor / pk["bf16_tflops"],
+                "step_roofline_ms": t_roof, "step_frac_of_roofline": t_roof / max(all_ms, 1e-9),
                 "note": "achieved = algorithmic 2*M*K*N FLOPs of the conv launches / their CUDA-event time inside "
                         "the step; fp32 mode issues 3 bf16 MMAs per algorithmic MAC (hi*hi+hi*lo+lo*hi), so the "
                         "ceiling of frac is 1/3",

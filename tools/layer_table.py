@@ -1,0 +1,15 @@
+#!/usr/bin/env python
+"""bench JSON line -> markdown per-layer roofline table (profiles/)."""
+import json
+import sys
+
+d = json.load(open(sys.argv[1]))
+r = d["roofline"]
+print(f"# per-layer roofline, {d['config']['workload']}\n")
+print(f"step {d['ms_per_step']:.3f} ms = {d['value']:.1f} {d['unit']}; sum of per-layer rooflines {r.get('step_roofline_ms', 0):.3f} ms "
+      f"({100 * r.get('step_frac_of_roofline', 0):.0f} % of the event-timed kernel time); MMA work factor {r['mma_work_factor']}\n")
+print("| stage | ms | TFLOP/s (algorithmic) | GB/s (algorithmic) | bound | roofline ms | frac |")
+print("|---|---|---|---|---|---|---|")
+for k, v in r["per_layer"].items():
+    print(f"| {k} | {v['ms']:.4f} | {v['tflops']:.1f} | {v['gbs']:.0f} | {v.get('bound', '')} | {v.get('roofline_ms', 0):.4f} | "
+          f"{v.get('frac_of_roofline', 0):.2f} |")
