@@ -262,6 +262,28 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = t.tolist()
+    # second headline of BASELINE.json ("train samples/s @1/2/4/8 B200"): a short training measurement attached to the
+    # same line (all ranks take part: data-parallel step with NCCL gradient all-reduce)
+    train = None
+    if not args.no_train:
+        import copy
+        targs = copy.copy(args)
+        targs.steps, targs.warmup = min(args.steps, 10), 3
+        try:
+            del net, x
+            torch.cuda.empty_cache()
+            full = {}
+            for tag, no_pert in (("customLoss", True), ("customLoss+pert_loss", False)):
+                targs.no_perturb = no_pert
+                tl = measure_train(targs, own_process_group=False)
+                if tl is not None:
+                    full[tag] = {"value": tl["value"], "unit": tl["unit"], "ms_per_step": tl["ms_per_step"],
+                                 "e2e": tl["e2e"]["value"], "gemm_tflops": tl["roofline"]["achieved"],
+                                 "gemm_frac_of_sustained_peak": tl["roofline"]["frac"],
+                                 "workload": tl["config"]["workload"]}
+            train = full
+        except Exception as ex:   # the inference line must still be printed
+            train = {"error": repr(ex)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -321,7 +343,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
-            "roofline": roofline}
+            "roofline": roofline,
+            "train": train}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sec = cpu_forward_timer(make_params(), H, W, 2, 1)
@@ -340,7 +363,8 @@ TRAIN_FLOP_PER_SAMPLE = 3 * 747680.0 * 512 * 512           # fwd + dgrad + wgrad
 PERT_FLOP_PER_SAMPLE = 3 * 747680.0 * 512 * 512            # + 3 no-grad forwards of the perturbation loss
 
 
-def run_b200_train(args):
+def measure_train(args, own_process_group=True):
+    """Times the training step; returns the JSON line (rank 0) or None (other ranks)."""
     import torch.distributed as dist
     import nsm
     from Unetmodel import Unet
@@ -352,12 +376,12 @@ def run_b200_train(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and own_process_group:
         dist.init_process_group("nccl", device_id=dev)
     nsm.require_device()
-    precision = args.precision or "bf16"
-    B = args.batch or 32
-    H, W = args.height or 512, args.width or 512
+    precision = args.train_precision or "bf16"
+    B = args.train_batch or 32
+    H, W = args.train_size or 512, args.train_size or 512
     use_pert = not args.no_perturb
 
     torch.manual_seed(42)
@@ -388,6 +412,7 @@ def run_b200_train(args):
         opt.step()                                  # non-finite scan + clip_grad_norm_(1.0) + AdamW, no host sync
         return loss
 
+    steps = args.steps
     for _ in range(max(args.warmup, 3)):
         step(x, t)
     barrier()
@@ -429,9 +454,9 @@ def run_b200_train(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = tt.tolist()
     if rank != 0:
-        if world > 1:
+        if world > 1 and own_process_group:
             dist.destroy_process_group()
-        return
+        return None
     value = world * B * args.steps / (dev_ms * 1e-3)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
     pk = peaks()
@@ -475,9 +500,15 @@ def run_b200_train(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_loss": last},
             "gpu_launches": launches,
             "roofline": roofline}
-    print(json.dumps(line), flush=True)
-    if world > 1:
+    if world > 1 and own_process_group:
         dist.destroy_process_group()
+    return line
+
+
+def run_b200_train(args):
+    line = measure_train(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -493,10 +524,17 @@ def main():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-perturb", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="inference workload: skip the attached training measurement")
+    ap.add_argument("--train-precision", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--train-batch", type=int, default=None)
+    ap.add_argument("--train-size", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":
+        args.train_precision = args.train_precision or args.precision
+        args.train_batch = args.train_batch or args.batch
+        args.train_size = args.train_size or args.height
         run_b200_train(args)
     else:
         args.precision = args.precision or "fp32"
