@@ -323,7 +323,7 @@ def run_b200(args):
                 "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json)",
                 "mma_work_factor": mma_factor,
                 "frac_of_issued_mma": achieved * mma_factor / pk["bf16_tflops"],
-                "step_roofline_ms": t_roof, "step_frac_of_roofline": t_roof / max(all_ms, 1e-9),
+                "step_roofline_ms": t_roof, "step_frac_of_roofline": t_roof / max(all_ms / max(args.steps, 1), 1e-9),
                 "note": "achieved = algorithmic 2*M*K*N FLOPs of the conv launches / their CUDA-event time inside "
                         "the step; fp32 mode issues 3 bf16 MMAs per algorithmic MAC (hi*hi+hi*lo+lo*hi), so the "
                         "ceiling of frac is 1/3",

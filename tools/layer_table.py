@@ -7,7 +7,7 @@ d = json.load(open(sys.argv[1]))
 r = d["roofline"]
 print(f"# per-layer roofline, {d['config']['workload']}\n")
 print(f"step {d['ms_per_step']:.3f} ms = {d['value']:.1f} {d['unit']}; sum of per-layer rooflines {r.get('step_roofline_ms', 0):.3f} ms "
-      f"({100 * r.get('step_frac_of_roofline', 0):.0f} % of the event-timed kernel time); MMA work factor {r['mma_work_factor']}\n")
+      f"({100 * r.get('step_frac_of_roofline', 0):.0f} % of the event-timed kernel time per step); MMA work factor {r['mma_work_factor']}\n")
 print("| stage | ms | TFLOP/s (algorithmic) | GB/s (algorithmic) | bound | roofline ms | frac |")
 print("|---|---|---|---|---|---|---|")
 for k, v in r["per_layer"].items():
