@@ -267,6 +267,9 @@ class _UnetTrainFn(torch.autograd.Function):
 def unet_train_forward(model, x, mode):
     """Entry point used by Unet.forward when model.training is True."""
     tmode = nsm.MODE_BF16 if mode == nsm.MODE_BF16 else nsm.MODE_FP32_TRAIN
+    # the BN kernels update running_mean / running_var through raw pointers (no Tensor._version bump): drop the eval-mode
+    # packed blob (it folds those buffers) so that the next model.eval() forward re-packs
+    model._packed.clear()
     params = [p for _, p in model.named_parameters()]
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
     if needs_grad:

@@ -340,3 +340,31 @@ def test_fused_adamw_clip_matches_torch(nsm):
         assert torch.equal(x, b)                        # update skipped
     sd = oa.state_dict()["state"][0]
     assert set(sd) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_eval_after_training_uses_updated_running_stats(nsm):
+    """validate_direct (main.py:583-664) runs model.eval() right after training steps: the eval path must see the running
+    statistics the training kernels just wrote."""
+    from Unetmodel import Unet
+    P = oracle.init_params(42)
+    net = Unet(dropout_rate=0.0, precision="fp32")
+    net.load_state_dict(P)
+    net = net.cuda()
+    x = torch.randn(2, 4, 64, 96, generator=gen(31))
+    net.eval()
+    with torch.no_grad():
+        y0 = net(x.cuda()).cpu()               # packs the eval blob with the initial buffers (mean 0, var 1)
+    net.train()
+    with torch.no_grad():
+        for _ in range(3):
+            net(x.cuda())
+    net.eval()
+    with torch.no_grad():
+        y1 = net(x.cuda()).cpu()
+    Po = oracle.init_params(42)
+    with torch.no_grad():
+        for _ in range(3):
+            oracle.unet_forward(x, Po, training=True, dropout_rate=0.0)
+        ref = oracle.unet_forward(x, Po, training=False)
+    assert (y1 - y0).abs().max().item() > 1e-3      # the buffers did change the result
+    assert (y1 - ref).abs().max().item() <= 1e-4
