@@ -368,3 +368,47 @@ def test_eval_after_training_uses_updated_running_stats(nsm):
         ref = oracle.unet_forward(x, Po, training=False)
     assert (y1 - y0).abs().max().item() > 1e-3      # the buffers did change the result
     assert (y1 - ref).abs().max().item() <= 1e-4
+
+
+def test_loss_curve_matches_oracle(nsm):
+    """north_star: "training loss curve within 1% of the reference" -- a short version that fits the test budget: 40
+    optimisation steps (Dropout2d masks replayed, CustomLoss, grad clip 1.0, AdamW lr 7e-4 / wd 1e-3 as main.py:955) on
+    the B200 path (fused AdamW kernel) and on the CPU oracle (torch AdamW + clip_grad_norm_), same data every step."""
+    from Unetmodel import Unet
+    from customLoss import CustomLoss
+    from nsm_optim import FusedAdamWClip
+    steps, N = 40, 2
+    P = oracle.init_params(42)
+    net = Unet(dropout_rate=0.2, precision="fp32")
+    net.load_state_dict({k: v.clone() for k, v in P.items()})
+    net = net.cuda().train()
+    opt = FusedAdamWClip(net.parameters(), lr=7e-4, weight_decay=1e-3, max_norm=1.0)
+    crit = CustomLoss("cuda", alpha=0.9)
+    # oracle side: leaf tensors + torch AdamW
+    names = oracle.param_names()
+    Po = {k: v.clone() for k, v in P.items()}
+    leaves = [Po[k].requires_grad_(True) for k in names]
+    opt_ref = torch.optim.AdamW(leaves, lr=7e-4, weight_decay=1e-3)
+    g = gen(55)
+    data = [(torch.randn(N, 4, 32, 48, generator=g), torch.rand(N, 1, 32, 48, generator=g)) for _ in range(4)]
+    curve, curve_ref = [], []
+    for it in range(steps):
+        x, t = data[it % len(data)]
+        masks = _masks(1000 + it, N)
+        net._replay_masks = masks
+        opt.zero_grad(set_to_none=True)
+        loss = crit(net(x.cuda()), t.cuda(), None)
+        loss.backward()
+        opt.step()
+        curve.append(loss.item())
+        opt_ref.zero_grad(set_to_none=True)
+        out = oracle.unet_forward(x, Po, training=True, masks=masks)
+        lr_ = oracle.custom_loss(out, t, 0.9)
+        lr_.backward()
+        torch.nn.utils.clip_grad_norm_(leaves, max_norm=1.0)
+        opt_ref.step()
+        curve_ref.append(lr_.item())
+    rel_dev = max(abs(a - b) / b for a, b in zip(curve, curve_ref))
+    print("loss curve: first", curve[0], curve_ref[0], "last", curve[-1], curve_ref[-1], "max rel deviation", rel_dev)
+    assert curve[-1] < curve[0]            # it trains
+    assert rel_dev <= 0.01
