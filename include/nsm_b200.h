@@ -61,6 +61,12 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
 /* Same with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, stream synchronise. */
 int nsm_unet_infer_host(const void* blob, int mode, const float* x_host, int B, int H, int W, const float* mean,
                         const float* std, float* y_host, void* workspace, size_t workspace_bytes, void* stream);
+/* Output path of infer.py:79-80 fused into the last kernel: y_u8 = (uint8)(y * 255), [B,1,H',W'] bytes,
+ * a quarter of the D2H traffic of the fp32 result. */
+int nsm_unet_infer_u8(const void* blob, int mode, const float* x, int B, int H, int W, const float* mean,
+                      const float* std, uint8_t* y_u8, void* workspace, size_t workspace_bytes, void* stream);
+int nsm_unet_infer_host_u8(const void* blob, int mode, const float* x_host, int B, int H, int W, const float* mean,
+                           const float* std, uint8_t* y_host, void* workspace, size_t workspace_bytes, void* stream);
 /* Copy a named intermediate of the last nsm_unet_infer() on this workspace to NCHW fp32 (tests / debugging).
  * names: c2 p2 t3 c3 p3 t4 c4 p4 t5 c5 u6 t6 m6 u7 t7 m7 u8 t8 m8 u9 t9.  *C,*h,*w receive its shape. */
 int nsm_unet_tap(const void* workspace, int B, int H, int W, int mode, const char* name, float* out, int* C,

@@ -155,6 +155,26 @@ class Unet(nn.Module):
         return y_host
 
 
+def _infer_host_u8(self, x_host, y_host=None):
+    """As infer_host, but the last kernel also applies infer.py:79's `(out * 255).astype(uint8)`: the result comes back as
+    [B,1,H',W'] uint8 (a quarter of the D2H bytes)."""
+    dev = self.conv10.weight.device
+    nsm.require_device(self.conv10.weight)
+    mode = self._mode()
+    B, _, H, W = x_host.shape
+    if y_host is None:
+        y_host = torch.empty(B, 1, H - H % 2, W - W % 2, dtype=torch.uint8).pin_memory()
+    blob = self._packed_blob(mode)
+    ws = self._workspace(B, H, W, mode, dev)
+    mean, std = self.input_stats if self.input_stats is not None else (None, None)
+    with torch.no_grad():
+        nsm.unet_infer_host_u8(blob, mode, x_host, y_host, ws, mean, std)
+    return y_host
+
+
+Unet.infer_host_u8 = _infer_host_u8
+
+
 def makefilepath(folder_path):
     """Kept for interface parity with the reference helper (Unetmodel.py:152-154)."""
     os.makedirs(folder_path, exist_ok=True)

@@ -242,8 +242,8 @@ size_t nsm_unet_workspace_bytes(int B, int H, int W, int mode) {
   return workspace_layout(B, H, W, mode).total;
 }
 
-int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int W, const float* mean,
-                   const float* std, float* y, void* ws, size_t ws_bytes, void* stream) {
+static int infer_impl(const void* blob, int mode, const float* x, int B, int H, int W, const float* mean,
+                      const float* std, float* y, uint8_t* y_u8, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode < 0 || mode > 2) {
     set_error("nsm_unet_infer: bad mode %d", mode);
@@ -338,12 +338,21 @@ int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int
     TailParams tp;
     tp.a = buf("t9"); tp.N = B; tp.h = WL.lv[1].h; tp.w = WL.lv[1].w;
     tp.w1 = fvec(PL.w1[7][0]); tp.b1 = fvec(PL.v1[7][0]); tp.s1 = fvec(PL.v1[7][1]); tp.t1 = fvec(PL.v1[7][2]);
-    tp.w10 = fvec(PL.w10); tp.b10 = fvec(PL.b10); tp.fmt = mode; tp.y = y;
+    tp.w10 = fvec(PL.w10); tp.b10 = fvec(PL.b10); tp.fmt = mode; tp.y = y; tp.y_u8 = y_u8;
     const double px = double(B) * tp.h * tp.w;
     ProfScope ps("tail(conv9.1x1+conv10)", px * 2.0 * (64 * 16 + 16 * 4), px * (64 * 2.0 * np + 16), st);
     NSM_TRY(tail_eval(tp, st));
   }
   return 0;
+}
+
+int nsm_unet_infer(const void* blob, int mode, const float* x, int B, int H, int W, const float* mean,
+                   const float* std, float* y, void* ws, size_t ws_bytes, void* stream) {
+  return infer_impl(blob, mode, x, B, H, W, mean, std, y, nullptr, ws, ws_bytes, stream);
+}
+int nsm_unet_infer_u8(const void* blob, int mode, const float* x, int B, int H, int W, const float* mean,
+                      const float* std, uint8_t* y_u8, void* ws, size_t ws_bytes, void* stream) {
+  return infer_impl(blob, mode, x, B, H, W, mean, std, nullptr, y_u8, ws, ws_bytes, stream);
 }
 
 int nsm_unet_infer_host(const void* blob, int mode, const float* x_host, int B, int H, int W, const float* mean,
@@ -367,6 +376,36 @@ int nsm_unet_infer_host(const void* blob, int mode, const float* x_host, int B, 
     return 1;
   }
   NSM_TRY(nsm_unet_infer(blob, mode, xd, B, H, W, mean, std, yd, ws, ws_bytes, stream));
+  e = cudaMemcpyAsync(y_host, yd, yout, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error("D2H copy / sync: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int nsm_unet_infer_host_u8(const void* blob, int mode, const float* x_host, int B, int H, int W, const float* mean,
+                           const float* std, uint8_t* y_host, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 1 || H < 16 || W < 16) {
+    set_error("nsm_unet_infer_host_u8: bad shape");
+    return 1;
+  }
+  const WorkspaceLayout WL = workspace_layout(B, H, W, mode);
+  if (ws_bytes < WL.total) {
+    set_error("nsm_unet_infer_host_u8: workspace %zu B < required %zu B", ws_bytes, WL.total);
+    return 1;
+  }
+  float* xd = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + WL.x_stage);
+  uint8_t* yd = reinterpret_cast<uint8_t*>(ws) + WL.y_stage;   // the fp32 staging area is large enough for uint8
+  const size_t xin = size_t(B) * 4 * H * W * 4, yout = size_t(B) * WL.lv[0].h * WL.lv[0].w;
+  cudaError_t e = cudaMemcpyAsync(xd, x_host, xin, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) {
+    set_error("H2D copy: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  NSM_TRY(infer_impl(blob, mode, xd, B, H, W, mean, std, nullptr, yd, ws, ws_bytes, stream));
   e = cudaMemcpyAsync(y_host, yd, yout, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {

@@ -454,9 +454,15 @@ __global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ 
     const int x = int(pix32 - t * (unsigned)p.w);
     const unsigned n = t / (unsigned)p.h;
     const int y = int(t - n * (unsigned)p.h);
-    float* o = p.y + ((size_t)n * H + 2 * y) * W + 2 * x;
-    *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
-    *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
+    const size_t oo = ((size_t)n * H + 2 * y) * W + 2 * x;
+    if (p.y) {
+      *reinterpret_cast<float2*>(p.y + oo) = make_float2(r[0], r[1]);
+      *reinterpret_cast<float2*>(p.y + oo + W) = make_float2(r[2], r[3]);
+    }
+    if (p.y_u8) {   // (out * 255).astype(uint8): truncation toward zero of a value in [0, 255]
+      *reinterpret_cast<uchar2*>(p.y_u8 + oo) = make_uchar2((unsigned char)(r[0] * 255.f), (unsigned char)(r[1] * 255.f));
+      *reinterpret_cast<uchar2*>(p.y_u8 + oo + W) = make_uchar2((unsigned char)(r[2] * 255.f), (unsigned char)(r[3] * 255.f));
+    }
   }
 }
 

@@ -56,7 +56,8 @@ struct TailParams {
   const float* w10;  // [4][16]
   const float* b10;  // [4]
   int fmt;
-  float* y;          // [N,1,2h,2w] fp32
+  float* y;          // [N,1,2h,2w] fp32 (or nullptr)
+  uint8_t* y_u8;     // optional [N,1,2h,2w] uint8 = (uint8)(y * 255), the quantisation of infer.py:79 (or nullptr)
 };
 int tail_eval(const TailParams& p, cudaStream_t st);
 

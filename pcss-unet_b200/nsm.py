@@ -57,6 +57,8 @@ def _declare(lib):
                   c_size_t, c_void_p]
     lib.nsm_unet_infer.argtypes = infer_args
     lib.nsm_unet_infer_host.argtypes = infer_args
+    lib.nsm_unet_infer_u8.argtypes = infer_args
+    lib.nsm_unet_infer_host_u8.argtypes = infer_args
     lib.nsm_unet_tap.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_char_p, c_void_p, POINTER(c_int),
                                  POINTER(c_int), POINTER(c_int), c_void_p]
     lib.nsm_nchw_to_planes.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
@@ -97,7 +99,7 @@ def _declare(lib):
     for name in TRAIN_EXPORTS:
         if name != "nsm_wgrad_workspace_bytes":
             getattr(lib, name).restype = c_int
-    for name in ("nsm_profile_enable", "nsm_profile_read", "nsm_unet_pack", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
+    for name in ("nsm_unet_infer_u8", "nsm_unet_infer_host_u8", "nsm_profile_enable", "nsm_profile_read", "nsm_unet_pack", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
                  "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match",
                  "nsm_l1_loss_fwd_bwd", "nsm_channel_sums", "nsm_standardize", "nsm_perturb"):
         getattr(lib, name).restype = c_int
@@ -111,7 +113,7 @@ TRAIN_EXPORTS = [
 ]
 
 EXPORTS = TRAIN_EXPORTS + [
-    "nsm_launch_count",
+    "nsm_launch_count", "nsm_unet_infer_u8", "nsm_unet_infer_host_u8",
     "nsm_last_error", "nsm_version", "nsm_check_device", "nsm_unet_packed_bytes", "nsm_unet_pack",
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
@@ -215,6 +217,15 @@ def unet_infer_host(blob, mode, x_host, y_host, ws, mean=None, std=None):
     check(lib().nsm_unet_infer_host(blob.data_ptr(), mode, x_host.data_ptr(), B, H, W, ptr(mean), ptr(std),
                                     y_host.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()),
           "nsm_unet_infer_host")
+
+
+def unet_infer_host_u8(blob, mode, x_host, y_host, ws, mean=None, std=None):
+    B, C, H, W = x_host.shape
+    assert C == 4 and x_host.dtype == torch.float32 and x_host.is_contiguous() and not x_host.is_cuda
+    assert y_host.dtype == torch.uint8 and y_host.is_contiguous() and not y_host.is_cuda
+    check(lib().nsm_unet_infer_host_u8(blob.data_ptr(), mode, x_host.data_ptr(), B, H, W, ptr(mean), ptr(std),
+                                       y_host.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()),
+          "nsm_unet_infer_host_u8")
 
 
 def unet_tap(ws, B, H, W, mode, name) -> torch.Tensor:

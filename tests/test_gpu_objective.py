@@ -95,3 +95,27 @@ def test_channel_stats_match_reference_golden(nsm, golden, tmp_path):
     x = torch.randn(3, 4, 13, 7, generator=gen(5))
     s = nsm.channel_sums(x.cuda()).cpu()
     assert torch.allclose(s, x.double().sum(dim=(0, 2, 3)), rtol=1e-12, atol=1e-9)
+
+
+def test_device_feeder_matches_reference_standardisation(nsm, tmp_path):
+    """Pinned double-buffered feed + on-GPU standardise == MmapLiverDataset.__getitem__ of the reference (setdata.py:316),
+    bit for bit, in the loader's sequential order."""
+    from setdata_b200 import DeviceFeeder, MmapLiverDataset
+    rng = np.random.default_rng(3)
+    data = (rng.standard_normal((7, 4, 32, 48), dtype=np.float32) * 3 + 1).astype(np.float32)
+    labels = rng.random((7, 1, 32, 48), dtype=np.float32)
+    np.save(tmp_path / "train_inputs.npy", data)
+    np.save(tmp_path / "train_labels.npy", labels)
+    st = oracle.channel_stats(data)
+    np.save(tmp_path / "train_stats.npy", st)
+    ds = MmapLiverDataset(str(tmp_path), split="train")
+    assert len(ds) == 7 and torch.allclose(ds.means, torch.tensor(st["means"], dtype=torch.float32))
+    seen = 0
+    for xb, yb in DeviceFeeder(ds, batch_size=3):
+        assert xb.is_cuda and xb.requires_grad and yb.is_cuda
+        for j in range(xb.shape[0]):
+            ref = oracle.standardise(torch.from_numpy(data[seen]), ds.means.tolist(), ds.stds.tolist())
+            assert torch.equal(xb[j].detach().cpu(), ref)
+            assert torch.equal(yb[j].cpu(), torch.from_numpy(labels[seen]))
+            seen += 1
+    assert seen == 7

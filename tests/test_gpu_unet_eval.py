@@ -150,6 +150,9 @@ def test_fused_standardise_and_host_entry(nsm):
         # host-buffer entry point (H2D + forward + D2H inside one C-ABI call)
         yh = net.infer_host(raw.pin_memory())
         assert torch.equal(yh, y.cpu())
+        # uint8 output path fused into the last kernel == infer.py:79  (out * 255).astype(np.uint8)
+        y8 = net.infer_host_u8(raw.pin_memory())
+        assert y8.dtype == torch.uint8 and torch.equal(y8, (y.cpu() * 255).to(torch.uint8))
 
 
 def test_rejects_bad_input(nsm):
