@@ -164,12 +164,12 @@ int planes_to_nchw(const void* hi, const void* lo, int N, int C, int H, int W, i
 // ------------------------------------------------------------------------------------------------
 // head stage
 // ------------------------------------------------------------------------------------------------
-constexpr int HEAD_T = 16;  // output tile 16 x 16 pixels at (h, w) resolution, 256 threads
+constexpr int HEAD_TH = 16, HEAD_TW = 32;  // output tile (rows x cols) at (h, w) resolution; 256 threads x 2 pixels
 
 struct HeadSmem {
-  float x16[16][HEAD_T + 2][HEAD_T + 3];  // un-shuffled (optionally standardised / even-fixed) input + halo
-  float w0[16 * 9 * 16];                  // [ci][tap][co]
-  float w1[16 * 64];                      // [ci][co]
+  float x16[16][HEAD_TH + 2][HEAD_TW + 4];  // un-shuffled (optionally standardised / even-fixed) input + halo (pitch 36)
+  float w0[16 * 9 * 16];                    // [ci][tap][co]
+  float w1[16 * 64];                        // [ci][co]
   float b0[16], s0[16], t0[16];
   float b1[64], s1[64], t1[64];
 };
@@ -210,7 +210,10 @@ __device__ __forceinline__ void store_planes64(const Planes& dst, size_t elem_of
   }
 }
 
-__global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ HeadParams p) {
+// One thread computes TWO horizontally adjacent output pixels: every weight vector fetched from shared memory feeds two
+// FMAs (6-8 FMAs per LDS instead of 3-4), the two 3x3 input windows share 3x4 values, and the horizontal half of the
+// 2x2 average pool stays inside the thread.
+__global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant__ HeadParams p) {
   extern __shared__ uint8_t head_smem_raw[];
   HeadSmem& s = *reinterpret_cast<HeadSmem*>(head_smem_raw);
   const int H = p.Hin - (p.Hin & 1), W = p.Win - (p.Win & 1);
@@ -218,10 +221,9 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
   const bool resize = (p.Hin & 1) || (p.Win & 1);
   const bool rb = p.fmt == kFmtBf16;
   const int n = blockIdx.z;
-  const int y0 = blockIdx.y * HEAD_T, x0 = blockIdx.x * HEAD_T;
+  const int y0 = blockIdx.y * HEAD_TH, x0 = blockIdx.x * HEAD_TW;
   const int tid = threadIdx.x;
 
-  // parameters -> smem ([ci][tap][co] and [ci][co] so that one LDS.128 feeds four FMAs)
   for (int i = tid; i < 16 * 9 * 16; i += 256) {
     const int co = i & 15, tap = (i >> 4) % 9, ci = i / 144;
     s.w0[i] = p.w0[(co * 16 + ci) * 9 + tap];
@@ -233,10 +235,10 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
   if (tid < 16) { s.b0[tid] = p.b0[tid]; s.s0[tid] = p.s0[tid]; s.t0[tid] = p.t0[tid]; }
   if (tid < 64) { s.b1[tid] = p.b1[tid]; s.s1[tid] = p.s1[tid]; s.t1[tid] = p.t1[tid]; }
 
-  // input tile: full-resolution rows 2*(y0-1) .. 2*(y0+17)-1, zero outside the (even-fixed) image
-  constexpr int FR = 2 * (HEAD_T + 2);
-  for (int i = tid; i < 4 * FR * FR; i += 256) {
-    const int fx = i % FR, fy = (i / FR) % FR, c = i / (FR * FR);
+  // input tile: full-resolution rows 2*(y0-1) .. 2*(y0+HEAD_TH+1)-1, zero outside the (even-fixed) image
+  constexpr int FRH = 2 * (HEAD_TH + 2), FRW = 2 * (HEAD_TW + 2);
+  for (int i = tid; i < 4 * FRH * FRW; i += 256) {
+    const int fx = i % FRW, fy = (i / FRW) % FRH, c = i / (FRW * FRH);
     const int Y = 2 * (y0 - 1) + fy, X = 2 * (x0 - 1) + fx;
     float v = 0.f;
     if (Y >= 0 && Y < H && X >= 0 && X < W) {
@@ -247,98 +249,152 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const __grid_constant__ 
   }
   __syncthreads();
 
-  // thread -> pixel: a warp covers 2 rows x 16 columns so 2x2 pooling partners are lane^1 / lane^16
+  // thread -> pixels (y0 + ly, x0 + 2*lxp + {0,1}); a warp covers 2 rows x 32 columns, vertical pool partner = lane^16
   const int lane = tid & 31, wrp = tid >> 5;
-  const int ly = 2 * wrp + (lane >> 4), lx = lane & 15;
-  const int y = y0 + ly, x = x0 + lx;
-  const bool valid = y < h && x < w;
-  const size_t pix = ((size_t)n * h + y) * w + x;
+  const int ly = 2 * wrp + (lane >> 4), lxp = lane & 15;
+  const int y = y0 + ly, xa = x0 + 2 * lxp;
+  const bool valid0 = y < h && xa < w, valid1 = y < h && xa + 1 < w;
+  const size_t pix0 = ((size_t)n * h + y) * w + xa;
 
-  if (p.x16.p[0] && valid) {  // optional tap for tests
-    float t[16];
+  if (p.x16.p[0]) {  // optional tap for tests
 #pragma unroll
-    for (int c = 0; c < 16; ++c) t[c] = s.x16[c][ly + 1][lx + 1];
-    uint8_t* o0 = reinterpret_cast<uint8_t*>(p.x16.p[0]) + pix * 16 * 2;
-    uint8_t* o1 = p.fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(p.x16.p[1]) + pix * 16 * 2 : nullptr;
+    for (int px = 0; px < 2; ++px) {
+      if (!(px ? valid1 : valid0)) continue;
+      float t[16];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint32_t hw[4], lw[4];
+      for (int c = 0; c < 16; ++c) t[c] = s.x16[c][ly + 1][2 * lxp + px + 1];
+      uint8_t* o0 = reinterpret_cast<uint8_t*>(p.x16.p[0]) + (pix0 + px) * 16 * 2;
+      uint8_t* o1 = p.fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(p.x16.p[1]) + (pix0 + px) * 16 * 2 : nullptr;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float a = t[8 * j + 2 * e], b = t[8 * j + 2 * e + 1];
-        hw[e] = pack_hi(a, b, p.fmt);
-        lw[e] = pack_lo_resid(a, b, hw[e], p.fmt);
+      for (int j = 0; j < 2; ++j) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = t[8 * j + 2 * e], b = t[8 * j + 2 * e + 1];
+          hw[e] = pack_hi(a, b, p.fmt);
+          lw[e] = pack_lo_resid(a, b, hw[e], p.fmt);
+        }
+        stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
       }
-      stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-      if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
     }
   }
 
-  // conv2.conv.0 : 3x3, 16 -> 16
-  float a[16];
+  // conv2.conv.0 : 3x3, 16 -> 16, two pixels
+  float a[2][16];
 #pragma unroll
-  for (int co = 0; co < 16; ++co) a[co] = 0.f;
+  for (int co = 0; co < 16; ++co) a[0][co] = a[1][co] = 0.f;
 #pragma unroll 1
   for (int ci = 0; ci < 16; ++ci) {
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const float xv = s.x16[ci][ly + tap / 3][lx + tap % 3];
-      const float4* wv = reinterpret_cast<const float4*>(&s.w0[(ci * 9 + tap) * 16]);
+    for (int r = 0; r < 3; ++r) {
+      const float2 v01 = *reinterpret_cast<const float2*>(&s.x16[ci][ly + r][2 * lxp]);
+      const float2 v23 = *reinterpret_cast<const float2*>(&s.x16[ci][ly + r][2 * lxp + 2]);
+      const float xv[4] = {v01.x, v01.y, v23.x, v23.y};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 ww = wv[q];
-        a[4 * q] = fmaf(xv, ww.x, a[4 * q]); a[4 * q + 1] = fmaf(xv, ww.y, a[4 * q + 1]);
-        a[4 * q + 2] = fmaf(xv, ww.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(xv, ww.w, a[4 * q + 3]);
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4* wv = reinterpret_cast<const float4*>(&s.w0[(ci * 9 + r * 3 + kx) * 16]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = wv[q];
+          a[0][4 * q] = fmaf(xv[kx], ww.x, a[0][4 * q]); a[0][4 * q + 1] = fmaf(xv[kx], ww.y, a[0][4 * q + 1]);
+          a[0][4 * q + 2] = fmaf(xv[kx], ww.z, a[0][4 * q + 2]); a[0][4 * q + 3] = fmaf(xv[kx], ww.w, a[0][4 * q + 3]);
+          a[1][4 * q] = fmaf(xv[kx + 1], ww.x, a[1][4 * q]); a[1][4 * q + 1] = fmaf(xv[kx + 1], ww.y, a[1][4 * q + 1]);
+          a[1][4 * q + 2] = fmaf(xv[kx + 1], ww.z, a[1][4 * q + 2]); a[1][4 * q + 3] = fmaf(xv[kx + 1], ww.w, a[1][4 * q + 3]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int co = 0; co < 16; ++co) {
-    float v = a[co] + s.b0[co];
-    if (rb) v = rbf(v);
-    v = fmaf(v, s.s0[co], s.t0[co]);
-    if (rb) v = rbf(v);
-    v = lrelu02(v);
-    if (rb) v = rbf(v);
-    a[co] = v;
-  }
-  // conv2.conv.4 : 1x1, 16 -> 64
-  float o[64];
+  for (int px = 0; px < 2; ++px)
 #pragma unroll
-  for (int co = 0; co < 64; ++co) o[co] = 0.f;
+    for (int co = 0; co < 16; ++co) {
+      float v = a[px][co] + s.b0[co];
+      if (rb) v = rbf(v);
+      v = fmaf(v, s.s0[co], s.t0[co]);
+      if (rb) v = rbf(v);
+      v = lrelu02(v);
+      if (rb) v = rbf(v);
+      a[px][co] = v;
+    }
+  // conv2.conv.4 : 1x1, 16 -> 64, in two halves of 32 output channels (register budget)
+  const int hp = h >> 1, wp = w >> 1;
+  const bool pool_ok = !(lane & 16) && (y >> 1) < hp && (xa >> 1) < wp;
+  const size_t ppix = ((size_t)n * hp + (y >> 1)) * wp + (xa >> 1);
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float o[2][32];
 #pragma unroll
-  for (int ci = 0; ci < 16; ++ci) {
-    const float av = a[ci];
-    const float4* wv = reinterpret_cast<const float4*>(&s.w1[ci * 64]);
+    for (int co = 0; co < 32; ++co) o[0][co] = o[1][co] = 0.f;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const float4 ww = wv[q];
-      o[4 * q] = fmaf(av, ww.x, o[4 * q]); o[4 * q + 1] = fmaf(av, ww.y, o[4 * q + 1]);
-      o[4 * q + 2] = fmaf(av, ww.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(av, ww.w, o[4 * q + 3]);
+    for (int ci = 0; ci < 16; ++ci) {
+      const float4* wv = reinterpret_cast<const float4*>(&s.w1[ci * 64 + half * 32]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 ww = wv[q];
+        o[0][4 * q] = fmaf(a[0][ci], ww.x, o[0][4 * q]); o[0][4 * q + 1] = fmaf(a[0][ci], ww.y, o[0][4 * q + 1]);
+        o[0][4 * q + 2] = fmaf(a[0][ci], ww.z, o[0][4 * q + 2]); o[0][4 * q + 3] = fmaf(a[0][ci], ww.w, o[0][4 * q + 3]);
+        o[1][4 * q] = fmaf(a[1][ci], ww.x, o[1][4 * q]); o[1][4 * q + 1] = fmaf(a[1][ci], ww.y, o[1][4 * q + 1]);
+        o[1][4 * q + 2] = fmaf(a[1][ci], ww.z, o[1][4 * q + 2]); o[1][4 * q + 3] = fmaf(a[1][ci], ww.w, o[1][4 * q + 3]);
+      }
+    }
+    float pl[32];
+#pragma unroll
+    for (int co = 0; co < 32; ++co) {
+      const int c = half * 32 + co;
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        float v = o[px][co] + s.b1[c];
+        if (rb) v = rbf(v);
+        v = fmaf(v, s.s1[c], s.t1[c]);
+        if (rb) v = rbf(v);
+        v = lrelu02(v);
+        if (rb) v = rbf(v);
+        o[px][co] = v;
+      }
+      // AvgPool2d(2): horizontal pair in-thread, vertical partner = lane^16
+      float t = o[0][co] + o[1][co];
+      t += __shfl_xor_sync(0xffffffffu, t, 16);
+      t *= 0.25f;
+      pl[co] = rb ? rbf(t) : t;
+    }
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      if (!(px ? valid1 : valid0)) continue;
+      const size_t off = (pix0 + px) * 64 + half * 32;
+      uint8_t* o0 = reinterpret_cast<uint8_t*>(p.c2.p[0]) + off * 2;
+      uint8_t* o1 = p.fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(p.c2.p[1]) + off * 2 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float va = o[px][8 * j + 2 * e], vb = o[px][8 * j + 2 * e + 1];
+          hw[e] = pack_hi(va, vb, p.fmt);
+          lw[e] = pack_lo_resid(va, vb, hw[e], p.fmt);
+        }
+        stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+      }
+    }
+    if (pool_ok) {
+      const size_t off = ppix * 64 + half * 32;
+      uint8_t* o0 = reinterpret_cast<uint8_t*>(p.p2.p[0]) + off * 2;
+      uint8_t* o1 = p.fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(p.p2.p[1]) + off * 2 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float va = pl[8 * j + 2 * e], vb = pl[8 * j + 2 * e + 1];
+          hw[e] = pack_hi(va, vb, p.fmt);
+          lw[e] = pack_lo_resid(va, vb, hw[e], p.fmt);
+        }
+        stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+      }
     }
   }
-#pragma unroll
-  for (int co = 0; co < 64; ++co) {
-    float v = o[co] + s.b1[co];
-    if (rb) v = rbf(v);
-    v = fmaf(v, s.s1[co], s.t1[co]);
-    if (rb) v = rbf(v);
-    v = lrelu02(v);
-    if (rb) v = rbf(v);
-    o[co] = v;
-  }
-  if (valid) store_planes64(p.c2, pix * 64, o, p.fmt);
-  // AvgPool2d(2): partners lane^1 (x) and lane^16 (y)
-  const int hp = h >> 1, wp = w >> 1;
-#pragma unroll
-  for (int co = 0; co < 64; ++co) {
-    float t = o[co] + __shfl_xor_sync(0xffffffffu, o[co], 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 16);
-    t *= 0.25f;
-    o[co] = rb ? rbf(t) : t;
-  }
-  if (!(lane & 1) && !(lane & 16) && (y >> 1) < hp && (x >> 1) < wp)
-    store_planes64(p.p2, (((size_t)n * hp + (y >> 1)) * wp + (x >> 1)) * 64, o, p.fmt);
 }
 
 int head_eval(const HeadParams& p, cudaStream_t st) {
@@ -358,7 +414,7 @@ int head_eval(const HeadParams& p, cudaStream_t st) {
     }
     attr = true;
   }
-  dim3 grid((w + HEAD_T - 1) / HEAD_T, (h + HEAD_T - 1) / HEAD_T, p.N);
+  dim3 grid((w + HEAD_TW - 1) / HEAD_TW, (h + HEAD_TH - 1) / HEAD_TH, p.N);
   head_eval_kernel<<<grid, 256, sizeof(HeadSmem), st>>>(p);
   NSM_CHECK_LAUNCH("head_eval");
   return 0;
