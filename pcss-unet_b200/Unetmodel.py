@@ -11,8 +11,8 @@ kernels of ``libnsm_b200.so`` (tcgen05 implicit-GEMM convolutions with fused Bat
 SIMT head/tail stages, bilinear up-sampling).  There is no PyTorch or CPU fallback: a CPU tensor raises.
 
 Precision ("mode"):
-  * ``fp32`` (default outside autocast): fp32-accurate split-bf16 tensor-core arithmetic, output within 1e-4 of the
-    fp32 reference;
+  * ``fp32`` (default outside autocast): fp32-accurate tensor-core arithmetic on hi+lo half-precision planes (fp16
+    pairs in eval, bf16 pairs in training) with chunked fp32 accumulation, output within 1e-4 of the fp32 reference;
   * ``bf16`` (default under ``torch.autocast``): bf16 storage with the rounding points of the autocast reference.
 Force one with ``Unet(..., precision="bf16")`` or the ``NSM_PRECISION`` environment variable.
 """
