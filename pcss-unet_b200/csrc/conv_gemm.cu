@@ -70,7 +70,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes) {
+                      const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -86,8 +86,9 @@ int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUresult r = fn(map, dt, rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, dt, rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)", int(r), rank,
               (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
@@ -104,8 +105,8 @@ struct ConvKernelParams {
   int tiles_x, tiles_y, n_blocks, total_items, kc_per_tap;
   int fmt;
   int chunk_kb;       // fp32 modes: k-blocks per TMEM accumulation chunk
-  uint32_t idesc_hi;  // A hi-plane x B (bf16 x bf16 in bf16 mode; bf16 x fp16 in fp32 mode)
-  uint32_t idesc_lo;  // A lo-plane (fp16) x B hi-plane (fp16), fp32 mode only
+  uint32_t idesc_hi;    // M = 128, N = BN
+  uint32_t idesc_wide;  // M = 128, N = 2*BN: hi+lo modes, a_hi x [w_hi | w_lo] in one instruction
   ConvEpilogue ep;
 };
 
@@ -114,13 +115,15 @@ struct GemmCfg {
   static constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 elements (2 B)
   static constexpr int B_BYTES = BN * 128;   // BN channels x 64 elements
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  // 8 epilogue warps x 4 KB staging tiles for the TMA stores of the output (32 pixels x 32 channels x {hi, lo})
+  static constexpr int STAGING_BYTES = 8 * 4096;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STAGING_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // fp32 mode keeps two accumulators per stage: [main = a_hi*w_hi | cross = a_hi*w_lo + a_lo*w_hi]
   static constexpr int ACC_COLS = NP * BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two <= 512");
 };
@@ -144,11 +147,41 @@ __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item,
   x0 = tx * kTileW;
 }
 
+// Where one epilogue warp's 32 pixels (2 patch rows x 16 columns) go: the output leaves through TMA stores from a 4 KB
+// per-warp staging tile (one store instruction of 32 lanes x 16 B would touch 32 different cache lines and serialise in
+// the load/store unit: the profile of the thin layers showed the epilogue waiting on exactly those stores).
+// The skip tensor arrives the same way (TMA load into the slot its sum will leave from), issued before the warp waits for
+// the accumulator so that its latency hides behind the MMAs.
+struct EpiTile {
+  uint32_t stg;              // shared-memory address of the warp's 4 KB staging area (1024-byte aligned)
+  const CUtensorMap* out[2]; // box {32 ch, 16, 2, 1}, 64-byte swizzle
+  const CUtensorMap* pool[2];// box {32 ch, 8, 1, 1}
+  const CUtensorMap* res[2]; // as out
+  uint64_t* rbar;            // this warp's two "residual landed" mbarriers (one per slot)
+  uint32_t rphase[2];
+  int x0, y0, n;             // pixel coordinates of the warp's first row
+};
+// Staging slots: hi+lo modes use the whole area per 32-channel group (hi at +0, lo at +2048); the single-plane mode has
+// two 2 KB slots that alternate between groups.
+template <int NP>
+__device__ __forceinline__ uint32_t epi_slot(int g) { return NP == 2 ? 0u : uint32_t(g & 1) * 2048u; }
+template <int NP>
+__device__ __forceinline__ void epi_issue_residual(const EpiTile& et, int g, int cb) {  // one lane
+  uint64_t* bar = et.rbar + (NP == 2 ? 0 : (g & 1));
+  mbar_expect_tx(bar, NP * 2048);
+  const uint32_t dst = et.stg + epi_slot<NP>(g);
+  tma_load_4d_saddr(dst, et.res[0], bar, cb, et.x0, et.y0, et.n);
+  if (NP == 2) tma_load_4d_saddr(dst + 2048, et.res[1], bar, cb, et.x0, et.y0, et.n);
+}
+
 // Epilogue math + stores for 32 consecutive output channels [cb, cb+32) of one pixel (one thread).
 template <int NP>
 __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelParams& p, int cb, bool valid,
-                                              size_t pix, bool pool_anchor, size_t ppix, double& st1, double& st2) {
+                                              size_t pix, EpiTile& et, int g, int ng, double& st1, double& st2) {
   const ConvEpilogue& ep = p.ep;
+  const int lane = threadIdx.x & 31;
+  const bool has_res = ep.residual.p[0] != nullptr;
+  const uint32_t slot = et.stg + epi_slot<NP>(g);
   if (ep.bias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -175,7 +208,6 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
       s1[j] = valid ? v[j] : 0.f;
       s2[j] = s1[j] * s1[j];
     }
-    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
       const bool upper = (lane & off) != 0;
@@ -211,13 +243,16 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
       for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
     }
   }
-  if (ep.residual.p[0] && valid) {
-    const uint8_t* r0 = reinterpret_cast<const uint8_t*>(ep.residual.p[0]) + (pix * p.Cout + cb) * 2;
-    const uint8_t* r1 =
-        NP == 2 ? reinterpret_cast<const uint8_t*>(ep.residual.p[1]) + (pix * p.Cout + cb) * 2 : nullptr;
+  if (has_res) {
+    // the skip values of this group were requested earlier (tile start / after the slot's previous store)
+    const int b = NP == 2 ? 0 : (g & 1);
+    mbar_wait(et.rbar + b, et.rphase[b]);
+    et.rphase[b] ^= 1;
+    const uint32_t row = slot + lane * 64;
+    const uint32_t sw = (lane >> 1) & 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 h = ldg16(r0 + 16 * j);
+      const uint4 h = lds16(row + ((j ^ sw) << 4));
       const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -225,7 +260,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
         v[8 * j + 2 * e + 1] += hi_hi_to_f32(hw[e], p.fmt);
       }
       if (NP == 2) {
-        const uint4 l = ldg16(r1 + 16 * j);
+        const uint4 l = lds16(row + 2048 + ((j ^ sw) << 4));
         const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -239,9 +274,19 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
       for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
     }
   }
-  if (ep.out.p[0] && valid) {
-    uint8_t* o0 = reinterpret_cast<uint8_t*>(ep.out.p[0]) + (pix * p.Cout + cb) * 2;
-    uint8_t* o1 = NP == 2 ? reinterpret_cast<uint8_t*>(ep.out.p[1]) + (pix * p.Cout + cb) * 2 : nullptr;
+  if (ep.out.p[0]) {
+    // registers -> swizzled staging tile (row = lane = pixel, 64 B of channels per plane) -> one TMA store per plane;
+    // pixels outside the image are clipped by the TMA unit
+    if (!has_res) {
+      // the stores that last used this slot must have read it (with a residual the slot was already claimed for its
+      // load, and every lane overwrites only the row it has just read)
+      if (lane == 0) {
+        if (NP == 2 || ng == 1) bulk_wait_read0(); else bulk_wait_read1();   // two alternating slots when ng is even
+      }
+      __syncwarp();
+    }
+    const uint32_t row = slot + lane * 64;
+    const uint32_t sw = (lane >> 1) & 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t hw[4], lw[4];
@@ -251,11 +296,18 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
         hw[e] = pack_hi(a, b, p.fmt);
         if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e], p.fmt);
       }
-      stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-      if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+      sts16(row + ((j ^ sw) << 4), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      if (NP == 2) sts16(row + 2048 + ((j ^ sw) << 4), make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(et.out[0], slot, cb, et.x0, et.y0, et.n);
+      if (NP == 2) tma_store_4d(et.out[1], slot + 2048, cb, et.x0, et.y0, et.n);
+      bulk_commit();
     }
   }
-  if (ep.pool.p[0]) {  // warp-uniform: AvgPool2d(2) over (lane^1, lane^16) partners
+  if (ep.pool.p[0]) {  // warp-uniform: AvgPool2d(2) over (lane^1, lane^16) partners; the anchors are lanes 0,2,..,14
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float s = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 1);
@@ -263,9 +315,12 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
       s *= 0.25f;
       v[j] = ep.round_bf16 ? rbf(s) : s;
     }
-    if (pool_anchor) {
-      uint8_t* o0 = reinterpret_cast<uint8_t*>(ep.pool.p[0]) + (ppix * p.Cout + cb) * 2;
-      uint8_t* o1 = NP == 2 ? reinterpret_cast<uint8_t*>(ep.pool.p[1]) + (ppix * p.Cout + cb) * 2 : nullptr;
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    if ((lane & 17) == 0) {
+      const int r = lane >> 1;  // pooled column inside the warp's 8-pixel pooled row
+      const uint32_t row = slot + r * 64;
+      const uint32_t sw = (r >> 1) & 3;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t hw[4], lw[4];
@@ -275,9 +330,24 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
           hw[e] = pack_hi(a, b, p.fmt);
           if (NP == 2) lw[e] = pack_lo_resid(a, b, hw[e], p.fmt);
         }
-        stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-        if (NP == 2) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+        sts16(row + ((j ^ sw) << 4), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        if (NP == 2) sts16(row + 512 + ((j ^ sw) << 4), make_uint4(lw[0], lw[1], lw[2], lw[3]));
       }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(et.pool[0], slot, cb, et.x0 >> 1, et.y0 >> 1, et.n);
+      if (NP == 2) tma_store_4d(et.pool[1], slot + 512, cb, et.x0 >> 1, et.y0 >> 1, et.n);
+      bulk_commit();
+    }
+  }
+  if (has_res) {
+    // next group that will use this slot: request its skip values as soon as the store above has read the slot
+    const int gs = NP == 2 ? 1 : 2;
+    if (g + gs < ng && lane == 0) {
+      bulk_wait_read0();
+      epi_issue_residual<NP>(et, g + gs, cb + 32 * gs);
     }
   }
 }
@@ -286,17 +356,22 @@ template <int BN, int NP>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+                 const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
+                 const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ ConvKernelParams p) {
   using Cfg = GemmCfg<BN, NP>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // 1024-byte aligned (SWIZZLE_128B)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::STAGES;
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;   // [8 epilogue warps][2 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -308,6 +383,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmB1);
     }
+    if (p.ep.out.p[0]) {
+      tma_prefetch_desc(&tmO0);
+      if (NP == 2) tma_prefetch_desc(&tmO1);
+    }
+    if (p.ep.pool.p[0]) {
+      tma_prefetch_desc(&tmP0);
+      if (NP == 2) tma_prefetch_desc(&tmP1);
+    }
+    if (p.ep.residual.p[0]) {
+      tma_prefetch_desc(&tmR0);
+      if (NP == 2) tma_prefetch_desc(&tmR1);
+    }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -316,6 +403,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 8);
     }
+    for (int a = 0; a < 16; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -377,12 +465,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;  // first MMA of a chunk overwrites
               const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, 1024);
               const uint64_t db_hi = make_desc_sw128(b_hi + k * 32, 16, 1024);
-              umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
               if (NP == 2) {
+                // The weight planes lie back to back in the stage (hi rows, then lo rows) = ONE K-major tile of 2*BN rows:
+                // a_hi x [w_hi | w_lo] is a single MMA of width 2*BN that fills main (columns [0,BN)) and cross
+                // ([BN,2BN)) at once; a_lo x w_hi then accumulates into cross.  Same tensor cycles as three MMAs of
+                // width BN, but a_hi is fetched from shared memory once instead of twice.
                 const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
-                const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
-                umma_bf16(d_cross, da_hi, db_lo, p.idesc_hi, accum);
-                umma_bf16(d_cross, da_lo, db_hi, p.idesc_lo, 1u);
+                umma_bf16(d_main, da_hi, db_hi, p.idesc_wide, accum);
+                umma_bf16(d_cross, da_lo, db_hi, p.idesc_hi, 1u);
+              } else {
+                umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
               }
             }
             umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
@@ -407,6 +499,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int ly = row / kTileW, lx = row % kTileW;
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + half * HB;
     uint32_t acc = 0, acc_phase = 0;
+    EpiTile et;
+    et.stg = smem_u32(staging) + (warp - 2) * 4096;
+    et.out[0] = &tmO0; et.out[1] = &tmO1;
+    et.pool[0] = &tmP0; et.pool[1] = &tmP1;
+    et.res[0] = &tmR0; et.res[1] = &tmR1;
+    et.rbar = res_bar + 2 * (warp - 2);
+    et.rphase[0] = et.rphase[1] = 0;
+    constexpr int NG = HB / 32;   // 32-channel groups per epilogue warp and tile
     // fused BatchNorm statistics: lane l owns channels (column block base + 32*k + l), k < HB/32
     constexpr int NCH = HB / 32;
     double st1[NCH], st2[NCH];
@@ -433,10 +533,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int y = y0 + ly, x = x0 + lx;
       const bool valid = (y < p.H) && (x < p.W);
       const size_t pix = (size_t(n) * p.H + y) * p.W + x;
-      const int Hp = p.H >> 1, Wp = p.W >> 1;
-      const bool pool_anchor = ((lane & 1) == 0) && ((lane & 16) == 0) && ((y >> 1) < Hp) && ((x >> 1) < Wp);
-      const size_t ppix = (size_t(n) * Hp + (y >> 1)) * Wp + (x >> 1);
       const int cbase = nb * BN + half * HB;
+      et.x0 = x0; et.y0 = y0 + 2 * q; et.n = n;
+      if (p.ep.residual.p[0]) {
+        // request the skip values of the first group(s) now: they land in the staging slots while the MMAs run
+        if (lane == 0) {
+          bulk_wait_read0();
+          epi_issue_residual<NP>(et, 0, cbase);
+          if (NP == 1 && NG > 1) epi_issue_residual<NP>(et, 1, cbase + 32);
+        }
+        if (valid && NG > (NP == 2 ? 1 : 2)) {   // later groups: at least pull their lines into L2
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl)
+#pragma unroll
+            for (int off = 0; off < HB * 2; off += 128)
+              prefetch_l2(reinterpret_cast<const uint8_t*>(p.ep.residual.p[pl]) + (pix * p.Cout + cbase) * 2 + off);
+        }
+      }
 
       if (NP == 1) {
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -449,7 +562,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, pool_anchor, ppix, st1[c0 / 32], st2[c0 / 32]);
+          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, et, c0 / 32, NG, st1[c0 / 32], st2[c0 / 32]);
         }
         tc_fence_before();
         __syncwarp();
@@ -484,11 +597,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = sum[c0 + j];
-          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, pool_anchor, ppix, st1[c0 / 32], st2[c0 / 32]);
+          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, et, c0 / 32, NG, st1[c0 / 32], st2[c0 / 32]);
         }
       }
     }
     flush_stats(st_nb);
+    if (lane == 0) bulk_wait0();   // the staging tiles must outlive the TMA stores that read them
   }
 
   tc_fence_before();
@@ -516,7 +630,8 @@ static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int gri
     }
     attr_set = true;
   }
-  kern<<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  kern<<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
+                                                        maps[7], maps[8], maps[9], kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("conv_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
@@ -560,7 +675,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     return 1;
   }
   const int BN = conv_gemm_pick_bn(s);
-  CUtensorMap maps[4];
+  CUtensorMap maps[10];  // A hi/lo, B hi/lo, output hi/lo, pooled output hi/lo, skip hi/lo
   memset(maps, 0, sizeof(maps));
   const uint64_t adims[4] = {uint64_t(s.Cin), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
   const uint64_t astr[3] = {uint64_t(s.Cin) * 2, uint64_t(s.W) * s.Cin * 2, uint64_t(s.H) * s.W * s.Cin * 2};
@@ -582,6 +697,45 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     maps[1] = maps[0];
     maps[3] = maps[2];
   }
+  // output side: 64-byte swizzled boxes of 32 channels x (2 x 16) pixels = what one epilogue warp stages per plane
+  const uint64_t odims[4] = {uint64_t(s.Cout), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
+  const uint64_t ostr[3] = {uint64_t(s.Cout) * 2, uint64_t(s.W) * s.Cout * 2, uint64_t(s.H) * s.W * s.Cout * 2};
+  const uint32_t obox[4] = {32, uint32_t(kTileW), 2, 1};
+  const uint64_t pdims[4] = {uint64_t(s.Cout), uint64_t(s.W / 2), uint64_t(s.H / 2), uint64_t(s.N)};
+  const uint64_t pstr[3] = {uint64_t(s.Cout) * 2, uint64_t(s.W / 2) * s.Cout * 2,
+                            uint64_t(s.H / 2) * (s.W / 2) * s.Cout * 2};
+  const uint32_t pbox[4] = {32, uint32_t(kTileW / 2), 1, 1};
+  if (ep.pool.p[0] && (s.W < 2 || s.H < 2)) {
+    set_error("conv_gemm: pooled output requested for a %dx%d image", s.H, s.W);
+    return 1;
+  }
+  for (int pl = 0; pl < 2; ++pl) {
+    maps[4 + pl] = maps[0];
+    maps[6 + pl] = maps[0];
+    maps[8 + pl] = maps[0];
+    if (pl >= planes) continue;
+    if (ep.residual.p[0]) {
+      if (!ep.residual.p[pl] || !ep.out.p[0]) {
+        set_error("conv_gemm: skip tensor needs plane %d and an output", pl);
+        return 1;
+      }
+      if (encode_tmap_tiled(&maps[8 + pl], ep.residual.p[pl], 4, odims, ostr, obox, 2, 64)) return 1;
+    }
+    if (ep.out.p[0]) {
+      if (!ep.out.p[pl]) {
+        set_error("conv_gemm: null output plane %d", pl);
+        return 1;
+      }
+      if (encode_tmap_tiled(&maps[4 + pl], ep.out.p[pl], 4, odims, ostr, obox, 2, 64)) return 1;
+    }
+    if (ep.pool.p[0]) {
+      if (!ep.pool.p[pl]) {
+        set_error("conv_gemm: null pooled output plane %d", pl);
+        return 1;
+      }
+      if (encode_tmap_tiled(&maps[6 + pl], ep.pool.p[pl], 4, pdims, pstr, pbox, 2, 64)) return 1;
+    }
+  }
   ConvKernelParams kp;
   kp.N = s.N; kp.H = s.H; kp.W = s.W; kp.Cin = s.Cin; kp.Cout = s.Cout; kp.taps = s.taps;
   kp.tiles_x = (s.W + kTileW - 1) / kTileW;
@@ -593,7 +747,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.chunk_kb = g_chunk_kb;
   const uint32_t ef = s.fmt == kFmtF16x2 ? kFmtF16 : kFmtBF16;  // all operand planes of a launch share one element type
   kp.idesc_hi = make_idesc_f16(128, BN, ef, ef, 0, 0);
-  kp.idesc_lo = kp.idesc_hi;
+  kp.idesc_wide = planes == 2 ? make_idesc_f16(128, 2 * BN, ef, ef, 0, 0) : kp.idesc_hi;
   kp.ep = ep;
   const int grid = kp.total_items < num_sms() ? kp.total_items : num_sms();
   if (planes == 1) {

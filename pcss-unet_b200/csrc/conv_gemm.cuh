@@ -43,7 +43,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
 
 // resolved lazily through cudaGetDriverEntryPoint (no link-time dependency on libcuda)
 int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes);
+                      const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes, int swizzle_bytes = 128);
 
 void set_error(const char* fmt, ...);
 // number of kernels this library has launched (bench.py reports it as gpu_launches)
