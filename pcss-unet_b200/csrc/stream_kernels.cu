@@ -164,15 +164,26 @@ int planes_to_nchw(const void* hi, const void* lo, int N, int C, int H, int W, i
 // ------------------------------------------------------------------------------------------------
 // head stage
 // ------------------------------------------------------------------------------------------------
-constexpr int HEAD_TH = 16, HEAD_TW = 32;  // output tile (rows x cols) at (h, w) resolution; 256 threads x 2 pixels
+constexpr int HEAD_TH = 16, HEAD_TW = 32;             // output tile (rows x cols) at (h, w) resolution per 256-thread block
+constexpr int HEAD_HW = HEAD_TW + 2, HEAD_HH = HEAD_TH + 2;
+constexpr int HEAD_PIX = HEAD_HW * HEAD_HH;          // halo tile pixels
 
+// Both convolutions of the head run on the warp-level tensor-core path (mma.sync m16n8k16, fp32 accumulate): with 16
+// channels the layer is far too thin for a 128-wide tcgen05 tile, and as fp32 FMAs it was issue-bound at 13.7 k
+// instructions per warp (profiles/: 0.26 ms against an HBM floor of 0.03 ms).  The hi+lo modes issue the same three
+// products as the big kernel (hi*hi + hi*lo + lo*hi).
+// Shared-memory operands are 16-bit, 32 bytes (16 channels) per row, the two 16-byte halves XOR-swizzled with bit 2 of the
+// row index so that ldmatrix reads 8 consecutive rows without bank conflicts.
 struct HeadSmem {
-  float x16[16][HEAD_TH + 2][HEAD_TW + 4];  // un-shuffled (optionally standardised / even-fixed) input + halo (pitch 36)
-  float w0[16 * 9 * 16];                    // [ci][tap][co]
-  float w1[16 * 64];                        // [ci][co]
+  uint4 xt[2][HEAD_PIX * 2];   // [plane][halo pixel][half]   un-shuffled (standardised, even-fixed) input
+  uint4 w0[2][9 * 16 * 2];     // [plane][tap][co][half of ci]
+  uint4 w1[2][64 * 2];         // [plane][co][half of ci]
   float b0[16], s0[16], t0[16];
   float b1[64], s1[64], t1[64];
 };
+__device__ __forceinline__ uint32_t head_row_off(int row, int half) {
+  return uint32_t(row) * 32u + (uint32_t((half ^ (row >> 2)) & 1) << 4);
+}
 
 __device__ __forceinline__ float head_fetch(const HeadParams& p, int n, int c, int Y, int X, int H, int W,
                                             bool resize) {
@@ -193,223 +204,326 @@ __device__ __forceinline__ float head_fetch(const HeadParams& p, int n, int c, i
   return ly.w0 * (lx.w0 * v00 + lx.w1 * v01) + ly.w1 * (lx.w0 * v10 + lx.w1 * v11);
 }
 
-__device__ __forceinline__ void store_planes64(const Planes& dst, size_t elem_off, const float* v, int fmt) {
-  uint8_t* o0 = reinterpret_cast<uint8_t*>(dst.p[0]) + elem_off * 2;
-  uint8_t* o1 = fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(dst.p[1]) + elem_off * 2 : nullptr;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-      hw[e] = pack_hi(a, b, fmt);
-      lw[e] = pack_lo_resid(a, b, hw[e], fmt);
-    }
-    stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-    if (fmt != kFmtBf16) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+template <int FMT>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (FMT == kFmtF16x2) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   }
 }
+// d += a * w with the operand planes of the storage format (1 product in bf16 mode, 3 in the hi+lo modes)
+template <int FMT>
+__device__ __forceinline__ void head_mma(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                         uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma16816<FMT>(d, ah, bh0, bh1);
+  if (FMT != kFmtBf16) {
+    mma16816<FMT>(d, ah, bl0, bl1);
+    mma16816<FMT>(d, al, bh0, bh1);
+  }
+}
+__device__ __forceinline__ void sts8(uint32_t saddr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts2(uint32_t saddr, unsigned short v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void stg4(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
 
-// One thread computes TWO horizontally adjacent output pixels: every weight vector fetched from shared memory feeds two
-// FMAs (6-8 FMAs per LDS instead of 3-4), the two 3x3 input windows share 3x4 values, and the horizontal half of the
-// 2x2 average pool stays inside the thread.
+template <int FMT>
 __global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant__ HeadParams p) {
   extern __shared__ uint8_t head_smem_raw[];
   HeadSmem& s = *reinterpret_cast<HeadSmem*>(head_smem_raw);
+  constexpr bool rb = FMT == kFmtBf16;
+  constexpr bool two = FMT != kFmtBf16;
   const int H = p.Hin - (p.Hin & 1), W = p.Win - (p.Win & 1);
   const int h = H >> 1, w = W >> 1;
   const bool resize = (p.Hin & 1) || (p.Win & 1);
-  const bool rb = p.fmt == kFmtBf16;
   const int n = blockIdx.z;
   const int y0 = blockIdx.y * HEAD_TH, x0 = blockIdx.x * HEAD_TW;
   const int tid = threadIdx.x;
+  const uint32_t xt0 = smem_u32(&s.xt[0][0]), xt1 = smem_u32(&s.xt[1][0]);
+  const uint32_t w00 = smem_u32(&s.w0[0][0]), w01 = smem_u32(&s.w0[1][0]);
+  const uint32_t w10 = smem_u32(&s.w1[0][0]), w11 = smem_u32(&s.w1[1][0]);
 
-  for (int i = tid; i < 16 * 9 * 16; i += 256) {
-    const int co = i & 15, tap = (i >> 4) % 9, ci = i / 144;
-    s.w0[i] = p.w0[(co * 16 + ci) * 9 + tap];
+  // ---- weights -> 16-bit operand planes ------------------------------------------------------------------------------
+  for (int i = tid; i < 9 * 16 * 16; i += 256) {
+    const int ci = i & 15, co = (i >> 4) & 15, tap = i >> 8;
+    unsigned short hi, lo;
+    split_fmt(p.w0[(co * 16 + ci) * 9 + tap], FMT, hi, lo);
+    const uint32_t off = head_row_off(tap * 16 + co, ci >> 3) + (ci & 7) * 2;
+    sts2(w00 + off, hi);
+    if (two) sts2(w01 + off, lo);
   }
-  for (int i = tid; i < 16 * 64; i += 256) {
-    const int co = i & 63, ci = i >> 6;
-    s.w1[i] = p.w1[co * 16 + ci];
+  for (int i = tid; i < 64 * 16; i += 256) {
+    const int ci = i & 15, co = i >> 4;
+    unsigned short hi, lo;
+    split_fmt(p.w1[co * 16 + ci], FMT, hi, lo);
+    const uint32_t off = head_row_off(co, ci >> 3) + (ci & 7) * 2;
+    sts2(w10 + off, hi);
+    if (two) sts2(w11 + off, lo);
   }
   if (tid < 16) { s.b0[tid] = p.b0[tid]; s.s0[tid] = p.s0[tid]; s.t0[tid] = p.t0[tid]; }
   if (tid < 64) { s.b1[tid] = p.b1[tid]; s.s1[tid] = p.s1[tid]; s.t1[tid] = p.t1[tid]; }
 
-  // input tile: full-resolution rows 2*(y0-1) .. 2*(y0+HEAD_TH+1)-1, zero outside the (even-fixed) image
-  constexpr int FRH = 2 * (HEAD_TH + 2), FRW = 2 * (HEAD_TW + 2);
-  // Batches of 8 independent global loads per thread, all issued before the first use (the profile of the one-load-per-
-  // iteration loop showed 56 % of all stall samples on the load -> convert dependency).
-  constexpr int kLoadBatch = 8;
-  for (int base = tid; base < 4 * FRH * FRW; base += 256 * kLoadBatch) {
-    float v[kLoadBatch];
+  // ---- input: one item = one halo pixel x one of the 4 input channels = a 2x2 full-resolution quad = 4 of the 16
+  //      un-shuffled channels (ch = c*4 + dy*2 + dx), zero outside the (even-fixed) image --------------------------------
+  {
+    const bool vec_ok = !resize && ((reinterpret_cast<uintptr_t>(p.x) & 7) == 0);
+    const float* xn = p.x + (size_t)n * 4 * p.Hin * p.Win;
+    constexpr int kItems = HEAD_PIX * 4, kBatch = 5;
+    for (int base = tid; base < kItems; base += 256 * kBatch) {
+      float v[kBatch][4];
 #pragma unroll
-    for (int u = 0; u < kLoadBatch; ++u) {
-      const int i = base + u * 256;
-      v[u] = 0.f;
-      if (i < 4 * FRH * FRW) {
-        const int fx = i % FRW, fy = (i / FRW) % FRH, c = i / (FRW * FRH);
-        const int Y = 2 * (y0 - 1) + fy, X = 2 * (x0 - 1) + fx;
-        if (Y >= 0 && Y < H && X >= 0 && X < W) v[u] = head_fetch(p, n, c, Y, X, H, W, resize);
+      for (int u = 0; u < kBatch; ++u) {
+        const int item = base + u * 256;
+        v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+        if (item < kItems) {
+          const int c = item & 3, pi = item >> 2;
+          const int ry = pi / HEAD_HW, cx = pi - ry * HEAD_HW;
+          const int y = y0 - 1 + ry, x = x0 - 1 + cx;
+          if (y >= 0 && y < h && x >= 0 && x < w) {
+            if (vec_ok) {
+              const float* q = xn + ((size_t)c * p.Hin + 2 * y) * p.Win + 2 * x;
+              const float2 r0 = __ldg(reinterpret_cast<const float2*>(q));
+              const float2 r1 = __ldg(reinterpret_cast<const float2*>(q + p.Win));
+              v[u][0] = r0.x; v[u][1] = r0.y; v[u][2] = r1.x; v[u][3] = r1.y;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[u][k] = head_fetch(p, n, c, 2 * y + (k >> 1), 2 * x + (k & 1), H, W, resize);
+            }
+          }
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < kLoadBatch; ++u) {
-      const int i = base + u * 256;
-      if (i < 4 * FRH * FRW) {
-        const int fx = i % FRW, fy = (i / FRW) % FRH, c = i / (FRW * FRH);
-        // autocast casts the conv input to bf16; pixel_unshuffle(2): ch = c*4 + dy*2 + dx
-        s.x16[c * 4 + (fy & 1) * 2 + (fx & 1)][fy >> 1][fx >> 1] = rb ? rbf(v[u]) : v[u];
+      for (int u = 0; u < kBatch; ++u) {
+        const int item = base + u * 256;
+        if (item < kItems) {
+          const int c = item & 3, pi = item >> 2;
+          if (vec_ok && p.mean) {
+            const int ry = pi / HEAD_HW, cx = pi - ry * HEAD_HW;
+            const int y = y0 - 1 + ry, x = x0 - 1 + cx;
+            if (y >= 0 && y < h && x >= 0 && x < w) {   // the zero padding is applied AFTER standardisation
+              const float mu = p.mean[c], sd = p.std[c] + 1e-8f;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[u][k] = (v[u][k] - mu) / sd;
+            }
+          }
+          if (rb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = rbf(v[u][k]);   // autocast casts the conv input to bf16
+          }
+          const uint32_t h0 = pack_hi(v[u][0], v[u][1], FMT), h1 = pack_hi(v[u][2], v[u][3], FMT);
+          const uint32_t off = head_row_off(pi, c >> 1) + (c & 1) * 8;
+          sts8(xt0 + off, h0, h1);
+          if (two) sts8(xt1 + off, pack_lo_resid(v[u][0], v[u][1], h0, FMT), pack_lo_resid(v[u][2], v[u][3], h1, FMT));
+        }
       }
     }
   }
   __syncthreads();
 
-  // thread -> pixels (y0 + ly, x0 + 2*lxp + {0,1}); a warp covers 2 rows x 32 columns, vertical pool partner = lane^16
   const int lane = tid & 31, wrp = tid >> 5;
-  const int ly = 2 * wrp + (lane >> 4), lxp = lane & 15;
-  const int y = y0 + ly, xa = x0 + 2 * lxp;
-  const bool valid0 = y < h && xa < w, valid1 = y < h && xa + 1 < w;
-  const size_t pix0 = ((size_t)n * h + y) * w + xa;
+  const int g = lane >> 2, t = lane & 3;       // mma fragment coordinates
+  const int lm = lane >> 3, lr = lane & 7;     // ldmatrix: this lane addresses row lr of matrix lm
 
-  if (p.x16.p[0]) {  // optional tap for tests
+  if (p.x16.p[0]) {  // optional tap for tests: the 16-channel un-shuffled input of the tile's interior pixels
+    for (int i = tid; i < HEAD_TH * HEAD_TW; i += 256) {
+      const int ly = i / HEAD_TW, lx = i - ly * HEAD_TW;
+      const int y = y0 + ly, x = x0 + lx;
+      if (y < h && x < w) {
+        const int pi = (ly + 1) * HEAD_HW + lx + 1;
+        const size_t o = (((size_t)n * h + y) * w + x) * 16 * 2;
 #pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      if (!(px ? valid1 : valid0)) continue;
-      float t[16];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) t[c] = s.x16[c][ly + 1][2 * lxp + px + 1];
-      uint8_t* o0 = reinterpret_cast<uint8_t*>(p.x16.p[0]) + (pix0 + px) * 16 * 2;
-      uint8_t* o1 = p.fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(p.x16.p[1]) + (pix0 + px) * 16 * 2 : nullptr;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float a = t[8 * j + 2 * e], b = t[8 * j + 2 * e + 1];
-          hw[e] = pack_hi(a, b, p.fmt);
-          lw[e] = pack_lo_resid(a, b, hw[e], p.fmt);
+        for (int hf = 0; hf < 2; ++hf) {
+          stg16(reinterpret_cast<uint8_t*>(p.x16.p[0]) + o + 16 * hf, lds16(xt0 + head_row_off(pi, hf)));
+          if (two) stg16(reinterpret_cast<uint8_t*>(p.x16.p[1]) + o + 16 * hf, lds16(xt1 + head_row_off(pi, hf)));
         }
-        stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-        if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
       }
     }
   }
 
-  // conv2.conv.0 : 3x3, 16 -> 16, two pixels
-  float a[2][16];
+  // warp tile: rows 2*wrp, 2*wrp+1 of the block tile x 32 columns = 4 m-tiles of 16 consecutive pixels:
+  //   m-tile mt -> row 2*wrp + (mt >> 1), columns (mt & 1)*16 .. +15
+  // ---- conv2.conv.0 : 3x3, 16 -> 16 as 9 k-steps (one per tap) of K = 16 input channels --------------------------------
+  float acc[4][2][4];
 #pragma unroll
-  for (int co = 0; co < 16; ++co) a[0][co] = a[1][co] = 0.f;
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+  {
+    const int a_col = lr + 8 * (lm & 1), a_half = lm >> 1;         // A: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+    const int b_co = (lm >> 1) * 8 + lr, b_half = lm & 1;          // B: matrices (n-tile 0 | 1) x (k 0-7 | 8-15)
 #pragma unroll 1
-  for (int ci = 0; ci < 16; ++ci) {
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dyy = tap / 3, dxx = tap - dyy * 3;
+      uint32_t bh[4], bl[4] = {0, 0, 0, 0};
+      const uint32_t boff = head_row_off(tap * 16 + b_co, b_half);
+      ldmatrix_x4(bh, w00 + boff);
+      if (two) ldmatrix_x4(bl, w01 + boff);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const float2 v01 = *reinterpret_cast<const float2*>(&s.x16[ci][ly + r][2 * lxp]);
-      const float2 v23 = *reinterpret_cast<const float2*>(&s.x16[ci][ly + r][2 * lxp + 2]);
-      const float xv[4] = {v01.x, v01.y, v23.x, v23.y};
+      for (int mt = 0; mt < 4; ++mt) {
+        const int pi = (2 * wrp + (mt >> 1) + dyy) * HEAD_HW + (mt & 1) * 16 + a_col + dxx;
+        const uint32_t aoff = head_row_off(pi, a_half);
+        uint32_t ah[4], al[4] = {0, 0, 0, 0};
+        ldmatrix_x4(ah, xt0 + aoff);
+        if (two) ldmatrix_x4(al, xt1 + aoff);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float4* wv = reinterpret_cast<const float4*>(&s.w0[(ci * 9 + r * 3 + kx) * 16]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 ww = wv[q];
-          a[0][4 * q] = fmaf(xv[kx], ww.x, a[0][4 * q]); a[0][4 * q + 1] = fmaf(xv[kx], ww.y, a[0][4 * q + 1]);
-          a[0][4 * q + 2] = fmaf(xv[kx], ww.z, a[0][4 * q + 2]); a[0][4 * q + 3] = fmaf(xv[kx], ww.w, a[0][4 * q + 3]);
-          a[1][4 * q] = fmaf(xv[kx + 1], ww.x, a[1][4 * q]); a[1][4 * q + 1] = fmaf(xv[kx + 1], ww.y, a[1][4 * q + 1]);
-          a[1][4 * q + 2] = fmaf(xv[kx + 1], ww.z, a[1][4 * q + 2]); a[1][4 * q + 3] = fmaf(xv[kx + 1], ww.w, a[1][4 * q + 3]);
-        }
+        for (int nt = 0; nt < 2; ++nt)
+          head_mma<FMT>(acc[mt][nt], ah, al, bh[2 * nt], bh[2 * nt + 1], bl[2 * nt], bl[2 * nt + 1]);
       }
     }
   }
+  // bias + BN + LeakyReLU, then straight into the A fragments of the 1x1 convolution: the accumulator layout of two
+  // 8-wide n-tiles (row g / g+8, columns 2t, 2t+1) IS the m16k16 A layout
+  uint32_t a1h[4][4], a1l[4][4];
+  {
+    float pb[2][2], ps[2][2], pt[2][2];
 #pragma unroll
-  for (int px = 0; px < 2; ++px)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-    for (int co = 0; co < 16; ++co) {
-      float v = a[px][co] + s.b0[co];
-      if (rb) v = rbf(v);
-      v = fmaf(v, s.s0[co], s.t0[co]);
-      if (rb) v = rbf(v);
-      v = lrelu02(v);
-      if (rb) v = rbf(v);
-      a[px][co] = v;
+      for (int k = 0; k < 2; ++k) {
+        const int co = nt * 8 + 2 * t + k;
+        pb[nt][k] = s.b0[co]; ps[nt][k] = s.s0[co]; pt[nt][k] = s.t0[co];
+      }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = acc[mt][nt][i] + pb[nt][i & 1];
+          if (rb) v = rbf(v);
+          v = fmaf(v, ps[nt][i & 1], pt[nt][i & 1]);
+          if (rb) v = rbf(v);
+          v = lrelu02(v);
+          if (rb) v = rbf(v);
+          acc[mt][nt][i] = v;
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {   // a0: (g, nt0), a1: (g+8, nt0), a2: (g, nt1), a3: (g+8, nt1)
+        const float e0 = acc[mt][k >> 1][(k & 1) * 2], e1 = acc[mt][k >> 1][(k & 1) * 2 + 1];
+        a1h[mt][k] = pack_hi(e0, e1, FMT);
+        a1l[mt][k] = two ? pack_lo_resid(e0, e1, a1h[mt][k], FMT) : 0u;
+      }
     }
-  // conv2.conv.4 : 1x1, 16 -> 64, in two halves of 32 output channels (register budget)
+  }
+
+  // ---- conv2.conv.4 : 1x1, 16 -> 64, 16 output channels (two n-tiles) at a time ------------------------------------------
   const int hp = h >> 1, wp = w >> 1;
-  const bool pool_ok = !(lane & 16) && (y >> 1) < hp && (xa >> 1) < wp;
-  const size_t ppix = ((size_t)n * hp + (y >> 1)) * wp + (xa >> 1);
+  const int yrow = y0 + 2 * wrp;
+  uint8_t* const c2h = reinterpret_cast<uint8_t*>(p.c2.p[0]);
+  uint8_t* const c2l = reinterpret_cast<uint8_t*>(p.c2.p[1]);
+  uint8_t* const p2h = reinterpret_cast<uint8_t*>(p.p2.p[0]);
+  uint8_t* const p2l = reinterpret_cast<uint8_t*>(p.p2.p[1]);
 #pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    float o[2][32];
-#pragma unroll
-    for (int co = 0; co < 32; ++co) o[0][co] = o[1][co] = 0.f;
-#pragma unroll
-    for (int ci = 0; ci < 16; ++ci) {
-      const float4* wv = reinterpret_cast<const float4*>(&s.w1[ci * 64 + half * 32]);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 ww = wv[q];
-        o[0][4 * q] = fmaf(a[0][ci], ww.x, o[0][4 * q]); o[0][4 * q + 1] = fmaf(a[0][ci], ww.y, o[0][4 * q + 1]);
-        o[0][4 * q + 2] = fmaf(a[0][ci], ww.z, o[0][4 * q + 2]); o[0][4 * q + 3] = fmaf(a[0][ci], ww.w, o[0][4 * q + 3]);
-        o[1][4 * q] = fmaf(a[1][ci], ww.x, o[1][4 * q]); o[1][4 * q + 1] = fmaf(a[1][ci], ww.y, o[1][4 * q + 1]);
-        o[1][4 * q + 2] = fmaf(a[1][ci], ww.z, o[1][4 * q + 2]); o[1][4 * q + 3] = fmaf(a[1][ci], ww.w, o[1][4 * q + 3]);
-      }
+  for (int np = 0; np < 4; ++np) {
+    uint32_t bh[4], bl[4] = {0, 0, 0, 0};
+    {
+      const int co = np * 16 + (lm >> 1) * 8 + lr;
+      const uint32_t boff = head_row_off(co, lm & 1);
+      ldmatrix_x4(bh, w10 + boff);
+      if (two) ldmatrix_x4(bl, w11 + boff);
     }
-    float pl[32];
+    float o[4][2][4];
 #pragma unroll
-    for (int co = 0; co < 32; ++co) {
-      const int c = half * 32 + co;
+    for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        float v = o[px][co] + s.b1[c];
-        if (rb) v = rbf(v);
-        v = fmaf(v, s.s1[c], s.t1[c]);
-        if (rb) v = rbf(v);
-        v = lrelu02(v);
-        if (rb) v = rbf(v);
-        o[px][co] = v;
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[mt][nt][i] = 0.f;
+        head_mma<FMT>(o[mt][nt], a1h[mt], a1l[mt], bh[2 * nt], bh[2 * nt + 1], bl[2 * nt], bl[2 * nt + 1]);
       }
-      // AvgPool2d(2): horizontal pair in-thread, vertical partner = lane^16
-      float t = o[0][co] + o[1][co];
-      t += __shfl_xor_sync(0xffffffffu, t, 16);
-      t *= 0.25f;
-      pl[co] = rb ? rbf(t) : t;
-    }
+    float pb[2][2], ps[2][2], pt[2][2];
 #pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      if (!(px ? valid1 : valid0)) continue;
-      const size_t off = (pix0 + px) * 64 + half * 32;
-      uint8_t* o0 = reinterpret_cast<uint8_t*>(p.c2.p[0]) + off * 2;
-      uint8_t* o1 = p.fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(p.c2.p[1]) + off * 2 : nullptr;
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t hw[4], lw[4];
+      for (int k = 0; k < 2; ++k) {
+        const int co = np * 16 + nt * 8 + 2 * t + k;
+        pb[nt][k] = s.b1[co]; ps[nt][k] = s.s1[co]; pt[nt][k] = s.t1[co];
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float va = o[px][8 * j + 2 * e], vb = o[px][8 * j + 2 * e + 1];
-          hw[e] = pack_hi(va, vb, p.fmt);
-          lw[e] = pack_lo_resid(va, vb, hw[e], p.fmt);
+    for (int mt = 0; mt < 4; ++mt) {
+      const int y = yrow + (mt >> 1);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = o[mt][nt][i] + pb[nt][i & 1];
+          if (rb) v = rbf(v);
+          v = fmaf(v, ps[nt][i & 1], pt[nt][i & 1]);
+          if (rb) v = rbf(v);
+          v = lrelu02(v);
+          if (rb) v = rbf(v);
+          o[mt][nt][i] = v;
         }
-        stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-        if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-      }
-    }
-    if (pool_ok) {
-      const size_t off = ppix * 64 + half * 32;
-      uint8_t* o0 = reinterpret_cast<uint8_t*>(p.p2.p[0]) + off * 2;
-      uint8_t* o1 = p.fmt != kFmtBf16 ? reinterpret_cast<uint8_t*>(p.p2.p[1]) + off * 2 : nullptr;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float va = pl[8 * j + 2 * e], vb = pl[8 * j + 2 * e + 1];
-          hw[e] = pack_hi(va, vb, p.fmt);
-          lw[e] = pack_lo_resid(va, vb, hw[e], p.fmt);
+        for (int ih = 0; ih < 2; ++ih) {   // fragment rows g and g+8 = two pixels of the m-tile
+          const int x = x0 + (mt & 1) * 16 + g + 8 * ih;
+          if (y < h && x < w) {
+            const size_t off = ((((size_t)n * h + y) * w + x) * 64 + np * 16 + nt * 8 + 2 * t) * 2;
+            const uint32_t hw = pack_hi(o[mt][nt][2 * ih], o[mt][nt][2 * ih + 1], FMT);
+            stg4(c2h + off, hw);
+            if (two) stg4(c2l + off, pack_lo_resid(o[mt][nt][2 * ih], o[mt][nt][2 * ih + 1], hw, FMT));
+          }
         }
-        stg16(o0 + 16 * j, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-        if (o1) stg16(o1 + 16 * j, make_uint4(lw[0], lw[1], lw[2], lw[3]));
       }
     }
+    // AvgPool2d(2): vertical partner = m-tile + 2 (same lane), horizontal partner = fragment row g^1 = lane ^ 4
+    const int py = (y0 >> 1) + wrp;
+#pragma unroll
+    for (int mx = 0; mx < 2; ++mx)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float pl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float sv = o[mx][nt][i] + o[mx + 2][nt][i];
+          sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+          sv *= 0.25f;
+          pl[i] = rb ? rbf(sv) : sv;
+        }
+        if ((g & 1) == 0 && py < hp) {
+#pragma unroll
+          for (int ih = 0; ih < 2; ++ih) {
+            const int px = (x0 + mx * 16 + g + 8 * ih) >> 1;
+            if (px < wp) {
+              const size_t off = ((((size_t)n * hp + py) * wp + px) * 64 + np * 16 + nt * 8 + 2 * t) * 2;
+              const uint32_t hw = pack_hi(pl[2 * ih], pl[2 * ih + 1], FMT);
+              stg4(p2h + off, hw);
+              if (two) stg4(p2l + off, pack_lo_resid(pl[2 * ih], pl[2 * ih + 1], hw, FMT));
+            }
+          }
+        }
+      }
   }
+}
+
+template <int FMT>
+static int head_launch(const HeadParams& p, dim3 grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(head_eval_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(HeadSmem));
+    if (e != cudaSuccess) {
+      set_error("head_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr = true;
+  }
+  head_eval_kernel<FMT><<<grid, 256, sizeof(HeadSmem), st>>>(p);
+  return 0;
 }
 
 int head_eval(const HeadParams& p, cudaStream_t st) {
@@ -419,18 +533,12 @@ int head_eval(const HeadParams& p, cudaStream_t st) {
     set_error("head_eval: bad shape N=%d Hin=%d Win=%d", p.N, p.Hin, p.Win);
     return 1;
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(head_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(HeadSmem));
-    if (e != cudaSuccess) {
-      set_error("head_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return 1;
-    }
-    attr = true;
-  }
   dim3 grid((w + HEAD_TW - 1) / HEAD_TW, (h + HEAD_TH - 1) / HEAD_TH, p.N);
-  head_eval_kernel<<<grid, 256, sizeof(HeadSmem), st>>>(p);
+  int rc;
+  if (p.fmt == kFmtBf16) rc = head_launch<kFmtBf16>(p, grid, st);
+  else if (p.fmt == kFmtF16x2) rc = head_launch<kFmtF16x2>(p, grid, st);
+  else rc = head_launch<kFmtBf16x2>(p, grid, st);
+  if (rc) return rc;
   NSM_CHECK_LAUNCH("head_eval");
   return 0;
 }
@@ -667,6 +775,106 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
   if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
 }
 
+// 2x2 outputs per thread for the composite resize (hd >= hs, wd >= ws: adjacent outputs then start at most two source
+// indices apart, so a pair of outputs touches <= 5 consecutive source rows / columns).  Each source value is loaded and
+// unpacked once per thread and feeds up to four outputs; per output the FMA order is the same as in the one-pixel kernel
+// above (taps the output does not use enter with weight 0), so both produce identical bits.
+struct PairTaps {
+  int lo;          // first source index of the union
+  float w[2][5];   // weights of the two outputs on lo .. lo+4
+};
+__device__ __forceinline__ PairTaps pair_taps(int d0, int in_size, int out_size) {
+  const Tap3 a = composite_taps(d0, in_size, out_size);
+  const bool has_b = d0 + 1 < out_size;
+  const Tap3 b = has_b ? composite_taps(d0 + 1, in_size, out_size) : a;
+  PairTaps t;
+  t.lo = a.rmin;
+  const int sh = b.rmin - a.rmin;   // 0, 1 or 2
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    t.w[0][i] = i < 3 ? a.w[i] : 0.f;
+    const int k = i - sh;
+    t.w[1][i] = (has_b && k >= 0 && k < 3) ? (k == 0 ? b.w[0] : (k == 1 ? b.w[1] : b.w[2])) : 0.f;
+  }
+  return t;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) upsample_match2x2_kernel(const UpParams p, int cg_shift, int hpairs, int wpairs) {
+  const int cgs = 1 << cg_shift;
+  const int j = blockIdx.y * 256 + threadIdx.x;
+  const bool active = j < wpairs * cgs;
+  const int cg = j & (cgs - 1), xp = active ? (j >> cg_shift) : 0;
+  const int n = blockIdx.x / hpairs, yp = blockIdx.x - n * hpairs;
+  const bool rb = FMT == kFmtBf16;
+  __shared__ PairTaps s_ty, s_tx[257];
+  const int xp_first = (blockIdx.y * 256) >> cg_shift;
+  {
+    const int count = ((blockIdx.y * 256 + 255) >> cg_shift) - xp_first + 1;
+    if (threadIdx.x == 0) s_ty = pair_taps(2 * yp, p.hs, p.hd);
+    for (int i = threadIdx.x; i < count; i += 256)
+      if (xp_first + i < wpairs) s_tx[i] = pair_taps(2 * (xp_first + i), p.ws, p.wd);
+    __syncthreads();
+  }
+  if (!active) return;   // (only after the barrier; inactive threads must not index the tap tables)
+  const PairTaps ty = s_ty, tx = s_tx[xp - xp_first];
+  const size_t nbase = (size_t)n * p.hs * p.ws;
+  float acc[2][2][8];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[a][b][e] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    if (ty.w[0][r] == 0.f && ty.w[1][r] == 0.f) continue;   // block-uniform
+    const size_t rbase = nbase + (size_t)(ty.lo + r) * p.ws;
+    float h0[8], h1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h0[e] = h1[e] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      if (tx.w[0][c] == 0.f && tx.w[1][c] == 0.f) continue;
+      float v[8];
+      load8<FMT>(p, (rbase + tx.lo + c) * p.C + cg * 8, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        h0[e] = fmaf(tx.w[0][c], v[e], h0[e]);
+        h1[e] = fmaf(tx.w[1][c], v[e], h1[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][0][e] = fmaf(ty.w[0][r], h0[e], acc[0][0][e]);
+      acc[0][1][e] = fmaf(ty.w[0][r], h1[e], acc[0][1][e]);
+      acc[1][0][e] = fmaf(ty.w[1][r], h0[e], acc[1][0][e]);
+      acc[1][1][e] = fmaf(ty.w[1][r], h1[e], acc[1][1][e]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int y = 2 * yp + a;
+    if (y >= p.hd) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int x = 2 * xp + b;
+      if (x >= p.wd) continue;
+      const size_t o = (((size_t)n * p.hd + y) * p.wd + x) * p.C + cg * 8;
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v0 = acc[a][b][2 * e], v1 = acc[a][b][2 * e + 1];
+        if (rb) { v0 = rbf(v0); v1 = rbf(v1); }
+        hw[e] = pack_hi(v0, v1, FMT);
+        lw[e] = pack_lo_resid(v0, v1, hw[e], FMT);
+      }
+      stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    }
+  }
+}
+
 // Fast path of the plain x2 up-sample (destination exactly 2hs x 2ws): one thread produces a 2x2 output block of 8
 // channels from the 3x3 source neighbourhood (rows/cols {b-1, b, b+1} clamped).  With align_corners the even output row
 // 2b interpolates source rows (b-1, b) and the odd row 2b+1 rows (b, b+1) -- see make_lerp: src = dst*(hs-1)/(2hs-1) --
@@ -682,54 +890,70 @@ __device__ __forceinline__ void up2x_weights(int b, int in_size, float& we0, flo
   wo0 = 1.f - wo1;
 }
 
+// One thread walks down a strip of kUpStrip source rows at source column xb: every source row is loaded (3 columns),
+// unpacked and interpolated horizontally ONCE and then feeds the two output rows above and the two below it, so a 2x2
+// output block costs 3 loads instead of 9.
+constexpr int kUpStrip = 4;
+
 template <int FMT>
-__global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p, int cg_shift) {
+__device__ __forceinline__ void up2x_hrow(const UpParams& p, size_t rbase, const int (&cols)[3], int cg, float wxe0,
+                                          float wxe1, float wxo0, float wxo1, float (&he)[8], float (&ho)[8]) {
+  float a[8], b[8], c[8];
+  load8<FMT>(p, (rbase + cols[0]) * p.C + cg * 8, a);
+  load8<FMT>(p, (rbase + cols[1]) * p.C + cg * 8, b);
+  load8<FMT>(p, (rbase + cols[2]) * p.C + cg * 8, c);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    he[e] = wxe0 * a[e] + wxe1 * b[e];
+    ho[e] = wxo0 * b[e] + wxo1 * c[e];
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ void up2x_store(const UpParams& p, size_t o, float w0, float w1, const float (&top)[8],
+                                           const float (&bot)[8]) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v0 = w0 * top[2 * e] + w1 * bot[2 * e], v1 = w0 * top[2 * e + 1] + w1 * bot[2 * e + 1];
+    if (FMT == kFmtBf16) { v0 = rbf(v0); v1 = rbf(v1); }
+    hw[e] = pack_hi(v0, v1, FMT);
+    lw[e] = pack_lo_resid(v0, v1, hw[e], FMT);
+  }
+  stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+  if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p, int cg_shift, int strips) {
   const int cgs = 1 << cg_shift;
   const int j = blockIdx.y * 256 + threadIdx.x;
   if (j >= p.ws * cgs) return;
   const int cg = j & (cgs - 1), xb = j >> cg_shift;
-  const int n = blockIdx.x / p.hs, yb = blockIdx.x - n * p.hs;
-  const bool rb = FMT == kFmtBf16;
-  float wye0, wye1, wyo0, wyo1, wxe0, wxe1, wxo0, wxo1;
-  up2x_weights(yb, p.hs, wye0, wye1, wyo0, wyo1);
+  const int n = blockIdx.x / strips, y_first = (blockIdx.x - n * strips) * kUpStrip;
+  const int y_end = min(y_first + kUpStrip, p.hs);
+  float wxe0, wxe1, wxo0, wxo1;
   up2x_weights(xb, p.ws, wxe0, wxe1, wxo0, wxo1);
-  const int rows[3] = {yb > 0 ? yb - 1 : 0, yb, yb < p.hs - 1 ? yb + 1 : p.hs - 1};
   const int cols[3] = {xb > 0 ? xb - 1 : 0, xb, xb < p.ws - 1 ? xb + 1 : p.ws - 1};
-  float he[3][8], ho[3][8];   // horizontally interpolated source rows for the even / odd output column
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const size_t rbase = ((size_t)n * p.hs + rows[r]) * p.ws;
-    float a[8], b[8], c[8];
-    load8<FMT>(p, (rbase + cols[0]) * p.C + cg * 8, a);
-    load8<FMT>(p, (rbase + cols[1]) * p.C + cg * 8, b);
-    load8<FMT>(p, (rbase + cols[2]) * p.C + cg * 8, c);
+  const size_t nrow = (size_t)n * p.hs;
+  // horizontally interpolated source rows (even / odd output column): previous, current, next
+  float pe[8], po[8], ce[8], co[8], ne[8], no[8];
+  up2x_hrow<FMT>(p, (nrow + (y_first > 0 ? y_first - 1 : 0)) * p.ws, cols, cg, wxe0, wxe1, wxo0, wxo1, pe, po);
+  up2x_hrow<FMT>(p, (nrow + y_first) * p.ws, cols, cg, wxe0, wxe1, wxo0, wxo1, ce, co);
+  for (int yb = y_first; yb < y_end; ++yb) {
+    up2x_hrow<FMT>(p, (nrow + (yb < p.hs - 1 ? yb + 1 : p.hs - 1)) * p.ws, cols, cg, wxe0, wxe1, wxo0, wxo1, ne, no);
+    float wye0, wye1, wyo0, wyo1;
+    up2x_weights(yb, p.hs, wye0, wye1, wyo0, wyo1);
+    const size_t o = (((size_t)n * p.hd + 2 * yb) * p.wd + 2 * xb) * p.C + cg * 8;
+    const size_t down = (size_t)p.wd * p.C;
+    up2x_store<FMT>(p, o, wye0, wye1, pe, ce);                  // even row: source rows (yb-1, yb)
+    up2x_store<FMT>(p, o + p.C, wye0, wye1, po, co);
+    up2x_store<FMT>(p, o + down, wyo0, wyo1, ce, ne);           // odd row: (yb, yb+1)
+    up2x_store<FMT>(p, o + down + p.C, wyo0, wyo1, co, no);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      he[r][e] = wxe0 * a[e] + wxe1 * b[e];
-      ho[r][e] = wxo0 * b[e] + wxo1 * c[e];
-    }
-  }
-#pragma unroll
-  for (int oy = 0; oy < 2; ++oy) {
-    const float w0 = oy ? wyo0 : wye0, w1 = oy ? wyo1 : wye1;
-#pragma unroll
-    for (int ox = 0; ox < 2; ++ox) {
-      float r[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float top = ox ? ho[oy][e] : he[oy][e], bot = ox ? ho[oy + 1][e] : he[oy + 1][e];
-        const float v = w0 * top + w1 * bot;
-        r[e] = rb ? rbf(v) : v;
-      }
-      const size_t o = (((size_t)n * p.hd + 2 * yb + oy) * p.wd + 2 * xb + ox) * p.C + cg * 8;
-      uint32_t hw[4], lw[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        hw[e] = pack_hi(r[2 * e], r[2 * e + 1], FMT);
-        lw[e] = pack_lo_resid(r[2 * e], r[2 * e + 1], hw[e], FMT);
-      }
-      stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-      if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+      pe[e] = ce[e]; po[e] = co[e];
+      ce[e] = ne[e]; co[e] = no[e];
     }
   }
 }
@@ -748,12 +972,17 @@ int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes
   p.d0 = (uint8_t*)dst.p[0]; p.d1 = (uint8_t*)dst.p[1];
   p.N = N; p.hs = hs; p.ws = ws; p.C = C; p.hd = hd; p.wd = wd; p.fmt = fmt;
   if (hd == 2 * hs && wd == 2 * ws) {
-    dim3 grid((unsigned)(N * hs), (unsigned)((ws * cgs + 255) / 256));
-    {
-      if (fmt == kFmtBf16) upsample2x_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift);
-      else if (fmt == kFmtF16x2) upsample2x_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift);
-      else upsample2x_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift);
-    }
+    const int strips = (hs + kUpStrip - 1) / kUpStrip;
+    dim3 grid((unsigned)(N * strips), (unsigned)((ws * cgs + 255) / 256));
+    if (fmt == kFmtBf16) upsample2x_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift, strips);
+    else if (fmt == kFmtF16x2) upsample2x_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, strips);
+    else upsample2x_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, strips);
+  } else if (hd >= hs && wd >= ws) {
+    const int hpairs = (hd + 1) / 2, wpairs = (wd + 1) / 2;
+    dim3 grid((unsigned)(N * hpairs), (unsigned)((wpairs * cgs + 255) / 256));
+    if (fmt == kFmtBf16) upsample_match2x2_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift, hpairs, wpairs);
+    else if (fmt == kFmtF16x2) upsample_match2x2_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, hpairs, wpairs);
+    else upsample_match2x2_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, hpairs, wpairs);
   } else {
     dim3 grid((unsigned)(N * hd), (unsigned)((wd * cgs + 255) / 256));
     {
