@@ -34,6 +34,7 @@ struct PackedLayout {
   size_t v3[8][3];  // bias, scale, shift of the 3x3 stage  [cin]
   size_t v1[8][3];  // bias, scale, shift of the 1x1 stage  [cout]
   size_t w10, b10;
+  size_t head_img;  // conv2's operand image for the head kernel (head_pack_image)
   size_t total;
 };
 
@@ -62,6 +63,7 @@ static PackedLayout packed_layout(int mode) {
   }
   L.w10 = take(4 * 16 * 4);
   L.b10 = take(4 * 4);
+  L.head_img = take(kHeadImageBytes);
   L.total = off;
   return L;
 }
@@ -233,6 +235,9 @@ int nsm_unet_pack(const float* const* T, int mode, void* blob, void* stream) {
   }
   NSM_TRY(copy_round(T[96], reinterpret_cast<float*>(base + L.w10), 64, rb, st));
   NSM_TRY(copy_round(T[97], reinterpret_cast<float*>(base + L.b10), 4, rb, st));
+  auto fv = [&](size_t off) { return reinterpret_cast<const float*>(base + off); };
+  NSM_TRY(head_pack_image(fv(L.w3[0][0]), fv(L.v3[0][0]), fv(L.v3[0][1]), fv(L.v3[0][2]), fv(L.w1[0][0]), fv(L.v1[0][0]),
+                          fv(L.v1[0][1]), fv(L.v1[0][2]), mode, base + L.head_img, st));
   return 0;
 }
 
@@ -275,8 +280,7 @@ static int infer_impl(const void* blob, int mode, const float* x, int B, int H, 
   {
     HeadParams hp;
     hp.x = x; hp.N = B; hp.Hin = H; hp.Win = W; hp.mean = mean; hp.std = std;
-    hp.w0 = fvec(PL.w3[0][0]); hp.b0 = fvec(PL.v3[0][0]); hp.s0 = fvec(PL.v3[0][1]); hp.t0 = fvec(PL.v3[0][2]);
-    hp.w1 = fvec(PL.w1[0][0]); hp.b1 = fvec(PL.v1[0][0]); hp.s1 = fvec(PL.v1[0][1]); hp.t1 = fvec(PL.v1[0][2]);
+    hp.img = pb + PL.head_img;
     hp.fmt = mode; hp.c2 = buf("c2"); hp.p2 = buf("p2"); hp.x16 = none;
     const double px = double(B) * WL.lv[1].h * WL.lv[1].w;
     ProfScope ps("head(conv2)", px * 2.0 * (16 * 144 + 16 * 64),

@@ -174,13 +174,20 @@ constexpr int HEAD_PIX = HEAD_HW * HEAD_HH;          // halo tile pixels
 // products as the big kernel (hi*hi + hi*lo + lo*hi).
 // Shared-memory operands are 16-bit, 32 bytes (16 channels) per row, the two 16-byte halves XOR-swizzled with bit 2 of the
 // row index so that ldmatrix reads 8 consecutive rows without bank conflicts.
-struct HeadSmem {
-  uint4 xt[2][HEAD_PIX * 2];   // [plane][halo pixel][half]   un-shuffled (standardised, even-fixed) input
+struct HeadWeights {
   uint4 w0[2][9 * 16 * 2];     // [plane][tap][co][half of ci]
   uint4 w1[2][64 * 2];         // [plane][co][half of ci]
   float b0[16], s0[16], t0[16];
   float b1[64], s1[64], t1[64];
 };
+struct HeadSmem {
+  // per-warp staging for the TMA stores of one 16-channel slice: out hi / lo (2 rows x 32 px x 32 B each), pooled hi / lo
+  // (16 px x 32 B each); every sub-tile starts on a 256-byte boundary (32-byte swizzle = the XOR of head_row_off)
+  uint4 stage[8][320];
+  uint4 xt[2][HEAD_PIX * 2];   // [plane][halo pixel][half]   un-shuffled (standardised, even-fixed) input
+  HeadWeights wt;              // copied verbatim from the image head_pack_image() built at pack time
+};
+static_assert(sizeof(HeadWeights) == kHeadImageBytes, "head weight image size");
 __device__ __forceinline__ uint32_t head_row_off(int row, int half) {
   return uint32_t(row) * 32u + (uint32_t((half ^ (row >> 2)) & 1) << 4);
 }
@@ -237,12 +244,18 @@ __device__ __forceinline__ void sts8(uint32_t saddr, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void sts2(uint32_t saddr, unsigned short v) {
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
 }
-__device__ __forceinline__ void stg4(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
+__device__ __forceinline__ void sts4(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant__ HeadParams p) {
+__global__ void __launch_bounds__(256, 2)
+head_eval_kernel(const __grid_constant__ HeadParams p, const __grid_constant__ CUtensorMap tmC0,
+                 const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmP0,
+                 const __grid_constant__ CUtensorMap tmP1, int has_pool) {
   extern __shared__ uint8_t head_smem_raw[];
-  HeadSmem& s = *reinterpret_cast<HeadSmem*>(head_smem_raw);
+  const uint32_t raw_addr = smem_u32(head_smem_raw);
+  HeadSmem& s = *reinterpret_cast<HeadSmem*>(head_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr));
   constexpr bool rb = FMT == kFmtBf16;
   constexpr bool two = FMT != kFmtBf16;
   const int H = p.Hin - (p.Hin & 1), W = p.Win - (p.Win & 1);
@@ -252,28 +265,15 @@ __global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant
   const int y0 = blockIdx.y * HEAD_TH, x0 = blockIdx.x * HEAD_TW;
   const int tid = threadIdx.x;
   const uint32_t xt0 = smem_u32(&s.xt[0][0]), xt1 = smem_u32(&s.xt[1][0]);
-  const uint32_t w00 = smem_u32(&s.w0[0][0]), w01 = smem_u32(&s.w0[1][0]);
-  const uint32_t w10 = smem_u32(&s.w1[0][0]), w11 = smem_u32(&s.w1[1][0]);
+  const uint32_t w00 = smem_u32(&s.wt.w0[0][0]), w01 = smem_u32(&s.wt.w0[1][0]);
+  const uint32_t w10 = smem_u32(&s.wt.w1[0][0]), w11 = smem_u32(&s.wt.w1[1][0]);
 
-  // ---- weights -> 16-bit operand planes ------------------------------------------------------------------------------
-  for (int i = tid; i < 9 * 16 * 16; i += 256) {
-    const int ci = i & 15, co = (i >> 4) & 15, tap = i >> 8;
-    unsigned short hi, lo;
-    split_fmt(p.w0[(co * 16 + ci) * 9 + tap], FMT, hi, lo);
-    const uint32_t off = head_row_off(tap * 16 + co, ci >> 3) + (ci & 7) * 2;
-    sts2(w00 + off, hi);
-    if (two) sts2(w01 + off, lo);
+  // ---- weights: the ready-made operand image (split, swizzled at pack time) ----------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.img);
+    uint4* dst = reinterpret_cast<uint4*>(&s.wt);
+    for (int i = tid; i < kHeadImageBytes / 16; i += 256) dst[i] = __ldg(src + i);
   }
-  for (int i = tid; i < 64 * 16; i += 256) {
-    const int ci = i & 15, co = i >> 4;
-    unsigned short hi, lo;
-    split_fmt(p.w1[co * 16 + ci], FMT, hi, lo);
-    const uint32_t off = head_row_off(co, ci >> 3) + (ci & 7) * 2;
-    sts2(w10 + off, hi);
-    if (two) sts2(w11 + off, lo);
-  }
-  if (tid < 16) { s.b0[tid] = p.b0[tid]; s.s0[tid] = p.s0[tid]; s.t0[tid] = p.t0[tid]; }
-  if (tid < 64) { s.b1[tid] = p.b1[tid]; s.s1[tid] = p.s1[tid]; s.t1[tid] = p.t1[tid]; }
 
   // ---- input: one item = one halo pixel x one of the 4 input channels = a 2x2 full-resolution quad = 4 of the 16
   //      un-shuffled channels (ch = c*4 + dy*2 + dx), zero outside the (even-fixed) image --------------------------------
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int co = nt * 8 + 2 * t + k;
-        pb[nt][k] = s.b0[co]; ps[nt][k] = s.s0[co]; pt[nt][k] = s.t0[co];
+        pb[nt][k] = s.wt.b0[co]; ps[nt][k] = s.wt.s0[co]; pt[nt][k] = s.wt.t0[co];
       }
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
@@ -420,13 +420,10 @@ __global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant
     }
   }
 
-  // ---- conv2.conv.4 : 1x1, 16 -> 64, 16 output channels (two n-tiles) at a time ------------------------------------------
-  const int hp = h >> 1, wp = w >> 1;
+  // ---- conv2.conv.4 : 1x1, 16 -> 64, 16 output channels (two n-tiles) at a time; every slice leaves through the warp's
+  //      staging tile and TMA stores (which also clip the pixels outside the image) -----------------------------------------
   const int yrow = y0 + 2 * wrp;
-  uint8_t* const c2h = reinterpret_cast<uint8_t*>(p.c2.p[0]);
-  uint8_t* const c2l = reinterpret_cast<uint8_t*>(p.c2.p[1]);
-  uint8_t* const p2h = reinterpret_cast<uint8_t*>(p.p2.p[0]);
-  uint8_t* const p2l = reinterpret_cast<uint8_t*>(p.p2.p[1]);
+  const uint32_t stg = smem_u32(&s.stage[wrp][0]);
 #pragma unroll 1
   for (int np = 0; np < 4; ++np) {
     uint32_t bh[4], bl[4] = {0, 0, 0, 0};
@@ -451,11 +448,12 @@ __global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int co = np * 16 + nt * 8 + 2 * t + k;
-        pb[nt][k] = s.b1[co]; ps[nt][k] = s.s1[co]; pt[nt][k] = s.t1[co];
+        pb[nt][k] = s.wt.b1[co]; ps[nt][k] = s.wt.s1[co]; pt[nt][k] = s.wt.t1[co];
       }
+    if (lane == 0) bulk_wait_read0();   // the previous slice has left the staging tile
+    __syncwarp();
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-      const int y = yrow + (mt >> 1);
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
@@ -470,18 +468,15 @@ __global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant
         }
 #pragma unroll
         for (int ih = 0; ih < 2; ++ih) {   // fragment rows g and g+8 = two pixels of the m-tile
-          const int x = x0 + (mt & 1) * 16 + g + 8 * ih;
-          if (y < h && x < w) {
-            const size_t off = ((((size_t)n * h + y) * w + x) * 64 + np * 16 + nt * 8 + 2 * t) * 2;
-            const uint32_t hw = pack_hi(o[mt][nt][2 * ih], o[mt][nt][2 * ih + 1], FMT);
-            stg4(c2h + off, hw);
-            if (two) stg4(c2l + off, pack_lo_resid(o[mt][nt][2 * ih], o[mt][nt][2 * ih + 1], hw, FMT));
-          }
+          const int row = (mt >> 1) * 32 + (mt & 1) * 16 + g + 8 * ih;
+          const uint32_t off = head_row_off(row, nt) + 4 * t;
+          const uint32_t hw = pack_hi(o[mt][nt][2 * ih], o[mt][nt][2 * ih + 1], FMT);
+          sts4(stg + off, hw);
+          if (two) sts4(stg + 2048 + off, pack_lo_resid(o[mt][nt][2 * ih], o[mt][nt][2 * ih + 1], hw, FMT));
         }
       }
     }
     // AvgPool2d(2): vertical partner = m-tile + 2 (same lane), horizontal partner = fragment row g^1 = lane ^ 4
-    const int py = (y0 >> 1) + wrp;
 #pragma unroll
     for (int mx = 0; mx < 2; ++mx)
 #pragma unroll
@@ -494,50 +489,121 @@ __global__ void __launch_bounds__(256, 2) head_eval_kernel(const __grid_constant
           sv *= 0.25f;
           pl[i] = rb ? rbf(sv) : sv;
         }
-        if ((g & 1) == 0 && py < hp) {
+        if ((g & 1) == 0) {
 #pragma unroll
           for (int ih = 0; ih < 2; ++ih) {
-            const int px = (x0 + mx * 16 + g + 8 * ih) >> 1;
-            if (px < wp) {
-              const size_t off = ((((size_t)n * hp + py) * wp + px) * 64 + np * 16 + nt * 8 + 2 * t) * 2;
-              const uint32_t hw = pack_hi(pl[2 * ih], pl[2 * ih + 1], FMT);
-              stg4(p2h + off, hw);
-              if (two) stg4(p2l + off, pack_lo_resid(pl[2 * ih], pl[2 * ih + 1], hw, FMT));
-            }
+            const int row = mx * 8 + (g >> 1) + 4 * ih;   // pooled pixel inside the warp's 16-pixel pooled row
+            const uint32_t off = head_row_off(row, nt) + 4 * t;
+            const uint32_t hw = pack_hi(pl[2 * ih], pl[2 * ih + 1], FMT);
+            sts4(stg + 4096 + off, hw);
+            if (two) sts4(stg + 4608 + off, pack_lo_resid(pl[2 * ih], pl[2 * ih + 1], hw, FMT));
           }
         }
       }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(&tmC0, stg, np * 16, x0, yrow, n);
+      if (two) tma_store_4d(&tmC1, stg + 2048, np * 16, x0, yrow, n);
+      if (has_pool) {
+        tma_store_4d(&tmP0, stg + 4096, np * 16, x0 >> 1, yrow >> 1, n);
+        if (two) tma_store_4d(&tmP1, stg + 4608, np * 16, x0 >> 1, yrow >> 1, n);
+      }
+      bulk_commit();
+    }
   }
+  if (lane == 0) bulk_wait0();
+}
+
+// Builds the head's shared-memory weight image once per parameter version (nsm_unet_pack).
+struct HeadPackArgs {
+  const float *w0, *b0, *s0, *t0, *w1, *b1, *s1, *t1;
+  int fmt;
+  HeadWeights* img;
+};
+__global__ void head_pack_kernel(const HeadPackArgs a) {
+  uint8_t* w0p[2] = {reinterpret_cast<uint8_t*>(&a.img->w0[0][0]), reinterpret_cast<uint8_t*>(&a.img->w0[1][0])};
+  uint8_t* w1p[2] = {reinterpret_cast<uint8_t*>(&a.img->w1[0][0]), reinterpret_cast<uint8_t*>(&a.img->w1[1][0])};
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * 16 * 16; i += blockDim.x) {
+    const int ci = i & 15, co = (i >> 4) & 15, tap = i >> 8;
+    unsigned short hi, lo;
+    split_fmt(a.w0[(co * 16 + ci) * 9 + tap], a.fmt, hi, lo);
+    const uint32_t off = head_row_off(tap * 16 + co, ci >> 3) + (ci & 7) * 2;
+    *reinterpret_cast<unsigned short*>(w0p[0] + off) = hi;
+    *reinterpret_cast<unsigned short*>(w0p[1] + off) = a.fmt == kFmtBf16 ? (unsigned short)0 : lo;
+  }
+  for (int i = tid; i < 64 * 16; i += blockDim.x) {
+    const int ci = i & 15, co = i >> 4;
+    unsigned short hi, lo;
+    split_fmt(a.w1[co * 16 + ci], a.fmt, hi, lo);
+    const uint32_t off = head_row_off(co, ci >> 3) + (ci & 7) * 2;
+    *reinterpret_cast<unsigned short*>(w1p[0] + off) = hi;
+    *reinterpret_cast<unsigned short*>(w1p[1] + off) = a.fmt == kFmtBf16 ? (unsigned short)0 : lo;
+  }
+  if (tid < 16) { a.img->b0[tid] = a.b0[tid]; a.img->s0[tid] = a.s0[tid]; a.img->t0[tid] = a.t0[tid]; }
+  if (tid < 64) { a.img->b1[tid] = a.b1[tid]; a.img->s1[tid] = a.s1[tid]; a.img->t1[tid] = a.t1[tid]; }
+}
+int head_pack_image(const float* w0, const float* b0, const float* s0, const float* t0, const float* w1,
+                    const float* b1, const float* s1, const float* t1, int fmt, void* img, cudaStream_t st) {
+  HeadPackArgs a{w0, b0, s0, t0, w1, b1, s1, t1, fmt, reinterpret_cast<HeadWeights*>(img)};
+  head_pack_kernel<<<1, 256, 0, st>>>(a);
+  NSM_CHECK_LAUNCH("head_pack_image");
+  return 0;
 }
 
 template <int FMT>
-static int head_launch(const HeadParams& p, dim3 grid, cudaStream_t st) {
+static int head_launch(const HeadParams& p, const CUtensorMap* maps, int has_pool, dim3 grid, cudaStream_t st) {
+  constexpr int kSmem = (int)sizeof(HeadSmem) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(head_eval_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(HeadSmem));
+    cudaError_t e = cudaFuncSetAttribute(head_eval_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) {
       set_error("head_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return 1;
     }
     attr = true;
   }
-  head_eval_kernel<FMT><<<grid, 256, sizeof(HeadSmem), st>>>(p);
+  head_eval_kernel<FMT><<<grid, 256, kSmem, st>>>(p, maps[0], maps[1], maps[2], maps[3], has_pool);
   return 0;
 }
 
 int head_eval(const HeadParams& p, cudaStream_t st) {
   const int H = p.Hin - (p.Hin & 1), W = p.Win - (p.Win & 1);
   const int h = H / 2, w = W / 2;
-  if (h < 1 || w < 1 || p.N < 1) {
-    set_error("head_eval: bad shape N=%d Hin=%d Win=%d", p.N, p.Hin, p.Win);
+  if (h < 1 || w < 1 || p.N < 1 || !p.img) {
+    set_error("head_eval: bad shape N=%d Hin=%d Win=%d or missing weight image", p.N, p.Hin, p.Win);
     return 1;
+  }
+  const int planes = fmt_planes(p.fmt);
+  const int hp = h / 2, wp = w / 2;
+  const int has_pool = (p.p2.p[0] && hp > 0 && wp > 0) ? 1 : 0;
+  CUtensorMap maps[4];   // c2 hi/lo, p2 hi/lo: boxes of 16 channels (32 bytes, 32-byte swizzle)
+  memset(maps, 0, sizeof(maps));
+  const uint64_t cdims[4] = {64, uint64_t(w), uint64_t(h), uint64_t(p.N)};
+  const uint64_t cstr[3] = {128, uint64_t(w) * 128, uint64_t(h) * w * 128};
+  const uint32_t cbox[4] = {16, HEAD_TW, 2, 1};
+  const uint64_t pdims[4] = {64, uint64_t(wp > 0 ? wp : 1), uint64_t(hp > 0 ? hp : 1), uint64_t(p.N)};
+  const uint64_t pstr[3] = {128, uint64_t(wp > 0 ? wp : 1) * 128, uint64_t(hp > 0 ? hp : 1) * (wp > 0 ? wp : 1) * 128};
+  const uint32_t pbox[4] = {16, HEAD_TW / 2, 1, 1};
+  for (int pl = 0; pl < 2; ++pl) {
+    const int src = pl < planes ? pl : 0;
+    if (!p.c2.p[src]) {
+      set_error("head_eval: null output plane %d", src);
+      return 1;
+    }
+    if (encode_tmap_tiled(&maps[pl], p.c2.p[src], 4, cdims, cstr, cbox, 2, 32)) return 1;
+    if (has_pool) {
+      if (encode_tmap_tiled(&maps[2 + pl], p.p2.p[src], 4, pdims, pstr, pbox, 2, 32)) return 1;
+    } else {
+      maps[2 + pl] = maps[pl];
+    }
   }
   dim3 grid((w + HEAD_TW - 1) / HEAD_TW, (h + HEAD_TH - 1) / HEAD_TH, p.N);
   int rc;
-  if (p.fmt == kFmtBf16) rc = head_launch<kFmtBf16>(p, grid, st);
-  else if (p.fmt == kFmtF16x2) rc = head_launch<kFmtF16x2>(p, grid, st);
-  else rc = head_launch<kFmtBf16x2>(p, grid, st);
+  if (p.fmt == kFmtBf16) rc = head_launch<kFmtBf16>(p, maps, has_pool, grid, st);
+  else if (p.fmt == kFmtF16x2) rc = head_launch<kFmtF16x2>(p, maps, has_pool, grid, st);
+  else rc = head_launch<kFmtBf16x2>(p, maps, has_pool, grid, st);
   if (rc) return rc;
   NSM_CHECK_LAUNCH("head_eval");
   return 0;

@@ -30,20 +30,18 @@ struct HeadParams {
   int N, Hin, Win;  // raw input size; the stage works on H = Hin - Hin%2, W = Win - Win%2, h = H/2, w = W/2
   const float* mean;  // [4] or nullptr: fused (x - mean) / (std + 1e-8)
   const float* std;
-  const float* w0;  // [16][16][3][3] fp32 (values pre-rounded to bf16 in bf16 mode)
-  const float* b0;  // [16]
-  const float* s0;  // [16] BN affine
-  const float* t0;
-  const float* w1;  // [64][16]
-  const float* b1;  // [64]
-  const float* s1;
-  const float* t1;
+  const void* img;  // kHeadImageBytes: conv2's weights / bias / BN affine as built by head_pack_image()
   int fmt;          // storage format: 0 bf16 (autocast rounding points), 1 fp16 hi+lo, 2 bf16 hi+lo
   Planes c2;        // [N,h,w,64]
   Planes p2;        // [N,h/2,w/2,64]
   Planes x16;       // optional tap of the un-shuffled input [N,h,w,16] (tests) or {nullptr}
 };
 int head_eval(const HeadParams& p, cudaStream_t st);
+// The head's operand image: both convolutions' weights split into 16-bit planes in the kernel's swizzled shared-memory
+// layout, followed by the per-channel vectors.  w0 [16][16][3][3], w1 [64][16] fp32 (pre-rounded to bf16 in bf16 mode).
+constexpr int kHeadImageBytes = 2 * 9 * 16 * 32 + 2 * 64 * 32 + (3 * 16 + 3 * 64) * 4;
+int head_pack_image(const float* w0, const float* b0, const float* s0, const float* t0, const float* w1,
+                    const float* b1, const float* s1, const float* t1, int fmt, void* img, cudaStream_t st);
 
 // ---- tail: conv9 1x1 (64->16) + BN + LReLU + conv10 (16->4) + sigmoid + pixel_shuffle(2) ----------------------
 struct TailParams {
