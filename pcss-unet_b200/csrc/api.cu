@@ -35,6 +35,7 @@ struct PackedLayout {
   size_t v1[8][3];  // bias, scale, shift of the 1x1 stage  [cout]
   size_t w10, b10;
   size_t head_img;  // conv2's operand image for the head kernel (head_pack_image)
+  size_t tail_img;  // conv9 1x1 + conv10 operand image for the tail kernel (tail_pack_image)
   size_t total;
 };
 
@@ -64,6 +65,7 @@ static PackedLayout packed_layout(int mode) {
   L.w10 = take(4 * 16 * 4);
   L.b10 = take(4 * 4);
   L.head_img = take(kHeadImageBytes);
+  L.tail_img = take(kTailImageBytes);
   L.total = off;
   return L;
 }
@@ -238,6 +240,8 @@ int nsm_unet_pack(const float* const* T, int mode, void* blob, void* stream) {
   auto fv = [&](size_t off) { return reinterpret_cast<const float*>(base + off); };
   NSM_TRY(head_pack_image(fv(L.w3[0][0]), fv(L.v3[0][0]), fv(L.v3[0][1]), fv(L.v3[0][2]), fv(L.w1[0][0]), fv(L.v1[0][0]),
                           fv(L.v1[0][1]), fv(L.v1[0][2]), mode, base + L.head_img, st));
+  NSM_TRY(tail_pack_image(fv(L.w1[7][0]), fv(L.v1[7][0]), fv(L.v1[7][1]), fv(L.v1[7][2]), fv(L.w10), fv(L.b10), mode,
+                          base + L.tail_img, st));
   return 0;
 }
 
@@ -341,8 +345,7 @@ static int infer_impl(const void* blob, int mode, const float* x, int B, int H, 
   {
     TailParams tp;
     tp.a = buf("t9"); tp.N = B; tp.h = WL.lv[1].h; tp.w = WL.lv[1].w;
-    tp.w1 = fvec(PL.w1[7][0]); tp.b1 = fvec(PL.v1[7][0]); tp.s1 = fvec(PL.v1[7][1]); tp.t1 = fvec(PL.v1[7][2]);
-    tp.w10 = fvec(PL.w10); tp.b10 = fvec(PL.b10); tp.fmt = mode; tp.y = y; tp.y_u8 = y_u8;
+    tp.img = pb + PL.tail_img; tp.fmt = mode; tp.y = y; tp.y_u8 = y_u8;
     const double px = double(B) * tp.h * tp.w;
     ProfScope ps("tail(conv9.1x1+conv10)", px * 2.0 * (64 * 16 + 16 * 4), px * (64 * 2.0 * np + 16), st);
     NSM_TRY(tail_eval(tp, st));

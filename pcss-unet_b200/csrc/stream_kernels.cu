@@ -612,116 +612,229 @@ int head_eval(const HeadParams& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // tail stage
 // ------------------------------------------------------------------------------------------------
-struct TailSmem {
-  float w1[64 * 16];  // [ci][co]
-  float w10[16 * 4];  // [ci][co]
+// conv9's 1x1 (64 -> 16) and conv10 (16 -> 4, padded to 8 outputs) on mma.sync like the head.  A warp works on 32
+// consecutive pixels: their 64 channels are 4 KB contiguous per plane, copied with coalesced 16-byte cp.async into a
+// warp-private swizzled tile (pixel rows of 128 B, chunk ^ (pixel & 7)) and read back as A fragments with ldmatrix.  The
+// weight B fragments come from an image in per-lane register order built at pack time (tail_pack_image).
+struct TailImage {
+  uint4 w1f[2][4][32];   // [plane][k-step of 16 ci][lane] = {b0, b1 of n-tile 0, b0, b1 of n-tile 1}
+  uint2 w10f[2][32];     // [plane][lane] = {b0, b1} of the single (zero-padded) n-tile
   float b1[16], s1[16], t1[16], b10[4];
 };
+static_assert(sizeof(TailImage) == kTailImageBytes, "tail weight image size");
+constexpr int kTailWarps = 8;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 = zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int FMT>
-__global__ void __launch_bounds__(256) tail_eval_kernel(const __grid_constant__ TailParams p) {
-  __shared__ TailSmem s;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 64 * 16; i += 256) {
-    const int co = i & 15, ci = i >> 4;
-    s.w1[i] = p.w1[co * 64 + ci];
+__global__ void __launch_bounds__(32 * kTailWarps) tail_eval_kernel(const __grid_constant__ TailParams p) {
+  extern __shared__ uint8_t tail_smem_raw[];   // [warp][plane][32 px][128 B]
+  constexpr bool rb = FMT == kFmtBf16;
+  constexpr bool two = FMT != kFmtBf16;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3, lm = lane >> 3, lr = lane & 7;
+  const uint32_t raw_addr = smem_u32(tail_smem_raw);
+  const uint32_t tile0 = ((raw_addr + 127u) & ~127u) + wrp * 8192, tile1 = tile0 + 4096;
+  const TailImage* img = reinterpret_cast<const TailImage*>(p.img);
+
+  uint32_t wh[4][4], wl[4][4], w10h[2], w10l[2] = {0, 0};
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint4 a = __ldg(&img->w1f[0][ks][lane]);
+    wh[ks][0] = a.x; wh[ks][1] = a.y; wh[ks][2] = a.z; wh[ks][3] = a.w;
+    if (two) {
+      const uint4 b = __ldg(&img->w1f[1][ks][lane]);
+      wl[ks][0] = b.x; wl[ks][1] = b.y; wl[ks][2] = b.z; wl[ks][3] = b.w;
+    } else {
+      wl[ks][0] = wl[ks][1] = wl[ks][2] = wl[ks][3] = 0;
+    }
   }
-  if (tid < 64) {
-    const int co = tid & 3, ci = tid >> 2;
-    s.w10[tid] = p.w10[co * 16 + ci];
+  {
+    const uint2 a = __ldg(&img->w10f[0][lane]);
+    w10h[0] = a.x; w10h[1] = a.y;
+    if (two) {
+      const uint2 b = __ldg(&img->w10f[1][lane]);
+      w10l[0] = b.x; w10l[1] = b.y;
+    }
   }
-  if (tid < 16) { s.b1[tid] = p.b1[tid]; s.s1[tid] = p.s1[tid]; s.t1[tid] = p.t1[tid]; }
-  if (tid < 4) s.b10[tid] = p.b10[tid];
-  __syncthreads();
-  const bool rb = FMT == kFmtBf16;
+  float pb[2][2], ps[2][2], pt[2][2], pb10[2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int co = nt * 8 + 2 * t + k;
+      pb[nt][k] = __ldg(&img->b1[co]); ps[nt][k] = __ldg(&img->s1[co]); pt[nt][k] = __ldg(&img->t1[co]);
+    }
+  pb10[0] = t < 2 ? __ldg(&img->b10[2 * t]) : 0.f;
+  pb10[1] = t < 2 ? __ldg(&img->b10[2 * t + 1]) : 0.f;
+
   const long long npix = (long long)p.N * p.h * p.w;
+  const long long units = (npix + 31) >> 5;
   const int W = 2 * p.w, H = 2 * p.h;
-  for (long long pix = blockIdx.x * 256LL + tid; pix < npix; pix += (long long)gridDim.x * 256) {
-    float a[16];
+  const uint8_t* a0 = reinterpret_cast<const uint8_t*>(p.a.p[0]);
+  const uint8_t* a1 = reinterpret_cast<const uint8_t*>(p.a.p[1]);
+  for (long long unit = (long long)blockIdx.x * kTailWarps + wrp; unit < units; unit += (long long)gridDim.x * kTailWarps) {
+    const long long pix0 = unit << 5;
+    // 32 px x 128 B per plane: instruction i moves pixels 4i .. 4i+3 (lane -> pixel 4i + lane/8, chunk lane%8)
 #pragma unroll
-    for (int co = 0; co < 16; ++co) a[co] = 0.f;
-    const uint8_t* a0 = reinterpret_cast<const uint8_t*>(p.a.p[0]) + pix * 128;
-    const uint8_t* a1 = FMT != kFmtBf16 ? reinterpret_cast<const uint8_t*>(p.a.p[1]) + pix * 128 : nullptr;
+    for (int i = 0; i < 8; ++i) {
+      const int px = 4 * i + (lane >> 3), ch = lane & 7;
+      const bool ok = pix0 + px < npix;
+      const size_t goff = ok ? (size_t)(pix0 + px) * 128 + ch * 16 : 0;
+      const uint32_t soff = px * 128 + ((ch ^ (px & 7)) << 4);
+      cp_async16(tile0 + soff, a0 + goff, ok);
+      if (two) cp_async16(tile1 + soff, a1 + goff, ok);
+    }
+    cp_async_wait_all();
+    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint4 hv = ldg16(a0 + 16 * j);
-      uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-      float xin[8];
+    for (int mt = 0; mt < 2; ++mt) {
+      float acc[2][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        xin[2 * e] = hi_lo_to_f32(hw[e], FMT);
-        xin[2 * e + 1] = hi_hi_to_f32(hw[e], FMT);
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+      const int px = mt * 16 + lr + 8 * (lm & 1);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t soff = px * 128 + (((2 * ks + (lm >> 1)) ^ (px & 7)) << 4);
+        uint32_t ah[4], al[4] = {0, 0, 0, 0};
+        ldmatrix_x4(ah, tile0 + soff);
+        if (two) ldmatrix_x4(al, tile1 + soff);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+          head_mma<FMT>(acc[nt], ah, al, wh[ks][2 * nt], wh[ks][2 * nt + 1], wl[ks][2 * nt], wl[ks][2 * nt + 1]);
       }
-      if (a1) {
-        const uint4 lv = ldg16(a1 + 16 * j);
-        uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+      // bias + BN + LeakyReLU -> A fragments of conv10
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          xin[2 * e] += lo_lo_to_f32(lw[e], FMT);
-          xin[2 * e + 1] += lo_hi_to_f32(lw[e], FMT);
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = acc[nt][i] + pb[nt][i & 1];
+          if (rb) v = rbf(v);
+          v = fmaf(v, ps[nt][i & 1], pt[nt][i & 1]);
+          if (rb) v = rbf(v);
+          v = lrelu02(v);
+          if (rb) v = rbf(v);
+          acc[nt][i] = v;
+        }
+      uint32_t bh[4], bl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float e0 = acc[k >> 1][(k & 1) * 2], e1 = acc[k >> 1][(k & 1) * 2 + 1];
+        bh[k] = pack_hi(e0, e1, FMT);
+        bl[k] = two ? pack_lo_resid(e0, e1, bh[k], FMT) : 0u;
+      }
+      float c10[4] = {0.f, 0.f, 0.f, 0.f};
+      head_mma<FMT>(c10, bh, bl, w10h[0], w10h[1], w10l[0], w10l[1]);
+      if (t < 2) {   // columns 2t, 2t+1 = channels (dy = t, dx = 0 / 1) of pixel_shuffle(2)
+#pragma unroll
+        for (int ih = 0; ih < 2; ++ih) {
+          const long long pix = pix0 + mt * 16 + g + 8 * ih;
+          if (pix < npix) {
+            float r[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              float v = c10[2 * ih + k] + pb10[k];
+              if (rb) v = rbf(v);
+              v = 1.f / (1.f + expf(-v));
+              r[k] = rb ? rbf(v) : v;
+            }
+            const unsigned pix32 = (unsigned)pix;           // npix < 2^31 (checked on the host): 32-bit div/mod
+            const unsigned q = pix32 / (unsigned)p.w;
+            const int x = int(pix32 - q * (unsigned)p.w);
+            const unsigned n = q / (unsigned)p.h;
+            const int y = int(q - n * (unsigned)p.h);
+            const size_t oo = ((size_t)n * H + 2 * y + t) * W + 2 * x;
+            if (p.y) *reinterpret_cast<float2*>(p.y + oo) = make_float2(r[0], r[1]);
+            if (p.y_u8)   // (out * 255).astype(uint8): truncation toward zero of a value in [0, 255]
+              *reinterpret_cast<uchar2*>(p.y_u8 + oo) =
+                  make_uchar2((unsigned char)(r[0] * 255.f), (unsigned char)(r[1] * 255.f));
+          }
         }
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float4* wv = reinterpret_cast<const float4*>(&s.w1[(8 * j + e) * 16]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 ww = wv[q];
-          a[4 * q] = fmaf(xin[e], ww.x, a[4 * q]); a[4 * q + 1] = fmaf(xin[e], ww.y, a[4 * q + 1]);
-          a[4 * q + 2] = fmaf(xin[e], ww.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(xin[e], ww.w, a[4 * q + 3]);
-        }
-      }
     }
-    float c10[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ci = 0; ci < 16; ++ci) {
-      float v = a[ci] + s.b1[ci];
-      if (rb) v = rbf(v);
-      v = fmaf(v, s.s1[ci], s.t1[ci]);
-      if (rb) v = rbf(v);
-      v = lrelu02(v);
-      if (rb) v = rbf(v);
-      const float4 ww = *reinterpret_cast<const float4*>(&s.w10[ci * 4]);
-      c10[0] = fmaf(v, ww.x, c10[0]); c10[1] = fmaf(v, ww.y, c10[1]);
-      c10[2] = fmaf(v, ww.z, c10[2]); c10[3] = fmaf(v, ww.w, c10[3]);
-    }
-    float r[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float v = c10[k] + s.b10[k];
-      if (rb) v = rbf(v);
-      v = 1.f / (1.f + expf(-v));
-      r[k] = rb ? rbf(v) : v;
-    }
-    // pixel_shuffle(2): channel k = dy*2 + dx -> (2y+dy, 2x+dx)
-    const unsigned pix32 = (unsigned)pix;           // npix < 2^31 (checked on the host): 32-bit div/mod
-    const unsigned t = pix32 / (unsigned)p.w;
-    const int x = int(pix32 - t * (unsigned)p.w);
-    const unsigned n = t / (unsigned)p.h;
-    const int y = int(t - n * (unsigned)p.h);
-    const size_t oo = ((size_t)n * H + 2 * y) * W + 2 * x;
-    if (p.y) {
-      *reinterpret_cast<float2*>(p.y + oo) = make_float2(r[0], r[1]);
-      *reinterpret_cast<float2*>(p.y + oo + W) = make_float2(r[2], r[3]);
-    }
-    if (p.y_u8) {   // (out * 255).astype(uint8): truncation toward zero of a value in [0, 255]
-      *reinterpret_cast<uchar2*>(p.y_u8 + oo) = make_uchar2((unsigned char)(r[0] * 255.f), (unsigned char)(r[1] * 255.f));
-      *reinterpret_cast<uchar2*>(p.y_u8 + oo + W) = make_uchar2((unsigned char)(r[2] * 255.f), (unsigned char)(r[3] * 255.f));
-    }
+    __syncwarp();   // all lanes are done with the tile before the next unit's copies overwrite it
   }
+}
+
+struct TailPackArgs {
+  const float *w1, *b1, *s1, *t1, *w10, *b10;
+  int fmt;
+  TailImage* img;
+};
+__global__ void tail_pack_kernel(const TailPackArgs a) {
+  const int lane = threadIdx.x;   // one warp
+  const int g = lane >> 2, t = lane & 3;
+  auto pair = [&](float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_hi(v0, v1, a.fmt);
+    lo = a.fmt == kFmtBf16 ? 0u : pack_lo_resid(v0, v1, hi, a.fmt);
+  };
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t h[4], l[4];
+    for (int nt = 0; nt < 2; ++nt)
+      for (int kh = 0; kh < 2; ++kh) {   // b0: k = 2t, 2t+1 ; b1: k + 8 ; n = nt*8 + g   (w1 is [16 co][64 ci])
+        const int co = nt * 8 + g, ci = ks * 16 + kh * 8 + 2 * t;
+        pair(a.w1[co * 64 + ci], a.w1[co * 64 + ci + 1], h[2 * nt + kh], l[2 * nt + kh]);
+      }
+    a.img->w1f[0][ks][lane] = make_uint4(h[0], h[1], h[2], h[3]);
+    a.img->w1f[1][ks][lane] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+  {
+    uint32_t h[2], l[2];
+    for (int kh = 0; kh < 2; ++kh) {   // w10 is [4 co][16 ci]; output columns 4..7 are padding
+      const int ci = kh * 8 + 2 * t;
+      const float v0 = g < 4 ? a.w10[g * 16 + ci] : 0.f, v1 = g < 4 ? a.w10[g * 16 + ci + 1] : 0.f;
+      pair(v0, v1, h[kh], l[kh]);
+    }
+    a.img->w10f[0][lane] = make_uint2(h[0], h[1]);
+    a.img->w10f[1][lane] = make_uint2(l[0], l[1]);
+  }
+  if (lane < 16) { a.img->b1[lane] = a.b1[lane]; a.img->s1[lane] = a.s1[lane]; a.img->t1[lane] = a.t1[lane]; }
+  if (lane < 4) a.img->b10[lane] = a.b10[lane];
+}
+int tail_pack_image(const float* w1, const float* b1, const float* s1, const float* t1, const float* w10,
+                    const float* b10, int fmt, void* img, cudaStream_t st) {
+  TailPackArgs a{w1, b1, s1, t1, w10, b10, fmt, reinterpret_cast<TailImage*>(img)};
+  tail_pack_kernel<<<1, 32, 0, st>>>(a);
+  NSM_CHECK_LAUNCH("tail_pack_image");
+  return 0;
+}
+
+template <int FMT>
+static int tail_launch(const TailParams& p, int grid, cudaStream_t st) {
+  constexpr int kSmem = kTailWarps * 8192 + 128;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tail_eval_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) {
+      set_error("tail_eval: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr = true;
+  }
+  tail_eval_kernel<FMT><<<grid, 32 * kTailWarps, kSmem, st>>>(p);
+  return 0;
 }
 
 int tail_eval(const TailParams& p, cudaStream_t st) {
   const long long npix = (long long)p.N * p.h * p.w;
-  if (npix >= (1LL << 31)) {
-    set_error("tail_eval: too many pixels");
+  if (npix >= (1LL << 31) || !p.img) {
+    set_error("tail_eval: too many pixels or missing weight image");
     return 1;
   }
-  {
-    if (p.fmt == kFmtBf16) tail_eval_kernel<kFmtBf16><<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
-    else if (p.fmt == kFmtF16x2) tail_eval_kernel<kFmtF16x2><<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
-    else tail_eval_kernel<kFmtBf16x2><<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(p);
-  }
+  const long long units = (npix + 31) / 32;
+  long long blocks = (units + kTailWarps - 1) / kTailWarps;
+  if (blocks > 148 * 3) blocks = 148 * 3;
+  int rc;
+  if (p.fmt == kFmtBf16) rc = tail_launch<kFmtBf16>(p, (int)blocks, st);
+  else if (p.fmt == kFmtF16x2) rc = tail_launch<kFmtF16x2>(p, (int)blocks, st);
+  else rc = tail_launch<kFmtBf16x2>(p, (int)blocks, st);
+  if (rc) return rc;
   NSM_CHECK_LAUNCH("tail_eval");
   return 0;
 }

@@ -47,17 +47,16 @@ int head_pack_image(const float* w0, const float* b0, const float* s0, const flo
 struct TailParams {
   Planes a;         // [N,h,w,64] activated output of conv9's 3x3 stage
   int N, h, w;
-  const float* w1;  // [16][64]
-  const float* b1;  // [16]
-  const float* s1;
-  const float* t1;
-  const float* w10;  // [4][16]
-  const float* b10;  // [4]
+  const void* img;  // kTailImageBytes: conv9's 1x1 / conv10 operand image built by tail_pack_image()
   int fmt;
   float* y;          // [N,1,2h,2w] fp32 (or nullptr)
   uint8_t* y_u8;     // optional [N,1,2h,2w] uint8 = (uint8)(y * 255), the quantisation of infer.py:79 (or nullptr)
 };
 int tail_eval(const TailParams& p, cudaStream_t st);
+// w1 [16][64], w10 [4][16] fp32 (pre-rounded to bf16 in bf16 mode) -> mma.sync B fragments in per-lane order + vectors
+constexpr int kTailImageBytes = 2 * 4 * 32 * 16 + 2 * 32 * 8 + (3 * 16 + 4) * 4;
+int tail_pack_image(const float* w1, const float* b1, const float* s1, const float* t1, const float* w10,
+                    const float* b10, int fmt, void* img, cudaStream_t st);
 
 // ---- nn.Upsample(x2, bilinear, align_corners) followed by F.interpolate(size=(hd, wd)) -----------------------
 int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes& dst, int hd, int wd, int fmt,
