@@ -244,6 +244,11 @@ __device__ __forceinline__ void sts8(uint32_t saddr, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void sts2(uint32_t saddr, unsigned short v) {
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 = zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void sts4(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
@@ -269,10 +274,11 @@ head_eval_kernel(const __grid_constant__ HeadParams p, const __grid_constant__ C
   const uint32_t w10 = smem_u32(&s.wt.w1[0][0]), w11 = smem_u32(&s.wt.w1[1][0]);
 
   // ---- weights: the ready-made operand image (split, swizzled at pack time) ----------------------------------------------
+  //      asynchronous copies: they fly while the input tile below is fetched and converted
   {
-    const uint4* src = reinterpret_cast<const uint4*>(p.img);
-    uint4* dst = reinterpret_cast<uint4*>(&s.wt);
-    for (int i = tid; i < kHeadImageBytes / 16; i += 256) dst[i] = __ldg(src + i);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.img);
+    const uint32_t dst = smem_u32(&s.wt);
+    for (int i = tid; i < kHeadImageBytes / 16; i += 256) cp_async16(dst + i * 16, src + i * 16, true);
   }
 
   // ---- input: one item = one halo pixel x one of the 4 input channels = a 2x2 full-resolution quad = 4 of the 16
@@ -330,6 +336,7 @@ head_eval_kernel(const __grid_constant__ HeadParams p, const __grid_constant__ C
       }
     }
   }
+  cp_async_wait_all();
   __syncthreads();
 
   const int lane = tid & 31, wrp = tid >> 5;
@@ -624,11 +631,6 @@ struct TailImage {
 static_assert(sizeof(TailImage) == kTailImageBytes, "tail weight image size");
 constexpr int kTailWarps = 8;
 
-__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;   // src-size 0 = zero fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int FMT>
 __global__ void __launch_bounds__(32 * kTailWarps) tail_eval_kernel(const __grid_constant__ TailParams p) {
@@ -954,10 +956,9 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
   if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
 }
 
-// 2x2 outputs per thread for the composite resize (hd >= hs, wd >= ws: adjacent outputs then start at most two source
-// indices apart, so a pair of outputs touches <= 5 consecutive source rows / columns).  Each source value is loaded and
-// unpacked once per thread and feeds up to four outputs; per output the FMA order is the same as in the one-pixel kernel
-// above (taps the output does not use enter with weight 0), so both produce identical bits.
+// Taps of a PAIR of adjacent outputs of the composite resize (hd >= hs, wd >= ws: adjacent outputs then start at most two
+// source indices apart, so the pair touches <= 5 consecutive source indices).  Taps an output does not use enter with
+// weight 0, so the per-output FMA order is the same as in the one-pixel kernel above and both produce identical bits.
 struct PairTaps {
   int lo;          // first source index of the union
   float w[2][5];   // weights of the two outputs on lo .. lo+4
@@ -978,63 +979,78 @@ __device__ __forceinline__ PairTaps pair_taps(int d0, int in_size, int out_size)
   return t;
 }
 
+// Strip-walking form of the composite resize: one thread owns an output column pair (8 channels) and walks down
+// kMatchStrip output rows, keeping the three source rows of the current vertical stencil horizontally interpolated in
+// registers; moving to the next output row shifts that window by 0, 1 or 2 source rows, so every source row is loaded and
+// unpacked once per strip instead of once per output row.  Same FMA order per output as the kernels above.
+constexpr int kMatchStrip = 8;
+
 template <int FMT>
-__global__ void __launch_bounds__(256) upsample_match2x2_kernel(const UpParams p, int cg_shift, int hpairs, int wpairs) {
+__device__ __forceinline__ void match_hrow(const UpParams& p, size_t nbase, int r, const PairTaps& tx, int cg,
+                                           float (&h)[2][8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) h[0][e] = h[1][e] = 0.f;
+  if (r > p.hs - 1) return;   // only reached with zero vertical weight
+  const size_t rbase = nbase + (size_t)r * p.ws;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    if (tx.w[0][c] == 0.f && tx.w[1][c] == 0.f) continue;
+    float v[8];
+    load8<FMT>(p, (rbase + tx.lo + c) * p.C + cg * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      h[0][e] = fmaf(tx.w[0][c], v[e], h[0][e]);
+      h[1][e] = fmaf(tx.w[1][c], v[e], h[1][e]);
+    }
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) upsample_match_strip_kernel(const UpParams p, int cg_shift, int strips,
+                                                                   int wpairs) {
   const int cgs = 1 << cg_shift;
   const int j = blockIdx.y * 256 + threadIdx.x;
   const bool active = j < wpairs * cgs;
   const int cg = j & (cgs - 1), xp = active ? (j >> cg_shift) : 0;
-  const int n = blockIdx.x / hpairs, yp = blockIdx.x - n * hpairs;
-  const bool rb = FMT == kFmtBf16;
-  __shared__ PairTaps s_ty, s_tx[257];
+  const int n = blockIdx.x / strips, y_first = (blockIdx.x - n * strips) * kMatchStrip;
+  const int y_end = min(y_first + kMatchStrip, p.hd);
+  __shared__ Tap3 s_ty[kMatchStrip];
+  __shared__ PairTaps s_tx[257];
   const int xp_first = (blockIdx.y * 256) >> cg_shift;
   {
     const int count = ((blockIdx.y * 256 + 255) >> cg_shift) - xp_first + 1;
-    if (threadIdx.x == 0) s_ty = pair_taps(2 * yp, p.hs, p.hd);
+    if ((int)threadIdx.x < y_end - y_first) s_ty[threadIdx.x] = composite_taps(y_first + threadIdx.x, p.hs, p.hd);
     for (int i = threadIdx.x; i < count; i += 256)
       if (xp_first + i < wpairs) s_tx[i] = pair_taps(2 * (xp_first + i), p.ws, p.wd);
     __syncthreads();
   }
   if (!active) return;   // (only after the barrier; inactive threads must not index the tap tables)
-  const PairTaps ty = s_ty, tx = s_tx[xp - xp_first];
+  const PairTaps tx = s_tx[xp - xp_first];
   const size_t nbase = (size_t)n * p.hs * p.ws;
-  float acc[2][2][8];
+  float h0[2][8], h1[2][8], h2[2][8];   // source rows base, base+1, base+2, interpolated to the two output columns
+  int base = s_ty[0].rmin;
+  match_hrow<FMT>(p, nbase, base, tx, cg, h0);
+  match_hrow<FMT>(p, nbase, base + 1, tx, cg, h1);
+  match_hrow<FMT>(p, nbase, base + 2, tx, cg, h2);
+  for (int y = y_first; y < y_end; ++y) {
+    const Tap3 ty = s_ty[y - y_first];
+    const int d = ty.rmin - base;   // block-uniform, 0..2 for hd >= hs
+    if (d == 1) {
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
+        for (int e = 0; e < 8; ++e) { h0[b][e] = h1[b][e]; h1[b][e] = h2[b][e]; }
+      match_hrow<FMT>(p, nbase, base + 3, tx, cg, h2);
+      base += 1;
+    } else if (d >= 2) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[a][b][e] = 0.f;
+      for (int b = 0; b < 2; ++b)
 #pragma unroll
-  for (int r = 0; r < 5; ++r) {
-    if (ty.w[0][r] == 0.f && ty.w[1][r] == 0.f) continue;   // block-uniform
-    const size_t rbase = nbase + (size_t)(ty.lo + r) * p.ws;
-    float h0[8], h1[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) h0[e] = h1[e] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-      if (tx.w[0][c] == 0.f && tx.w[1][c] == 0.f) continue;
-      float v[8];
-      load8<FMT>(p, (rbase + tx.lo + c) * p.C + cg * 8, v);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        h0[e] = fmaf(tx.w[0][c], v[e], h0[e]);
-        h1[e] = fmaf(tx.w[1][c], v[e], h1[e]);
-      }
+        for (int e = 0; e < 8; ++e) h0[b][e] = h2[b][e];
+      match_hrow<FMT>(p, nbase, base + 3, tx, cg, h1);
+      match_hrow<FMT>(p, nbase, base + 4, tx, cg, h2);
+      base += 2;
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[0][0][e] = fmaf(ty.w[0][r], h0[e], acc[0][0][e]);
-      acc[0][1][e] = fmaf(ty.w[0][r], h1[e], acc[0][1][e]);
-      acc[1][0][e] = fmaf(ty.w[1][r], h0[e], acc[1][0][e]);
-      acc[1][1][e] = fmaf(ty.w[1][r], h1[e], acc[1][1][e]);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    const int y = 2 * yp + a;
-    if (y >= p.hd) continue;
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       const int x = 2 * xp + b;
@@ -1043,30 +1059,21 @@ __global__ void __launch_bounds__(256) upsample_match2x2_kernel(const UpParams p
       uint32_t hw[4], lw[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float v0 = acc[a][b][2 * e], v1 = acc[a][b][2 * e + 1];
-        if (rb) { v0 = rbf(v0); v1 = rbf(v1); }
-        hw[e] = pack_hi(v0, v1, FMT);
-        lw[e] = pack_lo_resid(v0, v1, hw[e], FMT);
+        float v[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float a = fmaf(ty.w[0], h0[b][2 * e + k], 0.f);
+          a = fmaf(ty.w[1], h1[b][2 * e + k], a);
+          a = fmaf(ty.w[2], h2[b][2 * e + k], a);
+          v[k] = FMT == kFmtBf16 ? rbf(a) : a;
+        }
+        hw[e] = pack_hi(v[0], v[1], FMT);
+        lw[e] = pack_lo_resid(v[0], v[1], hw[e], FMT);
       }
       stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
       if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
     }
   }
-}
-
-// Fast path of the plain x2 up-sample (destination exactly 2hs x 2ws): one thread produces a 2x2 output block of 8
-// channels from the 3x3 source neighbourhood (rows/cols {b-1, b, b+1} clamped).  With align_corners the even output row
-// 2b interpolates source rows (b-1, b) and the odd row 2b+1 rows (b, b+1) -- see make_lerp: src = dst*(hs-1)/(2hs-1) --
-// so all register indices are static; horizontal interpolation is done once per source row (separable).
-__device__ __forceinline__ void up2x_weights(int b, int in_size, float& we0, float& we1, float& wo0, float& wo1) {
-  const int out_size = 2 * in_size;
-  const float scale = out_size > 1 ? float(in_size - 1) / float(out_size - 1) : 0.f;
-  const float se = scale * float(2 * b), so = scale * float(2 * b + 1);
-  // even: rows (b-1, b); ATen's (i0, lambda) may be (b, 0) when se rounds to b: identical value with weights (0, 1)
-  we1 = b == 0 ? 1.f : fminf(fmaxf(se - float(b - 1), 0.f), 1.f);
-  we0 = 1.f - we1;
-  wo1 = b >= in_size - 1 ? 0.f : fminf(fmaxf(so - float(b), 0.f), 1.f);
-  wo0 = 1.f - wo1;
 }
 
 // One thread walks down a strip of kUpStrip source rows at source column xb: every source row is loaded (3 columns),
@@ -1157,11 +1164,11 @@ int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes
     else if (fmt == kFmtF16x2) upsample2x_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, strips);
     else upsample2x_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, strips);
   } else if (hd >= hs && wd >= ws) {
-    const int hpairs = (hd + 1) / 2, wpairs = (wd + 1) / 2;
-    dim3 grid((unsigned)(N * hpairs), (unsigned)((wpairs * cgs + 255) / 256));
-    if (fmt == kFmtBf16) upsample_match2x2_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift, hpairs, wpairs);
-    else if (fmt == kFmtF16x2) upsample_match2x2_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, hpairs, wpairs);
-    else upsample_match2x2_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, hpairs, wpairs);
+    const int strips = (hd + kMatchStrip - 1) / kMatchStrip, wpairs = (wd + 1) / 2;
+    dim3 grid((unsigned)(N * strips), (unsigned)((wpairs * cgs + 255) / 256));
+    if (fmt == kFmtBf16) upsample_match_strip_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
+    else if (fmt == kFmtF16x2) upsample_match_strip_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
+    else upsample_match_strip_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
   } else {
     dim3 grid((unsigned)(N * hd), (unsigned)((wd * cgs + 255) / 256));
     {
