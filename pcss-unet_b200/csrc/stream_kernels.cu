@@ -1076,6 +1076,21 @@ __global__ void __launch_bounds__(256) upsample_match_strip_kernel(const UpParam
   }
 }
 
+// Fast path of the plain x2 up-sample (destination exactly 2hs x 2ws): one thread produces a 2x2 output block of 8
+// channels from the 3x3 source neighbourhood (rows/cols {b-1, b, b+1} clamped).  With align_corners the even output row
+// 2b interpolates source rows (b-1, b) and the odd row 2b+1 rows (b, b+1) -- see make_lerp: src = dst*(hs-1)/(2hs-1) --
+// so all register indices are static; horizontal interpolation is done once per source row (separable).
+__device__ __forceinline__ void up2x_weights(int b, int in_size, float& we0, float& we1, float& wo0, float& wo1) {
+  const int out_size = 2 * in_size;
+  const float scale = out_size > 1 ? float(in_size - 1) / float(out_size - 1) : 0.f;
+  const float se = scale * float(2 * b), so = scale * float(2 * b + 1);
+  // even: rows (b-1, b); ATen's (i0, lambda) may be (b, 0) when se rounds to b: identical value with weights (0, 1)
+  we1 = b == 0 ? 1.f : fminf(fmaxf(se - float(b - 1), 0.f), 1.f);
+  we0 = 1.f - we1;
+  wo1 = b >= in_size - 1 ? 0.f : fminf(fmaxf(so - float(b), 0.f), 1.f);
+  wo0 = 1.f - wo1;
+}
+
 // One thread walks down a strip of kUpStrip source rows at source column xb: every source row is loaded (3 columns),
 // unpacked and interpolated horizontally ONCE and then feeds the two output rows above and the two below it, so a 2x2
 // output block costs 3 loads instead of 9.
