@@ -8,8 +8,9 @@ Workload at N=1 (BASELINE.json configs[1], the configuration the metric is quote
 (frames shard with no collective: weak scaling) and `value` is the sum over ranks / max-over-ranks time.
 
   value : K steps timed on the device with CUDA events, inputs resident in HBM, L2 flushed before every step
-  e2e   : the same step through the reference-facing call with HOST buffers (Unet.infer_host -> nsm_unet_infer_host:
-          pinned H2D copy + forward + D2H copy inside the timed region)
+  e2e   : the same step through the reference-facing calls with HOST buffers: the frame pipeline (Unet.open_pipe ->
+          nsm_unet_pipe_submit: pinned H2D copy + forward + D2H copy of every frame inside the timed region, copies of
+          neighbouring frames overlapping the kernels) and, as e2e.single_call, one synchronous nsm_unet_infer_host per frame
   roofline : the tcgen05 implicit-GEMM kernel, timed live with CUDA events on its launch stream inside the step
   cpu_baseline : the CPU oracle port of the reference (torch CPU ops, all host cores) on a bounded sample
 `--impl reference` times that CPU port alone (the reference is pure Python on PyTorch; its tree does not travel to the
@@ -236,17 +237,37 @@ def run_b200(args):
         barrier()
         launches = nsm.launch_count() - launches0
         dev_ms = sum(s.elapsed_time(e) for s, e in evs)
-        # ---- end-to-end timing through the host-buffer entry point -------------------------------------------
+        # ---- end-to-end timing through the host-buffer entry points --------------------------------------------
+        # (a) one synchronous call per frame: H2D + forward + D2H + stream sync inside nsm_unet_infer_host
         for _ in range(2):
             net.infer_host(x_host, y_host)
         barrier()
-        t_e2e = 0.0
+        t_single = 0.0
         for _ in range(args.steps):
             flush.zero_()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            net.infer_host(x_host, y_host)          # H2D + forward + D2H + stream sync inside the C-ABI call
-            t_e2e += time.perf_counter() - t0
+            net.infer_host(x_host, y_host)
+            t_single += time.perf_counter() - t0
+        # (b) the frame pipeline (nsm_unet_pipe_*): every frame is still copied in from pinned memory and its result
+        #     copied back inside the timed region, but the copies of frames k+1 / k-1 overlap the kernels of frame k.
+        #     No L2 flush between frames: one frame's intermediates (~1.5 GB) already exceed the 126 MB L2.
+        pipe = net.open_pipe(B, H, W)
+        xs_host = [x_host] + [torch.randn(B, 4, H, W, generator=torch.Generator().manual_seed(7 + k)).pin_memory()
+                              for k in range(2)]
+        ys_host = [torch.empty_like(y_host).pin_memory() for _ in range(3)]
+        for k in range(3):
+            pipe.submit(xs_host[k], ys_host[k])
+        pipe.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pipe.submit(xs_host[k % 3], ys_host[k % 3])
+        pipe.sync()
+        t_e2e = time.perf_counter() - t0
+        if not torch.equal(ys_host[0], y_host):
+            raise RuntimeError("frame pipeline result differs from the synchronous host call")
+        pipe.close()
         barrier()
         clocks = sampler.stop()
         # ---- per-kernel timing (CUDA events on the launch stream, same step) ---------------------------------
@@ -258,10 +279,10 @@ def run_b200(args):
         rows = nsm.profile_read()
         nsm.profile_enable(False)
 
-    t = torch.tensor([dev_ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, t_e2e * 1e3, t_single * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms, single_ms = t.tolist()
     # second headline of BASELINE.json ("train samples/s @1/2/4/8 B200"): a short training measurement attached to the
     # same line (all ranks take part: data-parallel step with NCCL gradient all-reduce)
     train = None
@@ -341,7 +362,13 @@ def run_b200(args):
                        "sharding": "frames per rank, no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": e2e_ms / args.steps,
+                    "path": "Unet.open_pipe -> nsm_unet_pipe_submit per frame (pinned host in/out, copies of "
+                            "neighbouring frames overlap the kernels), nsm_unet_pipe_sync at the end",
+                    "single_call": {"value": world * pix * args.steps / (single_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                                    "ms_per_step": single_ms / args.steps,
+                                    "path": "Unet.infer_host -> nsm_unet_infer_host (H2D + forward + D2H + sync "
+                                            "per call, L2 flushed between calls)"}},
             "gpu_launches": launches,
             "roofline": roofline,
             "train": train}

@@ -67,6 +67,18 @@ int nsm_unet_infer_u8(const void* blob, int mode, const float* x, int B, int H, 
                       const float* std, uint8_t* y_u8, void* workspace, size_t workspace_bytes, void* stream);
 int nsm_unet_infer_host_u8(const void* blob, int mode, const float* x_host, int B, int H, int W, const float* mean,
                            const float* std, uint8_t* y_host, void* workspace, size_t workspace_bytes, void* stream);
+/* Frame pipeline for sequences (infer.py:46-80 / inference.py:256-300 process one frame after another): two device
+ * staging slots and three internal streams, so that the H2D copy of frame k+1 and the D2H copy of result k-1 overlap the
+ * kernels of frame k.  workspace: caller-owned device memory of nsm_unet_pipe_workspace_bytes().  mean/std as above (they
+ * must outlive the pipe).  submit() takes PINNED host buffers, exactly one of y_host (fp32) / y_host_u8, and returns once
+ * the frame is queued; when submit() of frame k returns, result k-2 is complete; sync() completes all of them.  The input
+ * must not be rewritten before the frame's own result is complete. */
+size_t nsm_unet_pipe_workspace_bytes(int B, int H, int W, int mode);
+int nsm_unet_pipe_create(const void* blob, int mode, int B, int H, int W, const float* mean, const float* std,
+                         void* workspace, size_t workspace_bytes, void** pipe);
+int nsm_unet_pipe_submit(void* pipe, const float* x_host, float* y_host, uint8_t* y_host_u8);
+int nsm_unet_pipe_sync(void* pipe);
+int nsm_unet_pipe_destroy(void* pipe);
 /* Copy a named intermediate of the last nsm_unet_infer() on this workspace to NCHW fp32 (tests / debugging).
  * names: c2 p2 t3 c3 p3 t4 c4 p4 t5 c5 u6 t6 m6 u7 t7 m7 u8 t8 m8 u9 t9.  *C,*h,*w receive its shape. */
 int nsm_unet_tap(const void* workspace, int B, int H, int W, int mode, const char* name, float* out, int* C,

@@ -175,6 +175,21 @@ def _infer_host_u8(self, x_host, y_host=None):
 Unet.infer_host_u8 = _infer_host_u8
 
 
+def _open_pipe(self, B, H, W):
+    """Frame pipeline for sequences (the loop of infer.py / inference.py): `pipe.submit(x_pinned, y_pinned)` per frame,
+    `pipe.sync()` at the end.  Host<->device copies of neighbouring frames overlap the kernels (nsm_unet_pipe_*).  The
+    parameters are packed now: re-open the pipe after changing them."""
+    dev = self.conv10.weight.device
+    nsm.require_device(self.conv10.weight)
+    mode = self._mode()
+    mean, std = self.input_stats if self.input_stats is not None else (None, None)
+    with torch.no_grad():
+        return nsm.FramePipe(self._packed_blob(mode), mode, B, H, W, dev, mean, std)
+
+
+Unet.open_pipe = _open_pipe
+
+
 def makefilepath(folder_path):
     """Kept for interface parity with the reference helper (Unetmodel.py:152-154)."""
     os.makedirs(folder_path, exist_ok=True)

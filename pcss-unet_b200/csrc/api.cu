@@ -422,6 +422,153 @@ int nsm_unet_infer_host_u8(const void* blob, int mode, const float* x_host, int 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- frame pipeline
+// infer.py / inference.py feed one frame after another.  The pipe keeps two device staging slots for inputs and results
+// and three streams: the H2D copy of frame k+1 and the D2H copy of result k-1 overlap the kernels of frame k.
+namespace {
+struct FramePipe {
+  const void* blob;
+  int mode, B, H, W;
+  const float *mean, *std;
+  uint8_t* ws;
+  size_t ws_bytes;       // the part nsm_unet_infer uses
+  float* xd[2];
+  uint8_t* yd[2];
+  size_t x_bytes, y_elems;
+  cudaStream_t s_in, s_comp, s_out;
+  cudaEvent_t in_done[2], comp_done[2], out_done[2];
+  unsigned long long submitted;
+};
+size_t pipe_slot_bytes(const WorkspaceLayout& WL, int B, int H, int W, size_t* xb, size_t* yb) {
+  const size_t x = align_up(size_t(B) * 4 * H * W * 4, 256), y = align_up(size_t(B) * WL.lv[0].h * WL.lv[0].w * 4, 256);
+  if (xb) *xb = x;
+  if (yb) *yb = y;
+  return x + y;
+}
+}  // namespace
+
+size_t nsm_unet_pipe_workspace_bytes(int B, int H, int W, int mode) {
+  if (B < 1 || H < 16 || W < 16 || mode < 0 || mode > 2) return 0;
+  const WorkspaceLayout WL = workspace_layout(B, H, W, mode);
+  return align_up(WL.total, 256) + 2 * pipe_slot_bytes(WL, B, H, W, nullptr, nullptr);
+}
+
+int nsm_unet_pipe_create(const void* blob, int mode, int B, int H, int W, const float* mean, const float* std,
+                         void* ws, size_t ws_bytes, void** pipe) {
+  if (!pipe || !blob || !ws) {
+    set_error("nsm_unet_pipe_create: null argument");
+    return 1;
+  }
+  const size_t need = nsm_unet_pipe_workspace_bytes(B, H, W, mode);
+  if (need == 0 || ws_bytes < need) {
+    set_error("nsm_unet_pipe_create: bad shape/mode or workspace %zu B < required %zu B", ws_bytes, need);
+    return 1;
+  }
+  const WorkspaceLayout WL = workspace_layout(B, H, W, mode);
+  FramePipe* fp = new FramePipe();
+  fp->blob = blob; fp->mode = mode; fp->B = B; fp->H = H; fp->W = W; fp->mean = mean; fp->std = std;
+  fp->ws = reinterpret_cast<uint8_t*>(ws);
+  fp->ws_bytes = WL.total;
+  size_t xb, yb;
+  const size_t slot = pipe_slot_bytes(WL, B, H, W, &xb, &yb);
+  uint8_t* base = fp->ws + align_up(WL.total, 256);
+  for (int k = 0; k < 2; ++k) {
+    fp->xd[k] = reinterpret_cast<float*>(base + k * slot);
+    fp->yd[k] = base + k * slot + xb;
+  }
+  fp->x_bytes = size_t(B) * 4 * H * W * 4;
+  fp->y_elems = size_t(B) * WL.lv[0].h * WL.lv[0].w;
+  fp->submitted = 0;
+  cudaError_t e = cudaSuccess;
+  cudaStream_t* streams[3] = {&fp->s_in, &fp->s_comp, &fp->s_out};
+  for (auto sp : streams)
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    e = cudaEventCreateWithFlags(&fp->in_done[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fp->comp_done[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fp->out_done[k], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    set_error("nsm_unet_pipe_create: %s", cudaGetErrorString(e));
+    delete fp;
+    return 1;
+  }
+  *pipe = fp;
+  return 0;
+}
+
+// x_host [B,4,H,W] fp32; exactly one of y_host (fp32) / y_host_u8 receives [B,1,H',W'].  Returns once the frame is
+// queued; when the call for frame k returns, the result of frame k-2 is complete in its host buffer.
+int nsm_unet_pipe_submit(void* pipe, const float* x_host, float* y_host, uint8_t* y_host_u8) {
+  FramePipe* fp = reinterpret_cast<FramePipe*>(pipe);
+  if (!fp || !x_host || (!y_host == !y_host_u8)) {
+    set_error("nsm_unet_pipe_submit: need a pipe, an input and exactly one output buffer");
+    return 1;
+  }
+  const int k = int(fp->submitted & 1);
+  cudaError_t e = cudaSuccess;
+  if (fp->submitted >= 2) {
+    e = cudaEventSynchronize(fp->out_done[k]);   // bounds the queue; frame k-2 is now on the host
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(fp->s_in, fp->comp_done[k], 0);   // its input slot is free
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(fp->xd[k], x_host, fp->x_bytes, cudaMemcpyHostToDevice, fp->s_in);
+  if (e == cudaSuccess) e = cudaEventRecord(fp->in_done[k], fp->s_in);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(fp->s_comp, fp->in_done[k], 0);
+  if (e != cudaSuccess) {
+    set_error("nsm_unet_pipe_submit: H2D stage: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  // (the result slot is free: out_done[k] of frame k-2 was synchronised above)
+  NSM_TRY(infer_impl(fp->blob, fp->mode, fp->xd[k], fp->B, fp->H, fp->W, fp->mean, fp->std,
+                     y_host ? reinterpret_cast<float*>(fp->yd[k]) : nullptr, y_host ? nullptr : fp->yd[k], fp->ws,
+                     fp->ws_bytes, fp->s_comp));
+  e = cudaEventRecord(fp->comp_done[k], fp->s_comp);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(fp->s_out, fp->comp_done[k], 0);
+  if (e == cudaSuccess)
+    e = y_host ? cudaMemcpyAsync(y_host, fp->yd[k], fp->y_elems * 4, cudaMemcpyDeviceToHost, fp->s_out)
+               : cudaMemcpyAsync(y_host_u8, fp->yd[k], fp->y_elems, cudaMemcpyDeviceToHost, fp->s_out);
+  if (e == cudaSuccess) e = cudaEventRecord(fp->out_done[k], fp->s_out);
+  if (e != cudaSuccess) {
+    set_error("nsm_unet_pipe_submit: D2H stage: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  ++fp->submitted;
+  return 0;
+}
+
+int nsm_unet_pipe_sync(void* pipe) {
+  FramePipe* fp = reinterpret_cast<FramePipe*>(pipe);
+  if (!fp) {
+    set_error("nsm_unet_pipe_sync: null pipe");
+    return 1;
+  }
+  cudaError_t e = cudaStreamSynchronize(fp->s_out);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(fp->s_comp);
+  if (e != cudaSuccess) {
+    set_error("nsm_unet_pipe_sync: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int nsm_unet_pipe_destroy(void* pipe) {
+  FramePipe* fp = reinterpret_cast<FramePipe*>(pipe);
+  if (!fp) return 0;
+  cudaStreamSynchronize(fp->s_in);
+  cudaStreamSynchronize(fp->s_comp);
+  cudaStreamSynchronize(fp->s_out);
+  for (int k = 0; k < 2; ++k) {
+    cudaEventDestroy(fp->in_done[k]);
+    cudaEventDestroy(fp->comp_done[k]);
+    cudaEventDestroy(fp->out_done[k]);
+  }
+  cudaStreamDestroy(fp->s_in);
+  cudaStreamDestroy(fp->s_comp);
+  cudaStreamDestroy(fp->s_out);
+  delete fp;
+  return 0;
+}
+
 int nsm_unet_tap(const void* ws, int B, int H, int W, int mode, const char* name, float* out, int* C, int* h,
                  int* w, void* stream) {
   const int t = tap_index(name);

@@ -73,6 +73,15 @@ def _declare(lib):
     lib.nsm_standardize.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p]
     lib.nsm_perturb.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_longlong, c_void_p,
                                 c_float, c_void_p]
+    lib.nsm_unet_pipe_workspace_bytes.restype = c_size_t
+    lib.nsm_unet_pipe_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.nsm_unet_pipe_create.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         POINTER(c_void_p)]
+    lib.nsm_unet_pipe_submit.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.nsm_unet_pipe_sync.argtypes = [c_void_p]
+    lib.nsm_unet_pipe_destroy.argtypes = [c_void_p]
+    for name in ("nsm_unet_pipe_create", "nsm_unet_pipe_submit", "nsm_unet_pipe_sync", "nsm_unet_pipe_destroy"):
+        getattr(lib, name).restype = c_int
     lib.nsm_profile_enable.argtypes = [c_int]
     lib.nsm_profile_read.argtypes = [c_char_p, c_size_t]
     vp, ll, fp = c_void_p, c_longlong, c_float
@@ -113,7 +122,8 @@ TRAIN_EXPORTS = [
 ]
 
 EXPORTS = TRAIN_EXPORTS + [
-    "nsm_launch_count", "nsm_unet_infer_u8", "nsm_unet_infer_host_u8",
+    "nsm_launch_count", "nsm_unet_infer_u8", "nsm_unet_infer_host_u8", "nsm_unet_pipe_workspace_bytes",
+    "nsm_unet_pipe_create", "nsm_unet_pipe_submit", "nsm_unet_pipe_sync", "nsm_unet_pipe_destroy",
     "nsm_last_error", "nsm_version", "nsm_check_device", "nsm_unet_packed_bytes", "nsm_unet_pack",
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
@@ -226,6 +236,52 @@ def unet_infer_host_u8(blob, mode, x_host, y_host, ws, mean=None, std=None):
     check(lib().nsm_unet_infer_host_u8(blob.data_ptr(), mode, x_host.data_ptr(), B, H, W, ptr(mean), ptr(std),
                                        y_host.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()),
           "nsm_unet_infer_host_u8")
+
+
+class FramePipe:
+    """Frame pipeline (nsm_unet_pipe_*): copies of neighbouring frames overlap the kernels of the current one.
+    submit(x_host, y_host) takes pinned [B,4,H,W] fp32 and a pinned [B,1,H',W'] fp32 or uint8 result buffer; when the
+    call for frame k returns, result k-2 is complete; sync() completes everything submitted."""
+
+    def __init__(self, blob, mode, B, H, W, device, mean=None, std=None):
+        n = lib().nsm_unet_pipe_workspace_bytes(B, H, W, mode)
+        if n == 0:
+            raise NsmError(f"input {B}x4x{H}x{W} not supported (need H, W >= 16)")
+        self.shape = (B, 4, H, W)
+        self.out_shape = (B, 1, H - H % 2, W - W % 2)
+        self._keep = (blob, mean, std, torch.empty(n, dtype=torch.uint8, device=device))
+        torch.cuda.current_stream(device).synchronize()   # the blob / statistics were produced on torch's stream
+        h = c_void_p()
+        check(lib().nsm_unet_pipe_create(blob.data_ptr(), mode, B, H, W, ptr(mean), ptr(std), self._keep[3].data_ptr(),
+                                         n, byref(h)), "nsm_unet_pipe_create")
+        self._h = h
+
+    def submit(self, x_host, y_host):
+        assert tuple(x_host.shape) == self.shape and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        assert tuple(y_host.shape) == self.out_shape and y_host.is_contiguous()
+        if not (x_host.is_pinned() and y_host.is_pinned()):
+            raise NsmError("FramePipe.submit needs pinned host tensors (the copies are asynchronous)")
+        if y_host.dtype == torch.float32:
+            rc = lib().nsm_unet_pipe_submit(self._h, x_host.data_ptr(), y_host.data_ptr(), None)
+        elif y_host.dtype == torch.uint8:
+            rc = lib().nsm_unet_pipe_submit(self._h, x_host.data_ptr(), None, y_host.data_ptr())
+        else:
+            raise NsmError("FramePipe.submit: result buffer must be float32 or uint8")
+        check(rc, "nsm_unet_pipe_submit")
+
+    def sync(self):
+        check(lib().nsm_unet_pipe_sync(self._h), "nsm_unet_pipe_sync")
+
+    def close(self):
+        if self._h is not None:
+            lib().nsm_unet_pipe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def unet_tap(ws, B, H, W, mode, name) -> torch.Tensor:

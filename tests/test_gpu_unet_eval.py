@@ -155,6 +155,37 @@ def test_fused_standardise_and_host_entry(nsm):
         assert y8.dtype == torch.uint8 and torch.equal(y8, (y.cpu() * 255).to(torch.uint8))
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_frame_pipeline_matches_single_calls(nsm, precision):
+    """nsm_unet_pipe_*: a sequence of frames through the double-buffered copy/compute pipeline returns, frame by frame,
+    exactly what the synchronous host entry point returns (fp32 and fused uint8 results, odd frame size)."""
+    P, _ = calibrated((2, 4, 64, 64))
+    net = make_net(P, precision)
+    B, H, W = 1, 75, 98
+    frames = [torch.randn(B, 4, H, W, generator=gen(10 + k)).pin_memory() for k in range(7)]
+    with torch.no_grad():
+        want = [net.infer_host(f).clone() for f in frames]
+        want8 = [net.infer_host_u8(f).clone() for f in frames]
+        pipe = net.open_pipe(B, H, W)
+        outs = [torch.empty(B, 1, H - 1, W, dtype=torch.float32).pin_memory() for _ in frames]
+        for f, o in zip(frames, outs):
+            pipe.submit(f, o)
+        pipe.sync()
+        for k, (o, w) in enumerate(zip(outs, want)):
+            assert torch.equal(o, w), f"frame {k}"
+        outs8 = [torch.empty(B, 1, H - 1, W, dtype=torch.uint8).pin_memory() for _ in frames]
+        for k, (f, o) in enumerate(zip(frames, outs8)):
+            pipe.submit(f, o)
+            if k >= 2:   # contract: when submit(k) returns, result k-2 is complete
+                assert torch.equal(outs8[k - 2], want8[k - 2]), f"frame {k - 2} after submit {k}"
+        pipe.sync()
+        for k, (o, w) in enumerate(zip(outs8, want8)):
+            assert torch.equal(o, w), f"u8 frame {k}"
+        with pytest.raises(nsm.NsmError):
+            pipe.submit(frames[0].clone(), outs[0])      # pageable input: refused
+        pipe.close()
+
+
 def test_rejects_bad_input(nsm):
     from Unetmodel import Unet
     net = Unet().cuda().eval()
