@@ -458,16 +458,39 @@ def measure_train(args, own_process_group=True):
     barrier()
     launches = nsm.launch_count() - launches0
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
-    t_e2e = 0.0
-    last = None
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        xd = x_host.to(dev, non_blocking=True)
-        td = t_host.to(dev, non_blocking=True)
-        last = step(xd, td).item()                       # D2H read of the step's loss
-        t_e2e += time.perf_counter() - t0
+    # end to end like a training loop with a pinned, prefetching loader (setdata_b200.DeviceFeeder's scheme): every step's
+    # batch is copied from pinned host memory inside the timed region -- on a side stream, one step ahead -- and every
+    # step's loss is read back to the host (asynchronously into pinned memory; all of them are on the host at the end).
+    copy_stream = torch.cuda.Stream(device=dev)
+    xds = [torch.empty_like(x) for _ in range(2)]
+    tds = [torch.empty_like(t) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    losses_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+
+    def prefetch(k):
+        slot = k & 1
+        with torch.cuda.stream(copy_stream):
+            if k >= 2:
+                copy_stream.wait_event(consumed[slot])
+            xds[slot].copy_(x_host, non_blocking=True)
+            tds[slot].copy_(t_host, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    prefetch(0)
+    for k in range(args.steps):
+        slot = k & 1
+        if k + 1 < args.steps:
+            prefetch(k + 1)
+        torch.cuda.current_stream().wait_event(ready[slot])
+        loss = step(xds[slot], tds[slot])
+        consumed[slot].record()
+        losses_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the step's loss
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    last = float(losses_host[-1])
     barrier()
     clocks = sampler.stop()
     nsm.profile_enable(True)

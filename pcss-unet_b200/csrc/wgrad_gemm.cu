@@ -6,11 +6,16 @@
 //   16 KB apart (descriptor LBO), consecutive 8-pixel groups are 1024 B apart (SBO).  The x box is shifted by the filter
 //   tap exactly like in the forward kernel, so zero padding and ragged tiles come from the TMA's out-of-bounds fill.
 //
+//   BN = 256 (wide layers, single plane): 64-pixel k-blocks (box {64 ch, 16, 4, 1}) keep four pipeline stages in shared
+//   memory and eight epilogue warps (two column halves) keep the chunk sums in registers; per MMA it moves 1.5 KB of
+//   operands per 2 M MACs against 2 KB at BN = 128, which is what bounds this kernel (shared-memory bandwidth).
+//
 //   Work item = (co tile, ci tile, tap, K split).  The pixel axis is long (up to 2 M), so it is split over CTAs (split-K
 //   partial results reduced by wgrad_reduce_kernel, deterministic) AND chunked inside a CTA: the tensor core's truncating
-//   fp32 accumulator is drained every kWChunk patches and the chunk results are added in fp32 registers with
+//   fp32 accumulator is drained every kWChunkPix pixels and the chunk results are added in fp32 registers with
 //   round-to-nearest (see conv_gemm.cu).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "nsm_common.cuh"
@@ -18,11 +23,11 @@
 
 namespace nsm {
 
-constexpr int kWChunk = 8;  // patches (k-blocks of 128 pixels) per TMEM accumulation chunk
+constexpr int kWChunkPix = 1024;  // pixels per TMEM accumulation chunk
 
 struct WgradKernelParams {
   int N, H, W, Cout, Cin, taps;
-  int tiles_x, tiles_y, patches;   // patches = N * tiles_y * tiles_x
+  int tiles_x, tiles_y, patches;   // patches = N * tiles_y * tiles_x   (k-blocks of KPIX pixels)
   int co_blocks, ci_blocks, splits, patches_per_split, total_items;
   uint32_t idesc;
   float* partial;                  // [splits][Cout][taps][Cin] fp32
@@ -30,7 +35,13 @@ struct WgradKernelParams {
 
 template <int BN, int NP>
 struct WgradCfg {
-  static constexpr int BOX_BYTES = 128 * 128;                 // 128 pixels x 64 channels x 2 B
+  static constexpr int KPIX = BN == 256 ? 64 : 128;           // pixels per k-block (patch = 16 x KPIX/16)
+  static constexpr int TILE_H = KPIX / kTileW;
+  static constexpr int KSTEPS = KPIX / 16;
+  static constexpr int CHUNK = kWChunkPix / KPIX;             // k-blocks per accumulation chunk
+  static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int BOX_BYTES = KPIX * 128;                // KPIX pixels x 64 channels x 2 B
   static constexpr int A_BYTES = 2 * BOX_BYTES;               // 128 output channels
   static constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
@@ -55,7 +66,7 @@ __device__ __forceinline__ void wgrad_decode(const WgradKernelParams& p, int ite
 }
 
 template <int BN, int NP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(WgradCfg<BN, NP>::THREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                   const __grid_constant__ WgradKernelParams p) {
@@ -82,7 +93,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], Cfg::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -108,7 +119,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const int t2 = pt / p.tiles_x;
           const int ty = t2 % p.tiles_y;
           const int n = t2 / p.tiles_y;
-          const int x0 = tx * kTileW, y0 = ty * kTileH;
+          const int x0 = tx * kTileW, y0 = ty * Cfg::TILE_H;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -142,8 +153,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         wgrad_decode(p, item, cob, cib, tap, split);
         const int pt0 = split * p.patches_per_split;
         const int pt1 = pt0 + p.patches_per_split < p.patches ? pt0 + p.patches_per_split : p.patches;
-        for (int c0 = pt0; c0 < pt1; c0 += kWChunk) {
-          const int c1 = c0 + kWChunk < pt1 ? c0 + kWChunk : pt1;
+        for (int c0 = pt0; c0 < pt1; c0 += Cfg::CHUNK) {
+          const int c1 = c0 + Cfg::CHUNK < pt1 ? c0 + Cfg::CHUNK : pt1;
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
@@ -154,7 +165,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint32_t b_hi = a_hi + NP * Cfg::A_BYTES;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {   // 128 pixels = 8 x UMMA_K(16); 16 rows of 128 B = 2048 B per step
+            for (int k = 0; k < Cfg::KSTEPS; ++k) {   // UMMA_K = 16 pixels = 16 rows of 128 B = 2048 B per step
               const uint32_t accum = ((pt - c0) | k) != 0 ? 1u : 0u;
               const uint64_t da_hi = make_desc_sw128(a_hi + k * 2048, Cfg::BOX_BYTES, 1024);
               const uint64_t db_hi = make_desc_sw128(b_hi + k * 2048, Cfg::BOX_BYTES, 1024);
@@ -179,25 +190,28 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5): chunk sums in registers, fp32 partial tile to global ============
+    // ===================== epilogue (warps 2..): chunk sums in registers, fp32 partial tile to global ==============
+    // warp -> TMEM lane quarter (warp & 3, a hardware restriction) and, with eight warps, a column half
+    constexpr int CW = BN / (Cfg::EPI_WARPS / 4);   // columns per epilogue warp
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;   // output channel inside the co tile
-    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + half * CW;
     uint32_t acc = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int cob, cib, tap, split;
       wgrad_decode(p, item, cob, cib, tap, split);
       const int pt0 = split * p.patches_per_split;
       const int pt1 = pt0 + p.patches_per_split < p.patches ? pt0 + p.patches_per_split : p.patches;
-      const int nchunks = (pt1 - pt0 + kWChunk - 1) / kWChunk;
-      float sum[BN];
+      const int nchunks = (pt1 - pt0 + Cfg::CHUNK - 1) / Cfg::CHUNK;
+      float sum[CW];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+      for (int j = 0; j < CW; ++j) sum[j] = 0.f;
       for (int ch = 0; ch < nchunks; ++ch) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < CW; c0 += 32) {
           uint32_t r0[32];
           tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + c0, r0);
           if (NP == 2) {
@@ -220,9 +234,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       const int co = cob * 128 + row;
       if (co < p.Cout) {
-        float* o = p.partial + (((size_t)split * p.Cout + co) * p.taps + tap) * p.Cin + cib * BN;
+        float* o = p.partial + (((size_t)split * p.Cout + co) * p.taps + tap) * p.Cin + cib * BN + half * CW;
 #pragma unroll
-        for (int j = 0; j < BN; j += 4)
+        for (int j = 0; j < CW; j += 4)
           *reinterpret_cast<float4*>(o + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
       }
     }
@@ -258,20 +272,28 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // host side
 // ------------------------------------------------------------------------------------------------
 struct WgradPlan {
-  int BN, splits, patches_per_split, tiles_x, tiles_y, patches, co_blocks, ci_blocks, items;
+  int BN, tile_h, chunk, splits, patches_per_split, tiles_x, tiles_y, patches, co_blocks, ci_blocks, items;
 };
 
 static WgradPlan wgrad_plan(const WgradShape& s) {
   WgradPlan pl;
-  pl.BN = (s.fmt == kFmtBf16 && s.Cin % 128 == 0) ? 128 : 64;
+  // measured (profiles/): the 256-wide tile wins for Cin = 1024 (+10 %), the 128-wide one for Cin = 512 (+7 %)
+  pl.BN = s.fmt != kFmtBf16 ? 64 : ((s.Cin % 256 == 0 && s.Cin >= 1024) ? 256 : (s.Cin % 128 == 0 ? 128 : 64));
+  {
+    static const char* force = getenv("NSM_WGRAD_BN");   // tuning / A-B runs
+    const int f = force ? atoi(force) : 0;
+    if (s.fmt == kFmtBf16 && (f == 64 || f == 128 || f == 256) && s.Cin % f == 0) pl.BN = f;
+  }
+  pl.tile_h = pl.BN == 256 ? 4 : kTileH;
+  pl.chunk = kWChunkPix / (kTileW * pl.tile_h);
   pl.tiles_x = (s.W + kTileW - 1) / kTileW;
-  pl.tiles_y = (s.H + kTileH - 1) / kTileH;
+  pl.tiles_y = (s.H + pl.tile_h - 1) / pl.tile_h;
   pl.patches = s.N * pl.tiles_x * pl.tiles_y;
   pl.co_blocks = (s.Cout + 127) / 128;
   pl.ci_blocks = s.Cin / pl.BN;
   const int base = pl.co_blocks * pl.ci_blocks * s.taps;
   int splits = (2 * 148 + base - 1) / base;            // aim at ~2 waves of work items
-  const int max_splits = (pl.patches + kWChunk - 1) / kWChunk;
+  const int max_splits = (pl.patches + pl.chunk - 1) / pl.chunk;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   pl.patches_per_split = (pl.patches + splits - 1) / splits;
@@ -298,7 +320,7 @@ static int wgrad_launch_t(const CUtensorMap* maps, const WgradKernelParams& kp, 
     }
     attr_set = true;
   }
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("wgrad_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
@@ -323,7 +345,7 @@ int wgrad_launch(const WgradShape& s, const Planes& dz, const Planes& x, void* w
   const int planes = fmt_planes(s.fmt);
   CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
-  const uint32_t box[4] = {64, uint32_t(kTileW), uint32_t(kTileH), 1};
+  const uint32_t box[4] = {64, uint32_t(kTileW), uint32_t(pl.tile_h), 1};
   const uint64_t adims[4] = {uint64_t(s.Cout), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
   const uint64_t astr[3] = {uint64_t(s.Cout) * 2, uint64_t(s.W) * s.Cout * 2, uint64_t(s.H) * s.W * s.Cout * 2};
   const uint64_t bdims[4] = {uint64_t(s.Cin), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
@@ -355,7 +377,10 @@ int wgrad_launch(const WgradShape& s, const Planes& dz, const Planes& x, void* w
   }
   const int grid = kp.total_items < sms ? kp.total_items : sms;
   int rc;
-  if (planes == 1) rc = pl.BN == 128 ? wgrad_launch_t<128, 1>(maps, kp, grid, st) : wgrad_launch_t<64, 1>(maps, kp, grid, st);
+  if (planes == 1)
+    rc = pl.BN == 256   ? wgrad_launch_t<256, 1>(maps, kp, grid, st)
+         : pl.BN == 128 ? wgrad_launch_t<128, 1>(maps, kp, grid, st)
+                        : wgrad_launch_t<64, 1>(maps, kp, grid, st);
   else rc = wgrad_launch_t<64, 2>(maps, kp, grid, st);
   if (rc) return rc;
   const long long total = (long long)Cout_real * Cin_real * s.taps;
