@@ -39,6 +39,13 @@ struct PackedLayout {
   size_t total;
 };
 
+// fp32 mode: the decoder's up-sampled tensors (u6..u9) and the weights of the 3x3 convolutions that consume them use the
+// fp16 + 8-bit cross format (nsm_common.cuh: two MMA slots per k-step instead of three).  NSM_NO_X8=1 keeps fp16 hi+lo.
+static int decoder3x3_fmt(int mode) {
+  static const bool off = getenv("NSM_NO_X8") != nullptr;
+  return (mode == NSM_MODE_FP32 && !off) ? kFmtF16X8 : mode;
+}
+
 static PackedLayout packed_layout(int mode) {
   const int np = fmt_planes(mode);
   PackedLayout L;
@@ -220,7 +227,8 @@ int nsm_unet_pack(const float* const* T, int mode, void* blob, void* stream) {
     if (b == 0) {
       NSM_TRY(copy_round(t[0], reinterpret_cast<float*>(base + L.w3[b][0]), cin * cin * 9, rb, st));
     } else {
-      NSM_TRY(pack_conv_weight(t[0], cin, cin, 3, 0, mode, base + L.w3[b][0], rb ? nullptr : base + L.w3[b][1], st));
+      NSM_TRY(pack_conv_weight(t[0], cin, cin, 3, 0, b >= 4 ? decoder3x3_fmt(mode) : mode, base + L.w3[b][0],
+                               rb ? nullptr : base + L.w3[b][1], st));
     }
     NSM_TRY(copy_round(t[1], reinterpret_cast<float*>(base + L.v3[b][0]), cin, rb, st));
     NSM_TRY(bn_fold_eval(t[2], t[3], t[4], t[5], cin, 1e-5f, reinterpret_cast<float*>(base + L.v3[b][1]),
@@ -295,7 +303,7 @@ static int infer_impl(const void* blob, int mode, const float* x, int B, int H, 
   auto double_conv = [&](int b, int level, const Planes& in, const char* tname, const char* oname,
                          const char* resname, const char* poolname) -> int {
     const Level& lv = WL.lv[level];
-    ConvShape s3 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cin, 9, mode};
+    ConvShape s3 = {B, lv.h, lv.w, kBlocks[b].cin, kBlocks[b].cin, 9, b >= 4 ? decoder3x3_fmt(mode) : mode};
     ConvEpilogue e3;
     e3.bias = fvec(PL.v3[b][0]); e3.scale = fvec(PL.v3[b][1]); e3.shift = fvec(PL.v3[b][2]);
     e3.lrelu = 1; e3.round_bf16 = np == 1; e3.out = buf(tname); e3.residual = none; e3.pool = none;
@@ -328,7 +336,7 @@ static int infer_impl(const void* blob, int mode, const float* x, int B, int H, 
                  (double(B) * WL.lv[slevel].h * WL.lv[slevel].w + double(B) * WL.lv[dlevel].h * WL.lv[dlevel].w) *
                      C * 2.0 * np, st);
     return upsample_match(buf(src), B, WL.lv[slevel].h, WL.lv[slevel].w, C, buf(dst), WL.lv[dlevel].h,
-                          WL.lv[dlevel].w, mode, st);
+                          WL.lv[dlevel].w, decoder3x3_fmt(mode), st);
   };
   NSM_TRY(double_conv(1, 2, buf("p2"), "t3", "c3", nullptr, "p3"));   // conv3 + pool3
   NSM_TRY(double_conv(2, 3, buf("p3"), "t4", "c4", nullptr, "p4"));   // conv4 + pool4
@@ -584,7 +592,9 @@ int nsm_unet_tap(const void* ws, int B, int H, int W, int mode, const char* name
   if (w) *w = lv.w;
   if (!out) return 0;
   const Planes p = ws_planes(WL, const_cast<void*>(ws), name, np);
-  return planes_to_nchw(p.p[0], p.p[1], B, kTaps[t].C, lv.h, lv.w, mode, out, static_cast<cudaStream_t>(stream));
+  const bool upsampled = name[0] == 'u';   // u6..u9 live in the decoder's operand format
+  return planes_to_nchw(p.p[0], p.p[1], B, kTaps[t].C, lv.h, lv.w, upsampled ? decoder3x3_fmt(mode) : mode, out,
+                        static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------------------------- profiling

@@ -107,6 +107,8 @@ struct ConvKernelParams {
   int tiles_x, tiles_y, n_blocks, total_items, kc_per_tap;
   int fmt;
   int chunk_kb;       // fp32 modes: k-blocks per TMEM accumulation chunk
+  int x8;             // plane 1 of both operands holds 8-bit cross-term operands (kFmtF16X8, nsm_common.cuh)
+  float cross_scale;  // factor of the cross accumulator when the chunk results are summed (2^-17 with x8, else 1)
   uint32_t idesc_hi;    // M = 128, N = BN
   uint32_t idesc_wide;  // M = 128, N = 2*BN: hi+lo modes, a_hi x [w_hi | w_lo] in one instruction
   ConvEpilogue ep;
@@ -473,8 +475,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 // ([BN,2BN)) at once; a_lo x w_hi then accumulates into cross.  Same tensor cycles as three MMAs of
                 // width BN, but a_hi is fetched from shared memory once instead of twice.
                 const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
-                umma_bf16(d_main, da_hi, db_hi, p.idesc_wide, accum);
-                umma_bf16(d_cross, da_lo, db_hi, p.idesc_hi, 1u);
+                if (p.x8) {
+                  // 8-bit cross planes: one e4m3 MMA of K = 32 (16 channels x two halves) yields both cross terms at
+                  // twice the fp16 rate -> two MMA slots per k-step instead of three
+                  const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
+                  umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
+                  umma_f8(d_cross, da_lo, db_lo, p.idesc_hi, accum);
+                } else {
+                  umma_bf16(d_main, da_hi, db_hi, p.idesc_wide, accum);
+                  umma_bf16(d_cross, da_lo, db_hi, p.idesc_hi, 1u);
+                }
               } else {
                 umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
               }
@@ -586,7 +596,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tmem_ld_32x32(lane_addr + acc * Cfg::ACC_COLS + BN + c0, r1);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+            for (int j = 0; j < 32; ++j)
+              sum[c0 + j] += fmaf(__uint_as_float(r1[j]), p.cross_scale, __uint_as_float(r0[j]));
           }
           tc_fence_before();
           __syncwarp();
@@ -670,7 +681,7 @@ int conv_gemm_pick_bn(const ConvShape& s) {
 
 int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, const ConvEpilogue& ep,
                      cudaStream_t stream) {
-  if (s.Cin % kKChunk || s.Cout % 64 || (s.taps != 1 && s.taps != 9) || (s.fmt < 0 || s.fmt > 2) ||
+  if (s.Cin % kKChunk || s.Cout % 64 || (s.taps != 1 && s.taps != 9) || (s.fmt < 0 || s.fmt > 3) ||
       s.N <= 0 || s.H <= 0 || s.W <= 0) {
     set_error("conv_gemm: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d taps=%d fmt=%d", s.N, s.H, s.W,
               s.Cin, s.Cout, s.taps, s.fmt);
@@ -745,9 +756,12 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.n_blocks = s.Cout / BN;
   kp.total_items = s.N * kp.tiles_x * kp.tiles_y * kp.n_blocks;
   kp.kc_per_tap = s.Cin / kKChunk;
-  kp.fmt = s.fmt;
+  // kFmtF16X8 describes the OPERANDS (input + weights); the output, skip and pooled tensors are plain fp16 hi+lo planes
+  kp.fmt = s.fmt == kFmtF16X8 ? kFmtF16x2 : s.fmt;
   kp.chunk_kb = g_chunk_kb;
-  const uint32_t ef = s.fmt == kFmtF16x2 ? kFmtF16 : kFmtBF16;  // all operand planes of a launch share one element type
+  kp.x8 = s.fmt == kFmtF16X8 ? 1 : 0;
+  kp.cross_scale = kp.x8 ? kX8CrossScale : 1.f;
+  const uint32_t ef = fmt_is_f16(s.fmt) ? kFmtF16 : kFmtBF16;  // fp16 / e4m3 share the descriptor code 0
   kp.idesc_hi = make_idesc_f16(128, BN, ef, ef, 0, 0);
   kp.idesc_wide = planes == 2 ? make_idesc_f16(128, 2 * BN, ef, ef, 0, 0) : kp.idesc_hi;
   kp.ep = ep;

@@ -61,8 +61,17 @@ __device__ __forceinline__ float f16hi_to_f32(uint32_t w) {
 //   0  one bf16 plane                      (bf16 mode, autocast rounding points)
 //   1  hi + lo fp16 planes, |v| <= 65504   (fp32 mode, eval: 22 significand bits)
 //   2  hi + lo bf16 planes, full range     (fp32 mode, training: 16 significand bits, safe for tiny gradients)
-constexpr int kFmtBf16 = 0, kFmtF16x2 = 1, kFmtBf16x2 = 2;
+//   3  fp16 hi plane + an 8-bit "cross" plane (fp32 mode, eval, operands of the decoder's 3x3 convolutions only):
+//      per 16 channels the cross plane holds 16 bytes + 16 bytes of e4m3 values that ONE 8-bit MMA of K = 32 multiplies
+//      pairwise: activations [v * 2 | (v - hi) * 2^11], weights [(w - hi) * 2^16 | w * 2^6], so that
+//          sum_32 a8 * w8 = 2^17 * (v~ * w_lo + v_lo * w~)   = the two cross terms of the hi+lo product, at twice the
+//      tensor rate of the fp16 pipe.  The 3-bit mantissas cost 2^-4 relative on terms that are 2^-12 of the result
+//      (CPU emulation: 4e-6 rms per layer against 1.2e-6 for fp16 hi+lo and 2e-6 for bf16 hi+lo).
+constexpr int kFmtBf16 = 0, kFmtF16x2 = 1, kFmtBf16x2 = 2, kFmtF16X8 = 3;
+constexpr float kX8ActHi = 2.f, kX8ActLo = 2048.f, kX8WgtLo = 65536.f, kX8WgtHi = 64.f;
+constexpr float kX8CrossScale = 1.f / 131072.f;   // 2^-17 = 1 / (kX8ActHi * kX8WgtLo) = 1 / (kX8ActLo * kX8WgtHi)
 __host__ __device__ __forceinline__ int fmt_planes(int fmt) { return fmt == 0 ? 1 : 2; }
+__host__ __device__ __forceinline__ bool fmt_is_f16(int fmt) { return fmt == kFmtF16x2 || fmt == kFmtF16X8; }
 
 // two floats -> packed fp16 pair, saturating to +-65504 in ONE instruction (low half = a)
 __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
@@ -71,14 +80,41 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
   return r;
 }
 __device__ __forceinline__ uint32_t pack_hi(float a, float b, int fmt) {
-  return fmt == kFmtF16x2 ? pack_f16_sat(a, b) : pack_bf16(a, b);
+  return fmt_is_f16(fmt) ? pack_f16_sat(a, b) : pack_bf16(a, b);
 }
 __device__ __forceinline__ float hi_lo_to_f32(uint32_t w, int fmt) {
-  return fmt == kFmtF16x2 ? f16lo_to_f32(w) : bf16lo_to_f32(w);
+  return fmt_is_f16(fmt) ? f16lo_to_f32(w) : bf16lo_to_f32(w);
 }
 __device__ __forceinline__ float hi_hi_to_f32(uint32_t w, int fmt) {
-  return fmt == kFmtF16x2 ? f16hi_to_f32(w) : bf16hi_to_f32(w);
+  return fmt_is_f16(fmt) ? f16hi_to_f32(w) : bf16hi_to_f32(w);
 }
+// two floats -> two e4m3 bytes (low byte = a), round to nearest, saturating to +-448
+__device__ __forceinline__ uint32_t pack_e4m3x2(float a, float b) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float e4m3_to_f32(uint32_t byte) {
+  uint32_t h2;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"((unsigned short)(byte & 0xffu)));
+  return f16lo_to_f32(h2);
+}
+// kFmtF16X8 activations: 8 consecutive channels -> 8 bytes for the first half (v * 2) and 8 for the second ((v - hi) * 2^11)
+// of their 16-channel group; hw[] are the already packed fp16 hi words of the same 8 values.
+__device__ __forceinline__ void x8_act_bytes(const float (&v)[8], const uint32_t (&hw)[4], uint2& first, uint2& second) {
+  uint32_t a[4], b[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float v0 = v[2 * e], v1 = v[2 * e + 1];
+    a[e] = pack_e4m3x2(v0 * kX8ActHi, v1 * kX8ActHi);
+    b[e] = pack_e4m3x2((v0 - f16lo_to_f32(hw[e])) * kX8ActLo, (v1 - f16hi_to_f32(hw[e])) * kX8ActLo);
+  }
+  first = make_uint2(a[0] | (a[1] << 16), a[2] | (a[3] << 16));
+  second = make_uint2(b[0] | (b[1] << 16), b[2] | (b[3] << 16));
+}
+// byte offset, inside one pixel's (or weight row's) 2*C-byte cross-plane row, of channel c's byte in the first half of its
+// 16-channel group (the second-half byte is 16 further)
+__host__ __device__ __forceinline__ int x8_byte(int c) { return (c >> 4) * 32 + (c & 15); }
 // lo plane word of a value pair given the packed hi word
 __device__ __forceinline__ uint32_t pack_lo_resid(float a, float b, uint32_t hw, int fmt) {
   // |residual| <= half an ulp of hi, so it cannot overflow unless hi itself saturated (then satfinite clamps it)
@@ -93,6 +129,7 @@ __device__ __forceinline__ void split_fmt(float v, int fmt, unsigned short& hi, 
   hi = (unsigned short)(hw & 0xffffu);
   lo = (unsigned short)(pack_lo_resid(v, 0.f, hw, fmt) & 0xffffu);
 }
+// (formats 0..2; the cross plane of kFmtF16X8 is not element-addressable as 16-bit words)
 __device__ __forceinline__ float join_fmt(unsigned short hi, unsigned short lo, int fmt) {
   float v = hi_lo_to_f32(hi, fmt);
   if (fmt != kFmtBf16) v += lo_lo_to_f32(lo, fmt);
@@ -220,6 +257,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A * B with 8-bit floating-point operands (e4m3 / e5m2 per the instruction descriptor), K = 32 per instruction
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }

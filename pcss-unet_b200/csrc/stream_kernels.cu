@@ -46,6 +46,14 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
       ci = row; co = col; stap = taps - 1 - tap;
     }
     const float v = w[((long long)co * Cin + ci) * taps + stap];
+    if (fmt == kFmtF16X8) {   // fp16 hi plane + cross plane [(w - hi) * 2^16 | w * 2^6] per 16 inner channels
+      const uint32_t hw = pack_hi(v, 0.f, fmt);
+      hi[i] = (unsigned short)(hw & 0xffffu);
+      uint8_t* row = reinterpret_cast<uint8_t*>(lo) + (i - col) * 2;
+      row[x8_byte(col)] = (uint8_t)(pack_e4m3x2((v - f16lo_to_f32(hw)) * kX8WgtLo, 0.f) & 0xffu);
+      row[x8_byte(col) + 16] = (uint8_t)(pack_e4m3x2(v * kX8WgtHi, 0.f) & 0xffu);
+      continue;
+    }
     unsigned short h, l;
     split_fmt(v, fmt, h, l);
     hi[i] = h;
@@ -110,8 +118,17 @@ __global__ void nchw_to_planes_kernel(const float* __restrict__ x, int C, long l
     const int c = c0 + threadIdx.x;
     if (c < C && p < HW) {
       const long long o = ((long long)n * HW + p) * C + c;
+      const float v = tile[threadIdx.x][i];
+      if (fmt == kFmtF16X8) {   // cross plane [v * 2 | (v - hi) * 2^11] per 16 channels
+        const uint32_t hw = pack_hi(v, 0.f, fmt);
+        hi[o] = (unsigned short)(hw & 0xffffu);
+        uint8_t* row = reinterpret_cast<uint8_t*>(lo) + (o - c) * 2;
+        row[x8_byte(c)] = (uint8_t)(pack_e4m3x2(v * kX8ActHi, 0.f) & 0xffu);
+        row[x8_byte(c) + 16] = (uint8_t)(pack_e4m3x2((v - f16lo_to_f32(hw)) * kX8ActLo, 0.f) & 0xffu);
+        continue;
+      }
       unsigned short h, l;
-      split_fmt(tile[threadIdx.x][i], fmt, h, l);
+      split_fmt(v, fmt, h, l);
       hi[o] = h;
       if (fmt != kFmtBf16) lo[o] = l;
     }
@@ -137,7 +154,12 @@ __global__ void planes_to_nchw_kernel(const unsigned short* __restrict__ hi, con
     float v = 0.f;
     if (c < C && p < HW) {
       const long long o = ((long long)n * HW + p) * C + c;
-      v = join_fmt(hi[o], fmt != kFmtBf16 ? lo[o] : (unsigned short)0, fmt);
+      if (fmt == kFmtF16X8) {   // hi + the residual byte of the cross plane
+        const uint8_t* row = reinterpret_cast<const uint8_t*>(lo) + (o - c) * 2;
+        v = hi_lo_to_f32(hi[o], fmt) + e4m3_to_f32(row[x8_byte(c) + 16]) * (1.f / kX8ActLo);
+      } else {
+        v = join_fmt(hi[o], fmt != kFmtBf16 ? lo[o] : (unsigned short)0, fmt);
+      }
     }
     tile[i][threadIdx.x] = v;
   }
@@ -956,6 +978,28 @@ __global__ void __launch_bounds__(256) upsample_match_kernel(const UpParams p, i
   if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
 }
 
+// 8 channels of one output pixel -> destination planes.  o = element offset of the first channel (pixel * C + 8 * cg).
+// OFMT = kFmtF16X8 writes the fp16 hi plane and the 8-bit cross plane the decoder's 3x3 convolutions consume.
+template <int OFMT>
+__device__ __forceinline__ void up_store8(const UpParams& p, size_t o, int cg, float (&v)[8]) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (OFMT == kFmtBf16) { v[2 * e] = rbf(v[2 * e]); v[2 * e + 1] = rbf(v[2 * e + 1]); }
+    hw[e] = pack_hi(v[2 * e], v[2 * e + 1], OFMT);
+    if (OFMT == kFmtF16x2 || OFMT == kFmtBf16x2) lw[e] = pack_lo_resid(v[2 * e], v[2 * e + 1], hw[e], OFMT);
+  }
+  stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+  if (OFMT == kFmtF16x2 || OFMT == kFmtBf16x2) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+  if (OFMT == kFmtF16X8) {
+    uint2 first, second;
+    x8_act_bytes(v, hw, first, second);
+    uint8_t* row = p.d1 + (o - cg * 8) * 2 + (cg >> 1) * 32 + (cg & 1) * 8;
+    *reinterpret_cast<uint2*>(row) = first;
+    *reinterpret_cast<uint2*>(row + 16) = second;
+  }
+}
+
 // Taps of a PAIR of adjacent outputs of the composite resize (hd >= hs, wd >= ws: adjacent outputs then start at most two
 // source indices apart, so the pair touches <= 5 consecutive source indices).  Taps an output does not use enter with
 // weight 0, so the per-output FMA order is the same as in the one-pixel kernel above and both produce identical bits.
@@ -1005,7 +1049,7 @@ __device__ __forceinline__ void match_hrow(const UpParams& p, size_t nbase, int 
   }
 }
 
-template <int FMT>
+template <int FMT, int OFMT>
 __global__ void __launch_bounds__(256) upsample_match_strip_kernel(const UpParams p, int cg_shift, int strips,
                                                                    int wpairs) {
   const int cgs = 1 << cg_shift;
@@ -1056,22 +1100,14 @@ __global__ void __launch_bounds__(256) upsample_match_strip_kernel(const UpParam
       const int x = 2 * xp + b;
       if (x >= p.wd) continue;
       const size_t o = (((size_t)n * p.hd + y) * p.wd + x) * p.C + cg * 8;
-      uint32_t hw[4], lw[4];
+      float v[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float v[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          float a = fmaf(ty.w[0], h0[b][2 * e + k], 0.f);
-          a = fmaf(ty.w[1], h1[b][2 * e + k], a);
-          a = fmaf(ty.w[2], h2[b][2 * e + k], a);
-          v[k] = FMT == kFmtBf16 ? rbf(a) : a;
-        }
-        hw[e] = pack_hi(v[0], v[1], FMT);
-        lw[e] = pack_lo_resid(v[0], v[1], hw[e], FMT);
+      for (int e = 0; e < 8; ++e) {
+        float a = fmaf(ty.w[0], h0[b][e], 0.f);
+        a = fmaf(ty.w[1], h1[b][e], a);
+        v[e] = fmaf(ty.w[2], h2[b][e], a);
       }
-      stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-      if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+      up_store8<OFMT>(p, o, cg, v);
     }
   }
 }
@@ -1110,22 +1146,16 @@ __device__ __forceinline__ void up2x_hrow(const UpParams& p, size_t rbase, const
   }
 }
 
-template <int FMT>
-__device__ __forceinline__ void up2x_store(const UpParams& p, size_t o, float w0, float w1, const float (&top)[8],
-                                           const float (&bot)[8]) {
-  uint32_t hw[4], lw[4];
+template <int OFMT>
+__device__ __forceinline__ void up2x_store(const UpParams& p, size_t o, int cg, float w0, float w1,
+                                           const float (&top)[8], const float (&bot)[8]) {
+  float v[8];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float v0 = w0 * top[2 * e] + w1 * bot[2 * e], v1 = w0 * top[2 * e + 1] + w1 * bot[2 * e + 1];
-    if (FMT == kFmtBf16) { v0 = rbf(v0); v1 = rbf(v1); }
-    hw[e] = pack_hi(v0, v1, FMT);
-    lw[e] = pack_lo_resid(v0, v1, hw[e], FMT);
-  }
-  stg16(p.d0 + o * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-  if (FMT != kFmtBf16) stg16(p.d1 + o * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+  for (int e = 0; e < 8; ++e) v[e] = w0 * top[e] + w1 * bot[e];
+  up_store8<OFMT>(p, o, cg, v);
 }
 
-template <int FMT>
+template <int FMT, int OFMT>
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p, int cg_shift, int strips) {
   const int cgs = 1 << cg_shift;
   const int j = blockIdx.y * 256 + threadIdx.x;
@@ -1147,10 +1177,10 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p, int c
     up2x_weights(yb, p.hs, wye0, wye1, wyo0, wyo1);
     const size_t o = (((size_t)n * p.hd + 2 * yb) * p.wd + 2 * xb) * p.C + cg * 8;
     const size_t down = (size_t)p.wd * p.C;
-    up2x_store<FMT>(p, o, wye0, wye1, pe, ce);                  // even row: source rows (yb-1, yb)
-    up2x_store<FMT>(p, o + p.C, wye0, wye1, po, co);
-    up2x_store<FMT>(p, o + down, wyo0, wyo1, ce, ne);           // odd row: (yb, yb+1)
-    up2x_store<FMT>(p, o + down + p.C, wyo0, wyo1, co, no);
+    up2x_store<OFMT>(p, o, cg, wye0, wye1, pe, ce);                  // even row: source rows (yb-1, yb)
+    up2x_store<OFMT>(p, o + p.C, cg, wye0, wye1, po, co);
+    up2x_store<OFMT>(p, o + down, cg, wyo0, wyo1, ce, ne);           // odd row: (yb, yb+1)
+    up2x_store<OFMT>(p, o + down + p.C, cg, wyo0, wyo1, co, no);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       pe[e] = ce[e]; po[e] = co[e];
@@ -1172,19 +1202,30 @@ int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes
   p.s0 = (const uint8_t*)src.p[0]; p.s1 = (const uint8_t*)src.p[1];
   p.d0 = (uint8_t*)dst.p[0]; p.d1 = (uint8_t*)dst.p[1];
   p.N = N; p.hs = hs; p.ws = ws; p.C = C; p.hd = hd; p.wd = wd; p.fmt = fmt;
+  // fmt kFmtF16X8: source in the fp16 hi+lo format, destination as fp16 hi plane + 8-bit cross plane
   if (hd == 2 * hs && wd == 2 * ws) {
     const int strips = (hs + kUpStrip - 1) / kUpStrip;
     dim3 grid((unsigned)(N * strips), (unsigned)((ws * cgs + 255) / 256));
-    if (fmt == kFmtBf16) upsample2x_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift, strips);
-    else if (fmt == kFmtF16x2) upsample2x_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, strips);
-    else upsample2x_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, strips);
+    if (fmt == kFmtBf16) upsample2x_kernel<kFmtBf16, kFmtBf16><<<grid, 256, 0, st>>>(p, shift, strips);
+    else if (fmt == kFmtF16x2) upsample2x_kernel<kFmtF16x2, kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, strips);
+    else if (fmt == kFmtF16X8) upsample2x_kernel<kFmtF16x2, kFmtF16X8><<<grid, 256, 0, st>>>(p, shift, strips);
+    else upsample2x_kernel<kFmtBf16x2, kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, strips);
   } else if (hd >= hs && wd >= ws) {
     const int strips = (hd + kMatchStrip - 1) / kMatchStrip, wpairs = (wd + 1) / 2;
     dim3 grid((unsigned)(N * strips), (unsigned)((wpairs * cgs + 255) / 256));
-    if (fmt == kFmtBf16) upsample_match_strip_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
-    else if (fmt == kFmtF16x2) upsample_match_strip_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
-    else upsample_match_strip_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
+    if (fmt == kFmtBf16)
+      upsample_match_strip_kernel<kFmtBf16, kFmtBf16><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
+    else if (fmt == kFmtF16x2)
+      upsample_match_strip_kernel<kFmtF16x2, kFmtF16x2><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
+    else if (fmt == kFmtF16X8)
+      upsample_match_strip_kernel<kFmtF16x2, kFmtF16X8><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
+    else
+      upsample_match_strip_kernel<kFmtBf16x2, kFmtBf16x2><<<grid, 256, 0, st>>>(p, shift, strips, wpairs);
   } else {
+    if (fmt == kFmtF16X8) {
+      set_error("upsample_match: the 8-bit cross format is only produced by the up-sampling paths (hd >= hs, wd >= ws)");
+      return 1;
+    }
     dim3 grid((unsigned)(N * hd), (unsigned)((wd * cgs + 255) / 256));
     {
       if (fmt == kFmtBf16) upsample_match_kernel<kFmtBf16><<<grid, 256, 0, st>>>(p, shift);

@@ -19,6 +19,9 @@ LIB_PATH = os.path.join(HERE, "libnsm_b200.so")
 MODE_BF16 = 0
 MODE_FP32 = 1
 MODE_FP32_TRAIN = 2
+# storage format of the OPERANDS of the decoder's 3x3 convolutions in fp32 mode (fp16 hi plane + 8-bit cross plane, see
+# csrc/nsm_common.cuh); whole-network calls never take it, only the stage-level entry points
+FMT_F16_X8 = 3
 MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "fp32_train": MODE_FP32_TRAIN}
 NUM_TENSORS = 98
 
@@ -340,8 +343,9 @@ def conv_fwd(x: PlaneTensor, wp, ksize, Cout, mode, bias=None, bn_scale=None, bn
     """One fused conv stage on the tensor cores.  Returns (out PlaneTensor|None, pooled|None, raw fp32 NHWC|None)."""
     N, Cin, H, W = x.shape
     dev = x.p0.device
-    out = PlaneTensor(N, Cout, H, W, mode, dev) if want_out else None
-    pl = PlaneTensor(N, Cout, H // 2, W // 2, mode, dev) if pool else None
+    omode = MODE_FP32 if mode == FMT_F16_X8 else mode      # 8-bit cross operands, plain fp16 hi+lo results
+    out = PlaneTensor(N, Cout, H, W, omode, dev) if want_out else None
+    pl = PlaneTensor(N, Cout, H // 2, W // 2, omode, dev) if pool else None
     raw = torch.empty(N, H, W, Cout, dtype=torch.float32, device=dev) if want_f32 else None
     a = ConvArgs()
     a.N, a.H, a.W, a.Cin, a.Cout, a.ksize, a.mode = N, H, W, Cin, Cout, ksize, mode
@@ -358,10 +362,13 @@ def conv_fwd(x: PlaneTensor, wp, ksize, Cout, mode, bias=None, bn_scale=None, bn
     return out, pl, raw
 
 
-def upsample_match(x: PlaneTensor, hd, wd):
+def upsample_match(x: PlaneTensor, hd, wd, out_x8=False):
+    """out_x8: fp32-mode source, result in the 8-bit cross operand format of the decoder's 3x3 convolutions."""
     N, C, hs, ws = x.shape
-    out = PlaneTensor(N, C, hd, wd, x.mode, x.p0.device)
-    check(lib().nsm_upsample_match(x.pair(), N, hs, ws, C, out.pair(), hd, wd, x.mode, stream_ptr()),
+    omode = FMT_F16_X8 if out_x8 else x.mode
+    assert not out_x8 or x.mode == MODE_FP32
+    out = PlaneTensor(N, C, hd, wd, omode, x.p0.device)
+    check(lib().nsm_upsample_match(x.pair(), N, hs, ws, C, out.pair(), hd, wd, omode, stream_ptr()),
           "nsm_upsample_match")
     return out
 

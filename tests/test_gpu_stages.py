@@ -126,6 +126,51 @@ def test_conv_stage(nsm, mode_name, case):
         check_close(pl.to_nchw(), ref_pool, mode_name, "pooled output")
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[5] == 3] + [(1, 20, 40, 1024, 1024, 3, False, False)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_stage_x8_operands(nsm, case):
+    """fp32 mode, decoder 3x3 convolutions: fp16 hi plane + 8-bit (e4m3) cross plane operands, two MMA slots per k-step.
+    The cross terms carry 3-bit mantissas: tolerance 6e-5 * max(1, max|ref|) on the raw GEMM (measured ~1.5e-5), and the
+    whole-network tests keep the 1e-4 bound on the output."""
+    N, H, W, Cin, Cout, k, _, _ = case
+    g = gen(hash(case) % 1000)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    xt = nsm.PlaneTensor.from_nchw(x.cuda(), nsm.FMT_F16_X8)
+    # the activation format round-trips to ~2^-16 relative (hi + e4m3 residual)
+    assert (xt.to_nchw().cpu() - x).abs().max() <= 2.0 ** -15 * x.abs().max()
+    wp = nsm.pack_conv_weight(w.cuda(), nsm.FMT_F16_X8)
+    out, _, raw = nsm.conv_fwd(xt, wp, k, Cout, nsm.FMT_F16_X8, bias=b.cuda(), want_f32=True)
+    torch.cuda.synchronize()
+    assert out.mode == nsm.MODE_FP32
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1).float()
+    got = raw.permute(0, 3, 1, 2).cpu()
+    tol = 6e-5 * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() <= tol, "raw GEMM (x8 operands)\n" + describe(got - ref, ref)
+    assert (out.to_nchw().cpu() - ref).abs().max().item() <= tol + 3e-5 * max(1.0, ref.abs().max().item())
+    # against the plain fp16 hi+lo path on the same data: same result up to the cross-term quantisation
+    xt1 = nsm.PlaneTensor.from_nchw(x.cuda(), nsm.MODE_FP32)
+    _, _, raw1 = nsm.conv_fwd(xt1, nsm.pack_conv_weight(w.cuda(), nsm.MODE_FP32), k, Cout, nsm.MODE_FP32,
+                              bias=b.cuda(), want_f32=True)
+    assert (raw - raw1).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 67, 120, 135, 240), (1, 64, 20, 28, 20, 28), (1, 512, 5, 7, 10, 14)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_upsample_match_x8_output(nsm, shape):
+    """The up-samplers write the decoder operand format directly: same values as the fp16 hi+lo result up to the
+    e4m3 residual (2^-15 relative)."""
+    N, C, hs, ws, hd, wd = shape
+    x = torch.randn(N, C, hs, ws, generator=gen(5))
+    xt = nsm.PlaneTensor.from_nchw(x.cuda(), nsm.MODE_FP32)
+    a = nsm.upsample_match(xt, hd, wd).to_nchw()
+    b = nsm.upsample_match(xt, hd, wd, out_x8=True)
+    assert b.mode == nsm.FMT_F16_X8
+    assert (b.to_nchw() - a).abs().max().item() <= 2.0 ** -15 * a.abs().max().item()
+    assert torch.equal(b.p0, nsm.upsample_match(xt, hd, wd).p0)      # identical fp16 hi planes
+
+
 @pytest.mark.parametrize("mode_name", ["bf16", "fp32", "fp32_train"])
 @pytest.mark.parametrize("shape", [(1, 64, 8, 12, 16, 24), (2, 128, 67, 120, 135, 240), (1, 64, 20, 28, 20, 28),
                                    (1, 512, 5, 7, 10, 14), (1, 64, 3, 2, 7, 5)],
