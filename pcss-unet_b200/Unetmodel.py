@@ -8,7 +8,7 @@ unchanged with this directory ahead of the reference on ``sys.path``.
 
 Only ``forward`` differs: the nn.Modules are parameter containers, the arithmetic runs in the hand-written sm_100a
 kernels of ``libnsm_b200.so`` (tcgen05 implicit-GEMM convolutions with fused BatchNorm/LeakyReLU/skip/pool epilogues,
-SIMT head/tail stages, bilinear up-sampling).  There is no PyTorch or CPU fallback: a CPU tensor raises.
+warp-level tensor-core head/tail stages, bilinear up-sampling).  There is no PyTorch or CPU fallback: a CPU tensor raises.
 
 Precision ("mode"):
   * ``fp32`` (default outside autocast): fp32-accurate tensor-core arithmetic on hi+lo half-precision planes (fp16
