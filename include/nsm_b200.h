@@ -30,6 +30,12 @@ extern "C" {
 #define NSM_MODE_BF16 0
 #define NSM_MODE_FP32 1       /* eval / forward-only: hi+lo fp16 planes (|activation| <= 65504), 22 significand bits */
 #define NSM_MODE_FP32_TRAIN 2 /* training: hi+lo bf16 planes (full fp32 range, safe for tiny gradients), 16 bits     */
+/* Operand storage format of the decoder's 3x3 convolutions inside NSM_MODE_FP32 (stage-level entry points only:
+ * nsm_nchw_to_planes / nsm_planes_to_nchw / nsm_pack_conv_weight / nsm_conv_fwd take it as `mode`, nsm_upsample_match
+ * produces it from an NSM_MODE_FP32 source): plane 0 = fp16 hi, plane 1 = per 16 channels 16+16 e4m3 bytes that one 8-bit
+ * tensor-core MMA turns into both cross terms of the hi+lo product.  Results / skips / pooled tensors of such a convolution
+ * are plain NSM_MODE_FP32 planes.  The whole-network calls pick it internally (NSM_NO_X8=1 in the environment disables). */
+#define NSM_FMT_F16_X8 3
 
 /* number of fp32 tensors nsm_unet_pack() consumes, in this order:
  *   for K in conv2..conv9 (Unetmodel.py:39-61):
