@@ -105,19 +105,22 @@ int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64
 struct ConvKernelParams {
   int N, H, W, Cin, Cout, taps;
   int tiles_x, tiles_y, n_blocks, total_items, kc_per_tap;
+  int total_pairs;    // CTA-pair kernels: (pixel-tile pairs) x n_blocks
   int fmt;
   int chunk_kb;       // fp32 modes: k-blocks per TMEM accumulation chunk
   int x8;             // plane 1 of both operands holds 8-bit cross-term operands (kFmtF16X8, nsm_common.cuh)
   float cross_scale;  // factor of the cross accumulator when the chunk results are summed (2^-17 with x8, else 1)
-  uint32_t idesc_hi;    // M = 128, N = BN
+  uint32_t idesc_hi;    // M = 128 (256 for CTA pairs), N = BN
   uint32_t idesc_wide;  // M = 128, N = 2*BN: hi+lo modes, a_hi x [w_hi | w_lo] in one instruction
   ConvEpilogue ep;
 };
 
-template <int BN, int NP>
+// CG = 2: CTA pair (cta_group::2).  The pair computes two pixel tiles (M = 256) against one weight tile of which every CTA
+// holds half the rows: per MAC a CTA moves A + B/2 instead of A + B through L2 -> shared memory.
+template <int BN, int NP, int CG = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 elements (2 B)
-  static constexpr int B_BYTES = BN * 128;   // BN channels x 64 elements
+  static constexpr int B_BYTES = (BN / CG) * 128;   // this CTA's rows of the weight tile x 64 elements
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
   // 8 epilogue warps x 4 KB staging tiles for the TMA stores of the output (32 pixels x 32 channels x {hi, lo})
   static constexpr int STAGING_BYTES = 8 * 4096;
@@ -176,6 +179,20 @@ __device__ __forceinline__ void epi_issue_residual(const EpiTile& et, int g, int
   const uint32_t dst = et.stg + epi_slot<NP>(g);
   tma_load_4d_saddr(dst, et.res[0], bar, cb, et.x0, et.y0, et.n);
   if (NP == 2) tma_load_4d_saddr(dst + 2048, et.res[1], bar, cb, et.x0, et.y0, et.n);
+}
+
+// CTA-pair work item: pair index -> (column block, this CTA's pixel tile = 2 * tile-pair + rank).  A tile index past the end
+// (odd tile count) decodes to n == N: its loads are zero-filled and its stores clipped by the TMA unit.
+__device__ __forceinline__ void decode_pair(const ConvKernelParams& p, int pi, int rank, int& n, int& y0, int& x0,
+                                            int& nb) {
+  nb = pi % p.n_blocks;
+  int t = 2 * (pi / p.n_blocks) + rank;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  n = t / p.tiles_y;
+  y0 = ty * kTileH;
+  x0 = tx * kTileW;
 }
 
 // Epilogue math + stores for 32 consecutive output channels [cb, cb+32) of one pixel (one thread).
@@ -356,7 +373,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
   }
 }
 
-template <int BN, int NP>
+template <int BN, int NP, int CG>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -364,7 +381,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                  const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ ConvKernelParams p) {
-  using Cfg = GemmCfg<BN, NP>;
+  using Cfg = GemmCfg<BN, NP, CG>;
+  const int cta_rank = CG == 2 ? int(cluster_ctarank()) : 0;
+  // work items of this CTA (pair): first, stride, count
+  const int it_first = CG == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int it_step = CG == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
+  const int it_count = CG == 2 ? p.total_pairs : p.total_items;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // 1024-byte aligned (SWIZZLE_128B)
@@ -405,14 +427,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);
+      mbar_init(&tempty_bar[a], 8 * CG);   // the leader's copy collects the epilogue warps of both CTAs
     }
     for (int a = 0; a < 16; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -425,21 +451,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = it_first; item < it_count; item += it_step) {
         int n, y0, x0, nb;
-        decode_item(p, item, n, y0, x0, nb);
+        if (CG == 2) decode_pair(p, item, cta_rank, n, y0, x0, nb);
+        else decode_item(p, item, n, y0, x0, nb);
+        const int brow = nb * BN + cta_rank * (BN / CG);   // this CTA's rows of the weight tile
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
           const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + NP * Cfg::A_BYTES;
-            tma_load_4d(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
-            if (NP == 2) tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
-            tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, nb * BN);
-            if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, nb * BN);
+            if (CG == 2) {
+              // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the pair
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_pair(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+              if (NP == 2)
+                tma_load_4d_pair(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+              tma_load_2d_pair(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
+              if (NP == 2) tma_load_2d_pair(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
+            } else {
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_4d(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+              if (NP == 2) tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+              tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
+              if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
+            }
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -450,9 +488,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {   // CTA pairs: the leader issues for both
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = it_first; item < it_count; item += it_step) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_len) {
           const int kb1 = kb0 + chunk_len < num_kb ? kb0 + chunk_len : num_kb;
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -469,7 +507,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;  // first MMA of a chunk overwrites
               const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, 1024);
               const uint64_t db_hi = make_desc_sw128(b_hi + k * 32, 16, 1024);
-              if (NP == 2) {
+              if (CG == 2) {
+                umma_bf16_pair(d_main, da_hi, db_hi, p.idesc_hi, accum);
+                if (NP == 2) {
+                  const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
+                  const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
+                  if (p.x8) {
+                    umma_f8_pair(d_cross, da_lo, db_lo, p.idesc_hi, accum);
+                  } else {   // (the wide hi|lo trick does not survive the split of the weight rows over two CTAs)
+                    umma_bf16_pair(d_cross, da_hi, db_lo, p.idesc_hi, accum);
+                    umma_bf16_pair(d_cross, da_lo, db_hi, p.idesc_hi, 1u);
+                  }
+                }
+              } else if (NP == 2) {
                 // The weight planes lie back to back in the stage (hi rows, then lo rows) = ONE K-major tile of 2*BN rows:
                 // a_hi x [w_hi | w_lo] is a single MMA of width 2*BN that fills main (columns [0,BN)) and cross
                 // ([BN,2BN)) at once; a_lo x w_hi then accumulates into cross.  Same tensor cycles as three MMAs of
@@ -489,13 +539,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
               }
             }
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            if (CG == 2) umma_commit_pair(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&tfull_bar[acc]);  // chunk accumulator complete -> epilogue
+          if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
+          else umma_commit(&tfull_bar[acc]);  // chunk accumulator complete -> epilogue
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -535,15 +587,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         st1[k] = st2[k] = 0.0;
       }
     };
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    for (int item = it_first; item < it_count; item += it_step) {
       int n, y0, x0, nb;
-      decode_item(p, item, n, y0, x0, nb);
+      if (CG == 2) decode_pair(p, item, cta_rank, n, y0, x0, nb);
+      else decode_item(p, item, n, y0, x0, nb);
       if (nb != st_nb) {
         flush_stats(st_nb);
         st_nb = nb;
       }
       const int y = y0 + ly, x = x0 + lx;
-      const bool valid = (y < p.H) && (x < p.W);
+      const bool valid = (y < p.H) && (x < p.W) && (n < p.N);
       const size_t pix = (size_t(n) * p.H + y) * p.W + x;
       const int cbase = nb * BN + half * HB;
       et.x0 = x0; et.y0 = y0 + 2 * q; et.n = n;
@@ -578,7 +631,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       } else {
@@ -601,7 +657,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -619,35 +678,52 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // nobody leaves while the peer may still signal this CTA's barriers / read its smem
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NP>
+template <int BN, int NP, int CG = 1>
 static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, NP>;
-  auto kern = conv_gemm_kernel<BN, NP>;
+  using Cfg = GemmCfg<BN, NP, CG>;
+  auto kern = conv_gemm_kernel<BN, NP, CG>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(conv_gemm<%d,%d>, %d B smem): %s", BN, NP, Cfg::SMEM_BYTES,
+      set_error("cudaFuncSetAttribute(conv_gemm<%d,%d,%d>, %d B smem): %s", BN, NP, CG, Cfg::SMEM_BYTES,
                 cudaGetErrorString(e));
       return 1;
     }
     attr_set = true;
   }
-  kern<<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
-                                                        maps[7], maps[8], maps[9], kp);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (CG == 2) {   // CTA pairs = clusters of two (same TPC)
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7],
+                                     maps[8], maps[9], kp);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
-    set_error("conv_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
+    set_error("conv_gemm<%d,%d,%d> launch failed: %s", BN, NP, CG, cudaGetErrorString(e));
     return 1;
   }
   count_launch();
@@ -688,6 +764,14 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     return 1;
   }
   const int BN = conv_gemm_pick_bn(s);
+  // CTA pairs (EXPERIMENTAL, NSM_CG2=1): bf16 and 8-bit-cross operands (the wide hi|lo MMA of the other formats needs the
+  // whole weight tile in one CTA), BN = 128 tiles, at least two pixel tiles.  Verified by the parity tests, moves 25 % fewer
+  // bytes through L2 -> shared memory (ncu: 14.5 GB against 19.3 GB for conv6 3x3), but is 30 % SLOWER at the moment: the
+  // leader's MMA thread waits for operands (tensor pipe 38 % active) -- the stage hand-off across the pair needs work
+  // before this can become the default.
+  static const bool cg2_on = getenv("NSM_CG2") != nullptr;
+  const int m_tiles = s.N * ((s.W + kTileW - 1) / kTileW) * ((s.H + kTileH - 1) / kTileH);
+  const int CG = (cg2_on && BN == 128 && (s.fmt == kFmtBf16 || s.fmt == kFmtF16X8) && m_tiles >= 2) ? 2 : 1;
   CUtensorMap maps[10];  // A hi/lo, B hi/lo, output hi/lo, pooled output hi/lo, skip hi/lo
   memset(maps, 0, sizeof(maps));
   const uint64_t adims[4] = {uint64_t(s.Cin), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
@@ -696,7 +780,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   const uint64_t K = uint64_t(s.taps) * s.Cin;
   const uint64_t bdims[2] = {K, uint64_t(s.Cout)};
   const uint64_t bstr[1] = {K * 2};
-  const uint32_t bbox[2] = {uint32_t(kKChunk), uint32_t(BN)};
+  const uint32_t bbox[2] = {uint32_t(kKChunk), uint32_t(BN / CG)};
   const int planes = fmt_planes(s.fmt);
   for (int pl = 0; pl < planes; ++pl) {
     if (!in.p[pl] || !w.p[pl]) {
@@ -755,6 +839,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.tiles_y = (s.H + kTileH - 1) / kTileH;
   kp.n_blocks = s.Cout / BN;
   kp.total_items = s.N * kp.tiles_x * kp.tiles_y * kp.n_blocks;
+  kp.total_pairs = ((m_tiles + 1) / 2) * kp.n_blocks;
   kp.kc_per_tap = s.Cin / kKChunk;
   // kFmtF16X8 describes the OPERANDS (input + weights); the output, skip and pooled tensors are plain fp16 hi+lo planes
   kp.fmt = s.fmt == kFmtF16X8 ? kFmtF16x2 : s.fmt;
@@ -762,9 +847,14 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.x8 = s.fmt == kFmtF16X8 ? 1 : 0;
   kp.cross_scale = kp.x8 ? kX8CrossScale : 1.f;
   const uint32_t ef = fmt_is_f16(s.fmt) ? kFmtF16 : kFmtBF16;  // fp16 / e4m3 share the descriptor code 0
-  kp.idesc_hi = make_idesc_f16(128, BN, ef, ef, 0, 0);
+  kp.idesc_hi = make_idesc_f16(128 * CG, BN, ef, ef, 0, 0);
   kp.idesc_wide = planes == 2 ? make_idesc_f16(128, 2 * BN, ef, ef, 0, 0) : kp.idesc_hi;
   kp.ep = ep;
+  if (CG == 2) {
+    const int pairs = kp.total_pairs < num_sms() / 2 ? kp.total_pairs : num_sms() / 2;
+    if (planes == 1) return launch_t<128, 1, 2>(maps, kp, 2 * pairs, stream);
+    return launch_t<128, 2, 2>(maps, kp, 2 * pairs, stream);
+  }
   const int grid = kp.total_items < num_sms() ? kp.total_items : num_sms();
   if (planes == 1) {
     if (BN == 256) return launch_t<256, 1>(maps, kp, grid, stream);
