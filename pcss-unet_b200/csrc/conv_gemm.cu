@@ -767,8 +767,11 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   // CTA pairs (EXPERIMENTAL, NSM_CG2=1): bf16 and 8-bit-cross operands (the wide hi|lo MMA of the other formats needs the
   // whole weight tile in one CTA), BN = 128 tiles, at least two pixel tiles.  Verified by the parity tests, moves 25 % fewer
   // bytes through L2 -> shared memory (ncu: 14.5 GB against 19.3 GB for conv6 3x3), but is 30 % SLOWER at the moment: the
-  // leader's MMA thread waits for operands (tensor pipe 38 % active) -- the stage hand-off across the pair needs work
-  // before this can become the default.
+  // tensor pipe is 38 % active and a k-block takes ~1200 cycles instead of ~870.  Relaying the peer's "operands landed"
+  // with one arrival per stage instead of remote complete_tx updates changed nothing, so the loss is on the MMA side:
+  // 128-wide pair MMAs (eight dependent accumulating instructions per k-block) seem to pay a per-instruction hand-shake
+  // between the two SMs that 256-wide tiles would amortise -- but hi+lo modes have no TMEM left for 256-wide double-buffered
+  // accumulators.
   static const bool cg2_on = getenv("NSM_CG2") != nullptr;
   const int m_tiles = s.N * ((s.W + kTileW - 1) / kTileW) * ((s.H + kTileH - 1) / kTileH);
   const int CG = (cg2_on && BN == 128 && (s.fmt == kFmtBf16 || s.fmt == kFmtF16X8) && m_tiles >= 2) ? 2 : 1;
