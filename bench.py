@@ -387,6 +387,8 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "train": train}
+    if world == 1 and not args.no_stock:
+        line["stock_pytorch_gpu"] = stock_pytorch_baseline(net, x)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sec = cpu_forward_timer(make_params(), H, W, 2, 1)
@@ -396,6 +398,64 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stock_pytorch_forward(net, x):
+    """The reference's forward graph (Unetmodel.py:90-149) executed by stock PyTorch ops on the drop-in's own parameter
+    containers (real nn.Conv2d / nn.BatchNorm2d modules): the cuDNN / ATen baseline on the same GPU."""
+    import torch.nn.functional as F
+
+    def match(t, ref):
+        return t if t.shape[-2:] == ref.shape[-2:] else F.interpolate(t, size=ref.shape[-2:], mode="bilinear",
+                                                                      align_corners=True)
+    H, W = x.shape[-2] - x.shape[-2] % 2, x.shape[-1] - x.shape[-1] % 2
+    if (H, W) != tuple(x.shape[-2:]):
+        x = F.interpolate(x, size=(H, W), mode="bilinear", align_corners=True)
+    x = F.pixel_unshuffle(x.float(), 2)
+    c2 = net.conv2.conv(x); c3 = net.conv3.conv(F.avg_pool2d(c2, 2)); c4 = net.conv4.conv(F.avg_pool2d(c3, 2))
+    c5 = net.conv5.conv(F.avg_pool2d(c4, 2))
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)
+    c6 = net.conv6.conv(match(up(c5), c4)) + c4
+    c7 = net.conv7.conv(match(up(c6), c3)) + c3
+    c8 = net.conv8.conv(match(up(c7), c2)) + c2
+    c9 = net.conv9.conv(match(up(c8), c2))
+    return torch.sigmoid(F.pixel_shuffle(net.conv10(c9), 2))
+
+
+def stock_pytorch_baseline(net, x, steps=5):
+    """ms per frame of stock PyTorch on this GPU: fp32 with TF32 allowed (PyTorch's default conv setting), strict fp32, and
+    bf16 autocast with channels_last -- BASELINE.md section 3 item 5.  Measurement only; never on the product path."""
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=x.device)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32, amp in (("fp32_tf32", True, False), ("fp32_strict", False, False), ("bf16_autocast", True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            m = net.to(memory_format=torch.channels_last)
+            xin = x.contiguous(memory_format=torch.channels_last)
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                for _ in range(3):
+                    stock_pytorch_forward(m, xin)
+                ms = 0.0
+                for _ in range(steps):
+                    flush.zero_()
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    stock_pytorch_forward(m, xin)
+                    e.record()
+                    torch.cuda.synchronize()
+                    ms += s.elapsed_time(e)
+            out[name] = {"ms_per_step": ms / steps, "value": x.shape[0] * x.shape[-2] * x.shape[-1] / (ms / steps) / 1e3,
+                         "unit": "Mpix/s"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+        net.to(memory_format=torch.contiguous_format)
+    out["note"] = ("reference forward graph through stock PyTorch ops (cuDNN, channels_last, cudnn.benchmark) on the same "
+                   "GPU and parameters; fp32_tf32 = PyTorch's default conv precision (~2e-3 output error), fp32_strict "
+                   "= allow_tf32 off, the only stock setting within 1e-4 of the fp32 reference")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -588,6 +648,7 @@ def main():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stock", action="store_true", help="skip the stock PyTorch/cuDNN same-GPU baseline")
     ap.add_argument("--no-perturb", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="inference workload: skip the attached training measurement")
     ap.add_argument("--train-precision", default=None, choices=["fp32", "bf16"])
