@@ -287,6 +287,10 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, single_ms = t.tolist()
+    # stock PyTorch / cuDNN on the same GPU, same parameters, same frame (before the model is released for training)
+    stock = None
+    if world == 1 and not args.no_stock:
+        stock = stock_pytorch_baseline(net, x)
     # second headline of BASELINE.json ("train samples/s @1/2/4/8 B200"): a short training measurement attached to the
     # same line (all ranks take part: data-parallel step with NCCL gradient all-reduce)
     train = None
@@ -303,7 +307,8 @@ def run_b200(args):
                 tl = measure_train(targs, own_process_group=False)
                 if tl is not None:
                     full[tag] = {"value": tl["value"], "unit": tl["unit"], "ms_per_step": tl["ms_per_step"],
-                                 "e2e": tl["e2e"]["value"], "gemm_tflops": tl["roofline"]["achieved"],
+                                 "e2e": tl["e2e"]["value"], "stock_pytorch_gpu": tl.get("stock_pytorch_gpu"),
+                                 "gemm_tflops": tl["roofline"]["achieved"],
                                  "gemm_frac_of_sustained_peak": tl["roofline"]["frac"],
                                  "workload": tl["config"]["workload"]}
             train = full
@@ -387,8 +392,8 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "train": train}
-    if world == 1 and not args.no_stock:
-        line["stock_pytorch_gpu"] = stock_pytorch_baseline(net, x)
+    if stock is not None:
+        line["stock_pytorch_gpu"] = stock
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sec = cpu_forward_timer(make_params(), H, W, 2, 1)
@@ -463,6 +468,50 @@ def stock_pytorch_baseline(net, x, steps=5):
 # ----------------------------------------------------------------------------------------------------------------
 TRAIN_FLOP_PER_SAMPLE = 3 * 747680.0 * 512 * 512           # fwd + dgrad + wgrad
 PERT_FLOP_PER_SAMPLE = 3 * 747680.0 * 512 * 512            # + 3 no-grad forwards of the perturbation loss
+
+
+def stock_pytorch_train_baseline(B, H, W, dev, use_pert, steps=3):
+    """ms per training step of the same objective through stock PyTorch on this GPU (reference forward graph + autograd,
+    bf16 autocast, channels_last, cuDNN benchmark, L1 (+ 3 no-grad perturbed forwards), clip_grad_norm_ + fused AdamW).
+    Measurement only; a fresh model, never on the product path."""
+    from Unetmodel import Unet
+    torch.manual_seed(7)
+    net = Unet(dropout_rate=0.2).to(dev).to(memory_format=torch.channels_last).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=7e-4, weight_decay=1e-3, fused=True)
+    x = torch.randn(B, 4, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+    t = torch.rand(B, 1, H, W, device=dev)
+    saved = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = stock_pytorch_forward(net, x)
+            loss = 0.9 * (out.float() - t).abs().mean()
+            if use_pert:
+                with torch.no_grad():
+                    sd = x.float().std(dim=(0, 2, 3), keepdim=True)
+                    ys = [stock_pytorch_forward(net, x + torch.randn_like(x) * sd * 0.01) for _ in range(3)]
+                loss = loss + 0.1 * sum((out.float() - y.float()).abs().mean() for y in ys) / 3
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+
+    try:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            step()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / steps
+    finally:
+        torch.backends.cudnn.benchmark = saved
+    return {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "samples/s",
+            "note": "stock PyTorch autograd on the same GPU: bf16 autocast, channels_last, cudnn.benchmark, fused AdamW"}
 
 
 def measure_train(args, own_process_group=True):
@@ -625,6 +674,10 @@ def measure_train(args, own_process_group=True):
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_loss": last},
             "gpu_launches": launches,
             "roofline": roofline}
+    if world == 1 and not args.no_stock and precision == "bf16":
+        del net, crit, opt
+        torch.cuda.empty_cache()
+        line["stock_pytorch_gpu"] = stock_pytorch_train_baseline(B, H, W, dev, use_pert)
     if world > 1 and own_process_group:
         dist.destroy_process_group()
     return line
