@@ -370,14 +370,16 @@ def run_b200(args):
                 "kernel_share_of_step": conv_ms / all_ms if all_ms else None,
                 "per_layer": layers}
 
-    line = {"metric": "U-Net inference Mpix/s @1080p", "value": value, "unit": "Mpix/s", "n_gpus": world,
+    cfg_name = ("cfg1" if (B, H, W) == (1, 1080, 1920) else
+                "cfg4 (per-GPU share: 2 of the 16 4K frames)" if (B, H, W) == (2, 2160, 3840) else "custom shape")
+    line = {"metric": "U-Net inference Mpix/s @1080p" if H == 1080 else f"U-Net inference Mpix/s @{W}x{H}", "value": value, "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 (fp16 hi + fp16-lo / e4m3-cross operand planes, 2-3 MMA slots per MAC, fp32 accumulate; "
                      "output within 1e-4 of the fp32 reference)" if precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": f"cfg1: U-Net inference, one {W}x{H} synthetic G-buffer frame per GPU "
-                                   f"(batch {B}), {precision} mode, eval BatchNorm",
+            "config": {"workload": f"{cfg_name}: U-Net inference, {B} synthetic {W}x{H} G-buffer frame(s) per GPU "
+                                   f"per step, {precision} mode, eval BatchNorm",
                        "l2": "256 MiB buffer written before every timed step (L2 flush); step working set ~1.5 GB",
                        "sharding": "frames per rank, no collective"},
             "clocks": clocks,
