@@ -155,6 +155,20 @@ def test_fused_standardise_and_host_entry(nsm):
         assert y8.dtype == torch.uint8 and torch.equal(y8, (y.cpu() * 255).to(torch.uint8))
 
 
+def test_eval_in_training_storage_format(nsm):
+    """NSM_MODE_FP32_TRAIN (hi+lo bf16 planes, the range-safe format of fp32 training) also serves eval forwards, e.g.
+    validation inside a training run: 16 significand bits -> output within 5e-4 of the fp32 oracle (the fp32 eval mode
+    with its fp16 planes is the one held to 1e-4)."""
+    for shape in [(2, 4, 48, 64), (1, 4, 41, 57)]:
+        P, x = calibrated(shape)
+        net = make_net(P, "fp32_train")
+        with torch.no_grad():
+            ref = oracle.unet_forward(x, P, training=False)
+            y = net(x.cuda()).cpu()
+        assert y.shape == ref.shape
+        assert (y - ref).abs().max().item() <= 5e-4, (y - ref).abs().max().item()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_frame_pipeline_matches_single_calls(nsm, precision):
     """nsm_unet_pipe_*: a sequence of frames through the double-buffered copy/compute pipeline returns, frame by frame,
