@@ -14,14 +14,20 @@
 // Warp roles (320 threads, 1 CTA / SM, persistent over work items):
 //   warp 0    TMA producer          (smem full/empty mbarrier ring)
 //   warp 1    tcgen05.mma issuer    (single thread; accumulators double-buffered in TMEM)
-//   warps 2-9 epilogue              (tcgen05.ld -> bias, BN affine, LeakyReLU, residual add, 2x2 avg-pool,
-//                                    bf16 (or hi/lo split) NHWC stores); two warps per TMEM lane quarter, each
-//                                    owning half of the tile's columns, for memory-level parallelism on thin layers
+//   warps 2-9 epilogue              (tcgen05.ld -> bias, [BN statistics], BN affine, LeakyReLU, skip add, 2x2 avg-pool,
+//                                    bf16 / hi+lo split); two warps per TMEM lane quarter, each owning half of the
+//                                    tile's columns.  Results leave, and the skip tensor arrives, through per-warp
+//                                    swizzled staging tiles and TMA (cp.async.bulk.tensor) -- no per-lane global
+//                                    accesses, ragged tiles are clipped by the TMA unit.
 //
-// fp32 mode ("planes == 2"): activations and weights are stored as hi + lo fp16 planes (value = hi + lo, 22
-// significand bits) and the issuer runs a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into the same fp32 accumulator: operand
-// residuals <= 2^-23, dropped a_lo*w_lo <= 2^-22 -> ~4e-6 on the network output (CPU emulation), i.e. 3xTF32-class
-// accuracy at bf16-pipe speed.  Values are saturated to the fp16 range (|v| <= 65504).
+// fp32 mode ("planes == 2"): activations and weights are stored as hi + lo planes (value = hi + lo) and the issuer
+// accumulates a_hi*w_hi into a main and a_hi*w_lo + a_lo*w_hi into a cross TMEM accumulator (the dropped a_lo*w_lo is
+// <= 2^-22), in chunks of K that the epilogue warps add in fp32 registers because the tensor core's accumulator
+// truncates.  Three operand encodings:
+//   fp16 hi + fp16 lo (eval)  : a_hi x [w_hi | w_lo] as ONE MMA of width 2*BN, then a_lo x w_hi     (3 MMA slots / k-step)
+//   bf16 hi + bf16 lo (train) : same, full fp32 range
+//   fp16 hi + 8-bit cross     : a_hi x w_hi, then ONE e4m3 MMA of K = 32 for both cross terms        (2 MMA slots / k-step)
+// An experimental CTA-pair (cta_group::2) variant shares the weight tile between two CTAs (NSM_CG2=1).
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>

@@ -1,5 +1,6 @@
-// HBM-streaming kernels (see stream_kernels.cuh).  All are bandwidth-bound: vectorised 16-byte accesses, one pass
-// over each tensor, per-channel parameters broadcast from shared memory, warp-shuffle reductions.
+// HBM-streaming kernels (see stream_kernels.cuh): layout / packing, up-sampling, loss, statistics -- vectorised 16-byte
+// accesses, one pass over each tensor -- and the 16-channel head / tail stages of the network, whose two small
+// convolutions each run on the warp-level tensor path (mma.sync) inside one kernel.
 #include <stdio.h>
 
 #include "nsm_common.cuh"
