@@ -123,21 +123,31 @@ struct ConvKernelParams {
 
 // CG = 2: CTA pair (cta_group::2).  The pair computes two pixel tiles (M = 256) against one weight tile of which every CTA
 // holds half the rows: per MAC a CTA moves A + B/2 instead of A + B through L2 -> shared memory.
-template <int BN, int NP, int CG = 1>
+template <int BN, int NP, int CG = 1, bool HALO = false>
 struct GemmCfg {
+  // HALO (3x3 only): the pixel tile is 16 rows x 8 columns and ONE box of (16+2) x (8+2) pixels per 64-channel block
+  // serves all nine taps: the UMMA swizzle follows absolute shared-memory addresses (profiles/README.md), so the A
+  // descriptor of tap (dy, dx) simply starts (dy*10 + dx) rows into the box and steps 10 rows per 8-pixel group.
+  static constexpr int TW = HALO ? 8 : kTileW, TH = HALO ? 16 : kTileH;
+  static constexpr int HALO_PITCH = TW + 2;                          // pixels per halo row
+  static constexpr int HALO_BYTES = (TH + 2) * HALO_PITCH * 128;     // one plane, one channel block
+  static constexpr int HALO_STRIDE = (HALO_BYTES + 1023) / 1024 * 1024;
   static constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 elements (2 B)
   static constexpr int B_BYTES = (BN / CG) * 128;   // this CTA's rows of the weight tile x 64 elements
-  static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
+  // ring stage: A + B, or (HALO) B only next to two halo buffers
+  static constexpr int STAGE_BYTES = HALO ? NP * B_BYTES : NP * (A_BYTES + B_BYTES);
+  static constexpr int A_REGION = HALO ? 2 * NP * HALO_STRIDE : 0;
   // 8 epilogue warps x 4 KB staging tiles for the TMA stores of the output (32 pixels x 32 channels x {hi, lo})
   static constexpr int STAGING_BYTES = 8 * 4096;
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STAGING_BYTES;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STAGING_BYTES - A_REGION;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // fp32 mode keeps two accumulators per stage: [main = a_hi*w_hi | cross = a_hi*w_lo + a_lo*w_hi]
   static constexpr int ACC_COLS = NP * BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = A_REGION + STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(!(HALO && CG == 2), "halo tiles and CTA pairs are not combined");
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two <= 512");
 };
 
@@ -148,6 +158,7 @@ struct GemmCfg {
 constexpr int kChunkKBDefault = 16;
 constexpr int kConvThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two column halves x four lane quarters)
 
+template <int TW, int TH>
 __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item, int& n, int& y0, int& x0,
                                             int& nb) {
   nb = item % p.n_blocks;
@@ -156,8 +167,8 @@ __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item,
   t /= p.tiles_x;
   const int ty = t % p.tiles_y;
   n = t / p.tiles_y;
-  y0 = ty * kTileH;
-  x0 = tx * kTileW;
+  y0 = ty * TH;
+  x0 = tx * TW;
 }
 
 // Where one epilogue warp's 32 pixels (2 patch rows x 16 columns) go: the output leaves through TMA stores from a 4 KB
@@ -202,7 +213,8 @@ __device__ __forceinline__ void decode_pair(const ConvKernelParams& p, int pi, i
 }
 
 // Epilogue math + stores for 32 consecutive output channels [cb, cb+32) of one pixel (one thread).
-template <int NP>
+// TW = tile width: a warp's 32 pixels are 32/TW rows of TW columns (lane = row * TW + column).
+template <int NP, int TW>
 __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelParams& p, int cb, bool valid,
                                               size_t pix, EpiTile& et, int g, int ng, double& st1, double& st2) {
   const ConvEpilogue& ep = p.ep;
@@ -334,18 +346,19 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
       bulk_commit();
     }
   }
-  if (ep.pool.p[0]) {  // warp-uniform: AvgPool2d(2) over (lane^1, lane^16) partners; the anchors are lanes 0,2,..,14
+  if (ep.pool.p[0]) {  // warp-uniform: AvgPool2d(2) over (lane^1, lane^TW) partners; anchors: even column of an even row
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float s = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      s += __shfl_xor_sync(0xffffffffu, s, TW);
       s *= 0.25f;
       v[j] = ep.round_bf16 ? rbf(s) : s;
     }
     if (lane == 0) bulk_wait_read0();
     __syncwarp();
-    if ((lane & 17) == 0) {
-      const int r = lane >> 1;  // pooled column inside the warp's 8-pixel pooled row
+    if ((lane & (TW | 1)) == 0) {
+      // pooled pixel index inside the warp's pooled box (TW/2 columns x 16/TW rows, x fastest)
+      const int r = TW == 16 ? (lane >> 1) : (((lane >> 4) << 2) | ((lane >> 1) & 3));
       const uint32_t row = slot + r * 64;
       const uint32_t sw = (r >> 1) & 3;
 #pragma unroll
@@ -379,7 +392,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
   }
 }
 
-template <int BN, int NP, int CG>
+template <int BN, int NP, int CG, bool HALO>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -387,7 +400,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                  const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ ConvKernelParams p) {
-  using Cfg = GemmCfg<BN, NP, CG>;
+  using Cfg = GemmCfg<BN, NP, CG, HALO>;
+  constexpr int TW = Cfg::TW, TH = Cfg::TH;
   const int cta_rank = CG == 2 ? int(cluster_ctarank()) : 0;
   // work items of this CTA (pair): first, stride, count
   const int it_first = CG == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
@@ -395,7 +409,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int it_count = CG == 2 ? p.total_pairs : p.total_items;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // 1024-byte aligned (SWIZZLE_128B)
+  uint8_t* smem_base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // 1024-byte aligned (SWIZZLE_128B)
+  uint8_t* halo = smem_base;                      // HALO: two buffers of NP planes, HALO_STRIDE bytes each
+  uint8_t* smem = smem_base + Cfg::A_REGION;      // the stage ring
   uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
@@ -403,7 +419,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;   // [8 epilogue warps][2 slots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
+  uint64_t* afull_bar = res_bar + 16;   // HALO: the two halo buffers
+  uint64_t* aempty_bar = afull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -436,6 +454,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&tempty_bar[a], 8 * CG);   // the leader's copy collects the epilogue warps of both CTAs
     }
     for (int a = 0; a < 16; ++a) mbar_init(&res_bar[a], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&afull_bar[a], 1);
+      mbar_init(&aempty_bar[a], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -455,12 +477,42 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (HALO && lane == 0) {
+      // one (TH+2) x (TW+2)-pixel box per 64-channel block feeds all nine taps; the ring carries the weight tiles
+      uint32_t stage = 0, phase = 0, ab = 0, aphase = 0;
+      for (int item = it_first; item < it_count; item += it_step) {
+        int n, y0, x0, nb;
+        decode_item<TW, TH>(p, item, n, y0, x0, nb);
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(&aempty_bar[ab], aphase ^ 1);
+          mbar_expect_tx(&afull_bar[ab], NP * Cfg::HALO_BYTES);
+          uint8_t* ha = halo + ab * NP * Cfg::HALO_STRIDE;
+          tma_load_4d(ha, &tmA0, &afull_bar[ab], kc * kKChunk, x0 - 1, y0 - 1, n);
+          if (NP == 2) tma_load_4d(ha + Cfg::HALO_STRIDE, &tmA1, &afull_bar[ab], kc * kKChunk, x0 - 1, y0 - 1, n);
+          if (++ab == 2) {
+            ab = 0;
+            aphase ^= 1;
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            uint8_t* sb = smem + stage * Cfg::STAGE_BYTES;
+            tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, nb * BN);
+            if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, nb * BN);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    if (!HALO && lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int item = it_first; item < it_count; item += it_step) {
         int n, y0, x0, nb;
         if (CG == 2) decode_pair(p, item, cta_rank, n, y0, x0, nb);
-        else decode_item(p, item, n, y0, x0, nb);
+        else decode_item<TW, TH>(p, item, n, y0, x0, nb);
         const int brow = nb * BN + cta_rank * (BN / CG);   // this CTA's rows of the weight tile
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
@@ -495,7 +547,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && cta_rank == 0) {   // CTA pairs: the leader issues for both
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, ab = 0, aphase = 0;
       for (int item = it_first; item < it_count; item += it_step) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_len) {
           const int kb1 = kb0 + chunk_len < num_kb ? kb0 + chunk_len : num_kb;
@@ -504,19 +556,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
           const uint32_t d_cross = d_main + BN;  // fp32 mode only
           for (int kb = kb0; kb < kb1; ++kb) {
+            const int tap = HALO ? kb % 9 : 0;   // HALO: k-blocks run channel-block major, tap minor
+            if (HALO && tap == 0) {
+              mbar_wait(&afull_bar[ab], aphase);
+              tc_fence_after();
+            }
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint32_t b_hi = a_hi + NP * Cfg::A_BYTES;
+            // HALO: the A rows of tap (dy, dx) start (dy * pitch + dx) pixel rows into the halo box; 8-pixel groups (one
+            // tile row each) follow at a stride of one halo row
+            const uint32_t a_hi = HALO ? smem_u32(halo + ab * NP * Cfg::HALO_STRIDE) +
+                                             uint32_t((tap / 3) * Cfg::HALO_PITCH + tap % 3) * 128u
+                                       : smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t a_plane = HALO ? Cfg::HALO_STRIDE : Cfg::A_BYTES;   // distance hi plane -> second plane
+            const uint32_t a_sbo = HALO ? Cfg::HALO_PITCH * 128 : 1024;
+            const uint32_t b_hi = HALO ? smem_u32(smem + stage * Cfg::STAGE_BYTES)
+                                       : smem_u32(smem + stage * Cfg::STAGE_BYTES) + NP * Cfg::A_BYTES;
 #pragma unroll
             for (int k = 0; k < kKChunk / 16; ++k) {
               const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;  // first MMA of a chunk overwrites
-              const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, 1024);
+              const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, a_sbo);
               const uint64_t db_hi = make_desc_sw128(b_hi + k * 32, 16, 1024);
               if (CG == 2) {
                 umma_bf16_pair(d_main, da_hi, db_hi, p.idesc_hi, accum);
                 if (NP == 2) {
-                  const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
+                  const uint64_t da_lo = make_desc_sw128(a_hi + a_plane + k * 32, 16, a_sbo);
                   const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
                   if (p.x8) {
                     umma_f8_pair(d_cross, da_lo, db_lo, p.idesc_hi, accum);
@@ -530,7 +594,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 // a_hi x [w_hi | w_lo] is a single MMA of width 2*BN that fills main (columns [0,BN)) and cross
                 // ([BN,2BN)) at once; a_lo x w_hi then accumulates into cross.  Same tensor cycles as three MMAs of
                 // width BN, but a_hi is fetched from shared memory once instead of twice.
-                const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
+                const uint64_t da_lo = make_desc_sw128(a_hi + a_plane + k * 32, 16, a_sbo);
                 if (p.x8) {
                   // 8-bit cross planes: one e4m3 MMA of K = 32 (16 channels x two halves) yields both cross terms at
                   // twice the fp16 rate -> two MMA slots per k-step instead of three
@@ -551,6 +615,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               stage = 0;
               phase ^= 1;
             }
+            if (HALO && tap == 8) {   // all nine taps of this channel block issued: the halo buffer may be refilled
+              umma_commit(&aempty_bar[ab]);
+              if (++ab == 2) {
+                ab = 0;
+                aphase ^= 1;
+              }
+            }
           }
           if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
           else umma_commit(&tfull_bar[acc]);  // chunk accumulator complete -> epilogue
@@ -566,7 +637,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;  // pixel index inside the patch
-    const int ly = row / kTileW, lx = row % kTileW;
+    const int ly = row / TW, lx = row % TW;
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + half * HB;
     uint32_t acc = 0, acc_phase = 0;
     EpiTile et;
@@ -596,7 +667,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int item = it_first; item < it_count; item += it_step) {
       int n, y0, x0, nb;
       if (CG == 2) decode_pair(p, item, cta_rank, n, y0, x0, nb);
-      else decode_item(p, item, n, y0, x0, nb);
+      else decode_item<TW, TH>(p, item, n, y0, x0, nb);
       if (nb != st_nb) {
         flush_stats(st_nb);
         st_nb = nb;
@@ -605,7 +676,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const bool valid = (y < p.H) && (x < p.W) && (n < p.N);
       const size_t pix = (size_t(n) * p.H + y) * p.W + x;
       const int cbase = nb * BN + half * HB;
-      et.x0 = x0; et.y0 = y0 + 2 * q; et.n = n;
+      et.x0 = x0; et.y0 = y0 + (32 / TW) * q; et.n = n;   // a warp's 32 pixels = 32/TW tile rows
       if (p.ep.residual.p[0]) {
         // request the skip values of the first group(s) now: they land in the staging slots while the MMAs run
         if (lane == 0) {
@@ -633,7 +704,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, et, c0 / 32, NG, st1[c0 / 32], st2[c0 / 32]);
+          epilogue_cols<NP, TW>(v, p, cbase + c0, valid, pix, et, c0 / 32, NG, st1[c0 / 32], st2[c0 / 32]);
         }
         tc_fence_before();
         __syncwarp();
@@ -675,7 +746,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = sum[c0 + j];
-          epilogue_cols<NP>(v, p, cbase + c0, valid, pix, et, c0 / 32, NG, st1[c0 / 32], st2[c0 / 32]);
+          epilogue_cols<NP, TW>(v, p, cbase + c0, valid, pix, et, c0 / 32, NG, st1[c0 / 32], st2[c0 / 32]);
         }
       }
     }
@@ -696,10 +767,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NP, int CG = 1>
+template <int BN, int NP, int CG = 1, bool HALO = false>
 static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, NP, CG>;
-  auto kern = conv_gemm_kernel<BN, NP, CG>;
+  using Cfg = GemmCfg<BN, NP, CG, HALO>;
+  auto kern = conv_gemm_kernel<BN, NP, CG, HALO>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -779,13 +850,19 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   // between the two SMs that 256-wide tiles would amortise -- but hi+lo modes have no TMEM left for 256-wide double-buffered
   // accumulators.
   static const bool cg2_on = getenv("NSM_CG2") != nullptr;
-  const int m_tiles = s.N * ((s.W + kTileW - 1) / kTileW) * ((s.H + kTileH - 1) / kTileH);
+  // halo tiles for 3x3 convolutions (EXPERIMENTAL, NSM_HALO=1): parity-green and 45 % less L2 -> shared-memory traffic, but
+  // 0-7 % slower than one box per tap -- the activation boxes were never the expensive part of the feed (every CTA reads
+  // its own), the weight tiles are (eighteen CTAs read the same tile at the same time); not combined with pairs
+  static const bool halo_on = getenv("NSM_HALO") != nullptr;
+  const bool halo = s.taps == 9 && halo_on && !cg2_on;
+  const int TW = halo ? 8 : kTileW, TH = halo ? 16 : kTileH;
+  const int m_tiles = s.N * ((s.W + TW - 1) / TW) * ((s.H + TH - 1) / TH);
   const int CG = (cg2_on && BN == 128 && (s.fmt == kFmtBf16 || s.fmt == kFmtF16X8) && m_tiles >= 2) ? 2 : 1;
   CUtensorMap maps[10];  // A hi/lo, B hi/lo, output hi/lo, pooled output hi/lo, skip hi/lo
   memset(maps, 0, sizeof(maps));
   const uint64_t adims[4] = {uint64_t(s.Cin), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
   const uint64_t astr[3] = {uint64_t(s.Cin) * 2, uint64_t(s.W) * s.Cin * 2, uint64_t(s.H) * s.W * s.Cin * 2};
-  const uint32_t abox[4] = {uint32_t(kKChunk), uint32_t(kTileW), uint32_t(kTileH), 1};
+  const uint32_t abox[4] = {uint32_t(kKChunk), uint32_t(halo ? TW + 2 : TW), uint32_t(halo ? TH + 2 : TH), 1};
   const uint64_t K = uint64_t(s.taps) * s.Cin;
   const uint64_t bdims[2] = {K, uint64_t(s.Cout)};
   const uint64_t bstr[1] = {K * 2};
@@ -806,11 +883,11 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   // output side: 64-byte swizzled boxes of 32 channels x (2 x 16) pixels = what one epilogue warp stages per plane
   const uint64_t odims[4] = {uint64_t(s.Cout), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
   const uint64_t ostr[3] = {uint64_t(s.Cout) * 2, uint64_t(s.W) * s.Cout * 2, uint64_t(s.H) * s.W * s.Cout * 2};
-  const uint32_t obox[4] = {32, uint32_t(kTileW), 2, 1};
+  const uint32_t obox[4] = {32, uint32_t(TW), uint32_t(32 / TW), 1};   // one epilogue warp = 32 pixels
   const uint64_t pdims[4] = {uint64_t(s.Cout), uint64_t(s.W / 2), uint64_t(s.H / 2), uint64_t(s.N)};
   const uint64_t pstr[3] = {uint64_t(s.Cout) * 2, uint64_t(s.W / 2) * s.Cout * 2,
                             uint64_t(s.H / 2) * (s.W / 2) * s.Cout * 2};
-  const uint32_t pbox[4] = {32, uint32_t(kTileW / 2), 1, 1};
+  const uint32_t pbox[4] = {32, uint32_t(TW / 2), uint32_t(16 / TW), 1};
   if (ep.pool.p[0] && (s.W < 2 || s.H < 2)) {
     set_error("conv_gemm: pooled output requested for a %dx%d image", s.H, s.W);
     return 1;
@@ -844,8 +921,8 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   }
   ConvKernelParams kp;
   kp.N = s.N; kp.H = s.H; kp.W = s.W; kp.Cin = s.Cin; kp.Cout = s.Cout; kp.taps = s.taps;
-  kp.tiles_x = (s.W + kTileW - 1) / kTileW;
-  kp.tiles_y = (s.H + kTileH - 1) / kTileH;
+  kp.tiles_x = (s.W + TW - 1) / TW;
+  kp.tiles_y = (s.H + TH - 1) / TH;
   kp.n_blocks = s.Cout / BN;
   kp.total_items = s.N * kp.tiles_x * kp.tiles_y * kp.n_blocks;
   kp.total_pairs = ((m_tiles + 1) / 2) * kp.n_blocks;
@@ -865,6 +942,15 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     return launch_t<128, 2, 2>(maps, kp, 2 * pairs, stream);
   }
   const int grid = kp.total_items < num_sms() ? kp.total_items : num_sms();
+  if (halo) {
+    if (planes == 1) {
+      if (BN == 256) return launch_t<256, 1, 1, true>(maps, kp, grid, stream);
+      if (BN == 128) return launch_t<128, 1, 1, true>(maps, kp, grid, stream);
+      return launch_t<64, 1, 1, true>(maps, kp, grid, stream);
+    }
+    if (BN == 128) return launch_t<128, 2, 1, true>(maps, kp, grid, stream);
+    return launch_t<64, 2, 1, true>(maps, kp, grid, stream);
+  }
   if (planes == 1) {
     if (BN == 256) return launch_t<256, 1>(maps, kp, grid, stream);
     if (BN == 128) return launch_t<128, 1>(maps, kp, grid, stream);

@@ -177,9 +177,10 @@ for mode, (N, H, W, C, k) in [(nsm.MODE_BF16, (1, 23, 37, 128, 3)), (nsm.FMT_F16
 print("pairs ok")
 ''' % (os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pcss-unet_b200"),
        os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    env = dict(os.environ, NSM_CG2="1")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "pairs ok" in r.stdout, r.stdout + r.stderr
+    for flag in ("NSM_CG2", "NSM_HALO"):     # the halo-tile variant (one activation box for all nine taps) likewise
+        env = dict(os.environ, **{flag: "1"})
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "pairs ok" in r.stdout, flag + "\n" + r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("shape", [(2, 128, 67, 120, 135, 240), (1, 64, 20, 28, 20, 28), (1, 512, 5, 7, 10, 14)],
