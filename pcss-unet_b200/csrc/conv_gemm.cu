@@ -765,6 +765,237 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// 256-wide tiles for the 8-bit-cross format (column blocks of 256 output channels).
+//
+// The 128-wide hi+lo kernel above is bound by shared-memory traffic: a 128-wide MMA needs 8 KB of operands for 64 cycles
+// of math, and issuing the same MMAs 256 wide costs only 0.62x the time per MAC (profiles/README.md).  A 256-wide tile
+// needs main + cross accumulators of 256 columns = all 512 TMEM columns, so the accumulators are NOT double-buffered here:
+// the issuer waits while the epilogue warps drain a chunk (~10 % of a chunk's MMA time).  K blocks are 32 channels (64-byte
+// rows, 64-byte swizzle) so that four stages of A (2 x 8 KB) + B (2 x 16 KB) fit next to the epilogue staging tiles.
+// ------------------------------------------------------------------------------------------------
+struct WideCfg {
+  static constexpr int BN = 256, BK = 32;
+  static constexpr int A_BYTES = 128 * 64;     // 128 pixels x 32 channels x 2 B (or 64 e4m3 bytes)
+  static constexpr int B_BYTES = BN * 64;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = 4;
+  static constexpr int STAGING_BYTES = 8 * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                      const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                      const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+                      const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
+                      const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
+                      const __grid_constant__ ConvKernelParams p) {
+  using Cfg = WideCfg;
+  constexpr int BN = Cfg::BN, NP = 2, TW = kTileW, TH = kTileH;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint64_t* res_bar = tempty_bar + 1;   // [8 epilogue warps][2 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB0); tma_prefetch_desc(&tmB1);
+    if (p.ep.out.p[0]) { tma_prefetch_desc(&tmO0); tma_prefetch_desc(&tmO1); }
+    if (p.ep.pool.p[0]) { tma_prefetch_desc(&tmP0); tma_prefetch_desc(&tmP1); }
+    if (p.ep.residual.p[0]) { tma_prefetch_desc(&tmR0); tma_prefetch_desc(&tmR1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 8);
+    for (int a = 0; a < 16; ++a) mbar_init(&res_bar[a], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kc_per_tap = p.Cin / Cfg::BK;
+  const int num_kb = p.taps * kc_per_tap;
+  // accumulation chunks of the same K extent as in the 128-wide kernel (chunk_kb counts 64-channel blocks)
+  const int chunk_kb = 2 * p.chunk_kb;
+  const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
+  const int chunk_len = (num_kb + num_chunks - 1) / num_chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int n, y0, x0, nb;
+        decode_item<TW, TH>(p, item, n, y0, x0, nb);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
+          const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < kc_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + 2 * Cfg::A_BYTES;
+            tma_load_4d(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
+            tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
+            tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
+            tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      const uint32_t d_main = tmem_base, d_cross = tmem_base + BN;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_len) {
+          const int kb1 = kb0 + chunk_len < num_kb ? kb0 + chunk_len : num_kb;
+          mbar_wait(tempty_bar, acc_phase ^ 1);   // the epilogue warps have drained the previous chunk
+          acc_phase ^= 1;
+          tc_fence_after();
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              // main: a fresh accumulation per chunk (truncating tensor-core adds).  cross: one
+              // accumulation over the whole K -- its terms are 2^-12 of the result, 576 truncations cost nothing -- so the
+              // per-chunk drain touches only the main half of TMEM
+              const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
+              umma_bf16(d_main, make_desc_sw64(a_hi + k * 32), make_desc_sw64(b_hi + k * 32), p.idesc_hi, accum);
+              umma_f8(d_cross, make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32),
+                      make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32), p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(tfull_bar);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    constexpr int HB = BN / 2;      // 128 columns per epilogue warp
+    constexpr int NG = HB / 32;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int ly = row / TW, lx = row % TW;
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + half * HB;
+    uint32_t acc_phase = 0;
+    EpiTile et;
+    et.stg = smem_u32(staging) + (warp - 2) * 4096;
+    et.out[0] = &tmO0; et.out[1] = &tmO1;
+    et.pool[0] = &tmP0; et.pool[1] = &tmP1;
+    et.res[0] = &tmR0; et.res[1] = &tmR1;
+    et.rbar = res_bar + 2 * (warp - 2);
+    et.rphase[0] = et.rphase[1] = 0;
+    double st1[NG], st2[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) st1[k] = st2[k] = 0.0;
+    int st_nb = -1;
+    auto flush_stats = [&](int nb_old) {
+      if (p.ep.stats == nullptr || nb_old < 0) return;
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        const int c = nb_old * BN + half * HB + 32 * k + lane;
+        if (st1[k] != 0.0) atomicAdd(p.ep.stats + c, st1[k]);
+        if (st2[k] != 0.0) atomicAdd(p.ep.stats + p.Cout + c, st2[k]);
+        st1[k] = st2[k] = 0.0;
+      }
+    };
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int n, y0, x0, nb;
+      decode_item<TW, TH>(p, item, n, y0, x0, nb);
+      if (nb != st_nb) {
+        flush_stats(st_nb);
+        st_nb = nb;
+      }
+      const int y = y0 + ly, x = x0 + lx;
+      const bool valid = (y < p.H) && (x < p.W);
+      const size_t pix = (size_t(n) * p.H + y) * p.W + x;
+      const int cbase = nb * BN + half * HB;
+      et.x0 = x0; et.y0 = y0 + 2 * q; et.n = n;
+      if (p.ep.residual.p[0] && lane == 0) {
+        bulk_wait_read0();
+        epi_issue_residual<NP>(et, 0, cbase);
+      }
+      float sum[HB];
+#pragma unroll
+      for (int j = 0; j < HB; ++j) sum[j] = 0.f;
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(tfull_bar, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < HB; c0 += 16) {
+          uint32_t r0[16];
+          tmem_ld_32x16(lane_addr + c0, r0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(r0[j]);
+        }
+        if (ch == num_chunks - 1) {   // the cross accumulator holds the whole K by now
+#pragma unroll
+          for (int c0 = 0; c0 < HB; c0 += 16) {
+            uint32_t r1[16];
+            tmem_ld_32x16(lane_addr + BN + c0, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[c0 + j] = fmaf(__uint_as_float(r1[j]), p.cross_scale, sum[c0 + j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < HB; c0 += 32) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = sum[c0 + j];
+        epilogue_cols<NP, TW>(v, p, cbase + c0, valid, pix, et, c0 / 32, NG, st1[c0 / 32], st2[c0 / 32]);
+      }
+    }
+    flush_stats(st_nb);
+    if (lane == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
 template <int BN, int NP, int CG = 1, bool HALO = false>
@@ -840,7 +1071,12 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
               s.Cin, s.Cout, s.taps, s.fmt);
     return 1;
   }
-  const int BN = conv_gemm_pick_bn(s);
+  int BN = conv_gemm_pick_bn(s);
+  // 8-bit-cross operands with column blocks of 256: conv_gemm_wide_kernel (NSM_NO_WIDE=1: the 128-wide kernel)
+  static const bool wide_off = getenv("NSM_NO_WIDE") != nullptr;
+  static const bool exp_on = getenv("NSM_CG2") != nullptr || getenv("NSM_HALO") != nullptr;
+  const bool wide = s.fmt == kFmtF16X8 && s.Cout % 256 == 0 && s.Cin % 32 == 0 && !wide_off && !exp_on;
+  if (wide) BN = 256;
   // CTA pairs (EXPERIMENTAL, NSM_CG2=1): bf16 and 8-bit-cross operands (the wide hi|lo MMA of the other formats needs the
   // whole weight tile in one CTA), BN = 128 tiles, at least two pixel tiles.  Verified by the parity tests, moves 25 % fewer
   // bytes through L2 -> shared memory (ncu: 14.5 GB against 19.3 GB for conv6 3x3), but is 30 % SLOWER at the moment: the
@@ -862,19 +1098,21 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   memset(maps, 0, sizeof(maps));
   const uint64_t adims[4] = {uint64_t(s.Cin), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
   const uint64_t astr[3] = {uint64_t(s.Cin) * 2, uint64_t(s.W) * s.Cin * 2, uint64_t(s.H) * s.W * s.Cin * 2};
-  const uint32_t abox[4] = {uint32_t(kKChunk), uint32_t(halo ? TW + 2 : TW), uint32_t(halo ? TH + 2 : TH), 1};
+  const uint32_t kblk = wide ? WideCfg::BK : kKChunk;   // channels per k-block = 64- or 128-byte operand rows
+  const int op_swz = wide ? 64 : 128;
+  const uint32_t abox[4] = {kblk, uint32_t(halo ? TW + 2 : TW), uint32_t(halo ? TH + 2 : TH), 1};
   const uint64_t K = uint64_t(s.taps) * s.Cin;
   const uint64_t bdims[2] = {K, uint64_t(s.Cout)};
   const uint64_t bstr[1] = {K * 2};
-  const uint32_t bbox[2] = {uint32_t(kKChunk), uint32_t(BN / CG)};
+  const uint32_t bbox[2] = {kblk, uint32_t(BN / CG)};
   const int planes = fmt_planes(s.fmt);
   for (int pl = 0; pl < planes; ++pl) {
     if (!in.p[pl] || !w.p[pl]) {
       set_error("conv_gemm: null operand plane %d", pl);
       return 1;
     }
-    if (encode_tmap_tiled(&maps[pl], in.p[pl], 4, adims, astr, abox, 2)) return 1;
-    if (encode_tmap_tiled(&maps[2 + pl], w.p[pl], 2, bdims, bstr, bbox, 2)) return 1;
+    if (encode_tmap_tiled(&maps[pl], in.p[pl], 4, adims, astr, abox, 2, op_swz)) return 1;
+    if (encode_tmap_tiled(&maps[2 + pl], w.p[pl], 2, bdims, bstr, bbox, 2, op_swz)) return 1;
   }
   if (planes == 1) {
     maps[1] = maps[0];
@@ -936,6 +1174,28 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.idesc_hi = make_idesc_f16(128 * CG, BN, ef, ef, 0, 0);
   kp.idesc_wide = planes == 2 ? make_idesc_f16(128, 2 * BN, ef, ef, 0, 0) : kp.idesc_hi;
   kp.ep = ep;
+  if (wide) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           WideCfg::SMEM_BYTES);
+      if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(conv_gemm_wide, %d B smem): %s", WideCfg::SMEM_BYTES, cudaGetErrorString(e));
+        return 1;
+      }
+      attr_set = true;
+    }
+    const int g = kp.total_items < num_sms() ? kp.total_items : num_sms();
+    conv_gemm_wide_kernel<<<g, kConvThreads, WideCfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4],
+                                                                            maps[5], maps[6], maps[7], maps[8], maps[9], kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("conv_gemm_wide launch failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    count_launch();
+    return 0;
+  }
   if (CG == 2) {
     const int pairs = kp.total_pairs < num_sms() / 2 ? kp.total_pairs : num_sms() / 2;
     if (planes == 1) return launch_t<128, 1, 2>(maps, kp, 2 * pairs, stream);
