@@ -784,6 +784,9 @@ struct WideCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// MC = 2: two CTAs (a cluster) work on two pixel tiles of the same column block; each fetches HALF of the weight tile and
+// multicasts it into both -- a CTA then has 32 KB instead of 48 KB of TMA requests in flight per k-block.
+template <int MC>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -793,6 +796,10 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
                       const __grid_constant__ ConvKernelParams p) {
   using Cfg = WideCfg;
   constexpr int BN = Cfg::BN, NP = 2, TW = kTileW, TH = kTileH;
+  const int cta_rank = MC > 1 ? int(cluster_ctarank()) : 0;
+  const int it_first = int(blockIdx.x) / MC, it_step = int(gridDim.x) / MC;
+  const int it_count = MC > 1 ? p.total_pairs : p.total_items;
+  constexpr unsigned short kAllCtas = (unsigned short)((1u << MC) - 1);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -816,7 +823,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     if (p.ep.residual.p[0]) { tma_prefetch_desc(&tmR0); tma_prefetch_desc(&tmR1); }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC);   // free once every CTA that receives multicast slices in it has consumed it
     }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 8);
@@ -825,7 +832,8 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
-  __syncthreads();
+  if (MC > 1) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -840,9 +848,10 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = it_first; item < it_count; item += it_step) {
         int n, y0, x0, nb;
-        decode_item<TW, TH>(p, item, n, y0, x0, nb);
+        if (MC > 1) decode_pair(p, item, cta_rank, n, y0, x0, nb);
+        else decode_item<TW, TH>(p, item, n, y0, x0, nb);
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
           const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
@@ -853,8 +862,16 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             uint8_t* sb = sa + 2 * Cfg::A_BYTES;
             tma_load_4d(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
             tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
-            tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
-            tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
+            if (MC > 1) {   // this CTA's slice of the weight rows, into every CTA of the cluster
+              const int rows = BN / MC;
+              uint8_t* sl = sb + cta_rank * rows * 64;
+              tma_load_2d_mc(sl, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN + cta_rank * rows, kAllCtas);
+              tma_load_2d_mc(sl + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK,
+                             nb * BN + cta_rank * rows, kAllCtas);
+            } else {
+              tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
+              tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
+            }
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -868,7 +885,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc_phase = 0;
       const uint32_t d_main = tmem_base, d_cross = tmem_base + BN;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = it_first; item < it_count; item += it_step) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_len) {
           const int kb1 = kb0 + chunk_len < num_kb ? kb0 + chunk_len : num_kb;
           mbar_wait(tempty_bar, acc_phase ^ 1);   // the epilogue warps have drained the previous chunk
@@ -889,7 +906,8 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
               umma_f8(d_cross, make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32),
                       make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32), p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (MC > 1) umma_commit_mc(&empty_bar[stage], kAllCtas);
+            else umma_commit(&empty_bar[stage]);
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -930,15 +948,16 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         st1[k] = st2[k] = 0.0;
       }
     };
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    for (int item = it_first; item < it_count; item += it_step) {
       int n, y0, x0, nb;
-      decode_item<TW, TH>(p, item, n, y0, x0, nb);
+      if (MC > 1) decode_pair(p, item, cta_rank, n, y0, x0, nb);
+      else decode_item<TW, TH>(p, item, n, y0, x0, nb);
       if (nb != st_nb) {
         flush_stats(st_nb);
         st_nb = nb;
       }
       const int y = y0 + ly, x = x0 + lx;
-      const bool valid = (y < p.H) && (x < p.W);
+      const bool valid = (y < p.H) && (x < p.W) && (n < p.N);
       const size_t pix = (size_t(n) * p.H + y) * p.W + x;
       const int cbase = nb * BN + half * HB;
       et.x0 = x0; et.y0 = y0 + 2 * q; et.n = n;
@@ -988,7 +1007,8 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (MC > 1) cluster_sync_all();   // the peer may still multicast into this CTA / signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1077,6 +1097,9 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   static const bool exp_on = getenv("NSM_CG2") != nullptr || getenv("NSM_HALO") != nullptr;
   const bool wide = s.fmt == kFmtF16X8 && s.Cout % 256 == 0 && s.Cin % 32 == 0 && !wide_off && !exp_on;
   if (wide) BN = 256;
+  // ... in clusters of two CTAs that multicast halves of the weight tile to each other (NSM_NO_WIDE_MC=1: single CTAs)
+  static const bool wide_mc_on = getenv("NSM_NO_WIDE_MC") == nullptr;
+  const int wide_mc = (wide && wide_mc_on && s.N * ((s.W + kTileW - 1) / kTileW) * ((s.H + kTileH - 1) / kTileH) >= 8) ? 2 : 1;
   // CTA pairs (EXPERIMENTAL, NSM_CG2=1): bf16 and 8-bit-cross operands (the wide hi|lo MMA of the other formats needs the
   // whole weight tile in one CTA), BN = 128 tiles, at least two pixel tiles.  Verified by the parity tests, moves 25 % fewer
   // bytes through L2 -> shared memory (ncu: 14.5 GB against 19.3 GB for conv6 3x3), but is 30 % SLOWER at the moment: the
@@ -1104,7 +1127,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   const uint64_t K = uint64_t(s.taps) * s.Cin;
   const uint64_t bdims[2] = {K, uint64_t(s.Cout)};
   const uint64_t bstr[1] = {K * 2};
-  const uint32_t bbox[2] = {kblk, uint32_t(BN / CG)};
+  const uint32_t bbox[2] = {kblk, uint32_t(BN / (CG * wide_mc))};
   const int planes = fmt_planes(s.fmt);
   for (int pl = 0; pl < planes; ++pl) {
     if (!in.p[pl] || !w.p[pl]) {
@@ -1177,18 +1200,40 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   if (wide) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_gemm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            WideCfg::SMEM_BYTES);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_gemm_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg::SMEM_BYTES);
       if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute(conv_gemm_wide, %d B smem): %s", WideCfg::SMEM_BYTES, cudaGetErrorString(e));
         return 1;
       }
       attr_set = true;
     }
-    const int g = kp.total_items < num_sms() ? kp.total_items : num_sms();
-    conv_gemm_wide_kernel<<<g, kConvThreads, WideCfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4],
-                                                                            maps[5], maps[6], maps[7], maps[8], maps[9], kp);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = WideCfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    cudaError_t e;
+    if (wide_mc == 2) {
+      const int groups = kp.total_pairs < num_sms() / 2 ? kp.total_pairs : num_sms() / 2;
+      cfg.gridDim = dim3(2 * groups);
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, conv_gemm_wide_kernel<2>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
+                             maps[7], maps[8], maps[9], kp);
+    } else {
+      cfg.gridDim = dim3(kp.total_items < num_sms() ? kp.total_items : num_sms());
+      e = cudaLaunchKernelEx(&cfg, conv_gemm_wide_kernel<1>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
+                             maps[7], maps[8], maps[9], kp);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("conv_gemm_wide launch failed: %s", cudaGetErrorString(e));
       return 1;
