@@ -353,8 +353,8 @@ def run_b200(args):
                      "roofline_ms": max(t_tensor, t_hbm), "frac_of_roofline": max(t_tensor, t_hbm) / max(ms, 1e-9)}
     t_roof = sum(v["roofline_ms"] for v in layers.values())
     planes = 2 if precision == "fp32" else 1
-    roofline = {"kernel": f"conv_gemm_kernel<BN,{planes}> (tcgen05 implicit GEMM, {len(conv) // max(args.steps, 1)} "
-                          "launches/step)",
+    roofline = {"kernel": f"conv_gemm_kernel<BN,{planes}> + conv_gemm_wide_kernel (tcgen05 implicit GEMM, "
+                          f"{len(conv) // max(args.steps, 1)} launches/step)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"], "traffic": measured_traffic(),
                 "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json)",
