@@ -765,7 +765,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// 256-wide tiles for the hi+lo formats (column blocks of 256 output channels; 8-bit-cross and, for long K, 16-bit lo planes).
+// 256-wide tiles for the 8-bit-cross format (column blocks of 256 output channels).
 //
 // The 128-wide hi+lo kernel above is bound by shared-memory traffic: a 128-wide MMA needs 8 KB of operands for 64 cycles
 // of math, and issuing the same MMAs 256 wide costs only 0.62x the time per MAC (profiles/README.md).  A 256-wide tile
@@ -902,17 +902,9 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
               // accumulation over the whole K -- its terms are 2^-12 of the result, 576 truncations cost nothing -- so the
               // per-chunk drain touches only the main half of TMEM
               const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
-              const uint32_t caccum = (kb | k) != 0 ? 1u : 0u;
-              const uint64_t da_hi = make_desc_sw64(a_hi + k * 32), db_hi = make_desc_sw64(b_hi + k * 32);
-              const uint64_t da_lo = make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32);
-              const uint64_t db_lo = make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32);
-              umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
-              if (p.x8) {
-                umma_f8(d_cross, da_lo, db_lo, p.idesc_hi, caccum);
-              } else {   // 16-bit lo planes: the two cross products as two 256-wide MMAs
-                umma_bf16(d_cross, da_hi, db_lo, p.idesc_hi, caccum);
-                umma_bf16(d_cross, da_lo, db_hi, p.idesc_hi, 1u);
-              }
+              umma_bf16(d_main, make_desc_sw64(a_hi + k * 32), make_desc_sw64(b_hi + k * 32), p.idesc_hi, accum);
+              umma_f8(d_cross, make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32),
+                      make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32), p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
             }
             if (MC > 1) umma_commit_mc(&empty_bar[stage], kAllCtas);
             else umma_commit(&empty_bar[stage]);
@@ -1103,9 +1095,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   // 8-bit-cross operands with column blocks of 256: conv_gemm_wide_kernel (NSM_NO_WIDE=1: the 128-wide kernel)
   static const bool wide_off = getenv("NSM_NO_WIDE") != nullptr;
   static const bool exp_on = getenv("NSM_CG2") != nullptr || getenv("NSM_HALO") != nullptr;
-  // (also the 16-bit hi+lo formats when K is long: the single-buffered accumulators cost a drain per tile)
-  const bool wide = s.Cout % 256 == 0 && s.Cin % 32 == 0 && !wide_off && !exp_on &&
-                    (s.fmt == kFmtF16X8 || (fmt_planes(s.fmt) == 2 && s.taps * s.Cin >= 1024));
+  const bool wide = s.fmt == kFmtF16X8 && s.Cout % 256 == 0 && s.Cin % 32 == 0 && !wide_off && !exp_on;
   if (wide) BN = 256;
   // ... in clusters of two CTAs that multicast halves of the weight tile to each other (NSM_NO_WIDE_MC=1: single CTAs)
   static const bool wide_mc_on = getenv("NSM_NO_WIDE_MC") == nullptr;
