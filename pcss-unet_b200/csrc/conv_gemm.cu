@@ -773,20 +773,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // the issuer waits while the epilogue warps drain a chunk (~10 % of a chunk's MMA time).  K blocks are 32 channels (64-byte
 // rows, 64-byte swizzle) so that four stages of A (2 x 8 KB) + B (2 x 16 KB) fit next to the epilogue staging tiles.
 // ------------------------------------------------------------------------------------------------
+// (BN_ = 128 for layers with 128 output channels: same 32-channel ring, six finer stages and the weight-tile multicast;
+//  its MMAs stay 128 wide.)
+constexpr int kWideBK = 32;
+template <int BN_>
 struct WideCfg {
-  static constexpr int BN = 256, BK = 32;
+  static constexpr int BN = BN_, BK = kWideBK;
   static constexpr int A_BYTES = 128 * 64;     // 128 pixels x 32 channels x 2 B (or 64 e4m3 bytes)
   static constexpr int B_BYTES = BN * 64;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = 4;
   static constexpr int STAGING_BYTES = 8 * 4096;
+  static constexpr int STAGES = (227 * 1024 - 1024 - 512 - STAGING_BYTES) / STAGE_BYTES;   // 4 (BN 256) / 6 (BN 128)
+  static constexpr int TMEM_COLS = 2 * BN;     // main + cross, single-buffered
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(SMEM_BYTES <= 227 * 1024 && STAGES >= 3 && STAGES <= 8, "shared memory budget");
 };
 
 // MC = 2: two CTAs (a cluster) work on two pixel tiles of the same column block; each fetches HALF of the weight tile and
 // multicasts it into both -- a CTA then has 32 KB instead of 48 KB of TMA requests in flight per k-block.
-template <int MC>
+template <int BN_, int MC>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -794,7 +799,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
                       const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                       const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                       const __grid_constant__ ConvKernelParams p) {
-  using Cfg = WideCfg;
+  using Cfg = WideCfg<BN_>;
   constexpr int BN = Cfg::BN, NP = 2, TW = kTileW, TH = kTileH;
   const int cta_rank = MC > 1 ? int(cluster_ctarank()) : 0;
   const int it_first = int(blockIdx.x) / MC, it_step = int(gridDim.x) / MC;
@@ -830,7 +835,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     for (int a = 0; a < 16; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   if (MC > 1) cluster_sync_all();
   else __syncthreads();
@@ -1011,7 +1016,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -1095,8 +1100,11 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   // 8-bit-cross operands with column blocks of 256: conv_gemm_wide_kernel (NSM_NO_WIDE=1: the 128-wide kernel)
   static const bool wide_off = getenv("NSM_NO_WIDE") != nullptr;
   static const bool exp_on = getenv("NSM_CG2") != nullptr || getenv("NSM_HALO") != nullptr;
-  const bool wide = s.fmt == kFmtF16X8 && s.Cout % 256 == 0 && s.Cin % 32 == 0 && !wide_off && !exp_on;
-  if (wide) BN = 256;
+  // (the same kernel with 128-wide tiles is available -- NSM_WIDE128=1 -- but slower than the 64-channel double-buffered
+  //  kernel for conv8 3x3, 0.42 vs 0.34 ms: short K, so the single-buffered drain and the finer ring cost more than they save)
+  static const bool wide128 = getenv("NSM_WIDE128") != nullptr;
+  const bool wide = s.fmt == kFmtF16X8 && s.Cout % (wide128 ? 128 : 256) == 0 && s.Cin % 32 == 0 && !wide_off && !exp_on;
+  if (wide) BN = s.Cout % 256 == 0 ? 256 : 128;
   // ... in clusters of two CTAs that multicast halves of the weight tile to each other (NSM_NO_WIDE_MC=1: single CTAs)
   static const bool wide_mc_on = getenv("NSM_NO_WIDE_MC") == nullptr;
   const int wide_mc = (wide && wide_mc_on && s.N * ((s.W + kTileW - 1) / kTileW) * ((s.H + kTileH - 1) / kTileH) >= 8) ? 2 : 1;
@@ -1121,7 +1129,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   memset(maps, 0, sizeof(maps));
   const uint64_t adims[4] = {uint64_t(s.Cin), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
   const uint64_t astr[3] = {uint64_t(s.Cin) * 2, uint64_t(s.W) * s.Cin * 2, uint64_t(s.H) * s.W * s.Cin * 2};
-  const uint32_t kblk = wide ? WideCfg::BK : kKChunk;   // channels per k-block = 64- or 128-byte operand rows
+  const uint32_t kblk = wide ? kWideBK : kKChunk;   // channels per k-block = 64- or 128-byte operand rows
   const int op_swz = wide ? 64 : 128;
   const uint32_t abox[4] = {kblk, uint32_t(halo ? TW + 2 : TW), uint32_t(halo ? TH + 2 : TH), 1};
   const uint64_t K = uint64_t(s.taps) * s.Cin;
@@ -1198,25 +1206,11 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.idesc_wide = planes == 2 ? make_idesc_f16(128, 2 * BN, ef, ef, 0, 0) : kp.idesc_hi;
   kp.ep = ep;
   if (wide) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_gemm_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           WideCfg::SMEM_BYTES);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_gemm_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg::SMEM_BYTES);
-      if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(conv_gemm_wide, %d B smem): %s", WideCfg::SMEM_BYTES, cudaGetErrorString(e));
-        return 1;
-      }
-      attr_set = true;
-    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = WideCfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    cudaError_t e;
     if (wide_mc == 2) {
       const int groups = kp.total_pairs < num_sms() / 2 ? kp.total_pairs : num_sms() / 2;
       cfg.gridDim = dim3(2 * groups);
@@ -1226,16 +1220,30 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, conv_gemm_wide_kernel<2>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
-                             maps[7], maps[8], maps[9], kp);
     } else {
       cfg.gridDim = dim3(kp.total_items < num_sms() ? kp.total_items : num_sms());
-      e = cudaLaunchKernelEx(&cfg, conv_gemm_wide_kernel<1>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
-                             maps[7], maps[8], maps[9], kp);
     }
+    auto launch = [&](auto kern, int smem_bytes, bool& attr_set) -> cudaError_t {
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+      }
+      cfg.dynamicSmemBytes = smem_bytes;
+      return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], maps[8],
+                                maps[9], kp);
+    };
+    static bool attr_set[4] = {false, false, false, false};
+    cudaError_t e;
+    if (BN == 256)
+      e = wide_mc == 2 ? launch(conv_gemm_wide_kernel<256, 2>, WideCfg<256>::SMEM_BYTES, attr_set[0])
+                       : launch(conv_gemm_wide_kernel<256, 1>, WideCfg<256>::SMEM_BYTES, attr_set[1]);
+    else
+      e = wide_mc == 2 ? launch(conv_gemm_wide_kernel<128, 2>, WideCfg<128>::SMEM_BYTES, attr_set[2])
+                       : launch(conv_gemm_wide_kernel<128, 1>, WideCfg<128>::SMEM_BYTES, attr_set[3]);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
-      set_error("conv_gemm_wide launch failed: %s", cudaGetErrorString(e));
+      set_error("conv_gemm_wide<%d,%d> launch failed: %s", BN, wide_mc, cudaGetErrorString(e));
       return 1;
     }
     count_launch();
