@@ -38,6 +38,8 @@ import torch  # noqa: E402
 
 FLOP_PER_FRAME_1080P = 1550.0e9       # BASELINE.md section 3 (convolutions only, 2*MAC)
 H1080, W1080 = 1080, 1920
+# one string for both arms (the driver compares config.workload of the two lines)
+CFG1_WORKLOAD = "cfg1: U-Net inference, 1 synthetic 1920x1080 G-buffer frame per step, fp32, eval BatchNorm"
 
 
 def peaks():
@@ -152,38 +154,80 @@ def make_model(precision, dev, seed=42):
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU port of the reference path
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_forward_timer(P, H, W, steps, warmup, bf16=False):
-    import oracle
+def reference_unet():
+    """The reference's OWN `Unet` class (baseline/_ref/Unetmodel.py, an unmodified run-time copy of
+    /root/reference/Unetmodel.py staged by __graft_entry__.build()), seeded like main.py:73-92, BN buffers calibrated by one
+    train-mode pass of the reference itself.  Returns None when baseline/_ref is absent (then the oracle port is timed)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_harness
+        if not ref_harness.available():
+            return None
+        Unet = ref_harness.reference_unet_class()
+    except Exception:
+        return None
+    torch.manual_seed(42)
+    net = Unet()
+    g = torch.Generator().manual_seed(0)
+    bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    with torch.no_grad():
+        for m in bns:
+            m.weight.copy_(torch.empty(m.num_features).uniform_(0.5, 1.5, generator=g))
+            m.bias.copy_(torch.empty(m.num_features).uniform_(-0.5, 0.5, generator=g))
+            m.momentum = 1.0
+        net.train()
+        net(torch.randn(1, 4, 64, 64, generator=g))
+        for m in bns:
+            m.momentum = 0.1
+    return net.eval()
+
+
+def cpu_forward_timer(H, W, steps, warmup, bf16=False):
+    """Seconds per eval forward of one HxW frame on the host cores.  Returns (seconds, kind): kind "reference" = the
+    unmodified reference class from baseline/_ref, "port" = the oracle restatement (fallback when _ref is absent)."""
     torch.set_num_threads(os.cpu_count() or 1)
     x = torch.randn(1, 4, H, W, generator=torch.Generator().manual_seed(1))
+    net = reference_unet()
+    if net is not None:
+        kind = "reference"
+        fwd = (lambda: net(x)) if not bf16 else None
+        if bf16:
+            def fwd():
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    return net(x)
+    else:
+        import oracle
+        kind = "port"
+        P = make_params()
+        fwd = lambda: oracle.unet_forward(x, P, training=False, bf16=bf16)  # noqa: E731
     with torch.no_grad():
         for _ in range(warmup):
-            oracle.unet_forward(x, P, training=False, bf16=bf16)
+            fwd()
         t0 = time.perf_counter()
         for _ in range(steps):
-            oracle.unet_forward(x, P, training=False, bf16=bf16)
+            fwd()
         dt = time.perf_counter() - t0
-    return dt / steps
+    return dt / steps, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    P = make_params()
     cores = os.cpu_count() or 1
     full = (args.steps + args.warmup) <= 40
     H, W = (H1080, W1080) if full else (H1080 // 2, W1080)
-    sec = cpu_forward_timer(P, H, W, args.steps, args.warmup)
+    sec, kind = cpu_forward_timer(H, W, args.steps, args.warmup)
     mpix = H * W / 1e6 / sec
-    sample = (f"{args.steps} timed + {args.warmup} warm-up eval forwards of one {W}x{H} frame, fp32, torch CPU "
+    what = ("the reference's own Unet class (unmodified copy of Unetmodel.py in baseline/_ref), model.eval(), "
+            "torch.no_grad()" if kind == "reference" else "oracle port of Unetmodel.py:90-149 (baseline/_ref absent)")
+    sample = (f"{args.steps} timed + {args.warmup} warm-up eval forwards of one {W}x{H} frame, fp32, torch CPU, {what} "
               f"({'full frame' if full else 'half-height frame, Mpix/s is size-normalised'})")
     line = {"impl": "reference", "metric": "U-Net inference Mpix/s @1080p", "value": mpix, "unit": "Mpix/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "cfg1: U-Net inference, one 1920x1080 synthetic G-buffer frame, fp32 (CPU port "
-                                   "of the reference path on the host cores)"},
-            "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": CFG1_WORKLOAD},
+            "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -308,6 +352,7 @@ def run_b200(args):
                 if tl is not None:
                     full[tag] = {"value": tl["value"], "unit": tl["unit"], "ms_per_step": tl["ms_per_step"],
                                  "e2e": tl["e2e"]["value"], "stock_pytorch_gpu": tl.get("stock_pytorch_gpu"),
+                                 "dp_check": tl.get("dp_check"),
                                  "gemm_tflops": tl["roofline"]["achieved"],
                                  "gemm_frac_of_sustained_peak": tl["roofline"]["frac"],
                                  "workload": tl["config"]["workload"]}
@@ -371,15 +416,26 @@ def run_b200(args):
                 "per_layer": layers}
 
     cfg_name = ("cfg1" if (B, H, W) == (1, 1080, 1920) else
+                f"cfg4 (16 4K frames sharded by frame over {world} GPU(s), {B} per GPU, no collective)"
+                if (H, W) == (2160, 3840) and B * world == 16 else
                 "cfg4 (per-GPU share: 2 of the 16 4K frames)" if (B, H, W) == (2, 2160, 3840) else "custom shape")
+    summary = None
+    if isinstance(train, dict) and "error" not in train:
+        summary = {k: {"samples_per_s": round(v["value"], 1), "ms_per_step": round(v["ms_per_step"], 3),
+                       "e2e_samples_per_s": round(v["e2e"], 1), "n_gpus": world,
+                       "dp_check_rel_l2": (v.get("dp_check") or {}).get("allreduced_vs_mean_of_local_rel_l2")}
+                   for k, v in train.items()}
     line = {"metric": "U-Net inference Mpix/s @1080p" if H == 1080 else f"U-Net inference Mpix/s @{W}x{H}", "value": value, "unit": "Mpix/s", "n_gpus": world,
+            "train_summary": summary,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 (fp16 hi + fp16-lo / e4m3-cross operand planes, 2-3 MMA slots per MAC, fp32 accumulate; "
                      "output within 1e-4 of the fp32 reference)" if precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{cfg_name}: U-Net inference, {B} synthetic {W}x{H} G-buffer frame(s) per GPU "
+            "config": {"workload": CFG1_WORKLOAD if (B, H, W, precision) == (1, 1080, 1920, "fp32") else
+                                   f"{cfg_name}: U-Net inference, {B} synthetic {W}x{H} G-buffer frame(s) per GPU "
                                    f"per step, {precision} mode, eval BatchNorm",
+                       "frames_per_gpu_per_step": B,
                        "l2": "256 MiB buffer written before every timed step (L2 flush); step working set ~1.5 GB",
                        "sharding": "frames per rank, no collective"},
             "clocks": clocks,
@@ -398,10 +454,15 @@ def run_b200(args):
         line["stock_pytorch_gpu"] = stock
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sec = cpu_forward_timer(make_params(), H, W, 2, 1)
-        line["cpu_baseline"] = {"value": H * W / 1e6 / sec, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                                "sample": f"2 timed + 1 warm-up eval forwards of one {W}x{H} frame, fp32, torch CPU "
-                                          f"ops on {cores} threads (oracle port of Unetmodel.py:90-149)"}
+        Hc, Wc = (H, W) if H * W <= H1080 * W1080 else (H1080, W1080)
+        sec, kind = cpu_forward_timer(Hc, Wc, 5, 1)
+        line["cpu_baseline"] = {"value": Hc * Wc / 1e6 / sec, "unit": "Mpix/s", "cores": cores, "kind": kind,
+                                "sample": f"5 timed + 1 warm-up eval forwards of one {Wc}x{Hc} frame, fp32, torch CPU "
+                                          f"on {cores} threads, " +
+                                          ("the reference's own Unet class (unmodified copy in baseline/_ref)"
+                                           if kind == "reference" else "oracle port of Unetmodel.py:90-149")}
+    line["summary"] = {"infer_mpix_per_s": round(value, 1), "e2e_mpix_per_s": round(e2e_value, 1), "n_gpus": world,
+                       "train": summary}        # repeated at the very end: a truncated tail of the line still holds it
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -516,6 +577,48 @@ def stock_pytorch_train_baseline(B, H, W, dev, use_pert, steps=3):
             "note": "stock PyTorch autograd on the same GPU: bf16 autocast, channels_last, cudnn.benchmark, fused AdamW"}
 
 
+def dp_gradient_check(net, crit, sync, x, t, world):
+    """Data-parallel parity inside the bench run (every rank): the gradients the overlapped, bucketed NCCL all-reduce leaves
+    in p.grad must equal the mean over ranks of the gradients each rank computes alone on its own shard (same Dropout2d
+    masks replayed, per-replica BatchNorm).  Returns the global rel-L2 difference (max over ranks)."""
+    import torch.distributed as dist
+    import nsm_train
+    B = x.shape[0]
+    gm = torch.Generator().manual_seed(4242 + dist.get_rank())
+    masks = []
+    for name, cin, _ in nsm_train.BLOCKS:
+        p = getattr(net, name).conv[3].p
+        masks.append(torch.empty(B, cin, 1, 1).bernoulli_(1 - p, generator=gm).div_(1 - p) if p > 0 else None)
+
+    def grads(with_sync):
+        net._grad_sync = sync if with_sync else None
+        for p in net.parameters():
+            p.grad = None
+        nsm_train.replay_masks(net, masks)
+        out = net(x)
+        was = crit.perturb_weight
+        crit.perturb_weight = 0.0                      # the perturbed forwards draw fresh noise: keep the check exact
+        loss, _ = crit(net, out, t, x)
+        crit.perturb_weight = was
+        loss.backward()
+        if with_sync:
+            sync.finish()
+        return torch.cat([p.grad.detach().reshape(-1).double() for p in net.parameters()])
+
+    local_g = grads(False)
+    dist.all_reduce(local_g, op=dist.ReduceOp.SUM)
+    want = local_g / world
+    got = grads(True)
+    net._grad_sync = sync
+    r = ((got - want).norm() / want.norm()).reshape(1)
+    dist.all_reduce(r, op=dist.ReduceOp.MAX)
+    for p in net.parameters():
+        p.grad = None
+    return {"allreduced_vs_mean_of_local_rel_l2": float(r.item()), "ok": bool(r.item() <= 1e-4),
+            "what": "p.grad after GradSync (bucketed NCCL all-reduce overlapped with backward) vs all_reduce(SUM)/N of "
+                    "the same step's local gradients, all 66 tensors, max over ranks"}
+
+
 def measure_train(args, own_process_group=True):
     """Times the training step; returns the JSON line (rank 0) or None (other ranks)."""
     import torch.distributed as dist
@@ -569,6 +672,7 @@ def measure_train(args, own_process_group=True):
     for _ in range(max(args.warmup, 3)):
         step(x, t)
     barrier()
+    dp_check = dp_gradient_check(net, crit, sync, x, t, world) if world > 1 else None
     sampler = ClockSampler(local)
     sampler.start()
     evs = []
@@ -675,7 +779,10 @@ def measure_train(args, own_process_group=True):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": (x_host.numel() + t_host.numel()) * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_loss": last},
             "gpu_launches": launches,
+            "dp_check": dp_check,
             "roofline": roofline}
+    if dp_check is not None and not dp_check["ok"]:
+        raise RuntimeError(f"data-parallel gradient check failed: {dp_check}")
     if world == 1 and not args.no_stock and precision == "bf16":
         del net, crit, opt
         torch.cuda.empty_cache()
@@ -697,7 +804,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "cfg4"],
+                    help="infer: cfg1 (one 1080p frame per GPU, fp32 mode; the headline) + attached cfg2/cfg3 training "
+                         "measurement; train: cfg2/cfg3 alone; cfg4: 16 frames of 3840x2160, bf16, sharded by frame over "
+                         "the N GPUs")
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
@@ -717,6 +827,13 @@ def main():
         args.train_batch = args.train_batch or args.batch
         args.train_size = args.train_size or args.height
         run_b200_train(args)
+    elif args.workload == "cfg4":
+        from parallel import shard_frames
+        world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+        args.precision = args.precision or "bf16"
+        args.batch, args.height, args.width = len(shard_frames(16, rank, world)), 2160, 3840
+        args.no_train = args.no_stock = args.no_cpu_baseline = True
+        run_b200(args)
     else:
         args.precision = args.precision or "fp32"
         args.batch, args.height, args.width = args.batch or 1, args.height or H1080, args.width or W1080

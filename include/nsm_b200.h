@@ -12,8 +12,10 @@
  *
  * `mode` selects the arithmetic:
  *   NSM_MODE_BF16  activations/weights bf16, fp32 accumulate, rounding points of torch.autocast(bfloat16)
- *   NSM_MODE_FP32  fp32-accurate: every tensor is held as hi+lo bf16 planes, products hi*hi+hi*lo+lo*hi are
- *                  accumulated in fp32 on the tensor cores (network output within 1e-4 of the fp32 reference)
+ *   NSM_MODE_FP32  fp32-accurate: every tensor is held as hi+lo half-precision planes (fp16 pairs in eval, bf16 pairs
+ *                  in NSM_MODE_FP32_TRAIN; 8-bit cross planes for the decoder's 3x3 layers), products
+ *                  hi*hi+hi*lo+lo*hi are accumulated in fp32 on the tensor cores (network output within 1e-4 of the
+ *                  fp32 reference)
  *
  * Each entry point cites the reference interface (file:line in SDU-Gary/PCSS-Unet) it stands in for.
  */
@@ -205,11 +207,15 @@ int nsm_wgrad(const void* dz0, const void* dz1, const void* x0, const void* x1, 
  * Optimizer + gradient hygiene (main.py:295-423, :955): non-finite scan, global-norm clip
  * (torch.nn.utils.clip_grad_norm_ semantics) and AdamW over up to 128 tensors in two launches, no host sync.
  *   acc[0] = sum of squared gradients (before clipping), acc[1] = number of NaN/Inf gradient elements; when
- *   acc[1] != 0 the update is skipped entirely (GradScaler.step behaviour).  `step` is the 1-based AdamW step.
+ *   acc[1] != 0 the update is skipped entirely (GradScaler.step behaviour).  `step` > 0 is the 1-based AdamW step; with
+ *   `step` <= 0 the counter lives on the device: acc has THREE doubles, acc[2] = number of updates applied so far (kept
+ *   across calls, seeded by the caller), the bias corrections use acc[2] + 1 and acc[2] advances only when the update was
+ *   applied -- so a skipped step does not run the bias corrections ahead of the moments (torch AdamW under GradScaler).
  * --------------------------------------------------------------------------------------------------------- */
 int nsm_adamw_clip_step(int count, float* const* params, const float* const* grads, float* const* exp_avg,
                         float* const* exp_avg_sq, const long long* numel, float lr, float beta1, float beta2, float eps,
-                        float weight_decay, float max_norm, int step, double* acc /*[2] device*/, void* stream);
+                        float weight_decay, float max_norm, int step, double* acc /*[2], or [3] when step <= 0; device*/,
+                        void* stream);
 
 #ifdef __cplusplus
 }

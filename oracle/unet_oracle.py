@@ -194,7 +194,7 @@ def replay_conv5_checkpoint(P, taps, dropout_rate=0.2, masks=None, bf16=False, m
     """Second train-mode evaluation of conv5 that ``torch.utils.checkpoint`` performs during backward
     (Unetmodel.py:114-116): same input ``p4``, same Dropout2d draw (RNG state restored), result
     discarded; only the BN buffer side effects remain."""
-    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
+    ctx = torch.autocast(taps["p4"].device.type, dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
     with torch.no_grad(), ctx, torch.random.fork_rng():
         torch.set_rng_state(taps["_rng_conv5"])
         m = None if masks is None else masks[3]

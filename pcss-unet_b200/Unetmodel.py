@@ -61,8 +61,6 @@ class Unet(nn.Module):
             setattr(self, name, DoubleConv(cin, cout, drops.get(name, dropout_rate)))
             if name in ("conv2", "conv3", "conv4"):
                 setattr(self, "pool" + name[-1], nn.AvgPool2d(2))
-            if name == "conv5":
-                pass
             nxt = _BLOCKS[i + 1][0] if i + 1 < len(_BLOCKS) else None
             if nxt in ("conv6", "conv7", "conv8", "conv9"):
                 setattr(self, "up" + nxt[-1], nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True))
@@ -82,9 +80,26 @@ class Unet(nn.Module):
 
     # -- plumbing -----------------------------------------------------------------------------------------------
     def _mode(self):
+        """Arithmetic mode of this call.  Outside autocast: fp32 mode.  Under ``autocast(bfloat16)``: bf16 mode.  Under
+        ``autocast(float16)`` -- what main.py:257 / infer.py:64 / inference.py:188 use on CUDA -- eval forwards run the
+        fp32 mode (at least the reference's fp16 accuracy; its 2^-11 output step matters for infer.py:79's 8-bit
+        quantisation) and training forwards the bf16 tensor path (same tensor-core rate as fp16, and GradScaler's 2^16
+        loss scale cannot overflow bf16 planes)."""
         if self.precision is not None:
             return nsm.MODES[self.precision]
-        return nsm.MODE_BF16 if torch.is_autocast_enabled() else nsm.MODE_FP32
+        if not torch.is_autocast_enabled():
+            return nsm.MODE_FP32
+        if torch.get_autocast_dtype("cuda") == torch.float16 and not self.training:
+            return nsm.MODE_FP32
+        return nsm.MODE_BF16
+
+    @staticmethod
+    def _out_dtype(mode):
+        """dtype the reference would return: the autocast dtype under autocast (Unetmodel.py:148 runs inside it), else
+        fp32; a forced bf16 mode outside autocast keeps returning bf16."""
+        if torch.is_autocast_enabled():
+            return torch.get_autocast_dtype("cuda")
+        return torch.bfloat16 if mode == nsm.MODE_BF16 else torch.float32
 
     def _all_tensors(self):
         ts = []
@@ -135,7 +150,8 @@ class Unet(nn.Module):
         mean, std = self.input_stats if self.input_stats is not None else (None, None)
         nsm.unet_infer(blob, mode, xin, y, ws, mean, std)
         self.last_workspace = (ws, B, H, W, mode)
-        return y.to(torch.bfloat16) if mode == nsm.MODE_BF16 else y
+        dt = self._out_dtype(mode)
+        return y if dt == torch.float32 else y.to(dt)
 
     @torch.no_grad()
     def infer_host(self, x_host, y_host=None):

@@ -173,7 +173,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+    // ~60 s at 2 GHz: far beyond any legitimate wait even when the context is time-sliced or preempted (a trap is sticky and
+    // kills the CUDA context), still short enough that a protocol bug ends the launch instead of hanging the GPU box
+    if (clock64() - t0 > 120000000000LL) {
       printf("nsm: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }

@@ -83,11 +83,18 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(const __grid_constant__ 
 struct AdamWArgs {
   float lr, beta1, beta2, eps, weight_decay, max_norm;
   float bias_c1, bias_c2_sqrt;   // 1 - beta1^step, sqrt(1 - beta2^step)
+  int device_step;               // step <= 0 at the ABI: the 1-based step is acc[2] + 1 (applied updates so far)
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ MultiTensor t, const AdamWArgs a,
                                                     const double* acc) {
   if (acc[1] != 0.0) return;   // non-finite gradients: skip the update (what GradScaler.step does, main.py:421)
+  float bias_c1 = a.bias_c1, bias_c2_sqrt = a.bias_c2_sqrt;
+  if (a.device_step) {         // step counter lives in acc[2] and only counts APPLIED updates (torch AdamW under GradScaler)
+    const float step = float(acc[2]) + 1.f;
+    bias_c1 = 1.f - powf(a.beta1, step);
+    bias_c2_sqrt = sqrtf(1.f - powf(a.beta2, step));
+  }
   const float norm = float(sqrt(acc[0]));
   const float clip = a.max_norm > 0.f ? fminf(1.f, a.max_norm / (norm + 1e-6f)) : 1.f;
   const int ti = find_tensor(t, blockIdx.x);
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ Mult
   const float* g = t.g[ti];
   float* m = t.m[ti];
   float* v = t.v[ti];
-  const float step_size = a.lr / a.bias_c1;
+  const float step_size = a.lr / bias_c1;
   for (int it = 0; it < 16; ++it) {
     const long long i0 = base + ((long long)it * 256 + threadIdx.x) * 4;
     if (i0 >= n) break;
@@ -107,12 +114,16 @@ __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ Mult
       float pp = p[i] * (1.f - a.lr * a.weight_decay);
       const float mm = a.beta1 * m[i] + (1.f - a.beta1) * gg;
       const float vv = a.beta2 * v[i] + (1.f - a.beta2) * gg * gg;
-      pp -= step_size * (mm / (sqrtf(vv) / a.bias_c2_sqrt + a.eps));
+      pp -= step_size * (mm / (sqrtf(vv) / bias_c2_sqrt + a.eps));
       p[i] = pp;
       m[i] = mm;
       v[i] = vv;
     }
   }
+}
+
+__global__ void adamw_advance_kernel(double* acc) {
+  if (acc[1] == 0.0) acc[2] += 1.0;   // after every block of adamw_kernel has read acc[2] (stream order)
 }
 
 }  // namespace nsm
@@ -145,14 +156,16 @@ extern "C" int nsm_adamw_clip_step(int count, float* const* params, const float*
   grad_norm_kernel<<<blocks, 256, 0, st>>>(t, acc);
   AdamWArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
-  a.bias_c1 = 1.f - powf(beta1, float(step));
-  a.bias_c2_sqrt = sqrtf(1.f - powf(beta2, float(step)));
+  a.device_step = step <= 0 ? 1 : 0;
+  a.bias_c1 = 1.f - powf(beta1, float(step > 0 ? step : 1));
+  a.bias_c2_sqrt = sqrtf(1.f - powf(beta2, float(step > 0 ? step : 1)));
   adamw_kernel<<<blocks, 256, 0, st>>>(t, a, acc);
+  if (a.device_step) adamw_advance_kernel<<<1, 1, 0, st>>>(acc);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("nsm_adamw_clip_step launch failed: %s", cudaGetErrorString(e));
     return 1;
   }
-  count_launch(2);
+  count_launch(a.device_step ? 3 : 2);
   return 0;
 }

@@ -375,14 +375,19 @@ def upsample_match(x: PlaneTensor, hd, wd, out_x8=False):
 
 def l1_loss_fwd_bwd(out, target=None, perturbed=(), coef_l1=0.0, coef_pert=0.0, want_grad=True):
     """Returns (acc[3] float64 device tensor: sum|o-t|, sum_i sum|o-y_i|, #out-of-range; grad or None)."""
-    out = out.contiguous()
+    def aligned(t):
+        # the kernel streams float4: a contiguous view at an odd element offset (e.g. a slice of a larger buffer) is
+        # copied to a fresh, 16-byte aligned allocation instead of faulting
+        t = t.contiguous()
+        return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+    out = aligned(out)
     assert out.dtype == torch.float32
     n = out.numel()
     acc = torch.zeros(3, dtype=torch.float64, device=out.device)
     grad = torch.empty_like(out) if want_grad else None
-    pert = [p.contiguous() for p in perturbed]
+    pert = [aligned(p) for p in perturbed]
     arr = (c_void_p * max(1, len(pert)))(*[p.data_ptr() for p in pert])
-    tgt = None if target is None else target.to(torch.float32).contiguous()
+    tgt = None if target is None else aligned(target.to(torch.float32))
     check(lib().nsm_l1_loss_fwd_bwd(out.data_ptr(), ptr(tgt), arr, len(pert), n, coef_l1, coef_pert, ptr(grad),
                                     acc.data_ptr(), stream_ptr()), "nsm_l1_loss_fwd_bwd")
     return acc, grad

@@ -30,25 +30,38 @@ class FusedAdamWClip(torch.optim.Optimizer):
     def last_nonfinite(self):
         return None if self._acc is None else self._acc[1]
 
+    @property
+    def applied_steps(self):
+        """Number of updates actually applied (device counter; non-finite steps are skipped and not counted)."""
+        return None if self._acc is None else self._acc[2]
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        if sum(1 for g in self.param_groups if any(p.grad is not None for p in g["params"])) > 1:
+            # clip_grad_norm_(model.parameters()) is ONE norm over everything (main.py:405); a per-group norm would differ
+            raise nsm.NsmError("FusedAdamWClip supports one param group (the global gradient norm comes from one launch)")
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
             nsm.require_device(ps[0])
-            if self._acc is None:
-                self._acc = torch.zeros(2, dtype=torch.float64, device=ps[0].device)
-            step = None
+            fresh = self._acc is None
+            if fresh:
+                self._acc = torch.zeros(3, dtype=torch.float64, device=ps[0].device)
+            loaded = 0
             for p in ps:
                 st = self.state[p]
                 if not st:
                     st["step"] = torch.zeros((), dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                step = int(st["step"])
+                loaded = max(loaded, int(st["step"]))
+                st["step"] += 1       # host-side count of step() calls (state_dict layout of torch AdamW); the step the
+                #                       kernel uses is the device counter acc[2], which skips non-finite steps
+            if fresh and loaded:
+                self._acc[2] = float(loaded)          # resumed from a checkpoint (load_state_dict)
+            step = 0                                  # device-side counter mode of nsm_adamw_clip_step
             for i in range(0, len(ps), 128):
                 chunk = ps[i:i + 128]
                 if len(ps) > 128:

@@ -120,7 +120,9 @@ def _bn_replay(sums, P, gamma, beta, bn):
 def _draw_masks(model, N, mode, device):
     """The eight Dropout2d draws in block order, exactly as F.dropout2d / feature_dropout makes them
     (noise = empty(N, C, 1, 1).bernoulli_(1 - p).div_(1 - p) in the activation dtype)."""
-    replay = getattr(model, "_replay_masks", None)
+    # parity tests replay given draws: set by `replay_masks(model, masks)` for exactly ONE forward (popped here, so a
+    # model object reused afterwards draws fresh masks again)
+    replay = model.__dict__.pop("_replay_masks", None)
     dt = torch.bfloat16 if mode == nsm.MODE_BF16 else torch.float32
     masks = []
     for i, (name, cin, _) in enumerate(BLOCKS):
@@ -138,6 +140,13 @@ def _draw_masks(model, N, mode, device):
             m = full
         masks.append(m)
     return masks
+
+
+def replay_masks(model, masks):
+    """Parity-test hook: the NEXT training-mode forward of `model` uses these eight Dropout2d masks ([N,Cin,1,1], already
+    divided by 1-p, block order conv2..conv9; None = no dropout for that block) instead of drawing from the CUDA generator.
+    One-shot: the forward consumes them."""
+    model.__dict__["_replay_masks"] = list(masks)
 
 
 def _block_forward(model, pk, i, x, mode, mask, residual=None, pool=False, save=True):
@@ -242,6 +251,7 @@ def _backward(model, st, dy, mode, need_dx):
         dx = nsm.train_input_grad(dx16, Hin, Win)
     if sync is not None:
         sync.flush()
+    model._packed.clear()      # _bn_replay moved conv5's running statistics after the forward's clear
     return dx, G
 
 
@@ -277,4 +287,5 @@ def unet_train_forward(model, x, mode):
     else:
         with torch.no_grad():
             y, _ = _forward(model, x, tmode, save=False)
-    return y.to(torch.bfloat16) if tmode == nsm.MODE_BF16 else y
+    dt = model._out_dtype(tmode)
+    return y if dt == torch.float32 else y.to(dt)

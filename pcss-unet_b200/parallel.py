@@ -59,7 +59,11 @@ class GradSync:
         if self.world == 1:
             return
         for t in list(self.model.parameters()) + list(self.model.buffers()):
-            dist.broadcast(t.data, src, group=self.group)
+            dist.broadcast(t, src, group=self.group)     # on the tensor itself: bumps Tensor._version
+        # packed-operand caches are keyed on (data_ptr, _version); drop them anyway so that no rank can keep operands
+        # packed from its pre-broadcast parameters
+        getattr(self.model, "_packed", {}).clear()
+        self.model.__dict__.pop("_train_packed", None)
 
     # ---- overlapped path: called from inside backward ------------------------------------------------------------
     def reduce_ready(self, grads: Dict[str, torch.Tensor]):

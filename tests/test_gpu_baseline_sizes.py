@@ -1,0 +1,285 @@
+"""Parity at the sizes BASELINE.json quotes its configurations on (cfg1 1080p, cfg2 batch 32 x 512^2 training step,
+cfg4 one 3840x2160 frame) and over the 1k-step horizon north_star names for the loss curve.
+
+Checkers: the oracle restatement fed CUDA tensors (= the reference's call sequence through stock PyTorch on the same GPU,
+TF32 switched off) for the large shapes, the CPU oracle on a slice.  Tolerances (north_star): output max-abs 1e-4 (fp32
+mode) / 1e-2 (bf16 mode); stage gradients rel-L2 1e-3 / 1e-2; loss curve within 1 %.
+
+bf16 at 2-8 Mpixel: the 1e-2 bound is below the reference's own bf16 reproducibility there (its CPU and GPU bf16 paths
+differ from each other by 0.03 on a 1080p frame), so the bf16 mode is judged against the fp32 TRUTH: its error may not
+exceed the error of the reference's own bf16 path against that same truth (x1.1)."""
+import contextlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nsm():
+    import nsm as _nsm
+    _nsm.require_device()
+    return _nsm
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double().to(a.device)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@contextlib.contextmanager
+def strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def calibrated_params():
+    P = oracle.init_params(42)
+    oracle.calibrate_bn(P, torch.randn(1, 4, 64, 64, generator=gen(1)), generator=gen(2))
+    return P
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# eval: bf16 mode judged against the fp32 truth, fp32 mode against 1e-4, at 1080p (cfg1) and 2160x3840 (cfg4)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [(1080, 1920), (2160, 3840)], ids=["cfg1_1080p", "cfg4_4k"])
+def test_eval_frame_bf16_and_fp32_against_fp32_truth(nsm, size):
+    from Unetmodel import Unet
+    H, W = size
+    P = calibrated_params()
+    x = torch.randn(1, 4, H, W, generator=gen(9))
+    Pg = {k: v.cuda() for k, v in P.items()}
+    with torch.no_grad(), strict_fp32():
+        truth = oracle.unet_forward(x.cuda(), Pg, training=False).float()              # stock PyTorch, strict fp32
+        ref_bf16 = oracle.unet_forward(x.cuda(), Pg, training=False, bf16=True).float()  # the reference's bf16 path
+    outs = {}
+    for precision in ("fp32", "bf16"):
+        net = Unet(precision=precision)
+        net.load_state_dict(P)
+        net = net.cuda().eval()
+        with torch.inference_mode():
+            outs[precision] = net(x.cuda()).float()
+        del net
+    e32 = (outs["fp32"] - truth).abs().max().item()
+    mine = ((outs["bf16"] - truth).abs().max().item(), (outs["bf16"] - truth).abs().mean().item())
+    theirs = ((ref_bf16 - truth).abs().max().item(), (ref_bf16 - truth).abs().mean().item())
+    print(f"{W}x{H}: fp32 mode vs strict-fp32 truth max-abs {e32:.3g}; bf16 mode vs truth max {mine[0]:.4g} mean "
+          f"{mine[1]:.4g}; reference bf16 (stock PyTorch autocast, same GPU) vs truth max {theirs[0]:.4g} mean "
+          f"{theirs[1]:.4g}; bf16 mode vs reference bf16 max {(outs['bf16'] - ref_bf16).abs().max().item():.4g}")
+    assert e32 <= 1e-4
+    assert mine[0] <= 1.1 * theirs[0] and mine[1] <= 1.1 * theirs[1], (mine, theirs)
+    if H == 1080:   # also against the CPU truth (the oracle proper) -- one frame is affordable on the host
+        with torch.no_grad():
+            truth_cpu = oracle.unet_forward(x, P, training=False).float()
+        assert (outs["fp32"].cpu() - truth_cpu).abs().max().item() <= 1e-4
+        assert (truth.cpu() - truth_cpu).abs().max().item() <= 2e-5     # the GPU truth is the same truth
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cfg2 layer shapes (batch 32 of 512x512): forward conv, dgrad and wgrad per stage on identical inputs
+# ---------------------------------------------------------------------------------------------------------------------
+CFG2_LAYERS = [  # (name, N, Cin, H, W, Cout, k)  -- SURVEY 8a table, M = 32*h*w
+    ("conv3.3x3", 32, 64, 128, 128, 64, 3), ("conv4.1x1", 32, 128, 64, 64, 512, 1),
+    ("conv5.3x3", 32, 512, 32, 32, 512, 3), ("conv5.1x1", 32, 512, 32, 32, 1024, 1),
+    ("conv6.3x3", 32, 1024, 64, 64, 1024, 3), ("conv6.1x1", 32, 1024, 64, 64, 512, 1),
+    ("conv7.3x3", 32, 512, 128, 128, 512, 3), ("conv8.3x3", 32, 128, 256, 256, 128, 3),
+    ("conv9.3x3", 32, 64, 256, 256, 64, 3), ("conv8.1x1", 32, 128, 256, 256, 64, 1),
+]
+
+
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32_train"])
+@pytest.mark.parametrize("layer", CFG2_LAYERS, ids=[l[0] for l in CFG2_LAYERS])
+def test_cfg2_layer_fwd_dgrad_wgrad(nsm, mode_name, layer):
+    name, N, Cin, H, W, Cout, k = layer
+    mode = nsm.MODES[mode_name]
+    tol = 1e-2 if mode_name == "bf16" else 1e-3
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout + H)
+    x = torch.randn(N, Cin, H, W, generator=g, device="cuda")
+    w = torch.randn(Cout, Cin, k, k, generator=g, device="cuda") / (Cin * k * k) ** 0.5
+    dz = torch.randn(N, Cout, H, W, generator=g, device="cuda") * 1e-2
+    if mode_name == "bf16":
+        x, dz = bf(x), bf(dz)
+    wr = (bf(w) if mode_name == "bf16" else w).clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    with strict_fp32():
+        y_ref = F.conv2d(xr, wr, None, padding=k // 2)
+        y_ref.backward(dz)
+    xt, dzt = nsm.PlaneTensor.from_nchw(x, mode), nsm.PlaneTensor.from_nchw(dz, mode)
+    y, _, _ = nsm.conv_fwd(xt, nsm.pack_conv_weight(w, mode), k, Cout, mode)
+    r_fwd = rel(y.to_nchw(), bf(y_ref.detach()) if mode_name == "bf16" else y_ref)
+    del y, y_ref
+    dx, _, _ = nsm.conv_fwd(dzt, nsm.pack_conv_weight(w, mode, dgrad=True), k, Cin, mode)
+    r_dx = rel(dx.to_nchw(), xr.grad)
+    del dx
+    dw = nsm.wgrad(dzt, xt, k, Cout, Cin)
+    r_dw = rel(dw, wr.grad)
+    print(f"{name} {mode_name}: fwd {r_fwd:.2e} dgrad {r_dx:.2e} wgrad {r_dw:.2e} (tol {tol})")
+    assert r_fwd <= tol and r_dx <= tol and r_dw <= tol
+    torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cfg2 whole training step: batch 32 of 512x512, CustomLoss, Dropout2d masks replayed
+# ---------------------------------------------------------------------------------------------------------------------
+def _masks(seed, N):
+    torch.manual_seed(seed)
+    out = []
+    for name, cin, _ in oracle.BLOCKS:
+        p = oracle.DROPOUT_P(name, 0.2)
+        out.append(torch.empty(N, cin, 1, 1).bernoulli_(1 - p).div_(1 - p))
+    return out
+
+
+def _dropin_step(P, x, t, masks, precision):
+    import nsm_train
+    from Unetmodel import Unet
+    from customLoss import CustomLoss
+    net = Unet(dropout_rate=0.2, precision=precision)
+    net.load_state_dict({k: v.clone() for k, v in P.items()})
+    net = net.cuda().train()
+    nsm_train.replay_masks(net, masks)
+    out = net(x)
+    loss = CustomLoss("cuda", alpha=0.9, vgg_loss=None)(out, t, x)
+    loss.backward()
+    return net, out.detach().float(), loss.item(), {n: p.grad.detach() for n, p in net.named_parameters()}
+
+
+def _block_rel(grads, ref):
+    """rel-L2 per DoubleConv block (all its parameter gradients concatenated; pre-BN conv biases have true gradient 0
+    and drop out of a concatenated norm) and globally."""
+    out = {}
+    names = oracle.param_names()
+    for blk in [b[0] for b in oracle.BLOCKS] + ["conv10"]:
+        ks = [n for n in names if n.startswith(blk + ".")]
+        num = sum(float((grads[n].double() - ref[n].double().to(grads[n].device)).pow(2).sum()) for n in ks)
+        den = sum(float(ref[n].double().pow(2).sum()) for n in ks)
+        out[blk] = (num / den) ** 0.5
+    num = sum(float((grads[n].double() - ref[n].double().to(grads[n].device)).pow(2).sum()) for n in names)
+    den = sum(float(ref[n].double().pow(2).sum()) for n in names)
+    out["all"] = (num / den) ** 0.5
+    return out
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_cfg2_training_step_batch32_512(nsm, precision):
+    """BASELINE configs[2] at full size against the reference's call sequence on stock PyTorch (same GPU, TF32 off,
+    autocast(bfloat16) for the bf16 mode), and -- fp32 -- a batch-2 slice against the CPU oracle."""
+    B, S = 32, 512
+    P = oracle.init_params(42)
+    x = torch.randn(B, 4, S, S, generator=gen(5))
+    t = torch.rand(B, 1, S, S, generator=gen(6))
+    masks = _masks(9, B)
+    bf16 = precision == "bf16"
+    Pg = {k: v.cuda() for k, v in P.items()}
+    with strict_fp32():
+        o_ref, l_ref, g_ref = oracle.train_step_grads(x.cuda(), t.cuda(), Pg, masks=[m.cuda() for m in masks], bf16=bf16)
+    o_ref = o_ref.float()
+    torch.cuda.empty_cache()
+    net, out, loss, grads = _dropin_step(P, x.cuda(), t.cuda(), masks, precision)
+    err = (out - o_ref).abs().max().item()
+    r = _block_rel(grads, g_ref)
+    print(f"cfg2 step {precision}: out max-abs err {err:.3g} (mean {(out - o_ref).abs().mean().item():.3g}); loss "
+          f"{loss:.6f} vs {l_ref.item():.6f}; grad rel-L2 per block " + " ".join(f"{k}:{v:.2e}" for k, v in r.items()))
+    assert abs(loss - l_ref.item()) <= (1e-5 if not bf16 else 1e-3)
+    # end-to-end gradients carry LeakyReLU-mask flips (reference-vs-reference floor 1.2e-3..2.5e-3 fp32, ~0.2 bf16-vs-fp32,
+    # SURVEY 3.7); the per-stage 1e-3 / 1e-2 bounds are asserted on identical inputs in test_cfg2_layer_* above
+    assert err <= (1e-4 if not bf16 else 2e-2)
+    assert r["all"] <= (1e-2 if not bf16 else 0.3)
+    sd = net.state_dict()
+    for k in oracle.buffer_names():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(Pg[k]), k
+        elif not bf16:
+            assert torch.allclose(sd[k], Pg[k], rtol=1e-3, atol=1e-4), k
+    if not bf16:
+        del net, grads
+        torch.cuda.empty_cache()
+        Po = {k: v.clone() for k, v in P.items()}
+        m2 = [m[:2] for m in masks]
+        o_cpu, l_cpu, g_cpu = oracle.train_step_grads(x[:2], t[:2], Po, masks=m2)
+        _, out2, loss2, grads2 = _dropin_step(P, x[:2].cuda(), t[:2].cuda(), m2, precision)
+        r2 = _block_rel({k: v.cpu() for k, v in grads2.items()}, g_cpu)
+        print(f"  batch-2 slice vs CPU oracle: out err {(out2.cpu() - o_cpu).abs().max().item():.3g}, loss {loss2:.6f} vs "
+              f"{l_cpu.item():.6f}, grad rel-L2 all {r2['all']:.2e}")
+        assert (out2.cpu() - o_cpu).abs().max().item() <= 1e-4 and abs(loss2 - l_cpu.item()) <= 1e-5
+        assert r2["all"] <= 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# loss curve over 1000 optimisation steps (north_star: within 1 % of the reference)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_loss_curve_1k_steps(nsm, precision):
+    """1000 steps of main.py's recipe (CustomLoss alpha 0.9, clip_grad_norm_ 1.0, AdamW lr 7e-4 wd 1e-3, Dropout2d) on the
+    drop-in (fused clip+AdamW kernel) and on the reference call sequence through stock PyTorch on the same GPU (TF32 off;
+    autocast(bfloat16) for the bf16 mode; torch AdamW + clip_grad_norm_), same data and the same replayed Dropout2d masks
+    every step.  Two trajectories of a chaotic system separate (LeakyReLU-mask flips amplified by Adam), so single steps
+    scatter around each other; the curve -- the 20-step moving average -- must stay within 1 %."""
+    import nsm_train
+    from Unetmodel import Unet
+    from customLoss import CustomLoss
+    from nsm_optim import FusedAdamWClip
+    steps, N, H, W = 1000, 4, 64, 64
+    bf16 = precision == "bf16"
+    P = oracle.init_params(42)
+    net = Unet(dropout_rate=0.2, precision=precision)
+    net.load_state_dict({k: v.clone() for k, v in P.items()})
+    net = net.cuda().train()
+    opt = FusedAdamWClip(net.parameters(), lr=7e-4, weight_decay=1e-3, max_norm=1.0)
+    crit = CustomLoss("cuda", alpha=0.9, vgg_loss=None)
+    names = oracle.param_names()
+    Po = {k: v.clone().cuda() for k, v in P.items()}
+    leaves = [Po[k].requires_grad_(True) for k in names]
+    opt_ref = torch.optim.AdamW(leaves, lr=7e-4, weight_decay=1e-3)
+    g = gen(55)
+    data = []
+    for _ in range(8):
+        x = torch.randn(N, 4, H, W, generator=g)
+        t = torch.sigmoid(0.8 * x[:, :1] + 0.3 * x[:, 1:2] * x[:, 2:3])        # learnable target in (0,1)
+        data.append((x.cuda(), t.cuda()))
+    curve, curve_ref = [], []
+    with strict_fp32():
+        for it in range(steps):
+            x, t = data[it % len(data)]
+            masks = [m.cuda() for m in _masks(1000 + it, N)]
+            nsm_train.replay_masks(net, masks)
+            opt.zero_grad(set_to_none=True)
+            loss = crit(net(x), t, None)
+            loss.backward()
+            opt.step()
+            curve.append(loss.detach())
+            opt_ref.zero_grad(set_to_none=True)
+            out = oracle.unet_forward(x, Po, training=True, masks=masks, bf16=bf16)
+            lr_ = oracle.custom_loss(out.float(), t, 0.9)
+            lr_.backward()
+            torch.nn.utils.clip_grad_norm_(leaves, max_norm=1.0)
+            opt_ref.step()
+            curve_ref.append(lr_.detach())
+    a = torch.stack(curve).double().cpu()
+    b = torch.stack(curve_ref).double().cpu()
+    dev = ((a - b).abs() / b)
+    win = 20
+    ma = lambda c: c.unfold(0, win, 1).mean(dim=1)  # noqa: E731
+    ma_dev = ((ma(a) - ma(b)).abs() / ma(b))
+    print(f"1k-step loss curve {precision}: start {a[0]:.5f}/{b[0]:.5f} end {a[-1]:.5f}/{b[-1]:.5f}; per-step rel dev "
+          f"mean {dev.mean():.4f} max {dev.max():.4f} (first 100 steps max {dev[:100].max():.4f}); {win}-step moving "
+          f"average rel dev max {ma_dev.max():.4f} mean {ma_dev.mean():.4f}")
+    assert a[-50:].mean() < 0.6 * a[:50].mean()            # it trains
+    assert ma_dev.max() <= 0.01
+    assert dev.mean() <= 0.01

@@ -31,7 +31,8 @@ def _step(rank, x, t, masks, sync_cls=None):
     from customLoss import CustomLoss
     torch.manual_seed(42)
     net = Unet(dropout_rate=0.2, precision="fp32").cuda().train()
-    net._replay_masks = masks
+    import nsm_train
+    nsm_train.replay_masks(net, masks)
     sync = sync_cls(net) if sync_cls is not None else None
     out = net(x.cuda())
     CustomLoss("cuda")(out, t.cuda(), None).backward()

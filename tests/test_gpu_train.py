@@ -213,7 +213,8 @@ def _gpu_step(P, x, t, masks, precision, alpha=0.9, input_grad=True):
     net = Unet(dropout_rate=0.2, precision=precision)
     net.load_state_dict({k: v.clone() for k, v in P.items()})
     net = net.cuda().train()
-    net._replay_masks = masks
+    import nsm_train
+    nsm_train.replay_masks(net, masks)
     xg = x.cuda().requires_grad_(input_grad)
     out = net(xg)
     loss = CustomLoss("cuda", alpha=alpha)(out, t.cuda(), xg)
@@ -395,7 +396,8 @@ def test_loss_curve_matches_oracle(nsm):
     for it in range(steps):
         x, t = data[it % len(data)]
         masks = _masks(1000 + it, N)
-        net._replay_masks = masks
+        import nsm_train
+        nsm_train.replay_masks(net, masks)
         opt.zero_grad(set_to_none=True)
         loss = crit(net(x.cuda()), t.cuda(), None)
         loss.backward()
