@@ -119,7 +119,7 @@ typedef struct nsm_conv_args {
   const float* bias;       /* [Cout] or NULL                           nn.Conv2d bias      Unetmodel.py:21,26 */
   const float* bn_scale;   /* [Cout] or NULL  gamma/sqrt(var+eps)      nn.BatchNorm2d      Unetmodel.py:22,27 */
   const float* bn_shift;   /* [Cout]          beta - mean*scale                                              */
-  int lrelu;               /* LeakyReLU(0.2)                                               Unetmodel.py:23,28 */
+  int lrelu;               /* 1: LeakyReLU(0.2)  Unetmodel.py:23,28;  2: ReLU (VGG19 stacks, customLoss.py:20) */
   void* out[2];            /* [N,H,W,Cout] planes or NULL */
   const void* residual[2]; /* [N,H,W,Cout] planes or NULL: skip add    Unetmodel.py:125,131,137              */
   void* pool[2];           /* [N,H/2,W/2,Cout] planes or NULL: AvgPool2d(2)               Unetmodel.py:40,43,46 */
@@ -141,6 +141,22 @@ int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, voi
  * target may be NULL; n_perturbed <= 4.  acc must be zeroed by the caller. */
 int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
                         long long numel, float coef_l1, float coef_pert, float* grad, double* acc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Perceptual term: MultiLayerVGGLoss (customLoss.py:7-90) = weighted L1 between VGG19 features of output and target.
+ * The VGG19 convolutions run through nsm_conv_fwd (lrelu = 2 for the fused ReLU, 0 for a tapped pre-activation
+ * feature); these are the passes around them.
+ * --------------------------------------------------------------------------------------------------------- */
+/* customLoss.py:44-61: clamp(0,1), nan_to_num(nan=.5), grey -> 3 channels, (v-0.485)/(0.229+1e-8).  output, target:
+ * [B,1,H,W] fp32; out: planes [2B,H,W,64] (images 0..B-1 = output, B..2B-1 = target; channels 3..63 zero) */
+int nsm_vgg_input_prep(const float* output, const float* target, int B, int H, int W, int mode, void* out0, void* out1,
+                       void* stream);
+/* nn.ReLU [+ nn.MaxPool2d(2) when pool != 0]: in [N,H,W,C] -> out [N,H/2,W/2,C] or [N,H,W,C] */
+int nsm_relu_maxpool(const void* in0, const void* in1, int N, int H, int W, int C, int pool, int mode, void* out0,
+                     void* out1, void* stream);
+/* customLoss.py:76-80: *acc += sum |nan_to_num(a) - nan_to_num(b)| where a = the first numel_half elements of the
+ * planes, b = the next numel_half (nan -> 0, +inf -> 1, -inf -> -1); acc fp64, device, zeroed by the caller */
+int nsm_feature_l1(const void* f0, const void* f1, long long numel_half, int mode, double* acc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Input statistics / standardisation / perturbation

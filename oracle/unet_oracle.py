@@ -19,7 +19,7 @@ __all__ = [
     "BLOCKS", "DROPOUT_P", "init_params", "param_names", "buffer_names", "even_fix", "double_conv",
     "unet_forward", "upsample_and_match", "upsample_and_match_bf16", "l1_loss", "custom_loss", "custom_loss_grad",
     "perturb_inputs", "perturbation_loss", "perturbation_loss_grad", "standardise",
-    "conv_stage_eval", "train_step_grads", "calibrate_bn", "replay_conv5_checkpoint",
+    "conv_stage_eval", "train_step_grads", "calibrate_bn", "replay_conv5_checkpoint", "vgg_perceptual_loss",
 ]
 
 # (name, in_ch, out_ch) in construction AND forward order -- Unetmodel.py:39,42,45,48,52,55,58,61
@@ -327,3 +327,40 @@ def train_step_grads(x, target, P, masks=None, alpha=0.9, dropout_rate=0.2, bf16
     if input_grad:
         grads["input"] = xin.grad
     return out.detach(), loss.detach(), grads
+
+
+# ------------------------------------------------------------------------------------------------
+# Perceptual term
+# ------------------------------------------------------------------------------------------------
+
+def vgg_perceptual_loss(output, target, features, feature_layers=(2, 7, 12, 21, 30),
+                        weights=(0.25, 0.25, 0.3, 0.1, 0.1)):
+    """MultiLayerVGGLoss.forward (customLoss.py:43-90) for a given frozen ``features`` stack
+    (``torchvision.models.vgg19(...).features``): clamp to [0,1] (:44-45), grey -> 3 channels (:55-56),
+    ``(x - 0.485) / (0.229 + 1e-8)`` (:59-61), then for every tapped layer the truncated stack
+    ``features[:idx+1]`` is run from the image under no_grad (:70-72), features are nan_to_num'ed (:76-77)
+    and compared with F.l1_loss (:80); the weights are normalised to sum 1 (:34-36).  The result is a
+    detached constant (:90).  Runs under whatever autocast context the caller has set (main.py:257)."""
+    w = torch.tensor(weights, dtype=torch.float32)
+    w = w / w.sum()
+    layers = list(features.children())
+    o = torch.clamp(output.to(torch.float32), 0.0, 1.0)
+    t = torch.clamp(target.to(torch.float32), 0.0, 1.0)
+    o = torch.nan_to_num(o, nan=0.5, posinf=1.0, neginf=0.0).repeat(1, 3, 1, 1)
+    t = torch.nan_to_num(t, nan=0.5, posinf=1.0, neginf=0.0).repeat(1, 3, 1, 1)
+    o = (o - 0.485) / (0.229 + 1e-8)
+    t = (t - 0.485) / (0.229 + 1e-8)
+    total = 0.0
+    with torch.no_grad():
+        for k, idx in enumerate(feature_layers):
+            fo, ft = o, t
+            for m in layers[:idx + 1]:
+                # torchvision's ReLUs are in-place modules; functional form keeps o / t intact
+                if isinstance(m, torch.nn.ReLU):
+                    fo, ft = F.relu(fo), F.relu(ft)
+                else:
+                    fo, ft = m(fo), m(ft)
+            fo = torch.nan_to_num(fo, nan=0.0, posinf=1.0, neginf=-1.0)
+            ft = torch.nan_to_num(ft, nan=0.0, posinf=1.0, neginf=-1.0)
+            total = total + w[k].to(fo.device) * F.l1_loss(fo, ft)
+    return total.detach().float()

@@ -275,8 +275,9 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
     }
   }
   if (ep.lrelu) {
+    const float slope = ep.lrelu == 2 ? 0.f : 0.2f;   // 2 = ReLU (the VGG19 stacks of the perceptual term)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = lrelu02(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : slope * v[j];
     if (ep.round_bf16) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);

@@ -20,7 +20,7 @@ struct ConvEpilogue {
   const float* bias;     // [Cout] conv bias or nullptr
   const float* scale;    // [Cout] BatchNorm scale  (gamma * rsqrt(var + eps)) or nullptr
   const float* shift;    // [Cout] BatchNorm shift  (beta - mean * scale)
-  int lrelu;             // LeakyReLU(0.2) after the affine
+  int lrelu;             // activation after the affine: 0 none, 1 LeakyReLU(0.2), 2 ReLU
   int round_bf16;        // round to bf16 after conv, affine, activation, residual (autocast rounding points)
   Planes out;            // [N,H,W,Cout]
   Planes residual;       // [N,H,W,Cout] added after the activation (skip connection) or {nullptr}

@@ -5,18 +5,143 @@ customLoss.py:129-193, keeps the attributes the trainer reads (``.l1`` callable,
 asserts ``0 <= output <= 1`` (customLoss.py:131).  The L1 value, its gradient ``alpha * sign(o - t) / N`` and the range
 check come out of ONE vectorised, warp-shuffle-reduced streaming kernel (``nsm_l1_loss_fwd_bwd``).
 
-The reference's VGG19 perceptual term is a detached constant (re-wrapped by ``torch.tensor(..., requires_grad=True)``,
-customLoss.py:90): it shifts the loss value and contributes no gradient.  It needs ImageNet weights (not available
-offline) and is listed as a follow-up in SURVEY 8f; pass ``vgg_loss=<callable(output, target) -> scalar>`` (for
-instance the reference's own ``MultiLayerVGGLoss``) to include it, the default contributes 0.  The high-frequency,
-penumbra and Sobel terms the reference computes and then discards (customLoss.py:139-185) are not computed.
+``MultiLayerVGGLoss(device, feature_layers, weights)`` (customLoss.py:7-90) is the perceptual term: weighted L1 between
+the pre-activation VGG19 features ``features[:3], [:8], [:13], [:22], [:31]`` of output and target.  The reference re-runs
+each truncated stack from the image (five passes over a shared prefix) for output and target separately; here ONE pass
+over the 2B images goes through the tcgen05 implicit-GEMM kernel (``nsm_conv_fwd`` with a fused ReLU epilogue) and the
+five features are tapped on the way (``nsm_vgg_input_prep``, ``nsm_relu_maxpool``, ``nsm_feature_l1``).  The result is
+a detached constant, as in the reference (re-wrapped by ``torch.tensor(..., requires_grad=True)``, customLoss.py:90): it
+shifts the loss value and contributes no gradient.  The frozen network is built exactly like the reference builds it
+(``torchvision.models.vgg19(weights=IMAGENET1K_V1).features``); ``CustomLoss(..., vgg_loss="auto")`` (the default) uses
+it when those weights are obtainable without a download (cached file, or a replaced constructor as in the offline
+tests) and otherwise logs a warning and lets the term contribute 0; ``vgg_loss=None`` switches it off, a callable
+``(output, target) -> scalar`` replaces it.  The high-frequency, penumbra and Sobel terms the reference computes and
+then discards (customLoss.py:139-185) are not computed.
 """
 from __future__ import annotations
+
+import logging
+import os
 
 import torch
 import torch.nn as nn
 
 import nsm
+
+
+class MultiLayerVGGLoss(nn.Module):
+    """Same constructor and module layout as the reference class (customLoss.py:7-41): ``feature_extractors`` is a
+    ModuleList of truncated ``vgg.features`` stacks sharing their layers, ``weights`` / ``mean`` / ``std`` buffers."""
+
+    def __init__(self, device, feature_layers=(2, 7, 12, 21, 30), weights=(0.25, 0.25, 0.3, 0.1, 0.1)):
+        super().__init__()
+        assert len(feature_layers) == len(weights), "特征层和权重数量必须相同"
+        from torchvision import models
+        vgg = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1).features.eval()
+        self.feature_extractors = nn.ModuleList()
+        for layer_idx in feature_layers:
+            layers = nn.Sequential(*list(vgg.children())[:layer_idx + 1])
+            for param in layers.parameters():
+                param.requires_grad = False
+            self.feature_extractors.append(layers.to(device))
+        w = torch.tensor(weights)
+        self.register_buffer("weights", (w / w.sum()).to(device))
+        self.register_buffer("mean", torch.tensor([0.485]).view(1, 1, 1, 1).to(device))
+        self.register_buffer("std", torch.tensor([0.229]).view(1, 1, 1, 1).to(device))
+        self.feature_layers = tuple(int(i) for i in feature_layers)
+        self._stack = list(vgg.children())[:max(self.feature_layers) + 1]
+        for i, m in enumerate(self._stack):
+            ok = (isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3) and m.padding == (1, 1) and m.stride == (1, 1)) \
+                or isinstance(m, nn.ReLU) or (isinstance(m, nn.MaxPool2d) and m.kernel_size == 2 and m.stride == 2)
+            if not ok:
+                raise nsm.NsmError(f"MultiLayerVGGLoss: unsupported layer {i}: {m}")
+        for i in self.feature_layers:
+            if not isinstance(self._stack[i], nn.Conv2d):
+                raise nsm.NsmError("MultiLayerVGGLoss: feature layers must be convolutions (pre-activation taps)")
+        self._packed = {}
+
+    def _weights(self, mode):
+        convs = [(i, m) for i, m in enumerate(self._stack) if isinstance(m, nn.Conv2d)]
+        key = (mode,) + tuple((m.weight.data_ptr(), m.weight._version) for _, m in convs)
+        hit = self._packed.get(mode)
+        if hit is None or hit[0] != key:
+            pk = {}
+            for i, m in convs:
+                cin, cout = m.in_channels, m.out_channels
+                if cout % 64:
+                    raise nsm.NsmError(f"MultiLayerVGGLoss: conv {i} has {cout} output channels (multiple of 64 needed)")
+                cip = max(64, cin)
+                wp = (nsm.pack_conv_weight_padded(m.weight, mode, cout, cip) if cip != cin
+                      else nsm.pack_conv_weight(m.weight, mode))
+                b = None if m.bias is None else m.bias.detach().to(torch.float32).contiguous()
+                pk[i] = (wp, b, cout)
+            self._packed[mode] = (key, pk)
+        return self._packed[mode][1]
+
+    @torch.no_grad()
+    def forward(self, output, target):
+        nsm.require_device(output)
+        # the reference's convolutions run in the autocast dtype under autocast (main.py:257) and in fp32 otherwise
+        mode = nsm.MODE_BF16 if torch.is_autocast_enabled() else nsm.MODE_FP32
+        o = output.detach().to(torch.float32).contiguous()
+        t = target.detach().to(torch.float32).contiguous()
+        if o.shape != t.shape or o.dim() != 4 or o.shape[1] != 1:
+            raise ValueError(f"expected output/target [B,1,H,W], got {tuple(o.shape)} / {tuple(t.shape)}")
+        pk = self._weights(mode)
+        x = nsm.vgg_input_prep(o, t, mode)
+        acc = torch.zeros(len(self.feature_layers), dtype=torch.float64, device=o.device)
+        numel = []
+        stack, i = self._stack, 0
+        while i < len(stack):
+            m = stack[i]
+            if isinstance(m, nn.Conv2d):
+                wp, b, cout = pk[i]
+                if i in self.feature_layers:          # pre-activation tap: raw conv + bias
+                    x, _, _ = nsm.conv_fwd(x, wp, 3, cout, mode, bias=b, lrelu=0)
+                    k = self.feature_layers.index(i)
+                    nsm.feature_l1(x, acc[k:k + 1])
+                    numel.append((x.shape[0] // 2) * m.out_channels * x.shape[2] * x.shape[3])
+                    i += 1
+                else:                                  # conv + bias + ReLU in one epilogue
+                    fused = i + 1 < len(stack) and isinstance(stack[i + 1], nn.ReLU)
+                    x, _, _ = nsm.conv_fwd(x, wp, 3, cout, mode, bias=b, lrelu=2 if fused else 0)
+                    i += 2 if fused else 1
+            elif isinstance(m, nn.ReLU):
+                pool = i + 1 < len(stack) and isinstance(stack[i + 1], nn.MaxPool2d)
+                x = nsm.relu_maxpool(x, pool)
+                i += 2 if pool else 1
+            else:                                      # MaxPool2d behind a fused ReLU (ReLU is idempotent)
+                x = nsm.relu_maxpool(x, True)
+                i += 1
+        per_layer = acc / torch.tensor(numel, dtype=torch.float64, device=o.device)
+        total = (per_layer * self.weights.to(torch.float64)).sum().to(torch.float32)
+        return total.detach()
+
+
+def vgg_weights_available():
+    """True when ``torchvision.models.vgg19(weights=IMAGENET1K_V1)`` can be built without touching the network."""
+    try:
+        from torchvision import models
+        fn = models.vgg19
+        if not getattr(fn, "__module__", "").startswith("torchvision."):
+            return True                                  # replaced constructor (offline harness / tests)
+        url = models.VGG19_Weights.IMAGENET1K_V1.url
+        return os.path.exists(os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(url)))
+    except Exception:
+        return False
+
+
+def make_vgg_term(device, vgg_loss):
+    """Resolves the ``vgg_loss`` constructor argument of CustomLoss / EnhancedCustomLoss."""
+    if vgg_loss != "auto":
+        return vgg_loss
+    if os.environ.get("NSM_VGG", "1") == "0":
+        return None
+    if vgg_weights_available():
+        return MultiLayerVGGLoss(device)
+    logging.warning("CustomLoss: VGG19 ImageNet weights are not cached and cannot be downloaded here; the perceptual "
+                    "term contributes 0 (it is a zero-gradient constant, customLoss.py:90)")
+    return None
 
 
 class _FusedL1(torch.autograd.Function):
@@ -53,13 +178,13 @@ class L1Loss(nn.Module):
 
 
 class CustomLoss(nn.Module):
-    def __init__(self, device, alpha=0.9, vgg_loss=None):
+    def __init__(self, device, alpha=0.9, vgg_loss="auto"):
         super().__init__()
         self.alpha = alpha
         self.device = device
         self.l1 = L1Loss()
         self._l1_checked = L1Loss(check_range=True)
-        self.vgg_loss = vgg_loss
+        self.vgg_loss = make_vgg_term(device, vgg_loss)
 
     def forward(self, output, target, inputs):
         nsm.require_device(output)

@@ -108,6 +108,11 @@ def _declare(lib):
     lib.nsm_wgrad.argtypes = [vp, vp, vp, vp] + [c_int] * 9 + [vp, c_size_t, vp, vp]
     lib.nsm_adamw_clip_step.argtypes = [c_int, POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(ll), fp, fp,
                                         fp, fp, fp, fp, c_int, vp, vp]
+    lib.nsm_vgg_input_prep.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp]
+    lib.nsm_relu_maxpool.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp]
+    lib.nsm_feature_l1.argtypes = [vp, vp, ll, c_int, vp, vp]
+    for name in ("nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1"):
+        getattr(lib, name).restype = c_int
     for name in TRAIN_EXPORTS:
         if name != "nsm_wgrad_workspace_bytes":
             getattr(lib, name).restype = c_int
@@ -131,6 +136,7 @@ EXPORTS = TRAIN_EXPORTS + [
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
     "nsm_channel_sums", "nsm_standardize", "nsm_perturb", "nsm_profile_enable", "nsm_profile_read",
+    "nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1",
 ]
 
 
@@ -371,6 +377,28 @@ def upsample_match(x: PlaneTensor, hd, wd, out_x8=False):
     check(lib().nsm_upsample_match(x.pair(), N, hs, ws, C, out.pair(), hd, wd, omode, stream_ptr()),
           "nsm_upsample_match")
     return out
+
+
+def vgg_input_prep(output, target, mode):
+    """[B,1,H,W] fp32 output / target -> PlaneTensor [2B,64,H,W] (3 real channels), customLoss.py:44-61."""
+    B, _, H, W = output.shape
+    x = PlaneTensor(2 * B, 64, H, W, mode, output.device)
+    check(lib().nsm_vgg_input_prep(output.data_ptr(), target.data_ptr(), B, H, W, mode, *_pp(x), stream_ptr()),
+          "nsm_vgg_input_prep")
+    return x
+
+
+def relu_maxpool(x: PlaneTensor, pool: bool):
+    N, C, H, W = x.shape
+    out = PlaneTensor(N, C, H // 2 if pool else H, W // 2 if pool else W, x.mode, x.p0.device)
+    check(lib().nsm_relu_maxpool(*_pp(x), N, H, W, C, int(pool), x.mode, *_pp(out), stream_ptr()), "nsm_relu_maxpool")
+    return out
+
+
+def feature_l1(f: PlaneTensor, acc):
+    """acc (fp64 device scalar view) += sum |a - b| over the two halves of the batch of f."""
+    N, C, H, W = f.shape
+    check(lib().nsm_feature_l1(*_pp(f), (N // 2) * C * H * W, f.mode, acc.data_ptr(), stream_ptr()), "nsm_feature_l1")
 
 
 def l1_loss_fwd_bwd(out, target=None, perturbed=(), coef_l1=0.0, coef_pert=0.0, want_grad=True):

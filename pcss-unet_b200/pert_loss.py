@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 import nsm
-from customLoss import L1Loss
+from customLoss import L1Loss, make_vgg_term
 
 
 def channel_stds_unbiased(x):
@@ -95,12 +95,12 @@ class PerturbationLoss(nn.Module):
 
 
 class EnhancedCustomLoss(nn.Module):
-    def __init__(self, device, alpha=0.9, perturb_weight=0.5, vgg_loss=None):
+    def __init__(self, device, alpha=0.9, perturb_weight=0.5, vgg_loss="auto"):
         super().__init__()
         self.alpha = alpha
         self.perturb_weight = perturb_weight
         self.l1 = L1Loss()
-        self.vgg_loss = vgg_loss
+        self.vgg_loss = make_vgg_term(device, vgg_loss)
         self.perturbation_loss = PerturbationLoss()
         logging.info(f"初始化增强版损失函数: alpha={alpha}, perturb_weight={perturb_weight}")
 

@@ -105,26 +105,16 @@ def main():
     import torchvision
 
     # ImageNet weights cannot be downloaded: the same seeded random VGG19 in both arms (SURVEY 8c "VGG19 weights")
-    _vgg19 = torchvision.models.vgg19
-
-    def vgg19_seeded(weights=None, **kw):
-        dev = torch.get_default_device()
-        torch.set_default_device("cpu")
-        try:
-            g = torch.random.get_rng_state()
-            torch.manual_seed(1234)
-            net = _vgg19(weights=None, **kw)
-            torch.random.set_rng_state(g)
-        finally:
-            torch.set_default_device(dev)
-        return net
-    torchvision.models.vgg19 = vgg19_seeded
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from vgg_fixture import seeded_vgg19
+    torchvision.models.vgg19 = seeded_vgg19
 
     os.makedirs(args.workdir, exist_ok=True)
     os.chdir(args.workdir)
     with open("config.ini", "w") as f:
         f.write(CONFIG.format(batch=args.batch, epochs=args.epochs, dropout=args.dropout, loss_type=args.loss_type))
     data_dir = make_dataset(args.workdir, 3 * args.batch, args.batch, args.height, args.width)
+    os.makedirs("checkpoints", exist_ok=True)     # main.py:539 does not create save_dir
 
     # a1: the statistics file main.load_dataset insists on (main.py:793-798) comes from calculate_dataset_stats -- the
     # drop-in's (GPU kernel) in the drop-in arm, the reference's (NumPy) in the reference arm

@@ -119,3 +119,59 @@ def test_device_feeder_matches_reference_standardisation(nsm, tmp_path):
             assert torch.equal(yb[j].cpu(), torch.from_numpy(labels[seen]))
             seen += 1
     assert seen == 7
+
+
+def test_vgg_perceptual_term(nsm):
+    """MultiLayerVGGLoss (customLoss.py:7-90) on the tcgen05 conv kernel: against the golden values of the unmodified
+    reference class (seeded VGG19 stand-in, tests/golden/make_golden_vgg.py), against the oracle on a larger, odd-sized
+    batch, and inside CustomLoss (value parity of `alpha*L1 + (1-alpha)*vgg`, customLoss.py:160,193)."""
+    import os
+    import sys
+    import numpy as np
+    import torchvision
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from vgg_fixture import cases, seeded_vgg19
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vgg_vectors.npz"))
+    saved = torchvision.models.vgg19
+    torchvision.models.vgg19 = seeded_vgg19
+    try:
+        from customLoss import CustomLoss, MultiLayerVGGLoss, vgg_weights_available
+        assert vgg_weights_available()
+        crit = MultiLayerVGGLoss("cuda")
+        full = CustomLoss("cuda", alpha=0.9)          # vgg_loss="auto" picks the term up
+        assert isinstance(full.vgg_loss, MultiLayerVGGLoss)
+    finally:
+        torchvision.models.vgg19 = saved
+    assert [k for k in crit.state_dict()][:3] == ["weights", "mean", "std"]
+    for tag, (o, t) in cases().items():
+        v = crit(o.cuda(), t.cuda())
+        assert v.dim() == 0 and not v.requires_grad
+        want = float(gold[f"vgg_{tag}"])
+        print(f"vgg {tag}: fp32 mode {v.item():.8f} reference {want:.8f}")
+        assert abs(v.item() - want) <= 1e-4 * want
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            vb = crit(o.cuda(), t.cuda())
+        wantb = float(gold[f"vgg_{tag}_bf16"])
+        print(f"vgg {tag}: bf16 mode {vb.item():.8f} reference (CPU autocast bf16) {wantb:.8f}")
+        assert abs(vb.item() - wantb) <= 1e-2 * wantb
+    o, t = cases()["a"]
+    og = o.cuda().requires_grad_(True)
+    loss = full(og, t.cuda(), None)
+    loss.backward()
+    assert abs(loss.item() - float(gold["custom_loss_a"])) <= 1e-5
+    assert torch.equal(og.grad.cpu(), oracle.custom_loss_grad(o, t, 0.9))      # the term carries no gradient
+    # larger, odd-sized batch (sizes that do not divide by 16: ragged tiles, floor in every max-pool) vs stock PyTorch
+    g = gen(5)
+    o = torch.rand(3, 1, 150, 202, generator=g)
+    t = torch.rand(3, 1, 150, 202, generator=g)
+    o[0, 0, 0, 0], t[0, 0, 1, 1] = float("nan"), float("inf")                    # scrubbed like customLoss.py:48-52
+    feats = seeded_vgg19().features.eval().cuda()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        want = oracle.vgg_perceptual_loss(o.cuda(), t.cuda(), feats).item()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    got = crit(o.cuda(), t.cuda()).item()
+    print(f"vgg 3x150x202: {got:.8f} vs stock PyTorch strict fp32 {want:.8f}")
+    assert abs(got - want) <= 1e-4 * want

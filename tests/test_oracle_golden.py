@@ -1,5 +1,7 @@
 """Pins the CPU oracle (oracle/) against vectors produced by the unmodified reference classes
 (tests/golden/make_golden.py -> tests/golden/reference_vectors.npz).  CPU only."""
+import os
+
 import numpy as np
 import torch
 
@@ -118,3 +120,23 @@ def test_custom_loss_value_and_grad(golden):
     t = torch.from_numpy(golden["loss_t"])
     assert abs(oracle.custom_loss(o, t, 0.9).item() - float(golden["loss_val"])) <= 1e-7
     assert torch.equal(oracle.custom_loss_grad(o, t, 0.9), torch.from_numpy(golden["loss_grad"]))
+
+
+def test_vgg_perceptual_term_matches_reference():
+    """oracle.vgg_perceptual_loss vs the unmodified reference MultiLayerVGGLoss / CustomLoss (tests/golden/
+    make_golden_vgg.py; same seeded VGG19 stand-in on both sides)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from vgg_fixture import cases, seeded_vgg19
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vgg_vectors.npz"))
+    feats = seeded_vgg19().features.eval()
+    torch.set_num_threads(1)
+    for tag, (o, t) in cases().items():
+        v = oracle.vgg_perceptual_loss(o, t, feats).item()
+        assert abs(v - float(gold[f"vgg_{tag}"])) <= 1e-6 * abs(float(gold[f"vgg_{tag}"])), (tag, v)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            vb = oracle.vgg_perceptual_loss(o, t, feats).item()
+        assert abs(vb - float(gold[f"vgg_{tag}_bf16"])) <= 1e-6 * abs(vb), (tag, vb)
+    o, t = cases()["a"]
+    full = oracle.custom_loss(o, t, 0.9, vgg_const=oracle.vgg_perceptual_loss(o, t, feats)).item()
+    assert abs(full - float(gold["custom_loss_a"])) <= 1e-6
