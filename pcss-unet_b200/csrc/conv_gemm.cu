@@ -777,11 +777,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // (BN_ = 128 for layers with 128 output channels: same 32-channel ring, six finer stages and the weight-tile multicast;
 //  its MMAs stay 128 wide.)
 constexpr int kWideBK = 32;
-template <int BN_>
+template <int BN_, int CG = 1>
 struct WideCfg {
   static constexpr int BN = BN_, BK = kWideBK;
   static constexpr int A_BYTES = 128 * 64;     // 128 pixels x 32 channels x 2 B (or 64 e4m3 bytes)
-  static constexpr int B_BYTES = BN * 64;
+  static constexpr int B_BYTES = (BN / CG) * 64;   // CTA pairs: every CTA holds half the rows of the weight tile
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   static constexpr int STAGING_BYTES = 8 * 4096;
   static constexpr int STAGES = (227 * 1024 - 1024 - 512 - STAGING_BYTES) / STAGE_BYTES;   // 4 (BN 256) / 6 (BN 128)
@@ -792,7 +792,12 @@ struct WideCfg {
 
 // MC = 2: two CTAs (a cluster) work on two pixel tiles of the same column block; each fetches HALF of the weight tile and
 // multicasts it into both -- a CTA then has 32 KB instead of 48 KB of TMA requests in flight per k-block.
-template <int BN_, int MC>
+// CG = 2 (with MC = 1): the two CTAs are a cta_group::2 PAIR executing one MMA of M = 256 (two pixel tiles) x N = BN.  Each
+// CTA keeps only ITS half of the weight rows in shared memory (no multicast, no second copy): per k-block a CTA writes
+// 32 KB and its tensor core reads 32 KB instead of 48 + 48 KB -- the single-CTA kernel sits on the shared-memory bandwidth
+// (96 B/clk written by TMA + 96 B/clk read by the MMAs at full tensor rate), the pair needs 64 + 64 -- and the 32 KB stages
+// make the ring six deep.  The leader (rank 0) issues all MMAs; both CTAs' TMA boxes complete on the leader's barrier.
+template <int BN_, int MC, int CG = 1>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -800,11 +805,14 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
                       const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                       const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                       const __grid_constant__ ConvKernelParams p) {
-  using Cfg = WideCfg<BN_>;
+  using Cfg = WideCfg<BN_, CG>;
+  static_assert(!(MC > 1 && CG > 1), "multicast clusters and CTA pairs are alternatives");
   constexpr int BN = Cfg::BN, NP = 2, TW = kTileW, TH = kTileH;
-  const int cta_rank = MC > 1 ? int(cluster_ctarank()) : 0;
-  const int it_first = int(blockIdx.x) / MC, it_step = int(gridDim.x) / MC;
-  const int it_count = MC > 1 ? p.total_pairs : p.total_items;
+  constexpr bool PAIR = CG == 2;
+  constexpr int CL = (MC > 1 || PAIR) ? 2 : 1;   // CTAs per cluster
+  const int cta_rank = CL > 1 ? int(cluster_ctarank()) : 0;
+  const int it_first = int(blockIdx.x) / CL, it_step = int(gridDim.x) / CL;
+  const int it_count = CL > 1 ? p.total_pairs : p.total_items;
   constexpr unsigned short kAllCtas = (unsigned short)((1u << MC) - 1);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -832,13 +840,16 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       mbar_init(&empty_bar[s], MC);   // free once every CTA that receives multicast slices in it has consumed it
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 8);
+    mbar_init(tempty_bar, 8 * CG);   // pairs: the leader's copy collects the epilogue warps of both CTAs
     for (int a = 0; a < 16; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
-  if (MC > 1) cluster_sync_all();
+  if (CL > 1) cluster_sync_all();
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -856,16 +867,30 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       uint32_t stage = 0, phase = 0;
       for (int item = it_first; item < it_count; item += it_step) {
         int n, y0, x0, nb;
-        if (MC > 1) decode_pair(p, item, cta_rank, n, y0, x0, nb);
+        if (CL > 1) decode_pair(p, item, cta_rank, n, y0, x0, nb);
         else decode_item<TW, TH>(p, item, n, y0, x0, nb);
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
           const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
           for (int kc = 0; kc < kc_per_tap; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + 2 * Cfg::A_BYTES;
+            if (PAIR) {
+              // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the pair
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              const int brow = nb * BN + cta_rank * (BN / 2);   // this CTA's rows of the weight tile
+              tma_load_4d_pair(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
+              tma_load_4d_pair(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
+              tma_load_2d_pair(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
+              tma_load_2d_pair(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
+              if (++stage == Cfg::STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
+            }
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_4d(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
             tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
             if (MC > 1) {   // this CTA's slice of the weight rows, into every CTA of the cluster
@@ -888,7 +913,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && (!PAIR || cta_rank == 0)) {   // CTA pairs: the leader issues for both
       uint32_t stage = 0, phase = 0, acc_phase = 0;
       const uint32_t d_main = tmem_base, d_cross = tmem_base + BN;
       for (int item = it_first; item < it_count; item += it_step) {
@@ -908,18 +933,26 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
               // accumulation over the whole K -- its terms are 2^-12 of the result, 576 truncations cost nothing -- so the
               // per-chunk drain touches only the main half of TMEM
               const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
-              umma_bf16(d_main, make_desc_sw64(a_hi + k * 32), make_desc_sw64(b_hi + k * 32), p.idesc_hi, accum);
-              umma_f8(d_cross, make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32),
-                      make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32), p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
+              if (PAIR) {
+                umma_bf16_pair(d_main, make_desc_sw64(a_hi + k * 32), make_desc_sw64(b_hi + k * 32), p.idesc_hi, accum);
+                umma_f8_pair(d_cross, make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32),
+                             make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32), p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
+              } else {
+                umma_bf16(d_main, make_desc_sw64(a_hi + k * 32), make_desc_sw64(b_hi + k * 32), p.idesc_hi, accum);
+                umma_f8(d_cross, make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32),
+                        make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32), p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
+              }
             }
-            if (MC > 1) umma_commit_mc(&empty_bar[stage], kAllCtas);
+            if (PAIR) umma_commit_pair(&empty_bar[stage]);
+            else if (MC > 1) umma_commit_mc(&empty_bar[stage], kAllCtas);
             else umma_commit(&empty_bar[stage]);
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(tfull_bar);
+          if (PAIR) umma_commit_pair(tfull_bar);
+          else umma_commit(tfull_bar);
         }
       }
     }
@@ -956,7 +989,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     };
     for (int item = it_first; item < it_count; item += it_step) {
       int n, y0, x0, nb;
-      if (MC > 1) decode_pair(p, item, cta_rank, n, y0, x0, nb);
+      if (CL > 1) decode_pair(p, item, cta_rank, n, y0, x0, nb);
       else decode_item<TW, TH>(p, item, n, y0, x0, nb);
       if (nb != st_nb) {
         flush_stats(st_nb);
@@ -998,7 +1031,10 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(tempty_bar);
+          else mbar_arrive(tempty_bar);
+        }
       }
 #pragma unroll
       for (int c0 = 0; c0 < HB; c0 += 32) {
@@ -1013,11 +1049,12 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   }
 
   tc_fence_before();
-  if (MC > 1) cluster_sync_all();   // the peer may still multicast into this CTA / signal its barriers
+  if (CL > 1) cluster_sync_all();   // the peer may still multicast into this CTA / signal its barriers / read its smem
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -1108,7 +1145,11 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   if (wide) BN = s.Cout % 256 == 0 ? 256 : 128;
   // ... in clusters of two CTAs that multicast halves of the weight tile to each other (NSM_NO_WIDE_MC=1: single CTAs)
   static const bool wide_mc_on = getenv("NSM_NO_WIDE_MC") == nullptr;
-  const int wide_mc = (wide && wide_mc_on && s.N * ((s.W + kTileW - 1) / kTileW) * ((s.H + kTileH - 1) / kTileH) >= 8) ? 2 : 1;
+  const int wide_tiles = s.N * ((s.W + kTileW - 1) / kTileW) * ((s.H + kTileH - 1) / kTileH);
+  // ... or, for 256-wide column blocks, as cta_group::2 pairs that split the weight tile (NSM_NO_WIDE_PAIR=1: multicast)
+  static const bool wide_pair_on = getenv("NSM_NO_WIDE_PAIR") == nullptr;
+  const bool wide_pair = wide && wide_pair_on && BN == 256 && wide_tiles >= 8;
+  const int wide_mc = (wide && !wide_pair && wide_mc_on && wide_tiles >= 8) ? 2 : 1;
   // CTA pairs (EXPERIMENTAL, NSM_CG2=1): bf16 and 8-bit-cross operands (the wide hi|lo MMA of the other formats needs the
   // whole weight tile in one CTA), BN = 128 tiles, at least two pixel tiles.  Verified by the parity tests, moves 25 % fewer
   // bytes through L2 -> shared memory (ncu: 14.5 GB against 19.3 GB for conv6 3x3), but is 30 % SLOWER at the moment: the
@@ -1136,7 +1177,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   const uint64_t K = uint64_t(s.taps) * s.Cin;
   const uint64_t bdims[2] = {K, uint64_t(s.Cout)};
   const uint64_t bstr[1] = {K * 2};
-  const uint32_t bbox[2] = {kblk, uint32_t(BN / (CG * wide_mc))};
+  const uint32_t bbox[2] = {kblk, uint32_t(BN / (CG * wide_mc * (wide_pair ? 2 : 1)))};
   const int planes = fmt_planes(s.fmt);
   for (int pl = 0; pl < planes; ++pl) {
     if (!in.p[pl] || !w.p[pl]) {
@@ -1203,7 +1244,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.x8 = s.fmt == kFmtF16X8 ? 1 : 0;
   kp.cross_scale = kp.x8 ? kX8CrossScale : 1.f;
   const uint32_t ef = fmt_is_f16(s.fmt) ? kFmtF16 : kFmtBF16;  // fp16 / e4m3 share the descriptor code 0
-  kp.idesc_hi = make_idesc_f16(128 * CG, BN, ef, ef, 0, 0);
+  kp.idesc_hi = make_idesc_f16(128 * CG * (wide_pair ? 2 : 1), BN, ef, ef, 0, 0);
   kp.idesc_wide = planes == 2 ? make_idesc_f16(128, 2 * BN, ef, ef, 0, 0) : kp.idesc_hi;
   kp.ep = ep;
   if (wide) {
@@ -1212,7 +1253,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     cfg.blockDim = dim3(kConvThreads);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    if (wide_mc == 2) {
+    if (wide_mc == 2 || wide_pair) {
       const int groups = kp.total_pairs < num_sms() / 2 ? kp.total_pairs : num_sms() / 2;
       cfg.gridDim = dim3(2 * groups);
       attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1234,9 +1275,11 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
       return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], maps[8],
                                 maps[9], kp);
     };
-    static bool attr_set[4] = {false, false, false, false};
+    static bool attr_set[5] = {false, false, false, false, false};
     cudaError_t e;
-    if (BN == 256)
+    if (wide_pair)
+      e = launch(conv_gemm_wide_kernel<256, 1, 2>, WideCfg<256, 2>::SMEM_BYTES, attr_set[4]);
+    else if (BN == 256)
       e = wide_mc == 2 ? launch(conv_gemm_wide_kernel<256, 2>, WideCfg<256>::SMEM_BYTES, attr_set[0])
                        : launch(conv_gemm_wide_kernel<256, 1>, WideCfg<256>::SMEM_BYTES, attr_set[1]);
     else
@@ -1244,7 +1287,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
                        : launch(conv_gemm_wide_kernel<128, 1>, WideCfg<128>::SMEM_BYTES, attr_set[3]);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
-      set_error("conv_gemm_wide<%d,%d> launch failed: %s", BN, wide_mc, cudaGetErrorString(e));
+      set_error("conv_gemm_wide<%d,%d,%d> launch failed: %s", BN, wide_mc, wide_pair ? 2 : 1, cudaGetErrorString(e));
       return 1;
     }
     count_launch();
