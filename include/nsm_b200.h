@@ -213,6 +213,26 @@ int nsm_sigmoid_shuffle_bwd(const float* dy, const float* y, int N, int h, int w
 int nsm_pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int dgrad, int mode,
                                 void* plane0, void* plane1, void* stream);
 int nsm_pad_vector(const float* src, int n, int npad, float fill, int round_bf16, float* dst, void* stream);
+/* Pixel-packed thin layers (conv2, conv9 1x1, conv10: 16 / 4 channels).  Instead of zero-padding 16 channels to the 64 the
+ * tensor-core kernel needs, four horizontally adjacent pixels x C channels are addressed as ONE pixel of 4C "virtual"
+ * channels ([N,H,W,C] and [N,H,W/4,4C] are the same bytes; W % 4 == 0).  A 1x1 convolution becomes a 1x1 convolution
+ * with a block-diagonal weight, a 3x3 convolution a 3x3 convolution over pixel groups with a banded weight
+ * (nsm_pack_conv_weight_px4; CoutV / CinV = 4*Cout / 4*Cin, or 64 when that is smaller: conv10); nsm_conv_fwd and
+ * nsm_wgrad then run on the virtual shapes.  nsm_px4_reduce_dw folds the virtual weight gradient [CoutV][CinV][k][k]
+ * back to [Cout][Cin][k][k]; nsm_fold_channel_sums folds per-virtual-channel sums (BatchNorm statistics of the conv
+ * epilogue, bias gradients) to the real channels: out[v][c] = sum_g in[v][g*C + c]; nsm_tile_vector repeats a bias. */
+int nsm_pack_conv_weight_px4(const float* w, int Cout, int Cin, int ksize, int CoutV, int CinV, int dgrad, int mode,
+                             void* plane0, void* plane1, void* stream);
+int nsm_px4_reduce_dw(const float* dwv, int Cout, int Cin, int ksize, int CoutV, int CinV, float* dw, void* stream);
+int nsm_fold_channel_sums(const double* in, int nvec, int CV, int groups, int C, double* out, void* stream);
+int nsm_tile_vector(const float* src, int n, int rep, int npad, float fill, int round_bf16, float* dst, void* stream);
+/* input / output stages with un-padded tensors: x16 planes [N,h,w,16]; c10 planes [N,h,w/4,64] (pixel po of a group
+ * holds its 4 channels at [4*po, 4*po+4), channels 16..63 zero) */
+int nsm_train_input_prep_c16(const float* x, int N, int Hin, int Win, void* out0, void* out1, int mode, void* stream);
+int nsm_train_input_grad_c16(const void* d0, const void* d1, int N, int H, int W, float* dx, int mode, void* stream);
+int nsm_sigmoid_shuffle_fwd_px4(const void* c0, const void* c1, int N, int h, int w, int mode, float* y, void* stream);
+int nsm_sigmoid_shuffle_bwd_px4(const float* dy, const float* y, int N, int h, int w, int mode, void* d0, void* d1,
+                                void* stream);
 /* weight gradient dW = dz^T (*) x  (autograd of nn.Conv2d): tcgen05 GEMM over the pixel axis with split-K */
 size_t nsm_wgrad_workspace_bytes(int N, int H, int W, int Cout, int Cin, int ksize, int mode);
 int nsm_wgrad(const void* dz0, const void* dz1, const void* x0, const void* x1, int N, int H, int W, int Cout, int Cin,

@@ -773,6 +773,35 @@ int nsm_pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, in
                                 void* plane0, void* plane1, void* stream) {
   return pack_conv_weight_padded(w, Cout, Cin, ksize, CoutP, CinP, dgrad, mode, plane0, plane1, S(stream));
 }
+int nsm_train_input_prep_c16(const float* x, int N, int Hin, int Win, void* out0, void* out1, int mode, void* stream) {
+  ProfScope ps_("train_input_prep", 0.0, double(N) * Hin * Win * (4.0 + 2.0 * fmt_planes(mode)), S(stream));
+  return train_input_prep(x, N, Hin, Win, mk(out0, out1), mode, S(stream), 16);
+}
+int nsm_train_input_grad_c16(const void* d0, const void* d1, int N, int H, int W, float* dx, int mode, void* stream) {
+  return train_input_grad(mk(d0, d1), N, H, W, dx, mode, S(stream), 16);
+}
+int nsm_sigmoid_shuffle_fwd_px4(const void* c0, const void* c1, int N, int h, int w, int mode, float* y, void* stream) {
+  ProfScope ps_("sigmoid_shuffle_fwd", 0.0, double(N) * h * w * (16.0 + 32.0 * fmt_planes(mode)), S(stream));
+  return sigmoid_shuffle_fwd(mk(c0, c1), N, h, w, mode, y, S(stream), 1);
+}
+int nsm_sigmoid_shuffle_bwd_px4(const float* dy, const float* y, int N, int h, int w, int mode, void* d0, void* d1,
+                                void* stream) {
+  ProfScope ps_("sigmoid_shuffle_bwd", 0.0, double(N) * h * w * (32.0 + 32.0 * fmt_planes(mode)), S(stream));
+  return sigmoid_shuffle_bwd(dy, y, N, h, w, mode, mk(d0, d1), S(stream), 1);
+}
+int nsm_pack_conv_weight_px4(const float* w, int Cout, int Cin, int ksize, int CoutV, int CinV, int dgrad, int mode,
+                             void* plane0, void* plane1, void* stream) {
+  return pack_conv_weight_px4(w, Cout, Cin, ksize, CoutV, CinV, dgrad, mode, plane0, plane1, S(stream));
+}
+int nsm_px4_reduce_dw(const float* dwv, int Cout, int Cin, int ksize, int CoutV, int CinV, float* dw, void* stream) {
+  return px4_reduce_dw(dwv, Cout, Cin, ksize, CoutV, CinV, dw, S(stream));
+}
+int nsm_fold_channel_sums(const double* in, int nvec, int CV, int groups, int C, double* out, void* stream) {
+  return fold_channel_sums(in, nvec, CV, groups, C, out, S(stream));
+}
+int nsm_tile_vector(const float* src, int n, int rep, int npad, float fill, int round_bf16, float* dst, void* stream) {
+  return tile_vector(src, n, rep, npad, fill, round_bf16, dst, S(stream));
+}
 int nsm_pad_vector(const float* src, int n, int npad, float fill, int round_bf16, float* dst, void* stream) {
   return pad_vector(src, n, npad, fill, round_bf16, dst, S(stream));
 }

@@ -30,14 +30,14 @@ static inline int grid_for(long long work, int block, int cap = 148 * 16) {
 constexpr int kBatch = 4;   // independent pixels in flight per thread (memory-level parallelism)
 
 // Block-level per-channel reduction of NV value sets; thread t owns channel group (t % groups), 256 threads.
-template <int NV>
-__device__ __forceinline__ void block_channel_reduce(const double (&acc)[NV][8], int C, double* out) {
+template <int NV, typename T>
+__device__ __forceinline__ void block_channel_reduce(const T (&acc)[NV][8], int C, double* out) {
   __shared__ double red[256][NV * 8 + 1];
   const int tid = threadIdx.x, groups = C / 8, lanes = 256 / groups;
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) red[tid][v * 8 + e] = acc[v][e];
+    for (int e = 0; e < 8; ++e) red[tid][v * 8 + e] = double(acc[v][e]);
   __syncthreads();
   for (int i = tid; i < NV * C; i += 256) {
     const int v = i / C, c = i % C;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const Planes z, long long
       acc[1][e] += double(fq[e]);
     }
   }
-  block_channel_reduce<2>(acc, C, sums);
+  block_channel_reduce<2, double>(acc, C, sums);
 }
 
 static int check_32(const char* who, long long total) {
@@ -193,7 +193,7 @@ __device__ __forceinline__ void bn_act8(float* v, const BnActParams& p, const Ch
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
+__global__ void __launch_bounds__(256, 3) bn_act_kernel(const BnActParams p) {
   const int cgs = p.C / 8;
   const bool rb = FMT == kFmtBf16;
   const long long total = (long long)p.N * p.H * p.W * cgs;
@@ -201,21 +201,39 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
   const unsigned HW = (unsigned)(p.H * p.W);
   // the grid stride (gridDim.x * 256) is a multiple of cgs, so a thread's channel group never changes
   const Chan8 ch = load_chan8(p.scale, p.shift, int((blockIdx.x * 256u + threadIdx.x) & (unsigned)(cgs - 1)) * 8);
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const unsigned iu = (unsigned)i;                   // total < 2^32 (host check): 32-bit index math only
-    const int cg = int(iu & (unsigned)(cgs - 1));
-    const unsigned pix = iu >> cg_shift;
-    const int n = int(pix / HW);
-    float v[8];
-    load8(p.z, (size_t)pix * p.C + cg * 8, FMT, v);
-    bn_act8(v, p, ch, n, cg * 8, rb);
-    if (p.residual.p[0]) {
-      float r[8];
-      load8(p.residual, (size_t)pix * p.C + cg * 8, FMT, r);
+  // kBatch independent 16-byte loads (x2 with a skip tensor) per thread and iteration: the pass is latency-bound otherwise
+  // (ncu: 47-53 % of DRAM peak with one load in flight per thread)
+  const bool has_res = p.residual.p[0] != nullptr;
+  const long long step = (long long)gridDim.x * 256;
+  for (long long i0 = blockIdx.x * 256LL + threadIdx.x; i0 < total; i0 += kBatch * step) {
+    Raw8 rz[kBatch], rr[kBatch];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = rb ? rbf(v[e] + r[e]) : v[e] + r[e];
+    for (int u = 0; u < kBatch; ++u) {
+      const long long i = i0 + u * step;
+      if (i < total) {
+        rz[u] = load_raw8(p.z, (size_t)i * 8, FMT);    // element offset (pix * C + cg * 8) == i * 8
+        if (has_res) rr[u] = load_raw8(p.residual, (size_t)i * 8, FMT);
+      }
     }
-    store8(p.out, (size_t)pix * p.C + cg * 8, FMT, v);
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const long long i = i0 + u * step;
+      if (i >= total) break;
+      const unsigned iu = (unsigned)i;                 // total < 2^32 (host check): 32-bit index math only
+      const int cg = int(iu & (unsigned)(cgs - 1));
+      const unsigned pix = iu >> cg_shift;
+      const int n = int(pix / HW);
+      float v[8];
+      unpack8(rz[u], FMT, v);
+      bn_act8(v, p, ch, n, cg * 8, rb);
+      if (has_res) {
+        float r[8];
+        unpack8(rr[u], FMT, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = rb ? rbf(v[e] + r[e]) : v[e] + r[e];
+      }
+      store8(p.out, (size_t)i * 8, FMT, v);
+    }
   }
 }
 
@@ -238,13 +256,19 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
     float s[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    Raw8 rq[4];   // the quad's four loads are issued before any of them is used
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int y = 2 * qy + (k >> 1), x = 2 * qx + (k & 1);
+      if (y < p.H && x < p.W) rq[k] = load_raw8(p.z, (((size_t)n * p.H + y) * p.W + x) * p.C + cg * 8, FMT);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int y = 2 * qy + (k >> 1), x = 2 * qx + (k & 1);
       if (y < p.H && x < p.W) {
         const size_t pix = ((size_t)n * p.H + y) * p.W + x;
         float v[8];
-        load8(p.z, pix * p.C + cg * 8, FMT, v);
+        unpack8(rq[k], FMT, v);
         bn_act8(v, p, ch, n, cg * 8, rb);
         store8(p.out, pix * p.C + cg * 8, FMT, v);
 #pragma unroll
@@ -346,78 +370,14 @@ __device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, const BwdChan8& 
   }
 }
 
-template <int NPL>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
-  const int groups = p.C / 8, lanes = 256 / groups;
-  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
-  const long long P = (long long)p.N * p.H * p.W;
-  const unsigned HW = (unsigned)(p.H * p.W);
-  BwdChan8 ch;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    ch.s[e] = __ldg(p.scale + cg * 8 + e);
-    ch.t[e] = __ldg(p.shift + cg * 8 + e);
-  }
-  double acc[2][8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.0;
-  const long long stride = (long long)gridDim.x * lanes;
-  long long px = (long long)blockIdx.x * lanes + lane;
-  while (px < P) {
-    float fs[8], fq[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) fs[e] = fq[e] = 0.f;
-    for (int it = 0; it < 8 && px < P; ++it, px += 2 * stride) {
-      const bool ok1 = px + stride < P;
-      const size_t e0 = (size_t)px * p.C + cg * 8, e1 = (size_t)(px + stride) * p.C + cg * 8;
-      Raw8 dy0 = load_raw8_t<NPL>(p.dy, e0), z0 = load_raw8_t<NPL>(p.z, e0), dy1, z1;
-      if (ok1) {
-        dy1 = load_raw8_t<NPL>(p.dy, e1);
-        z1 = load_raw8_t<NPL>(p.z, e1);
-      }
-      float g[8], z[8];
-      bn_bwd_g8<NPL>(p, ch, dy0, z0, int((unsigned)px / HW), cg * 8, g, z);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        fs[e] += g[e];
-        fq[e] = fmaf(g[e], z[e], fq[e]);
-      }
-      if (ok1) {
-        bn_bwd_g8<NPL>(p, ch, dy1, z1, int((unsigned)(px + stride) / HW), cg * 8, g, z);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          fs[e] += g[e];
-          fq[e] = fmaf(g[e], z[e], fq[e]);
-        }
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[0][e] += double(fs[e]);
-      acc[1][e] += double(fq[e]);
-    }
-  }
-  block_channel_reduce<2>(acc, p.C, p.sums);
-}
-
-int bn_bwd_reduce(const BnBwdParams& p, cudaStream_t st) {
-  if (check_c("bn_bwd_reduce", p.C)) return 1;
-  if (p.fmt == kFmtF16x2) {
-    set_error("bn_bwd: training tensors use fmt 0 or 2");
-    return 1;
-  }
-  const long long P = (long long)p.N * p.H * p.W;
-  const int lanes = 256 / (p.C / 8);
-  const int grid = grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8);
-  if (p.fmt == kFmtBf16) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(p);
-  else bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(p);
-  NSM_CHECK_LAUNCH("bn_bwd_reduce");
-  return 0;
-}
-
-template <int NPL>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+// One kernel for both passes (APPLY = false: the two sums; true: dz and the conv-bias gradient).  A thread owns one
+// 8-channel group and walks pixels with a grid stride; PB pixels = 2*PB independent 16-byte loads are in flight per thread
+// (ncu of the first version: 128 registers, 24 % occupancy, 40-46 % of DRAM peak -- latency-bound).  Per-thread runs are
+// short (P / (grid * lanes) pixels), so the per-thread accumulators are fp32; the cross-thread reduction is fp64.
+template <int NPL, bool APPLY>
+__global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
   constexpr bool rb = NPL == 1;
+  constexpr int PB = NPL == 1 ? 4 : 2;
   const int groups = p.C / 8, lanes = 256 / groups;
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const long long P = (long long)p.N * p.H * p.W;
@@ -429,64 +389,89 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
     const int c = cg * 8 + e;
     ch.s[e] = __ldg(p.scale + c);
     ch.t[e] = __ldg(p.shift + c);
-    const double mu = double(__ldg(p.mean + c)), is = double(__ldg(p.invstd + c));
-    const double m1 = p.sums[c] / double(P);
-    const double m2 = (p.sums[p.C + c] - mu * p.sums[c]) * is / double(P);
-    A[e] = float(-double(ch.s[e]) * is * m2);
-    B[e] = float(-double(ch.s[e]) * m1 + double(ch.s[e]) * is * m2 * mu);
+    if (APPLY) {
+      const double mu = double(__ldg(p.mean + c)), is = double(__ldg(p.invstd + c));
+      const double m1 = p.sums[c] / double(P);
+      const double m2 = (p.sums[p.C + c] - mu * p.sums[c]) * is / double(P);
+      A[e] = float(-double(ch.s[e]) * is * m2);
+      B[e] = float(-double(ch.s[e]) * m1 + double(ch.s[e]) * is * m2 * mu);
+    }
   }
-  double acc[1][8];
+  float acc[APPLY ? 1 : 2][8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[0][e] = 0.0;
+  for (int e = 0; e < 8; ++e) {
+    acc[0][e] = 0.f;
+    if (!APPLY) acc[1][e] = 0.f;
+  }
   const long long stride = (long long)gridDim.x * lanes;
-  long long px = (long long)blockIdx.x * lanes + lane;
-  while (px < P) {
-    float fs[8];
+  for (long long px = (long long)blockIdx.x * lanes + lane; px < P; px += PB * stride) {
+    Raw8 rdy[PB], rz[PB];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) fs[e] = 0.f;
-    for (int it = 0; it < 8 && px < P; ++it, px += 2 * stride) {
-      const bool ok1 = px + stride < P;
-      const size_t e0 = (size_t)px * p.C + cg * 8, e1 = (size_t)(px + stride) * p.C + cg * 8;
-      Raw8 dy0 = load_raw8_t<NPL>(p.dy, e0), z0 = load_raw8_t<NPL>(p.z, e0), dy1, z1;
-      if (ok1) {
-        dy1 = load_raw8_t<NPL>(p.dy, e1);
-        z1 = load_raw8_t<NPL>(p.z, e1);
+    for (int u = 0; u < PB; ++u) {
+      const long long q = px + u * stride;
+      if (q < P) {
+        rdy[u] = load_raw8_t<NPL>(p.dy, (size_t)q * p.C + cg * 8);
+        rz[u] = load_raw8_t<NPL>(p.z, (size_t)q * p.C + cg * 8);
       }
-      float g[8], z[8], dz[8];
-      bn_bwd_g8<NPL>(p, ch, dy0, z0, int((unsigned)px / HW), cg * 8, g, z);
+    }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float t = fmaf(ch.s[e], g[e], fmaf(A[e], z[e], B[e]));
-        if (rb) t = rbf(t);
-        dz[e] = t;
-        fs[e] += t;
-      }
-      store8(p.dz, e0, p.fmt, dz);
-      if (ok1) {
-        bn_bwd_g8<NPL>(p, ch, dy1, z1, int((unsigned)(px + stride) / HW), cg * 8, g, z);
+    for (int u = 0; u < PB; ++u) {
+      const long long q = px + u * stride;
+      if (q >= P) break;
+      float g[8], z[8];
+      bn_bwd_g8<NPL>(p, ch, rdy[u], rz[u], int((unsigned)q / HW), cg * 8, g, z);
+      if (APPLY) {
+        float dz[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float t = fmaf(ch.s[e], g[e], fmaf(A[e], z[e], B[e]));
           if (rb) t = rbf(t);
           dz[e] = t;
-          fs[e] += t;
+          acc[0][e] += t;
         }
-        store8(p.dz, e1, p.fmt, dz);
+        store8(p.dz, (size_t)q * p.C + cg * 8, p.fmt, dz);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[0][e] += g[e];
+          acc[1][e] = fmaf(g[e], z[e], acc[1][e]);
+        }
       }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[0][e] += double(fs[e]);
   }
-  if (p.dbias) block_channel_reduce<1>(acc, p.C, p.dbias);
+  if (!APPLY) block_channel_reduce<APPLY ? 1 : 2, float>(acc, p.C, p.sums);
+  else if (p.dbias) block_channel_reduce<APPLY ? 1 : 2, float>(acc, p.C, p.dbias);
+}
+
+static int bn_bwd_grid(const BnBwdParams& p) {
+  const long long P = (long long)p.N * p.H * p.W;
+  const int lanes = 256 / (p.C / 8);
+  // per-thread runs of <= 64 pixels keep the fp32 accumulators exact enough; at least 148 * 8 blocks when there is work
+  long long want = (P + lanes * 64 - 1) / (lanes * 64);
+  if (want < 148 * 8) want = (P + lanes * 8 - 1) / (lanes * 8) < 148 * 8 ? (P + lanes * 8 - 1) / (lanes * 8) : 148 * 8;
+  if (want < 1) want = 1;
+  if (want > 148 * 64) want = 148 * 64;
+  return int(want);
+}
+
+int bn_bwd_reduce(const BnBwdParams& p, cudaStream_t st) {
+  if (check_c("bn_bwd_reduce", p.C)) return 1;
+  if (p.fmt == kFmtF16x2) {
+    set_error("bn_bwd: training tensors use fmt 0 or 2");
+    return 1;
+  }
+  const int grid = bn_bwd_grid(p);
+  if (p.fmt == kFmtBf16) bn_bwd_kernel<1, false><<<grid, 256, 0, st>>>(p);
+  else bn_bwd_kernel<2, false><<<grid, 256, 0, st>>>(p);
+  NSM_CHECK_LAUNCH("bn_bwd_reduce");
+  return 0;
 }
 
 int bn_bwd_apply(const BnBwdParams& p, cudaStream_t st) {
   if (check_c("bn_bwd_apply", p.C)) return 1;
-  const long long P = (long long)p.N * p.H * p.W;
-  const int lanes = 256 / (p.C / 8);
-  const int grid = grid_for((P + lanes * 16 - 1) / (lanes * 16), 1, 148 * 8);
-  if (p.fmt == kFmtBf16) bn_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(p);
-  else bn_bwd_apply_kernel<2><<<grid, 256, 0, st>>>(p);
+  const int grid = bn_bwd_grid(p);
+  if (p.fmt == kFmtBf16) bn_bwd_kernel<1, true><<<grid, 256, 0, st>>>(p);
+  else bn_bwd_kernel<2, true><<<grid, 256, 0, st>>>(p);
   NSM_CHECK_LAUNCH("bn_bwd_apply");
   return 0;
 }
@@ -851,15 +836,16 @@ int bilinear_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes&
 // network input / output stages
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) train_input_prep_kernel(const float* __restrict__ x, int N, int Hin, int Win,
-                                                               const Planes out, int fmt) {
+                                                               const Planes out, int fmt, int cpad) {
   const int H = Hin - (Hin & 1), W = Win - (Win & 1), h = H / 2, w = W / 2;
   const bool resize = (Hin & 1) || (Win & 1);
   const bool rb = fmt == kFmtBf16;
-  // one thread = one output pixel x one 8-channel group of the 64 padded channels (groups 2..7 are zero)
-  const long long total = (long long)N * h * w * 8;
+  // one thread = one output pixel x one 8-channel group of the cpad (16, or 64 zero-padded) channels (groups >= 2 are zero)
+  const int gshift = cpad == 16 ? 1 : 3;
+  const long long total = ((long long)N * h * w) << gshift;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int cg = int(i & 7);
-    const long long pix = i >> 3;
+    const int cg = int(i & ((1 << gshift) - 1));
+    const long long pix = i >> gshift;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
@@ -886,18 +872,22 @@ __global__ void __launch_bounds__(256) train_input_prep_kernel(const float* __re
         v[e] = rb ? rbf(val) : val;
       }
     }
-    store8(out, (size_t)pix * 64 + cg * 8, fmt, v);
+    store8(out, (size_t)pix * cpad + cg * 8, fmt, v);
   }
 }
-int train_input_prep(const float* x, int N, int Hin, int Win, const Planes& out, int fmt, cudaStream_t st) {
-  const long long total = (long long)N * (Hin / 2) * (Win / 2) * 8;
-  train_input_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, N, Hin, Win, out, fmt);
+int train_input_prep(const float* x, int N, int Hin, int Win, const Planes& out, int fmt, cudaStream_t st, int cpad) {
+  if (cpad != 16 && cpad != 64) {
+    set_error("train_input_prep: channel pitch %d (16 or 64)", cpad);
+    return 1;
+  }
+  const long long total = (long long)N * (Hin / 2) * (Win / 2) * (cpad / 8);
+  train_input_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, N, Hin, Win, out, fmt, cpad);
   NSM_CHECK_LAUNCH("train_input_prep");
   return 0;
 }
 
 __global__ void __launch_bounds__(256) train_input_grad_kernel(const Planes dx16, int N, int H, int W, float* dx,
-                                                               int fmt) {
+                                                               int fmt, int cpad) {
   const int h = H / 2, w = W / 2;
   const long long total = (long long)N * h * w * 2;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -908,7 +898,7 @@ __global__ void __launch_bounds__(256) train_input_grad_kernel(const Planes dx16
     const int n = int(t / (unsigned)h);
     const int py = int(t - (unsigned)n * (unsigned)h);
     float v[8];
-    load8(dx16, (size_t)pix * 64 + cg * 8, fmt, v);
+    load8(dx16, (size_t)pix * cpad + cg * 8, fmt, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int ch = cg * 8 + e;
@@ -917,28 +907,34 @@ __global__ void __launch_bounds__(256) train_input_grad_kernel(const Planes dx16
     }
   }
 }
-int train_input_grad(const Planes& dx16, int N, int H, int W, float* dx, int fmt, cudaStream_t st) {
+int train_input_grad(const Planes& dx16, int N, int H, int W, float* dx, int fmt, cudaStream_t st, int cpad) {
   if ((H & 1) || (W & 1)) {
     set_error("train_input_grad: odd input sizes are not supported for the input gradient");
     return 1;
   }
-  train_input_grad_kernel<<<grid_for((long long)N * (H / 2) * (W / 2) * 2, 256), 256, 0, st>>>(dx16, N, H, W, dx, fmt);
+  if (cpad != 16 && cpad != 64) {
+    set_error("train_input_grad: channel pitch %d (16 or 64)", cpad);
+    return 1;
+  }
+  train_input_grad_kernel<<<grid_for((long long)N * (H / 2) * (W / 2) * 2, 256), 256, 0, st>>>(dx16, N, H, W, dx, fmt, cpad);
   NSM_CHECK_LAUNCH("train_input_grad");
   return 0;
 }
 
 __global__ void __launch_bounds__(256) sigmoid_shuffle_fwd_kernel(const Planes c10, int N, int h, int w, int fmt,
-                                                                  float* y) {
+                                                                  float* y, int px4) {
   const bool rb = fmt == kFmtBf16;
   const long long total = (long long)N * h * w;
   const int W = 2 * w, H = 2 * h;
   for (long long pix = blockIdx.x * 256LL + threadIdx.x; pix < total; pix += (long long)gridDim.x * 256) {
     float v[8];
-    load8(c10, (size_t)pix * 64, fmt, v);
+    // px4: four pixels share one 64-channel row, pixel po of the group holds its 4 channels at [4*po, 4*po+4)
+    const int off = px4 ? int(pix & 3) * 4 : 0;
+    load8(c10, px4 ? (size_t)(pix >> 2) * 64 + (off & 8) : (size_t)pix * 64, fmt, v);
     float r[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float s = 1.f / (1.f + expf(-v[k]));
+      const float s = 1.f / (1.f + expf(-((off & 4) ? v[4 + k] : v[k])));
       r[k] = rb ? rbf(s) : s;
     }
     const unsigned t = (unsigned)pix / (unsigned)w;
@@ -950,10 +946,51 @@ __global__ void __launch_bounds__(256) sigmoid_shuffle_fwd_kernel(const Planes c
     *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
   }
 }
-int sigmoid_shuffle_fwd(const Planes& c10, int N, int h, int w, int fmt, float* y, cudaStream_t st) {
-  sigmoid_shuffle_fwd_kernel<<<grid_for((long long)N * h * w, 256), 256, 0, st>>>(c10, N, h, w, fmt, y);
+int sigmoid_shuffle_fwd(const Planes& c10, int N, int h, int w, int fmt, float* y, cudaStream_t st, int px4) {
+  if (px4 && (w & 3)) {
+    set_error("sigmoid_shuffle_fwd: pixel-packed layout needs w %% 4 == 0 (w = %d)", w);
+    return 1;
+  }
+  sigmoid_shuffle_fwd_kernel<<<grid_for((long long)N * h * w, 256), 256, 0, st>>>(c10, N, h, w, fmt, y, px4);
   NSM_CHECK_LAUNCH("sigmoid_shuffle_fwd");
   return 0;
+}
+
+// px4: one thread = one group of four pixels x one 8-channel group: groups 0 and 1 carry two pixels each, 2..7 are zero
+__global__ void __launch_bounds__(256) sigmoid_shuffle_bwd_px4_kernel(const float* __restrict__ dy,
+                                                                      const float* __restrict__ y, int N, int h, int w,
+                                                                      int fmt, const Planes dc10) {
+  const bool rb = fmt == kFmtBf16;
+  const long long total = (long long)N * h * (w / 4) * 8;
+  const int W = 2 * w, H = 2 * h;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cg = int(i & 7);
+    const long long grp = i >> 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (cg < 2) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const long long pix = grp * 4 + cg * 2 + half;
+        const unsigned t = (unsigned)pix / (unsigned)w;
+        const int x = int((unsigned)pix - t * (unsigned)w);
+        const unsigned n = t / (unsigned)h;
+        const int yy = int(t - n * (unsigned)h);
+        const size_t o = ((size_t)n * H + 2 * yy) * W + 2 * x;
+        const float2 g0 = *reinterpret_cast<const float2*>(dy + o), g1 = *reinterpret_cast<const float2*>(dy + o + W);
+        const float2 s0 = *reinterpret_cast<const float2*>(y + o), s1 = *reinterpret_cast<const float2*>(y + o + W);
+        const float g[4] = {g0.x, g0.y, g1.x, g1.y}, s[4] = {s0.x, s0.y, s1.x, s1.y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float gg = rb ? rbf(g[k]) : g[k];
+          const float d = gg * ((1.f - s[k]) * s[k]);
+          v[half * 4 + k] = rb ? rbf(d) : d;
+        }
+      }
+    }
+    store8(dc10, (size_t)grp * 64 + cg * 8, fmt, v);
+  }
 }
 
 __global__ void __launch_bounds__(256) sigmoid_shuffle_bwd_kernel(const float* __restrict__ dy,
@@ -988,8 +1025,13 @@ __global__ void __launch_bounds__(256) sigmoid_shuffle_bwd_kernel(const float* _
   }
 }
 int sigmoid_shuffle_bwd(const float* dy, const float* y, int N, int h, int w, int fmt, const Planes& dc10,
-                        cudaStream_t st) {
-  sigmoid_shuffle_bwd_kernel<<<grid_for((long long)N * h * w * 8, 256), 256, 0, st>>>(dy, y, N, h, w, fmt, dc10);
+                        cudaStream_t st, int px4) {
+  if (px4 && (w & 3)) {
+    set_error("sigmoid_shuffle_bwd: pixel-packed layout needs w %% 4 == 0 (w = %d)", w);
+    return 1;
+  }
+  if (px4) sigmoid_shuffle_bwd_px4_kernel<<<grid_for((long long)N * h * (w / 4) * 8, 256), 256, 0, st>>>(dy, y, N, h, w, fmt, dc10);
+  else sigmoid_shuffle_bwd_kernel<<<grid_for((long long)N * h * w * 8, 256), 256, 0, st>>>(dy, y, N, h, w, fmt, dc10);
   NSM_CHECK_LAUNCH("sigmoid_shuffle_bwd");
   return 0;
 }
@@ -1028,6 +1070,116 @@ int pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, int Co
   pack_conv_weight_padded_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, Cout, Cin, taps, CoutP, CinP, flip_transpose,
                                                                        fmt, (unsigned short*)hi, (unsigned short*)lo);
   NSM_CHECK_LAUNCH("pack_conv_weight_padded");
+  return 0;
+}
+
+// Pixel-packed thin layers.  A convolution with few channels (16 -> 16, 16 -> 64, 64 -> 16, 16 -> 4) runs on the tcgen05
+// kernel -- which wants multiples of 64 channels -- WITHOUT padding its tensors: four horizontally adjacent pixels x C
+// channels are read as ONE pixel of 4C "virtual" channels ([N,H,W,C] is byte-identical to [N,H,W/4,4C]).  A 1x1 convolution
+// becomes a 1x1 convolution with a block-diagonal weight, a 3x3 convolution a 3x3 convolution over pixel groups with a
+// banded weight: virtual output (po, co) takes virtual input (pi, ci) of the group at horizontal offset dg with the real
+// tap dx = 4*dg + pi - po when that lies in [-1, 1].  Bytes are the real ones (a quarter of the zero-padded layout).
+__device__ __forceinline__ float px4_weight(const float* __restrict__ w, int Cout, int Cin, int taps, int co_v, int ci_v,
+                                            int tap) {
+  const int po = co_v / Cout, co = co_v - po * Cout, pi = ci_v / Cin, ci = ci_v - pi * Cin;
+  if (po >= 4 || pi >= 4) return 0.f;   // zero-padded virtual channels (conv10: 4 x 4 = 16 of 64)
+  if (taps == 1) return po == pi ? w[(long long)co * Cin + ci] : 0.f;
+  const int dy = tap / 3, dg = tap % 3 - 1;
+  const int dx = 4 * dg + pi - po;
+  if (dx < -1 || dx > 1) return 0.f;
+  return w[((long long)co * Cin + ci) * 9 + dy * 3 + dx + 1];
+}
+__global__ void pack_conv_weight_px4_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int CoutV,
+                                            int CinV, int flip_t, int fmt, unsigned short* __restrict__ hi,
+                                            unsigned short* __restrict__ lo) {
+  const long long total = (long long)CoutV * CinV * taps;
+  const int inner = flip_t ? CoutV : CinV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = int(i % inner);
+    long long t = i / inner;
+    const int tap = int(t % taps);
+    const int row = int(t / taps);
+    int co, ci, stap;
+    if (!flip_t) {
+      co = row; ci = col; stap = tap;
+    } else {
+      ci = row; co = col; stap = taps - 1 - tap;
+    }
+    unsigned short h, l;
+    split_fmt(px4_weight(w, Cout, Cin, taps, co, ci, stap), fmt, h, l);
+    hi[i] = h;
+    if (fmt != kFmtBf16) lo[i] = l;
+  }
+}
+int pack_conv_weight_px4(const float* w, int Cout, int Cin, int ksize, int CoutV, int CinV, int flip_transpose, int fmt,
+                         void* hi, void* lo, cudaStream_t st) {
+  if (CoutV < 4 * Cout || CinV < 4 * Cin || (ksize != 1 && ksize != 3)) {
+    set_error("pack_conv_weight_px4: %d->%d k%d does not fit %d->%d virtual channels", Cin, Cout, ksize, CinV, CoutV);
+    return 1;
+  }
+  const int taps = ksize * ksize;
+  const long long total = (long long)CoutV * CinV * taps;
+  pack_conv_weight_px4_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, Cout, Cin, taps, CoutV, CinV, flip_transpose, fmt,
+                                                                    (unsigned short*)hi, (unsigned short*)lo);
+  NSM_CHECK_LAUNCH("pack_conv_weight_px4");
+  return 0;
+}
+// gradient of the real weight = sum of the virtual weight's gradient over every (po, pi, dg) that maps onto the same tap
+__global__ void px4_reduce_dw_kernel(const float* __restrict__ dwv, int Cout, int Cin, int taps, int CoutV, int CinV,
+                                     float* __restrict__ dw) {
+  const int total = Cout * Cin * taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % taps, ci = (i / taps) % Cin, co = i / (taps * Cin);
+    float s = 0.f;
+    for (int po = 0; po < 4; ++po)
+      for (int pi = 0; pi < 4; ++pi) {
+        int vtap;
+        if (taps == 1) {
+          if (po != pi) continue;
+          vtap = 0;
+        } else {
+          const int dx = tap % 3 - 1, d = dx - pi + po;   // 4 * dg
+          if (d != -4 && d != 0 && d != 4) continue;
+          vtap = (tap / 3) * 3 + d / 4 + 1;
+        }
+        s += dwv[((long long)(po * Cout + co) * CinV + pi * Cin + ci) * taps + vtap];
+      }
+    dw[i] = s;
+  }
+}
+int px4_reduce_dw(const float* dwv, int Cout, int Cin, int ksize, int CoutV, int CinV, float* dw, cudaStream_t st) {
+  const int taps = ksize * ksize;
+  px4_reduce_dw_kernel<<<(Cout * Cin * taps + 255) / 256, 256, 0, st>>>(dwv, Cout, Cin, taps, CoutV, CinV, dw);
+  NSM_CHECK_LAUNCH("px4_reduce_dw");
+  return 0;
+}
+// out[v][c] = sum over the `groups` copies of in[v][g*C + c] (per-channel sums of a pixel-packed tensor -> real channels)
+__global__ void fold_channel_sums_kernel(const double* in, int nvec, int CV, int groups, int C, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec * C) return;
+  const int v = i / C, c = i - v * C;
+  double s = 0.0;
+  for (int g = 0; g < groups; ++g) s += in[(long long)v * CV + g * C + c];
+  out[i] = s;
+}
+int fold_channel_sums(const double* in, int nvec, int CV, int groups, int C, double* out, cudaStream_t st) {
+  if (groups * C > CV) {
+    set_error("fold_channel_sums: %d x %d channels do not fit %d", groups, C, CV);
+    return 1;
+  }
+  fold_channel_sums_kernel<<<(nvec * C + 127) / 128, 128, 0, st>>>(in, nvec, CV, groups, C, out);
+  NSM_CHECK_LAUNCH("fold_channel_sums");
+  return 0;
+}
+// dst[i] = src[i % n] for i < rep * n, `fill` beyond (bias of the virtual channels of a pixel-packed convolution)
+__global__ void tile_vector_kernel(const float* src, int n, int rep, int npad, float fill, int rb, float* dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npad) dst[i] = i < rep * n ? (rb ? rbf(src[i % n]) : src[i % n]) : fill;
+}
+int tile_vector(const float* src, int n, int rep, int npad, float fill, int round_bf16, float* dst, cudaStream_t st) {
+  tile_vector_kernel<<<(npad + 127) / 128, 128, 0, st>>>(src, n, rep, npad, fill, round_bf16, dst);
+  NSM_CHECK_LAUNCH("tile_vector");
   return 0;
 }
 

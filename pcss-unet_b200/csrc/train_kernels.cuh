@@ -63,14 +63,21 @@ int upsample_match_bwd(const Planes& dout, int N, int ho, int wo, int C, const P
 
 // ---- network input / output stages of the training path ----------------------------------------------------------------
 // x [N,4,Hin,Win] fp32 -> (even-size fix) -> pixel_unshuffle(2) -> NHWC planes [N,h,w,64] (channels 16..63 zero)
-int train_input_prep(const float* x, int N, int Hin, int Win, const Planes& out, int fmt, cudaStream_t st);
+int train_input_prep(const float* x, int N, int Hin, int Win, const Planes& out, int fmt, cudaStream_t st, int cpad = 64);
 // adjoint for even Hin/Win: d x16 planes [N,h,w,64] -> dx [N,4,H,W] fp32
-int train_input_grad(const Planes& dx16, int N, int H, int W, float* dx, int fmt, cudaStream_t st);
+int train_input_grad(const Planes& dx16, int N, int H, int W, float* dx, int fmt, cudaStream_t st, int cpad = 64);
 // c10 planes [N,h,w,64] (first 4 channels) -> sigmoid(pixel_shuffle) -> y [N,1,2h,2w] fp32
-int sigmoid_shuffle_fwd(const Planes& c10, int N, int h, int w, int fmt, float* y, cudaStream_t st);
+int sigmoid_shuffle_fwd(const Planes& c10, int N, int h, int w, int fmt, float* y, cudaStream_t st, int px4 = 0);
 // dy [N,1,2h,2w], y -> d c10 planes [N,h,w,64] (channels 4..63 zero)
 int sigmoid_shuffle_bwd(const float* dy, const float* y, int N, int h, int w, int fmt, const Planes& dc10,
-                        cudaStream_t st);
+                        cudaStream_t st, int px4 = 0);
+// pixel-packed thin layers (train_kernels.cu): four horizontally adjacent pixels x C channels = one pixel of 4C virtual
+// channels; weights [Cout][Cin][k][k] -> virtual conv [CoutV][tap][CinV] (block-diagonal / banded), and back for dW
+int pack_conv_weight_px4(const float* w, int Cout, int Cin, int ksize, int CoutV, int CinV, int flip_transpose, int fmt,
+                         void* hi, void* lo, cudaStream_t st);
+int px4_reduce_dw(const float* dwv, int Cout, int Cin, int ksize, int CoutV, int CinV, float* dw, cudaStream_t st);
+int fold_channel_sums(const double* in, int nvec, int CV, int groups, int C, double* out, cudaStream_t st);
+int tile_vector(const float* src, int n, int rep, int npad, float fill, int round_bf16, float* dst, cudaStream_t st);
 // zero-padded weight packing: OIHW [Cout][Cin][k][k] -> [CoutP][tap][CinP] planes (dgrad: [CinP][tap'][CoutP])
 int pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int flip_transpose,
                             int fmt, void* hi, void* lo, cudaStream_t st);

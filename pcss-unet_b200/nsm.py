@@ -108,6 +108,16 @@ def _declare(lib):
     lib.nsm_wgrad.argtypes = [vp, vp, vp, vp] + [c_int] * 9 + [vp, c_size_t, vp, vp]
     lib.nsm_adamw_clip_step.argtypes = [c_int, POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(ll), fp, fp,
                                         fp, fp, fp, fp, c_int, vp, vp]
+    lib.nsm_train_input_prep_c16.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, vp]
+    lib.nsm_train_input_grad_c16.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_int, vp]
+    lib.nsm_sigmoid_shuffle_fwd_px4.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp]
+    lib.nsm_sigmoid_shuffle_bwd_px4.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp]
+    lib.nsm_pack_conv_weight_px4.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp]
+    lib.nsm_px4_reduce_dw.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, vp, vp]
+    lib.nsm_fold_channel_sums.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
+    lib.nsm_tile_vector.argtypes = [vp, c_int, c_int, c_int, fp, c_int, vp, vp]
+    for name in PX4_EXPORTS:
+        getattr(lib, name).restype = c_int
     lib.nsm_vgg_input_prep.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp]
     lib.nsm_relu_maxpool.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp]
     lib.nsm_feature_l1.argtypes = [vp, vp, ll, c_int, vp, vp]
@@ -121,6 +131,11 @@ def _declare(lib):
                  "nsm_l1_loss_fwd_bwd", "nsm_channel_sums", "nsm_standardize", "nsm_perturb"):
         getattr(lib, name).restype = c_int
 
+
+PX4_EXPORTS = [
+    "nsm_train_input_prep_c16", "nsm_train_input_grad_c16", "nsm_sigmoid_shuffle_fwd_px4", "nsm_sigmoid_shuffle_bwd_px4",
+    "nsm_pack_conv_weight_px4", "nsm_px4_reduce_dw", "nsm_fold_channel_sums", "nsm_tile_vector",
+]
 
 TRAIN_EXPORTS = [
     "nsm_bn_stats", "nsm_bn_finalize", "nsm_bn_act", "nsm_bn_bwd", "nsm_pool_bwd_add", "nsm_planes_add",
@@ -137,7 +152,7 @@ EXPORTS = TRAIN_EXPORTS + [
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
     "nsm_channel_sums", "nsm_standardize", "nsm_perturb", "nsm_profile_enable", "nsm_profile_read",
     "nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1",
-]
+] + PX4_EXPORTS
 
 
 def lib():
@@ -330,6 +345,23 @@ class PlaneTensor:
 
     def pair(self):
         return (c_void_p * 2)(ptr(self.p0), ptr(self.p1))
+
+    def px_view(self, px):
+        """The same bytes addressed as [N, H, W/px, px*C]: px horizontally adjacent pixels = one pixel of px*C virtual
+        channels (px > 0), or the inverse view (px < 0: [N, H, W*|px|, C/|px|])."""
+        N, C, H, W = self.shape
+        v = object.__new__(PlaneTensor)
+        if px > 0:
+            assert W % px == 0
+            v.shape = (N, C * px, H, W // px)
+        else:
+            assert C % (-px) == 0
+            v.shape = (N, C // (-px), H, W * (-px))
+        v.mode = self.mode
+        n, c, h, w = v.shape
+        v.p0 = self.p0.view(n, h, w, c)
+        v.p1 = None if self.p1 is None else self.p1.view(n, h, w, c)
+        return v
 
 
 def pack_conv_weight(w, mode, dgrad=False):
@@ -540,34 +572,77 @@ def upsample_match_bwd(dout: PlaneTensor, hs, ws):
     return din
 
 
-def train_input_prep(x, mode):
+def pack_conv_weight_px4(w, mode, CoutV, CinV, dgrad=False):
+    """Pixel-packed (4 pixels = one virtual pixel) operand of a thin convolution, see nsm_b200.h."""
+    Cout, Cin, k, _ = w.shape
+    w = w.detach().to(torch.float32).contiguous()
+    rows, inner = (CinV, CoutV) if dgrad else (CoutV, CinV)
+    p0 = torch.empty(rows, k * k, inner, dtype=torch.bfloat16, device=w.device)
+    p1 = torch.empty_like(p0) if mode != MODE_BF16 else None
+    check(lib().nsm_pack_conv_weight_px4(w.data_ptr(), Cout, Cin, k, CoutV, CinV, int(dgrad), mode, ptr(p0), ptr(p1),
+                                         stream_ptr()), "nsm_pack_conv_weight_px4")
+    return p0, p1
+
+
+def px4_reduce_dw(dwv, Cout, Cin, ksize):
+    CoutV, CinV = dwv.shape[0], dwv.shape[1]
+    dw = torch.empty(Cout, Cin, ksize, ksize, dtype=torch.float32, device=dwv.device)
+    check(lib().nsm_px4_reduce_dw(dwv.data_ptr(), Cout, Cin, ksize, CoutV, CinV, dw.data_ptr(), stream_ptr()),
+          "nsm_px4_reduce_dw")
+    return dw
+
+
+def fold_channel_sums(sums, nvec, groups, C):
+    """[nvec * CV] fp64 per-virtual-channel sums -> [nvec * C]: out[v][c] = sum_g in[v][g*C + c]."""
+    CV = sums.numel() // nvec
+    out = torch.empty(nvec * C, dtype=torch.float64, device=sums.device)
+    check(lib().nsm_fold_channel_sums(sums.data_ptr(), nvec, CV, groups, C, out.data_ptr(), stream_ptr()),
+          "nsm_fold_channel_sums")
+    return out
+
+
+def tile_vector(v, rep, npad, fill=0.0, round_bf16=False):
+    v = v.detach().to(torch.float32).contiguous()
+    out = torch.empty(npad, dtype=torch.float32, device=v.device)
+    check(lib().nsm_tile_vector(v.data_ptr(), v.numel(), rep, npad, fill, int(round_bf16), out.data_ptr(), stream_ptr()),
+          "nsm_tile_vector")
+    return out
+
+
+def train_input_prep(x, mode, c16=False):
+    """x [N,4,Hin,Win] -> un-shuffled NHWC planes: 64 zero-padded channels, or (c16) the 16 real ones."""
     N, _, Hin, Win = x.shape
-    out = PlaneTensor(N, 64, (Hin - Hin % 2) // 2, (Win - Win % 2) // 2, mode, x.device)
-    check(lib().nsm_train_input_prep(x.data_ptr(), N, Hin, Win, *_pp(out), mode, stream_ptr()), "nsm_train_input_prep")
+    out = PlaneTensor(N, 16 if c16 else 64, (Hin - Hin % 2) // 2, (Win - Win % 2) // 2, mode, x.device)
+    fn = lib().nsm_train_input_prep_c16 if c16 else lib().nsm_train_input_prep
+    check(fn(x.data_ptr(), N, Hin, Win, *_pp(out), mode, stream_ptr()), "nsm_train_input_prep")
     return out
 
 
 def train_input_grad(d: PlaneTensor, H, W):
     N = d.shape[0]
     dx = torch.empty(N, 4, H, W, dtype=torch.float32, device=d.p0.device)
-    check(lib().nsm_train_input_grad(*_pp(d), N, H, W, dx.data_ptr(), d.mode, stream_ptr()), "nsm_train_input_grad")
+    fn = lib().nsm_train_input_grad_c16 if d.shape[1] == 16 else lib().nsm_train_input_grad
+    check(fn(*_pp(d), N, H, W, dx.data_ptr(), d.mode, stream_ptr()), "nsm_train_input_grad")
     return dx
 
 
-def sigmoid_shuffle_fwd(c10: PlaneTensor):
+def sigmoid_shuffle_fwd(c10: PlaneTensor, px4=False):
+    """c10: [N,64,h,w] (4 real channels), or px4: the pixel-packed [N,64,h,w/4] (see nsm_b200.h)."""
     N, _, h, w = c10.shape
+    if px4:
+        w *= 4
     y = torch.empty(N, 1, 2 * h, 2 * w, dtype=torch.float32, device=c10.p0.device)
-    check(lib().nsm_sigmoid_shuffle_fwd(*_pp(c10), N, h, w, c10.mode, y.data_ptr(), stream_ptr()),
-          "nsm_sigmoid_shuffle_fwd")
+    fn = lib().nsm_sigmoid_shuffle_fwd_px4 if px4 else lib().nsm_sigmoid_shuffle_fwd
+    check(fn(*_pp(c10), N, h, w, c10.mode, y.data_ptr(), stream_ptr()), "nsm_sigmoid_shuffle_fwd")
     return y
 
 
-def sigmoid_shuffle_bwd(dy, y, mode):
+def sigmoid_shuffle_bwd(dy, y, mode, px4=False):
     N, _, H, W = y.shape
-    d = PlaneTensor(N, 64, H // 2, W // 2, mode, y.device)
+    d = PlaneTensor(N, 64, H // 2, W // 8 if px4 else W // 2, mode, y.device)
     dy = dy.to(torch.float32).contiguous()
-    check(lib().nsm_sigmoid_shuffle_bwd(dy.data_ptr(), y.data_ptr(), N, H // 2, W // 2, mode, *_pp(d), stream_ptr()),
-          "nsm_sigmoid_shuffle_bwd")
+    fn = lib().nsm_sigmoid_shuffle_bwd_px4 if px4 else lib().nsm_sigmoid_shuffle_bwd
+    check(fn(dy.data_ptr(), y.data_ptr(), N, H // 2, W // 2, mode, *_pp(d), stream_ptr()), "nsm_sigmoid_shuffle_bwd")
     return d
 
 

@@ -15,9 +15,13 @@ Thin layers (16 / 4 channels) are zero-padded to 64 channels so that every convo
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 import nsm
+
+_NO_PX4 = bool(os.environ.get("NSM_NO_PX4"))     # A/B switch: zero-pad the thin layers to 64 channels instead
 
 BLOCKS = (("conv2", 16, 64), ("conv3", 64, 128), ("conv4", 128, 512), ("conv5", 512, 1024),
           ("conv6", 1024, 512), ("conv7", 512, 128), ("conv8", 128, 64), ("conv9", 64, 16))
@@ -36,38 +40,81 @@ def _param_list(model):
     return ps + [model.conv10.weight, model.conv10.bias]
 
 
-class _Packed:
-    """Per-step packed operands: forward and dgrad weight planes, padded bias / BN vectors."""
+class _Conv:
+    """One convolution of the training path with its packed operands (forward and dgrad weight planes, bias).
 
-    def __init__(self, model, mode):
+    Layers with fewer than 64 input or output channels (conv2, conv9 1x1, conv10) run PIXEL-PACKED when the level width is
+    a multiple of 4 (``px``): four horizontally adjacent pixels x C channels are one pixel of 4C virtual channels, the
+    weight becomes block-diagonal (1x1) / banded (3x3) -- tensors keep their real channel counts (``cin_s`` / ``cout_s``)
+    and bytes (see nsm_b200.h, nsm_pack_conv_weight_px4).  Otherwise thin layers are zero-padded to 64 channels."""
+
+    def __init__(self, conv, mode, px4):
         rb = mode == nsm.MODE_BF16
+        self.cout, self.cin, self.k = conv.weight.shape[0], conv.weight.shape[1], conv.weight.shape[2]
+        self.px = bool(px4) and (self.cin < 64 or self.cout < 64)
+        if self.px:
+            self.cin_v, self.cout_v = max(64, 4 * self.cin), max(64, 4 * self.cout)
+            self.cin_s, self.cout_s = self.cin, self.cout
+            self.w = nsm.pack_conv_weight_px4(conv.weight, mode, self.cout_v, self.cin_v)
+            self.wt = nsm.pack_conv_weight_px4(conv.weight, mode, self.cout_v, self.cin_v, dgrad=True)
+            self.b = nsm.tile_vector(conv.bias, 4, self.cout_v, 0.0, rb)
+        else:
+            self.cin_v = self.cin_s = _pad64(self.cin)
+            self.cout_v = self.cout_s = _pad64(self.cout)
+            self.w = nsm.pack_conv_weight_padded(conv.weight, mode, self.cout_v, self.cin_v)
+            self.wt = nsm.pack_conv_weight_padded(conv.weight, mode, self.cout_v, self.cin_v, dgrad=True)
+            self.b = nsm.pad_vector(conv.bias, self.cout_v, 0.0, rb)
+
+    def _in(self, x, c_v):      # stored tensor -> the view the GEMM reads (c_v virtual channels)
+        return x if (not self.px or x.shape[1] == c_v) else x.px_view(4)
+
+    def _stored(self, t, c_s):   # GEMM result (virtual channels) -> stored tensor with c_s channels per pixel
+        if not self.px or t.shape[1] == c_s:
+            return t
+        return t.px_view(-(t.shape[1] // c_s)) if t.shape[1] == 4 * c_s else t   # conv10: 16 of 64 virtual channels stay
+
+    def forward(self, x, mode, stats=True):
+        """Raw convolution + bias; returns (z with cout_s channels per pixel, fp64 [2*cout_s] sums | None)."""
+        sums = torch.zeros(2 * self.cout_v, dtype=torch.float64, device=x.p0.device) if stats else None
+        z, _, _ = nsm.conv_fwd(self._in(x, self.cin_v), self.w, self.k, self.cout_v, mode, bias=self.b, stats=sums)
+        if self.px and stats:
+            sums = nsm.fold_channel_sums(sums, 2, 4, self.cout)
+        return self._stored(z, self.cout_s), sums
+
+    def dgrad(self, dz, mode):
+        dx, _, _ = nsm.conv_fwd(self._in(dz, self.cout_v), self.wt, self.k, self.cin_v, mode)
+        return self._stored(dx, self.cin_s)
+
+    def wgrad(self, dz, x):
+        if not self.px:
+            return nsm.wgrad(dz, x, self.k, self.cout, self.cin)
+        dwv = nsm.wgrad(self._in(dz, self.cout_v), self._in(x, self.cin_v), self.k, self.cout_v, self.cin_v)
+        return nsm.px4_reduce_dw(dwv, self.cout, self.cin, self.k)
+
+
+class _Packed:
+    """Per-step packed operands of all 17 convolutions and the padded BN vectors."""
+
+    def __init__(self, model, mode, px4):
+        self.px4 = px4
         self.blocks = []
         for name, cin, cout in BLOCKS:
             seq = getattr(model, name).conv
-            cip, cop = _pad64(cin), _pad64(cout)
-            d = {}
-            d["w3"] = nsm.pack_conv_weight_padded(seq[0].weight, mode, cip, cip)
-            d["w3t"] = nsm.pack_conv_weight_padded(seq[0].weight, mode, cip, cip, dgrad=True)
-            d["b3"] = nsm.pad_vector(seq[0].bias, cip, 0.0, rb)
-            d["g3"] = nsm.pad_vector(seq[1].weight, cip, 0.0)
-            d["be3"] = nsm.pad_vector(seq[1].bias, cip, 0.0)
-            d["w1"] = nsm.pack_conv_weight_padded(seq[4].weight, mode, cop, cip)
-            d["w1t"] = nsm.pack_conv_weight_padded(seq[4].weight, mode, cop, cip, dgrad=True)
-            d["b1"] = nsm.pad_vector(seq[4].bias, cop, 0.0, rb)
-            d["g1"] = nsm.pad_vector(seq[5].weight, cop, 0.0)
-            d["be1"] = nsm.pad_vector(seq[5].bias, cop, 0.0)
+            d = {"c3": _Conv(seq[0], mode, px4), "c1": _Conv(seq[4], mode, px4)}
+            d["g3"] = nsm.pad_vector(seq[1].weight, d["c3"].cout_s, 0.0)
+            d["be3"] = nsm.pad_vector(seq[1].bias, d["c3"].cout_s, 0.0)
+            d["g1"] = nsm.pad_vector(seq[5].weight, d["c1"].cout_s, 0.0)
+            d["be1"] = nsm.pad_vector(seq[5].bias, d["c1"].cout_s, 0.0)
             self.blocks.append(d)
-        self.w10 = nsm.pack_conv_weight_padded(model.conv10.weight, mode, 64, 64)
-        self.w10t = nsm.pack_conv_weight_padded(model.conv10.weight, mode, 64, 64, dgrad=True)
-        self.b10 = nsm.pad_vector(model.conv10.bias, 64, 0.0, rb)
+        self.c10 = _Conv(model.conv10, mode, px4)
 
 
-def _packed(model, mode):
+def _packed(model, mode, px4):
     ps = _param_list(model)
-    key = (mode,) + tuple((p.data_ptr(), p._version) for p in ps)
+    key = (mode, px4) + tuple((p.data_ptr(), p._version) for p in ps)
     hit = getattr(model, "_train_packed", None)
     if hit is None or hit[0] != key:
-        model._train_packed = (key, _Packed(model, mode))
+        model._train_packed = (key, _Packed(model, mode, px4))
     return model._train_packed[1]
 
 
@@ -81,13 +128,6 @@ def _running(bn, cpad):
     rm[:c].copy_(bn.running_mean)
     rv[:c].copy_(bn.running_var)
     return rm, rv, c
-
-
-def _conv_stats(x, w, ksize, cout, mode, bias):
-    """Raw convolution (+bias) with the BatchNorm batch statistics accumulated by the conv epilogue itself."""
-    sums = torch.zeros(2 * cout, dtype=torch.float64, device=x.p0.device)
-    z, _, _ = nsm.conv_fwd(x, w, ksize, cout, mode, bias=bias, stats=sums)
-    return z, sums
 
 
 def _bn_train(z, gamma, beta, bn, updates=1, sums=None):
@@ -117,9 +157,10 @@ def _bn_replay(sums, P, gamma, beta, bn):
     bn.num_batches_tracked += 1
 
 
-def _draw_masks(model, N, mode, device):
+def _draw_masks(model, N, mode, device, cpads):
     """The eight Dropout2d draws in block order, exactly as F.dropout2d / feature_dropout makes them
-    (noise = empty(N, C, 1, 1).bernoulli_(1 - p).div_(1 - p) in the activation dtype)."""
+    (noise = empty(N, C, 1, 1).bernoulli_(1 - p).div_(1 - p) in the activation dtype).  cpads[i] = channels per pixel of
+    block i's stored 3x3 output (the real count, or 64 when a thin layer runs zero-padded)."""
     # parity tests replay given draws: set by `replay_masks(model, masks)` for exactly ONE forward (popped here, so a
     # model object reused afterwards draws fresh masks again)
     replay = model.__dict__.pop("_replay_masks", None)
@@ -135,9 +176,13 @@ def _draw_masks(model, N, mode, device):
         else:
             m = None
         if m is not None:
-            full = torch.zeros(N, _pad64(cin), dtype=torch.float32, device=device)
-            full[:, :cin] = m.reshape(N, cin).to(torch.float32)
-            m = full
+            cs = cpads[i]
+            if cs == cin:
+                m = m.reshape(N, cin).to(torch.float32).contiguous()
+            else:
+                full = torch.zeros(N, cs, dtype=torch.float32, device=device)
+                full[:, :cin] = m.reshape(N, cin).to(torch.float32)
+                m = full
         masks.append(m)
     return masks
 
@@ -153,11 +198,10 @@ def _block_forward(model, pk, i, x, mode, mask, residual=None, pool=False, save=
     name, cin, cout = BLOCKS[i]
     seq = getattr(model, name).conv
     d = pk.blocks[i]
-    cip, cop = _pad64(cin), _pad64(cout)
-    z0, s0 = _conv_stats(x, d["w3"], 3, cip, mode, d["b3"])
+    z0, s0 = d["c3"].forward(x, mode)
     st0, sums0 = _bn_train(z0, d["g3"], d["be3"], seq[1], sums=s0)
     a0, _ = nsm.bn_act(z0, st0[0], st0[1], mask=mask, lrelu=True)
-    z1, s1 = _conv_stats(a0, d["w1"], 1, cop, mode, d["b1"])
+    z1, s1 = d["c1"].forward(a0, mode)
     st1, sums1 = _bn_train(z1, d["g1"], d["be1"], seq[5], sums=s1)
     y, pooled = nsm.bn_act(z1, st1[0], st1[1], mask=None, lrelu=True, residual=residual, pool=pool)
     saved = dict(x=x, z0=z0, a0=a0, z1=z1, st0=st0, st1=st1, mask=mask, sums0=sums0, sums1=sums1) if save else None
@@ -172,22 +216,24 @@ def _block_backward(model, pk, i, sv, dy, mode, need_dx=True):
     g = {}
     dz1, dg1, dbe1, db1 = nsm.bn_bwd(dy, sv["z1"], st1[0], st1[1], st1[2], st1[3], mask=None, lrelu=True)
     g[f"{name}.conv.5.weight"], g[f"{name}.conv.5.bias"], g[f"{name}.conv.4.bias"] = dg1[:cout], dbe1[:cout], db1[:cout]
-    g[f"{name}.conv.4.weight"] = nsm.wgrad(dz1, sv["a0"], 1, cout, cin)
-    da0, _, _ = nsm.conv_fwd(dz1, d["w1t"], 1, _pad64(cin), mode)
+    g[f"{name}.conv.4.weight"] = d["c1"].wgrad(dz1, sv["a0"])
+    da0 = d["c1"].dgrad(dz1, mode)
     dz0, dg0, dbe0, db0 = nsm.bn_bwd(da0, sv["z0"], st0[0], st0[1], st0[2], st0[3], mask=sv["mask"], lrelu=True)
     g[f"{name}.conv.1.weight"], g[f"{name}.conv.1.bias"], g[f"{name}.conv.0.bias"] = dg0[:cin], dbe0[:cin], db0[:cin]
-    g[f"{name}.conv.0.weight"] = nsm.wgrad(dz0, sv["x"], 3, cin, cin)
-    dx = nsm.conv_fwd(dz0, d["w3t"], 3, _pad64(cin), mode)[0] if need_dx else None
+    g[f"{name}.conv.0.weight"] = d["c3"].wgrad(dz0, sv["x"])
+    dx = d["c3"].dgrad(dz0, mode) if need_dx else None
     return dx, g
 
 
 def _forward(model, x, mode, save):
     dev = x.device
     N, _, Hin, Win = x.shape
-    pk = _packed(model, mode)
-    masks = _draw_masks(model, N, mode, dev)
+    # thin layers run pixel-packed (real channel counts) when the first level's width is a multiple of 4
+    px4 = ((Win - Win % 2) // 2) % 4 == 0 and not _NO_PX4
+    pk = _packed(model, mode, px4)
+    masks = _draw_masks(model, N, mode, dev, [d["c3"].cout_s for d in pk.blocks])
     st = {"pk": pk, "in_shape": (N, Hin, Win)} if save else None
-    x16 = nsm.train_input_prep(x.detach().to(torch.float32).contiguous(), mode)
+    x16 = nsm.train_input_prep(x.detach().to(torch.float32).contiguous(), mode, c16=px4)
     sv = [None] * 8
     c2, p2, sv[0] = _block_forward(model, pk, 0, x16, mode, masks[0], pool=True, save=save)
     c3, p3, sv[1] = _block_forward(model, pk, 1, p2, mode, masks[1], pool=True, save=save)
@@ -201,8 +247,8 @@ def _forward(model, x, mode, save):
     m8, _, sv[6] = _block_forward(model, pk, 6, u8, mode, masks[6], residual=c2, save=save)
     u9 = nsm.upsample_match(m8, x16.shape[2], x16.shape[3])
     c9, _, sv[7] = _block_forward(model, pk, 7, u9, mode, masks[7], save=save)
-    c10, _, _ = nsm.conv_fwd(c9, pk.w10, 1, 64, mode, bias=pk.b10)
-    y = nsm.sigmoid_shuffle_fwd(c10)
+    c10, _ = pk.c10.forward(c9, mode, stats=False)
+    y = nsm.sigmoid_shuffle_fwd(c10, px4=pk.c10.px)
     if save:
         st.update(sv=sv, c9=c9, y=y,
                   sizes=dict(c5=c5.shape[2:], m6=m6.shape[2:], m7=m7.shape[2:], m8=m8.shape[2:],
@@ -221,10 +267,12 @@ def _backward(model, st, dy, mode, need_dx):
                 sync.reduce_ready(g)
 
     G = _G()
-    dc10 = nsm.sigmoid_shuffle_bwd(dy, st["y"], mode)
-    G.update({"conv10.weight": nsm.wgrad(dc10, st["c9"], 1, 4, 16),
-              "conv10.bias": nsm.bn_stats(dc10)[:4].to(torch.float32)})
-    dc9, _, _ = nsm.conv_fwd(dc10, pk.w10t, 1, 64, mode)
+    dc10 = nsm.sigmoid_shuffle_bwd(dy, st["y"], mode, px4=pk.c10.px)
+    db10 = nsm.bn_stats(dc10)                       # per-channel sums of dc10 = the bias gradient
+    if pk.c10.px:
+        db10 = nsm.fold_channel_sums(db10, 2, 4, 4)
+    G.update({"conv10.weight": pk.c10.wgrad(dc10, st["c9"]), "conv10.bias": db10[:4].to(torch.float32)})
+    dc9 = pk.c10.dgrad(dc10, mode)
     du9, g = _block_backward(model, pk, 7, sv[7], dc9, mode); G.update(g)
     dm8 = nsm.upsample_match_bwd(du9, *st["sizes"]["m8"])
     du8, g = _block_backward(model, pk, 6, sv[6], dm8, mode); G.update(g)      # skip: d c2 += dm8
