@@ -347,26 +347,25 @@ struct BwdChan8 {
   float s[8], t[8];
 };
 
+// g = dy * mask * LeakyReLU'(z*s + t).  The products are formed in fp32 and rounded once, when dz is stored: gradients are
+// held to a relative L2 bound (1e-2 in bf16 mode), not to autograd's intermediate bf16 rounding points, and every extra
+// convert costs issue slots in a pass that is instruction-limited (ncu: 60 instructions per 16-byte load).
 template <int NPL>
 __device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, const BwdChan8& ch, const Raw8& rdy, const Raw8& rz, int n,
                                           int c0, float* g, float* z) {
-  constexpr bool rb = NPL == 1;
-  float dy[8], m[8];
+  float dy[8];
   unpack8_bf16<NPL>(rdy, dy);
   unpack8_bf16<NPL>(rz, z);
-  if (p.mask) load_mask8(p.mask, (size_t)n * p.C + c0, m);
+  if (p.mask) {
+    float m[8];
+    load_mask8(p.mask, (size_t)n * p.C + c0, m);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dy[e] *= m[e];
+  }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    float t = dy[e];
-    if (p.mask) {
-      t *= m[e];
-      if (rb) t = rbf(t);
-    }
-    if (p.lrelu && !(fmaf(z[e], ch.s[e], ch.t[e]) > 0.f)) {   // the sign of y survives its bf16 rounding
-      t *= 0.2f;
-      if (rb) t = rbf(t);
-    }
-    g[e] = t;
+    const bool pos = !p.lrelu || fmaf(z[e], ch.s[e], ch.t[e]) > 0.f;   // the sign of y survives its bf16 rounding
+    g[e] = pos ? dy[e] : 0.2f * dy[e];
   }
 }
 
