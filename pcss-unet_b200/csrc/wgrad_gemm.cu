@@ -33,7 +33,11 @@ struct WgradKernelParams {
   float* partial;                  // [splits][Cout][taps][Cin] fp32
 };
 
-template <int BN, int NP>
+// CG = 2: cta_group::2 pairs.  Two CTAs compute two output-channel tiles (M = 256) against one input-channel block of
+// which each holds HALF the columns in shared memory: per 64-pixel k-block a CTA writes 32 KB and its tensor core reads
+// 32 KB (16 KB of dz, 16 KB of x) where the single-CTA 256-wide tile moves 48 + 48 KB -- the kernel is bound by exactly
+// that shared-memory traffic (ncu: tensor pipe 59-65 % active).  The leader issues the MMAs for both.
+template <int BN, int NP, int CG = 1>
 struct WgradCfg {
   static constexpr int KPIX = BN == 256 ? 64 : 128;           // pixels per k-block (patch = 16 x KPIX/16)
   static constexpr int TILE_H = KPIX / kTileW;
@@ -43,7 +47,7 @@ struct WgradCfg {
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int BOX_BYTES = KPIX * 128;                // KPIX pixels x 64 channels x 2 B
   static constexpr int A_BYTES = 2 * BOX_BYTES;               // 128 output channels
-  static constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
+  static constexpr int B_BYTES = (BN / 64 / CG) * BOX_BYTES;   // pairs: this CTA's half of the input-channel block
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
   static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -65,12 +69,17 @@ __device__ __forceinline__ void wgrad_decode(const WgradKernelParams& p, int ite
   split = t / p.taps;
 }
 
-template <int BN, int NP>
-__global__ void __launch_bounds__(WgradCfg<BN, NP>::THREADS, 1)
+template <int BN, int NP, int CG>
+__global__ void __launch_bounds__(WgradCfg<BN, NP, CG>::THREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                   const __grid_constant__ WgradKernelParams p) {
-  using Cfg = WgradCfg<BN, NP>;
+  using Cfg = WgradCfg<BN, NP, CG>;
+  constexpr bool PAIR = CG == 2;
+  static_assert(!PAIR || NP == 1, "CTA pairs: single-plane operands");
+  const int cta_rank = PAIR ? int(cluster_ctarank()) : 0;
+  // work items of this CTA (pair): p.co_blocks counts tiles of 128 * CG output channels
+  const int it_first = int(blockIdx.x) / CG, it_step = int(gridDim.x) / CG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -93,13 +102,17 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], Cfg::EPI_WARPS);
+      mbar_init(&tempty_bar[a], Cfg::EPI_WARPS * CG);   // pairs: the leader's copy collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -107,9 +120,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = it_first; item < p.total_items; item += it_step) {
         int cob, cib, tap, split;
         wgrad_decode(p, item, cob, cib, tap, split);
+        cob = cob * CG + cta_rank;                       // this CTA's tile of 128 output channels
+        const int ci0 = cib * BN + cta_rank * (BN / CG); // ... and its share of the input-channel block
         const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
         const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
         const int pt0 = split * p.patches_per_split;
@@ -121,9 +136,23 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const int n = t2 / p.tiles_y;
           const int x0 = tx * kTileW, y0 = ty * Cfg::TILE_H;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + NP * Cfg::A_BYTES;
+          if (PAIR) {   // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the pair
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              tma_load_4d_pair(sa + g * Cfg::BOX_BYTES, &tmA0, &full_bar[stage], cob * 128 + g * 64, x0, y0, n);
+#pragma unroll
+            for (int g = 0; g < BN / 64 / CG; ++g)
+              tma_load_4d_pair(sb + g * Cfg::BOX_BYTES, &tmB0, &full_bar[stage], ci0 + g * 64, x0 + dx, y0 + dy, n);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
           for (int pl = 0; pl < NP; ++pl) {
             const CUtensorMap* ma = pl == 0 ? &tmA0 : &tmA1;
@@ -146,9 +175,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {   // pairs: the leader issues for both
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = it_first; item < p.total_items; item += it_step) {
         int cob, cib, tap, split;
         wgrad_decode(p, item, cob, cib, tap, split);
         const int pt0 = split * p.patches_per_split;
@@ -169,7 +198,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               const uint32_t accum = ((pt - c0) | k) != 0 ? 1u : 0u;
               const uint64_t da_hi = make_desc_sw128(a_hi + k * 2048, Cfg::BOX_BYTES, 1024);
               const uint64_t db_hi = make_desc_sw128(b_hi + k * 2048, Cfg::BOX_BYTES, 1024);
-              umma_bf16(d_main, da_hi, db_hi, p.idesc, accum);
+              if (PAIR) umma_bf16_pair(d_main, da_hi, db_hi, p.idesc, accum);
+              else umma_bf16(d_main, da_hi, db_hi, p.idesc, accum);
               if (NP == 2) {
                 const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 2048, Cfg::BOX_BYTES, 1024);
                 const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 2048, Cfg::BOX_BYTES, 1024);
@@ -177,13 +207,15 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 umma_bf16(d_cross, da_lo, db_hi, p.idesc, 1u);
               }
             }
-            umma_commit(&empty_bar[stage]);
+            if (PAIR) umma_commit_pair(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&tfull_bar[acc]);
+          if (PAIR) umma_commit_pair(&tfull_bar[acc]);
+          else umma_commit(&tfull_bar[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -198,9 +230,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int row = q * 32 + lane;   // output channel inside the co tile
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + half * CW;
     uint32_t acc = 0, acc_phase = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    for (int item = it_first; item < p.total_items; item += it_step) {
       int cob, cib, tap, split;
       wgrad_decode(p, item, cob, cib, tap, split);
+      cob = cob * CG + cta_rank;
       const int pt0 = split * p.patches_per_split;
       const int pt1 = pt0 + p.patches_per_split < p.patches ? pt0 + p.patches_per_split : p.patches;
       const int nchunks = (pt1 - pt0 + Cfg::CHUNK - 1) / Cfg::CHUNK;
@@ -228,7 +261,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -243,10 +279,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // nobody leaves while the peer may still signal this CTA's barriers / read its smem
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -272,7 +310,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // host side
 // ------------------------------------------------------------------------------------------------
 struct WgradPlan {
-  int BN, tile_h, chunk, splits, patches_per_split, tiles_x, tiles_y, patches, co_blocks, ci_blocks, items;
+  int BN, CG, tile_h, chunk, splits, patches_per_split, tiles_x, tiles_y, patches, co_blocks, ci_blocks, items;
 };
 
 static WgradPlan wgrad_plan(const WgradShape& s) {
@@ -284,16 +322,35 @@ static WgradPlan wgrad_plan(const WgradShape& s) {
     const int f = force ? atoi(force) : 0;
     if (s.fmt == kFmtBf16 && (f == 64 || f == 128 || f == 256) && s.Cin % f == 0) pl.BN = f;
   }
+  // CTA pairs (M = 256 x N = 256) wherever both channel counts allow it (NSM_NO_WGRAD_PAIR=1: single CTAs)
+  static const bool pair_off = getenv("NSM_NO_WGRAD_PAIR") != nullptr;
+  pl.CG = (!pair_off && s.fmt == kFmtBf16 && s.Cin % 256 == 0 && s.Cout % 256 == 0) ? 2 : 1;
+  if (pl.CG == 2) pl.BN = 256;
   pl.tile_h = pl.BN == 256 ? 4 : kTileH;
   pl.chunk = kWChunkPix / (kTileW * pl.tile_h);
   pl.tiles_x = (s.W + kTileW - 1) / kTileW;
   pl.tiles_y = (s.H + pl.tile_h - 1) / pl.tile_h;
   pl.patches = s.N * pl.tiles_x * pl.tiles_y;
-  pl.co_blocks = (s.Cout + 127) / 128;
+  pl.co_blocks = (s.Cout + 128 * pl.CG - 1) / (128 * pl.CG);   // tiles of 128 (256 for pairs) output channels
   pl.ci_blocks = s.Cin / pl.BN;
   const int base = pl.co_blocks * pl.ci_blocks * s.taps;
-  int splits = (2 * 148 + base - 1) / base;            // aim at ~2 waves of work items
+  // K splits: enough work items for every CTA (pair), chosen so that the last wave is nearly full
+  const int workers = 148 / pl.CG;
   const int max_splits = (pl.patches + pl.chunk - 1) / pl.chunk;
+  int s_lo = (workers + base - 1) / base;
+  if (s_lo < 1) s_lo = 1;
+  int splits = s_lo;
+  double best = 0.0;
+  for (int cand = s_lo; cand <= 3 * s_lo + 2 && cand <= max_splits; ++cand) {
+    const int items = base * cand;
+    const int rounds = (items + workers - 1) / workers;
+    const double eff = double(items) / (double(rounds) * workers) - 0.004 * (cand - s_lo);   // mild cost per extra split
+    if (eff > best) {
+      best = eff;
+      splits = cand;
+    }
+    if (eff >= 0.96) break;
+  }
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   pl.patches_per_split = (pl.patches + splits - 1) / splits;
@@ -307,10 +364,10 @@ size_t wgrad_workspace_bytes(const WgradShape& s) {
   return (size_t)pl.splits * s.Cout * s.taps * s.Cin * 4;
 }
 
-template <int BN, int NP>
+template <int BN, int NP, int CG = 1>
 static int wgrad_launch_t(const CUtensorMap* maps, const WgradKernelParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = WgradCfg<BN, NP>;
-  auto kern = wgrad_gemm_kernel<BN, NP>;
+  using Cfg = WgradCfg<BN, NP, CG>;
+  auto kern = wgrad_gemm_kernel<BN, NP, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -320,8 +377,23 @@ static int wgrad_launch_t(const CUtensorMap* maps, const WgradKernelParams& kp, 
     }
     attr_set = true;
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (CG == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], kp);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("wgrad_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
     return 1;
@@ -367,7 +439,7 @@ int wgrad_launch(const WgradShape& s, const Planes& dz, const Planes& x, void* w
   kp.tiles_x = pl.tiles_x; kp.tiles_y = pl.tiles_y; kp.patches = pl.patches;
   kp.co_blocks = pl.co_blocks; kp.ci_blocks = pl.ci_blocks; kp.splits = pl.splits;
   kp.patches_per_split = pl.patches_per_split; kp.total_items = pl.items;
-  kp.idesc = make_idesc_f16(128, pl.BN, kFmtBF16, kFmtBF16, 1, 1);   // both operands MN-major
+  kp.idesc = make_idesc_f16(128 * pl.CG, pl.BN, kFmtBF16, kFmtBF16, 1, 1);   // both operands MN-major
   kp.partial = reinterpret_cast<float*>(workspace);
   int sms = 148;
   {
@@ -375,9 +447,11 @@ int wgrad_launch(const WgradShape& s, const Planes& dz, const Planes& x, void* w
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = kp.total_items < sms ? kp.total_items : sms;
+  int grid = kp.total_items < sms ? kp.total_items : sms;
+  if (pl.CG == 2) grid = 2 * (kp.total_items < sms / 2 ? kp.total_items : sms / 2);
   int rc;
-  if (planes == 1)
+  if (pl.CG == 2) rc = wgrad_launch_t<256, 1, 2>(maps, kp, grid, st);
+  else if (planes == 1)
     rc = pl.BN == 256   ? wgrad_launch_t<256, 1>(maps, kp, grid, st)
          : pl.BN == 128 ? wgrad_launch_t<128, 1>(maps, kp, grid, st)
                         : wgrad_launch_t<64, 1>(maps, kp, grid, st);
