@@ -391,11 +391,14 @@ def run_b200(args):
         f_k = 2 if (precision == "fp32" and k in x8_layers) else mma_factor
         if k.startswith("conv"):
             issued += fl * f_k
-        t_tensor = fl * f_k / (pk["bf16_tflops"] * 1e12) * 1e3
+        t_alg = fl / (pk["bf16_tflops"] * 1e12) * 1e3          # algorithmic 2*M*K*N FLOPs at the measured bf16 peak
+        t_tensor = t_alg * f_k                                  # the MMA slots this mode actually issues
         t_hbm = by / (pk["hbm_gbs"] * 1e9) * 1e3
-        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        bound = "tensor" if t_alg >= t_hbm else "hbm"
         layers[k] = {"ms": ms, "tflops": fl / max(ms, 1e-9) / 1e9, "gbs": by / max(ms, 1e-9) / 1e6, "bound": bound,
-                     "roofline_ms": max(t_tensor, t_hbm), "frac_of_roofline": max(t_tensor, t_hbm) / max(ms, 1e-9)}
+                     "roofline_ms": max(t_alg, t_hbm), "frac_of_roofline": max(t_alg, t_hbm) / max(ms, 1e-9),
+                     "mma_slots_per_mac": f_k if k.startswith("conv") else None,
+                     "frac_of_issued_roofline": max(t_tensor, t_hbm) / max(ms, 1e-9)}
     t_roof = sum(v["roofline_ms"] for v in layers.values())
     planes = 2 if precision == "fp32" else 1
     roofline = {"kernel": f"conv_gemm_kernel<BN,{planes}> + conv_gemm_wide_kernel (tcgen05 implicit GEMM, "
@@ -408,6 +411,9 @@ def run_b200(args):
                 "frac_of_issued_mma": issued * args.steps / (conv_ms * 1e-3) / 1e12 / pk["bf16_tflops"]
                 if conv_ms > 0 else None,
                 "step_roofline_ms": t_roof, "step_frac_of_roofline": t_roof / max(all_ms / max(args.steps, 1), 1e-9),
+                "per_layer_note": "frac_of_roofline = slower of (algorithmic FLOPs / measured bf16 peak) and (algorithmic "
+                                  "bytes / measured HBM GB/s), divided by the event-timed stage time; "
+                                  "frac_of_issued_roofline counts the 2-3 MMA slots per MAC of the fp32 mode instead",
                 "note": "achieved = algorithmic 2*M*K*N FLOPs of the conv launches / their CUDA-event time inside "
                         "the step; fp32 mode issues 3 bf16-rate MMA slots per algorithmic MAC (hi*hi+hi*lo+lo*hi), "
                         "2 in the decoder's 3x3 convolutions (cross terms as one e4m3 MMA), so the ceiling of frac "

@@ -27,7 +27,8 @@
 //   fp16 hi + fp16 lo (eval)  : a_hi x [w_hi | w_lo] as ONE MMA of width 2*BN, then a_lo x w_hi     (3 MMA slots / k-step)
 //   bf16 hi + bf16 lo (train) : same, full fp32 range
 //   fp16 hi + 8-bit cross     : a_hi x w_hi, then ONE e4m3 MMA of K = 32 for both cross terms        (2 MMA slots / k-step)
-// An experimental CTA-pair (cta_group::2) variant shares the weight tile between two CTAs (NSM_CG2=1).
+// The 256-wide 8-bit-cross layers (conv6 / conv7 3x3 in fp32 mode, 79 % of the FLOPs) run conv_gemm_wide_kernel as
+// cta_group::2 pairs: M = 256 (two pixel tiles) x N = 256, each CTA holds half of the weight tile.
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>
@@ -121,33 +122,22 @@ struct ConvKernelParams {
   ConvEpilogue ep;
 };
 
-// CG = 2: CTA pair (cta_group::2).  The pair computes two pixel tiles (M = 256) against one weight tile of which every CTA
-// holds half the rows: per MAC a CTA moves A + B/2 instead of A + B through L2 -> shared memory.
-template <int BN, int NP, int CG = 1, bool HALO = false>
+template <int BN, int NP>
 struct GemmCfg {
-  // HALO (3x3 only): the pixel tile is 16 rows x 8 columns and ONE box of (16+2) x (8+2) pixels per 64-channel block
-  // serves all nine taps: the UMMA swizzle follows absolute shared-memory addresses (profiles/README.md), so the A
-  // descriptor of tap (dy, dx) simply starts (dy*10 + dx) rows into the box and steps 10 rows per 8-pixel group.
-  static constexpr int TW = HALO ? 8 : kTileW, TH = HALO ? 16 : kTileH;
-  static constexpr int HALO_PITCH = TW + 2;                          // pixels per halo row
-  static constexpr int HALO_BYTES = (TH + 2) * HALO_PITCH * 128;     // one plane, one channel block
-  static constexpr int HALO_STRIDE = (HALO_BYTES + 1023) / 1024 * 1024;
+  static constexpr int TW = kTileW, TH = kTileH;
   static constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 elements (2 B)
-  static constexpr int B_BYTES = (BN / CG) * 128;   // this CTA's rows of the weight tile x 64 elements
-  // ring stage: A + B, or (HALO) B only next to two halo buffers
-  static constexpr int STAGE_BYTES = HALO ? NP * B_BYTES : NP * (A_BYTES + B_BYTES);
-  static constexpr int A_REGION = HALO ? 2 * NP * HALO_STRIDE : 0;
+  static constexpr int B_BYTES = BN * 128;   // weight tile rows x 64 elements
+  static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
   // 8 epilogue warps x 4 KB staging tiles for the TMA stores of the output (32 pixels x 32 channels x {hi, lo})
   static constexpr int STAGING_BYTES = 8 * 4096;
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STAGING_BYTES - A_REGION;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STAGING_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // fp32 mode keeps two accumulators per stage: [main = a_hi*w_hi | cross = a_hi*w_lo + a_lo*w_hi]
   static constexpr int ACC_COLS = NP * BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = A_REGION + STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
-  static_assert(!(HALO && CG == 2), "halo tiles and CTA pairs are not combined");
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two <= 512");
 };
 
@@ -393,7 +383,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
   }
 }
 
-template <int BN, int NP, int CG, bool HALO>
+template <int BN, int NP>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -401,18 +391,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                  const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ ConvKernelParams p) {
-  using Cfg = GemmCfg<BN, NP, CG, HALO>;
+  using Cfg = GemmCfg<BN, NP>;
   constexpr int TW = Cfg::TW, TH = Cfg::TH;
-  const int cta_rank = CG == 2 ? int(cluster_ctarank()) : 0;
-  // work items of this CTA (pair): first, stride, count
-  const int it_first = CG == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
-  const int it_step = CG == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
-  const int it_count = CG == 2 ? p.total_pairs : p.total_items;
+  const int it_first = int(blockIdx.x), it_step = int(gridDim.x), it_count = p.total_items;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem_base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // 1024-byte aligned (SWIZZLE_128B)
-  uint8_t* halo = smem_base;                      // HALO: two buffers of NP planes, HALO_STRIDE bytes each
-  uint8_t* smem = smem_base + Cfg::A_REGION;      // the stage ring
+  uint8_t* smem = smem_base;                      // the stage ring
   uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
@@ -420,9 +405,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;   // [8 epilogue warps][2 slots]
-  uint64_t* afull_bar = res_bar + 16;   // HALO: the two halo buffers
-  uint64_t* aempty_bar = afull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -452,22 +435,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8 * CG);   // the leader's copy collects the epilogue warps of both CTAs
+      mbar_init(&tempty_bar[a], 8);
     }
     for (int a = 0; a < 16; ++a) mbar_init(&res_bar[a], 1);
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&afull_bar[a], 1);
-      mbar_init(&aempty_bar[a], 1);
-    }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    if (CG == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
-    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
-  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -478,43 +453,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (HALO && lane == 0) {
-      // one (TH+2) x (TW+2)-pixel box per 64-channel block feeds all nine taps; the ring carries the weight tiles
-      uint32_t stage = 0, phase = 0, ab = 0, aphase = 0;
-      for (int item = it_first; item < it_count; item += it_step) {
-        int n, y0, x0, nb;
-        decode_item<TW, TH>(p, item, n, y0, x0, nb);
-        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
-          mbar_wait(&aempty_bar[ab], aphase ^ 1);
-          mbar_expect_tx(&afull_bar[ab], NP * Cfg::HALO_BYTES);
-          uint8_t* ha = halo + ab * NP * Cfg::HALO_STRIDE;
-          tma_load_4d(ha, &tmA0, &afull_bar[ab], kc * kKChunk, x0 - 1, y0 - 1, n);
-          if (NP == 2) tma_load_4d(ha + Cfg::HALO_STRIDE, &tmA1, &afull_bar[ab], kc * kKChunk, x0 - 1, y0 - 1, n);
-          if (++ab == 2) {
-            ab = 0;
-            aphase ^= 1;
-          }
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            uint8_t* sb = smem + stage * Cfg::STAGE_BYTES;
-            tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, nb * BN);
-            if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, nb * BN);
-            if (++stage == Cfg::STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-      }
-    }
-    if (!HALO && lane == 0) {
+    if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int item = it_first; item < it_count; item += it_step) {
         int n, y0, x0, nb;
-        if (CG == 2) decode_pair(p, item, cta_rank, n, y0, x0, nb);
-        else decode_item<TW, TH>(p, item, n, y0, x0, nb);
-        const int brow = nb * BN + cta_rank * (BN / CG);   // this CTA's rows of the weight tile
+        decode_item<TW, TH>(p, item, n, y0, x0, nb);
+        const int brow = nb * BN;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
           const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
@@ -522,21 +466,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + NP * Cfg::A_BYTES;
-            if (CG == 2) {
-              // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the pair
-              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-              tma_load_4d_pair(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
-              if (NP == 2)
-                tma_load_4d_pair(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
-              tma_load_2d_pair(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
-              if (NP == 2) tma_load_2d_pair(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
-            } else {
-              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-              tma_load_4d(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
-              if (NP == 2) tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
-              tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
-              if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
-            }
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_4d(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+            if (NP == 2) tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+            tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
+            if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -547,8 +481,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && cta_rank == 0) {   // CTA pairs: the leader issues for both
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, ab = 0, aphase = 0;
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int item = it_first; item < it_count; item += it_step) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_len) {
           const int kb1 = kb0 + chunk_len < num_kb ? kb0 + chunk_len : num_kb;
@@ -557,40 +491,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
           const uint32_t d_cross = d_main + BN;  // fp32 mode only
           for (int kb = kb0; kb < kb1; ++kb) {
-            const int tap = HALO ? kb % 9 : 0;   // HALO: k-blocks run channel-block major, tap minor
-            if (HALO && tap == 0) {
-              mbar_wait(&afull_bar[ab], aphase);
-              tc_fence_after();
-            }
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            // HALO: the A rows of tap (dy, dx) start (dy * pitch + dx) pixel rows into the halo box; 8-pixel groups (one
-            // tile row each) follow at a stride of one halo row
-            const uint32_t a_hi = HALO ? smem_u32(halo + ab * NP * Cfg::HALO_STRIDE) +
-                                             uint32_t((tap / 3) * Cfg::HALO_PITCH + tap % 3) * 128u
-                                       : smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint32_t a_plane = HALO ? Cfg::HALO_STRIDE : Cfg::A_BYTES;   // distance hi plane -> second plane
-            const uint32_t a_sbo = HALO ? Cfg::HALO_PITCH * 128 : 1024;
-            const uint32_t b_hi = HALO ? smem_u32(smem + stage * Cfg::STAGE_BYTES)
-                                       : smem_u32(smem + stage * Cfg::STAGE_BYTES) + NP * Cfg::A_BYTES;
+            const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t a_plane = Cfg::A_BYTES;   // distance hi plane -> second plane
+            const uint32_t a_sbo = 1024;
+            const uint32_t b_hi = a_hi + NP * Cfg::A_BYTES;
 #pragma unroll
             for (int k = 0; k < kKChunk / 16; ++k) {
               const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;  // first MMA of a chunk overwrites
               const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, a_sbo);
               const uint64_t db_hi = make_desc_sw128(b_hi + k * 32, 16, 1024);
-              if (CG == 2) {
-                umma_bf16_pair(d_main, da_hi, db_hi, p.idesc_hi, accum);
-                if (NP == 2) {
-                  const uint64_t da_lo = make_desc_sw128(a_hi + a_plane + k * 32, 16, a_sbo);
-                  const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
-                  if (p.x8) {
-                    umma_f8_pair(d_cross, da_lo, db_lo, p.idesc_hi, accum);
-                  } else {   // (the wide hi|lo trick does not survive the split of the weight rows over two CTAs)
-                    umma_bf16_pair(d_cross, da_hi, db_lo, p.idesc_hi, accum);
-                    umma_bf16_pair(d_cross, da_lo, db_hi, p.idesc_hi, 1u);
-                  }
-                }
-              } else if (NP == 2) {
+              if (NP == 2) {
                 // The weight planes lie back to back in the stage (hi rows, then lo rows) = ONE K-major tile of 2*BN rows:
                 // a_hi x [w_hi | w_lo] is a single MMA of width 2*BN that fills main (columns [0,BN)) and cross
                 // ([BN,2BN)) at once; a_lo x w_hi then accumulates into cross.  Same tensor cycles as three MMAs of
@@ -610,22 +522,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
               }
             }
-            if (CG == 2) umma_commit_pair(&empty_bar[stage]);
-            else umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
             }
-            if (HALO && tap == 8) {   // all nine taps of this channel block issued: the halo buffer may be refilled
-              umma_commit(&aempty_bar[ab]);
-              if (++ab == 2) {
-                ab = 0;
-                aphase ^= 1;
-              }
-            }
           }
-          if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
-          else umma_commit(&tfull_bar[acc]);  // chunk accumulator complete -> epilogue
+          umma_commit(&tfull_bar[acc]);  // chunk accumulator complete -> epilogue
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -667,8 +570,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     };
     for (int item = it_first; item < it_count; item += it_step) {
       int n, y0, x0, nb;
-      if (CG == 2) decode_pair(p, item, cta_rank, n, y0, x0, nb);
-      else decode_item<TW, TH>(p, item, n, y0, x0, nb);
+      decode_item<TW, TH>(p, item, n, y0, x0, nb);
       if (nb != st_nb) {
         flush_stats(st_nb);
         st_nb = nb;
@@ -709,10 +611,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
-          else mbar_arrive(&tempty_bar[acc]);
-        }
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       } else {
@@ -735,10 +634,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
-            else mbar_arrive(&tempty_bar[acc]);
-          }
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -756,12 +652,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 
   tc_fence_before();
-  if (CG == 2) cluster_sync_all();   // nobody leaves while the peer may still signal this CTA's barriers / read its smem
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
-    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -1061,40 +955,24 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NP, int CG = 1, bool HALO = false>
+template <int BN, int NP>
 static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, NP, CG, HALO>;
-  auto kern = conv_gemm_kernel<BN, NP, CG, HALO>;
+  using Cfg = GemmCfg<BN, NP>;
+  auto kern = conv_gemm_kernel<BN, NP>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(conv_gemm<%d,%d,%d>, %d B smem): %s", BN, NP, CG, Cfg::SMEM_BYTES,
-                cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(conv_gemm<%d,%d>, %d B smem): %s", BN, NP, Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return 1;
     }
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  if (CG == 2) {   // CTA pairs = clusters of two (same TPC)
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7],
-                                     maps[8], maps[9], kp);
-  if (e == cudaSuccess) e = cudaGetLastError();
+  kern<<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7],
+                                                        maps[8], maps[9], kp);
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
-    set_error("conv_gemm<%d,%d,%d> launch failed: %s", BN, NP, CG, cudaGetErrorString(e));
+    set_error("conv_gemm<%d,%d> launch failed: %s", BN, NP, cudaGetErrorString(e));
     return 1;
   }
   count_launch();
@@ -1135,49 +1013,30 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     return 1;
   }
   int BN = conv_gemm_pick_bn(s);
-  // 8-bit-cross operands with column blocks of 256: conv_gemm_wide_kernel (NSM_NO_WIDE=1: the 128-wide kernel)
+  // 8-bit-cross operands with column blocks of 256: conv_gemm_wide_kernel (NSM_NO_WIDE=1: the 128-wide kernel) ...
   static const bool wide_off = getenv("NSM_NO_WIDE") != nullptr;
-  static const bool exp_on = getenv("NSM_CG2") != nullptr || getenv("NSM_HALO") != nullptr;
-  // (the same kernel with 128-wide tiles is available -- NSM_WIDE128=1 -- but slower than the 64-channel double-buffered
-  //  kernel for conv8 3x3, 0.42 vs 0.34 ms: short K, so the single-buffered drain and the finer ring cost more than they save)
-  static const bool wide128 = getenv("NSM_WIDE128") != nullptr;
-  const bool wide = s.fmt == kFmtF16X8 && s.Cout % (wide128 ? 128 : 256) == 0 && s.Cin % 32 == 0 && !wide_off && !exp_on;
-  if (wide) BN = s.Cout % 256 == 0 ? 256 : 128;
-  // ... in clusters of two CTAs that multicast halves of the weight tile to each other (NSM_NO_WIDE_MC=1: single CTAs)
-  static const bool wide_mc_on = getenv("NSM_NO_WIDE_MC") == nullptr;
+  const bool wide = s.fmt == kFmtF16X8 && s.Cout % 256 == 0 && s.Cin % 32 == 0 && !wide_off;
+  if (wide) BN = 256;
   const int wide_tiles = s.N * ((s.W + kTileW - 1) / kTileW) * ((s.H + kTileH - 1) / kTileH);
-  // ... or, for 256-wide column blocks, as cta_group::2 pairs that split the weight tile (NSM_NO_WIDE_PAIR=1: multicast)
+  // ... as cta_group::2 pairs that split the weight tile (NSM_NO_WIDE_PAIR=1: clusters of two CTAs that multicast halves of
+  // it to each other; NSM_NO_WIDE_MC=1 on top of that: single CTAs)
   static const bool wide_pair_on = getenv("NSM_NO_WIDE_PAIR") == nullptr;
-  const bool wide_pair = wide && wide_pair_on && BN == 256 && wide_tiles >= 8;
+  static const bool wide_mc_on = getenv("NSM_NO_WIDE_MC") == nullptr;
+  const bool wide_pair = wide && wide_pair_on && wide_tiles >= 8;
   const int wide_mc = (wide && !wide_pair && wide_mc_on && wide_tiles >= 8) ? 2 : 1;
-  // CTA pairs (EXPERIMENTAL, NSM_CG2=1): bf16 and 8-bit-cross operands (the wide hi|lo MMA of the other formats needs the
-  // whole weight tile in one CTA), BN = 128 tiles, at least two pixel tiles.  Verified by the parity tests, moves 25 % fewer
-  // bytes through L2 -> shared memory (ncu: 14.5 GB against 19.3 GB for conv6 3x3), but is 30 % SLOWER at the moment: the
-  // tensor pipe is 38 % active and a k-block takes ~1200 cycles instead of ~870.  Relaying the peer's "operands landed"
-  // with one arrival per stage instead of remote complete_tx updates changed nothing, so the loss is on the MMA side:
-  // 128-wide pair MMAs (eight dependent accumulating instructions per k-block) seem to pay a per-instruction hand-shake
-  // between the two SMs that 256-wide tiles would amortise -- but hi+lo modes have no TMEM left for 256-wide double-buffered
-  // accumulators.
-  static const bool cg2_on = getenv("NSM_CG2") != nullptr;
-  // halo tiles for 3x3 convolutions (EXPERIMENTAL, NSM_HALO=1): parity-green and 45 % less L2 -> shared-memory traffic, but
-  // 0-7 % slower than one box per tap -- the activation boxes were never the expensive part of the feed (every CTA reads
-  // its own), the weight tiles are (eighteen CTAs read the same tile at the same time); not combined with pairs
-  static const bool halo_on = getenv("NSM_HALO") != nullptr;
-  const bool halo = s.taps == 9 && halo_on && !cg2_on;
-  const int TW = halo ? 8 : kTileW, TH = halo ? 16 : kTileH;
+  constexpr int TW = kTileW, TH = kTileH;
   const int m_tiles = s.N * ((s.W + TW - 1) / TW) * ((s.H + TH - 1) / TH);
-  const int CG = (cg2_on && BN == 128 && (s.fmt == kFmtBf16 || s.fmt == kFmtF16X8) && m_tiles >= 2) ? 2 : 1;
   CUtensorMap maps[10];  // A hi/lo, B hi/lo, output hi/lo, pooled output hi/lo, skip hi/lo
   memset(maps, 0, sizeof(maps));
   const uint64_t adims[4] = {uint64_t(s.Cin), uint64_t(s.W), uint64_t(s.H), uint64_t(s.N)};
   const uint64_t astr[3] = {uint64_t(s.Cin) * 2, uint64_t(s.W) * s.Cin * 2, uint64_t(s.H) * s.W * s.Cin * 2};
   const uint32_t kblk = wide ? kWideBK : kKChunk;   // channels per k-block = 64- or 128-byte operand rows
   const int op_swz = wide ? 64 : 128;
-  const uint32_t abox[4] = {kblk, uint32_t(halo ? TW + 2 : TW), uint32_t(halo ? TH + 2 : TH), 1};
+  const uint32_t abox[4] = {kblk, uint32_t(TW), uint32_t(TH), 1};
   const uint64_t K = uint64_t(s.taps) * s.Cin;
   const uint64_t bdims[2] = {K, uint64_t(s.Cout)};
   const uint64_t bstr[1] = {K * 2};
-  const uint32_t bbox[2] = {kblk, uint32_t(BN / (CG * wide_mc * (wide_pair ? 2 : 1)))};
+  const uint32_t bbox[2] = {kblk, uint32_t(BN / (wide_mc * (wide_pair ? 2 : 1)))};
   const int planes = fmt_planes(s.fmt);
   for (int pl = 0; pl < planes; ++pl) {
     if (!in.p[pl] || !w.p[pl]) {
@@ -1244,7 +1103,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.x8 = s.fmt == kFmtF16X8 ? 1 : 0;
   kp.cross_scale = kp.x8 ? kX8CrossScale : 1.f;
   const uint32_t ef = fmt_is_f16(s.fmt) ? kFmtF16 : kFmtBF16;  // fp16 / e4m3 share the descriptor code 0
-  kp.idesc_hi = make_idesc_f16(128 * CG * (wide_pair ? 2 : 1), BN, ef, ef, 0, 0);
+  kp.idesc_hi = make_idesc_f16(wide_pair ? 256 : 128, BN, ef, ef, 0, 0);
   kp.idesc_wide = planes == 2 ? make_idesc_f16(128, 2 * BN, ef, ef, 0, 0) : kp.idesc_hi;
   kp.ep = ep;
   if (wide) {
@@ -1275,16 +1134,13 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
       return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], maps[8],
                                 maps[9], kp);
     };
-    static bool attr_set[5] = {false, false, false, false, false};
+    static bool attr_set[3] = {false, false, false};
     cudaError_t e;
     if (wide_pair)
-      e = launch(conv_gemm_wide_kernel<256, 1, 2>, WideCfg<256, 2>::SMEM_BYTES, attr_set[4]);
-    else if (BN == 256)
+      e = launch(conv_gemm_wide_kernel<256, 1, 2>, WideCfg<256, 2>::SMEM_BYTES, attr_set[2]);
+    else
       e = wide_mc == 2 ? launch(conv_gemm_wide_kernel<256, 2>, WideCfg<256>::SMEM_BYTES, attr_set[0])
                        : launch(conv_gemm_wide_kernel<256, 1>, WideCfg<256>::SMEM_BYTES, attr_set[1]);
-    else
-      e = wide_mc == 2 ? launch(conv_gemm_wide_kernel<128, 2>, WideCfg<128>::SMEM_BYTES, attr_set[2])
-                       : launch(conv_gemm_wide_kernel<128, 1>, WideCfg<128>::SMEM_BYTES, attr_set[3]);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("conv_gemm_wide<%d,%d,%d> launch failed: %s", BN, wide_mc, wide_pair ? 2 : 1, cudaGetErrorString(e));
@@ -1293,21 +1149,7 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     count_launch();
     return 0;
   }
-  if (CG == 2) {
-    const int pairs = kp.total_pairs < num_sms() / 2 ? kp.total_pairs : num_sms() / 2;
-    if (planes == 1) return launch_t<128, 1, 2>(maps, kp, 2 * pairs, stream);
-    return launch_t<128, 2, 2>(maps, kp, 2 * pairs, stream);
-  }
   const int grid = kp.total_items < num_sms() ? kp.total_items : num_sms();
-  if (halo) {
-    if (planes == 1) {
-      if (BN == 256) return launch_t<256, 1, 1, true>(maps, kp, grid, stream);
-      if (BN == 128) return launch_t<128, 1, 1, true>(maps, kp, grid, stream);
-      return launch_t<64, 1, 1, true>(maps, kp, grid, stream);
-    }
-    if (BN == 128) return launch_t<128, 2, 1, true>(maps, kp, grid, stream);
-    return launch_t<64, 2, 1, true>(maps, kp, grid, stream);
-  }
   if (planes == 1) {
     if (BN == 256) return launch_t<256, 1>(maps, kp, grid, stream);
     if (BN == 128) return launch_t<128, 1>(maps, kp, grid, stream);

@@ -156,33 +156,6 @@ def test_conv_stage_x8_operands(nsm, case):
     assert (raw - raw1).abs().max().item() <= tol
 
 
-def test_conv_stage_cta_pairs():
-    """The experimental CTA-pair (cta_group::2) variant of the conv kernel, enabled with NSM_CG2=1 (read once per process,
-    hence the subprocess): same results as the single-CTA kernel on bf16 and 8-bit-cross operands, odd tile counts."""
-    import os, subprocess, sys
-    code = r'''
-import sys, torch
-sys.path[:0] = [%r, %r]
-import nsm
-torch.manual_seed(0)
-for mode, (N, H, W, C, k) in [(nsm.MODE_BF16, (1, 23, 37, 128, 3)), (nsm.FMT_F16_X8, (3, 9, 17, 256, 3)),
-                              (nsm.MODE_BF16, (2, 16, 16, 128, 1))]:
-    x = torch.randn(N, C, H, W).to(torch.bfloat16).float()
-    w = (torch.randn(128, C, k, k) / (C * k * k) ** 0.5).to(torch.bfloat16).float()
-    xt = nsm.PlaneTensor.from_nchw(x.cuda(), mode)
-    _, _, raw = nsm.conv_fwd(xt, nsm.pack_conv_weight(w.cuda(), mode), k, 128, mode, want_f32=True)
-    ref = torch.nn.functional.conv2d(x.double(), w.double(), padding=k // 2).float()
-    err = (raw.permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
-    assert err <= 6e-5 * max(1.0, ref.abs().max().item()), (mode, err)
-print("pairs ok")
-''' % (os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pcss-unet_b200"),
-       os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    for flag in ("NSM_CG2", "NSM_HALO"):     # the halo-tile variant (one activation box for all nine taps) likewise
-        env = dict(os.environ, **{flag: "1"})
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0 and "pairs ok" in r.stdout, flag + "\n" + r.stdout + r.stderr
-
-
 @pytest.mark.parametrize("shape", [(2, 128, 67, 120, 135, 240), (1, 64, 20, 28, 20, 28), (1, 512, 5, 7, 10, 14)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_upsample_match_x8_output(nsm, shape):
