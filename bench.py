@@ -679,6 +679,25 @@ def measure_train(args, own_process_group=True):
         step(x, t)
     barrier()
     dp_check = dp_gradient_check(net, crit, sync, x, t, world) if world > 1 else None
+    # The whole step (forward, loss, backward, NCCL gradient buckets, clip + AdamW) as ONE CUDA graph launch
+    # (nsm_graph.GraphedTrainStep): same kernels, same arithmetic, no Python between them.  --no-graph times the eager loop.
+    graphed = None
+    if not args.no_graph:
+        try:
+            from nsm_graph import GraphedTrainStep
+            graphed = GraphedTrainStep(net, crit, opt, x, t, sync=sync, warmup=2)
+            eager_step = step
+
+            def step(xd, td):                         # noqa: F811
+                return graphed(xd if xd is not graphed.x else None, td if td is not graphed.t else None)
+            x, t = graphed.x, graphed.t               # the device-resident timing feeds the static buffers in place
+        except Exception as ex:                       # capture refused (e.g. a collective that cannot be captured): eager
+            graphed = None
+            graph_error = repr(ex)[:200]
+            torch.cuda.synchronize()
+    for _ in range(2):
+        step(x, t)
+    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     evs = []
@@ -693,6 +712,12 @@ def measure_train(args, own_process_group=True):
         evs.append((s, e))
     barrier()
     launches = nsm.launch_count() - launches0
+    if graphed is not None:
+        # replays do not pass through the library's launch counter: count one eager step of the same sequence
+        l0 = nsm.launch_count()
+        eager_step(x, t)
+        torch.cuda.synchronize()
+        launches = (nsm.launch_count() - l0) * args.steps
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
     # end to end like a training loop with a pinned, prefetching loader (setdata_b200.DeviceFeeder's scheme): every step's
     # batch is copied from pinned host memory inside the timed region -- on a side stream, one step ahead -- and every
@@ -730,10 +755,12 @@ def measure_train(args, own_process_group=True):
     barrier()
     clocks = sampler.stop()
     nsm.profile_enable(True)
-    step(x, t)
+    (eager_step if graphed is not None else step)(x, t)
     torch.cuda.synchronize()
     rows = nsm.profile_read()
     nsm.profile_enable(False)
+    if graphed is not None:
+        graphed.check()
 
     tt = torch.tensor([dev_ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -785,6 +812,7 @@ def measure_train(args, own_process_group=True):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": (x_host.numel() + t_host.numel()) * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_loss": last},
             "gpu_launches": launches,
+            "cuda_graph": (graphed is not None),
             "dp_check": dp_check,
             "roofline": roofline}
     if dp_check is not None and not dp_check["ok"]:
@@ -821,6 +849,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock", action="store_true", help="skip the stock PyTorch/cuDNN same-GPU baseline")
     ap.add_argument("--no-perturb", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="training: eager Python-driven launches instead of the CUDA graph")
     ap.add_argument("--no-train", action="store_true", help="inference workload: skip the attached training measurement")
     ap.add_argument("--train-precision", default=None, choices=["fp32", "bf16"])
     ap.add_argument("--train-batch", type=int, default=None)

@@ -2,6 +2,7 @@
 // per-channel reductions: fp32 in registers over short runs -> fp64 per thread -> shared memory -> one fp64 atomic per
 // channel and block.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "nsm_common.cuh"
 #include "plane_io.cuh"
@@ -782,6 +783,85 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const Planes dout, i
   store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, FMT, acc);
 }
 
+// Strip-walking adjoint for the two shapes that carry the bytes: the plain x2 up-sample (ho == 2hi: levels 6-8 at sizes
+// divisible by 8) and the same-size composite of level 9 (x2 up, then back down: a position-dependent 3-tap blur).
+//   din[r][q] = sum_y wy(y, r) * T[y][q],   T[y][q] = sum_x wx(x, q) * dout[y][x]
+// The weights are read off the forward taps (resample.cuh: composite_taps), so forward and adjoint cannot drift apart.
+// Source row r only receives from WIN consecutive output rows (x2: 2r-1 .. 2r+2; same size: r-2 .. r+2, the outer two with
+// zero weight away from the borders), and columns likewise.  One thread owns a source column (8 channels) and walks down a
+// strip of source rows: every horizontally reduced row T[y] is formed ONCE (WIN loads) and feeds all source rows that touch
+// it -- 4-5 loads per source pixel where the gather kernels below issue 16-25 -- and stays in registers (static indices).
+constexpr int kBwdStrip = 16;
+template <int FMT, bool X2>
+__global__ void __launch_bounds__(256) upsample_bwd_strip_kernel(const Planes dout, int N, int C, const Planes din, int hi,
+                                                                 int wi, int cg_shift, int strips) {
+  constexpr int WIN = X2 ? 4 : 5, STEP = X2 ? 2 : 1, OFF = X2 ? 1 : 2;   // window of output rows y = STEP*r - OFF + j
+  const int ho = X2 ? 2 * hi : hi, wo = X2 ? 2 * wi : wi;
+  const int cgs = 1 << cg_shift;
+  const int j = blockIdx.y * 256 + threadIdx.x;
+  const bool active = j < wi * cgs;
+  const int cg = j & (cgs - 1), q = active ? (j >> cg_shift) : 0;
+  const int n = blockIdx.x / strips, r0 = (blockIdx.x - n * strips) * kBwdStrip;
+  const int r1 = min(r0 + kBwdStrip, hi);
+  auto weight_of = [](int src, int out_idx, int in_size, int out_size) {
+    if (out_idx < 0 || out_idx >= out_size) return 0.f;
+    const Tap3 t = composite_taps(out_idx, in_size, out_size);
+    const int d = src - t.rmin;
+    return d == 0 ? t.w[0] : (d == 1 ? t.w[1] : (d == 2 ? t.w[2] : 0.f));
+  };
+  __shared__ float s_wy[kBwdStrip][WIN];
+  for (int k = threadIdx.x; k < kBwdStrip * WIN; k += 256) {
+    const int rr = r0 + k / WIN, jj = k % WIN;
+    s_wy[k / WIN][jj] = rr < hi ? weight_of(rr, STEP * rr - OFF + jj, hi, ho) : 0.f;
+  }
+  __syncthreads();
+  if (!active) return;
+  float wx[WIN];
+#pragma unroll
+  for (int b = 0; b < WIN; ++b) wx[b] = weight_of(q, STEP * q - OFF + b, wi, wo);
+  const int x0 = STEP * q - OFF;
+  // T rows of the window, horizontally reduced; a row outside the image (or with all-zero weights) is zero
+  auto hrow = [&](int y, float (&t)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t[e] = 0.f;
+    if (y < 0 || y >= ho) return;
+    const size_t rbase = ((size_t)n * ho + y) * wo;
+    Raw8 raw[WIN];
+#pragma unroll
+    for (int b = 0; b < WIN; ++b)
+      if (wx[b] != 0.f) raw[b] = load_raw8(dout, (rbase + x0 + b) * C + cg * 8, FMT);   // wx != 0 implies 0 <= x < wo
+#pragma unroll
+    for (int b = 0; b < WIN; ++b) {
+      if (wx[b] == 0.f) continue;
+      float d[8];
+      unpack8(raw[b], FMT, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = fmaf(wx[b], d[e], t[e]);
+    }
+  };
+  float T[WIN][8];
+#pragma unroll
+  for (int a = STEP; a < WIN; ++a) hrow(STEP * r0 - OFF + a - STEP, T[a]);   // rows the first iteration shifts into place
+  for (int r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int a = 0; a + STEP < WIN; ++a)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) T[a][e] = T[a + STEP][e];
+#pragma unroll
+    for (int a = WIN - STEP; a < WIN; ++a) hrow(STEP * r - OFF + a, T[a]);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int a = 0; a < WIN; ++a) {
+      const float w = s_wy[r - r0][a];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, T[a][e], acc[e]);
+    }
+    store8(din, (((size_t)n * hi + r) * wi + q) * C + cg * 8, FMT, acc);
+  }
+}
+
 int upsample_match_bwd(const Planes& dout, int N, int ho, int wo, int C, const Planes& din, int hi, int wi, int fmt,
                        cudaStream_t st) {
   if (check_c("upsample_match_bwd", C)) return 1;
@@ -789,7 +869,19 @@ int upsample_match_bwd(const Planes& dout, int N, int ho, int wo, int C, const P
   int shift = 0;
   while ((1 << shift) < cgs) ++shift;
   dim3 grid((unsigned)(N * hi), (unsigned)((wi * cgs + 255) / 256));
-  if (ho == 2 * hi && wo == 2 * wi) {
+  static const bool strip_off = getenv("NSM_NO_BWD_STRIP") != nullptr;   // A/B switch: the per-pixel gather kernels
+  const bool x2 = ho == 2 * hi && wo == 2 * wi, same = ho == hi && wo == wi;
+  if ((x2 || same) && !strip_off && hi >= 2 && wi >= 2) {
+    const int strips = (hi + kBwdStrip - 1) / kBwdStrip;
+    dim3 sgrid((unsigned)(N * strips), (unsigned)((wi * cgs + 255) / 256));
+#define NSM_BWD_STRIP(F)                                                                                               \
+    if (x2) upsample_bwd_strip_kernel<F, true><<<sgrid, 256, 0, st>>>(dout, N, C, din, hi, wi, shift, strips);          \
+    else upsample_bwd_strip_kernel<F, false><<<sgrid, 256, 0, st>>>(dout, N, C, din, hi, wi, shift, strips)
+    if (fmt == kFmtBf16) { NSM_BWD_STRIP(kFmtBf16); }
+    else if (fmt == kFmtF16x2) { NSM_BWD_STRIP(kFmtF16x2); }
+    else { NSM_BWD_STRIP(kFmtBf16x2); }
+#undef NSM_BWD_STRIP
+  } else if (x2) {
     if (fmt == kFmtBf16) upsample2x_bwd_kernel<kFmtBf16><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
     else if (fmt == kFmtF16x2) upsample2x_bwd_kernel<kFmtF16x2><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);
     else upsample2x_bwd_kernel<kFmtBf16x2><<<grid, 256, 0, st>>>(dout, N, C, din, hi, wi, fmt, shift);

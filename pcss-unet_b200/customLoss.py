@@ -148,24 +148,46 @@ class _FusedL1(torch.autograd.Function):
     """mean|o - t| with the gradient produced by the same kernel pass."""
 
     @staticmethod
-    def forward(ctx, output, target, check_range):
+    def forward(ctx, output, target, check_range, owner=None):
         o32 = output.detach().to(torch.float32).contiguous()
         acc, sign = nsm.l1_loss_fwd_bwd(o32, target.detach(), (), coef_l1=1.0, want_grad=True)
         ctx.save_for_backward(sign)       # sign(o - t) in {-1, 0, +1}
         ctx.numel = o32.numel()
         ctx.out_dtype = output.dtype
-        if check_range and float(acc[2].item()) != 0.0:     # one sync; the reference does two (:131)
-            raise AssertionError("输出必须经过Sigmoid激活!")
+        if check_range:
+            if owner is not None and owner.lazy_range_check:
+                owner.note_range_flag(acc[2])               # read back later (CUDA-graph capture: no sync inside a step)
+            elif float(acc[2].item()) != 0.0:               # one sync; the reference does two (:131)
+                raise AssertionError("输出必须经过Sigmoid激活!")
         return (acc[0] / o32.numel()).to(torch.float32)
 
     @staticmethod
     def backward(ctx, g):
         (sign,) = ctx.saved_tensors
         # same evaluation order as autograd of (o - t).abs().mean(): (g / N) * sign  -> bit-identical gradient
-        return (sign * (g / ctx.numel)).to(ctx.out_dtype), None, None
+        return (sign * (g / ctx.numel)).to(ctx.out_dtype), None, None, None
 
 
-class L1Loss(nn.Module):
+class _LazyRangeCheck:
+    """`assert 0 <= output <= 1` (customLoss.py:131) without a host synchronisation inside the step: with
+    ``lazy_range_check = True`` the kernel's out-of-range count is accumulated on the device and
+    ``raise_if_out_of_range()`` reads it when the caller chooses to (nsm_graph.GraphedTrainStep.check)."""
+    lazy_range_check = False
+
+    def note_range_flag(self, flag):
+        acc = self.__dict__.get("_range_acc")
+        if acc is None:
+            acc = self.__dict__["_range_acc"] = torch.zeros((), dtype=torch.float64, device=flag.device)
+        acc += flag
+
+    def raise_if_out_of_range(self):
+        acc = self.__dict__.get("_range_acc")
+        if acc is not None and float(acc.item()) != 0.0:
+            acc.zero_()
+            raise AssertionError("输出必须经过Sigmoid激活!")
+
+
+class L1Loss(nn.Module, _LazyRangeCheck):
     """nn.L1Loss() stand-in (customLoss.py:96) backed by the fused kernel."""
 
     def __init__(self, check_range=False):
@@ -174,7 +196,7 @@ class L1Loss(nn.Module):
 
     def forward(self, output, target):
         nsm.require_device(output)
-        return _FusedL1.apply(output, target, self.check_range)
+        return _FusedL1.apply(output, target, self.check_range, self)
 
 
 class CustomLoss(nn.Module):

@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 import nsm
-from customLoss import L1Loss, make_vgg_term
+from customLoss import L1Loss, _LazyRangeCheck, make_vgg_term
 
 
 def channel_stds_unbiased(x):
@@ -94,7 +94,7 @@ class PerturbationLoss(nn.Module):
         return total
 
 
-class EnhancedCustomLoss(nn.Module):
+class EnhancedCustomLoss(nn.Module, _LazyRangeCheck):
     def __init__(self, device, alpha=0.9, perturb_weight=0.5, vgg_loss="auto"):
         super().__init__()
         self.alpha = alpha
@@ -110,7 +110,9 @@ class EnhancedCustomLoss(nn.Module):
         ys = self.perturbation_loss.perturbed_outputs(model, inputs, noise) if use_pert else []
         total, l1, pert, bad = _FusedPerturbL1.apply(output, target.detach(), self.alpha,
                                                      self.perturb_weight if use_pert else 0.0, *ys)
-        if float(bad.item()) != 0.0:
+        if self.lazy_range_check:
+            self.note_range_flag(bad)
+        elif float(bad.item()) != 0.0:
             raise AssertionError("输出必须经过Sigmoid激活!")
         if self.vgg_loss is None:
             vgg = torch.zeros((), dtype=torch.float32, device=output.device)

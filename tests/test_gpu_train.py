@@ -422,3 +422,129 @@ def test_loss_curve_matches_oracle(nsm):
     ma_dev = max(abs(ma(curve, i) - ma(curve_ref, i)) / ma(curve_ref, i) for i in range(steps - 7))
     print("moving-average deviation", ma_dev, "mean deviation", sum(devs) / len(devs))
     assert ma_dev <= 0.01 and rel_dev <= 0.03 and sum(devs) / len(devs) <= 0.005
+
+
+@pytest.mark.parametrize("mode_name", MODES)
+@pytest.mark.parametrize("case", [(16, 16, 3), (16, 64, 1), (64, 16, 1), (16, 4, 1)], ids=lambda c: "x".join(map(str, c)))
+def test_pixel_packed_thin_layers(nsm, mode_name, case):
+    """conv2 / conv9 1x1 / conv10 at their REAL channel counts: four adjacent pixels = one virtual pixel of 4C channels,
+    block-diagonal / banded weights (nsm_pack_conv_weight_px4).  Forward (+ fused BN statistics folded back to the real
+    channels), dgrad and wgrad against autograd of F.conv2d, and against the zero-padded path."""
+    import nsm_train
+    Cin, Cout, k = case
+    mode = nsm.MODES[mode_name]
+    g = gen(Cin * 7 + Cout)
+    N, H, W = 2, 11, 20                       # W % 4 == 0, ragged tiles in both directions
+    x = torch.randn(N, Cin, H, W, generator=g)
+    dz = torch.randn(N, Cout, H, W, generator=g) * 1e-2
+    conv = torch.nn.Conv2d(Cin, Cout, k, padding=k // 2)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5)
+        conv.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+    if mode_name == "bf16":
+        x, dz = bf(x), bf(dz)
+        with torch.no_grad():
+            conv.weight.copy_(bf(conv.weight)); conv.bias.copy_(bf(conv.bias))
+    xr = x.clone().requires_grad_(True)
+    y_ref = conv(xr)
+    y_ref.backward(dz)
+    dw_ref = conv.weight.grad.clone()
+    conv = conv.cuda()
+    outs = {}
+    for px4 in (True, False):
+        layer = nsm_train._Conv(conv, mode, px4)
+        assert layer.px == px4
+        cs_in, cs_out = layer.cin_s, layer.cout_s
+        xp = torch.zeros(N, cs_in, H, W); xp[:, :Cin] = x
+        dzp = torch.zeros(N, cs_out, H, W); dzp[:, :Cout] = dz
+        xt, dzt = planes(nsm, xp, mode), planes(nsm, dzp, mode)
+        z, sums = layer.forward(xt, mode)
+        if px4 and Cout == 4:                 # conv10 keeps its virtual layout: 16 of 64 channels, pixel po at [4po, 4po+4)
+            zz = z.to_nchw().cpu()[:, :16].reshape(N, 4, 4, H, W // 4).permute(0, 2, 3, 4, 1).reshape(N, 4, H, W)
+        else:
+            zz = z.to_nchw().cpu()[:, :Cout]
+        assert rel(zz, y_ref) <= (1e-4 if mode_name != "bf16" else 1e-2)
+        s = sums.cpu().reshape(2, -1)[:, :Cout]
+        ref64 = y_ref.detach().double()
+        if mode_name == "bf16":
+            ref64 = bf(y_ref.detach()).double()
+        assert torch.allclose(s[0], ref64.sum(dim=(0, 2, 3)), rtol=2e-2 if mode_name == "bf16" else 1e-4, atol=5e-2)
+        assert torch.allclose(s[1], (ref64 * ref64).sum(dim=(0, 2, 3)), rtol=2e-2 if mode_name == "bf16" else 1e-4, atol=5e-2)
+        if px4 and Cout == 4:                 # the gradient of conv10's output arrives in the virtual layout too
+            v = torch.zeros(N, 64, H, W // 4)
+            v[:, :16] = dz.reshape(N, 4, H, W // 4, 4).permute(0, 4, 1, 2, 3).reshape(N, 16, H, W // 4)
+            dzt = planes(nsm, v, mode)
+        dx = layer.dgrad(dzt, mode).to_nchw().cpu()[:, :Cin]
+        dw = layer.wgrad(dzt, xt).cpu()
+        assert dw.shape == conv.weight.shape
+        assert rel(dx, xr.grad) <= GTOL[mode_name] and rel(dw, dw_ref) <= GTOL[mode_name]
+        outs[px4] = (zz, dx, dw)
+    for a, b in zip(outs[True], outs[False]):
+        assert rel(a, b) <= (1e-5 if mode_name != "bf16" else 1e-2)
+
+
+def test_train_step_padded_fallback(nsm):
+    """Level width not a multiple of 4 (52 / 2 = 26): the thin layers fall back to zero-padding; same parity bar."""
+    P = oracle.init_params(42)
+    x = torch.randn(1, 4, 36, 52, generator=gen(15))
+    t = torch.rand(1, 1, 36, 52, generator=gen(16))
+    masks = _masks(19, 1)
+    Po = {k: v.clone() for k, v in P.items()}
+    o_ref, l_ref, g_ref = oracle.train_step_grads(x, t, Po, masks=masks, input_grad=True)
+    net, out, loss, grads = _gpu_step(P, x, t, masks, "fp32")
+    assert getattr(net, "_train_packed")[1].px4 is False
+    assert (out - o_ref).abs().max().item() <= 1e-4 and abs(loss - l_ref.item()) <= 1e-5
+    names = oracle.param_names()
+    num = sum(float((grads[n].double() - g_ref[n].double()).pow(2).sum()) for n in names)
+    den = sum(float(g_ref[n].double().pow(2).sum()) for n in names)
+    assert (num / den) ** 0.5 <= 1e-2
+    assert rel(grads["input"], g_ref["input"]) <= 1e-2
+
+
+def test_cuda_graph_training_step_matches_eager(nsm):
+    """nsm_graph.GraphedTrainStep: the captured step (forward, CustomLoss, backward, fused clip + AdamW) replays to the same
+    losses and parameters as the eager Python-driven step, including BN running statistics and the device-side AdamW step
+    counter; the deferred [0,1] range check still fires."""
+    from Unetmodel import Unet
+    from customLoss import CustomLoss
+    from nsm_optim import FusedAdamWClip
+    from nsm_graph import GraphedTrainStep
+    P = oracle.init_params(42)
+    g = gen(91)
+    data = [(torch.randn(2, 4, 64, 96, generator=g).cuda(), torch.rand(2, 1, 64, 96, generator=g).cuda()) for _ in range(4)]
+
+    def make():
+        net = Unet(dropout_rate=0.0, precision="fp32")
+        net.load_state_dict({k: v.clone() for k, v in P.items()})
+        net = net.cuda().train()
+        return net, CustomLoss("cuda", alpha=0.9, vgg_loss=None), None
+
+    net_a, crit_a, _ = make()
+    opt_a = FusedAdamWClip(net_a.parameters(), lr=7e-4, weight_decay=1e-3, max_norm=1.0)
+    net_b, crit_b, _ = make()
+    opt_b = FusedAdamWClip(net_b.parameters(), lr=7e-4, weight_decay=1e-3, max_norm=1.0)
+    warm = 2
+    gs = GraphedTrainStep(net_b, crit_b, opt_b, data[0][0], data[0][1], warmup=warm)   # warm-up + capture = warm + 1 steps
+    losses_a, losses_b = [], []
+    for k in range(warm + 1):                        # the eager twin takes the same steps on the same first batch
+        opt_a.zero_grad(set_to_none=True)
+        loss = crit_a(net_a(data[0][0]), data[0][1], None)
+        loss.backward()
+        opt_a.step()
+    for x, t in data:
+        opt_a.zero_grad(set_to_none=True)
+        loss = crit_a(net_a(x), t, None)
+        loss.backward()
+        opt_a.step()
+        losses_a.append(loss.item())
+        losses_b.append(gs(x, t).item())
+    gs.check()
+    print("eager", losses_a, "graph", losses_b)
+    assert max(abs(a - b) for a, b in zip(losses_a, losses_b)) <= 2e-6
+    sa, sb = net_a.state_dict(), net_b.state_dict()
+    for k in sa:
+        if sa[k].is_floating_point():
+            assert torch.allclose(sa[k], sb[k], rtol=1e-4, atol=1e-6), k
+        else:
+            assert int(sa[k]) == int(sb[k]), k
+    assert float(opt_a.applied_steps) == float(opt_b.applied_steps) == warm + 1 + len(data)
