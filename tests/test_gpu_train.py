@@ -524,9 +524,9 @@ def test_cuda_graph_training_step_matches_eager(nsm):
     net_b, crit_b, _ = make()
     opt_b = FusedAdamWClip(net_b.parameters(), lr=7e-4, weight_decay=1e-3, max_norm=1.0)
     warm = 2
-    gs = GraphedTrainStep(net_b, crit_b, opt_b, data[0][0], data[0][1], warmup=warm)   # warm-up + capture = warm + 1 steps
+    gs = GraphedTrainStep(net_b, crit_b, opt_b, data[0][0], data[0][1], warmup=warm)   # `warm` real steps; capturing executes nothing
     losses_a, losses_b = [], []
-    for k in range(warm + 1):                        # the eager twin takes the same steps on the same first batch
+    for k in range(warm):                            # the eager twin takes the same steps on the same first batch
         opt_a.zero_grad(set_to_none=True)
         loss = crit_a(net_a(data[0][0]), data[0][1], None)
         loss.backward()
@@ -547,4 +547,4 @@ def test_cuda_graph_training_step_matches_eager(nsm):
             assert torch.allclose(sa[k], sb[k], rtol=1e-4, atol=1e-6), k
         else:
             assert int(sa[k]) == int(sb[k]), k
-    assert float(opt_a.applied_steps) == float(opt_b.applied_steps) == warm + 1 + len(data)
+    assert float(opt_a.applied_steps) == float(opt_b.applied_steps) == warm + len(data)
