@@ -129,6 +129,35 @@ typedef struct nsm_conv_args {
 } nsm_conv_args;
 int nsm_conv_fwd(const nsm_conv_args* a, void* stream);
 
+/* Fused eval-mode decoder block, ONE launch (Unetmodel.py:51-60, 134-148 with DoubleConv :20-30):
+ *   x = F.interpolate(nn.Upsample(x2)(src), size=(H,W))  -- composite bilinear stencil built on the 3x3 convolution's
+ *       operand path in shared memory, never written to HBM
+ *   t = LeakyReLU(BN(conv3x3(x)));  o = LeakyReLU(BN(conv1x1(t)))   -- t stays in tensor memory
+ *   tail == 0:  out = o + residual                                                       (conv8 + skip, :137)
+ *   tail == 1:  y = sigmoid(pixel_shuffle(conv10(o), 2)), optional uint8 copy            (conv9 .. output, :143-148)
+ * mode NSM_MODE_BF16 or NSM_MODE_FP32 (eval); weight3 = 3x3 planes as nsm_unet_pack stores them for the decoder
+ * (fp32 mode: fp16 hi + 8-bit cross plane), weight1 = 1x1 planes ([Cout][Cmid], fp32 mode: fp16 hi + lo). */
+typedef struct nsm_upblock_args {
+  int mode, N, Hs, Ws, H, W, Cmid, Cout;   /* Cmid 64|128, Cout 16|64 */
+  const void* src[2];                      /* [N,Hs,Ws,Cmid] planes */
+  const void* weight3[2];
+  const void* weight1[2];
+  const float *bias3, *bn_scale3, *bn_shift3;   /* [Cmid] */
+  const float *bias1, *bn_scale1, *bn_shift1;   /* [Cout] */
+  const void* residual[2];                 /* [N,H,W,Cout] planes or NULL */
+  void* out[2];                            /* [N,H,W,Cout] planes (tail == 0) */
+  int tail;
+  const float *w10, *b10;                  /* conv10 [4][16], [4] fp32 (tail == 1; pre-rounded to bf16 in bf16 mode) */
+  float* y;                                /* [N,1,2H,2W] */
+  uint8_t* y_u8;                           /* optional */
+} nsm_upblock_args;
+int nsm_upblock(const nsm_upblock_args* a, void* stream);
+/* 1 when nsm_unet_infer runs conv8 / conv9 as fused blocks (default), 0 with NSM_NO_FUSED=1 in the environment */
+int nsm_unet_fused_decoder(void);
+/* tests: 1 / 0 force the fused / stage-by-stage decoder (the latter leaves u8 t8 u9 t9 visible to nsm_unet_tap), -1 restores
+ * the environment default */
+int nsm_unet_set_fused_decoder(int on);
+
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) then F.interpolate(size=(hd,wd)) -- Unetmodel.py:51-60,
  * 118-141 */
 int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, void* const* dst, int hd, int wd,

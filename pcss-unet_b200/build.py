@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnsm_b200.so")
-SOURCES = ["conv_gemm.cu", "stream_kernels.cu", "train_kernels.cu", "wgrad_gemm.cu", "optim_kernels.cu", "vgg_kernels.cu", "api.cu"]
+SOURCES = ["conv_gemm.cu", "stream_kernels.cu", "train_kernels.cu", "wgrad_gemm.cu", "optim_kernels.cu", "vgg_kernels.cu", "upblock.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

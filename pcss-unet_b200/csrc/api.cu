@@ -2,6 +2,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -11,6 +12,7 @@
 #include "nsm_common.cuh"
 #include "stream_kernels.cuh"
 #include "train_kernels.cuh"
+#include "upblock.cuh"
 
 namespace nsm {
 const char* last_error();
@@ -34,6 +36,7 @@ struct PackedLayout {
   size_t v3[8][3];  // bias, scale, shift of the 3x3 stage  [cin]
   size_t v1[8][3];  // bias, scale, shift of the 1x1 stage  [cout]
   size_t w10, b10;
+  size_t w1g7[2];   // conv9's 1x1 weights as GEMM operand planes [16][64] (fused decoder block)
   size_t head_img;  // conv2's operand image for the head kernel (head_pack_image)
   size_t tail_img;  // conv9 1x1 + conv10 operand image for the tail kernel (tail_pack_image)
   size_t total;
@@ -44,6 +47,15 @@ struct PackedLayout {
 static int decoder3x3_fmt(int mode) {
   static const bool off = getenv("NSM_NO_X8") != nullptr;
   return (mode == NSM_MODE_FP32 && !off) ? kFmtF16X8 : mode;
+}
+
+// conv8 / conv9 (+ conv10, sigmoid, pixel_shuffle) of the eval forward as fused blocks (upblock.cu): no up-sample launch,
+// no u8 / t8 / u9 / t9 in HBM.  NSM_NO_FUSED=1: the stage-by-stage path (every intermediate visible to nsm_unet_tap).
+static std::atomic<int> g_fused_override{-1};   // nsm_unet_set_fused_decoder: -1 = environment default
+static bool fused_decoder(int mode) {
+  static const bool off = getenv("NSM_NO_FUSED") != nullptr;
+  const int ov = g_fused_override.load(std::memory_order_relaxed);
+  return (ov < 0 ? !off : ov != 0) && (mode == NSM_MODE_BF16 || mode == NSM_MODE_FP32);
 }
 
 static PackedLayout packed_layout(int mode) {
@@ -71,6 +83,7 @@ static PackedLayout packed_layout(int mode) {
   }
   L.w10 = take(4 * 16 * 4);
   L.b10 = take(4 * 4);
+  for (int p = 0; p < 2; ++p) L.w1g7[p] = p < np ? take(16 * 64 * 2) : 0;
   L.head_img = take(kHeadImageBytes);
   L.tail_img = take(kTailImageBytes);
   L.total = off;
@@ -245,6 +258,7 @@ int nsm_unet_pack(const float* const* T, int mode, void* blob, void* stream) {
   }
   NSM_TRY(copy_round(T[96], reinterpret_cast<float*>(base + L.w10), 64, rb, st));
   NSM_TRY(copy_round(T[97], reinterpret_cast<float*>(base + L.b10), 4, rb, st));
+  NSM_TRY(pack_conv_weight(T[12 * 7 + 6], 16, 64, 1, 0, mode, base + L.w1g7[0], rb ? nullptr : base + L.w1g7[1], st));
   auto fv = [&](size_t off) { return reinterpret_cast<const float*>(base + off); };
   NSM_TRY(head_pack_image(fv(L.w3[0][0]), fv(L.v3[0][0]), fv(L.v3[0][1]), fv(L.v3[0][2]), fv(L.w1[0][0]), fv(L.v1[0][0]),
                           fv(L.v1[0][1]), fv(L.v1[0][2]), mode, base + L.head_img, st));
@@ -345,6 +359,34 @@ static int infer_impl(const void* blob, int mode, const float* x, int B, int H, 
   NSM_TRY(double_conv(4, 3, buf("u6"), "t6", "m6", "c4", nullptr));   // conv6 + skip
   NSM_TRY(up("m6", 3, 512, "u7", 2));
   NSM_TRY(double_conv(5, 2, buf("u7"), "t7", "m7", "c3", nullptr));   // conv7 + skip
+  if (fused_decoder(mode)) {
+    // ---- conv8 (+ skip) and conv9 + conv10 + sigmoid + pixel_shuffle as two fused blocks
+    auto block = [&](int b, int slevel, const char* src, const char* res, const char* dst) -> int {
+      UpBlockArgs a;
+      memset(&a, 0, sizeof(a));
+      a.mode = mode; a.N = B; a.Hs = WL.lv[slevel].h; a.Ws = WL.lv[slevel].w; a.H = WL.lv[1].h; a.W = WL.lv[1].w;
+      a.Cmid = kBlocks[b].cin; a.Cout = kBlocks[b].cout;
+      a.src = buf(src);
+      a.w3 = wplanes(PL.w3[b]);
+      a.w1 = b == 7 ? wplanes(PL.w1g7) : wplanes(PL.w1[b]);
+      a.bias3 = fvec(PL.v3[b][0]); a.scale3 = fvec(PL.v3[b][1]); a.shift3 = fvec(PL.v3[b][2]);
+      a.bias1 = fvec(PL.v1[b][0]); a.scale1 = fvec(PL.v1[b][1]); a.shift1 = fvec(PL.v1[b][2]);
+      a.residual = res ? buf(res) : none;
+      a.out = dst ? buf(dst) : none;
+      a.tail = dst ? 0 : 1;
+      a.w10 = fvec(PL.w10); a.b10 = fvec(PL.b10);
+      a.y = y; a.y_u8 = y_u8;
+      const double px = double(B) * a.H * a.W, spx = double(B) * a.Hs * a.Ws, ci = a.Cmid, co = a.Cout;
+      char nm[48];
+      snprintf(nm, sizeof(nm), "conv%d block (up+3x3+1x1%s)", b + 2, dst ? "+skip" : "+conv10+sigmoid");
+      ProfScope ps(nm, 2.0 * px * (9 * ci * ci + ci * co + (dst ? 0 : 64)),
+                   (spx * ci + (dst ? px * co * 2 : 0) + 9 * ci * ci + ci * co) * 2.0 * np + (dst ? 0 : px * 16), st);
+      return upblock_launch(a, st);
+    };
+    NSM_TRY(block(6, 2, "m7", "c2", "m8"));
+    NSM_TRY(block(7, 1, "m8", nullptr, nullptr));
+    return 0;
+  }
   NSM_TRY(up("m7", 2, 128, "u8", 1));
   NSM_TRY(double_conv(6, 1, buf("u8"), "t8", "m8", "c2", nullptr));   // conv8 + skip
   NSM_TRY(up("m8", 1, 64, "u9", 1));                                   // x2 up then back down to (h1, w1)
@@ -671,6 +713,33 @@ int nsm_conv_fwd(const nsm_conv_args* a, void* stream) {
                (px * (a->Cin + a->Cout) + double(s.taps) * a->Cin * a->Cout) * 2.0 * fmt_planes(a->mode),
                static_cast<cudaStream_t>(stream));
   return conv_gemm_launch(s, in, w, e, static_cast<cudaStream_t>(stream));
+}
+
+int nsm_unet_fused_decoder(void) { return fused_decoder(NSM_MODE_FP32) ? 1 : 0; }
+int nsm_unet_set_fused_decoder(int on) {
+  g_fused_override.store(on < 0 ? -1 : (on ? 1 : 0), std::memory_order_relaxed);
+  return 0;
+}
+
+int nsm_upblock(const nsm_upblock_args* a, void* stream) {
+  if (!a) {
+    set_error("nsm_upblock: null args");
+    return 1;
+  }
+  UpBlockArgs u;
+  memset(&u, 0, sizeof(u));
+  u.mode = a->mode; u.N = a->N; u.Hs = a->Hs; u.Ws = a->Ws; u.H = a->H; u.W = a->W; u.Cmid = a->Cmid; u.Cout = a->Cout;
+  u.src = mk(a->src[0], a->src[1]);
+  u.w3 = mk(a->weight3[0], a->weight3[1]);
+  u.w1 = mk(a->weight1[0], a->weight1[1]);
+  u.bias3 = a->bias3; u.scale3 = a->bn_scale3; u.shift3 = a->bn_shift3;
+  u.bias1 = a->bias1; u.scale1 = a->bn_scale1; u.shift1 = a->bn_shift1;
+  u.residual = mk(a->residual[0], a->residual[1]);
+  u.out = mk(a->out[0], a->out[1]);
+  u.tail = a->tail; u.w10 = a->w10; u.b10 = a->b10; u.y = a->y; u.y_u8 = a->y_u8;
+  ProfScope ps("upblock", 2.0 * double(a->N) * a->H * a->W * (9.0 * a->Cmid * a->Cmid + double(a->Cmid) * a->Cout), 0.0,
+               S(stream));
+  return upblock_launch(u, S(stream));
 }
 
 int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, void* const* dst, int hd, int wd,

@@ -93,7 +93,8 @@ int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const CUtensorMapSwizzle sw = swizzle_bytes == 32   ? CU_TENSOR_MAP_SWIZZLE_32B
+  const CUtensorMapSwizzle sw = swizzle_bytes == 0    ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                       : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = fn(map, dt, rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,

@@ -9,7 +9,7 @@ struct Lerp {
   int i0, i1;
   float w0, w1;
 };
-__device__ __forceinline__ Lerp make_lerp(int dst, int in_size, int out_size) {
+__host__ __device__ __forceinline__ Lerp make_lerp(int dst, int in_size, int out_size) {
   const float scale = out_size > 1 ? float(in_size - 1) / float(out_size - 1) : 0.f;
   const float src = scale * float(dst);
   int i0 = int(src);
@@ -31,7 +31,7 @@ struct Tap3 {
   int rmin;
   float w[3];
 };
-__device__ __forceinline__ Tap3 composite_taps(int dst, int in_size, int out_size) {
+__host__ __device__ __forceinline__ Tap3 composite_taps(int dst, int in_size, int out_size) {
   const int mid = 2 * in_size;
   const Lerp m = make_lerp(dst, mid, out_size);
   const Lerp a = make_lerp(m.i0, in_size, mid), b = make_lerp(m.i1, in_size, mid);

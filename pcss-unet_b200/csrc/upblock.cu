@@ -1,0 +1,696 @@
+// Fused decoder block of the eval-mode U-Net (Unetmodel.py:134-148): ONE kernel per thin DoubleConv of the decoder,
+//
+//   conv8:  up8 = resize(up2x(merge7)) -> 3x3 (128->128) + BN + LReLU -> 1x1 (128->64) + BN + LReLU -> + c2      = merge8
+//   conv9:  up9 = resize(up2x(merge8)) -> 3x3 (64->64)   + BN + LReLU -> 1x1 (64->16)  + BN + LReLU
+//           -> conv10 (16->4) + bias -> sigmoid -> pixel_shuffle(2)                                               = output
+//
+// instead of six launches (two up-samplers, two 3x3 GEMMs, a 1x1 GEMM, the tail) that wrote and re-read the up-sampled
+// tensors u8 / u9 and the intermediates t8 / t9 (1.2 GB of HBM traffic per 1080p frame in fp32 mode).
+//
+// Work item = 16 x 8 output pixels (M = 128 TMEM lanes, lane = row * 8 + column).  Per item and 64-channel chunk:
+//   * warp 2 fetches the low-resolution source box the tile's (16+2) x (8+2) halo depends on with ONE TMA box load;
+//   * the 16 worker warps interpolate the halo (composite of the x2 bilinear up-sample and the resize to the skip's size:
+//     a separable, position-dependent stencil of up to 3 x 3 source pixels, resample.cuh) and write it to shared memory
+//     directly in the K-major 128-byte-swizzled UMMA operand layout, pixel rows in halo order;
+//   * the nine taps of the 3x3 convolution are nine UMMA descriptors into that ONE halo tile (start shifted by
+//     (dy * 10 + dx) pixel rows, 8-row groups at a stride of one halo row = 1280 B; the swizzle follows absolute
+//     shared-memory address bits, so a descriptor may start at any 128-byte row) -- no im2col, no per-tap re-load;
+//   * weights stream through a TMA ring; accumulators live in TMEM;
+//   * the workers turn the 3x3 accumulator into the 1x1 convolution's A operand (bias, BN, LeakyReLU, hi/lo split) and
+//     store it back to TENSOR MEMORY (tcgen05.st); the 1x1 GEMM reads A from TMEM (.ts form), B from the ring;
+//   * final epilogue: bias, BN, LeakyReLU, then the skip add and the store (conv8), or conv10 + sigmoid + pixel_shuffle
+//     in registers (conv9).
+// fp32 mode: source planes fp16 hi+lo; 3x3 operands fp16 hi + 8-bit cross plane (two MMA slots per k-step, nsm_common.cuh);
+// 1x1 operands fp16 hi+lo (a_hi x [w_hi | w_lo] as one wide MMA + a_lo x w_hi).  bf16 mode: one plane, autocast rounding
+// points (the composite resize is rounded once, like upsample_match).
+#include <stdio.h>
+#include <string.h>
+
+#include "conv_gemm.cuh"
+#include "nsm_common.cuh"
+#include "resample.cuh"
+#include "upblock.cuh"
+
+namespace nsm {
+
+namespace {
+
+constexpr int kUbTW = 8, kUbTH = 16;                  // output tile
+constexpr int kHaloW = kUbTW + 2, kHaloH = kUbTH + 2;  // 10 x 18 halo pixels
+constexpr int kHaloRows = kHaloW * kHaloH;             // 180 rows of 128 B
+constexpr int kHaloPlaneBytes = kHaloRows * 128;       // 23040
+constexpr int kUbThreads = 640;                        // warps 0-3: B producer, MMA, source producer, idle; 4-19: workers
+constexpr int kWorkers = 16;
+constexpr int kWorkerThreads = kWorkers * 32;
+
+struct UbKernelParams {
+  int N, Hs, Ws, H, W;
+  int Cout, tail;
+  int tiles_x, tiles_y, total_tiles;
+  int sbw, sbh;                       // source box in pixels
+  uint32_t off_src, off_b, off_vec, off_taps, off_bar;
+  uint32_t src_plane_bytes, b_stage_bytes, b_stages;
+  uint32_t tm_acc2, tm_a2, tmem_cols;  // TMEM column offsets
+  uint32_t idesc1, idesc2w, idesc2c;
+  const float *bias3, *scale3, *shift3, *bias1, *scale1, *shift1, *w10, *b10;
+  Planes out, residual;
+  float* y;
+  uint8_t* y_u8;
+};
+
+struct TileCoord {
+  int n, y0, x0;
+};
+__device__ __forceinline__ TileCoord ub_tile(const UbKernelParams& p, int item) {
+  TileCoord t;
+  const int tx = item % p.tiles_x;
+  int r = item / p.tiles_x;
+  const int ty = r % p.tiles_y;
+  t.n = r / p.tiles_y;
+  t.y0 = ty * kUbTH;
+  t.x0 = tx * kUbTW;
+  return t;
+}
+// first source row / column the tile's halo touches (= origin of the TMA source box)
+__device__ __forceinline__ void ub_src_origin(const UbKernelParams& p, const TileCoord& t, int& sy0, int& sx0) {
+  sy0 = composite_taps(t.y0 > 0 ? t.y0 - 1 : 0, p.Hs, p.H).rmin;
+  sx0 = composite_taps(t.x0 > 0 ? t.x0 - 1 : 0, p.Ws, p.W).rmin;
+}
+
+// 8 consecutive channels of one source pixel from the staged box (hi [+ lo] planes) as fp32
+template <int NP>
+__device__ __forceinline__ void ub_load8(uint32_t saddr, uint32_t plane_bytes, float (&v)[8]) {
+  const uint4 h = lds16(saddr);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+  constexpr int FMT = NP == 2 ? kFmtF16x2 : kFmtBf16;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = hi_lo_to_f32(hw[e], FMT);
+    v[2 * e + 1] = hi_hi_to_f32(hw[e], FMT);
+  }
+  if (NP == 2) {
+    const uint4 l = lds16(saddr + plane_bytes);
+    const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] += lo_lo_to_f32(lw[e], FMT);
+      v[2 * e + 1] += lo_hi_to_f32(lw[e], FMT);
+    }
+  }
+}
+
+template <int NP, int CMID>
+__global__ void __launch_bounds__(kUbThreads, 1)
+upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1,
+               const __grid_constant__ CUtensorMap tmW3a, const __grid_constant__ CUtensorMap tmW3b,
+               const __grid_constant__ CUtensorMap tmW1a, const __grid_constant__ CUtensorMap tmW1b,
+               const __grid_constant__ UbKernelParams p) {
+  constexpr int NCH = CMID / 64;                 // 64-channel chunks of the 3x3 convolution's K (per tap)
+  constexpr int FMT = NP == 2 ? kFmtF16x2 : kFmtBf16;
+  constexpr bool rb = NP == 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t sbase = smem_u32(smem);
+  // halo ring at offset 0: buffer b, plane pl at (b * NP + pl) * kHaloPlaneBytes
+  float* vec = reinterpret_cast<float*>(smem + p.off_vec);
+  Tap3* taps = reinterpret_cast<Tap3*>(smem + p.off_taps);   // [2][kHaloH + kHaloW]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* b_full = bars;                 // [b_stages]
+  uint64_t* b_empty = bars + 8;            // [b_stages]
+  uint64_t* halo_full = bars + 16;         // [2]
+  uint64_t* halo_empty = bars + 18;        // [2]
+  uint64_t* src_full = bars + 20;
+  uint64_t* src_empty = bars + 21;
+  uint64_t* acc1_full = bars + 22;
+  uint64_t* acc1_empty = bars + 23;
+  uint64_t* a2_full = bars + 24;
+  uint64_t* acc2_full = bars + 25;
+  uint64_t* acc2_empty = bars + 26;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = (p.total_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // tiles of this CTA
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmS0); tma_prefetch_desc(&tmW3a); tma_prefetch_desc(&tmW1a);
+    if (NP == 2) { tma_prefetch_desc(&tmS1); tma_prefetch_desc(&tmW3b); tma_prefetch_desc(&tmW1b); }
+    for (uint32_t s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&halo_full[b], kWorkers);
+      mbar_init(&halo_empty[b], 1);
+    }
+    mbar_init(src_full, 1);
+    mbar_init(src_empty, kWorkers);
+    mbar_init(acc1_full, 1);
+    mbar_init(acc1_empty, kWorkers);
+    mbar_init(a2_full, kWorkers);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, kWorkers);
+    fence_barrier_init();
+  }
+  // per-channel vectors -> shared memory: [bias3 | scale3 | shift3](CMID) [bias1 | scale1 | shift1](Cout) [w10 64] [b10 4]
+  for (int i = threadIdx.x; i < CMID; i += kUbThreads) {
+    vec[i] = p.bias3[i]; vec[CMID + i] = p.scale3[i]; vec[2 * CMID + i] = p.shift3[i];
+  }
+  for (int i = threadIdx.x; i < p.Cout; i += kUbThreads) {
+    vec[3 * CMID + i] = p.bias1[i]; vec[3 * CMID + p.Cout + i] = p.scale1[i]; vec[3 * CMID + 2 * p.Cout + i] = p.shift1[i];
+  }
+  if (p.tail && threadIdx.x < 68)
+    vec[3 * CMID + 3 * p.Cout + threadIdx.x] = threadIdx.x < 64 ? p.w10[threadIdx.x] : p.b10[threadIdx.x - 64];
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_acc1 = tmem_base, tm_acc2 = tmem_base + p.tm_acc2, tm_a2 = tmem_base + p.tm_a2;
+
+  if (warp == 0) {
+    // ===================== weight producer: 3x3 tiles (chunk, tap), then the 1x1 tiles (chunk) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      auto advance = [&]() {
+        if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+      };
+      for (int j = 0; j < nt; ++j) {
+        for (int c = 0; c < NCH; ++c)
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
+            mbar_expect_tx(&b_full[stage], NP * CMID * 128);
+            tma_load_2d(sb, &tmW3a, &b_full[stage], tap * CMID + c * 64, 0);
+            if (NP == 2) tma_load_2d(sb + CMID * 128, &tmW3b, &b_full[stage], tap * CMID + c * 64, 0);
+            advance();
+          }
+        for (int c = 0; c < NCH; ++c) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
+          mbar_expect_tx(&b_full[stage], NP * p.Cout * 128);
+          tma_load_2d(sb, &tmW1a, &b_full[stage], c * 64, 0);
+          if (NP == 2) tma_load_2d(sb + p.Cout * 128, &tmW1b, &b_full[stage], c * 64, 0);   // lo rows right after hi rows
+          advance();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== source producer: one box per (tile, chunk) =====================
+    if (lane == 0) {
+      for (int j = 0, q = 0; j < nt; ++j) {
+        const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
+        int sy0, sx0;
+        ub_src_origin(p, t, sy0, sx0);
+        for (int c = 0; c < NCH; ++c, ++q) {
+          mbar_wait(src_empty, (q & 1) ^ 1);
+          mbar_expect_tx(src_full, NP * p.sbw * p.sbh * 128);
+          tma_load_4d(smem + p.off_src, &tmS0, src_full, c * 64, sx0, sy0, t.n);
+          if (NP == 2) tma_load_4d(smem + p.off_src + p.src_plane_bytes, &tmS1, src_full, c * 64, sx0, sy0, t.n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      auto advance = [&]() {
+        if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+      };
+      for (int j = 0; j < nt; ++j) {
+        // ---- GEMM 1: 3x3 convolution out of the halo tiles ----
+        mbar_wait(acc1_empty, (j & 1) ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < NCH; ++c) {
+          const int q = j * NCH + c, hb = q & 1;
+          mbar_wait(&halo_full[hb], (q >> 1) & 1);
+          tc_fence_after();
+          const uint32_t halo = sbase + uint32_t(hb * NP) * kHaloPlaneBytes;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a0 = halo + uint32_t((tap / 3) * kHaloW + tap % 3) * 128u;
+            const uint32_t b0 = sbase + p.off_b + stage * p.b_stage_bytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t accum = (c | tap | k) != 0 ? 1u : 0u;
+              umma_bf16(tm_acc1, make_desc_sw128(a0 + k * 32, 16, kHaloW * 128),
+                        make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc1, accum);
+              if (NP == 2)   // both cross terms as one e4m3 MMA of K = 32 (8-bit cross planes)
+                umma_f8(tm_acc1 + CMID, make_desc_sw128(a0 + kHaloPlaneBytes + k * 32, 16, kHaloW * 128),
+                        make_desc_sw128(b0 + CMID * 128 + k * 32, 16, 1024), p.idesc1, accum);
+            }
+            umma_commit(&b_empty[stage]);
+            advance();
+          }
+          umma_commit(&halo_empty[hb]);
+        }
+        umma_commit(acc1_full);
+        // ---- GEMM 2: 1x1 convolution, A from tensor memory ----
+        mbar_wait(a2_full, j & 1);
+        mbar_wait(acc2_empty, (j & 1) ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < NCH; ++c) {
+          mbar_wait(&b_full[stage], phase);
+          tc_fence_after();
+          const uint32_t b0 = sbase + p.off_b + stage * p.b_stage_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accum = (c | k) != 0 ? 1u : 0u;
+            const uint32_t a_hi = tm_a2 + uint32_t(c * 4 + k) * 8u;
+            if (NP == 2) {
+              umma_bf16_ts(tm_acc2, a_hi, make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc2w, accum);
+              umma_bf16_ts(tm_acc2 + p.Cout, a_hi + CMID / 2, make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc2c, 1u);
+            } else {
+              umma_bf16_ts(tm_acc2, a_hi, make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc2c, accum);
+            }
+          }
+          umma_commit(&b_empty[stage]);
+          advance();
+        }
+        umma_commit(acc2_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== workers: halo interpolation, both epilogues =====================
+    const int w = warp - 4;
+    const int qd = w & 3;              // TMEM lane quarter (= warp id % 4)
+    const int cs = w >> 2;             // column slice
+    const int wt = threadIdx.x - 128;  // 0 .. 511
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    const int ly = qd * 4 + (lane >> 3), lx = lane & 7;   // this lane's pixel inside the tile
+
+    // ---- one (tile, chunk) job: interpolate the halo of 64 channels into halo buffer q & 1 ----
+    auto do_job = [&](int q) {
+      const int j = q / NCH, c = q - j * NCH;
+      (void)c;
+      const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
+      Tap3* tb = taps + (q & 1) * (kHaloH + kHaloW);
+      if (wt < kHaloH) {
+        const int gy = t.y0 - 1 + wt;
+        if (gy >= 0 && gy < p.H) tb[wt] = composite_taps(gy, p.Hs, p.H);
+      } else if (wt < kHaloH + kHaloW) {
+        const int gx = t.x0 - 1 + (wt - kHaloH);
+        if (gx >= 0 && gx < p.W) tb[wt] = composite_taps(gx, p.Ws, p.W);
+      }
+      int sy0, sx0;
+      ub_src_origin(p, t, sy0, sx0);
+      named_bar_sync(1, kWorkerThreads);
+      const int hb = q & 1;
+      mbar_wait(&halo_empty[hb], ((q >> 1) & 1) ^ 1);   // the MMAs of the buffer's previous use have read it
+      mbar_wait(src_full, q & 1);
+      const int cg = wt & 7, slot = wt >> 3;
+      if (slot < 60) {
+        const int hx = slot % kHaloW, strip = slot / kHaloW;
+        const int gx = t.x0 - 1 + hx;
+        const bool colok = gx >= 0 && gx < p.W;
+        Tap3 tx;
+        tx.rmin = 0; tx.w[0] = tx.w[1] = tx.w[2] = 0.f;
+        if (colok) tx = tb[kHaloH + hx];
+        const uint32_t src0 = sbase + p.off_src + uint32_t(cg) * 16u;
+        // horizontally interpolated source row r (8 channels)
+        auto hrow = [&](int r, float (&h)[8]) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = 0.f;
+          if (r > p.Hs - 1 || r - sy0 >= p.sbh) return;   // only reached with zero vertical weight (outside the box)
+#pragma unroll
+          for (int jx = 0; jx < 3; ++jx) {
+            if (tx.w[jx] == 0.f) continue;
+            float v[8];
+            ub_load8<NP>(src0 + uint32_t((r - sy0) * p.sbw + (tx.rmin + jx - sx0)) * 128u, p.src_plane_bytes, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h[e] = fmaf(tx.w[jx], v[e], h[e]);
+          }
+        };
+        float h0[8], h1[8], h2[8];
+        int base = -1000000;
+        const uint32_t halo = sbase + uint32_t(hb * NP) * kHaloPlaneBytes;
+#pragma unroll 1
+        for (int rr = 0; rr < 3; ++rr) {
+          const int hy = strip * 3 + rr;
+          const int gy = t.y0 - 1 + hy;
+          const uint32_t row = halo + uint32_t(hy * kHaloW + hx) * 128u;
+          const uint32_t sw = (row >> 7) & 7u;
+          if (!colok || gy < 0 || gy >= p.H) {   // the convolution's zero padding (and rows below a ragged tile)
+            sts16(row + ((uint32_t(cg) ^ sw) << 4), make_uint4(0, 0, 0, 0));
+            if (NP == 2) {
+              const uint32_t row2 = row + kHaloPlaneBytes;
+              sts16(row2 + ((uint32_t(cg) ^ ((row2 >> 7) & 7u)) << 4), make_uint4(0, 0, 0, 0));
+            }
+            continue;
+          }
+          const Tap3 ty = tb[hy];
+          if (ty.rmin - base > 2 || ty.rmin < base) {   // (re)start the three-row window
+            base = ty.rmin;
+            hrow(base, h0); hrow(base + 1, h1); hrow(base + 2, h2);
+          } else {
+            while (base < ty.rmin) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { h0[e] = h1[e]; h1[e] = h2[e]; }
+              hrow(base + 3, h2);
+              ++base;
+            }
+          }
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float a = fmaf(ty.w[0], h0[e], 0.f);
+            a = fmaf(ty.w[1], h1[e], a);
+            v[e] = fmaf(ty.w[2], h2[e], a);
+            if (rb) v[e] = rbf(v[e]);
+          }
+          uint32_t hw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hw[e] = pack_hi(v[2 * e], v[2 * e + 1], FMT);
+          sts16(row + ((uint32_t(cg) ^ sw) << 4), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          if (NP == 2) {
+            // 8-bit cross plane: per 16 channels [16 B of e4m3(2 v) | 16 B of e4m3(2^11 (v - hi))]
+            uint2 first, second;
+            x8_act_bytes(v, hw, first, second);
+            const uint32_t row2 = row + kHaloPlaneBytes;
+            const uint32_t sw2 = (row2 >> 7) & 7u;
+            const uint32_t ch = uint32_t(cg >> 1) * 2u, sub = uint32_t(cg & 1) * 8u;
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row2 + ((ch ^ sw2) << 4) + sub), "r"(first.x), "r"(first.y)
+                         : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row2 + (((ch + 1u) ^ sw2) << 4) + sub), "r"(second.x),
+                         "r"(second.y)
+                         : "memory");
+          }
+        }
+      }
+      fence_proxy_async();   // generic-proxy writes of the halo -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&halo_full[hb]);
+        mbar_arrive(src_empty);
+      }
+    };
+
+    // ---- 3x3 accumulator -> A operand of the 1x1 GEMM in tensor memory ----
+    auto mid_epilogue = [&](int j) {
+      mbar_wait(acc1_full, j & 1);
+      tc_fence_after();
+      constexpr int CW = CMID / 4;   // columns per warp
+#pragma unroll
+      for (int g = 0; g < CW / 16; ++g) {
+        const int col = cs * CW + g * 16;
+        uint32_t r0[16], r1[16];
+        tmem_ld_32x16(tm_acc1 + lane_base + col, r0);
+        if (NP == 2) tmem_ld_32x16(tm_acc1 + lane_base + CMID + col, r1);
+        tmem_ld_wait();
+        uint32_t hw[8], lw[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float a[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int ch = col + 2 * e + k;
+            float v = __uint_as_float(r0[2 * e + k]);
+            if (NP == 2) v = fmaf(__uint_as_float(r1[2 * e + k]), kX8CrossScale, v);
+            v += vec[ch];
+            if (rb) v = rbf(v);
+            v = fmaf(v, vec[CMID + ch], vec[2 * CMID + ch]);
+            if (rb) v = rbf(v);
+            v = lrelu02(v);
+            if (rb) v = rbf(v);
+            a[k] = v;
+          }
+          hw[e] = pack_hi(a[0], a[1], FMT);
+          if (NP == 2) lw[e] = pack_lo_resid(a[0], a[1], hw[e], FMT);
+        }
+        tmem_st_32x8(tm_a2 + lane_base + col / 2, hw);
+        if (NP == 2) tmem_st_32x8(tm_a2 + lane_base + CMID / 2 + col / 2, lw);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc1_empty);   // the 3x3 accumulator may be overwritten by the next tile
+        mbar_arrive(a2_full);      // the 1x1 GEMM's A operand is in place
+      }
+    };
+
+    // ---- 1x1 accumulator -> output ----
+    auto final_epilogue = [&](int j) {
+      mbar_wait(acc2_full, j & 1);
+      tc_fence_after();
+      if (cs * 16 < p.Cout) {
+        const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
+        const int col = cs * 16;
+        uint32_t r0[16], r1[16];
+        tmem_ld_32x16(tm_acc2 + lane_base + col, r0);
+        if (NP == 2) tmem_ld_32x16(tm_acc2 + lane_base + p.Cout + col, r1);
+        tmem_ld_wait();
+        const float* v1 = vec + 3 * CMID;
+        float a[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float v = __uint_as_float(r0[e]);
+          if (NP == 2) v += __uint_as_float(r1[e]);
+          v += v1[col + e];
+          if (rb) v = rbf(v);
+          v = fmaf(v, v1[p.Cout + col + e], v1[2 * p.Cout + col + e]);
+          if (rb) v = rbf(v);
+          v = lrelu02(v);
+          if (rb) v = rbf(v);
+          a[e] = v;
+        }
+        const int y = t.y0 + ly, x = t.x0 + lx;
+        if (y < p.H && x < p.W) {
+          if (p.tail) {
+            // conv10 (16 -> 4) + bias, sigmoid, pixel_shuffle(2): channel k = dy * 2 + dx -> pixel (2y + dy, 2x + dx)
+            const float* w10 = v1 + 3 * p.Cout;
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float s = 0.f;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) s = fmaf(w10[k * 16 + e], a[e], s);
+              s += w10[64 + k];
+              if (rb) s = rbf(s);
+              s = 1.f / (1.f + expf(-s));
+              o[k] = rb ? rbf(s) : s;
+            }
+            const int Wo = 2 * p.W, Ho = 2 * p.H;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const size_t oo = ((size_t)t.n * Ho + 2 * y + dy) * Wo + 2 * x;
+              if (p.y) *reinterpret_cast<float2*>(p.y + oo) = make_float2(o[2 * dy], o[2 * dy + 1]);
+              if (p.y_u8)   // (out * 255).astype(uint8): truncation toward zero of a value in [0, 255]
+                *reinterpret_cast<uchar2*>(p.y_u8 + oo) =
+                    make_uchar2((unsigned char)(o[2 * dy] * 255.f), (unsigned char)(o[2 * dy + 1] * 255.f));
+            }
+          } else {
+            const size_t off = (((size_t)t.n * p.H + y) * p.W + x) * p.Cout + col;   // element offset
+            if (p.residual.p[0]) {
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const uint4 h = ldg16(reinterpret_cast<const uint8_t*>(p.residual.p[0]) + (off + 8 * hf) * 2);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  a[8 * hf + 2 * e] += hi_lo_to_f32(hw[e], FMT);
+                  a[8 * hf + 2 * e + 1] += hi_hi_to_f32(hw[e], FMT);
+                }
+                if (NP == 2) {
+                  const uint4 l = ldg16(reinterpret_cast<const uint8_t*>(p.residual.p[1]) + (off + 8 * hf) * 2);
+                  const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    a[8 * hf + 2 * e] += lo_lo_to_f32(lw[e], FMT);
+                    a[8 * hf + 2 * e + 1] += lo_hi_to_f32(lw[e], FMT);
+                  }
+                }
+              }
+              if (rb) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) a[e] = rbf(a[e]);
+              }
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hw[e] = pack_hi(a[8 * hf + 2 * e], a[8 * hf + 2 * e + 1], FMT);
+                if (NP == 2) lw[e] = pack_lo_resid(a[8 * hf + 2 * e], a[8 * hf + 2 * e + 1], hw[e], FMT);
+              }
+              stg16(reinterpret_cast<uint8_t*>(p.out.p[0]) + (off + 8 * hf) * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+              if (NP == 2)
+                stg16(reinterpret_cast<uint8_t*>(p.out.p[1]) + (off + 8 * hf) * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty);
+    };
+
+    int q_next = 0;
+    for (; q_next < NCH && q_next < nt * NCH; ++q_next) do_job(q_next);
+    for (int j = 0; j < nt; ++j) {
+      if (j + 1 < nt) do_job(q_next++);        // first chunk of the next tile: overlaps this tile's 3x3 MMAs
+      mid_epilogue(j);
+      final_epilogue(j);
+      if (j + 1 < nt)
+        for (int c = 1; c < NCH; ++c) do_job(q_next++);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int g_ub_sms = 0;
+
+// extent of the source box a tile's halo can touch along one axis (brute force over all tiles; same float arithmetic as
+// the device's composite_taps, taps with zero weight do not count)
+int src_box_extent(int in_size, int out_size, int tile, int halo) {
+  int best = 1;
+  for (int t0 = 0; t0 < out_size; t0 += tile) {
+    const int first = t0 > 0 ? t0 - 1 : 0;
+    const int last = t0 + halo - 2 < out_size ? t0 + halo - 2 : out_size - 1;   // t0 - 1 + halo - 1
+    const int lo = composite_taps(first, in_size, out_size).rmin;
+    int hi = lo;
+    for (int d = first; d <= last; ++d) {
+      const Tap3 tp = composite_taps(d, in_size, out_size);
+      for (int k = 0; k < 3; ++k)
+        if (tp.w[k] != 0.f && tp.rmin + k > hi) hi = tp.rmin + k;
+    }
+    if (hi - lo + 1 > best) best = hi - lo + 1;
+  }
+  return best;
+}
+
+template <int NP, int CMID>
+int launch_ub(const CUtensorMap* maps, const UbKernelParams& kp, int grid, size_t smem_bytes, cudaStream_t st) {
+  auto kern = upblock_kernel<NP, CMID>;
+  static size_t attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
+    if (e != cudaSuccess) {
+      set_error("upblock<%d,%d>: cudaFuncSetAttribute(%zu B): %s", NP, CMID, smem_bytes, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_bytes = smem_bytes;
+  }
+  kern<<<grid, kUbThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], kp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("upblock<%d,%d> launch failed: %s", NP, CMID, cudaGetErrorString(e));
+    return 1;
+  }
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+int upblock_launch(const UpBlockArgs& a, cudaStream_t st) {
+  const int NP = a.mode == kFmtBf16 ? 1 : 2;
+  if ((a.mode != kFmtBf16 && a.mode != kFmtF16x2) || (a.Cmid != 64 && a.Cmid != 128) ||
+      (a.Cout != 16 && a.Cout != 64) || a.N < 1 || a.H < 1 || a.W < 1 || a.Hs < 1 || a.Ws < 1 || a.H < a.Hs ||
+      a.W < a.Ws || (a.tail && a.Cout != 16) || (!a.tail && !a.out.p[0])) {
+    set_error("upblock: unsupported configuration mode=%d Cmid=%d Cout=%d src %dx%d dst %dx%d tail=%d", a.mode, a.Cmid,
+              a.Cout, a.Hs, a.Ws, a.H, a.W, a.tail);
+    return 1;
+  }
+  if (g_ub_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_ub_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_ub_sms <= 0) g_ub_sms = 148;
+  }
+  UbKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.N = a.N; kp.Hs = a.Hs; kp.Ws = a.Ws; kp.H = a.H; kp.W = a.W; kp.Cout = a.Cout; kp.tail = a.tail;
+  kp.tiles_x = (a.W + kUbTW - 1) / kUbTW;
+  kp.tiles_y = (a.H + kUbTH - 1) / kUbTH;
+  kp.total_tiles = a.N * kp.tiles_x * kp.tiles_y;
+  kp.sbh = src_box_extent(a.Hs, a.H, kUbTH, kHaloH);
+  kp.sbw = src_box_extent(a.Ws, a.W, kUbTW, kHaloW);
+  if (kp.sbh > 256 || kp.sbw > 256) {
+    set_error("upblock: source box %dx%d too large", kp.sbh, kp.sbw);
+    return 1;
+  }
+  // shared-memory layout (offsets from the 1024-byte aligned base)
+  auto up = [](size_t v, size_t al) { return (v + al - 1) / al * al; };
+  size_t off = size_t(2) * NP * kHaloPlaneBytes;
+  kp.off_src = uint32_t(off = up(off, 128));
+  kp.src_plane_bytes = uint32_t(up(size_t(kp.sbw) * kp.sbh * 128, 128));
+  off += size_t(NP) * kp.src_plane_bytes;
+  const size_t fixed_tail = up(size_t(3 * a.Cmid + 3 * a.Cout + 68) * 4, 16) + 2 * (kHaloH + kHaloW) * sizeof(Tap3) + 256;
+  kp.off_b = uint32_t(off = up(off, 1024));
+  kp.b_stage_bytes = uint32_t(NP * a.Cmid * 128);
+  const size_t budget = size_t(227) * 1024 - 1024;
+  if (off + fixed_tail + 2 * kp.b_stage_bytes > budget) {
+    set_error("upblock: shared-memory budget exceeded (source box %dx%d)", kp.sbh, kp.sbw);
+    return 1;
+  }
+  size_t stages = (budget - off - fixed_tail) / kp.b_stage_bytes;
+  if (stages > 8) stages = 8;
+  kp.b_stages = uint32_t(stages);
+  off += stages * kp.b_stage_bytes;
+  kp.off_vec = uint32_t(off = up(off, 16));
+  off += up(size_t(3 * a.Cmid + 3 * a.Cout + 68) * 4, 16);
+  kp.off_taps = uint32_t(off);
+  off += 2 * (kHaloH + kHaloW) * sizeof(Tap3);
+  kp.off_bar = uint32_t(off = up(off, 8));
+  off += 256;
+  const size_t smem_bytes = off + 1024;
+  // tensor memory: [3x3 main | 3x3 cross] [1x1 main | 1x1 cross] [A2 hi | A2 lo]
+  kp.tm_acc2 = uint32_t(NP * a.Cmid);
+  kp.tm_a2 = kp.tm_acc2 + uint32_t(NP * a.Cout);
+  const uint32_t need = kp.tm_a2 + uint32_t(NP * a.Cmid / 2);
+  kp.tmem_cols = need <= 128 ? 128 : (need <= 256 ? 256 : 512);
+  if (need > 512) {
+    set_error("upblock: %u tensor-memory columns needed", need);
+    return 1;
+  }
+  const uint32_t ef = NP == 2 ? kFmtF16 : kFmtBF16;   // fp16 / e4m3 share descriptor code 0
+  kp.idesc1 = make_idesc_f16(128, a.Cmid, ef, ef, 0, 0);
+  kp.idesc2c = make_idesc_f16(128, a.Cout, ef, ef, 0, 0);
+  kp.idesc2w = make_idesc_f16(128, 2 * a.Cout, ef, ef, 0, 0);
+  kp.bias3 = a.bias3; kp.scale3 = a.scale3; kp.shift3 = a.shift3;
+  kp.bias1 = a.bias1; kp.scale1 = a.scale1; kp.shift1 = a.shift1;
+  kp.w10 = a.w10; kp.b10 = a.b10;
+  kp.out = a.out; kp.residual = a.residual; kp.y = a.y; kp.y_u8 = a.y_u8;
+  if (a.tail && (!a.w10 || !a.b10 || (!a.y && !a.y_u8))) {
+    set_error("upblock: the tail needs conv10's weights and an output");
+    return 1;
+  }
+  CUtensorMap maps[6];
+  memset(maps, 0, sizeof(maps));
+  const uint64_t sdims[4] = {uint64_t(a.Cmid), uint64_t(a.Ws), uint64_t(a.Hs), uint64_t(a.N)};
+  const uint64_t sstr[3] = {uint64_t(a.Cmid) * 2, uint64_t(a.Ws) * a.Cmid * 2, uint64_t(a.Hs) * a.Ws * a.Cmid * 2};
+  const uint32_t sbox[4] = {64, uint32_t(kp.sbw), uint32_t(kp.sbh), 1};
+  const uint64_t K3 = uint64_t(9) * a.Cmid;
+  const uint64_t w3dims[2] = {K3, uint64_t(a.Cmid)};
+  const uint64_t w3str[1] = {K3 * 2};
+  const uint32_t w3box[2] = {64, uint32_t(a.Cmid)};
+  const uint64_t w1dims[2] = {uint64_t(a.Cmid), uint64_t(a.Cout)};
+  const uint64_t w1str[1] = {uint64_t(a.Cmid) * 2};
+  const uint32_t w1box[2] = {64, uint32_t(a.Cout)};
+  for (int pl = 0; pl < NP; ++pl) {
+    if (!a.src.p[pl] || !a.w3.p[pl] || !a.w1.p[pl]) {
+      set_error("upblock: null operand plane %d", pl);
+      return 1;
+    }
+    if (encode_tmap_tiled(&maps[pl], a.src.p[pl], 4, sdims, sstr, sbox, 2, 0)) return 1;
+    if (encode_tmap_tiled(&maps[2 + pl], a.w3.p[pl], 2, w3dims, w3str, w3box, 2, 128)) return 1;
+    if (encode_tmap_tiled(&maps[4 + pl], a.w1.p[pl], 2, w1dims, w1str, w1box, 2, 128)) return 1;
+  }
+  if (NP == 1) { maps[1] = maps[0]; maps[3] = maps[2]; maps[5] = maps[4]; }
+  const int grid = kp.total_tiles < g_ub_sms ? kp.total_tiles : g_ub_sms;
+  if (NP == 2) {
+    return a.Cmid == 128 ? launch_ub<2, 128>(maps, kp, grid, smem_bytes, st) : launch_ub<2, 64>(maps, kp, grid, smem_bytes, st);
+  }
+  return a.Cmid == 128 ? launch_ub<1, 128>(maps, kp, grid, smem_bytes, st) : launch_ub<1, 64>(maps, kp, grid, smem_bytes, st);
+}
+
+}  // namespace nsm

@@ -46,6 +46,20 @@ class ConvArgs(Structure):
     ]
 
 
+class UpBlockArgs(Structure):
+    _fields_ = [
+        ("mode", c_int), ("N", c_int), ("Hs", c_int), ("Ws", c_int), ("H", c_int), ("W", c_int), ("Cmid", c_int),
+        ("Cout", c_int),
+        ("src", c_void_p * 2), ("weight3", c_void_p * 2), ("weight1", c_void_p * 2),
+        ("bias3", c_void_p), ("bn_scale3", c_void_p), ("bn_shift3", c_void_p),
+        ("bias1", c_void_p), ("bn_scale1", c_void_p), ("bn_shift1", c_void_p),
+        ("residual", c_void_p * 2), ("out", c_void_p * 2),
+        ("tail", c_int),
+        ("w10", c_void_p), ("b10", c_void_p),
+        ("y", c_void_p), ("y_u8", c_void_p),
+    ]
+
+
 def _declare(lib):
     lib.nsm_last_error.restype = c_char_p
     lib.nsm_version.restype = c_int
@@ -68,6 +82,9 @@ def _declare(lib):
     lib.nsm_planes_to_nchw.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.nsm_pack_conv_weight.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.nsm_conv_fwd.argtypes = [POINTER(ConvArgs), c_void_p]
+    lib.nsm_upblock.argtypes = [POINTER(UpBlockArgs), c_void_p]
+    lib.nsm_unet_fused_decoder.restype = c_int
+    lib.nsm_unet_set_fused_decoder.argtypes = [c_int]
     lib.nsm_upsample_match.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int, POINTER(c_void_p), c_int,
                                        c_int, c_int, c_void_p]
     lib.nsm_l1_loss_fwd_bwd.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_longlong, c_float, c_float,
@@ -151,7 +168,7 @@ EXPORTS = TRAIN_EXPORTS + [
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
     "nsm_channel_sums", "nsm_standardize", "nsm_perturb", "nsm_profile_enable", "nsm_profile_read",
-    "nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1",
+    "nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1", "nsm_upblock", "nsm_unet_fused_decoder", "nsm_unet_set_fused_decoder",
 ] + PX4_EXPORTS
 
 
@@ -398,6 +415,36 @@ def conv_fwd(x: PlaneTensor, wp, ksize, Cout, mode, bias=None, bn_scale=None, bn
     a.stats = ptr(stats) or None
     check(lib().nsm_conv_fwd(byref(a), stream_ptr()), "nsm_conv_fwd")
     return out, pl, raw
+
+
+def upblock(src: PlaneTensor, H, W, w3p, w1p, Cout, v3, v1, residual: PlaneTensor = None, tail=None, want_u8=False):
+    """Fused decoder block (nsm_upblock): composite up-sample of `src` to (H, W) on the operand path -> 3x3 + BN + LReLU
+    -> 1x1 + BN + LReLU -> + residual, or (tail = (w10 [4,16], b10 [4])) conv10 + sigmoid + pixel_shuffle.
+    v3 / v1 = (bias, bn_scale, bn_shift) of the two stages.  Returns the output PlaneTensor, or (y, y_u8 | None)."""
+    N, Cmid, Hs, Ws = src.shape
+    dev = src.p0.device
+    a = UpBlockArgs()
+    a.mode, a.N, a.Hs, a.Ws, a.H, a.W, a.Cmid, a.Cout = src.mode, N, Hs, Ws, H, W, Cmid, Cout
+    a.src = src.pair()
+    a.weight3 = (c_void_p * 2)(ptr(w3p[0]), ptr(w3p[1]))
+    a.weight1 = (c_void_p * 2)(ptr(w1p[0]), ptr(w1p[1]))
+    a.bias3, a.bn_scale3, a.bn_shift3 = (ptr(t) for t in v3)
+    a.bias1, a.bn_scale1, a.bn_shift1 = (ptr(t) for t in v1)
+    a.residual = residual.pair() if residual is not None else (c_void_p * 2)(None, None)
+    out = y = y8 = None
+    if tail is None:
+        out = PlaneTensor(N, Cout, H, W, src.mode, dev)
+        a.out, a.tail = out.pair(), 0
+    else:
+        a.out, a.tail = (c_void_p * 2)(None, None), 1
+        a.w10, a.b10 = ptr(tail[0]), ptr(tail[1])
+        y = torch.empty(N, 1, 2 * H, 2 * W, dtype=torch.float32, device=dev)
+        a.y = y.data_ptr()
+        if want_u8:
+            y8 = torch.empty(N, 1, 2 * H, 2 * W, dtype=torch.uint8, device=dev)
+            a.y_u8 = y8.data_ptr()
+    check(lib().nsm_upblock(byref(a), stream_ptr()), "nsm_upblock")
+    return out if tail is None else (y, y8)
 
 
 def upsample_match(x: PlaneTensor, hd, wd, out_x8=False):

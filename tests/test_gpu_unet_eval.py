@@ -68,9 +68,14 @@ def test_every_intermediate_against_oracle(nsm, precision, shape):
     P, x = calibrated(shape)
     net = make_net(P, precision)
     taps = {}
-    with torch.no_grad():
-        ref = oracle.unet_forward(x, P, training=False, bf16=(precision == "bf16"), taps=taps)
-        y = net(x.cuda())
+    nsm.lib().nsm_unet_set_fused_decoder(0)     # stage-by-stage decoder: u8 / t8 / u9 / t9 exist in the workspace
+    try:
+        with torch.no_grad():
+            ref = oracle.unet_forward(x, P, training=False, bf16=(precision == "bf16"), taps=taps)
+            y = net(x.cuda())
+            torch.cuda.synchronize()
+    finally:
+        nsm.lib().nsm_unet_set_fused_decoder(-1)
     ws, B, H, W, mode = net.last_workspace
     report = []
     worst = 0.0
@@ -85,6 +90,9 @@ def test_every_intermediate_against_oracle(nsm, precision, shape):
     print(precision, shape, "out err", err, " ".join(report))
     assert worst <= (3e-4 if precision == "fp32" else 0.1), " ".join(report)
     assert err <= TOL[precision], (err, " ".join(report))
+    with torch.no_grad():                       # the fused decoder blocks (default) give the same output
+        y_fused = net(x.cuda())
+    assert (y_fused.float() - y.float()).abs().max().item() <= (2e-5 if precision == "fp32" else 1.6e-2)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
