@@ -381,7 +381,10 @@ def run_b200(args):
         d[0] += ms; d[1] += fl; d[2] += by; d[3] += 1
     # MMA slots (in units of one bf16-rate MMA) per algorithmic MAC: bf16 mode 1; fp32 mode 3 (hi*hi + hi*lo + lo*hi), or 2
     # for the decoder's 3x3 convolutions whose two cross terms are ONE e4m3 MMA at twice the rate (fp16 hi + 8-bit cross)
-    x8_layers = () if os.environ.get("NSM_NO_X8") else ("conv6.3x3", "conv7.3x3", "conv8.3x3", "conv9.3x3")
+    # (the fused decoder blocks "convK block (...)" are 95 % 3x3 work in that format)
+    x8_names = () if os.environ.get("NSM_NO_X8") else ("conv6.3x3", "conv7.3x3", "conv8.3x3", "conv9.3x3", "conv8 block",
+                                                       "conv9 block")
+    x8_layers = tuple(k for k in per_layer if k.startswith(x8_names)) if x8_names else ()
     mma_factor = 3 if precision == "fp32" else 1
     issued = 0.0
     layers = {}
@@ -401,7 +404,8 @@ def run_b200(args):
                      "frac_of_issued_roofline": max(t_tensor, t_hbm) / max(ms, 1e-9)}
     t_roof = sum(v["roofline_ms"] for v in layers.values())
     planes = 2 if precision == "fp32" else 1
-    roofline = {"kernel": f"conv_gemm_kernel<BN,{planes}> + conv_gemm_wide_kernel (tcgen05 implicit GEMM, "
+    roofline = {"kernel": f"conv_gemm_kernel<BN,{planes}> + conv_gemm_wide_kernel + upblock_kernel (tcgen05 implicit GEMM; "
+                          f"conv8 and conv9..output as fused up-sample/3x3/1x1 blocks; "
                           f"{len(conv) // max(args.steps, 1)} launches/step)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"], "traffic": measured_traffic(),

@@ -157,6 +157,8 @@ int nsm_unet_fused_decoder(void);
 /* tests: 1 / 0 force the fused / stage-by-stage decoder (the latter leaves u8 t8 u9 t9 visible to nsm_unet_tap), -1 restores
  * the environment default */
 int nsm_unet_set_fused_decoder(int on);
+/* debugging (NSM_UB_DBG=64): cycle counters of one worker warp of the fused block kernel, read and cleared */
+int nsm_upblock_prof(unsigned long long* out16);
 
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) then F.interpolate(size=(hd,wd)) -- Unetmodel.py:51-60,
  * 118-141 */

@@ -359,7 +359,8 @@ static int infer_impl(const void* blob, int mode, const float* x, int B, int H, 
   NSM_TRY(double_conv(4, 3, buf("u6"), "t6", "m6", "c4", nullptr));   // conv6 + skip
   NSM_TRY(up("m6", 3, 512, "u7", 2));
   NSM_TRY(double_conv(5, 2, buf("u7"), "t7", "m7", "c3", nullptr));   // conv7 + skip
-  if (fused_decoder(mode)) {
+  if (fused_decoder(mode) && upblock_supported(WL.lv[2].h, WL.lv[2].w, WL.lv[1].h, WL.lv[1].w) &&
+      upblock_supported(WL.lv[1].h, WL.lv[1].w, WL.lv[1].h, WL.lv[1].w)) {
     // ---- conv8 (+ skip) and conv9 + conv10 + sigmoid + pixel_shuffle as two fused blocks
     auto block = [&](int b, int slevel, const char* src, const char* res, const char* dst) -> int {
       UpBlockArgs a;
@@ -720,6 +721,8 @@ int nsm_unet_set_fused_decoder(int on) {
   g_fused_override.store(on < 0 ? -1 : (on ? 1 : 0), std::memory_order_relaxed);
   return 0;
 }
+
+int nsm_upblock_prof(unsigned long long* out8) { return upblock_prof(out8); }
 
 int nsm_upblock(const nsm_upblock_args* a, void* stream) {
   if (!a) {

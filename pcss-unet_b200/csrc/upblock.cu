@@ -24,6 +24,7 @@
 // 1x1 operands fp16 hi+lo (a_hi x [w_hi | w_lo] as one wide MMA + a_lo x w_hi).  bf16 mode: one plane, autocast rounding
 // points (the composite resize is rounded once, like upsample_match).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_gemm.cuh"
@@ -41,15 +42,16 @@ constexpr int kHaloRows = kHaloW * kHaloH;             // 180 rows of 128 B
 constexpr int kHaloPlaneBytes = kHaloRows * 128;       // 23040
 constexpr int kUbThreads = 640;                        // warps 0-3: B producer, MMA, source producer, idle; 4-19: workers
 constexpr int kWorkers = 16;
-constexpr int kWorkerThreads = kWorkers * 32;
 
 struct UbKernelParams {
   int N, Hs, Ws, H, W;
   int Cout, tail;
+  int dbg;   // timing experiments (NSM_UB_DBG bit mask, results wrong): 1 no halo math, 2 no mid epilogue math, 4 no final
   int tiles_x, tiles_y, total_tiles;
   int sbw, sbh;                       // source box in pixels
   uint32_t off_src, off_b, off_vec, off_taps, off_bar;
   uint32_t src_plane_bytes, b_stage_bytes, b_stages;
+  uint32_t halo_bufs, src_bufs;       // ring depths (1 or 2) of the halo tiles and of the staged source boxes
   uint32_t tm_acc2, tm_a2, tmem_cols;  // TMEM column offsets
   uint32_t idesc1, idesc2w, idesc2c;
   const float *bias3, *scale3, *shift3, *bias1, *scale1, *shift1, *w10, *b10;
@@ -57,6 +59,19 @@ struct UbKernelParams {
   float* y;
   uint8_t* y_u8;
 };
+
+constexpr int kStrips = kHaloH / 3;   // 3-row strips of the halo
+constexpr int kStripRows = 6;         // source rows one strip may touch (host-checked)
+struct JobTab {
+  float colw[kHaloW][4];
+  float roww[kHaloH][kStripRows];
+  int colp[kHaloW];
+  int strip_r0[kStrips], strip_rn[kStrips];
+};
+
+// cycle counters of block 0's worker warp 0 (NSM_UB_DBG bit 64; read with nsm_upblock_prof): where a worker's time goes
+__device__ unsigned long long g_ub_prof[16];   // [tail][phase]
+#define UB_T(i) do { if (prof) { const long long c_ = clock64(); acc_[i] += c_ - t_; t_ = c_; } } while (0)
 
 struct TileCoord {
   int n, y0, x0;
@@ -114,23 +129,28 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
   const uint32_t sbase = smem_u32(smem);
   // halo ring at offset 0: buffer b, plane pl at (b * NP + pl) * kHaloPlaneBytes
   float* vec = reinterpret_cast<float*>(smem + p.off_vec);
-  Tap3* taps = reinterpret_cast<Tap3*>(smem + p.off_taps);   // [2][kHaloH + kHaloW]
+  JobTab* tabs = reinterpret_cast<JobTab*>(smem + p.off_taps);   // [2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* b_full = bars;                 // [b_stages]
   uint64_t* b_empty = bars + 8;            // [b_stages]
   uint64_t* halo_full = bars + 16;         // [2]
   uint64_t* halo_empty = bars + 18;        // [2]
-  uint64_t* src_full = bars + 20;
-  uint64_t* src_empty = bars + 21;
-  uint64_t* acc1_full = bars + 22;
-  uint64_t* acc1_empty = bars + 23;
-  uint64_t* a2_full = bars + 24;
-  uint64_t* acc2_full = bars + 25;
-  uint64_t* acc2_empty = bars + 26;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  uint64_t* src_full = bars + 20;          // [2]
+  uint64_t* src_empty = bars + 22;         // [2]
+  uint64_t* acc1_full = bars + 24;
+  uint64_t* acc1_empty = bars + 25;
+  uint64_t* a2_full = bars + 26;
+  uint64_t* acc2_full = bars + 27;
+  uint64_t* acc2_empty = bars + 28;
+  uint64_t* tab_full = bars + 29;          // [2]
+  uint64_t* tab_empty = bars + 31;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.total_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // tiles of this CTA
+  // Every CTA streams the SAME weight tiles; in lockstep all 148 SMs would ask the same L2 lines at the same time (one
+  // slice per line serves them one after the other).  Rotating the tap order per CTA spreads the requests over nine tiles.
+  const int tap_rot = (p.dbg & 8) ? 0 : int(blockIdx.x % 9);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmS0); tma_prefetch_desc(&tmW3a); tma_prefetch_desc(&tmW1a);
@@ -143,8 +163,12 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       mbar_init(&halo_full[b], kWorkers);
       mbar_init(&halo_empty[b], 1);
     }
-    mbar_init(src_full, 1);
-    mbar_init(src_empty, kWorkers);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&src_full[b], 1);
+      mbar_init(&src_empty[b], kWorkers);
+      mbar_init(&tab_full[b], 1);
+      mbar_init(&tab_empty[b], kWorkers);
+    }
     mbar_init(acc1_full, 1);
     mbar_init(acc1_empty, kWorkers);
     mbar_init(a2_full, kWorkers);
@@ -177,9 +201,11 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       };
       for (int j = 0; j < nt; ++j) {
         for (int c = 0; c < NCH; ++c)
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int ti = 0; ti < 9; ++ti) {
+            const int tap = (ti + tap_rot) % 9;
             mbar_wait(&b_empty[stage], phase ^ 1);
             uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
+            if (p.dbg & 16) { mbar_arrive(&b_full[stage]); advance(); continue; }
             mbar_expect_tx(&b_full[stage], NP * CMID * 128);
             tma_load_2d(sb, &tmW3a, &b_full[stage], tap * CMID + c * 64, 0);
             if (NP == 2) tma_load_2d(sb + CMID * 128, &tmW3b, &b_full[stage], tap * CMID + c * 64, 0);
@@ -196,18 +222,67 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       }
     }
   } else if (warp == 2) {
-    // ===================== source producer: one box per (tile, chunk) =====================
-    if (lane == 0) {
-      for (int j = 0, q = 0; j < nt; ++j) {
-        const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
-        int sy0, sx0;
-        ub_src_origin(p, t, sy0, sx0);
-        for (int c = 0; c < NCH; ++c, ++q) {
-          mbar_wait(src_empty, (q & 1) ^ 1);
-          mbar_expect_tx(src_full, NP * p.sbw * p.sbh * 128);
-          tma_load_4d(smem + p.off_src, &tmS0, src_full, c * 64, sx0, sy0, t.n);
-          if (NP == 2) tma_load_4d(smem + p.off_src + p.src_plane_bytes, &tmS1, src_full, c * 64, sx0, sy0, t.n);
+    // ===================== job preparation (runs ahead of the workers): interpolation table + source box =====================
+    // Per (tile, chunk) job: lanes 0-9 the halo columns' horizontal taps, lanes 16-21 the 3-row strips' vertical taps
+    // (composite_taps: a few float divisions each -- off the workers' critical path here), lane 0 the TMA load of the source
+    // box.  Tables are double-buffered (tab_full / tab_empty), source boxes ring through src_bufs buffers.
+    for (int j = 0, q = 0; j < nt; ++j) {
+      const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
+      int sy0, sx0;
+      ub_src_origin(p, t, sy0, sx0);
+      for (int c = 0; c < NCH; ++c, ++q) {
+        JobTab* tb = tabs + (q & 1);
+        mbar_wait(&tab_empty[q & 1], ((q >> 1) & 1) ^ 1);
+        if (lane < kHaloW) {
+          const int gx = t.x0 - 1 + lane;
+          Tap3 tp;
+          tp.rmin = sx0; tp.w[0] = tp.w[1] = tp.w[2] = 0.f;
+          if (gx >= 0 && gx < p.W) tp = composite_taps(gx, p.Ws, p.W);
+          tb->colp[lane] = tp.rmin - sx0;
+          tb->colw[lane][0] = tp.w[0]; tb->colw[lane][1] = tp.w[1]; tb->colw[lane][2] = tp.w[2];
+        } else if (lane >= 16 && lane < 16 + kStrips) {
+          const int s = lane - 16;
+          int r0 = -1, rn = 0;
+          float wv[3][kStripRows];
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+            for (int k = 0; k < kStripRows; ++k) wv[rr][k] = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr) {
+            const int gy = t.y0 - 1 + 3 * s + rr;
+            if (gy < 0 || gy >= p.H) continue;
+            const Tap3 tp = composite_taps(gy, p.Hs, p.H);
+            if (r0 < 0) r0 = tp.rmin;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int k = tp.rmin - r0 + i;   // < kStripRows (checked on the host for every strip of the launch)
+              if (tp.w[i] != 0.f && k < kStripRows) {
+#pragma unroll
+                for (int kk = 0; kk < kStripRows; ++kk)
+                  if (kk == k) wv[rr][kk] = tp.w[i];
+                if (k + 1 > rn) rn = k + 1;
+              }
+            }
+          }
+          tb->strip_r0[s] = r0 < 0 ? 0 : r0 - sy0;
+          tb->strip_rn[s] = rn;
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+            for (int k = 0; k < kStripRows; ++k) tb->roww[3 * s + rr][k] = wv[rr][k];
         }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&tab_full[q & 1]);   // (mbarrier arrive has release semantics for the table writes above)
+          const uint32_t sb = uint32_t(q) % p.src_bufs, use = uint32_t(q) / p.src_bufs;
+          uint8_t* dst = smem + p.off_src + sb * NP * p.src_plane_bytes;
+          mbar_wait(&src_empty[sb], (use & 1) ^ 1);
+          mbar_expect_tx(&src_full[sb], NP * p.sbw * p.sbh * 128);
+          tma_load_4d(dst, &tmS0, &src_full[sb], c * 64, sx0, sy0, t.n);
+          if (NP == 2) tma_load_4d(dst + p.src_plane_bytes, &tmS1, &src_full[sb], c * 64, sx0, sy0, t.n);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -222,18 +297,19 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
         mbar_wait(acc1_empty, (j & 1) ^ 1);
         tc_fence_after();
         for (int c = 0; c < NCH; ++c) {
-          const int q = j * NCH + c, hb = q & 1;
-          mbar_wait(&halo_full[hb], (q >> 1) & 1);
+          const uint32_t q = uint32_t(j * NCH + c), hb = q % p.halo_bufs;
+          mbar_wait(&halo_full[hb], (q / p.halo_bufs) & 1);
           tc_fence_after();
           const uint32_t halo = sbase + uint32_t(hb * NP) * kHaloPlaneBytes;
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int ti = 0; ti < 9; ++ti) {
+            const int tap = (ti + tap_rot) % 9;
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
             const uint32_t a0 = halo + uint32_t((tap / 3) * kHaloW + tap % 3) * 128u;
             const uint32_t b0 = sbase + p.off_b + stage * p.b_stage_bytes;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t accum = (c | tap | k) != 0 ? 1u : 0u;
+            for (int k = 0; k < ((p.dbg & 32) ? 0 : 4); ++k) {
+              const uint32_t accum = (c | ti | k) != 0 ? 1u : 0u;
               umma_bf16(tm_acc1, make_desc_sw128(a0 + k * 32, 16, kHaloW * 128),
                         make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc1, accum);
               if (NP == 2)   // both cross terms as one e4m3 MMA of K = 32 (8-bit cross planes)
@@ -279,85 +355,60 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
     const int wt = threadIdx.x - 128;  // 0 .. 511
     const uint32_t lane_base = uint32_t(qd * 32) << 16;
     const int ly = qd * 4 + (lane >> 3), lx = lane & 7;   // this lane's pixel inside the tile
+    const bool prof = (p.dbg & 64) && blockIdx.x == 0 && w == 0 && lane == 0;
+    long long acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_ = clock64();
 
     // ---- one (tile, chunk) job: interpolate the halo of 64 channels into halo buffer q & 1 ----
+    // Branch-free per element: a job table (built ahead of time by warp 2, double-buffered) holds per halo column the first source
+    // column and three horizontal weights, per 3-row strip the first source row and row count, per halo row its weights on
+    // the strip's source rows.  Rows / columns outside the image have all-zero weights = the convolution's zero padding.
     auto do_job = [&](int q) {
-      const int j = q / NCH, c = q - j * NCH;
-      (void)c;
-      const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
-      Tap3* tb = taps + (q & 1) * (kHaloH + kHaloW);
-      if (wt < kHaloH) {
-        const int gy = t.y0 - 1 + wt;
-        if (gy >= 0 && gy < p.H) tb[wt] = composite_taps(gy, p.Hs, p.H);
-      } else if (wt < kHaloH + kHaloW) {
-        const int gx = t.x0 - 1 + (wt - kHaloH);
-        if (gx >= 0 && gx < p.W) tb[wt] = composite_taps(gx, p.Ws, p.W);
-      }
-      int sy0, sx0;
-      ub_src_origin(p, t, sy0, sx0);
-      named_bar_sync(1, kWorkerThreads);
-      const int hb = q & 1;
-      mbar_wait(&halo_empty[hb], ((q >> 1) & 1) ^ 1);   // the MMAs of the buffer's previous use have read it
-      mbar_wait(src_full, q & 1);
+      JobTab* tb = tabs + (q & 1);
+      mbar_wait(&tab_full[q & 1], (q >> 1) & 1);
+      const uint32_t hb = uint32_t(q) % p.halo_bufs, sb = uint32_t(q) % p.src_bufs;
+      mbar_wait(&halo_empty[hb], ((uint32_t(q) / p.halo_bufs) & 1) ^ 1);   // the MMAs of the buffer's previous use have read it
+      mbar_wait(&src_full[sb], (uint32_t(q) / p.src_bufs) & 1);
+      UB_T(0);
       const int cg = wt & 7, slot = wt >> 3;
-      if (slot < 60) {
+      if (slot < kStrips * kHaloW && !(p.dbg & 1)) {
         const int hx = slot % kHaloW, strip = slot / kHaloW;
-        const int gx = t.x0 - 1 + hx;
-        const bool colok = gx >= 0 && gx < p.W;
-        Tap3 tx;
-        tx.rmin = 0; tx.w[0] = tx.w[1] = tx.w[2] = 0.f;
-        if (colok) tx = tb[kHaloH + hx];
-        const uint32_t src0 = sbase + p.off_src + uint32_t(cg) * 16u;
-        // horizontally interpolated source row r (8 channels)
-        auto hrow = [&](int r, float (&h)[8]) {
+        const float cw0 = tb->colw[hx][0], cw1 = tb->colw[hx][1], cw2 = tb->colw[hx][2];
+        const int px0 = tb->colp[hx];
+        const int px1 = px0 + 1 < p.sbw ? px0 + 1 : p.sbw - 1, px2 = px0 + 2 < p.sbw ? px0 + 2 : p.sbw - 1;
+        const int r0 = tb->strip_r0[strip], rn = tb->strip_rn[strip];
+        const uint32_t src0 = sbase + p.off_src + sb * NP * p.src_plane_bytes + uint32_t(cg) * 16u;
+        float o0[8], o1[8], o2[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) h[e] = 0.f;
-          if (r > p.Hs - 1 || r - sy0 >= p.sbh) return;   // only reached with zero vertical weight (outside the box)
-#pragma unroll
-          for (int jx = 0; jx < 3; ++jx) {
-            if (tx.w[jx] == 0.f) continue;
-            float v[8];
-            ub_load8<NP>(src0 + uint32_t((r - sy0) * p.sbw + (tx.rmin + jx - sx0)) * 128u, p.src_plane_bytes, v);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) h[e] = fmaf(tx.w[jx], v[e], h[e]);
-          }
-        };
-        float h0[8], h1[8], h2[8];
-        int base = -1000000;
-        const uint32_t halo = sbase + uint32_t(hb * NP) * kHaloPlaneBytes;
+        for (int e = 0; e < 8; ++e) o0[e] = o1[e] = o2[e] = 0.f;
 #pragma unroll 1
-        for (int rr = 0; rr < 3; ++rr) {
-          const int hy = strip * 3 + rr;
-          const int gy = t.y0 - 1 + hy;
-          const uint32_t row = halo + uint32_t(hy * kHaloW + hx) * 128u;
-          const uint32_t sw = (row >> 7) & 7u;
-          if (!colok || gy < 0 || gy >= p.H) {   // the convolution's zero padding (and rows below a ragged tile)
-            sts16(row + ((uint32_t(cg) ^ sw) << 4), make_uint4(0, 0, 0, 0));
-            if (NP == 2) {
-              const uint32_t row2 = row + kHaloPlaneBytes;
-              sts16(row2 + ((uint32_t(cg) ^ ((row2 >> 7) & 7u)) << 4), make_uint4(0, 0, 0, 0));
-            }
-            continue;
-          }
-          const Tap3 ty = tb[hy];
-          if (ty.rmin - base > 2 || ty.rmin < base) {   // (re)start the three-row window
-            base = ty.rmin;
-            hrow(base, h0); hrow(base + 1, h1); hrow(base + 2, h2);
-          } else {
-            while (base < ty.rmin) {
+        for (int k = 0; k < rn; ++k) {
+          const int r = r0 + k < p.sbh ? r0 + k : p.sbh - 1;   // rows past the box carry zero weight only
+          const uint32_t rowa = src0 + uint32_t(r * p.sbw) * 128u;
+          float v0[8], v1[8], h[8];
+          ub_load8<NP>(rowa + uint32_t(px0) * 128u, p.src_plane_bytes, v0);
+          ub_load8<NP>(rowa + uint32_t(px1) * 128u, p.src_plane_bytes, v1);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { h0[e] = h1[e]; h1[e] = h2[e]; }
-              hrow(base + 3, h2);
-              ++base;
-            }
+          for (int e = 0; e < 8; ++e) h[e] = fmaf(cw1, v1[e], fmaf(cw0, v0[e], 0.f));
+          if (cw2 != 0.f) {
+            ub_load8<NP>(rowa + uint32_t(px2) * 128u, p.src_plane_bytes, v0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h[e] = fmaf(cw2, v0[e], h[e]);
           }
-          float v[8];
+          const float w0 = tb->roww[3 * strip][k], w1 = tb->roww[3 * strip + 1][k], w2 = tb->roww[3 * strip + 2][k];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float a = fmaf(ty.w[0], h0[e], 0.f);
-            a = fmaf(ty.w[1], h1[e], a);
-            v[e] = fmaf(ty.w[2], h2[e], a);
-            if (rb) v[e] = rbf(v[e]);
+            o0[e] = fmaf(w0, h[e], o0[e]);
+            o1[e] = fmaf(w1, h[e], o1[e]);
+            o2[e] = fmaf(w2, h[e], o2[e]);
+          }
+        }
+        const uint32_t halo = sbase + uint32_t(hb * NP) * kHaloPlaneBytes;
+        auto put = [&](int rr, float (&v)[8]) {
+          const uint32_t row = halo + uint32_t((strip * 3 + rr) * kHaloW + hx) * 128u;
+          const uint32_t sw = (row >> 7) & 7u;
+          if (rb) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = rbf(v[e]);
           }
           uint32_t hw[4];
 #pragma unroll
@@ -376,23 +427,28 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
                          "r"(second.y)
                          : "memory");
           }
-        }
+        };
+        put(0, o0); put(1, o1); put(2, o2);
       }
+      UB_T(1);
       fence_proxy_async();   // generic-proxy writes of the halo -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&halo_full[hb]);
-        mbar_arrive(src_empty);
+        mbar_arrive(&src_empty[sb]);
+        mbar_arrive(&tab_empty[q & 1]);
       }
+      UB_T(2);
     };
 
     // ---- 3x3 accumulator -> A operand of the 1x1 GEMM in tensor memory ----
     auto mid_epilogue = [&](int j) {
       mbar_wait(acc1_full, j & 1);
       tc_fence_after();
+      UB_T(3);
       constexpr int CW = CMID / 4;   // columns per warp
 #pragma unroll
-      for (int g = 0; g < CW / 16; ++g) {
+      for (int g = 0; g < ((p.dbg & 2) ? 0 : CW / 16); ++g) {
         const int col = cs * CW + g * 16;
         uint32_t r0[16], r1[16];
         tmem_ld_32x16(tm_acc1 + lane_base + col, r0);
@@ -400,23 +456,30 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
         tmem_ld_wait();
         uint32_t hw[8], lw[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float a[2];
+        for (int e4 = 0; e4 < 16; e4 += 4) {
+          const float4 B = *reinterpret_cast<const float4*>(vec + col + e4);
+          const float4 S = *reinterpret_cast<const float4*>(vec + CMID + col + e4);
+          const float4 T = *reinterpret_cast<const float4*>(vec + 2 * CMID + col + e4);
+          const float bb[4] = {B.x, B.y, B.z, B.w}, sc[4] = {S.x, S.y, S.z, S.w}, sh[4] = {T.x, T.y, T.z, T.w};
+          float a[4];
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int ch = col + 2 * e + k;
-            float v = __uint_as_float(r0[2 * e + k]);
-            if (NP == 2) v = fmaf(__uint_as_float(r1[2 * e + k]), kX8CrossScale, v);
-            v += vec[ch];
+          for (int k = 0; k < 4; ++k) {
+            float v = __uint_as_float(r0[e4 + k]);
+            if (NP == 2) v = fmaf(__uint_as_float(r1[e4 + k]), kX8CrossScale, v);
+            v += bb[k];
             if (rb) v = rbf(v);
-            v = fmaf(v, vec[CMID + ch], vec[2 * CMID + ch]);
+            v = fmaf(v, sc[k], sh[k]);
             if (rb) v = rbf(v);
             v = lrelu02(v);
             if (rb) v = rbf(v);
             a[k] = v;
           }
-          hw[e] = pack_hi(a[0], a[1], FMT);
-          if (NP == 2) lw[e] = pack_lo_resid(a[0], a[1], hw[e], FMT);
+          hw[e4 / 2] = pack_hi(a[0], a[1], FMT);
+          hw[e4 / 2 + 1] = pack_hi(a[2], a[3], FMT);
+          if (NP == 2) {
+            lw[e4 / 2] = pack_lo_resid(a[0], a[1], hw[e4 / 2], FMT);
+            lw[e4 / 2 + 1] = pack_lo_resid(a[2], a[3], hw[e4 / 2 + 1], FMT);
+          }
         }
         tmem_st_32x8(tm_a2 + lane_base + col / 2, hw);
         if (NP == 2) tmem_st_32x8(tm_a2 + lane_base + CMID / 2 + col / 2, lw);
@@ -428,35 +491,57 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
         mbar_arrive(acc1_empty);   // the 3x3 accumulator may be overwritten by the next tile
         mbar_arrive(a2_full);      // the 1x1 GEMM's A operand is in place
       }
+      UB_T(4);
     };
 
     // ---- 1x1 accumulator -> output ----
-    auto final_epilogue = [&](int j) {
+    auto final_epilogue = [&](int j, const TileCoord& t) {
+      const bool active = cs * 16 < p.Cout && !(p.dbg & 4);
+      const int col = cs * 16;
+      const int y = t.y0 + ly, x = t.x0 + lx;
+      const bool inside = active && y < p.H && x < p.W;
+      const size_t off = (((size_t)t.n * p.H + y) * p.W + x) * p.Cout + col;   // element offset (conv8 form)
+      // the skip values do not depend on the accumulator: request them before waiting for it
+      uint4 rh[2], rl[2];
+      const bool has_res = !p.tail && p.residual.p[0] != nullptr;
+      if (inside && has_res) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          rh[hf] = ldg16(reinterpret_cast<const uint8_t*>(p.residual.p[0]) + (off + 8 * hf) * 2);
+          if (NP == 2) rl[hf] = ldg16(reinterpret_cast<const uint8_t*>(p.residual.p[1]) + (off + 8 * hf) * 2);
+        }
+      }
+      UB_T(5);
       mbar_wait(acc2_full, j & 1);
       tc_fence_after();
-      if (cs * 16 < p.Cout) {
-        const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
-        const int col = cs * 16;
+      UB_T(6);
+      if (active) {
         uint32_t r0[16], r1[16];
         tmem_ld_32x16(tm_acc2 + lane_base + col, r0);
         if (NP == 2) tmem_ld_32x16(tm_acc2 + lane_base + p.Cout + col, r1);
-        tmem_ld_wait();
         const float* v1 = vec + 3 * CMID;
+        tmem_ld_wait();
         float a[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float v = __uint_as_float(r0[e]);
-          if (NP == 2) v += __uint_as_float(r1[e]);
-          v += v1[col + e];
-          if (rb) v = rbf(v);
-          v = fmaf(v, v1[p.Cout + col + e], v1[2 * p.Cout + col + e]);
-          if (rb) v = rbf(v);
-          v = lrelu02(v);
-          if (rb) v = rbf(v);
-          a[e] = v;
+        for (int e4 = 0; e4 < 16; e4 += 4) {
+          const float4 B = *reinterpret_cast<const float4*>(v1 + col + e4);
+          const float4 S = *reinterpret_cast<const float4*>(v1 + p.Cout + col + e4);
+          const float4 T = *reinterpret_cast<const float4*>(v1 + 2 * p.Cout + col + e4);
+          const float bb[4] = {B.x, B.y, B.z, B.w}, sc[4] = {S.x, S.y, S.z, S.w}, sh[4] = {T.x, T.y, T.z, T.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float v = __uint_as_float(r0[e4 + k]);
+            if (NP == 2) v += __uint_as_float(r1[e4 + k]);
+            v += bb[k];
+            if (rb) v = rbf(v);
+            v = fmaf(v, sc[k], sh[k]);
+            if (rb) v = rbf(v);
+            v = lrelu02(v);
+            if (rb) v = rbf(v);
+            a[e4 + k] = v;
+          }
         }
-        const int y = t.y0 + ly, x = t.x0 + lx;
-        if (y < p.H && x < p.W) {
+        if (inside) {
           if (p.tail) {
             // conv10 (16 -> 4) + bias, sigmoid, pixel_shuffle(2): channel k = dy * 2 + dx -> pixel (2y + dy, 2x + dx)
             const float* w10 = v1 + 3 * p.Cout;
@@ -465,7 +550,10 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
             for (int k = 0; k < 4; ++k) {
               float s = 0.f;
 #pragma unroll
-              for (int e = 0; e < 16; ++e) s = fmaf(w10[k * 16 + e], a[e], s);
+              for (int e = 0; e < 16; e += 4) {
+                const float4 w = *reinterpret_cast<const float4*>(w10 + k * 16 + e);
+                s = fmaf(w.x, a[e], s); s = fmaf(w.y, a[e + 1], s); s = fmaf(w.z, a[e + 2], s); s = fmaf(w.w, a[e + 3], s);
+              }
               s += w10[64 + k];
               if (rb) s = rbf(s);
               s = 1.f / (1.f + expf(-s));
@@ -481,20 +569,17 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
                     make_uchar2((unsigned char)(o[2 * dy] * 255.f), (unsigned char)(o[2 * dy + 1] * 255.f));
             }
           } else {
-            const size_t off = (((size_t)t.n * p.H + y) * p.W + x) * p.Cout + col;   // element offset
-            if (p.residual.p[0]) {
+            if (has_res) {
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
-                const uint4 h = ldg16(reinterpret_cast<const uint8_t*>(p.residual.p[0]) + (off + 8 * hf) * 2);
-                const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                const uint32_t hw[4] = {rh[hf].x, rh[hf].y, rh[hf].z, rh[hf].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   a[8 * hf + 2 * e] += hi_lo_to_f32(hw[e], FMT);
                   a[8 * hf + 2 * e + 1] += hi_hi_to_f32(hw[e], FMT);
                 }
                 if (NP == 2) {
-                  const uint4 l = ldg16(reinterpret_cast<const uint8_t*>(p.residual.p[1]) + (off + 8 * hf) * 2);
-                  const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+                  const uint32_t lw[4] = {rl[hf].x, rl[hf].y, rl[hf].z, rl[hf].w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     a[8 * hf + 2 * e] += lo_lo_to_f32(lw[e], FMT);
@@ -525,17 +610,24 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
+      UB_T(7);
     };
 
+    // Program order of a worker warp: the halo jobs of tile j+1 are interleaved with the epilogues of tile j so that each
+    // job's source box (single-buffered) is in flight while an epilogue runs, and the 3x3 MMAs of tile j+1 start as soon
+    // as the 3x3 accumulator of tile j has been drained.
     int q_next = 0;
     for (; q_next < NCH && q_next < nt * NCH; ++q_next) do_job(q_next);
     for (int j = 0; j < nt; ++j) {
-      if (j + 1 < nt) do_job(q_next++);        // first chunk of the next tile: overlaps this tile's 3x3 MMAs
+      const bool more = j + 1 < nt;
+      const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
+      if (more) do_job(q_next++);              // first chunk of the next tile: overlaps this tile's 3x3 MMAs
       mid_epilogue(j);
-      final_epilogue(j);
-      if (j + 1 < nt)
-        for (int c = 1; c < NCH; ++c) do_job(q_next++);
+      if (more && NCH > 1) do_job(q_next++);   // second chunk: its halo buffer was released by this tile's MMAs
+      final_epilogue(j, t);
     }
+    if (prof)
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_ub_prof[(p.tail ? 8 : 0) + i], (unsigned long long)acc_[i]);
   }
 
   tc_fence_before();
@@ -567,6 +659,24 @@ int src_box_extent(int in_size, int out_size, int tile, int halo) {
   return best;
 }
 
+// most source rows a 3-row strip of any tile's halo touches (the kernel's job table holds kStripRows of them)
+int max_strip_rows(int in_size, int out_size) {
+  int best = 1;
+  for (int t0 = 0; t0 < out_size; t0 += kUbTH)
+    for (int s = 0; s < kStrips; ++s) {
+      int r0 = -1;
+      for (int rr = 0; rr < 3; ++rr) {
+        const int g = t0 - 1 + 3 * s + rr;
+        if (g < 0 || g >= out_size) continue;
+        const Tap3 tp = composite_taps(g, in_size, out_size);
+        if (r0 < 0) r0 = tp.rmin;
+        for (int i = 0; i < 3; ++i)
+          if (tp.w[i] != 0.f && tp.rmin - r0 + i + 1 > best) best = tp.rmin - r0 + i + 1;
+      }
+    }
+  return best;
+}
+
 template <int NP, int CMID>
 int launch_ub(const CUtensorMap* maps, const UbKernelParams& kp, int grid, size_t smem_bytes, cudaStream_t st) {
   auto kern = upblock_kernel<NP, CMID>;
@@ -591,6 +701,18 @@ int launch_ub(const CUtensorMap* maps, const UbKernelParams& kp, int grid, size_
 
 }  // namespace
 
+// debugging: read and clear the cycle counters (2 x 8 values, block with skip / block with tail: job wait / math / publish, mid wait / math, final prefetch /
+// wait / math)
+int upblock_prof(unsigned long long* out) {
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out, g_ub_prof, sizeof(z)) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(g_ub_prof, z, sizeof(z)) != cudaSuccess;
+}
+
+bool upblock_supported(int Hs, int Ws, int H, int W) {
+  return H >= Hs && W >= Ws && Hs >= 1 && Ws >= 1 && max_strip_rows(Hs, H) <= kStripRows;
+}
+
 int upblock_launch(const UpBlockArgs& a, cudaStream_t st) {
   const int NP = a.mode == kFmtBf16 ? 1 : 2;
   if ((a.mode != kFmtBf16 && a.mode != kFmtF16x2) || (a.Cmid != 64 && a.Cmid != 128) ||
@@ -608,38 +730,64 @@ int upblock_launch(const UpBlockArgs& a, cudaStream_t st) {
   }
   UbKernelParams kp;
   memset(&kp, 0, sizeof(kp));
+  {
+    static const int dbg = getenv("NSM_UB_DBG") ? atoi(getenv("NSM_UB_DBG")) : 0;
+    kp.dbg = dbg;
+  }
   kp.N = a.N; kp.Hs = a.Hs; kp.Ws = a.Ws; kp.H = a.H; kp.W = a.W; kp.Cout = a.Cout; kp.tail = a.tail;
   kp.tiles_x = (a.W + kUbTW - 1) / kUbTW;
   kp.tiles_y = (a.H + kUbTH - 1) / kUbTH;
   kp.total_tiles = a.N * kp.tiles_x * kp.tiles_y;
   kp.sbh = src_box_extent(a.Hs, a.H, kUbTH, kHaloH);
   kp.sbw = src_box_extent(a.Ws, a.W, kUbTW, kHaloW);
+  if (max_strip_rows(a.Hs, a.H) > kStripRows) {
+    set_error("upblock: a 3-row strip spans more than %d source rows (%d -> %d)", kStripRows, a.Hs, a.H);
+    return 1;
+  }
   if (kp.sbh > 256 || kp.sbw > 256) {
     set_error("upblock: source box %dx%d too large", kp.sbh, kp.sbw);
     return 1;
   }
   // shared-memory layout (offsets from the 1024-byte aligned base)
   auto up = [](size_t v, size_t al) { return (v + al - 1) / al * al; };
-  size_t off = size_t(2) * NP * kHaloPlaneBytes;
-  kp.off_src = uint32_t(off = up(off, 128));
+  // ring depths: two halo buffers + two source buffers where they fit next to >= 3 weight stages; otherwise the
+  // configuration picked by measurement (NSM_UB_RINGS=<halo><src> overrides, e.g. 21, 12)
   kp.src_plane_bytes = uint32_t(up(size_t(kp.sbw) * kp.sbh * 128, 128));
-  off += size_t(NP) * kp.src_plane_bytes;
-  const size_t fixed_tail = up(size_t(3 * a.Cmid + 3 * a.Cout + 68) * 4, 16) + 2 * (kHaloH + kHaloW) * sizeof(Tap3) + 256;
-  kp.off_b = uint32_t(off = up(off, 1024));
-  kp.b_stage_bytes = uint32_t(NP * a.Cmid * 128);
+  const size_t stage_bytes = size_t(NP) * a.Cmid * 128;
+  const size_t fixed_tail = up(size_t(3 * a.Cmid + 3 * a.Cout + 68) * 4, 16) + 2 * sizeof(JobTab) + 256;
   const size_t budget = size_t(227) * 1024 - 1024;
+  auto fits = [&](int hb, int sb, int stages) {
+    return up(size_t(hb) * NP * kHaloPlaneBytes + size_t(sb) * NP * kp.src_plane_bytes, 1024) + stages * stage_bytes +
+               fixed_tail <= budget;
+  };
+  int hb = 2, sb = 2;
+  if (!fits(2, 2, 3)) sb = 1;   // measured (profiles/README.md): one halo buffer + two source buffers is slower than 2 + 1
+  {
+    static const int force = getenv("NSM_UB_RINGS") ? atoi(getenv("NSM_UB_RINGS")) : 0;
+    if (force >= 11 && force <= 22 && force % 10 >= 1 && force % 10 <= 2) { hb = force / 10; sb = force % 10; }
+  }
+  kp.halo_bufs = uint32_t(hb); kp.src_bufs = uint32_t(sb);
+  size_t off = size_t(hb) * NP * kHaloPlaneBytes;
+  kp.off_src = uint32_t(off = up(off, 128));
+  off += size_t(sb) * NP * kp.src_plane_bytes;
+  kp.off_b = uint32_t(off = up(off, 1024));
+  kp.b_stage_bytes = uint32_t(stage_bytes);
   if (off + fixed_tail + 2 * kp.b_stage_bytes > budget) {
     set_error("upblock: shared-memory budget exceeded (source box %dx%d)", kp.sbh, kp.sbw);
     return 1;
   }
   size_t stages = (budget - off - fixed_tail) / kp.b_stage_bytes;
   if (stages > 8) stages = 8;
+  {
+    static const int force = getenv("NSM_UB_BSTAGES") ? atoi(getenv("NSM_UB_BSTAGES")) : 0;
+    if (force >= 2 && size_t(force) < stages) stages = size_t(force);
+  }
   kp.b_stages = uint32_t(stages);
   off += stages * kp.b_stage_bytes;
   kp.off_vec = uint32_t(off = up(off, 16));
   off += up(size_t(3 * a.Cmid + 3 * a.Cout + 68) * 4, 16);
   kp.off_taps = uint32_t(off);
-  off += 2 * (kHaloH + kHaloW) * sizeof(Tap3);
+  off += 2 * sizeof(JobTab);
   kp.off_bar = uint32_t(off = up(off, 8));
   off += 256;
   const size_t smem_bytes = off + 1024;

@@ -26,5 +26,8 @@ struct UpBlockArgs {
   uint8_t* y_u8;       // optional uint8 form of y
 };
 int upblock_launch(const UpBlockArgs& a, cudaStream_t st);
+// false: the resize needs a wider vertical stencil than the kernel's job table holds (use the stage-by-stage path)
+bool upblock_supported(int Hs, int Ws, int H, int W);
+int upblock_prof(unsigned long long* out);
 
 }  // namespace nsm

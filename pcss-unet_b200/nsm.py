@@ -168,7 +168,7 @@ EXPORTS = TRAIN_EXPORTS + [
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
     "nsm_channel_sums", "nsm_standardize", "nsm_perturb", "nsm_profile_enable", "nsm_profile_read",
-    "nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1", "nsm_upblock", "nsm_unet_fused_decoder", "nsm_unet_set_fused_decoder",
+    "nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1", "nsm_upblock", "nsm_unet_fused_decoder", "nsm_unet_set_fused_decoder", "nsm_upblock_prof",
 ] + PX4_EXPORTS
 
 
