@@ -226,7 +226,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
   }
   if (ep.round_bf16) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+    for (int j = 0; j < 32; j += 2) rbf2(v[j], v[j + 1]);
   }
   if (ep.stats) {
     // Per-channel sum / sum of squares over the warp's 32 pixels by a butterfly "transpose reduction" (31 shuffles per
@@ -262,7 +262,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
     }
     if (ep.round_bf16) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+      for (int j = 0; j < 32; j += 2) rbf2(v[j], v[j + 1]);
     }
   }
   if (ep.lrelu) {
@@ -271,7 +271,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
     for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : slope * v[j];
     if (ep.round_bf16) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+      for (int j = 0; j < 32; j += 2) rbf2(v[j], v[j + 1]);
     }
   }
   if (has_res) {
@@ -302,7 +302,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
     }
     if (ep.round_bf16) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);
+      for (int j = 0; j < 32; j += 2) rbf2(v[j], v[j + 1]);
     }
   }
   if (ep.out.p[0]) {
@@ -343,8 +343,11 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
     for (int j = 0; j < 32; ++j) {
       float s = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 1);
       s += __shfl_xor_sync(0xffffffffu, s, TW);
-      s *= 0.25f;
-      v[j] = ep.round_bf16 ? rbf(s) : s;
+      v[j] = s * 0.25f;
+    }
+    if (ep.round_bf16) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) rbf2(v[j], v[j + 1]);
     }
     if (lane == 0) bulk_wait_read0();
     __syncwarp();

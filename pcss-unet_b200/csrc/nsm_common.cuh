@@ -29,6 +29,15 @@ __device__ __forceinline__ bool elect_one() {
 
 // round-to-nearest-even fp32 -> bf16 -> fp32 (the rounding points of torch.autocast(bfloat16))
 __device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// the same for two values with ONE packed conversion (F2FP.BF16.PACK_AB on the ALU pipe) + two unpacking logic ops; the
+// single conversion above is an F2F on the quarter-rate conversion pipe, which bounded the bf16-mode epilogues (three to
+// four roundings per output element)
+__device__ __forceinline__ void rbf2(float& a, float& b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  const uint32_t r = *reinterpret_cast<const uint32_t*>(&t);
+  a = __uint_as_float(r << 16);
+  b = __uint_as_float(r & 0xffff0000u);
+}
 
 // fp32-mode split of activations and weights: v ~= hi (fp16, saturated to +-65504) + lo (fp16):
 // |v - hi - lo| <= max(2^-23 |v|, 2^-25) for |v| <= 65504; the dropped lo*lo product of the 3-term GEMM is <= 2^-22

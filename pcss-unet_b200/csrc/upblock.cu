@@ -408,7 +408,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
           const uint32_t sw = (row >> 7) & 7u;
           if (rb) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = rbf(v[e]);
+            for (int e = 0; e < 8; e += 2) rbf2(v[e], v[e + 1]);
           }
           uint32_t hw[4];
 #pragma unroll
@@ -466,14 +466,15 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
           for (int k = 0; k < 4; ++k) {
             float v = __uint_as_float(r0[e4 + k]);
             if (NP == 2) v = fmaf(__uint_as_float(r1[e4 + k]), kX8CrossScale, v);
-            v += bb[k];
-            if (rb) v = rbf(v);
-            v = fmaf(v, sc[k], sh[k]);
-            if (rb) v = rbf(v);
-            v = lrelu02(v);
-            if (rb) v = rbf(v);
-            a[k] = v;
+            a[k] = v + bb[k];
           }
+          if (rb) { rbf2(a[0], a[1]); rbf2(a[2], a[3]); }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a[k] = fmaf(a[k], sc[k], sh[k]);
+          if (rb) { rbf2(a[0], a[1]); rbf2(a[2], a[3]); }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a[k] = lrelu02(a[k]);
+          if (rb) { rbf2(a[0], a[1]); rbf2(a[2], a[3]); }
           hw[e4 / 2] = pack_hi(a[0], a[1], FMT);
           hw[e4 / 2 + 1] = pack_hi(a[2], a[3], FMT);
           if (NP == 2) {
@@ -532,14 +533,15 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
           for (int k = 0; k < 4; ++k) {
             float v = __uint_as_float(r0[e4 + k]);
             if (NP == 2) v += __uint_as_float(r1[e4 + k]);
-            v += bb[k];
-            if (rb) v = rbf(v);
-            v = fmaf(v, sc[k], sh[k]);
-            if (rb) v = rbf(v);
-            v = lrelu02(v);
-            if (rb) v = rbf(v);
-            a[e4 + k] = v;
+            a[e4 + k] = v + bb[k];
           }
+          if (rb) { rbf2(a[e4], a[e4 + 1]); rbf2(a[e4 + 2], a[e4 + 3]); }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a[e4 + k] = fmaf(a[e4 + k], sc[k], sh[k]);
+          if (rb) { rbf2(a[e4], a[e4 + 1]); rbf2(a[e4 + 2], a[e4 + 3]); }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a[e4 + k] = lrelu02(a[e4 + k]);
+          if (rb) { rbf2(a[e4], a[e4 + 1]); rbf2(a[e4 + 2], a[e4 + 3]); }
         }
         if (inside) {
           if (p.tail) {
@@ -589,7 +591,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
               }
               if (rb) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) a[e] = rbf(a[e]);
+                for (int e = 0; e < 16; e += 2) rbf2(a[e], a[e + 1]);
               }
             }
 #pragma unroll
