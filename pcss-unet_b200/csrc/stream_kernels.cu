@@ -1250,6 +1250,7 @@ struct LossParams {
   float coef_l1, coef_pert;
   float* grad;
   double* acc;
+  int vec;
 };
 __device__ __forceinline__ float sgn(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
 
@@ -1261,7 +1262,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __global__ void __launch_bounds__(256) l1_loss_kernel(const LossParams p) {
   float s_l1 = 0.f, s_p = 0.f, bad = 0.f;
-  const long long n4 = p.numel >> 2;
+  const long long n4 = p.vec ? p.numel >> 2 : 0;   // 16-byte path only when every pointer is 16-byte aligned
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     const float4 o = __ldg(reinterpret_cast<const float4*>(p.out) + i);
     const float ov[4] = {o.x, o.y, o.z, o.w};
@@ -1329,6 +1330,10 @@ int l1_loss_fwd_bwd(const float* out, const float* target, const float* const* p
   p.out = out; p.target = target; p.n_pert = n_perturbed; p.numel = numel;
   for (int k = 0; k < 4; ++k) p.pert[k] = k < n_perturbed ? perturbed[k] : nullptr;
   p.coef_l1 = coef_l1; p.coef_pert = coef_pert; p.grad = grad; p.acc = acc;
+  // a contiguous view with an odd element offset (e.g. a slice of a larger buffer) is legal input: scalar loop then
+  uintptr_t bits = reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(grad);
+  for (int k = 0; k < n_perturbed; ++k) bits |= reinterpret_cast<uintptr_t>(perturbed[k]);
+  p.vec = (bits & 15) == 0 ? 1 : 0;
   l1_loss_kernel<<<grid_for((numel + 3) / 4, 256, 148 * 8), 256, 0, st>>>(p);
   NSM_CHECK_LAUNCH("l1_loss");
   return 0;

@@ -483,10 +483,9 @@ def feature_l1(f: PlaneTensor, acc):
 def l1_loss_fwd_bwd(out, target=None, perturbed=(), coef_l1=0.0, coef_pert=0.0, want_grad=True):
     """Returns (acc[3] float64 device tensor: sum|o-t|, sum_i sum|o-y_i|, #out-of-range; grad or None)."""
     def aligned(t):
-        # the kernel streams float4: a contiguous view at an odd element offset (e.g. a slice of a larger buffer) is
-        # copied to a fresh, 16-byte aligned allocation instead of faulting
-        t = t.contiguous()
-        return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+        # (the kernel takes its 16-byte vector path only when every pointer is 16-byte aligned, so a contiguous view at an
+        # odd element offset needs no copy)
+        return t.contiguous()
     out = aligned(out)
     assert out.dtype == torch.float32
     n = out.numel()

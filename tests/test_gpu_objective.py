@@ -36,6 +36,19 @@ def test_custom_loss_matches_reference_golden(nsm, golden):
     assert abs(((loss - crit.alpha * l1) / (1 - crit.alpha)).item()) < 1e-5     # main.py:277 back-derivation of vgg
 
 
+def test_l1_misaligned_views(nsm):
+    """Contiguous views whose first element is not 16-byte aligned (a slice of a larger buffer): the kernel must fall back to
+    its scalar loop instead of faulting on a 16-byte access."""
+    big_o = torch.rand(4 * 33 * 40 + 3, generator=gen(3)).cuda()
+    big_t = torch.rand(4 * 33 * 40 + 3, generator=gen(4)).cuda()
+    o = big_o[3:].view(4, 1, 33, 40)
+    t = big_t[1:-2].view(4, 1, 33, 40)
+    assert o.data_ptr() % 16 and t.data_ptr() % 16 and o.is_contiguous()
+    acc, grad = nsm.l1_loss_fwd_bwd(o, t, (), coef_l1=0.9 / o.numel())
+    assert abs(acc[0].item() / o.numel() - oracle.l1_loss(o.cpu(), t.cpu()).item()) <= 1e-6
+    assert torch.allclose(grad.cpu(), oracle.custom_loss_grad(o.cpu(), t.cpu(), 0.9), rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("shape", [(1, 1, 7, 9), (3, 1, 64, 96), (2, 1, 1080, 1920)])
 def test_l1_value_and_sign_gradient(nsm, shape):
     o = torch.rand(*shape, generator=gen(1))
