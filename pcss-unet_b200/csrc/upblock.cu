@@ -46,7 +46,7 @@ constexpr int kWorkers = 16;
 struct UbKernelParams {
   int N, Hs, Ws, H, W;
   int Cout, tail;
-  int dbg;   // timing experiments (NSM_UB_DBG bit mask, results wrong): 1 no halo math, 2 no mid epilogue math, 4 no final
+  int dbg;   // NSM_UB_DBG=64: cycle counters of one worker warp (nsm_upblock_prof)
   int tiles_x, tiles_y, total_tiles;
   int sbw, sbh;                       // source box in pixels
   uint32_t off_src, off_b, off_vec, off_taps, off_bar;
@@ -148,9 +148,6 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.total_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // tiles of this CTA
-  // Every CTA streams the SAME weight tiles; in lockstep all 148 SMs would ask the same L2 lines at the same time (one
-  // slice per line serves them one after the other).  Rotating the tap order per CTA spreads the requests over nine tiles.
-  const int tap_rot = (p.dbg & 8) ? 0 : int(blockIdx.x % 9);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmS0); tma_prefetch_desc(&tmW3a); tma_prefetch_desc(&tmW1a);
@@ -201,11 +198,9 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       };
       for (int j = 0; j < nt; ++j) {
         for (int c = 0; c < NCH; ++c)
-          for (int ti = 0; ti < 9; ++ti) {
-            const int tap = (ti + tap_rot) % 9;
+          for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[stage], phase ^ 1);
             uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
-            if (p.dbg & 16) { mbar_arrive(&b_full[stage]); advance(); continue; }
             mbar_expect_tx(&b_full[stage], NP * CMID * 128);
             tma_load_2d(sb, &tmW3a, &b_full[stage], tap * CMID + c * 64, 0);
             if (NP == 2) tma_load_2d(sb + CMID * 128, &tmW3b, &b_full[stage], tap * CMID + c * 64, 0);
@@ -301,15 +296,14 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
           mbar_wait(&halo_full[hb], (q / p.halo_bufs) & 1);
           tc_fence_after();
           const uint32_t halo = sbase + uint32_t(hb * NP) * kHaloPlaneBytes;
-          for (int ti = 0; ti < 9; ++ti) {
-            const int tap = (ti + tap_rot) % 9;
+          for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
             const uint32_t a0 = halo + uint32_t((tap / 3) * kHaloW + tap % 3) * 128u;
             const uint32_t b0 = sbase + p.off_b + stage * p.b_stage_bytes;
 #pragma unroll
-            for (int k = 0; k < ((p.dbg & 32) ? 0 : 4); ++k) {
-              const uint32_t accum = (c | ti | k) != 0 ? 1u : 0u;
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t accum = (c | tap | k) != 0 ? 1u : 0u;
               umma_bf16(tm_acc1, make_desc_sw128(a0 + k * 32, 16, kHaloW * 128),
                         make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc1, accum);
               if (NP == 2)   // both cross terms as one e4m3 MMA of K = 32 (8-bit cross planes)
@@ -370,7 +364,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       mbar_wait(&src_full[sb], (uint32_t(q) / p.src_bufs) & 1);
       UB_T(0);
       const int cg = wt & 7, slot = wt >> 3;
-      if (slot < kStrips * kHaloW && !(p.dbg & 1)) {
+      if (slot < kStrips * kHaloW) {
         const int hx = slot % kHaloW, strip = slot / kHaloW;
         const float cw0 = tb->colw[hx][0], cw1 = tb->colw[hx][1], cw2 = tb->colw[hx][2];
         const int px0 = tb->colp[hx];
@@ -448,7 +442,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       UB_T(3);
       constexpr int CW = CMID / 4;   // columns per warp
 #pragma unroll
-      for (int g = 0; g < ((p.dbg & 2) ? 0 : CW / 16); ++g) {
+      for (int g = 0; g < CW / 16; ++g) {
         const int col = cs * CW + g * 16;
         uint32_t r0[16], r1[16];
         tmem_ld_32x16(tm_acc1 + lane_base + col, r0);
@@ -497,7 +491,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
 
     // ---- 1x1 accumulator -> output ----
     auto final_epilogue = [&](int j, const TileCoord& t) {
-      const bool active = cs * 16 < p.Cout && !(p.dbg & 4);
+      const bool active = cs * 16 < p.Cout;
       const int col = cs * 16;
       const int y = t.y0 + ly, x = t.x0 + lx;
       const bool inside = active && y < p.H && x < p.W;
