@@ -55,7 +55,9 @@ static std::atomic<int> g_fused_override{-1};   // nsm_unet_set_fused_decoder: -
 static bool fused_decoder(int mode) {
   static const bool off = getenv("NSM_NO_FUSED") != nullptr;
   const int ov = g_fused_override.load(std::memory_order_relaxed);
-  return (ov < 0 ? !off : ov != 0) && (mode == NSM_MODE_BF16 || mode == NSM_MODE_FP32);
+  // (the fp32-mode blocks consume the 8-bit-cross form of the 3x3 weights: NSM_NO_X8 implies the stage-by-stage decoder)
+  return (ov < 0 ? !off : ov != 0) &&
+         (mode == NSM_MODE_BF16 || (mode == NSM_MODE_FP32 && decoder3x3_fmt(mode) == kFmtF16X8));
 }
 
 static PackedLayout packed_layout(int mode) {
