@@ -146,7 +146,10 @@ struct GemmCfg {
 // (#MMAs) * 2^-24 (measured: ~1e-4 relative after K = 9216).  The K loop is therefore cut into chunks of at most
 // kChunkKB k-blocks; every chunk accumulates from zero in TMEM and the epilogue warps add the chunk results into
 // fp32 registers with round-to-nearest.
-constexpr int kChunkKBDefault = 16;
+// Default 32 (round 2): with the cross terms in their own accumulator the measured output error no longer depends on the
+// chunk length up to 64 (1080p 3.6e-5, 3840x2160 4.2e-5 at 16 / 24 / 32; 5.0e-5 at 48 / 64; 5.3e-5 unchunked), while every drain
+// of the single-buffered 256-wide accumulator stalls the issuer: conv6 / conv7 3x3 0.879 / 0.917 -> 0.840 / 0.885 ms.
+constexpr int kChunkKBDefault = 32;
 constexpr int kConvThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two column halves x four lane quarters)
 
 template <int TW, int TH>
