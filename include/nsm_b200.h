@@ -158,7 +158,7 @@ int nsm_unet_fused_decoder(void);
  * the environment default */
 int nsm_unet_set_fused_decoder(int on);
 /* debugging (NSM_UB_DBG=64): cycle counters of one worker warp of the fused block kernel, read and cleared */
-int nsm_upblock_prof(unsigned long long* out16);
+int nsm_upblock_prof(unsigned long long* out32);
 
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) then F.interpolate(size=(hd,wd)) -- Unetmodel.py:51-60,
  * 118-141 */

@@ -51,7 +51,8 @@ struct UbKernelParams {
   int sbw, sbh;                       // source box in pixels
   uint32_t off_src, off_b, off_vec, off_taps, off_bar;
   uint32_t src_plane_bytes, b_stage_bytes, b_stages;
-  uint32_t halo_bufs, src_bufs;       // ring depths (1 or 2) of the halo tiles and of the staged source boxes
+  uint32_t halo_bufs, src_bufs;       // ring depths of the halo tiles (<= 4) and of the staged source boxes (<= 2)
+  uint32_t acc1_bufs;                 // 2: the 3x3 accumulator is double-buffered in TMEM, the MMAs run one tile ahead
   uint32_t tm_acc2, tm_a2, tmem_cols;  // TMEM column offsets
   uint32_t idesc1, idesc2w, idesc2c;
   const float *bias3, *scale3, *shift3, *bias1, *scale1, *shift1, *w10, *b10;
@@ -62,15 +63,18 @@ struct UbKernelParams {
 
 constexpr int kStrips = kHaloH / 3;   // 3-row strips of the halo
 constexpr int kStripRows = 6;         // source rows one strip may touch (host-checked)
+constexpr int kTabs = 4;              // interpolation tables in flight (one per tile, shared by its channel chunks)
 struct JobTab {
   float colw[kHaloW][4];
   float roww[kHaloH][kStripRows];
   int colp[kHaloW];
   int strip_r0[kStrips], strip_rn[kStrips];
+  int row_rmin[kHaloH];        // scratch of the preparing warp: per halo row first source row (-1: outside the image) ...
+  float row_w[kHaloH][4];      // ... and its three vertical weights
 };
 
 // cycle counters of block 0's worker warp 0 (NSM_UB_DBG bit 64; read with nsm_upblock_prof): where a worker's time goes
-__device__ unsigned long long g_ub_prof[16];   // [tail][phase]
+__device__ unsigned long long g_ub_prof[32];   // [tail][worker phases 0-7 | MMA-thread phases 8-15]
 #define UB_T(i) do { if (prof) { const long long c_ = clock64(); acc_[i] += c_ - t_; t_ = c_; } } while (0)
 
 struct TileCoord {
@@ -129,22 +133,22 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
   const uint32_t sbase = smem_u32(smem);
   // halo ring at offset 0: buffer b, plane pl at (b * NP + pl) * kHaloPlaneBytes
   float* vec = reinterpret_cast<float*>(smem + p.off_vec);
-  JobTab* tabs = reinterpret_cast<JobTab*>(smem + p.off_taps);   // [2]
+  JobTab* tabs = reinterpret_cast<JobTab*>(smem + p.off_taps);   // [kTabs]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* b_full = bars;                 // [b_stages]
   uint64_t* b_empty = bars + 8;            // [b_stages]
-  uint64_t* halo_full = bars + 16;         // [2]
-  uint64_t* halo_empty = bars + 18;        // [2]
-  uint64_t* src_full = bars + 20;          // [2]
-  uint64_t* src_empty = bars + 22;         // [2]
-  uint64_t* acc1_full = bars + 24;
-  uint64_t* acc1_empty = bars + 25;
-  uint64_t* a2_full = bars + 26;
-  uint64_t* acc2_full = bars + 27;
-  uint64_t* acc2_empty = bars + 28;
-  uint64_t* tab_full = bars + 29;          // [2]
-  uint64_t* tab_empty = bars + 31;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
+  uint64_t* halo_full = bars + 16;         // [4]
+  uint64_t* halo_empty = bars + 20;        // [4]
+  uint64_t* src_full = bars + 24;          // [2]
+  uint64_t* src_empty = bars + 26;         // [2]
+  uint64_t* acc1_full = bars + 28;         // [2]
+  uint64_t* acc1_empty = bars + 30;        // [2]
+  uint64_t* a2_full = bars + 32;
+  uint64_t* acc2_full = bars + 33;
+  uint64_t* acc2_empty = bars + 34;
+  uint64_t* tab_full = bars + 35;          // [kTabs]
+  uint64_t* tab_empty = bars + 39;         // [kTabs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 43);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.total_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // tiles of this CTA
@@ -156,18 +160,22 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(&halo_full[b], kWorkers);
       mbar_init(&halo_empty[b], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&src_full[b], 1);
       mbar_init(&src_empty[b], kWorkers);
+    }
+    for (int b = 0; b < kTabs; ++b) {
       mbar_init(&tab_full[b], 1);
       mbar_init(&tab_empty[b], kWorkers);
     }
-    mbar_init(acc1_full, 1);
-    mbar_init(acc1_empty, kWorkers);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc1_full[b], 1);
+      mbar_init(&acc1_empty[b], kWorkers);
+    }
     mbar_init(a2_full, kWorkers);
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, kWorkers);
@@ -187,7 +195,12 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_acc1 = tmem_base, tm_acc2 = tmem_base + p.tm_acc2, tm_a2 = tmem_base + p.tm_a2;
+  const uint32_t tm_acc2 = tmem_base + p.tm_acc2, tm_a2 = tmem_base + p.tm_a2;
+  const bool db = p.acc1_bufs == 2;
+  // 3x3 accumulator of tile j (double-buffered where tensor memory allows) and the phase of its barriers
+  auto tm_acc1_of = [&](int j) { return tmem_base + (db ? uint32_t(j & 1) * uint32_t(NP * CMID) : 0u); };
+  auto acc1_slot = [&](int j) { return db ? (j & 1) : 0; };
+  auto acc1_use = [&](int j) { return uint32_t(db ? (j >> 1) : j); };
 
   if (warp == 0) {
     // ===================== weight producer: 3x3 tiles (chunk, tap), then the 1x1 tiles (chunk) =====================
@@ -196,7 +209,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       auto advance = [&]() {
         if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
       };
-      for (int j = 0; j < nt; ++j) {
+      auto w3_tiles = [&]() {
         for (int c = 0; c < NCH; ++c)
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[stage], phase ^ 1);
@@ -206,6 +219,8 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
             if (NP == 2) tma_load_2d(sb + CMID * 128, &tmW3b, &b_full[stage], tap * CMID + c * 64, 0);
             advance();
           }
+      };
+      auto w1_tiles = [&]() {
         for (int c = 0; c < NCH; ++c) {
           mbar_wait(&b_empty[stage], phase ^ 1);
           uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
@@ -214,62 +229,85 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
           if (NP == 2) tma_load_2d(sb + p.Cout * 128, &tmW1b, &b_full[stage], c * 64, 0);   // lo rows right after hi rows
           advance();
         }
+      };
+      // same order as the MMA thread consumes them: with a double-buffered 3x3 accumulator the 3x3 GEMM of tile j+1 is
+      // issued before the 1x1 GEMM of tile j
+      if (db) w3_tiles();
+      for (int j = 0; j < nt; ++j) {
+        if (db) {
+          if (j + 1 < nt) w3_tiles();
+        } else {
+          w3_tiles();
+        }
+        w1_tiles();
       }
     }
   } else if (warp == 2) {
     // ===================== job preparation (runs ahead of the workers): interpolation table + source box =====================
-    // Per (tile, chunk) job: lanes 0-9 the halo columns' horizontal taps, lanes 16-21 the 3-row strips' vertical taps
-    // (composite_taps: a few float divisions each -- off the workers' critical path here), lane 0 the TMA load of the source
-    // box.  Tables are double-buffered (tab_full / tab_empty), source boxes ring through src_bufs buffers.
+    // Per tile: lanes 0-9 the halo columns' horizontal taps, lanes 10-27 the halo rows' vertical taps (one composite_taps =
+    // a few float divisions per lane, off the workers' critical path here), lanes 0-5 the 3-row strips' source-row windows;
+    // per (tile, chunk) job: lane 0 the TMA load of the source box.  Tables ring through kTabs buffers (tab_full / tab_empty),
+    // source boxes through src_bufs buffers.
     for (int j = 0, q = 0; j < nt; ++j) {
       const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
       int sy0, sx0;
       ub_src_origin(p, t, sy0, sx0);
-      for (int c = 0; c < NCH; ++c, ++q) {
-        JobTab* tb = tabs + (q & 1);
-        mbar_wait(&tab_empty[q & 1], ((q >> 1) & 1) ^ 1);
-        if (lane < kHaloW) {
-          const int gx = t.x0 - 1 + lane;
-          Tap3 tp;
-          tp.rmin = sx0; tp.w[0] = tp.w[1] = tp.w[2] = 0.f;
-          if (gx >= 0 && gx < p.W) tp = composite_taps(gx, p.Ws, p.W);
-          tb->colp[lane] = tp.rmin - sx0;
-          tb->colw[lane][0] = tp.w[0]; tb->colw[lane][1] = tp.w[1]; tb->colw[lane][2] = tp.w[2];
-        } else if (lane >= 16 && lane < 16 + kStrips) {
-          const int s = lane - 16;
-          int r0 = -1, rn = 0;
-          float wv[3][kStripRows];
+      // ---- the tile's table (one composite_taps per lane: 10 columns, 18 rows), then the strips' row windows
+      JobTab* tb = tabs + (j % kTabs);
+      mbar_wait(&tab_empty[j % kTabs], ((j / kTabs) & 1) ^ 1);
+      if (lane < kHaloW) {
+        const int gx = t.x0 - 1 + lane;
+        Tap3 tp;
+        tp.rmin = sx0; tp.w[0] = tp.w[1] = tp.w[2] = 0.f;
+        if (gx >= 0 && gx < p.W) tp = composite_taps(gx, p.Ws, p.W);
+        tb->colp[lane] = tp.rmin - sx0;
+        tb->colw[lane][0] = tp.w[0]; tb->colw[lane][1] = tp.w[1]; tb->colw[lane][2] = tp.w[2];
+      } else if (lane < kHaloW + kHaloH) {
+        const int r = lane - kHaloW, gy = t.y0 - 1 + r;
+        Tap3 tp;
+        tp.rmin = -1; tp.w[0] = tp.w[1] = tp.w[2] = 0.f;
+        if (gy >= 0 && gy < p.H) tp = composite_taps(gy, p.Hs, p.H);
+        tb->row_rmin[r] = tp.rmin;
+        tb->row_w[r][0] = tp.w[0]; tb->row_w[r][1] = tp.w[1]; tb->row_w[r][2] = tp.w[2];
+      }
+      __syncwarp();
+      if (lane < kStrips) {
+        const int s = lane;
+        int r0 = -1, rn = 0;
+        float wv[3][kStripRows];
 #pragma unroll
-          for (int rr = 0; rr < 3; ++rr)
+        for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
-            for (int k = 0; k < kStripRows; ++k) wv[rr][k] = 0.f;
+          for (int k = 0; k < kStripRows; ++k) wv[rr][k] = 0.f;
 #pragma unroll
-          for (int rr = 0; rr < 3; ++rr) {
-            const int gy = t.y0 - 1 + 3 * s + rr;
-            if (gy < 0 || gy >= p.H) continue;
-            const Tap3 tp = composite_taps(gy, p.Hs, p.H);
-            if (r0 < 0) r0 = tp.rmin;
+        for (int rr = 0; rr < 3; ++rr) {
+          const int rmin = tb->row_rmin[3 * s + rr];
+          if (rmin < 0) continue;
+          if (r0 < 0) r0 = rmin;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const int k = tp.rmin - r0 + i;   // < kStripRows (checked on the host for every strip of the launch)
-              if (tp.w[i] != 0.f && k < kStripRows) {
+          for (int i = 0; i < 3; ++i) {
+            const float wi = tb->row_w[3 * s + rr][i];
+            const int k = rmin - r0 + i;   // < kStripRows (checked on the host for every strip of the launch)
+            if (wi != 0.f && k < kStripRows) {
 #pragma unroll
-                for (int kk = 0; kk < kStripRows; ++kk)
-                  if (kk == k) wv[rr][kk] = tp.w[i];
-                if (k + 1 > rn) rn = k + 1;
-              }
+              for (int kk = 0; kk < kStripRows; ++kk)
+                if (kk == k) wv[rr][kk] = wi;
+              if (k + 1 > rn) rn = k + 1;
             }
           }
-          tb->strip_r0[s] = r0 < 0 ? 0 : r0 - sy0;
-          tb->strip_rn[s] = rn;
-#pragma unroll
-          for (int rr = 0; rr < 3; ++rr)
-#pragma unroll
-            for (int k = 0; k < kStripRows; ++k) tb->roww[3 * s + rr][k] = wv[rr][k];
         }
-        __syncwarp();
+        tb->strip_r0[s] = r0 < 0 ? 0 : r0 - sy0;
+        tb->strip_rn[s] = rn;
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int k = 0; k < kStripRows; ++k) tb->roww[3 * s + rr][k] = wv[rr][k];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tab_full[j % kTabs]);   // (mbarrier arrive has release semantics for the table writes above)
+      // ---- the source boxes of the tile's chunks
+      for (int c = 0; c < NCH; ++c, ++q) {
         if (lane == 0) {
-          mbar_arrive(&tab_full[q & 1]);   // (mbarrier arrive has release semantics for the table writes above)
           const uint32_t sb = uint32_t(q) % p.src_bufs, use = uint32_t(q) / p.src_bufs;
           uint8_t* dst = smem + p.off_src + sb * NP * p.src_plane_bytes;
           mbar_wait(&src_empty[sb], (use & 1) ^ 1);
@@ -287,42 +325,57 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       auto advance = [&]() {
         if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
       };
-      for (int j = 0; j < nt; ++j) {
-        // ---- GEMM 1: 3x3 convolution out of the halo tiles ----
-        mbar_wait(acc1_empty, (j & 1) ^ 1);
+      const bool prof = (p.dbg & 64) && blockIdx.x == 0;
+      long long acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_ = clock64();
+      // ---- GEMM 1: 3x3 convolution of tile j out of its halo tiles ----
+      auto gemm1 = [&](int j) {
+        UB_T(7);
+        mbar_wait(&acc1_empty[acc1_slot(j)], (acc1_use(j) & 1) ^ 1);
         tc_fence_after();
+        UB_T(0);
+        const uint32_t tm_acc1 = tm_acc1_of(j);
         for (int c = 0; c < NCH; ++c) {
           const uint32_t q = uint32_t(j * NCH + c), hb = q % p.halo_bufs;
           mbar_wait(&halo_full[hb], (q / p.halo_bufs) & 1);
           tc_fence_after();
+          UB_T(1);
           const uint32_t halo = sbase + uint32_t(hb * NP) * kHaloPlaneBytes;
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
+            UB_T(2);
             const uint32_t a0 = halo + uint32_t((tap / 3) * kHaloW + tap % 3) * 128u;
+            const uint32_t asbo = uint32_t(kHaloW * 128);
             const uint32_t b0 = sbase + p.off_b + stage * p.b_stage_bytes;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t accum = (c | tap | k) != 0 ? 1u : 0u;
-              umma_bf16(tm_acc1, make_desc_sw128(a0 + k * 32, 16, kHaloW * 128),
+              umma_bf16(tm_acc1, make_desc_sw128(a0 + k * 32, 16, asbo),
                         make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc1, accum);
               if (NP == 2)   // both cross terms as one e4m3 MMA of K = 32 (8-bit cross planes)
-                umma_f8(tm_acc1 + CMID, make_desc_sw128(a0 + kHaloPlaneBytes + k * 32, 16, kHaloW * 128),
+                umma_f8(tm_acc1 + CMID, make_desc_sw128(a0 + kHaloPlaneBytes + k * 32, 16, asbo),
                         make_desc_sw128(b0 + CMID * 128 + k * 32, 16, 1024), p.idesc1, accum);
             }
             umma_commit(&b_empty[stage]);
             advance();
+            UB_T(3);
           }
           umma_commit(&halo_empty[hb]);
         }
-        umma_commit(acc1_full);
-        // ---- GEMM 2: 1x1 convolution, A from tensor memory ----
+        umma_commit(&acc1_full[acc1_slot(j)]);
+      };
+      // ---- GEMM 2: 1x1 convolution of tile j, A from tensor memory ----
+      auto gemm2 = [&](int j) {
+        UB_T(7);
         mbar_wait(a2_full, j & 1);
+        UB_T(4);
         mbar_wait(acc2_empty, (j & 1) ^ 1);
         tc_fence_after();
+        UB_T(5);
         for (int c = 0; c < NCH; ++c) {
           mbar_wait(&b_full[stage], phase);
           tc_fence_after();
+          UB_T(2);
           const uint32_t b0 = sbase + p.off_b + stage * p.b_stage_bytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -337,9 +390,23 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
           }
           umma_commit(&b_empty[stage]);
           advance();
+          UB_T(6);
         }
         umma_commit(acc2_full);
+      };
+      // Double-buffered 3x3 accumulator: the 3x3 GEMM of tile j+1 is issued BEFORE this thread waits for the workers' 1x1
+      // operand of tile j, so the tensor pipe keeps working through the workers' accumulator -> operand pass.
+      if (db) gemm1(0);
+      for (int j = 0; j < nt; ++j) {
+        if (db) {
+          if (j + 1 < nt) gemm1(j + 1);
+        } else {
+          gemm1(j);
+        }
+        gemm2(j);
       }
+      if (prof)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_ub_prof[(p.tail ? 16 : 0) + 8 + i], (unsigned long long)acc_[i]);
     }
   } else if (warp >= 4) {
     // ===================== workers: halo interpolation, both epilogues =====================
@@ -357,8 +424,9 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
     // column and three horizontal weights, per 3-row strip the first source row and row count, per halo row its weights on
     // the strip's source rows.  Rows / columns outside the image have all-zero weights = the convolution's zero padding.
     auto do_job = [&](int q) {
-      JobTab* tb = tabs + (q & 1);
-      mbar_wait(&tab_full[q & 1], (q >> 1) & 1);
+      const int jt = q / NCH;                      // the job's tile: its table is shared by the tile's chunks
+      JobTab* tb = tabs + (jt % kTabs);
+      mbar_wait(&tab_full[jt % kTabs], (jt / kTabs) & 1);
       const uint32_t hb = uint32_t(q) % p.halo_bufs, sb = uint32_t(q) % p.src_bufs;
       mbar_wait(&halo_empty[hb], ((uint32_t(q) / p.halo_bufs) & 1) ^ 1);   // the MMAs of the buffer's previous use have read it
       mbar_wait(&src_full[sb], (uint32_t(q) / p.src_bufs) & 1);
@@ -430,15 +498,16 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       if (lane == 0) {
         mbar_arrive(&halo_full[hb]);
         mbar_arrive(&src_empty[sb]);
-        mbar_arrive(&tab_empty[q & 1]);
+        if (q - jt * NCH == NCH - 1) mbar_arrive(&tab_empty[jt % kTabs]);   // the tile's last chunk is done with the table
       }
       UB_T(2);
     };
 
     // ---- 3x3 accumulator -> A operand of the 1x1 GEMM in tensor memory ----
     auto mid_epilogue = [&](int j) {
-      mbar_wait(acc1_full, j & 1);
+      mbar_wait(&acc1_full[acc1_slot(j)], acc1_use(j) & 1);
       tc_fence_after();
+      const uint32_t tm_acc1 = tm_acc1_of(j);
       UB_T(3);
       constexpr int CW = CMID / 4;   // columns per warp
 #pragma unroll
@@ -483,7 +552,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(acc1_empty);   // the 3x3 accumulator may be overwritten by the next tile
+        mbar_arrive(&acc1_empty[acc1_slot(j)]);   // this 3x3 accumulator may be overwritten (tile j + acc1_bufs)
         mbar_arrive(a2_full);      // the 1x1 GEMM's A operand is in place
       }
       UB_T(4);
@@ -609,21 +678,35 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       UB_T(7);
     };
 
-    // Program order of a worker warp: the halo jobs of tile j+1 are interleaved with the epilogues of tile j so that each
-    // job's source box (single-buffered) is in flight while an epilogue runs, and the 3x3 MMAs of tile j+1 start as soon
-    // as the 3x3 accumulator of tile j has been drained.
+    // Program order of a worker warp.  Single 3x3 accumulator (fp32 mode, 128 channels: tensor memory is full): the halo jobs
+    // of tile j+1 are interleaved with the epilogues of tile j, and the 3x3 MMAs of tile j+1 start as soon as the accumulator
+    // of tile j has been drained.  Double-buffered accumulator: halo tiles are prepared TWO tiles ahead (2 * NCH buffers), so
+    // that the MMA thread can run the 3x3 GEMM of tile j+1 while the workers are still turning tile j's accumulator into the
+    // 1x1 operand; the jobs of tile j+2 sit between the two epilogues of tile j (the 1x1 GEMM of tile j executes behind the 3x3
+    // GEMM of tile j+1 in the tensor pipe, the workers use that time).
     int q_next = 0;
-    for (; q_next < NCH && q_next < nt * NCH; ++q_next) do_job(q_next);
-    for (int j = 0; j < nt; ++j) {
-      const bool more = j + 1 < nt;
-      const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
-      if (more) do_job(q_next++);              // first chunk of the next tile: overlaps this tile's 3x3 MMAs
-      mid_epilogue(j);
-      if (more && NCH > 1) do_job(q_next++);   // second chunk: its halo buffer was released by this tile's MMAs
-      final_epilogue(j, t);
+    if (db) {
+      for (; q_next < 2 * NCH && q_next < nt * NCH; ++q_next) do_job(q_next);
+      for (int j = 0; j < nt; ++j) {
+        const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
+        mid_epilogue(j);
+        if (j + 2 < nt)
+          for (int c = 0; c < NCH; ++c) do_job(q_next++);
+        final_epilogue(j, t);
+      }
+    } else {
+      for (; q_next < NCH && q_next < nt * NCH; ++q_next) do_job(q_next);
+      for (int j = 0; j < nt; ++j) {
+        const bool more = j + 1 < nt;
+        const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
+        if (more) do_job(q_next++);              // first chunk of the next tile: overlaps this tile's 3x3 MMAs
+        mid_epilogue(j);
+        if (more && NCH > 1) do_job(q_next++);   // second chunk: its halo buffer was released by this tile's MMAs
+        final_epilogue(j, t);
+      }
     }
     if (prof)
-      for (int i = 0; i < 8; ++i) atomicAdd(&g_ub_prof[(p.tail ? 8 : 0) + i], (unsigned long long)acc_[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_ub_prof[(p.tail ? 16 : 0) + i], (unsigned long long)acc_[i]);
   }
 
   tc_fence_before();
@@ -700,7 +783,7 @@ int launch_ub(const CUtensorMap* maps, const UbKernelParams& kp, int grid, size_
 // debugging: read and clear the cycle counters (2 x 8 values, block with skip / block with tail: job wait / math / publish, mid wait / math, final prefetch /
 // wait / math)
 int upblock_prof(unsigned long long* out) {
-  unsigned long long z[16] = {0};
+  unsigned long long z[32] = {0};
   if (cudaMemcpyFromSymbol(out, g_ub_prof, sizeof(z)) != cudaSuccess) return 1;
   return cudaMemcpyToSymbol(g_ub_prof, z, sizeof(z)) != cudaSuccess;
 }
@@ -750,19 +833,25 @@ int upblock_launch(const UpBlockArgs& a, cudaStream_t st) {
   // configuration picked by measurement (NSM_UB_RINGS=<halo><src> overrides, e.g. 21, 12)
   kp.src_plane_bytes = uint32_t(up(size_t(kp.sbw) * kp.sbh * 128, 128));
   const size_t stage_bytes = size_t(NP) * a.Cmid * 128;
-  const size_t fixed_tail = up(size_t(3 * a.Cmid + 3 * a.Cout + 68) * 4, 16) + 2 * sizeof(JobTab) + 256;
+  const size_t fixed_tail = up(size_t(3 * a.Cmid + 3 * a.Cout + 68) * 4, 16) + kTabs * sizeof(JobTab) + 384;
   const size_t budget = size_t(227) * 1024 - 1024;
   auto fits = [&](int hb, int sb, int stages) {
     return up(size_t(hb) * NP * kHaloPlaneBytes + size_t(sb) * NP * kp.src_plane_bytes, 1024) + stages * stage_bytes +
                fixed_tail <= budget;
   };
-  int hb = 2, sb = 2;
-  if (!fits(2, 2, 3)) sb = 1;   // measured (profiles/README.md): one halo buffer + two source buffers is slower than 2 + 1
+  // 3x3 accumulator double-buffered when [2 x 3x3 | 1x1 | operand] fit the 512 TMEM columns (everything but fp32 / 128 ch)
+  const int nch = a.Cmid / 64;
+  const uint32_t tm_need2 = uint32_t(2 * NP * a.Cmid + NP * a.Cout + NP * a.Cmid / 2);
+  static const bool db_off = getenv("NSM_UB_NO_DB") != nullptr;
+  bool dbuf = tm_need2 <= 512 && !db_off;
+  int hb = dbuf ? 2 * nch : 2, sb = 2;
+  if (dbuf && !fits(hb, 1, 2)) { dbuf = false; hb = 2; }
+  if (!fits(hb, 2, 3)) sb = 1;   // measured (profiles/README.md): one halo buffer + two source buffers is slower than 2 + 1
   {
     static const int force = getenv("NSM_UB_RINGS") ? atoi(getenv("NSM_UB_RINGS")) : 0;
-    if (force >= 11 && force <= 22 && force % 10 >= 1 && force % 10 <= 2) { hb = force / 10; sb = force % 10; }
+    if (!dbuf && force >= 11 && force <= 22 && force % 10 >= 1 && force % 10 <= 2) { hb = force / 10; sb = force % 10; }
   }
-  kp.halo_bufs = uint32_t(hb); kp.src_bufs = uint32_t(sb);
+  kp.halo_bufs = uint32_t(hb); kp.src_bufs = uint32_t(sb); kp.acc1_bufs = dbuf ? 2u : 1u;
   size_t off = size_t(hb) * NP * kHaloPlaneBytes;
   kp.off_src = uint32_t(off = up(off, 128));
   off += size_t(sb) * NP * kp.src_plane_bytes;
@@ -783,12 +872,12 @@ int upblock_launch(const UpBlockArgs& a, cudaStream_t st) {
   kp.off_vec = uint32_t(off = up(off, 16));
   off += up(size_t(3 * a.Cmid + 3 * a.Cout + 68) * 4, 16);
   kp.off_taps = uint32_t(off);
-  off += 2 * sizeof(JobTab);
+  off += kTabs * sizeof(JobTab);
   kp.off_bar = uint32_t(off = up(off, 8));
-  off += 256;
+  off += 384;
   const size_t smem_bytes = off + 1024;
   // tensor memory: [3x3 main | 3x3 cross] [1x1 main | 1x1 cross] [A2 hi | A2 lo]
-  kp.tm_acc2 = uint32_t(NP * a.Cmid);
+  kp.tm_acc2 = uint32_t(kp.acc1_bufs * NP * a.Cmid);
   kp.tm_a2 = kp.tm_acc2 + uint32_t(NP * a.Cout);
   const uint32_t need = kp.tm_a2 + uint32_t(NP * a.Cmid / 2);
   kp.tmem_cols = need <= 128 ? 128 : (need <= 256 ? 256 : 512);
