@@ -146,10 +146,12 @@ struct GemmCfg {
 // (#MMAs) * 2^-24 (measured: ~1e-4 relative after K = 9216).  The K loop is therefore cut into chunks of at most
 // kChunkKB k-blocks; every chunk accumulates from zero in TMEM and the epilogue warps add the chunk results into
 // fp32 registers with round-to-nearest.
-// Default 32 (round 2): with the cross terms in their own accumulator the measured output error no longer depends on the
-// chunk length up to 64 (1080p 3.6e-5, 3840x2160 4.2e-5 at 16 / 24 / 32; 5.0e-5 at 48 / 64; 5.3e-5 unchunked), while every drain
-// of the single-buffered 256-wide accumulator stalls the issuer: conv6 / conv7 3x3 0.879 / 0.917 -> 0.840 / 0.885 ms.
-constexpr int kChunkKBDefault = 32;
+// Default 24 (round 2; 16 in round 1).  Every drain of the single-buffered 256-wide accumulator stalls the MMA issuer: conv6 /
+// conv7 3x3 take 0.879 / 0.917 ms at 16, 0.859 / 0.882 at 24, 0.840 / 0.885 at 32.  With the cross terms in their own
+// accumulator the output error depends only weakly on the chunk length (1080p frame of the parity test: 3.6e-5 at 16 / 24 / 32,
+// 5.3e-5 unchunked; a 257 x 259 frame with other BatchNorm draws: 6.1e-5 at 16, 7.4e-5 at 32) -- 24 keeps most of the speed and
+// most of the margin to the 1e-4 bound.
+constexpr int kChunkKBDefault = 24;
 constexpr int kConvThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two column halves x four lane quarters)
 
 template <int TW, int TH>
