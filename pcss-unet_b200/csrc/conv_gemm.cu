@@ -123,14 +123,19 @@ struct ConvKernelParams {
   ConvEpilogue ep;
 };
 
-template <int BN, int NP>
+// EW = epilogue warps: 8 (two column halves x four TMEM lane quarters), or 16 (four column quarters) for the layers with a short
+// K loop.  Those are bound by their epilogue -- ~650 instructions per 32-column group in long dependent chains; with two
+// epilogue warps per scheduler the issue slots are 30 % used (profiles/r02_thin_conv_stalls.txt) -- so they get four warps
+// per scheduler at 96 registers (the bf16 epilogue needs no more; the hi+lo one keeps a quarter of the chunk sums).
+template <int BN, int NP, int EW = 8>
 struct GemmCfg {
   static constexpr int TW = kTileW, TH = kTileH;
+  static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int A_BYTES = 128 * 128;  // 128 pixels x 64 elements (2 B)
   static constexpr int B_BYTES = BN * 128;   // weight tile rows x 64 elements
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
   // 8 epilogue warps x 4 KB staging tiles for the TMA stores of the output (32 pixels x 32 channels x {hi, lo})
-  static constexpr int STAGING_BYTES = 8 * 4096;
+  static constexpr int STAGING_BYTES = EW * 4096;
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STAGING_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -392,15 +397,15 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
   }
 }
 
-template <int BN, int NP>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN, int NP, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                  const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                  const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ ConvKernelParams p) {
-  using Cfg = GemmCfg<BN, NP>;
+  using Cfg = GemmCfg<BN, NP, EW>;
   constexpr int TW = Cfg::TW, TH = Cfg::TH;
   const int it_first = int(blockIdx.x), it_step = int(gridDim.x), it_count = p.total_items;
   extern __shared__ uint8_t smem_raw[];
@@ -413,8 +418,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* empty_bar = bars + Cfg::STAGES;
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;   // [8 epilogue warps][2 slots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
+  uint64_t* res_bar = tempty_bar + 2;   // [EW epilogue warps][2 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * EW);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -444,9 +449,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);
+      mbar_init(&tempty_bar[a], EW);
     }
-    for (int a = 0; a < 16; ++a) mbar_init(&res_bar[a], 1);
+    for (int a = 0; a < 2 * EW; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -545,8 +550,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // warp -> TMEM lane quarter (warp & 3, a hardware restriction) and column half ((warp - 2) >> 2)
-    constexpr int HB = BN / 2;      // columns per epilogue warp
+    // warp -> TMEM lane quarter (warp & 3, a hardware restriction) and column slice ((warp - 2) >> 2: half or quarter)
+    constexpr int HB = BN / (EW / 4);      // columns per epilogue warp
+    static_assert(HB % 32 == 0, "an epilogue warp works on 32-column groups");
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;  // pixel index inside the patch
@@ -964,10 +970,10 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NP>
+template <int BN, int NP, int EW = 8>
 static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, NP>;
-  auto kern = conv_gemm_kernel<BN, NP>;
+  using Cfg = GemmCfg<BN, NP, EW>;
+  auto kern = conv_gemm_kernel<BN, NP, EW>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -977,7 +983,7 @@ static int launch_t(const CUtensorMap* maps, const ConvKernelParams& kp, int gri
     }
     attr_set = true;
   }
-  kern<<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7],
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7],
                                                         maps[8], maps[9], kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -1159,12 +1165,18 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
     return 0;
   }
   const int grid = kp.total_items < num_sms() ? kp.total_items : num_sms();
+  // sixteen epilogue warps for the layers with a short K loop (<= kb16 k-blocks per output tile; NSM_EW16_KB overrides, 0 = off).
+  // The hi+lo kernel at BN = 128 keeps only two 64 KB stages next to 64 KB of staging tiles: there only the shortest loops.
+  static const int kb16_env = getenv("NSM_EW16_KB") ? atoi(getenv("NSM_EW16_KB")) : -1;
+  const int num_kb = s.taps * (s.Cin / kKChunk);
+  const int kb16 = kb16_env >= 0 ? kb16_env : (planes == 1 ? 18 : 4);
+  const bool ew16 = BN >= 128 && num_kb <= kb16;
   if (planes == 1) {
-    if (BN == 256) return launch_t<256, 1>(maps, kp, grid, stream);
-    if (BN == 128) return launch_t<128, 1>(maps, kp, grid, stream);
+    if (BN == 256) return ew16 ? launch_t<256, 1, 16>(maps, kp, grid, stream) : launch_t<256, 1>(maps, kp, grid, stream);
+    if (BN == 128) return ew16 ? launch_t<128, 1, 16>(maps, kp, grid, stream) : launch_t<128, 1>(maps, kp, grid, stream);
     return launch_t<64, 1>(maps, kp, grid, stream);
   }
-  if (BN == 128) return launch_t<128, 2>(maps, kp, grid, stream);
+  if (BN == 128) return ew16 ? launch_t<128, 2, 16>(maps, kp, grid, stream) : launch_t<128, 2>(maps, kp, grid, stream);
   return launch_t<64, 2>(maps, kp, grid, stream);
 }
 
