@@ -46,6 +46,17 @@ extern "C" {
  *   conv10.weight, conv10.bias (Unetmodel.py:63)                                                      */
 #define NSM_UNET_NUM_TENSORS 98
 
+/* Order-independent accumulator slot.  Every cross-block reduction of this library (BatchNorm statistics and backward
+ * sums, loss sums, per-channel input statistics, the gradient norm) adds its per-block fp64 partials as 128-bit
+ * two's-complement fixed-point numbers (value = hi + lo * 2^-64) with integer atomics: the total is bit-identical
+ * from run to run whatever order the blocks arrive in (the reference asks for deterministic kernels, main.py:81-82;
+ * fp64 atomicAdd is not).  `bad` != 0: a non-finite or out-of-range (>= 2^62) partial was added, the slot reads as NaN.
+ * The caller zero-fills slots before the accumulating call; nsm_acc_to_double converts n slots to fp64. */
+typedef struct nsm_acc {
+  unsigned long long lo, hi, bad, pad;
+} nsm_acc;
+int nsm_acc_to_double(const nsm_acc* acc, long long n, double* out /* device */, void* stream);
+
 const char* nsm_last_error(void);
 int nsm_version(void);
 /* kernels launched by this library since load (bench.py: gpu_launches) */
@@ -124,7 +135,7 @@ typedef struct nsm_conv_args {
   const void* residual[2]; /* [N,H,W,Cout] planes or NULL: skip add    Unetmodel.py:125,131,137              */
   void* pool[2];           /* [N,H/2,W/2,Cout] planes or NULL: AvgPool2d(2)               Unetmodel.py:40,43,46 */
   float* out_f32;          /* optional [N,H,W,Cout] fp32: conv + bias before BN */
-  double* stats;           /* optional [2*Cout] fp64, zeroed by the caller: += per-channel sum / sum of squares of the
+  nsm_acc* stats;          /* optional [2*Cout] slots, zeroed by the caller: += per-channel sum / sum of squares of the
                               stored conv+bias output = train-mode BatchNorm statistics (Unetmodel.py:22,27) */
 } nsm_conv_args;
 int nsm_conv_fwd(const nsm_conv_args* a, void* stream);
@@ -169,9 +180,9 @@ int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, voi
  * Objective: nn.L1Loss value + gradient (customLoss.py:96,134,160; pert_loss.py:23,84-90) in one pass.
  *   acc[0] += sum|out-target|   acc[1] += sum_i sum|out-perturbed_i|   acc[2] += #{out<0 or out>1 or NaN}
  *   grad    = coef_l1*sign(out-target) + coef_pert*sum_i sign(out-perturbed_i)        (grad may be NULL)
- * target may be NULL; n_perturbed <= 4.  acc must be zeroed by the caller. */
+ * target may be NULL; n_perturbed <= 4.  acc: three slots, zeroed by the caller. */
 int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
-                        long long numel, float coef_l1, float coef_pert, float* grad, double* acc, void* stream);
+                        long long numel, float coef_l1, float coef_pert, float* grad, nsm_acc* acc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Perceptual term: MultiLayerVGGLoss (customLoss.py:7-90) = weighted L1 between VGG19 features of output and target.
@@ -186,14 +197,14 @@ int nsm_vgg_input_prep(const float* output, const float* target, int B, int H, i
 int nsm_relu_maxpool(const void* in0, const void* in1, int N, int H, int W, int C, int pool, int mode, void* out0,
                      void* out1, void* stream);
 /* customLoss.py:76-80: *acc += sum |nan_to_num(a) - nan_to_num(b)| where a = the first numel_half elements of the
- * planes, b = the next numel_half (nan -> 0, +inf -> 1, -inf -> -1); acc fp64, device, zeroed by the caller */
-int nsm_feature_l1(const void* f0, const void* f1, long long numel_half, int mode, double* acc, void* stream);
+ * planes, b = the next numel_half (nan -> 0, +inf -> 1, -inf -> -1); acc: one slot, device, zeroed by the caller */
+int nsm_feature_l1(const void* f0, const void* f1, long long numel_half, int mode, nsm_acc* acc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Input statistics / standardisation / perturbation
  * --------------------------------------------------------------------------------------------------------- */
 /* calculate_dataset_stats.py:59-79: x [S,C,HW] fp32; means==NULL: sums[c] += sum x, else sums[c] += sum (x-means[c])^2 */
-int nsm_channel_sums(const float* x, long long S, int C, long long HW, const double* means, double* sums,
+int nsm_channel_sums(const float* x, long long S, int C, long long HW, const double* means, nsm_acc* sums /*[C]*/,
                      void* stream);
 /* setdata.py:316: y = (x - mean[c]) / (std[c] + 1e-8) */
 int nsm_standardize(const float* x, float* y, long long S, int C, long long HW, const float* mean,
@@ -211,9 +222,9 @@ int nsm_perturb(const float* x, const float* noise, float* out, int count, long 
  * --------------------------------------------------------------------------------------------------------- */
 /* nn.BatchNorm2d in training mode (Unetmodel.py:22,27): batch statistics, running-stat update, affine + LeakyReLU(0.2)
  * + Dropout2d mask (Unetmodel.py:23-24) (+ skip add :125 / AvgPool2d :40) */
-int nsm_bn_stats(const void* z0, const void* z1, long long P, int C, int mode, double* sums /*[2C], zeroed*/,
+int nsm_bn_stats(const void* z0, const void* z1, long long P, int C, int mode, nsm_acc* sums /*[2C], zeroed*/,
                  void* stream);
-int nsm_bn_finalize(const double* sums, long long P, int C, const float* gamma, const float* beta, float eps,
+int nsm_bn_finalize(const nsm_acc* sums, long long P, int C, const float* gamma, const float* beta, float eps,
                     float momentum, int updates, float* running_mean, float* running_var, float* scale, float* shift,
                     float* save_mean, float* save_invstd, void* stream);
 int nsm_bn_act(const void* z0, const void* z1, int N, int H, int W, int C, int mode, const float* scale,
@@ -222,7 +233,7 @@ int nsm_bn_act(const void* z0, const void* z1, int N, int H, int W, int C, int m
 /* backward of the above: g = dy*mask*LeakyReLU'(.), BatchNorm backward with batch statistics */
 int nsm_bn_bwd(const void* dy0, const void* dy1, const void* z0, const void* z1, int N, int H, int W, int C, int mode,
                const float* scale, const float* shift, const float* mask, const float* mean, const float* invstd,
-               int lrelu, double* sums /*[3C] scratch, zeroed*/, void* dz0, void* dz1, float* dgamma, float* dbeta,
+               int lrelu, nsm_acc* sums /*[3C] scratch, zeroed*/, void* dz0, void* dz1, float* dgamma, float* dbeta,
                float* dbias /*conv bias grad = sum dz, or NULL*/, void* stream);
 /* adjoint of AvgPool2d(2) (+ optional second gradient `a`), plain add, adjoint of one bilinear align_corners resize */
 int nsm_pool_bwd_add(const void* a0, const void* a1, const void* dp0, const void* dp1, void* out0, void* out1, int N,
@@ -255,7 +266,7 @@ int nsm_pad_vector(const float* src, int n, int npad, float fill, int round_bf16
 int nsm_pack_conv_weight_px4(const float* w, int Cout, int Cin, int ksize, int CoutV, int CinV, int dgrad, int mode,
                              void* plane0, void* plane1, void* stream);
 int nsm_px4_reduce_dw(const float* dwv, int Cout, int Cin, int ksize, int CoutV, int CinV, float* dw, void* stream);
-int nsm_fold_channel_sums(const double* in, int nvec, int CV, int groups, int C, double* out, void* stream);
+int nsm_fold_channel_sums(const nsm_acc* in, int nvec, int CV, int groups, int C, nsm_acc* out, void* stream);
 int nsm_tile_vector(const float* src, int n, int rep, int npad, float fill, int round_bf16, float* dst, void* stream);
 /* input / output stages with un-padded tensors: x16 planes [N,h,w,16]; c10 planes [N,h,w/4,64] (pixel po of a group
  * holds its 4 channels at [4*po, 4*po+4), channels 16..63 zero) */
@@ -273,15 +284,17 @@ int nsm_wgrad(const void* dz0, const void* dz1, const void* x0, const void* x1, 
 /* ---------------------------------------------------------------------------------------------------------
  * Optimizer + gradient hygiene (main.py:295-423, :955): non-finite scan, global-norm clip
  * (torch.nn.utils.clip_grad_norm_ semantics) and AdamW over up to 128 tensors in two launches, no host sync.
- *   acc[0] = sum of squared gradients (before clipping), acc[1] = number of NaN/Inf gradient elements; when
+ *   acc = EIGHT doubles on the device: acc[0] = sum of squared gradients (before clipping), acc[1] = number of NaN/Inf
+ *   gradient elements, acc[2] = step counter (below), acc[3] unused, acc[4..7] = one nsm_acc slot of scratch (the sum of
+ *   squares is accumulated order-independently there and copied to acc[0]); when
  *   acc[1] != 0 the update is skipped entirely (GradScaler.step behaviour).  `step` > 0 is the 1-based AdamW step; with
- *   `step` <= 0 the counter lives on the device: acc has THREE doubles, acc[2] = number of updates applied so far (kept
+ *   `step` <= 0 the counter lives on the device: acc[2] = number of updates applied so far (kept
  *   across calls, seeded by the caller), the bias corrections use acc[2] + 1 and acc[2] advances only when the update was
  *   applied -- so a skipped step does not run the bias corrections ahead of the moments (torch AdamW under GradScaler).
  * --------------------------------------------------------------------------------------------------------- */
 int nsm_adamw_clip_step(int count, float* const* params, const float* const* grads, float* const* exp_avg,
                         float* const* exp_avg_sq, const long long* numel, float lr, float beta1, float beta2, float eps,
-                        float weight_decay, float max_norm, int step, double* acc /*[2], or [3] when step <= 0; device*/,
+                        float weight_decay, float max_norm, int step, double* acc /*[8]; device, 32-byte aligned*/,
                         void* stream);
 
 #ifdef __cplusplus

@@ -194,6 +194,10 @@ using namespace nsm;
 
 static inline Planes mk(const void* a, const void* b) { return Planes{{const_cast<void*>(a), const_cast<void*>(b)}}; }
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+// nsm_acc (C ABI) and nsm::Acc (nsm_common.cuh) are the same four 64-bit words
+static_assert(sizeof(nsm_acc) == sizeof(Acc), "nsm_acc layout");
+static inline Acc* A(nsm_acc* a) { return reinterpret_cast<Acc*>(a); }
+static inline const Acc* A(const nsm_acc* a) { return reinterpret_cast<const Acc*>(a); }
 
 #define NSM_TRY(expr)          \
   do {                         \
@@ -708,7 +712,7 @@ int nsm_conv_fwd(const nsm_conv_args* a, void* stream) {
   e.residual = {{const_cast<void*>(a->residual[0]), const_cast<void*>(a->residual[1])}};
   e.pool = {{a->pool[0], a->pool[1]}};
   e.out_f32 = a->out_f32;
-  e.stats = a->stats;
+  e.stats = A(a->stats);
   char nm[64];
   snprintf(nm, sizeof(nm), "conv_gemm k%d %d->%d @%dx%d", a->ksize, a->Cin, a->Cout, a->H, a->W);
   const double px = double(a->N) * a->H * a->W;
@@ -756,14 +760,29 @@ int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, voi
 }
 
 int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
-                        long long numel, float coef_l1, float coef_pert, float* grad, double* acc, void* stream) {
+                        long long numel, float coef_l1, float coef_pert, float* grad, nsm_acc* acc, void* stream) {
   ProfScope ps_("l1_loss", 0.0, double(numel) * 4.0 * (3 + n_perturbed), S(stream));
-  return l1_loss_fwd_bwd(out, target, perturbed, n_perturbed, numel, coef_l1, coef_pert, grad, acc,
+  return l1_loss_fwd_bwd(out, target, perturbed, n_perturbed, numel, coef_l1, coef_pert, grad, A(acc),
                          static_cast<cudaStream_t>(stream));
 }
-int nsm_channel_sums(const float* x, long long S, int C, long long HW, const double* means, double* sums,
+__global__ void acc_to_double_kernel(const Acc* acc, long long n, double* out) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  if (i < n) out[i] = acc_load(acc + i);
+}
+int nsm_acc_to_double(const nsm_acc* acc, long long n, double* out, void* stream) {
+  if (n <= 0) return 0;
+  acc_to_double_kernel<<<unsigned((n + 255) / 256), 256, 0, S(stream)>>>(A(acc), n, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("nsm_acc_to_double launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  count_launch();
+  return 0;
+}
+int nsm_channel_sums(const float* x, long long S, int C, long long HW, const double* means, nsm_acc* sums,
                      void* stream) {
-  return channel_sums(x, S, C, HW, means, sums, static_cast<cudaStream_t>(stream));
+  return channel_sums(x, S, C, HW, means, A(sums), static_cast<cudaStream_t>(stream));
 }
 int nsm_standardize(const float* x, float* y, long long S, int C, long long HW, const float* mean,
                     const float* std, void* stream) {
@@ -776,14 +795,14 @@ int nsm_perturb(const float* x, const float* noise, float* out, int count, long 
 
 // ---------------------------------------------------------------------------------------------- training stages
 
-int nsm_bn_stats(const void* z0, const void* z1, long long P, int C, int mode, double* sums, void* stream) {
+int nsm_bn_stats(const void* z0, const void* z1, long long P, int C, int mode, nsm_acc* sums, void* stream) {
   ProfScope ps_("bn_stats", 0.0, double(P) * C * 2.0 * fmt_planes(mode), S(stream));
-  return bn_stats(mk(z0, z1), P, C, mode, sums, S(stream));
+  return bn_stats(mk(z0, z1), P, C, mode, A(sums), S(stream));
 }
-int nsm_bn_finalize(const double* sums, long long P, int C, const float* gamma, const float* beta, float eps,
+int nsm_bn_finalize(const nsm_acc* sums, long long P, int C, const float* gamma, const float* beta, float eps,
                     float momentum, int updates, float* running_mean, float* running_var, float* scale, float* shift,
                     float* save_mean, float* save_invstd, void* stream) {
-  return bn_finalize(sums, P, C, gamma, beta, eps, momentum, updates, running_mean, running_var, scale, shift, save_mean,
+  return bn_finalize(A(sums), P, C, gamma, beta, eps, momentum, updates, running_mean, running_var, scale, shift, save_mean,
                      save_invstd, S(stream));
 }
 int nsm_bn_act(const void* z0, const void* z1, int N, int H, int W, int C, int mode, const float* scale,
@@ -797,15 +816,15 @@ int nsm_bn_act(const void* z0, const void* z1, int N, int H, int W, int C, int m
 }
 int nsm_bn_bwd(const void* dy0, const void* dy1, const void* z0, const void* z1, int N, int H, int W, int C, int mode,
                const float* scale, const float* shift, const float* mask, const float* mean, const float* invstd,
-               int lrelu, double* sums, void* dz0, void* dz1, float* dgamma, float* dbeta, float* dbias, void* stream) {
+               int lrelu, nsm_acc* sums, void* dz0, void* dz1, float* dgamma, float* dbeta, float* dbias, void* stream) {
   ProfScope ps_("bn_bwd", 0.0, double(N) * H * W * C * 10.0 * fmt_planes(mode), S(stream));
   BnBwdParams p;
   p.dy = mk(dy0, dy1); p.z = mk(z0, z1); p.dz = mk(dz0, dz1);
   p.N = N; p.H = H; p.W = W; p.C = C; p.fmt = mode; p.scale = scale; p.shift = shift; p.mask = mask; p.mean = mean;
-  p.invstd = invstd; p.lrelu = lrelu; p.sums = sums; p.dbias = sums + 2 * C;
+  p.invstd = invstd; p.lrelu = lrelu; p.sums = A(sums); p.dbias = A(sums) + 2 * C;
   NSM_TRY(bn_bwd_reduce(p, S(stream)));
   NSM_TRY(bn_bwd_apply(p, S(stream)));
-  return bn_bwd_finalize(sums, sums + 2 * C, mean, invstd, C, mode == NSM_MODE_BF16, dgamma, dbeta, dbias, S(stream));
+  return bn_bwd_finalize(A(sums), A(sums) + 2 * C, mean, invstd, C, mode == NSM_MODE_BF16, dgamma, dbeta, dbias, S(stream));
 }
 int nsm_pool_bwd_add(const void* a0, const void* a1, const void* dp0, const void* dp1, void* out0, void* out1, int N,
                      int H, int W, int C, int mode, void* stream) {
@@ -870,8 +889,8 @@ int nsm_pack_conv_weight_px4(const float* w, int Cout, int Cin, int ksize, int C
 int nsm_px4_reduce_dw(const float* dwv, int Cout, int Cin, int ksize, int CoutV, int CinV, float* dw, void* stream) {
   return px4_reduce_dw(dwv, Cout, Cin, ksize, CoutV, CinV, dw, S(stream));
 }
-int nsm_fold_channel_sums(const double* in, int nvec, int CV, int groups, int C, double* out, void* stream) {
-  return fold_channel_sums(in, nvec, CV, groups, C, out, S(stream));
+int nsm_fold_channel_sums(const nsm_acc* in, int nvec, int CV, int groups, int C, nsm_acc* out, void* stream) {
+  return fold_channel_sums(A(in), nvec, CV, groups, C, A(out), S(stream));
 }
 int nsm_tile_vector(const float* src, int n, int rep, int npad, float fill, int round_bf16, float* dst, void* stream) {
   return tile_vector(src, n, rep, npad, fill, round_bf16, dst, S(stream));

@@ -578,8 +578,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
       for (int k = 0; k < NCH; ++k) {
         const int c = nb_old * BN + half * HB + 32 * k + lane;
-        if (st1[k] != 0.0) atomicAdd(p.ep.stats + c, st1[k]);
-        if (st2[k] != 0.0) atomicAdd(p.ep.stats + p.Cout + c, st2[k]);
+        if (st1[k] != 0.0) acc_add(p.ep.stats + c, st1[k]);
+        if (st2[k] != 0.0) acc_add(p.ep.stats + p.Cout + c, st2[k]);
         st1[k] = st2[k] = 0.0;
       }
     };
@@ -891,8 +891,8 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 #pragma unroll
       for (int k = 0; k < NG; ++k) {
         const int c = nb_old * BN + half * HB + 32 * k + lane;
-        if (st1[k] != 0.0) atomicAdd(p.ep.stats + c, st1[k]);
-        if (st2[k] != 0.0) atomicAdd(p.ep.stats + p.Cout + c, st2[k]);
+        if (st1[k] != 0.0) acc_add(p.ep.stats + c, st1[k]);
+        if (st2[k] != 0.0) acc_add(p.ep.stats + p.Cout + c, st2[k]);
         st1[k] = st2[k] = 0.0;
       }
     };

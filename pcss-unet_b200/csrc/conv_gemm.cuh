@@ -6,6 +6,8 @@
 
 namespace nsm {
 
+struct Acc;   // order-independent accumulator slot (nsm_common.cuh) = nsm_acc of the C ABI
+
 constexpr int kTileW = 16;   // spatial patch = kTileH x kTileW = 128 output pixels = UMMA M
 constexpr int kTileH = 8;
 constexpr int kKChunk = 64;  // bf16 elements per 128-byte swizzled smem row (one K block)
@@ -26,7 +28,7 @@ struct ConvEpilogue {
   Planes residual;       // [N,H,W,Cout] added after the activation (skip connection) or {nullptr}
   Planes pool;           // [N,H/2,W/2,Cout] AvgPool2d(2) of the output or {nullptr}
   float* out_f32;        // optional fp32 NHWC output (raw accumulators + bias), or nullptr
-  double* stats;         // optional [2*Cout] fp64: += per-channel sum and sum of squares of the stored conv+bias values
+  Acc* stats;            // optional [2*Cout] accumulators: += per-channel sum and sum of squares of the stored conv+bias values
                          // (train-mode BatchNorm statistics fused into the producing convolution)
 };
 

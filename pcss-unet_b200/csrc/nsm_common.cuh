@@ -27,6 +27,47 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Order-independent accumulator (= nsm_acc of the C ABI).  Cross-block reductions (BatchNorm statistics, BatchNorm-backward
+// sums, loss sums, the gradient norm) add their per-block fp64 partials as 128-bit two's-complement FIXED-POINT numbers
+// (LSB 2^-64, |partial| < 2^62) with two integer atomics.  Integer addition is associative, so the total is bit-identical
+// whatever order the blocks arrive in -- an fp64 atomicAdd is not, and made training runs differ from run to run where
+// the reference asks for deterministic kernels (main.py:81-82).  A partial that is NaN / Inf / out of range sets `bad`
+// and the slot reads back as NaN, so non-finite values still surface in the loss and the statistics.
+// ---------------------------------------------------------------------------------------------
+struct Acc {
+  unsigned long long lo, hi, bad, pad;
+};
+static_assert(sizeof(Acc) == 32, "nsm_acc is four 64-bit words");
+
+__device__ __forceinline__ void acc_split(double v, unsigned long long& lo, unsigned long long& hi) {
+  const double f = floor(v);   // v - f is exact in [0, 1] (1 only when v is a tiny negative number: saturates below)
+  lo = __double2ull_rz((v - f) * 18446744073709551616.0);
+  hi = (unsigned long long)__double2ll_rz(f);
+}
+__device__ __forceinline__ void acc_add(Acc* a, double v) {
+  if (!(fabs(v) < 4611686018427387904.0)) {   // NaN, Inf, |v| >= 2^62
+    atomicOr(&a->bad, 1ull);
+    return;
+  }
+  unsigned long long lo, hi;
+  acc_split(v, lo, hi);
+  const unsigned long long old = atomicAdd(&a->lo, lo);
+  hi += (old + lo < lo) ? 1ull : 0ull;   // carry out of the low word: their number depends only on the total
+  if (hi) atomicAdd(&a->hi, hi);
+}
+__device__ __forceinline__ double acc_load(const Acc* a) {
+  if (a->bad) return __longlong_as_double(0x7ff8000000000000LL);
+  return double((long long)a->hi) + double(a->lo) * 5.42101086242752217e-20;
+}
+// plain (non-atomic) store of a value into a slot nobody else is writing
+__device__ __forceinline__ void acc_store(Acc* a, double v) {
+  Acc r{0ull, 0ull, 0ull, 0ull};
+  if (!(fabs(v) < 4611686018427387904.0)) r.bad = 1ull;
+  else acc_split(v, r.lo, r.hi);
+  *a = r;
+}
+
 // round-to-nearest-even fp32 -> bf16 -> fp32 (the rounding points of torch.autocast(bfloat16))
 __device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 // the same for two values with ONE packed conversion (F2FP.BF16.PACK_AB on the ALU pipe) + two unpacking logic ops; the

@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(const __grid_constant__ 
       a += double(r0[k]);
       b += double(r1[k]);
     }
-    atomicAdd(&acc[0], a);
-    if (b != 0.0) atomicAdd(&acc[1], b);
+    acc_add(reinterpret_cast<Acc*>(acc + 4), a);   // order-independent: the clip coefficient is reproducible run to run
+    if (b != 0.0) atomicAdd(&acc[1], b);           // a count: integer-valued doubles add exactly in any order
   }
 }
 
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ Mult
     bias_c1 = 1.f - powf(a.beta1, step);
     bias_c2_sqrt = sqrtf(1.f - powf(a.beta2, step));
   }
-  const float norm = float(sqrt(acc[0]));
+  const float norm = float(sqrt(acc_load(reinterpret_cast<const Acc*>(acc + 4))));
   const float clip = a.max_norm > 0.f ? fminf(1.f, a.max_norm / (norm + 1e-6f)) : 1.f;
   const int ti = find_tensor(t, blockIdx.x);
   const long long n = t.numel[ti];
@@ -122,8 +122,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ Mult
   }
 }
 
-__global__ void adamw_advance_kernel(double* acc) {
-  if (acc[1] == 0.0) acc[2] += 1.0;   // after every block of adamw_kernel has read acc[2] (stream order)
+__global__ void adamw_finish_kernel(double* acc, int device_step) {
+  acc[0] = acc_load(reinterpret_cast<const Acc*>(acc + 4));   // sum of squared gradients, for the host
+  if (device_step && acc[1] == 0.0) acc[2] += 1.0;   // after every block of adamw_kernel has read acc[2] (stream order)
 }
 
 }  // namespace nsm
@@ -149,6 +150,7 @@ extern "C" int nsm_adamw_clip_step(int count, float* const* params, const float*
   t.block_start[count] = blocks;
   t.count = count;
   cudaError_t e = cudaMemsetAsync(acc, 0, 2 * sizeof(double), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(acc + 4, 0, sizeof(Acc), st);
   if (e != cudaSuccess) {
     set_error("nsm_adamw_clip_step: memset: %s", cudaGetErrorString(e));
     return 1;
@@ -160,12 +162,12 @@ extern "C" int nsm_adamw_clip_step(int count, float* const* params, const float*
   a.bias_c1 = 1.f - powf(beta1, float(step > 0 ? step : 1));
   a.bias_c2_sqrt = sqrtf(1.f - powf(beta2, float(step > 0 ? step : 1)));
   adamw_kernel<<<blocks, 256, 0, st>>>(t, a, acc);
-  if (a.device_step) adamw_advance_kernel<<<1, 1, 0, st>>>(acc);
+  adamw_finish_kernel<<<1, 1, 0, st>>>(acc, a.device_step);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("nsm_adamw_clip_step launch failed: %s", cudaGetErrorString(e));
     return 1;
   }
-  count_launch(a.device_step ? 3 : 2);
+  count_launch(3);
   return 0;
 }

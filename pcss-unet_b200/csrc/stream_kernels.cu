@@ -1249,7 +1249,7 @@ struct LossParams {
   long long numel;
   float coef_l1, coef_pert;
   float* grad;
-  double* acc;
+  Acc* acc;
   int vec;
 };
 __device__ __forceinline__ float sgn(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
@@ -1316,12 +1316,12 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const LossParams p) {
   if (threadIdx.x < 3) {
     double t = 0.0;
     for (int k = 0; k < 8; ++k) t += double(red[threadIdx.x][k]);
-    if (t != 0.0) atomicAdd(&p.acc[threadIdx.x], t);
+    if (t != 0.0) acc_add(&p.acc[threadIdx.x], t);   // order-independent (nsm_common.cuh: Acc)
   }
 }
 
 int l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
-                    long long numel, float coef_l1, float coef_pert, float* grad, double* acc, cudaStream_t st) {
+                    long long numel, float coef_l1, float coef_pert, float* grad, Acc* acc, cudaStream_t st) {
   if (n_perturbed < 0 || n_perturbed > 4) {
     set_error("l1_loss: at most 4 perturbed outputs per launch (got %d)", n_perturbed);
     return 1;
@@ -1344,7 +1344,7 @@ int l1_loss_fwd_bwd(const float* out, const float* target, const float* const* p
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) channel_sums_kernel(const float* __restrict__ x, long long S, int C,
                                                            long long HW, const double* __restrict__ means,
-                                                           double* __restrict__ sums, int chunks) {
+                                                           Acc* __restrict__ sums, int chunks) {
   // blockIdx.x = (plane index s*C + c) * chunks + chunk
   const long long plane = blockIdx.x / chunks;
   const int chunk = blockIdx.x % chunks;
@@ -1377,11 +1377,11 @@ __global__ void __launch_bounds__(256) channel_sums_kernel(const float* __restri
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int k = 0; k < 8; ++k) t += red[k];
-    atomicAdd(&sums[c], t);
+    acc_add(&sums[c], t);
   }
 }
 
-int channel_sums(const float* x, long long S, int C, long long HW, const double* means, double* sums,
+int channel_sums(const float* x, long long S, int C, long long HW, const double* means, Acc* sums,
                  cudaStream_t st) {
   const long long planes = S * C;
   int chunks = int((148LL * 8 + planes - 1) / planes);

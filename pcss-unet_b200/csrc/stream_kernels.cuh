@@ -65,11 +65,11 @@ int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes
 // ---- objective ---------------------------------------------------------------------------------------------------
 // acc[0] += sum|o-t|, acc[1] += sum_i sum|o-y_i|, acc[2] += #(o<0 or o>1); grad = a_l1*sign(o-t)+a_p*sum_i sign(o-y_i)
 int l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
-                    long long numel, float coef_l1, float coef_pert, float* grad, double* acc, cudaStream_t st);
+                    long long numel, float coef_l1, float coef_pert, float* grad, Acc* acc, cudaStream_t st);
 
 // ---- statistics / standardise / perturb ------------------------------------------------------------------------------
 // x: [S][C][HW] fp32.  means == nullptr: sums[c] += sum x;  else sums[c] += sum (x - means[c])^2   (fp64)
-int channel_sums(const float* x, long long S, int C, long long HW, const double* means, double* sums,
+int channel_sums(const float* x, long long S, int C, long long HW, const double* means, Acc* sums,
                  cudaStream_t st);
 int standardize(const float* x, float* y, long long S, int C, long long HW, const float* mean, const float* std,
                 cudaStream_t st);

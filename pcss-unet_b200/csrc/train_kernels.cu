@@ -32,7 +32,7 @@ constexpr int kBatch = 4;   // independent pixels in flight per thread (memory-l
 
 // Block-level per-channel reduction of NV value sets; thread t owns channel group (t % groups), 256 threads.
 template <int NV, typename T>
-__device__ __forceinline__ void block_channel_reduce(const T (&acc)[NV][8], int C, double* out) {
+__device__ __forceinline__ void block_channel_reduce(const T (&acc)[NV][8], int C, Acc* out) {
   __shared__ double red[256][NV * 8 + 1];
   const int tid = threadIdx.x, groups = C / 8, lanes = 256 / groups;
 #pragma unroll
@@ -44,7 +44,7 @@ __device__ __forceinline__ void block_channel_reduce(const T (&acc)[NV][8], int 
     const int v = i / C, c = i % C;
     double s = 0.0;
     for (int l = 0; l < lanes; ++l) s += red[l * groups + (c >> 3)][v * 8 + (c & 7)];
-    if (s != 0.0) atomicAdd(&out[v * C + c], s);
+    if (s != 0.0) acc_add(&out[v * C + c], s);   // order-independent (nsm_common.cuh: Acc)
   }
 }
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ void block_channel_reduce(const T (&acc)[NV][8], int 
 // BatchNorm statistics
 // ------------------------------------------------------------------------------------------------
 template <int FMT>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const Planes z, long long P, int C, int fmt, double* sums) {
+__global__ void __launch_bounds__(256) bn_stats_kernel(const Planes z, long long P, int C, int fmt, Acc* sums) {
   const int groups = C / 8, lanes = 256 / groups;
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   double acc[2][8];
@@ -107,7 +107,7 @@ static int check_c(const char* who, int C) {
   return 0;
 }
 
-int bn_stats(const Planes& z, long long P, int C, int fmt, double* sums, cudaStream_t st) {
+int bn_stats(const Planes& z, long long P, int C, int fmt, Acc* sums, cudaStream_t st) {
   if (check_c("bn_stats", C)) return 1;
   const int lanes = 256 / (C / 8);
   {
@@ -119,14 +119,14 @@ int bn_stats(const Planes& z, long long P, int C, int fmt, double* sums, cudaStr
   return 0;
 }
 
-__global__ void bn_finalize_kernel(const double* sums, long long P, int C, const float* gamma, const float* beta,
+__global__ void bn_finalize_kernel(const Acc* sums, long long P, int C, const float* gamma, const float* beta,
                                    float eps, float momentum, int updates, float* running_mean, float* running_var,
                                    float* scale, float* shift, float* save_mean, float* save_invstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double n = double(P);
-  const double mean = sums[c] / n;
-  double var = sums[C + c] / n - mean * mean;
+  const double mean = acc_load(sums + c) / n;
+  double var = acc_load(sums + C + c) / n - mean * mean;
   if (var < 0.0) var = 0.0;
   const float invstd = 1.0f / sqrtf(float(var) + eps);
   const float s = gamma[c] * invstd;
@@ -146,7 +146,7 @@ __global__ void bn_finalize_kernel(const double* sums, long long P, int C, const
   }
 }
 
-int bn_finalize(const double* sums, long long P, int C, const float* gamma, const float* beta, float eps,
+int bn_finalize(const Acc* sums, long long P, int C, const float* gamma, const float* beta, float eps,
                 float momentum, int updates, float* running_mean, float* running_var, float* scale, float* shift,
                 float* save_mean, float* save_invstd, cudaStream_t st) {
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, updates, running_mean,
@@ -408,8 +408,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
     ch.t[e] = __ldg(p.shift + c);
     if (APPLY) {
       const double mu = double(__ldg(p.mean + c)), is = double(__ldg(p.invstd + c));
-      const double m1 = p.sums[c] / double(P);
-      const double m2 = (p.sums[p.C + c] - mu * p.sums[c]) * is / double(P);
+      const double s1 = acc_load(p.sums + c), s2 = acc_load(p.sums + p.C + c);
+      const double m1 = s1 / double(P);
+      const double m2 = (s2 - mu * s1) * is / double(P);
       A[e] = float(-double(ch.s[e]) * is * m2);
       B[e] = float(-double(ch.s[e]) * m1 + double(ch.s[e]) * is * m2 * mu);
     }
@@ -494,19 +495,20 @@ int bn_bwd_apply(const BnBwdParams& p, cudaStream_t st) {
   return 0;
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* sums, const double* dbias, const float* mean, const float* invstd,
+__global__ void bn_bwd_finalize_kernel(const Acc* sums, const Acc* dbias, const float* mean, const float* invstd,
                                        int C, int rb, float* dgamma, float* dbeta, float* dbias_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   // sums[c] = sum g, sums[C + c] = sum g*z  ->  dgamma = sum g*xhat, dbeta = sum g
-  dgamma[c] = float((sums[C + c] - double(mean[c]) * sums[c]) * double(invstd[c]));
-  dbeta[c] = float(sums[c]);
+  const double s1 = acc_load(sums + c), s2 = acc_load(sums + C + c);
+  dgamma[c] = float((s2 - double(mean[c]) * s1) * double(invstd[c]));
+  dbeta[c] = float(s1);
   if (dbias_out) {
-    const float v = dbias ? float(dbias[c]) : 0.f;
+    const float v = dbias ? float(acc_load(dbias + c)) : 0.f;
     dbias_out[c] = rb ? rbf(v) : v;
   }
 }
-int bn_bwd_finalize(const double* sums, const double* dbias, const float* mean, const float* invstd, int C,
+int bn_bwd_finalize(const Acc* sums, const Acc* dbias, const float* mean, const float* invstd, int C,
                     int round_bf16, float* dgamma, float* dbeta, float* dbias_out, cudaStream_t st) {
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dbias, mean, invstd, C, round_bf16, dgamma, dbeta,
                                                           dbias_out);
@@ -1272,15 +1274,15 @@ int px4_reduce_dw(const float* dwv, int Cout, int Cin, int ksize, int CoutV, int
   return 0;
 }
 // out[v][c] = sum over the `groups` copies of in[v][g*C + c] (per-channel sums of a pixel-packed tensor -> real channels)
-__global__ void fold_channel_sums_kernel(const double* in, int nvec, int CV, int groups, int C, double* out) {
+__global__ void fold_channel_sums_kernel(const Acc* in, int nvec, int CV, int groups, int C, Acc* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec * C) return;
   const int v = i / C, c = i - v * C;
   double s = 0.0;
-  for (int g = 0; g < groups; ++g) s += in[(long long)v * CV + g * C + c];
-  out[i] = s;
+  for (int g = 0; g < groups; ++g) s += acc_load(in + (long long)v * CV + g * C + c);   // fixed order
+  acc_store(out + i, s);
 }
-int fold_channel_sums(const double* in, int nvec, int CV, int groups, int C, double* out, cudaStream_t st) {
+int fold_channel_sums(const Acc* in, int nvec, int CV, int groups, int C, Acc* out, cudaStream_t st) {
   if (groups * C > CV) {
     set_error("fold_channel_sums: %d x %d channels do not fit %d", groups, C, CV);
     return 1;

@@ -10,10 +10,10 @@ namespace nsm {
 
 // ---- train-mode BatchNorm2d over NHWC planes z[P][C] ------------------------------------------------------------------
 // sums[0..C) += sum_p z, sums[C..2C) += sum_p z^2   (fp64 accumulators, zeroed by the caller)
-int bn_stats(const Planes& z, long long P, int C, int fmt, double* sums, cudaStream_t st);
+int bn_stats(const Planes& z, long long P, int C, int fmt, Acc* sums, cudaStream_t st);
 // batch mean / biased var -> scale = gamma*invstd, shift = beta - mean*scale; saves mean & invstd; running stats update
 // (momentum, unbiased variance) applied `updates` times (the reference's checkpoint re-runs conv5's BN, see oracle).
-int bn_finalize(const double* sums, long long P, int C, const float* gamma, const float* beta, float eps,
+int bn_finalize(const Acc* sums, long long P, int C, const float* gamma, const float* beta, float eps,
                 float momentum, int updates, float* running_mean, float* running_var, float* scale, float* shift,
                 float* save_mean, float* save_invstd, cudaStream_t st);
 // a = mask[n][c] * LeakyReLU(z*scale + shift) (+ residual); optional AvgPool2d(2) output
@@ -38,13 +38,13 @@ struct BnBwdParams {
   const float* mean;
   const float* invstd;
   int lrelu;
-  double* sums;     // [2C] (reduce) ; apply reads them
-  double* dbias;    // [C] sum of dz (apply), zeroed by the caller, or nullptr
+  Acc* sums;        // [2C] order-independent accumulators (reduce) ; apply reads them
+  Acc* dbias;       // [C] sum of dz (apply), zeroed by the caller, or nullptr
 };
 int bn_bwd_reduce(const BnBwdParams& p, cudaStream_t st);
 // dz = scale * (g - mean(g) - xhat * mean(g*xhat));  dgamma = sum g*xhat, dbeta = sum g written by bn_bwd_finalize
 int bn_bwd_apply(const BnBwdParams& p, cudaStream_t st);
-int bn_bwd_finalize(const double* sums, const double* dbias, const float* mean, const float* invstd, int C,
+int bn_bwd_finalize(const Acc* sums, const Acc* dbias, const float* mean, const float* invstd, int C,
                     int round_bf16, float* dgamma, float* dbeta, float* dbias_out, cudaStream_t st);
 
 // ---- adjoints of AvgPool2d(2) (+ skip-gradient add) and of one bilinear align_corners resize -------------------------
@@ -76,7 +76,7 @@ int sigmoid_shuffle_bwd(const float* dy, const float* y, int N, int h, int w, in
 int pack_conv_weight_px4(const float* w, int Cout, int Cin, int ksize, int CoutV, int CinV, int flip_transpose, int fmt,
                          void* hi, void* lo, cudaStream_t st);
 int px4_reduce_dw(const float* dwv, int Cout, int Cin, int ksize, int CoutV, int CinV, float* dw, cudaStream_t st);
-int fold_channel_sums(const double* in, int nvec, int CV, int groups, int C, double* out, cudaStream_t st);
+int fold_channel_sums(const Acc* in, int nvec, int CV, int groups, int C, Acc* out, cudaStream_t st);
 int tile_vector(const float* src, int n, int rep, int npad, float fill, int round_bf16, float* dst, cudaStream_t st);
 // zero-padded weight packing: OIHW [Cout][Cin][k][k] -> [CoutP][tap][CinP] planes (dgrad: [CinP][tap'][CoutP])
 int pack_conv_weight_padded(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int flip_transpose,

@@ -76,7 +76,7 @@ __device__ __forceinline__ float scrub_feat(float v) {   // nan_to_num(nan=0, po
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256) feature_l1_kernel(const Planes f, long long half8, double* acc) {
+__global__ void __launch_bounds__(256) feature_l1_kernel(const Planes f, long long half8, Acc* acc) {
   // f holds 2B images; the first half are the features of `output`, the second half those of `target`
   float s = 0.f;
   double tot = 0.0;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) feature_l1_kernel(const Planes f, long lo
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(acc, t);
+    acc_add(acc, t);
   }
 }
 
@@ -154,7 +154,7 @@ extern "C" int nsm_relu_maxpool(const void* in0, const void* in1, int N, int H, 
   return 0;
 }
 
-extern "C" int nsm_feature_l1(const void* f0, const void* f1, long long numel_half, int mode, double* acc, void* stream) {
+extern "C" int nsm_feature_l1(const void* f0, const void* f1, long long numel_half, int mode, nsm_acc* acc, void* stream) {
   if (!vgg_mode_ok("nsm_feature_l1", mode)) return 1;
   if (numel_half % 8 || numel_half < 8 || !acc) {
     set_error("nsm_feature_l1: numel_half %lld must be a positive multiple of 8", numel_half);
@@ -163,9 +163,10 @@ extern "C" int nsm_feature_l1(const void* f0, const void* f1, long long numel_ha
   Planes f{{const_cast<void*>(f0), const_cast<void*>(f1)}};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n8 = numel_half / 8;
-  if (mode == kFmtBf16) feature_l1_kernel<kFmtBf16><<<vgrid(n8, 256, 148 * 8), 256, 0, st>>>(f, n8, acc);
-  else if (mode == kFmtF16x2) feature_l1_kernel<kFmtF16x2><<<vgrid(n8, 256, 148 * 8), 256, 0, st>>>(f, n8, acc);
-  else feature_l1_kernel<kFmtBf16x2><<<vgrid(n8, 256, 148 * 8), 256, 0, st>>>(f, n8, acc);
+  Acc* slot = reinterpret_cast<Acc*>(acc);
+  if (mode == kFmtBf16) feature_l1_kernel<kFmtBf16><<<vgrid(n8, 256, 148 * 8), 256, 0, st>>>(f, n8, slot);
+  else if (mode == kFmtF16x2) feature_l1_kernel<kFmtF16x2><<<vgrid(n8, 256, 148 * 8), 256, 0, st>>>(f, n8, slot);
+  else feature_l1_kernel<kFmtBf16x2><<<vgrid(n8, 256, 148 * 8), 256, 0, st>>>(f, n8, slot);
   VGG_CHECK("feature_l1");
   return 0;
 }

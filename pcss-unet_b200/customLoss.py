@@ -89,7 +89,7 @@ class MultiLayerVGGLoss(nn.Module):
             raise ValueError(f"expected output/target [B,1,H,W], got {tuple(o.shape)} / {tuple(t.shape)}")
         pk = self._weights(mode)
         x = nsm.vgg_input_prep(o, t, mode)
-        acc = torch.zeros(len(self.feature_layers), dtype=torch.float64, device=o.device)
+        acc = nsm.acc_zeros(len(self.feature_layers), o.device)
         numel = []
         stack, i = self._stack, 0
         while i < len(stack):
@@ -113,7 +113,7 @@ class MultiLayerVGGLoss(nn.Module):
             else:                                      # MaxPool2d behind a fused ReLU (ReLU is idempotent)
                 x = nsm.relu_maxpool(x, True)
                 i += 1
-        per_layer = acc / torch.tensor(numel, dtype=torch.float64, device=o.device)
+        per_layer = nsm.acc_to_double(acc) / torch.tensor(numel, dtype=torch.float64, device=o.device)
         total = (per_layer * self.weights.to(torch.float64)).sum().to(torch.float32)
         return total.detach()
 

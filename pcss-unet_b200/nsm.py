@@ -138,7 +138,8 @@ def _declare(lib):
     lib.nsm_vgg_input_prep.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp]
     lib.nsm_relu_maxpool.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp]
     lib.nsm_feature_l1.argtypes = [vp, vp, ll, c_int, vp, vp]
-    for name in ("nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1"):
+    lib.nsm_acc_to_double.argtypes = [vp, ll, vp, vp]
+    for name in ("nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1", "nsm_acc_to_double"):
         getattr(lib, name).restype = c_int
     for name in TRAIN_EXPORTS:
         if name != "nsm_wgrad_workspace_bytes":
@@ -169,6 +170,7 @@ EXPORTS = TRAIN_EXPORTS + [
     "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match", "nsm_l1_loss_fwd_bwd",
     "nsm_channel_sums", "nsm_standardize", "nsm_perturb", "nsm_profile_enable", "nsm_profile_read",
     "nsm_vgg_input_prep", "nsm_relu_maxpool", "nsm_feature_l1", "nsm_upblock", "nsm_unet_fused_decoder", "nsm_unet_set_fused_decoder", "nsm_upblock_prof",
+    "nsm_acc_to_double",
 ] + PX4_EXPORTS
 
 
@@ -475,9 +477,22 @@ def relu_maxpool(x: PlaneTensor, pool: bool):
 
 
 def feature_l1(f: PlaneTensor, acc):
-    """acc (fp64 device scalar view) += sum |a - b| over the two halves of the batch of f."""
+    """acc (ONE accumulator slot: a [1, 4] row view of nsm.acc_zeros) += sum |a - b| over the two halves of the batch."""
     N, C, H, W = f.shape
     check(lib().nsm_feature_l1(*_pp(f), (N // 2) * C * H * W, f.mode, acc.data_ptr(), stream_ptr()), "nsm_feature_l1")
+
+
+def acc_zeros(n, device):
+    """n zeroed order-independent accumulator slots (include/nsm_b200.h: nsm_acc = four 64-bit words each)."""
+    return torch.zeros(n, 4, dtype=torch.int64, device=device)
+
+
+def acc_to_double(acc):
+    """fp64 values of accumulator slots [n, 4] -> float64 [n] (device)."""
+    n = acc.shape[0]
+    out = torch.empty(n, dtype=torch.float64, device=acc.device)
+    check(lib().nsm_acc_to_double(acc.data_ptr(), n, out.data_ptr(), stream_ptr()), "nsm_acc_to_double")
+    return out
 
 
 def l1_loss_fwd_bwd(out, target=None, perturbed=(), coef_l1=0.0, coef_pert=0.0, want_grad=True):
@@ -489,14 +504,14 @@ def l1_loss_fwd_bwd(out, target=None, perturbed=(), coef_l1=0.0, coef_pert=0.0, 
     out = aligned(out)
     assert out.dtype == torch.float32
     n = out.numel()
-    acc = torch.zeros(3, dtype=torch.float64, device=out.device)
+    acc = acc_zeros(3, out.device)
     grad = torch.empty_like(out) if want_grad else None
     pert = [aligned(p) for p in perturbed]
     arr = (c_void_p * max(1, len(pert)))(*[p.data_ptr() for p in pert])
     tgt = None if target is None else aligned(target.to(torch.float32))
     check(lib().nsm_l1_loss_fwd_bwd(out.data_ptr(), ptr(tgt), arr, len(pert), n, coef_l1, coef_pert, ptr(grad),
                                     acc.data_ptr(), stream_ptr()), "nsm_l1_loss_fwd_bwd")
-    return acc, grad
+    return acc_to_double(acc), grad
 
 
 def channel_sums(x, means=None):
@@ -504,11 +519,11 @@ def channel_sums(x, means=None):
     x = x.contiguous()
     S, C = x.shape[0], x.shape[1]
     HW = x.numel() // (S * C)
-    sums = torch.zeros(C, dtype=torch.float64, device=x.device)
+    sums = acc_zeros(C, x.device)
     m = None if means is None else means.to(device=x.device, dtype=torch.float64).contiguous()
     check(lib().nsm_channel_sums(x.data_ptr(), S, C, HW, ptr(m), sums.data_ptr(), stream_ptr()),
           "nsm_channel_sums")
-    return sums
+    return acc_to_double(sums)
 
 
 def standardize(x, mean, std):
@@ -548,7 +563,7 @@ def _pp(t):
 
 def bn_stats(z: PlaneTensor):
     N, C, H, W = z.shape
-    sums = torch.zeros(2 * C, dtype=torch.float64, device=z.p0.device)
+    sums = acc_zeros(2 * C, z.p0.device)
     check(lib().nsm_bn_stats(*_pp(z), N * H * W, C, z.mode, sums.data_ptr(), stream_ptr()), "nsm_bn_stats")
     return sums
 
@@ -578,7 +593,7 @@ def bn_bwd(dy: PlaneTensor, z: PlaneTensor, scale, shift, mean, invstd, mask=Non
     N, C, H, W = z.shape
     dev = z.p0.device
     dz = PlaneTensor(N, C, H, W, z.mode, dev)
-    sums = torch.zeros(3 * C, dtype=torch.float64, device=dev)
+    sums = acc_zeros(3 * C, dev)
     g = torch.empty(3, C, dtype=torch.float32, device=dev)
     check(lib().nsm_bn_bwd(*_pp(dy), *_pp(z), N, H, W, C, z.mode, scale.data_ptr(), shift.data_ptr(), ptr(mask),
                            mean.data_ptr(), invstd.data_ptr(), int(lrelu), sums.data_ptr(), *_pp(dz),
@@ -639,9 +654,9 @@ def px4_reduce_dw(dwv, Cout, Cin, ksize):
 
 
 def fold_channel_sums(sums, nvec, groups, C):
-    """[nvec * CV] fp64 per-virtual-channel sums -> [nvec * C]: out[v][c] = sum_g in[v][g*C + c]."""
-    CV = sums.numel() // nvec
-    out = torch.empty(nvec * C, dtype=torch.float64, device=sums.device)
+    """[nvec * CV] per-virtual-channel accumulator slots -> [nvec * C]: out[v][c] = sum_g in[v][g*C + c]."""
+    CV = sums.shape[0] // nvec
+    out = torch.empty(nvec * C, 4, dtype=torch.int64, device=sums.device)
     check(lib().nsm_fold_channel_sums(sums.data_ptr(), nvec, CV, groups, C, out.data_ptr(), stream_ptr()),
           "nsm_fold_channel_sums")
     return out

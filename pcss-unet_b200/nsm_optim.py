@@ -48,7 +48,7 @@ class FusedAdamWClip(torch.optim.Optimizer):
             nsm.require_device(ps[0])
             fresh = self._acc is None
             if fresh:
-                self._acc = torch.zeros(3, dtype=torch.float64, device=ps[0].device)
+                self._acc = torch.zeros(8, dtype=torch.float64, device=ps[0].device)   # [0..2] + one nsm_acc slot of scratch
             loaded = 0
             for p in ps:
                 st = self.state[p]

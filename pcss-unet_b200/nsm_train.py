@@ -74,8 +74,8 @@ class _Conv:
         return t.px_view(-(t.shape[1] // c_s)) if t.shape[1] == 4 * c_s else t   # conv10: 16 of 64 virtual channels stay
 
     def forward(self, x, mode, stats=True):
-        """Raw convolution + bias; returns (z with cout_s channels per pixel, fp64 [2*cout_s] sums | None)."""
-        sums = torch.zeros(2 * self.cout_v, dtype=torch.float64, device=x.p0.device) if stats else None
+        """Raw convolution + bias; returns (z with cout_s channels per pixel, [2*cout_s] accumulator slots | None)."""
+        sums = nsm.acc_zeros(2 * self.cout_v, x.p0.device) if stats else None
         z, _, _ = nsm.conv_fwd(self._in(x, self.cin_v), self.w, self.k, self.cout_v, mode, bias=self.b, stats=sums)
         if self.px and stats:
             sums = nsm.fold_channel_sums(sums, 2, 4, self.cout)
@@ -132,7 +132,7 @@ def _running(bn, cpad):
 
 def _bn_train(z, gamma, beta, bn, updates=1, sums=None):
     """Batch statistics + running-stat update of one nn.BatchNorm2d (eps 1e-5, momentum 0.1).  Returns the [4, C]
-    (scale, shift, mean, invstd) tensor and the fp64 sums (kept for the checkpoint replay of conv5)."""
+    (scale, shift, mean, invstd) tensor and the accumulator slots of the sums (kept for the checkpoint replay of conv5)."""
     N, C, H, W = z.shape
     if sums is None:
         sums = nsm.bn_stats(z)
@@ -271,7 +271,7 @@ def _backward(model, st, dy, mode, need_dx):
     db10 = nsm.bn_stats(dc10)                       # per-channel sums of dc10 = the bias gradient
     if pk.c10.px:
         db10 = nsm.fold_channel_sums(db10, 2, 4, 4)
-    G.update({"conv10.weight": pk.c10.wgrad(dc10, st["c9"]), "conv10.bias": db10[:4].to(torch.float32)})
+    G.update({"conv10.weight": pk.c10.wgrad(dc10, st["c9"]), "conv10.bias": nsm.acc_to_double(db10[:4]).to(torch.float32)})
     dc9 = pk.c10.dgrad(dc10, mode)
     du9, g = _block_backward(model, pk, 7, sv[7], dc9, mode); G.update(g)
     dm8 = nsm.upsample_match_bwd(du9, *st["sizes"]["m8"])

@@ -90,15 +90,16 @@ def test_conv_epilogue_bn_statistics(nsm, mode_name):
     b = torch.randn(128, generator=g) * 0.1
     if mode_name == "bf16":
         x, b = bf(x), bf(b)
-    sums = torch.zeros(256, dtype=torch.float64, device="cuda")
+    slots = nsm.acc_zeros(256, "cuda")
     z, _, _ = nsm.conv_fwd(planes(nsm, x, mode), nsm.pack_conv_weight(w.cuda(), mode), 3, 128, mode, bias=b.cuda(),
-                           stats=sums)
+                           stats=slots)
+    sums = nsm.acc_to_double(slots)
     zz = z.to_nchw().double().cpu()
     # bf16: statistics of exactly the stored (rounded) values; fp32_train: of the fp32 values before the hi+lo split
     rt = 1e-6 if mode_name == "bf16" else 1e-4
     assert torch.allclose(sums[:128].cpu(), zz.sum(dim=(0, 2, 3)), rtol=rt, atol=1e-3)
     assert torch.allclose(sums[128:].cpu(), (zz * zz).sum(dim=(0, 2, 3)), rtol=rt, atol=1e-3)
-    assert torch.allclose(nsm.bn_stats(z).cpu(), sums.cpu(), rtol=rt, atol=1e-3)
+    assert torch.allclose(nsm.acc_to_double(nsm.bn_stats(z)).cpu(), sums.cpu(), rtol=rt, atol=1e-3)
 
 
 @pytest.mark.parametrize("mode_name", MODES)
@@ -464,7 +465,7 @@ def test_pixel_packed_thin_layers(nsm, mode_name, case):
         else:
             zz = z.to_nchw().cpu()[:, :Cout]
         assert rel(zz, y_ref) <= (1e-4 if mode_name != "bf16" else 1e-2)
-        s = sums.cpu().reshape(2, -1)[:, :Cout]
+        s = nsm.acc_to_double(sums).cpu().reshape(2, -1)[:, :Cout]
         ref64 = y_ref.detach().double()
         if mode_name == "bf16":
             ref64 = bf(y_ref.detach()).double()
@@ -548,3 +549,67 @@ def test_cuda_graph_training_step_matches_eager(nsm):
         else:
             assert int(sa[k]) == int(sb[k]), k
     assert float(opt_a.applied_steps) == float(opt_b.applied_steps) == warm + len(data)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_is_bit_reproducible(nsm, precision):
+    """The reference asks for deterministic kernels (main.py:81-82: cudnn.deterministic = True, benchmark = False).  Every
+    cross-block reduction here (BatchNorm statistics in the conv epilogue, BatchNorm-backward sums, loss sums, the clip
+    norm) goes through the order-independent nsm_acc slots (include/nsm_b200.h), the split-K weight-gradient reduction has a
+    fixed order, and the Dropout2d draws come from the seeded torch generator: two runs from the same seed must end with
+    bit-identical losses, parameters, BatchNorm buffers and optimizer moments."""
+    from Unetmodel import Unet
+    from customLoss import CustomLoss
+    from nsm_optim import FusedAdamWClip
+    P = oracle.init_params(7)
+    g = gen(123)
+    data = [(torch.randn(2, 4, 128, 160, generator=g).cuda(), torch.rand(2, 1, 128, 160, generator=g).cuda())
+            for _ in range(3)]
+
+    def run():
+        torch.manual_seed(2024)
+        torch.cuda.manual_seed_all(2024)
+        net = Unet(dropout_rate=0.2, precision=precision)
+        net.load_state_dict({k: v.clone() for k, v in P.items()})
+        net = net.cuda().train()
+        crit = CustomLoss("cuda", alpha=0.9, vgg_loss=None)
+        opt = FusedAdamWClip(net.parameters(), lr=7e-4, weight_decay=1e-3, max_norm=1.0)
+        losses = []
+        for _ in range(2):
+            for x, t in data:
+                opt.zero_grad(set_to_none=True)
+                loss = crit(net(x), t, None)
+                loss.backward()
+                opt.step()
+                losses.append(loss.detach().clone())
+        moments = [opt.state[p]["exp_avg_sq"].clone() for p in net.parameters()]
+        return torch.stack(losses), {k: v.clone() for k, v in net.state_dict().items()}, moments, opt.last_grad_norm.clone()
+
+    la, sa, ma, na = run()
+    lb, sb, mb, nb = run()
+    assert torch.equal(la, lb), (la - lb).abs().max().item()
+    assert torch.equal(na, nb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    for a, b in zip(ma, mb):
+        assert torch.equal(a, b)
+
+
+def test_acc_slots_are_exact_and_flag_nonfinite(nsm):
+    """nsm_acc: channel sums of values spanning 40 orders of magnitude equal the exactly rounded fixed-point total, do not
+    depend on the launch geometry, and a NaN / Inf input reads back as NaN (the loss must still show a blown-up output)."""
+    g = gen(5)
+    x = (torch.randn(3, 4, 64, 257, generator=g) * torch.tensor([1e-12, 1.0, 1e6, 1e-3]).view(1, 4, 1, 1)).cuda()
+    s = nsm.channel_sums(x).cpu()
+    ref = x.double().sum(dim=(0, 2, 3)).cpu()
+    assert torch.allclose(s, ref, rtol=1e-12, atol=1e-15)     # per-block partials are quantised to 2^-64 = 5.4e-20
+    assert torch.equal(s, nsm.channel_sums(x).cpu())
+    y = x.clone()
+    y[1, 2, 3, 4] = float("nan")
+    y[0, 0, 0, 0] = float("inf")
+    s = nsm.channel_sums(y).cpu()
+    assert torch.isnan(s[0]) and torch.isnan(s[2]) and torch.isfinite(s[1]) and torch.isfinite(s[3])
+    o = torch.rand(2, 1, 32, 32).cuda()
+    o[0, 0, 0, 0] = float("nan")
+    acc, _ = nsm.l1_loss_fwd_bwd(o, torch.rand(2, 1, 32, 32).cuda(), (), coef_l1=1.0)
+    assert torch.isnan(acc[0]) and acc[2].item() == 1

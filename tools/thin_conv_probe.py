@@ -20,7 +20,7 @@ for name, N, Cin, H, W, Cout, k in CASES:
     for stats in (False, True):
         ms = []
         R = 8    # launches queued back to back: the host side (tensor-map encoding, ctypes) hides behind the kernels
-        sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda") if stats else None
+        sums = nsm.acc_zeros(2 * Cout, "cuda") if stats else None
         for it in range(4):
             flush.zero_()
             torch.cuda._sleep(400000)      # let the host run ahead
