@@ -462,6 +462,237 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
   else if (p.dbias) block_channel_reduce<APPLY ? 1 : 2, float>(acc, p.C, p.dbias);
 }
 
+// ---- the same two passes with the operands STAGED THROUGH SHARED MEMORY BY THE TMA UNIT --------------------------------------
+// ncu of the register-staged kernel above (profiles/r02_bn_stream_full_cfg2_bf16.txt): 108-122 registers, 24 % occupancy,
+// 2.6-5.6 TB/s in the reduction and 2.9-4.4 TB/s in the apply pass depending on the tensor size -- bytes in flight are tied
+// to registers x resident warps.  Here one persistent CTA per SM streams dy and z as contiguous 8 KB chunks (NHWC tensors are
+// flat arrays of 16-byte channel groups) through a ring of kSbStages shared-memory stages filled by 1-D bulk copies
+// (cp.async.bulk, one producer lane, full / empty mbarriers): 96-192 KB per SM are in flight whatever the consumers do.
+// Sixteen consumer warps take one 16-byte group per thread and chunk; a thread's channel group never changes (chunk and
+// thread counts are multiples of the channel-group count), so the per-channel constants stay in registers.
+constexpr int kSbConsumers = 512;                 // consumer threads (16 warps) + one producer warp
+constexpr int kSbThreads = kSbConsumers + 32;
+constexpr int kSbChunk = kSbConsumers * 16;       // bytes per plane and stage: one 16-byte group per consumer thread
+constexpr int kSbStages = 6;
+template <int NPL>
+struct SbCfg {
+  static constexpr int STAGE_BYTES = 2 * NPL * kSbChunk;   // dy planes, then z planes
+  static constexpr int RED_BYTES = kSbConsumers * 17 * 8;   // final cross-thread reduction reuses the ring
+  static constexpr int RING_BYTES = kSbStages * STAGE_BYTES > RED_BYTES ? kSbStages * STAGE_BYTES : RED_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + 2 * kSbStages * 8 + 128;
+};
+
+template <int NPL, bool APPLY>
+__global__ void __launch_bounds__(kSbThreads, 1) bn_bwd_stream_kernel(const BnBwdParams p) {
+  using Cfg = SbCfg<NPL>;
+  extern __shared__ __align__(128) uint8_t sb_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(sb_smem + Cfg::RING_BYTES);
+  uint64_t* empty = full + kSbStages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int groups = p.C / 8;
+  const long long P = (long long)p.N * p.H * p.W;
+  const long long plane_bytes = P * p.C * 2;
+  const long long nchunks = (plane_bytes + kSbChunk - 1) / kSbChunk;
+  if (tid == 0) {
+    for (int s = 0; s < kSbStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kSbConsumers / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  constexpr int NV = APPLY ? 1 : 2;
+  double acc64[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc64[v][e] = 0.0;
+
+  if (warp == kSbConsumers / 32) {
+    // ===================== producer: one lane keeps the ring full =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long ci = blockIdx.x; ci < nchunks; ci += gridDim.x) {
+        mbar_wait(&empty[s], ph ^ 1);   // first pass over the ring: passes immediately
+        const long long off = ci * kSbChunk;
+        const uint32_t bytes = uint32_t(plane_bytes - off < kSbChunk ? plane_bytes - off : kSbChunk);
+        mbar_expect_tx(&full[s], 2 * NPL * bytes);
+        const uint32_t dst = smem_u32(sb_smem) + s * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+          bulk_load_1d(dst + pl * kSbChunk, reinterpret_cast<const uint8_t*>(p.dy.p[pl]) + off, bytes, &full[s]);
+          bulk_load_1d(dst + (NPL + pl) * kSbChunk, reinterpret_cast<const uint8_t*>(p.z.p[pl]) + off, bytes, &full[s]);
+        }
+        if (++s == kSbStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== consumers =====================
+    // (instruction budget: the first version spent 173 / 236 instructions per 16-byte group -- 64-bit index divisions, a mask
+    //  load per group, generic-format packing -- and was issue-bound at 60 % issue-active; everything per-sample is now
+    //  carried incrementally and the Dropout2d mask is folded with the LeakyReLU slope into two factors per channel)
+    constexpr bool rb = NPL == 1;
+    const int cg = tid % groups;   // kSbConsumers and the groups per chunk are multiples of `groups`
+    const int gs = __ffs(groups) - 1;
+    const unsigned HW = (unsigned)(p.H * p.W);
+    BwdChan8 ch;
+    float A[8], B[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      ch.s[e] = __ldg(p.scale + c);
+      ch.t[e] = __ldg(p.shift + c);
+      if (APPLY) {
+        const double mu = double(__ldg(p.mean + c)), is = double(__ldg(p.invstd + c));
+        const double s1 = acc_load(p.sums + c), s2 = acc_load(p.sums + p.C + c);
+        const double m1 = s1 / double(P);
+        const double m2 = (s2 - mu * s1) * is / double(P);
+        A[e] = float(-double(ch.s[e]) * is * m2);
+        B[e] = float(-double(ch.s[e]) * m1 + double(ch.s[e]) * is * m2 * mu);
+      }
+    }
+    const unsigned ngrp = (unsigned)(plane_bytes >> 4);            // 16-byte groups per plane (< 2^32: host check)
+    unsigned grp = blockIdx.x * (unsigned)kSbConsumers + tid;      // this thread's group in the current chunk
+    const unsigned dgrp = gridDim.x * (unsigned)kSbConsumers;
+    const unsigned dpix = dgrp >> gs;
+    unsigned n = (grp >> gs) / HW, rem = (grp >> gs) - n * HW;     // sample index and pixel inside the sample
+    // factor on dy where the activation passed / was on the leaky side: mask, 0.2 * mask (1, 0.2 without a mask)
+    const float slope = p.lrelu ? 0.2f : 1.f;
+    float fpos[8], fneg[8];
+    auto load_factors = [&](unsigned nn) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fpos[e] = 1.f;
+      if (p.mask && nn < (unsigned)p.N) load_mask8(p.mask, (size_t)nn * p.C + cg * 8, fpos);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fneg[e] = slope * fpos[e];
+    };
+    load_factors(n);
+    float acc[NV][8];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[v][e] = 0.f;
+    int run = 0, s = 0;
+    uint32_t ph = 0;
+    for (long long ci = blockIdx.x; ci < nchunks; ci += gridDim.x) {
+      mbar_wait(&full[s], ph);
+      if (grp < ngrp) {
+        const uint32_t src = smem_u32(sb_smem) + s * Cfg::STAGE_BYTES + tid * 16;
+        Raw8 rdy, rz;
+        rdy.h = lds16(src);
+        rz.h = lds16(src + NPL * kSbChunk);
+        if (NPL == 2) {
+          rdy.l = lds16(src + kSbChunk);
+          rz.l = lds16(src + 3 * kSbChunk);
+        }
+        float g[8], z[8];
+        unpack8_bf16<NPL>(rdy, g);
+        unpack8_bf16<NPL>(rz, z);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)   // (the sign of y survives its bf16 rounding)
+          g[e] *= fmaf(z[e], ch.s[e], ch.t[e]) > 0.f ? fpos[e] : fneg[e];
+        if (APPLY) {
+          float dz[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dz[e] = fmaf(ch.s[e], g[e], fmaf(A[e], z[e], B[e]));
+          uint4 hv, lv;
+          uint32_t* hw = &hv.x;
+          uint32_t* lw = &lv.x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hw[e] = pack_bf16(dz[2 * e], dz[2 * e + 1]);
+            const float h0 = bf16lo_to_f32(hw[e]), h1 = bf16hi_to_f32(hw[e]);
+            if (rb) {          // bf16 mode: the bias gradient sums the STORED (rounded) values
+              acc[0][2 * e] += h0;
+              acc[0][2 * e + 1] += h1;
+            } else {
+              acc[0][2 * e] += dz[2 * e];
+              acc[0][2 * e + 1] += dz[2 * e + 1];
+              lw[e] = pack_bf16(dz[2 * e] - h0, dz[2 * e + 1] - h1);
+            }
+          }
+          stg16(reinterpret_cast<uint8_t*>(p.dz.p[0]) + (size_t)grp * 16, hv);
+          if (NPL == 2) stg16(reinterpret_cast<uint8_t*>(p.dz.p[1]) + (size_t)grp * 16, lv);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[0][e] += g[e];
+            acc[NV - 1][e] = fmaf(g[e], z[e], acc[NV - 1][e]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);   // this warp has read its part of the stage
+      if (++s == kSbStages) { s = 0; ph ^= 1; }
+      grp += dgrp;
+      rem += dpix;
+      if (rem >= HW) {     // next sample(s): new Dropout2d mask row
+        do { rem -= HW; ++n; } while (rem >= HW);
+        if (p.mask) load_factors(n);
+      }
+      if (++run == 32) {   // short fp32 runs, fp64 across them
+        run = 0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc64[v][e] += double(acc[v][e]);
+            acc[v][e] = 0.f;
+          }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc64[v][e] += double(acc[v][e]);
+  }
+  // ---- per-channel totals of the CTA: fixed summation order, then the order-independent accumulator slots
+  Acc* out = APPLY ? p.dbias : p.sums;
+  __syncthreads();   // every bulk copy has landed and has been read: the ring is free
+  if (out == nullptr) return;
+  double* red = reinterpret_cast<double*>(sb_smem);
+  if (tid < kSbConsumers) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[tid * 17 + v * 8 + e] = acc64[v][e];
+  }
+  __syncthreads();
+  const int lanes = kSbConsumers / groups;
+  for (int i = tid; i < NV * p.C; i += kSbThreads) {
+    const int v = i / p.C, c = i % p.C;
+    double t = 0.0;
+    for (int l = 0; l < lanes; ++l) t += red[(l * groups + (c >> 3)) * 17 + v * 8 + (c & 7)];
+    if (t != 0.0) acc_add(&out[v * p.C + c], t);
+  }
+}
+
+template <int NPL, bool APPLY>
+static int bn_bwd_stream_launch(const BnBwdParams& p, cudaStream_t st) {
+  using Cfg = SbCfg<NPL>;
+  auto kern = bn_bwd_stream_kernel<NPL, APPLY>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("bn_bwd_stream: cudaFuncSetAttribute(%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const long long plane_bytes = (long long)p.N * p.H * p.W * p.C * 2;
+  const long long nchunks = (plane_bytes + kSbChunk - 1) / kSbChunk;
+  const int grid = int(nchunks < 148 ? nchunks : 148);
+  kern<<<grid, kSbThreads, Cfg::SMEM_BYTES, st>>>(p);
+  return 0;
+}
+static bool bn_bwd_use_stream(const BnBwdParams& p) {
+  static const bool off = getenv("NSM_BN_NO_STREAM") != nullptr;
+  // (a thread's channel group must not change from chunk to chunk: the groups per chunk are a multiple of C / 8)
+  return !off && kSbConsumers % (p.C / 8) == 0 && (long long)p.N * p.H * p.W * p.C / 8 < (1LL << 31);   // 32-bit group index
+}
+
 static int bn_bwd_grid(const BnBwdParams& p) {
   const long long P = (long long)p.N * p.H * p.W;
   const int lanes = 256 / (p.C / 8);
@@ -479,6 +710,11 @@ int bn_bwd_reduce(const BnBwdParams& p, cudaStream_t st) {
     set_error("bn_bwd: training tensors use fmt 0 or 2");
     return 1;
   }
+  if (bn_bwd_use_stream(p)) {
+    if (p.fmt == kFmtBf16 ? bn_bwd_stream_launch<1, false>(p, st) : bn_bwd_stream_launch<2, false>(p, st)) return 1;
+    NSM_CHECK_LAUNCH("bn_bwd_reduce");
+    return 0;
+  }
   const int grid = bn_bwd_grid(p);
   if (p.fmt == kFmtBf16) bn_bwd_kernel<1, false><<<grid, 256, 0, st>>>(p);
   else bn_bwd_kernel<2, false><<<grid, 256, 0, st>>>(p);
@@ -488,6 +724,11 @@ int bn_bwd_reduce(const BnBwdParams& p, cudaStream_t st) {
 
 int bn_bwd_apply(const BnBwdParams& p, cudaStream_t st) {
   if (check_c("bn_bwd_apply", p.C)) return 1;
+  if (bn_bwd_use_stream(p)) {
+    if (p.fmt == kFmtBf16 ? bn_bwd_stream_launch<1, true>(p, st) : bn_bwd_stream_launch<2, true>(p, st)) return 1;
+    NSM_CHECK_LAUNCH("bn_bwd_apply");
+    return 0;
+  }
   const int grid = bn_bwd_grid(p);
   if (p.fmt == kFmtBf16) bn_bwd_kernel<1, true><<<grid, 256, 0, st>>>(p);
   else bn_bwd_kernel<2, true><<<grid, 256, 0, st>>>(p);
