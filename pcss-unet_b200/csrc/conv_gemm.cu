@@ -259,7 +259,7 @@ __device__ __forceinline__ void epilogue_cols(float (&v)[32], const ConvKernelPa
         s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
       }
     }
-    st1 += double(s1[0]);   // flushed with one fp64 atomic per channel when the CTA's column block changes / at the end
+    st1 += double(s1[0]);   // flushed into the channel's order-independent accumulator slot (nsm_common.cuh: Acc) when the CTA's column block changes / at the end
     st2 += double(s2[0]);
   }
   if (ep.scale) {

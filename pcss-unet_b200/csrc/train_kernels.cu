@@ -1,6 +1,6 @@
 // Streaming kernels of the training path (see train_kernels.cuh).  NHWC planes, 8 channels (16 bytes) per thread,
-// per-channel reductions: fp32 in registers over short runs -> fp64 per thread -> shared memory -> one fp64 atomic per
-// channel and block.
+// per-channel reductions: fp32 in registers over short runs -> fp64 per thread -> shared memory (fixed order) -> one add per
+// channel and block into an order-independent accumulator slot (nsm_common.cuh: Acc), so results are bit-reproducible.
 #include <stdio.h>
 #include <stdlib.h>
 
