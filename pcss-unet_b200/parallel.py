@@ -11,7 +11,7 @@ Bucket plan, in the order backward produces the gradients:
     . {conv4, conv3, conv2}
 `nsm_train._backward` hands every block's gradients to `reduce_ready` as soon as they exist; a bucket whose members
 are complete is flattened and all-reduced asynchronously (NCCL runs on its own stream), `flush` (end of backward) makes
-the compute stream wait for the collectives, applies 1/world and scatters the results back.  Works with any
+the compute stream wait for the collectives and scatters the averaged results back (NCCL averages inside the collective).  Works with any
 torch.distributed backend (gloo on CPU in the tests).
 """
 from __future__ import annotations
@@ -50,6 +50,9 @@ class GradSync:
         self._pending: List[Dict[str, torch.Tensor]] = [dict() for _ in self.buckets]
         self._inflight = []      # (bucket index, flat tensor, [tensors], work handle)
         self.synced_in_backward = False
+        # NCCL averages inside the collective (ReduceOp.AVG): no arithmetic left on the PyTorch side, only the bucket
+        # gather / scatter copies.  gloo (CPU tests) has no AVG: sum, then scale.
+        self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
         model._grad_sync = self  # picked up by nsm_train._backward
 
     # ---- start-up consistency ---------------------------------------------------------------------------------
@@ -82,7 +85,8 @@ class GradSync:
     def _launch(self, b):
         tensors = [self._pending[b][n] for n in self.buckets[b]]
         flat = torch.cat([t.reshape(-1) for t in tensors])
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        work = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
         self._inflight.append((b, flat, tensors, work))
         self._pending[b] = dict()
 
@@ -90,7 +94,8 @@ class GradSync:
         """End of backward: order the compute stream after the collectives, average, scatter back in place."""
         for b, flat, tensors, work in self._inflight:
             work.wait()                     # NCCL: stream-level wait, the host does not block
-            flat.mul_(1.0 / self.world)
+            if not self._avg:
+                flat.mul_(1.0 / self.world)
             off = 0
             for t in tensors:
                 n = t.numel()
@@ -111,8 +116,9 @@ class GradSync:
             if not ts:
                 continue
             flat = torch.cat([t.reshape(-1) for t in ts])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.mul_(1.0 / self.world)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, group=self.group)
+            if not self._avg:
+                flat.mul_(1.0 / self.world)
             off = 0
             for t in ts:
                 n = t.numel()
