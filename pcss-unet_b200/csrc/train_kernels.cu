@@ -301,6 +301,11 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const BnActParams p) {
   }
 }
 
+// TMA-staged variants (defined below, next to the BatchNorm backward that introduced the ring)
+template <int NPL>
+static int bn_act_stream_launch(const BnActParams& p, cudaStream_t st);
+static bool sb_stream_ok(int N, int H, int W, int C);
+
 int bn_act(const BnActParams& p, cudaStream_t st) {
   if (check_c("bn_act", p.C)) return 1;
   if (p.pool.p[0]) {
@@ -314,6 +319,11 @@ int bn_act(const BnActParams& p, cudaStream_t st) {
       else if (p.fmt == kFmtF16x2) bn_act_pool_kernel<kFmtF16x2><<<grid_for(total, 256), 256, 0, st>>>(p);
       else bn_act_pool_kernel<kFmtBf16x2><<<grid_for(total, 256), 256, 0, st>>>(p);
     }
+  } else if (p.fmt == kFmtBf16x2 && sb_stream_ok(p.N, p.H, p.W, p.C)) {
+    // hi+lo planes: TMA-staged (cfg2 sizes: 3.9 -> 6.2 TB/s).  The single-plane pass is bound by its instructions (three bf16
+    // rounding points per element), not by bytes in flight: staged it runs at 4.77 TB/s, one or two CTAs per SM alike,
+    // against 4.95 TB/s for the register-staged kernel below, which therefore stays (tools/bn_probe.py).
+    if (bn_act_stream_launch<2>(p, st)) return 1;
   } else {
     const long long total = (long long)p.N * p.H * p.W * (p.C / 8);
     {
@@ -467,11 +477,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
 // 2.6-5.6 TB/s in the reduction and 2.9-4.4 TB/s in the apply pass depending on the tensor size -- bytes in flight are tied
 // to registers x resident warps.  Here one persistent CTA per SM streams dy and z as contiguous 8 KB chunks (NHWC tensors are
 // flat arrays of 16-byte channel groups) through a ring of kSbStages shared-memory stages filled by 1-D bulk copies
-// (cp.async.bulk, one producer lane, full / empty mbarriers): 96-192 KB per SM are in flight whatever the consumers do.
+// (cp.async.bulk issued by thread 0, full / empty mbarriers): 96-192 KB per SM are in flight whatever the consumers do.
 // Sixteen consumer warps take one 16-byte group per thread and chunk; a thread's channel group never changes (chunk and
 // thread counts are multiples of the channel-group count), so the per-channel constants stay in registers.
-constexpr int kSbConsumers = 512;                 // consumer threads (16 warps) + one producer warp
-constexpr int kSbThreads = kSbConsumers + 32;
+constexpr int kSbConsumers = 512;                 // sixteen warps = four per scheduler at up to 128 registers; thread 0 also feeds the ring
+constexpr int kSbThreads = kSbConsumers;
 constexpr int kSbChunk = kSbConsumers * 16;       // bytes per plane and stage: one 16-byte group per consumer thread
 constexpr int kSbStages = 6;
 template <int NPL>
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bn_bwd_stream_kernel(const BnBw
   extern __shared__ __align__(128) uint8_t sb_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(sb_smem + Cfg::RING_BYTES);
   uint64_t* empty = full + kSbStages;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int groups = p.C / 8;
   const long long P = (long long)p.N * p.H * p.W;
   const long long plane_bytes = P * p.C * 2;
@@ -508,26 +518,23 @@ __global__ void __launch_bounds__(kSbThreads, 1) bn_bwd_stream_kernel(const BnBw
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc64[v][e] = 0.0;
 
-  if (warp == kSbConsumers / 32) {
-    // ===================== producer: one lane keeps the ring full =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (long long ci = blockIdx.x; ci < nchunks; ci += gridDim.x) {
-        mbar_wait(&empty[s], ph ^ 1);   // first pass over the ring: passes immediately
-        const long long off = ci * kSbChunk;
-        const uint32_t bytes = uint32_t(plane_bytes - off < kSbChunk ? plane_bytes - off : kSbChunk);
-        mbar_expect_tx(&full[s], 2 * NPL * bytes);
-        const uint32_t dst = smem_u32(sb_smem) + s * Cfg::STAGE_BYTES;
+  // ring refill (thread 0): chunk number `k` of this CTA goes to stage k % kSbStages
+  auto issue_chunk = [&](long long ci, int s) {
+    const long long off = ci * kSbChunk;
+    const uint32_t bytes = uint32_t(plane_bytes - off < kSbChunk ? plane_bytes - off : kSbChunk);
+    mbar_expect_tx(&full[s], 2 * NPL * bytes);
+    const uint32_t dst = smem_u32(sb_smem) + s * Cfg::STAGE_BYTES;
 #pragma unroll
-        for (int pl = 0; pl < NPL; ++pl) {
-          bulk_load_1d(dst + pl * kSbChunk, reinterpret_cast<const uint8_t*>(p.dy.p[pl]) + off, bytes, &full[s]);
-          bulk_load_1d(dst + (NPL + pl) * kSbChunk, reinterpret_cast<const uint8_t*>(p.z.p[pl]) + off, bytes, &full[s]);
-        }
-        if (++s == kSbStages) { s = 0; ph ^= 1; }
-      }
+    for (int pl = 0; pl < NPL; ++pl) {
+      bulk_load_1d(dst + pl * kSbChunk, reinterpret_cast<const uint8_t*>(p.dy.p[pl]) + off, bytes, &full[s]);
+      bulk_load_1d(dst + (NPL + pl) * kSbChunk, reinterpret_cast<const uint8_t*>(p.z.p[pl]) + off, bytes, &full[s]);
     }
-  } else {
+  };
+  if (tid == 0) {
+    long long ci = blockIdx.x;
+    for (int s = 0; s < kSbStages && ci < nchunks; ++s, ci += gridDim.x) issue_chunk(ci, s);
+  }
+  {
     // ===================== consumers =====================
     // (instruction budget: the first version spent 173 / 236 instructions per 16-byte group -- 64-bit index divisions, a mask
     //  load per group, generic-format packing -- and was issue-bound at 60 % issue-active; everything per-sample is now
@@ -624,6 +631,16 @@ __global__ void __launch_bounds__(kSbThreads, 1) bn_bwd_stream_kernel(const BnBw
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);   // this warp has read its part of the stage
+      if (tid == 0) {
+        // refill the stage with the chunk kSbStages ahead once all sixteen warps have released it (this warp then trails the
+        // others by at most one chunk; kSbStages - 1 chunks stay in flight)
+        const long long nxt = ci + (long long)kSbStages * gridDim.x;
+        if (nxt < nchunks) {
+          mbar_wait(&empty[s], ph);
+          issue_chunk(nxt, s);
+        }
+      }
+      __syncwarp();
       if (++s == kSbStages) { s = 0; ph ^= 1; }
       grp += dgrp;
       rem += dpix;
@@ -652,7 +669,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bn_bwd_stream_kernel(const BnBw
   __syncthreads();   // every bulk copy has landed and has been read: the ring is free
   if (out == nullptr) return;
   double* red = reinterpret_cast<double*>(sb_smem);
-  if (tid < kSbConsumers) {
+  {
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -687,10 +704,160 @@ static int bn_bwd_stream_launch(const BnBwdParams& p, cudaStream_t st) {
   kern<<<grid, kSbThreads, Cfg::SMEM_BYTES, st>>>(p);
   return 0;
 }
-static bool bn_bwd_use_stream(const BnBwdParams& p) {
+static bool sb_stream_ok(int N, int H, int W, int C) {
   static const bool off = getenv("NSM_BN_NO_STREAM") != nullptr;
   // (a thread's channel group must not change from chunk to chunk: the groups per chunk are a multiple of C / 8)
-  return !off && kSbConsumers % (p.C / 8) == 0 && (long long)p.N * p.H * p.W * p.C / 8 < (1LL << 31);   // 32-bit group index
+  return !off && kSbConsumers % (C / 8) == 0 && (long long)N * H * W * C / 8 < (1LL << 31);   // 32-bit group index
+}
+static bool bn_bwd_use_stream(const BnBwdParams& p) { return sb_stream_ok(p.N, p.H, p.W, p.C); }
+
+// ---- BN apply + LeakyReLU + Dropout2d mask (+ skip add) on the same TMA-staged ring (no pooling: that variant walks 2x2 quads) ----
+template <int NPL>
+struct SaCfg {
+  static constexpr int STAGE_BYTES = 2 * NPL * kSbChunk;   // z planes, then skip planes (unused without a skip tensor)
+  static constexpr int SMEM_BYTES = kSbStages * STAGE_BYTES + 2 * kSbStages * 8 + 128;
+};
+template <int NPL>
+__global__ void __launch_bounds__(kSbThreads, 1) bn_act_stream_kernel(const BnActParams p) {
+  using Cfg = SaCfg<NPL>;
+  extern __shared__ __align__(128) uint8_t sb_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(sb_smem + kSbStages * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + kSbStages;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int groups = p.C / 8;
+  const long long plane_bytes = (long long)p.N * p.H * p.W * p.C * 2;
+  const long long nchunks = (plane_bytes + kSbChunk - 1) / kSbChunk;
+  const bool has_res = p.residual.p[0] != nullptr;
+  if (tid == 0) {
+    for (int s = 0; s < kSbStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kSbConsumers / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue_chunk = [&](long long ci, int s) {
+    const long long off = ci * kSbChunk;
+    const uint32_t bytes = uint32_t(plane_bytes - off < kSbChunk ? plane_bytes - off : kSbChunk);
+    mbar_expect_tx(&full[s], (has_res ? 2 : 1) * NPL * bytes);
+    const uint32_t dst = smem_u32(sb_smem) + s * Cfg::STAGE_BYTES;
+#pragma unroll
+    for (int pl = 0; pl < NPL; ++pl) {
+      bulk_load_1d(dst + pl * kSbChunk, reinterpret_cast<const uint8_t*>(p.z.p[pl]) + off, bytes, &full[s]);
+      if (has_res)
+        bulk_load_1d(dst + (NPL + pl) * kSbChunk, reinterpret_cast<const uint8_t*>(p.residual.p[pl]) + off, bytes, &full[s]);
+    }
+  };
+  if (tid == 0) {
+    long long ci = blockIdx.x;
+    for (int s = 0; s < kSbStages && ci < nchunks; ++s, ci += gridDim.x) issue_chunk(ci, s);
+  }
+  constexpr bool rb = NPL == 1;
+  const int cg = tid % groups;
+  const int gs = __ffs(groups) - 1;
+  const unsigned HW = (unsigned)(p.H * p.W);
+  const Chan8 ch = load_chan8(p.scale, p.shift, cg * 8);
+  const unsigned ngrp = (unsigned)(plane_bytes >> 4);
+  unsigned grp = blockIdx.x * (unsigned)kSbConsumers + tid;
+  const unsigned dgrp = gridDim.x * (unsigned)kSbConsumers;
+  const unsigned dpix = dgrp >> gs;
+  unsigned n = (grp >> gs) / HW, rem = (grp >> gs) - n * HW;
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = 1.f;
+  if (p.mask && n < (unsigned)p.N) load_mask8(p.mask, (size_t)n * p.C + cg * 8, m);
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long ci = blockIdx.x; ci < nchunks; ci += gridDim.x) {
+    mbar_wait(&full[s], ph);
+    if (grp < ngrp) {
+      const uint32_t src = smem_u32(sb_smem) + s * Cfg::STAGE_BYTES + tid * 16;
+      Raw8 rz, rr;
+      rz.h = lds16(src);
+      if (NPL == 2) rz.l = lds16(src + kSbChunk);
+      if (has_res) {
+        rr.h = lds16(src + NPL * kSbChunk);
+        if (NPL == 2) rr.l = lds16(src + 3 * kSbChunk);
+      }
+      float v[8];
+      unpack8_bf16<NPL>(rz, v);
+      // same operation order and bf16 rounding points as bn_act8
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], ch.s[e], ch.t[e]);
+      if (rb) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) rbf2(v[e], v[e + 1]);
+      }
+      if (p.lrelu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = lrelu02(v[e]);
+        if (rb) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) rbf2(v[e], v[e + 1]);
+        }
+      }
+      if (p.mask) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= m[e];
+        if (rb) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) rbf2(v[e], v[e + 1]);
+        }
+      }
+      if (has_res) {
+        float r[8];
+        unpack8_bf16<NPL>(rr, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += r[e];
+      }
+      uint4 hv, lv;
+      uint32_t* hw = &hv.x;
+      uint32_t* lw = &lv.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        hw[e] = pack_bf16(v[2 * e], v[2 * e + 1]);   // (bf16 mode: this IS the rounding after the skip add / last step)
+        if (NPL == 2) lw[e] = pack_bf16(v[2 * e] - bf16lo_to_f32(hw[e]), v[2 * e + 1] - bf16hi_to_f32(hw[e]));
+      }
+      stg16(reinterpret_cast<uint8_t*>(p.out.p[0]) + (size_t)grp * 16, hv);
+      if (NPL == 2) stg16(reinterpret_cast<uint8_t*>(p.out.p[1]) + (size_t)grp * 16, lv);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (tid == 0) {
+      const long long nxt = ci + (long long)kSbStages * gridDim.x;
+      if (nxt < nchunks) {
+        mbar_wait(&empty[s], ph);
+        issue_chunk(nxt, s);
+      }
+    }
+    __syncwarp();
+    if (++s == kSbStages) { s = 0; ph ^= 1; }
+    grp += dgrp;
+    rem += dpix;
+    if (rem >= HW) {
+      do { rem -= HW; ++n; } while (rem >= HW);
+      if (p.mask && n < (unsigned)p.N) load_mask8(p.mask, (size_t)n * p.C + cg * 8, m);
+    }
+  }
+}
+
+template <int NPL>
+static int bn_act_stream_launch(const BnActParams& p, cudaStream_t st) {
+  using Cfg = SaCfg<NPL>;
+  auto kern = bn_act_stream_kernel<NPL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("bn_act_stream: cudaFuncSetAttribute(%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const long long plane_bytes = (long long)p.N * p.H * p.W * p.C * 2;
+  const long long nchunks = (plane_bytes + kSbChunk - 1) / kSbChunk;
+  kern<<<int(nchunks < 148 ? nchunks : 148), kSbThreads, Cfg::SMEM_BYTES, st>>>(p);
+  return 0;
 }
 
 static int bn_bwd_grid(const BnBwdParams& p) {
