@@ -61,6 +61,9 @@ const char* nsm_last_error(void);
 int nsm_version(void);
 /* kernels launched by this library since load (bench.py: gpu_launches) */
 long long nsm_launch_count(void);
+/* TMA descriptors (CUtensorMap) are encoded once per (buffer, shape, box, swizzle) and kept in a table behind a mutex:
+ * lookups that found / did not find their descriptor since load (a steady-state frame or step adds hits only) */
+void nsm_tmap_cache_stats(long long* hits, long long* misses);
 /* 0 if the current CUDA device is compute capability 10.x (B200), else non-zero + message */
 int nsm_check_device(void);
 

@@ -209,6 +209,7 @@ extern "C" {
 const char* nsm_last_error(void) { return nsm::last_error(); }
 int nsm_version(void) { return 100; }
 long long nsm_launch_count(void) { return launch_count(); }
+void nsm_tmap_cache_stats(long long* hits, long long* misses) { tmap_cache_stats(hits, misses); }
 
 int nsm_check_device(void) {
   int dev = 0;

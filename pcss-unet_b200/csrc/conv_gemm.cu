@@ -34,6 +34,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <unordered_map>
 
 #include "conv_gemm.cuh"
 #include "nsm_common.cuh"
@@ -76,6 +77,32 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// A descriptor is a pure function of (base, rank, dims, strides, box, element size, swizzle): the same buffers come back
+// every frame / training step (caller-owned workspaces, packed weights), so encoded descriptors are kept in a small table
+// behind a mutex and a launch costs one lookup instead of a driver call per operand (6-10 per conv launch).
+struct TmapKey {
+  uint64_t w[16];
+  bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : k.w) {
+      h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+      h *= 0xFF51AFD7ED558CCDull;
+    }
+    return size_t(h ^ (h >> 33));
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
+constexpr size_t kTmapCacheMax = 8192;   // entries of 128 B + key; flushed when full (a new shape / buffer set)
+void tmap_cache_stats(long long* hits, long long* misses) {
+  *hits = g_tmap_hits.load(std::memory_order_relaxed);
+  *misses = g_tmap_misses.load(std::memory_order_relaxed);
+}
+
 int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
@@ -83,6 +110,29 @@ int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64
     set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     return 1;
   }
+  if (rank < 1 || rank > 5) {
+    set_error("encode_tmap_tiled: rank %d", rank);
+    return 1;
+  }
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.w[0] = uint64_t(reinterpret_cast<uintptr_t>(base));
+  key.w[1] = uint64_t(rank) | (uint64_t(elem_bytes) << 8) | (uint64_t(swizzle_bytes) << 16);
+  for (int i = 0; i < rank; ++i) {
+    key.w[2 + i] = dims[i];
+    key.w[7 + i] = box[i];
+    if (i > 0) key.w[11 + i] = strides_bytes[i - 1];
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      memcpy(map, &it->second, sizeof(CUtensorMap));
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return 0;
+    }
+  }
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bdim[5], estr[5];
@@ -103,6 +153,11 @@ int encode_tmap_tiled(CUtensorMap* map, const void* base, int rank, const uint64
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)", int(r), rank,
               (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
     return 1;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+    memcpy(&g_tmap_cache[key], map, sizeof(CUtensorMap));
   }
   return 0;
 }
@@ -421,7 +476,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* res_bar = tempty_bar + 2;   // [EW epilogue warps][2 slots]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * EW);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -495,8 +550,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // Uniform control flow for the whole warp (its index comes out of a shuffle, so the compiler knows), ONE elected lane
+    // issues: the tcgen05 instructions are straight-line UTCHMMA / UTCBAR with descriptors advanced by one 64-bit add each.
+    // Under `if (lane == 0)` each was wrapped in an ELECT / BRA.U.ANY loop behind a chain of uniform-datapath descriptor
+    // arithmetic (~100+ cycles per MMA: more than the 32-64 cycles of math of an N <= 128 MMA).
+    {
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint64_t desc_hi = make_desc_sw128(0, 16, 1024);   // LBO 16 B, SBO 1024 B, 128-byte swizzle; address added below
+      auto desc_of = [&](uint32_t addr) { return desc_hi | uint64_t((addr & 0x3FFFFu) >> 4); };
       for (int item = it_first; item < it_count; item += it_step) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_len) {
           const int kb1 = kb0 + chunk_len < num_kb ? kb0 + chunk_len : num_kb;
@@ -508,41 +570,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint32_t a_plane = Cfg::A_BYTES;   // distance hi plane -> second plane
-            const uint32_t a_sbo = 1024;
             const uint32_t b_hi = a_hi + NP * Cfg::A_BYTES;
+            // K advances by 32 B per MMA = +2 in the descriptor's 16-byte address field
+            const uint64_t da_hi = desc_of(a_hi), db_hi = desc_of(b_hi);
+            const uint64_t da_lo = desc_of(a_hi + Cfg::A_BYTES), db_lo = desc_of(b_hi + Cfg::B_BYTES);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < kKChunk / 16; ++k) {
-              const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;  // first MMA of a chunk overwrites
-              const uint64_t da_hi = make_desc_sw128(a_hi + k * 32, 16, a_sbo);
-              const uint64_t db_hi = make_desc_sw128(b_hi + k * 32, 16, 1024);
-              if (NP == 2) {
-                // The weight planes lie back to back in the stage (hi rows, then lo rows) = ONE K-major tile of 2*BN rows:
-                // a_hi x [w_hi | w_lo] is a single MMA of width 2*BN that fills main (columns [0,BN)) and cross
-                // ([BN,2BN)) at once; a_lo x w_hi then accumulates into cross.  Same tensor cycles as three MMAs of
-                // width BN, but a_hi is fetched from shared memory once instead of twice.
-                const uint64_t da_lo = make_desc_sw128(a_hi + a_plane + k * 32, 16, a_sbo);
-                if (p.x8) {
-                  // 8-bit cross planes: one e4m3 MMA of K = 32 (16 channels x two halves) yields both cross terms at
-                  // twice the fp16 rate -> two MMA slots per k-step instead of three
-                  const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
-                  umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
-                  umma_f8(d_cross, da_lo, db_lo, p.idesc_hi, accum);
+              for (int k = 0; k < kKChunk / 16; ++k) {
+                const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;  // first MMA of a chunk overwrites
+                if (NP == 2) {
+                  // The weight planes lie back to back in the stage (hi rows, then lo rows) = ONE K-major tile of 2*BN rows:
+                  // a_hi x [w_hi | w_lo] is a single MMA of width 2*BN that fills main (columns [0,BN)) and cross
+                  // ([BN,2BN)) at once; a_lo x w_hi then accumulates into cross.  Same tensor cycles as three MMAs of
+                  // width BN, but a_hi is fetched from shared memory once instead of twice.
+                  if (p.x8) {
+                    // 8-bit cross planes: one e4m3 MMA of K = 32 (16 channels x two halves) yields both cross terms at
+                    // twice the fp16 rate -> two MMA slots per k-step instead of three
+                    umma_bf16(d_main, da_hi + 2 * k, db_hi + 2 * k, p.idesc_hi, accum);
+                    umma_f8(d_cross, da_lo + 2 * k, db_lo + 2 * k, p.idesc_hi, accum);
+                  } else {
+                    umma_bf16(d_main, da_hi + 2 * k, db_hi + 2 * k, p.idesc_wide, accum);
+                    umma_bf16(d_cross, da_lo + 2 * k, db_hi + 2 * k, p.idesc_hi, 1u);
+                  }
                 } else {
-                  umma_bf16(d_main, da_hi, db_hi, p.idesc_wide, accum);
-                  umma_bf16(d_cross, da_lo, db_hi, p.idesc_hi, 1u);
+                  umma_bf16(d_main, da_hi + 2 * k, db_hi + 2 * k, p.idesc_hi, accum);
                 }
-              } else {
-                umma_bf16(d_main, da_hi, db_hi, p.idesc_hi, accum);
               }
+              umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+              if (kb + 1 == kb1) umma_commit(&tfull_bar[acc]);  // chunk accumulator complete -> epilogue
             }
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            __syncwarp();
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&tfull_bar[acc]);  // chunk accumulator complete -> epilogue
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -735,7 +797,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   uint64_t* res_bar = tempty_bar + 1;   // [8 epilogue warps][2 slots]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -822,9 +884,13 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && (!PAIR || cta_rank == 0)) {   // CTA pairs: the leader issues for both
+    // uniform control flow, one elected lane issues (see conv_gemm_kernel): straight-line UTC*MMA, descriptors by 64-bit adds
+    if (!PAIR || cta_rank == 0) {   // CTA pairs: the leader issues for both
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0, acc_phase = 0;
       const uint32_t d_main = tmem_base, d_cross = tmem_base + BN;
+      const uint64_t desc_hi = make_desc_sw64(0);
+      auto desc_of = [&](uint32_t addr) { return desc_hi | uint64_t((addr & 0x3FFFFu) >> 4); };
       for (int item = it_first; item < it_count; item += it_step) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_len) {
           const int kb1 = kb0 + chunk_len < num_kb ? kb0 + chunk_len : num_kb;
@@ -836,32 +902,38 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
+            const uint64_t da = desc_of(a_hi), dbw = desc_of(b_hi);
+            const uint64_t da2 = desc_of(a_hi + Cfg::A_BYTES), dbw2 = desc_of(b_hi + Cfg::B_BYTES);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < Cfg::BK / 16; ++k) {
-              // main: a fresh accumulation per chunk (truncating tensor-core adds).  cross: one
-              // accumulation over the whole K -- its terms are 2^-12 of the result, 576 truncations cost nothing -- so the
-              // per-chunk drain touches only the main half of TMEM
-              const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
-              if (PAIR) {
-                umma_bf16_pair(d_main, make_desc_sw64(a_hi + k * 32), make_desc_sw64(b_hi + k * 32), p.idesc_hi, accum);
-                umma_f8_pair(d_cross, make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32),
-                             make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32), p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
-              } else {
-                umma_bf16(d_main, make_desc_sw64(a_hi + k * 32), make_desc_sw64(b_hi + k * 32), p.idesc_hi, accum);
-                umma_f8(d_cross, make_desc_sw64(a_hi + Cfg::A_BYTES + k * 32),
-                        make_desc_sw64(b_hi + Cfg::B_BYTES + k * 32), p.idesc_hi, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < Cfg::BK / 16; ++k) {
+                // main: a fresh accumulation per chunk (truncating tensor-core adds).  cross: one
+                // accumulation over the whole K -- its terms are 2^-12 of the result, 576 truncations cost nothing -- so the
+                // per-chunk drain touches only the main half of TMEM
+                const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
+                const uint32_t accum_x = (kb | k) != 0 ? 1u : 0u;
+                if (PAIR) {
+                  umma_bf16_pair(d_main, da + 2 * k, dbw + 2 * k, p.idesc_hi, accum);
+                  umma_f8_pair(d_cross, da2 + 2 * k, dbw2 + 2 * k, p.idesc_hi, accum_x);
+                } else {
+                  umma_bf16(d_main, da + 2 * k, dbw + 2 * k, p.idesc_hi, accum);
+                  umma_f8(d_cross, da2 + 2 * k, dbw2 + 2 * k, p.idesc_hi, accum_x);
+                }
+              }
+              if (PAIR) umma_commit_pair(&empty_bar[stage]);
+              else if (MC > 1) umma_commit_mc(&empty_bar[stage], kAllCtas);
+              else umma_commit(&empty_bar[stage]);
+              if (kb + 1 == kb1) {
+                if (PAIR) umma_commit_pair(tfull_bar);
+                else umma_commit(tfull_bar);
               }
             }
-            if (PAIR) umma_commit_pair(&empty_bar[stage]);
-            else if (MC > 1) umma_commit_mc(&empty_bar[stage], kAllCtas);
-            else umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          if (PAIR) umma_commit_pair(tfull_bar);
-          else umma_commit(tfull_bar);
         }
       }
     }

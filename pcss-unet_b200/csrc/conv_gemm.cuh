@@ -51,5 +51,6 @@ void set_error(const char* fmt, ...);
 // number of kernels this library has launched (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
 long long launch_count();
+void tmap_cache_stats(long long* hits, long long* misses);
 
 }  // namespace nsm

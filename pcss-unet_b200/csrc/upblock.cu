@@ -51,6 +51,7 @@ struct UbKernelParams {
   int sbw, sbh;                       // source box in pixels
   uint32_t off_src, off_b, off_vec, off_taps, off_bar;
   uint32_t src_plane_bytes, b_stage_bytes, b_stages;
+  uint32_t w_resident;                // every weight tile (9 * NCH of the 3x3, NCH of the 1x1) has its own stage: loaded once per CTA
   uint32_t halo_bufs, src_bufs;       // ring depths of the halo tiles (<= 4) and of the staged source boxes (<= 2)
   uint32_t acc1_bufs;                 // 2: the 3x3 accumulator is double-buffered in TMEM, the MMAs run one tile ahead
   uint32_t tm_acc2, tm_a2, tmem_cols;  // TMEM column offsets
@@ -150,15 +151,20 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
   uint64_t* tab_empty = bars + 39;         // [kTabs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 43);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, and the MMA warp below runs its loops with
+  // uniform control flow and ONE elected lane issuing (elect.sync): the tcgen05.mma / commit instructions come out as
+  // straight-line UTCHMMA with descriptors advanced by one 64-bit add.  Under `if (lane == 0)` every one of them was
+  // wrapped in a five-instruction ELECT / BRA.U.ANY loop behind a chain of uniform-datapath descriptor arithmetic, and the
+  // short MMAs of these blocks (N = 64 / 128: 32 / 64 cycles of math) were issue-bound at ~135 cycles each.
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nt = (p.total_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // tiles of this CTA
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmS0); tma_prefetch_desc(&tmW3a); tma_prefetch_desc(&tmW1a);
     if (NP == 2) { tma_prefetch_desc(&tmS1); tma_prefetch_desc(&tmW3b); tma_prefetch_desc(&tmW1b); }
     for (uint32_t s = 0; s < p.b_stages; ++s) {
-      mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_full[s], 1);                         // resident weights: up to 16 "full" barriers, no "empty" ones
+      if (!p.w_resident) mbar_init(&b_empty[s], 1);
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(&halo_full[b], kWorkers);
@@ -212,7 +218,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       auto w3_tiles = [&]() {
         for (int c = 0; c < NCH; ++c)
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_empty[stage], phase ^ 1);
+            if (!p.w_resident) mbar_wait(&b_empty[stage], phase ^ 1);
             uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
             mbar_expect_tx(&b_full[stage], NP * CMID * 128);
             tma_load_2d(sb, &tmW3a, &b_full[stage], tap * CMID + c * 64, 0);
@@ -222,7 +228,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       };
       auto w1_tiles = [&]() {
         for (int c = 0; c < NCH; ++c) {
-          mbar_wait(&b_empty[stage], phase ^ 1);
+          if (!p.w_resident) mbar_wait(&b_empty[stage], phase ^ 1);
           uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
           mbar_expect_tx(&b_full[stage], NP * p.Cout * 128);
           tma_load_2d(sb, &tmW1a, &b_full[stage], c * 64, 0);
@@ -232,14 +238,21 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       };
       // same order as the MMA thread consumes them: with a double-buffered 3x3 accumulator the 3x3 GEMM of tile j+1 is
       // issued before the 1x1 GEMM of tile j
-      if (db) w3_tiles();
-      for (int j = 0; j < nt; ++j) {
-        if (db) {
-          if (j + 1 < nt) w3_tiles();
-        } else {
-          w3_tiles();
-        }
+      if (p.w_resident) {
+        // the whole block's weights fit next to the halo ring: stage (c * 9 + tap) / (9 * NCH + c), loaded once, never
+        // released -- no weight traffic (L2 -> shared memory, shared-memory writes) per tile
+        w3_tiles();
         w1_tiles();
+      } else {
+        if (db) w3_tiles();
+        for (int j = 0; j < nt; ++j) {
+          if (db) {
+            if (j + 1 < nt) w3_tiles();
+          } else {
+            w3_tiles();
+          }
+          w1_tiles();
+        }
       }
     }
   } else if (warp == 2) {
@@ -320,13 +333,19 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp walks the loops (uniform control flow, all lanes poll the barriers); the elected lane issues
+    {
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0;
       auto advance = [&]() {
         if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
       };
       const bool prof = (p.dbg & 64) && blockIdx.x == 0;
       long long acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_ = clock64();
+      // descriptor halves that never change: LBO 16 B, SBO (one halo row for A, 1024 B for B), version 1, 128-byte swizzle
+      const uint64_t desc_a_hi = make_desc_sw128(0, 16, uint32_t(kHaloW * 128));
+      const uint64_t desc_b_hi = make_desc_sw128(0, 16, 1024);
+      auto desc_of = [](uint64_t hi, uint32_t addr) { return hi | uint64_t((addr & 0x3FFFFu) >> 4); };
       // ---- GEMM 1: 3x3 convolution of tile j out of its halo tiles ----
       auto gemm1 = [&](int j) {
         UB_T(7);
@@ -341,28 +360,34 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
           UB_T(1);
           const uint32_t halo = sbase + uint32_t(hb * NP) * kHaloPlaneBytes;
           for (int tap = 0; tap < 9; ++tap) {
+            if (p.w_resident) { stage = uint32_t(c * 9 + tap); phase = 0; }
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
             UB_T(2);
             const uint32_t a0 = halo + uint32_t((tap / 3) * kHaloW + tap % 3) * 128u;
-            const uint32_t asbo = uint32_t(kHaloW * 128);
             const uint32_t b0 = sbase + p.off_b + stage * p.b_stage_bytes;
+            // K advances by 32 B per MMA = +2 in the descriptor's 16-byte address field (shared memory ends below 2^18)
+            const uint64_t da = desc_of(desc_a_hi, a0), dbw = desc_of(desc_b_hi, b0);
+            const uint64_t da2 = desc_of(desc_a_hi, a0 + kHaloPlaneBytes), dbw2 = desc_of(desc_b_hi, b0 + CMID * 128);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t accum = (c | tap | k) != 0 ? 1u : 0u;
-              umma_bf16(tm_acc1, make_desc_sw128(a0 + k * 32, 16, asbo),
-                        make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc1, accum);
-              if (NP == 2)   // both cross terms as one e4m3 MMA of K = 32 (8-bit cross planes)
-                umma_f8(tm_acc1 + CMID, make_desc_sw128(a0 + kHaloPlaneBytes + k * 32, 16, asbo),
-                        make_desc_sw128(b0 + CMID * 128 + k * 32, 16, 1024), p.idesc1, accum);
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t accum = (c | tap | k) != 0 ? 1u : 0u;
+                umma_bf16(tm_acc1, da + 2 * k, dbw + 2 * k, p.idesc1, accum);
+                if (NP == 2)   // both cross terms as one e4m3 MMA of K = 32 (8-bit cross planes)
+                  umma_f8(tm_acc1 + CMID, da2 + 2 * k, dbw2 + 2 * k, p.idesc1, accum);
+              }
+              if (!p.w_resident) umma_commit(&b_empty[stage]);
+              if (tap == 8) {
+                umma_commit(&halo_empty[hb]);
+                if (c == NCH - 1) umma_commit(&acc1_full[acc1_slot(j)]);
+              }
             }
-            umma_commit(&b_empty[stage]);
-            advance();
+            __syncwarp();
+            if (!p.w_resident) advance();
             UB_T(3);
           }
-          umma_commit(&halo_empty[hb]);
         }
-        umma_commit(&acc1_full[acc1_slot(j)]);
       };
       // ---- GEMM 2: 1x1 convolution of tile j, A from tensor memory ----
       auto gemm2 = [&](int j) {
@@ -373,28 +398,33 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
         tc_fence_after();
         UB_T(5);
         for (int c = 0; c < NCH; ++c) {
+          if (p.w_resident) { stage = uint32_t(9 * NCH + c); phase = 0; }
           mbar_wait(&b_full[stage], phase);
           tc_fence_after();
           UB_T(2);
           const uint32_t b0 = sbase + p.off_b + stage * p.b_stage_bytes;
+          const uint64_t dbw = desc_of(desc_b_hi, b0);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t accum = (c | k) != 0 ? 1u : 0u;
-            const uint32_t a_hi = tm_a2 + uint32_t(c * 4 + k) * 8u;
-            if (NP == 2) {
-              umma_bf16_ts(tm_acc2, a_hi, make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc2w, accum);
-              umma_bf16_ts(tm_acc2 + p.Cout, a_hi + CMID / 2, make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc2c, 1u);
-            } else {
-              umma_bf16_ts(tm_acc2, a_hi, make_desc_sw128(b0 + k * 32, 16, 1024), p.idesc2c, accum);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t accum = (c | k) != 0 ? 1u : 0u;
+              const uint32_t a_hi = tm_a2 + uint32_t(c * 4 + k) * 8u;
+              if (NP == 2) {
+                umma_bf16_ts(tm_acc2, a_hi, dbw + 2 * k, p.idesc2w, accum);
+                umma_bf16_ts(tm_acc2 + p.Cout, a_hi + CMID / 2, dbw + 2 * k, p.idesc2c, 1u);
+              } else {
+                umma_bf16_ts(tm_acc2, a_hi, dbw + 2 * k, p.idesc2c, accum);
+              }
             }
+            if (!p.w_resident) umma_commit(&b_empty[stage]);
+            if (c == NCH - 1) umma_commit(acc2_full);
           }
-          umma_commit(&b_empty[stage]);
-          advance();
+          __syncwarp();
+          if (!p.w_resident) advance();
           UB_T(6);
         }
-        umma_commit(acc2_full);
       };
-      // Double-buffered 3x3 accumulator: the 3x3 GEMM of tile j+1 is issued BEFORE this thread waits for the workers' 1x1
+      // Double-buffered 3x3 accumulator: the 3x3 GEMM of tile j+1 is issued BEFORE this warp waits for the workers' 1x1
       // operand of tile j, so the tensor pipe keeps working through the workers' accumulator -> operand pass.
       if (db) gemm1(0);
       for (int j = 0; j < nt; ++j) {
@@ -405,7 +435,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
         }
         gemm2(j);
       }
-      if (prof)
+      if (prof && leader)
         for (int i = 0; i < 8; ++i) atomicAdd(&g_ub_prof[(p.tail ? 16 : 0) + 8 + i], (unsigned long long)acc_[i]);
     }
   } else if (warp >= 4) {
@@ -862,10 +892,15 @@ int upblock_launch(const UpBlockArgs& a, cudaStream_t st) {
     return 1;
   }
   size_t stages = (budget - off - fixed_tail) / kp.b_stage_bytes;
-  if (stages > 8) stages = 8;
+  // all 9 * nch + nch weight tiles resident (conv9 in bf16 mode: 10 stages of 8 KB) where they fit: loaded once per CTA
+  static const bool no_resident = getenv("NSM_UB_NO_RESIDENT") != nullptr;
+  const size_t all_tiles = size_t(10) * nch;
+  kp.w_resident = (!no_resident && all_tiles <= 16 && stages >= all_tiles) ? 1u : 0u;
+  if (kp.w_resident) stages = all_tiles;
+  if (stages > 8 && !kp.w_resident) stages = 8;
   {
     static const int force = getenv("NSM_UB_BSTAGES") ? atoi(getenv("NSM_UB_BSTAGES")) : 0;
-    if (force >= 2 && size_t(force) < stages) stages = size_t(force);
+    if (force >= 2 && size_t(force) < stages && !kp.w_resident) stages = size_t(force);
   }
   kp.b_stages = uint32_t(stages);
   off += stages * kp.b_stage_bytes;

@@ -90,7 +90,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -175,8 +175,13 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && cta_rank == 0) {   // pairs: the leader issues for both
+    // uniform control flow for the warp, one elected lane issues: straight-line UTCHMMA with descriptors advanced by one
+    // 64-bit add (under `if (lane == 0)` every tcgen05 instruction sat in an ELECT / BRA.U.ANY loop, see conv_gemm.cu)
+    if (cta_rank == 0) {   // pairs: the leader issues for both
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint64_t desc_hi = make_desc_sw128(0, Cfg::BOX_BYTES, 1024);
+      auto desc_of = [&](uint32_t addr) { return desc_hi | uint64_t((addr & 0x3FFFFu) >> 4); };
       for (int item = it_first; item < p.total_items; item += it_step) {
         int cob, cib, tap, split;
         wgrad_decode(p, item, cob, cib, tap, split);
@@ -193,29 +198,33 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint32_t b_hi = a_hi + NP * Cfg::A_BYTES;
+            const uint64_t da_hi = desc_of(a_hi), db_hi = desc_of(b_hi);
+            const uint64_t da_lo = desc_of(a_hi + Cfg::A_BYTES), db_lo = desc_of(b_hi + Cfg::B_BYTES);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < Cfg::KSTEPS; ++k) {   // UMMA_K = 16 pixels = 16 rows of 128 B = 2048 B per step
-              const uint32_t accum = ((pt - c0) | k) != 0 ? 1u : 0u;
-              const uint64_t da_hi = make_desc_sw128(a_hi + k * 2048, Cfg::BOX_BYTES, 1024);
-              const uint64_t db_hi = make_desc_sw128(b_hi + k * 2048, Cfg::BOX_BYTES, 1024);
-              if (PAIR) umma_bf16_pair(d_main, da_hi, db_hi, p.idesc, accum);
-              else umma_bf16(d_main, da_hi, db_hi, p.idesc, accum);
-              if (NP == 2) {
-                const uint64_t da_lo = make_desc_sw128(a_hi + Cfg::A_BYTES + k * 2048, Cfg::BOX_BYTES, 1024);
-                const uint64_t db_lo = make_desc_sw128(b_hi + Cfg::B_BYTES + k * 2048, Cfg::BOX_BYTES, 1024);
-                umma_bf16(d_cross, da_hi, db_lo, p.idesc, accum);
-                umma_bf16(d_cross, da_lo, db_hi, p.idesc, 1u);
+              for (int k = 0; k < Cfg::KSTEPS; ++k) {   // UMMA_K = 16 pixels = 16 rows of 128 B = 2048 B per step (+128 in the address field)
+                const uint32_t accum = ((pt - c0) | k) != 0 ? 1u : 0u;
+                const uint64_t step = uint64_t(k) * (2048 >> 4);
+                if (PAIR) umma_bf16_pair(d_main, da_hi + step, db_hi + step, p.idesc, accum);
+                else umma_bf16(d_main, da_hi + step, db_hi + step, p.idesc, accum);
+                if (NP == 2) {
+                  umma_bf16(d_cross, da_hi + step, db_lo + step, p.idesc, accum);
+                  umma_bf16(d_cross, da_lo + step, db_hi + step, p.idesc, 1u);
+                }
+              }
+              if (PAIR) umma_commit_pair(&empty_bar[stage]);
+              else umma_commit(&empty_bar[stage]);
+              if (pt + 1 == c1) {
+                if (PAIR) umma_commit_pair(&tfull_bar[acc]);
+                else umma_commit(&tfull_bar[acc]);
               }
             }
-            if (PAIR) umma_commit_pair(&empty_bar[stage]);
-            else umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          if (PAIR) umma_commit_pair(&tfull_bar[acc]);
-          else umma_commit(&tfull_bar[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }

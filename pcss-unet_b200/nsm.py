@@ -64,6 +64,8 @@ def _declare(lib):
     lib.nsm_last_error.restype = c_char_p
     lib.nsm_version.restype = c_int
     lib.nsm_launch_count.restype = c_longlong
+    lib.nsm_tmap_cache_stats.restype = None
+    lib.nsm_tmap_cache_stats.argtypes = [POINTER(c_longlong), POINTER(c_longlong)]
     lib.nsm_check_device.restype = c_int
     lib.nsm_unet_packed_bytes.restype = c_size_t
     lib.nsm_unet_packed_bytes.argtypes = [c_int]
@@ -163,7 +165,7 @@ TRAIN_EXPORTS = [
 ]
 
 EXPORTS = TRAIN_EXPORTS + [
-    "nsm_launch_count", "nsm_unet_infer_u8", "nsm_unet_infer_host_u8", "nsm_unet_pipe_workspace_bytes",
+    "nsm_launch_count", "nsm_tmap_cache_stats", "nsm_unet_infer_u8", "nsm_unet_infer_host_u8", "nsm_unet_pipe_workspace_bytes",
     "nsm_unet_pipe_create", "nsm_unet_pipe_submit", "nsm_unet_pipe_sync", "nsm_unet_pipe_destroy",
     "nsm_last_error", "nsm_version", "nsm_check_device", "nsm_unet_packed_bytes", "nsm_unet_pack",
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
@@ -222,6 +224,13 @@ def mode_planes(mode: int) -> int:
 
 def launch_count() -> int:
     return int(lib().nsm_launch_count())
+
+
+def tmap_cache_stats():
+    """(hits, misses) of the TMA-descriptor table since the library was loaded."""
+    h, m = c_longlong(0), c_longlong(0)
+    lib().nsm_tmap_cache_stats(ctypes.byref(h), ctypes.byref(m))
+    return int(h.value), int(m.value)
 
 
 def profile_enable(on: bool):

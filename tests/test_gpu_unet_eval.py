@@ -217,3 +217,18 @@ def test_rejects_bad_input(nsm):
         net(torch.zeros(1, 4, 8, 8, device="cuda"))
     with pytest.raises(nsm.NsmError):
         net(torch.zeros(1, 4, 32, 32))          # CPU tensor: no fallback
+
+
+def test_tma_descriptors_are_encoded_once(nsm):
+    """Steady state: a frame of the same size through the same model adds hits to the TMA-descriptor table and no
+    misses (no cuTensorMapEncodeTiled call per launch), and the cached descriptors give the same output bit for bit."""
+    P, x = calibrated((1, 4, 70, 90), seed=7)
+    net = make_net(P, "fp32")
+    xd = x.cuda()
+    with torch.inference_mode():
+        y0 = net(xd).clone()
+        h0, m0 = nsm.tmap_cache_stats()
+        y1 = net(xd).clone()
+        h1, m1 = nsm.tmap_cache_stats()
+    assert m0 > 0 and m1 == m0 and h1 > h0, (h0, m0, h1, m1)
+    assert torch.equal(y0, y1)
