@@ -522,7 +522,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // (uniform control flow for the warp, one elected lane issues the copies: straight-line UTMALDG, like the MMA warp)
+    {
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0;
       for (int item = it_first; item < it_count; item += it_step) {
         int n, y0, x0, nb;
@@ -535,11 +537,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + NP * Cfg::A_BYTES;
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_4d(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
-            if (NP == 2) tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
-            tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
-            if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
+            if (leader) {
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_4d(sa, &tmA0, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+              if (NP == 2) tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * kKChunk, x0 + dx, y0 + dy, n);
+              tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
+              if (NP == 2) tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * kKChunk, brow);
+            }
+            __syncwarp();
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -834,7 +839,9 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // (uniform control flow for the warp, one elected lane issues the copies)
+    {
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0;
       for (int item = it_first; item < it_count; item += it_step) {
         int n, y0, x0, nb;
@@ -847,33 +854,32 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + 2 * Cfg::A_BYTES;
-            if (PAIR) {
-              // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the pair
-              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-              const int brow = nb * BN + cta_rank * (BN / 2);   // this CTA's rows of the weight tile
-              tma_load_4d_pair(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
-              tma_load_4d_pair(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
-              tma_load_2d_pair(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
-              tma_load_2d_pair(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
-              if (++stage == Cfg::STAGES) {
-                stage = 0;
-                phase ^= 1;
+            if (leader) {
+              if (PAIR) {
+                // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the pair
+                if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                const int brow = nb * BN + cta_rank * (BN / 2);   // this CTA's rows of the weight tile
+                tma_load_4d_pair(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
+                tma_load_4d_pair(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
+                tma_load_2d_pair(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
+                tma_load_2d_pair(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
+              } else {
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_4d(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
+                tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
+                if (MC > 1) {   // this CTA's slice of the weight rows, into every CTA of the cluster
+                  const int rows = BN / MC;
+                  uint8_t* sl = sb + cta_rank * rows * 64;
+                  tma_load_2d_mc(sl, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN + cta_rank * rows, kAllCtas);
+                  tma_load_2d_mc(sl + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK,
+                                 nb * BN + cta_rank * rows, kAllCtas);
+                } else {
+                  tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
+                  tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
+                }
               }
-              continue;
             }
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_4d(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
-            tma_load_4d(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
-            if (MC > 1) {   // this CTA's slice of the weight rows, into every CTA of the cluster
-              const int rows = BN / MC;
-              uint8_t* sl = sb + cta_rank * rows * 64;
-              tma_load_2d_mc(sl, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN + cta_rank * rows, kAllCtas);
-              tma_load_2d_mc(sl + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK,
-                             nb * BN + cta_rank * rows, kAllCtas);
-            } else {
-              tma_load_2d(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
-              tma_load_2d(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, nb * BN);
-            }
+            __syncwarp();
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1;

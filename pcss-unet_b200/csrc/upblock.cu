@@ -210,7 +210,9 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
 
   if (warp == 0) {
     // ===================== weight producer: 3x3 tiles (chunk, tap), then the 1x1 tiles (chunk) =====================
-    if (lane == 0) {
+    // (uniform control flow for the warp, one elected lane issues the copies)
+    {
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0;
       auto advance = [&]() {
         if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
@@ -220,9 +222,12 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
           for (int tap = 0; tap < 9; ++tap) {
             if (!p.w_resident) mbar_wait(&b_empty[stage], phase ^ 1);
             uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
-            mbar_expect_tx(&b_full[stage], NP * CMID * 128);
-            tma_load_2d(sb, &tmW3a, &b_full[stage], tap * CMID + c * 64, 0);
-            if (NP == 2) tma_load_2d(sb + CMID * 128, &tmW3b, &b_full[stage], tap * CMID + c * 64, 0);
+            if (leader) {
+              mbar_expect_tx(&b_full[stage], NP * CMID * 128);
+              tma_load_2d(sb, &tmW3a, &b_full[stage], tap * CMID + c * 64, 0);
+              if (NP == 2) tma_load_2d(sb + CMID * 128, &tmW3b, &b_full[stage], tap * CMID + c * 64, 0);
+            }
+            __syncwarp();
             advance();
           }
       };
@@ -230,9 +235,12 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
         for (int c = 0; c < NCH; ++c) {
           if (!p.w_resident) mbar_wait(&b_empty[stage], phase ^ 1);
           uint8_t* sb = smem + p.off_b + stage * p.b_stage_bytes;
-          mbar_expect_tx(&b_full[stage], NP * p.Cout * 128);
-          tma_load_2d(sb, &tmW1a, &b_full[stage], c * 64, 0);
-          if (NP == 2) tma_load_2d(sb + p.Cout * 128, &tmW1b, &b_full[stage], c * 64, 0);   // lo rows right after hi rows
+          if (leader) {
+            mbar_expect_tx(&b_full[stage], NP * p.Cout * 128);
+            tma_load_2d(sb, &tmW1a, &b_full[stage], c * 64, 0);
+            if (NP == 2) tma_load_2d(sb + p.Cout * 128, &tmW1b, &b_full[stage], c * 64, 0);   // lo rows right after hi rows
+          }
+          __syncwarp();
           advance();
         }
       };
@@ -261,6 +269,7 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
     // a few float divisions per lane, off the workers' critical path here), lanes 0-5 the 3-row strips' source-row windows;
     // per (tile, chunk) job: lane 0 the TMA load of the source box.  Tables ring through kTabs buffers (tab_full / tab_empty),
     // source boxes through src_bufs buffers.
+    const bool leader2 = elect_one();
     for (int j = 0, q = 0; j < nt; ++j) {
       const TileCoord t = ub_tile(p, int(blockIdx.x) + j * int(gridDim.x));
       int sy0, sx0;
@@ -320,10 +329,10 @@ upblock_kernel(const __grid_constant__ CUtensorMap tmS0, const __grid_constant__
       if (lane == 0) mbar_arrive(&tab_full[j % kTabs]);   // (mbarrier arrive has release semantics for the table writes above)
       // ---- the source boxes of the tile's chunks
       for (int c = 0; c < NCH; ++c, ++q) {
-        if (lane == 0) {
-          const uint32_t sb = uint32_t(q) % p.src_bufs, use = uint32_t(q) / p.src_bufs;
-          uint8_t* dst = smem + p.off_src + sb * NP * p.src_plane_bytes;
-          mbar_wait(&src_empty[sb], (use & 1) ^ 1);
+        const uint32_t sb = uint32_t(q) % p.src_bufs, use = uint32_t(q) / p.src_bufs;
+        uint8_t* dst = smem + p.off_src + sb * NP * p.src_plane_bytes;
+        mbar_wait(&src_empty[sb], (use & 1) ^ 1);
+        if (leader2) {
           mbar_expect_tx(&src_full[sb], NP * p.sbw * p.sbh * 128);
           tma_load_4d(dst, &tmS0, &src_full[sb], c * 64, sx0, sy0, t.n);
           if (NP == 2) tma_load_4d(dst + p.src_plane_bytes, &tmS1, &src_full[sb], c * 64, sx0, sy0, t.n);

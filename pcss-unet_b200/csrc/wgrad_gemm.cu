@@ -118,7 +118,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // (uniform control flow for the warp, one elected lane issues the copies: straight-line UTMALDG)
+    {
+      const bool leader = elect_one();
       uint32_t stage = 0, phase = 0;
       for (int item = it_first; item < p.total_items; item += it_step) {
         int cob, cib, tap, split;
@@ -138,34 +140,33 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + NP * Cfg::A_BYTES;
-          if (PAIR) {   // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the pair
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          if (leader) {
+            if (PAIR) {   // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the pair
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
-              tma_load_4d_pair(sa + g * Cfg::BOX_BYTES, &tmA0, &full_bar[stage], cob * 128 + g * 64, x0, y0, n);
+              for (int g = 0; g < 2; ++g)
+                tma_load_4d_pair(sa + g * Cfg::BOX_BYTES, &tmA0, &full_bar[stage], cob * 128 + g * 64, x0, y0, n);
 #pragma unroll
-            for (int g = 0; g < BN / 64 / CG; ++g)
-              tma_load_4d_pair(sb + g * Cfg::BOX_BYTES, &tmB0, &full_bar[stage], ci0 + g * 64, x0 + dx, y0 + dy, n);
-            if (++stage == Cfg::STAGES) {
-              stage = 0;
-              phase ^= 1;
+              for (int g = 0; g < BN / 64 / CG; ++g)
+                tma_load_4d_pair(sb + g * Cfg::BOX_BYTES, &tmB0, &full_bar[stage], ci0 + g * 64, x0 + dx, y0 + dy, n);
+            } else {
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+              for (int pl = 0; pl < NP; ++pl) {
+                const CUtensorMap* ma = pl == 0 ? &tmA0 : &tmA1;
+                const CUtensorMap* mb = pl == 0 ? &tmB0 : &tmB1;
+#pragma unroll
+                for (int g = 0; g < 2; ++g)   // dz at the output pixel; channels beyond Cout are zero-filled
+                  tma_load_4d(sa + pl * Cfg::A_BYTES + g * Cfg::BOX_BYTES, ma, &full_bar[stage], cob * 128 + g * 64, x0,
+                              y0, n);
+#pragma unroll
+                for (int g = 0; g < BN / 64; ++g)   // x at the tap-shifted pixel
+                  tma_load_4d(sb + pl * Cfg::B_BYTES + g * Cfg::BOX_BYTES, mb, &full_bar[stage], cib * BN + g * 64,
+                              x0 + dx, y0 + dy, n);
+              }
             }
-            continue;
           }
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-#pragma unroll
-          for (int pl = 0; pl < NP; ++pl) {
-            const CUtensorMap* ma = pl == 0 ? &tmA0 : &tmA1;
-            const CUtensorMap* mb = pl == 0 ? &tmB0 : &tmB1;
-#pragma unroll
-            for (int g = 0; g < 2; ++g)   // dz at the output pixel; channels beyond Cout are zero-filled
-              tma_load_4d(sa + pl * Cfg::A_BYTES + g * Cfg::BOX_BYTES, ma, &full_bar[stage], cob * 128 + g * 64, x0, y0,
-                          n);
-#pragma unroll
-            for (int g = 0; g < BN / 64; ++g)   // x at the tap-shifted pixel
-              tma_load_4d(sb + pl * Cfg::B_BYTES + g * Cfg::BOX_BYTES, mb, &full_bar[stage], cib * BN + g * 64, x0 + dx,
-                          y0 + dy, n);
-          }
+          __syncwarp();
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;

@@ -6,7 +6,10 @@
 UTCHMMA / UTCQMMA = tcgen05.mma kind::f16 / kind::f8f6f4 (".2CTA" = cta_group::2), LDTM / STTM = tcgen05.ld / tcgen05.st (TMEM <-> registers; STTM: the fused blocks write the 1x1 GEMM's A operand to TMEM),
 UTMALDG / UTMASTG = TMA tensor loads / stores (cp.async.bulk.tensor), UBLKCP = 1-D bulk copies (cp.async.bulk: the TMA-staged
 BatchNorm backward), UTCBAR = tcgen05.commit, HMMA = mma.sync (warp-level
-tensor cores of the 16-channel head / tail stages), SYNCS = mbarrier operations.  Runs on the CPU box (cuobjdump only)."""
+tensor cores of the 16-channel head / tail stages), SYNCS = mbarrier operations, BRA.U.ANY = the loop the compiler wraps around a
+uniform-datapath instruction (UTC*MMA, UTMALDG, UTCBAR ...) issued under divergent control flow such as `if (lane == 0)`: one
+per tcgen05 / TMA instruction before the MMA and producer warps went to warp-uniform control flow + elect.sync, 0 there now
+(the rest: per-warp TMA loads / stores of the epilogues).  Runs on the CPU box (cuobjdump only)."""
 import collections
 import os
 import re
@@ -17,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pcss-unet_b200", "libnsm_b200.so")
 PATS = [("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("UTCHMMA", r"\bUTCHMMA\b(?!\.2CTA)"), ("UTCQMMA.2CTA", r"\bUTCQMMA\.2CTA"),
         ("UTCQMMA", r"\bUTCQMMA\b(?!\.2CTA)"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"), ("UBLKCP", r"\bUBLKCP"),
-        ("UTCBAR", r"\bUTCBAR"), ("HMMA", r"\bHMMA"), ("SYNCS", r"\bSYNCS"), ("STL/LDL", r"\b(STL|LDL)\b")]
+        ("UTCBAR", r"\bUTCBAR"), ("HMMA", r"\bHMMA"), ("SYNCS", r"\bSYNCS"), ("STL/LDL", r"\b(STL|LDL)\b"),
+        ("BRA.U.ANY", r"\bBRA\.U\.ANY")]
 
 
 def main():
