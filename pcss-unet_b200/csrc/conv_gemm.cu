@@ -172,6 +172,7 @@ struct ConvKernelParams {
   int fmt;
   int chunk_kb;       // fp32 modes: k-blocks per TMEM accumulation chunk
   int x8;             // plane 1 of both operands holds 8-bit cross-term operands (kFmtF16X8, nsm_common.cuh)
+  int w_evict_last;   // CTA-pair kernel: weight boxes are loaded with the L2 evict_last policy (NSM_NO_W_EVICT_LAST=1: off)
   float cross_scale;  // factor of the cross accumulator when the chunk results are summed (2^-17 with x8, else 1)
   uint32_t idesc_hi;    // M = 128 (256 for CTA pairs), N = BN
   uint32_t idesc_wide;  // M = 128, N = 2*BN: hi+lo modes, a_hi x [w_hi | w_lo] in one instruction
@@ -842,6 +843,7 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     // (uniform control flow for the warp, one elected lane issues the copies)
     {
       const bool leader = elect_one();
+      const uint64_t w_policy = l2_policy_evict_last();
       uint32_t stage = 0, phase = 0;
       for (int item = it_first; item < it_count; item += it_step) {
         int n, y0, x0, nb;
@@ -861,8 +863,13 @@ conv_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
                 const int brow = nb * BN + cta_rank * (BN / 2);   // this CTA's rows of the weight tile
                 tma_load_4d_pair(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
                 tma_load_4d_pair(sa + Cfg::A_BYTES, &tmA1, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
-                tma_load_2d_pair(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
-                tma_load_2d_pair(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
+                if (p.w_evict_last) {   // the weight matrix stays in L2 (every work item streams its column block again)
+                  tma_load_2d_pair_hint(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow, w_policy);
+                  tma_load_2d_pair_hint(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow, w_policy);
+                } else {
+                  tma_load_2d_pair(sb, &tmB0, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
+                  tma_load_2d_pair(sb + Cfg::B_BYTES, &tmB1, &full_bar[stage], tap * p.Cin + kc * Cfg::BK, brow);
+                }
               } else {
                 mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                 tma_load_4d(sa, &tmA0, &full_bar[stage], kc * Cfg::BK, x0 + dx, y0 + dy, n);
@@ -1194,6 +1201,10 @@ int conv_gemm_launch(const ConvShape& s, const Planes& in, const Planes& w, cons
   kp.fmt = s.fmt == kFmtF16X8 ? kFmtF16x2 : s.fmt;
   kp.chunk_kb = g_chunk_kb;
   kp.x8 = s.fmt == kFmtF16X8 ? 1 : 0;
+  {
+    static const bool off = getenv("NSM_NO_W_EVICT_LAST") != nullptr;
+    kp.w_evict_last = off ? 0 : 1;
+  }
   kp.cross_scale = kp.x8 ? kX8CrossScale : 1.f;
   const uint32_t ef = fmt_is_f16(s.fmt) ? kFmtF16 : kFmtBF16;  // fp16 / e4m3 share the descriptor code 0
   kp.idesc_hi = make_idesc_f16(wide_pair ? 256 : 128, BN, ef, ef, 0, 0);
