@@ -97,7 +97,7 @@ struct TmapKeyHash {
 static std::mutex g_tmap_mu;
 static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
 static std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
-constexpr size_t kTmapCacheMax = 8192;   // entries of 128 B + key; flushed when full (a new shape / buffer set)
+constexpr size_t kTmapCacheMax = 65536;  // entries of 128 B + key (<= 17 MB of host memory); flushed when full
 void tmap_cache_stats(long long* hits, long long* misses) {
   *hits = g_tmap_hits.load(std::memory_order_relaxed);
   *misses = g_tmap_misses.load(std::memory_order_relaxed);
