@@ -187,6 +187,14 @@ int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, voi
 int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
                         long long numel, float coef_l1, float coef_pert, float* grad, nsm_acc* acc, void* stream);
 
+/* customLoss.EnhancedCustomLoss (customLoss.py:195-238; not used by main.py, which takes pert_loss.EnhancedCustomLoss):
+ *   compute_perturbation_loss :226-231   out = clamp(x + eps * noise, lo, hi)      (noise: the caller's randn draw)
+ *   F.mse_loss(output, perturbed_output) :238   acc[0] += sum (out - ref)^2;  diff = out - ref (may be NULL): the
+ *   gradient of the mean is 2 * diff / numel.  acc: one slot, zeroed by the caller. */
+int nsm_add_noise_clamp(const float* x, const float* noise, long long numel, float eps, float lo, float hi, float* out,
+                        void* stream);
+int nsm_mse_loss_fwd_bwd(const float* out, const float* ref, long long numel, float* diff, nsm_acc* acc, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Perceptual term: MultiLayerVGGLoss (customLoss.py:7-90) = weighted L1 between VGG19 features of output and target.
  * The VGG19 convolutions run through nsm_conv_fwd (lrelu = 2 for the fused ReLU, 0 for a tapped pre-activation

@@ -760,6 +760,23 @@ int nsm_upsample_match(const void* const* src, int N, int hs, int ws, int C, voi
   return upsample_match(s, N, hs, ws, C, d, hd, wd, mode, static_cast<cudaStream_t>(stream));
 }
 
+int nsm_add_noise_clamp(const float* x, const float* noise, long long numel, float eps, float lo, float hi, float* out,
+                        void* stream) {
+  if (!x || !noise || !out) {
+    set_error("nsm_add_noise_clamp: null pointer");
+    return 1;
+  }
+  ProfScope ps_("add_noise_clamp", 0.0, double(numel) * 12.0, S(stream));
+  return add_noise_clamp(x, noise, numel, eps, lo, hi, out, S(stream));
+}
+int nsm_mse_loss_fwd_bwd(const float* out, const float* ref, long long numel, float* diff, nsm_acc* acc, void* stream) {
+  if (!out || !ref || !acc) {
+    set_error("nsm_mse_loss_fwd_bwd: null pointer");
+    return 1;
+  }
+  ProfScope ps_("mse_loss", 0.0, double(numel) * 4.0 * (diff ? 3 : 2), S(stream));
+  return mse_loss_fwd_bwd(out, ref, numel, diff, A(acc), S(stream));
+}
 int nsm_l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
                         long long numel, float coef_l1, float coef_pert, float* grad, nsm_acc* acc, void* stream) {
   ProfScope ps_("l1_loss", 0.0, double(numel) * 4.0 * (3 + n_perturbed), S(stream));

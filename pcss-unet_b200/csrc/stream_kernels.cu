@@ -1340,6 +1340,54 @@ int l1_loss_fwd_bwd(const float* out, const float* target, const float* const* p
 }
 
 // ------------------------------------------------------------------------------------------------
+// customLoss.EnhancedCustomLoss (customLoss.py:195-238): input jitter and the MSE stability term
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_noise_clamp_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                                              long long numel, float eps, float lo, float hi,
+                                                              float* __restrict__ out) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < numel; i += (long long)gridDim.x * 256) {
+    // torch: noise * eps, then inputs + (that), then clamp -- two roundings, no fused multiply-add
+    const float v = __fadd_rn(x[i], __fmul_rn(noise[i], eps));
+    out[i] = fminf(fmaxf(v, lo), hi);   // (a NaN input stays NaN in torch.clamp; fmaxf/fminf would drop it)
+    if (v != v) out[i] = v;
+  }
+}
+
+int add_noise_clamp(const float* x, const float* noise, long long numel, float eps, float lo, float hi, float* out,
+                    cudaStream_t st) {
+  if (numel <= 0) return 0;
+  add_noise_clamp_kernel<<<grid_for(numel, 256, 148 * 8), 256, 0, st>>>(x, noise, numel, eps, lo, hi, out);
+  NSM_CHECK_LAUNCH("add_noise_clamp");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) mse_loss_kernel(const float* __restrict__ out, const float* __restrict__ ref,
+                                                       long long numel, float* __restrict__ diff, Acc* acc) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < numel; i += (long long)gridDim.x * 256) {
+    const float d = out[i] - ref[i];
+    s = fmaf(d, d, s);
+    if (diff) diff[i] = d;
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += double(red[k]);
+    if (t != 0.0) acc_add(&acc[0], t);   // order-independent (nsm_common.cuh: Acc)
+  }
+}
+
+int mse_loss_fwd_bwd(const float* out, const float* ref, long long numel, float* diff, Acc* acc, cudaStream_t st) {
+  if (numel <= 0) return 0;
+  mse_loss_kernel<<<grid_for(numel, 256, 148 * 8), 256, 0, st>>>(out, ref, numel, diff, acc);
+  NSM_CHECK_LAUNCH("mse_loss");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-channel sums over [S][C][HW] in fp64 (two-pass statistics like calculate_dataset_stats.py)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) channel_sums_kernel(const float* __restrict__ x, long long S, int C,

@@ -64,6 +64,9 @@ int upsample_match(const Planes& src, int N, int hs, int ws, int C, const Planes
 
 // ---- objective ---------------------------------------------------------------------------------------------------
 // acc[0] += sum|o-t|, acc[1] += sum_i sum|o-y_i|, acc[2] += #(o<0 or o>1); grad = a_l1*sign(o-t)+a_p*sum_i sign(o-y_i)
+int add_noise_clamp(const float* x, const float* noise, long long numel, float eps, float lo, float hi, float* out,
+                    cudaStream_t st);
+int mse_loss_fwd_bwd(const float* out, const float* ref, long long numel, float* diff, Acc* acc, cudaStream_t st);
 int l1_loss_fwd_bwd(const float* out, const float* target, const float* const* perturbed, int n_perturbed,
                     long long numel, float coef_l1, float coef_pert, float* grad, Acc* acc, cudaStream_t st);
 

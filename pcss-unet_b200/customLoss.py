@@ -218,3 +218,59 @@ class CustomLoss(nn.Module):
                 vgg = torch.as_tensor(self.vgg_loss(output.detach(), target), dtype=torch.float32,
                                       device=output.device).detach()
         return self.alpha * l1 + (1 - self.alpha) * vgg
+
+
+class _FusedMSE(torch.autograd.Function):
+    """mean (o - r)^2 with the difference kept by the same kernel pass for the gradient 2 (o - r) / N."""
+
+    @staticmethod
+    def forward(ctx, output, ref):
+        o32 = output.detach().to(torch.float32).contiguous()
+        total, diff = nsm.mse_loss_fwd_bwd(o32, ref.detach(), want_diff=True)
+        ctx.save_for_backward(diff)
+        ctx.numel = o32.numel()
+        ctx.out_dtype = output.dtype
+        return (total / o32.numel()).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (diff,) = ctx.saved_tensors
+        return (diff * (g * (2.0 / ctx.numel))).to(ctx.out_dtype), None
+
+
+class EnhancedCustomLoss(nn.Module):
+    """customLoss.py:195-238 (the variant kept in customLoss.py; main.py:938 uses pert_loss.EnhancedCustomLoss instead):
+    ``forward(model, output, target, inputs) -> (alpha * L1 + (1 - alpha) * vgg + beta * perturbation, components)`` with
+    perturbation = ``F.mse_loss(output, model(clamp(inputs + 0.01 * randn_like(inputs), -10, 10)))`` under ``no_grad``.
+    The noise is one ``torch.randn_like`` draw like the reference's (same generator state -> same noise); jitter + clamp,
+    the L1 and the MSE value / gradient are one kernel pass each."""
+
+    def __init__(self, device, alpha=0.9, beta=0.05, vgg_loss="auto"):
+        super().__init__()
+        self.alpha = alpha
+        self.beta = beta
+        self.l1 = L1Loss()
+        self.vgg_loss = make_vgg_term(device, vgg_loss)
+
+    def forward(self, model, output, target, inputs):
+        nsm.require_device(output)
+        l1_loss = self.l1(output, target)
+        if self.vgg_loss is None:
+            vgg_loss = torch.zeros((), dtype=torch.float32, device=output.device)
+        else:
+            with torch.no_grad():
+                vgg_loss = torch.as_tensor(self.vgg_loss(output.detach(), target), dtype=torch.float32,
+                                           device=output.device).detach()
+        perturbation_loss = self.compute_perturbation_loss(model, output, inputs)
+        total_loss = self.alpha * l1_loss + (1 - self.alpha) * vgg_loss + self.beta * perturbation_loss
+        loss_components = {"l1_loss": l1_loss, "vgg_loss": vgg_loss, "perturbation_loss": perturbation_loss}
+        return total_loss, loss_components
+
+    def compute_perturbation_loss(self, model, output, inputs):
+        epsilon = 0.01
+        x = inputs.detach().to(torch.float32)
+        noise = torch.randn_like(x)                                    # customLoss.py:225 (same draw, same generator)
+        perturbed_inputs = nsm.add_noise_clamp(x, noise, epsilon, -10.0, 10.0).to(inputs.dtype)
+        with torch.no_grad():                                          # no second-order terms (customLoss.py:233)
+            perturbed_output = model(perturbed_inputs)
+        return _FusedMSE.apply(output, perturbed_output)

@@ -89,6 +89,8 @@ def _declare(lib):
     lib.nsm_unet_set_fused_decoder.argtypes = [c_int]
     lib.nsm_upsample_match.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int, POINTER(c_void_p), c_int,
                                        c_int, c_int, c_void_p]
+    lib.nsm_add_noise_clamp.argtypes = [c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_void_p, c_void_p]
+    lib.nsm_mse_loss_fwd_bwd.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]
     lib.nsm_l1_loss_fwd_bwd.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_longlong, c_float, c_float,
                                         c_void_p, c_void_p, c_void_p]
     lib.nsm_channel_sums.argtypes = [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p]
@@ -148,7 +150,8 @@ def _declare(lib):
             getattr(lib, name).restype = c_int
     for name in ("nsm_unet_infer_u8", "nsm_unet_infer_host_u8", "nsm_profile_enable", "nsm_profile_read", "nsm_unet_pack", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
                  "nsm_planes_to_nchw", "nsm_pack_conv_weight", "nsm_conv_fwd", "nsm_upsample_match",
-                 "nsm_l1_loss_fwd_bwd", "nsm_channel_sums", "nsm_standardize", "nsm_perturb"):
+                 "nsm_l1_loss_fwd_bwd", "nsm_channel_sums", "nsm_standardize", "nsm_perturb", "nsm_add_noise_clamp",
+                 "nsm_mse_loss_fwd_bwd"):
         getattr(lib, name).restype = c_int
 
 
@@ -165,7 +168,7 @@ TRAIN_EXPORTS = [
 ]
 
 EXPORTS = TRAIN_EXPORTS + [
-    "nsm_launch_count", "nsm_tmap_cache_stats", "nsm_unet_infer_u8", "nsm_unet_infer_host_u8", "nsm_unet_pipe_workspace_bytes",
+    "nsm_launch_count", "nsm_tmap_cache_stats", "nsm_add_noise_clamp", "nsm_mse_loss_fwd_bwd", "nsm_unet_infer_u8", "nsm_unet_infer_host_u8", "nsm_unet_pipe_workspace_bytes",
     "nsm_unet_pipe_create", "nsm_unet_pipe_submit", "nsm_unet_pipe_sync", "nsm_unet_pipe_destroy",
     "nsm_last_error", "nsm_version", "nsm_check_device", "nsm_unet_packed_bytes", "nsm_unet_pack",
     "nsm_unet_workspace_bytes", "nsm_unet_infer", "nsm_unet_infer_host", "nsm_unet_tap", "nsm_nchw_to_planes",
@@ -521,6 +524,29 @@ def l1_loss_fwd_bwd(out, target=None, perturbed=(), coef_l1=0.0, coef_pert=0.0, 
     check(lib().nsm_l1_loss_fwd_bwd(out.data_ptr(), ptr(tgt), arr, len(pert), n, coef_l1, coef_pert, ptr(grad),
                                     acc.data_ptr(), stream_ptr()), "nsm_l1_loss_fwd_bwd")
     return acc_to_double(acc), grad
+
+
+def add_noise_clamp(x, noise, eps, lo, hi):
+    """clamp(x + eps * noise, lo, hi) in one pass (customLoss.py:226-231)."""
+    x = x.contiguous()
+    noise = noise.contiguous()
+    assert x.dtype == torch.float32 and noise.dtype == torch.float32 and x.shape == noise.shape
+    out = torch.empty_like(x)
+    check(lib().nsm_add_noise_clamp(x.data_ptr(), noise.data_ptr(), x.numel(), eps, lo, hi, out.data_ptr(), stream_ptr()),
+          "nsm_add_noise_clamp")
+    return out
+
+
+def mse_loss_fwd_bwd(out, ref, want_diff=True):
+    """Returns (float64 device scalar sum (out-ref)^2, out - ref or None)."""
+    out = out.contiguous()
+    ref = ref.to(torch.float32).contiguous()
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    acc = acc_zeros(1, out.device)
+    diff = torch.empty_like(out) if want_diff else None
+    check(lib().nsm_mse_loss_fwd_bwd(out.data_ptr(), ref.data_ptr(), out.numel(), ptr(diff), acc.data_ptr(), stream_ptr()),
+          "nsm_mse_loss_fwd_bwd")
+    return acc_to_double(acc)[0], diff
 
 
 def channel_sums(x, means=None):

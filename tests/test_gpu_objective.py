@@ -190,3 +190,45 @@ def test_vgg_perceptual_term(nsm):
     got = crit(o.cuda(), t.cuda()).item()
     print(f"vgg 3x150x202: {got:.8f} vs stock PyTorch strict fp32 {want:.8f}")
     assert abs(got - want) <= 1e-4 * want
+
+
+def test_enhanced_custom_loss_of_customloss_py(nsm):
+    """customLoss.EnhancedCustomLoss (customLoss.py:195-238): alpha * L1 + (1 - alpha) * vgg + beta * MSE(output,
+    model(clamp(inputs + 0.01 * randn_like(inputs), -10, 10))) -- value, components and the gradient w.r.t. the output
+    against the same formula in stock PyTorch under the same generator state (vgg term off on both sides)."""
+    import torch.nn.functional as F
+    from customLoss import EnhancedCustomLoss
+    g = torch.Generator().manual_seed(11)
+    inputs = (torch.randn(2, 4, 33, 47, generator=g) * 4.0).cuda()
+    inputs[0, 0, 0, :4] = torch.tensor([11.0, -12.0, 9.995, -9.999])       # clamp is exercised
+    target = torch.rand(2, 1, 33, 47, generator=g).cuda()
+    w = torch.randn(1, 4, 3, 3, generator=g).cuda() * 0.3
+    model = lambda x: torch.sigmoid(F.conv2d(x, w, padding=1))              # noqa: E731  stand-in network (any callable)
+    crit = EnhancedCustomLoss("cuda", alpha=0.9, beta=0.05, vgg_loss=None)
+
+    out_a = model(inputs).detach().requires_grad_(True)
+    torch.manual_seed(123)
+    total, comp = crit(model, out_a, target, inputs)
+    total.backward()
+
+    out_b = out_a.detach().clone().requires_grad_(True)
+    torch.manual_seed(123)
+    noise = torch.randn_like(inputs) * 0.01                                  # customLoss.py:225-231
+    pin = torch.clamp(inputs + noise, -10.0, 10.0)
+    with torch.no_grad():
+        pout = model(pin)
+    l1 = F.l1_loss(out_b, target)
+    mse = F.mse_loss(out_b, pout)
+    ref = 0.9 * l1 + 0.05 * mse
+    ref.backward()
+
+    assert set(comp) == {"l1_loss", "vgg_loss", "perturbation_loss"}
+    l1, mse, ref = l1.detach(), mse.detach(), ref.detach()
+    assert abs(float(comp["l1_loss"]) - float(l1)) <= 1e-6 and float(comp["vgg_loss"]) == 0.0
+    assert float(mse) > 0 and abs(float(comp["perturbation_loss"]) - float(mse)) <= 1e-5 * float(mse)
+    assert abs(float(total) - float(ref)) <= 1e-6
+    assert torch.allclose(out_a.grad, out_b.grad, rtol=1e-5, atol=1e-9)
+    # the jitter kernel itself, bit for bit (two roundings like torch: noise * eps, then the add, then clamp)
+    torch.manual_seed(5)
+    nz = torch.randn_like(inputs)
+    assert torch.equal(nsm.add_noise_clamp(inputs, nz, 0.01, -10.0, 10.0), torch.clamp(inputs + nz * 0.01, -10.0, 10.0))
