@@ -223,7 +223,8 @@ def test_enhanced_custom_loss_of_customloss_py(nsm):
     ref.backward()
 
     assert set(comp) == {"l1_loss", "vgg_loss", "perturbation_loss"}
-    l1, mse, ref = l1.detach(), mse.detach(), ref.detach()
+    l1, mse, ref, total = l1.detach(), mse.detach(), ref.detach(), total.detach()
+    comp = {k: v.detach() for k, v in comp.items()}
     assert abs(float(comp["l1_loss"]) - float(l1)) <= 1e-6 and float(comp["vgg_loss"]) == 0.0
     assert float(mse) > 0 and abs(float(comp["perturbation_loss"]) - float(mse)) <= 1e-5 * float(mse)
     assert abs(float(total) - float(ref)) <= 1e-6
