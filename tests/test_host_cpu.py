@@ -61,3 +61,25 @@ def test_no_cpu_fallback():
     from customLoss import CustomLoss
     with pytest.raises(nsm.NsmError):
         CustomLoss("cpu")(torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8), None)
+    from customLoss import EnhancedCustomLoss
+    with pytest.raises(nsm.NsmError):
+        EnhancedCustomLoss("cpu", vgg_loss=None)(lambda x: x[:, :1], torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8),
+                                                 torch.rand(1, 4, 8, 8))
+
+
+def test_loss_classes_keep_the_reference_interfaces():
+    """Constructor arguments and the attributes the reference's trainer reads (main.py:215,265-277,938-944;
+    customLoss.py:196-201) -- host-side only, nothing is launched."""
+    import inspect
+    from customLoss import CustomLoss, EnhancedCustomLoss as EnhancedMSE
+    from pert_loss import EnhancedCustomLoss, PerturbationLoss
+    assert list(inspect.signature(CustomLoss.__init__).parameters)[:3] == ["self", "device", "alpha"]
+    assert list(inspect.signature(EnhancedMSE.__init__).parameters)[:4] == ["self", "device", "alpha", "beta"]
+    assert list(inspect.signature(EnhancedMSE.forward).parameters) == ["self", "model", "output", "target", "inputs"]
+    c = CustomLoss("cpu", alpha=0.8, vgg_loss=None)
+    assert c.alpha == 0.8 and callable(c.l1)
+    e = EnhancedMSE("cpu", alpha=0.7, beta=0.02, vgg_loss=None)
+    assert (e.alpha, e.beta) == (0.7, 0.02) and callable(e.l1) and e.vgg_loss is None
+    p = EnhancedCustomLoss("cpu", alpha=0.9, perturb_weight=0.1)
+    assert isinstance(p.perturbation_loss, PerturbationLoss)
+    assert list(inspect.signature(p.forward).parameters)[:4] == ["model", "output", "target", "inputs"]
