@@ -20,6 +20,7 @@ __all__ = [
     "unet_forward", "upsample_and_match", "upsample_and_match_bf16", "l1_loss", "custom_loss", "custom_loss_grad",
     "perturb_inputs", "perturbation_loss", "perturbation_loss_grad", "standardise",
     "conv_stage_eval", "train_step_grads", "calibrate_bn", "replay_conv5_checkpoint", "vgg_perceptual_loss",
+    "enhanced_mse_loss",
 ]
 
 # (name, in_ch, out_ch) in construction AND forward order -- Unetmodel.py:39,42,45,48,52,55,58,61
@@ -240,6 +241,24 @@ def custom_loss_grad(output, target, alpha=0.9):
     """d custom_loss / d output = alpha * sign(output - target) / numel  (autograd of nn.L1Loss;
     sign(0) = 0)."""
     return alpha * torch.sign(output - target) / output.numel()
+
+
+def enhanced_mse_loss(model_fn: Callable, output, target, inputs, alpha=0.9, beta=0.05, noise=None, vgg_const=0.0):
+    """customLoss.EnhancedCustomLoss.forward (customLoss.py:203-219) with compute_perturbation_loss (:221-238):
+    ``alpha * L1(output, target) + (1 - alpha) * vgg + beta * mse(output, model(clamp(inputs + 0.01 * noise, -10, 10)))``
+    where ``noise = torch.randn_like(inputs)`` (:225, passed in here so that the draw can be replayed) and the perturbed
+    forward runs under ``no_grad`` (:233).  Returns ``(total, {'l1_loss', 'vgg_loss', 'perturbation_loss'})`` like :212-219.
+    The VGG term is the detached constant of customLoss.py:90 (``vgg_const``)."""
+    if noise is None:
+        noise = torch.randn_like(inputs)
+    l1 = l1_loss(output, target)
+    perturbed = torch.clamp(inputs + noise * 0.01, -10.0, 10.0)
+    with torch.no_grad():
+        perturbed_output = model_fn(perturbed)
+    pert = F.mse_loss(output, perturbed_output)
+    vgg = torch.as_tensor(vgg_const, dtype=l1.dtype)
+    total = alpha * l1 + (1 - alpha) * vgg + beta * pert
+    return total, {"l1_loss": l1, "vgg_loss": vgg, "perturbation_loss": pert}
 
 
 def perturb_inputs(x, count=3, std_factor=0.01, noises: Optional[Sequence] = None):

@@ -140,3 +140,23 @@ def test_vgg_perceptual_term_matches_reference():
     o, t = cases()["a"]
     full = oracle.custom_loss(o, t, 0.9, vgg_const=oracle.vgg_perceptual_loss(o, t, feats)).item()
     assert abs(full - float(gold["custom_loss_a"])) <= 1e-6
+
+
+def test_enhanced_custom_loss_of_customloss_py_matches_reference():
+    """oracle.enhanced_mse_loss vs the unmodified reference customLoss.EnhancedCustomLoss (customLoss.py:195-238;
+    tests/golden/make_golden_enhanced.py): total, components and the gradient w.r.t. the output, with the reference's own
+    randn_like draw replayed."""
+    import torch.nn.functional as F
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "enhanced_vectors.npz"))
+    torch.set_num_threads(1)
+    inputs, target, w, noise = (torch.from_numpy(gold[k]) for k in ("inputs", "target", "w", "noise"))
+    model = lambda x: torch.sigmoid(F.conv2d(x, w, padding=1))             # noqa: E731
+    output = model(inputs).detach()
+    assert torch.equal(output, torch.from_numpy(gold["output"]))
+    output.requires_grad_(True)
+    total, comp = oracle.enhanced_mse_loss(model, output, target, inputs, alpha=0.9, beta=0.05, noise=noise)
+    total.backward()
+    assert abs(total.item() - float(gold["total"])) <= 1e-7
+    assert abs(comp["l1_loss"].item() - float(gold["l1"])) <= 1e-7 and float(comp["vgg_loss"]) == float(gold["vgg"])
+    assert abs(comp["perturbation_loss"].item() - float(gold["pert"])) <= 1e-9
+    assert torch.allclose(output.grad, torch.from_numpy(gold["grad"]), rtol=1e-6, atol=1e-10)
